@@ -1,0 +1,261 @@
+/*
+ * b200_decode.h — C ABI of libb200decode.so
+ *
+ * The drop-in boundary of the B200-native decode hot path.
+ * Every entry point takes raw DEVICE pointers, int64 shapes/strides counted in
+ * ELEMENTS (not bytes), plain scalars and the CUDA stream to launch on.  No
+ * torch types cross this boundary.  Every function returns B200_OK (0) or a
+ * negative b200_status; nothing here aborts the process, allocates device
+ * memory behind the caller's back, synchronises the host with the device or
+ * reads device metadata on the host, so every call is CUDA-graph capturable
+ * (the reference contract: src/engine/model_runner.cpp:141-210).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative
+ * to the ScaleLLM tree @ffee4ffd).  INTEGRATION.md shows the reference-side
+ * binding (C++ shim with the reference's own signatures, and the ctypes stub).
+ */
+#ifndef B200_DECODE_H_
+#define B200_DECODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200_API
+#else
+#define B200_API __attribute__((visibility("default")))
+#endif
+
+/* Opaque cudaStream_t (CUstream).  0 / NULL = legacy default stream. */
+typedef void* b200_stream_t;
+
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_INVALID_ARG = -1,  /* bad shape / alignment / null pointer          */
+  B200_ERR_UNSUPPORTED = -2,  /* valid in the reference, not implemented here  */
+  B200_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed             */
+  B200_ERR_WORKSPACE = -4     /* caller's workspace too small                  */
+} b200_status;
+
+/* Element types of activations / caches. */
+typedef enum b200_dtype {
+  B200_BF16 = 0,
+  B200_FP16 = 1,
+  B200_FP32 = 2 /* elementwise + norm kernels only */
+} b200_dtype;
+
+/* Library ABI version (bumped on any signature change). */
+B200_API int b200_abi_version(void);
+
+/* Human readable description of the last error on the calling thread. */
+B200_API const char* b200_last_error(void);
+
+/* Number of kernels this library launched on the calling thread since the
+ * last reset (bench.py's "gpu_launches" claim is read from here). */
+B200_API int64_t b200_launch_count(void);
+B200_API void b200_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------ *
+ * A4  RMSNorm                       src/kernels/layernorm_kernels.h:6-19
+ *     out = T(x * rsqrt(mean(x^2) + eps)) * w          (layernorm_kernels.cu:15-41)
+ *     residual form: r = r + x (stored), then the same on r   (:125-155)
+ *     in/out/residual: [rows, n] contiguous; weight: [n].
+ * ------------------------------------------------------------------------ */
+B200_API int b200_rms_norm(void* out, const void* in, const void* weight,
+                           int64_t rows, int64_t n, float eps, int dtype,
+                           b200_stream_t stream);
+
+B200_API int b200_rms_norm_residual(void* out, void* residual, const void* in,
+                                    const void* weight, int64_t rows, int64_t n,
+                                    float eps, int dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A3  Rotary embedding, in place    src/kernels/pos_embedding_kernels.h:7-13
+ *     q: [n_tokens, n_heads, head_dim]   (token stride q_stride, heads dense)
+ *     k: [n_tokens, n_kv_heads, head_dim](token stride k_stride, heads dense)
+ *     positions: [n_tokens] int32
+ *     cos_sin:  [max_pos, rotary_dim] = [cos(rotary_dim/2) | sin(rotary_dim/2)]
+ *     every multiply / add rounded to the element type (pos_embedding_kernels.cu:24-29)
+ * ------------------------------------------------------------------------ */
+B200_API int b200_rope_inplace(void* q, void* k, const int32_t* positions,
+                               const void* cos_sin, int64_t n_tokens,
+                               int64_t n_heads, int64_t n_kv_heads,
+                               int64_t head_dim, int64_t rotary_dim,
+                               int64_t q_stride, int64_t k_stride,
+                               int interleaved, int dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A2  KV-cache slot write           src/kernels/kv_cache_kernels.h:6-11
+ *     cache[slot_ids[t], h, :] = {k,v}[t, h, :]        (bit exact)
+ *     k,v: [n_tokens, n_kv_heads, head_dim], token strides k_stride/v_stride
+ *     caches: [n_slots, n_kv_heads, head_dim] contiguous
+ * ------------------------------------------------------------------------ */
+B200_API int b200_kv_write(const int32_t* slot_ids, const void* k, const void* v,
+                           void* k_cache, void* v_cache, int64_t n_tokens,
+                           int64_t n_kv_heads, int64_t head_dim,
+                           int64_t k_stride, int64_t v_stride, int dtype,
+                           b200_stream_t stream);
+
+/* Fusion of A3 + A2 (ScaleAttnHandler::apply_pos_emb + append_kv_cache,
+ * src/layers/attention/scale_attn_handler.cpp:31-42,71-84): rotates q and k in
+ * place AND scatters rotated k plus v into the cache in one pass.  Results are
+ * bit-identical to b200_rope_inplace followed by b200_kv_write. */
+B200_API int b200_rope_kv_write(void* q, void* k, const void* v,
+                                const int32_t* positions, const void* cos_sin,
+                                const int32_t* slot_ids, void* k_cache,
+                                void* v_cache, int64_t n_tokens, int64_t n_heads,
+                                int64_t n_kv_heads, int64_t head_dim,
+                                int64_t rotary_dim, int64_t q_stride,
+                                int64_t k_stride, int64_t v_stride,
+                                int interleaved, int dtype, b200_stream_t stream);
+
+/* Gather (test/debug helper; KVCache::get_kv_cache, src/memory/kv_cache.cpp:60-98):
+ * {k,v}_out[t] = cache[slot_ids[t]]. */
+B200_API int b200_kv_gather(const int32_t* slot_ids, const void* k_cache,
+                            const void* v_cache, void* k_out, void* v_out,
+                            int64_t n_tokens, int64_t n_kv_heads,
+                            int64_t head_dim, int dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A5  Activations                   src/kernels/activation_kernels.h:6-14
+ *     silu:      out[r, i] = T(x / (1 + exp(-x)))            in: [rows, n], row stride in_stride
+ *     silu_mul:  out[r, i] = T(silu(in[r, i])) * in[r, n+i]   in: [rows, 2n] contiguous
+ *     (two roundings, activation_kernels.cu:44-50,84-95)
+ * ------------------------------------------------------------------------ */
+B200_API int b200_silu(void* out, const void* in, int64_t rows, int64_t n,
+                       int64_t in_stride, int dtype, b200_stream_t stream);
+
+B200_API int b200_silu_mul(void* out, const void* in, int64_t rows, int64_t n,
+                           int dtype, b200_stream_t stream);
+
+/* silu(gate) * up with gate and up given as separate strided views — the exact
+ * op pair Llama's MLP issues (src/models/meta/llama.h:61-64): kernel::silu then
+ * a torch multiply.  gate/up: [rows, n] with row strides; out contiguous. */
+B200_API int b200_silu_mul_strided(void* out, const void* gate, const void* up,
+                                   int64_t rows, int64_t n, int64_t gate_stride,
+                                   int64_t up_stride, int dtype,
+                                   b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A1  Paged-KV variable-length attention (decode-shaped)
+ *                                   src/kernels/attention/attn_api.h:12-27
+ *     O = softmax(mask(softcap(Q K^T * sm_scale) + alibi)) V per sequence,
+ *     causal with diagonal kv_len - q_len, slot lookup
+ *     block_table[block_cu_lens[b] + (idx >> log2(bs))] + (idx & (bs-1))
+ *     (block_table holds FIRST-SLOT ids: block_id * block_size;
+ *      src/kernels/attention/kernel/sm80_kernel_mha.cuh:148-152, src/engine/batch.cpp:206-209)
+ *
+ *     out, q:  [n_tokens, n_heads, head_dim], strides (q_stride_t, q_stride_h, 1)
+ *     caches:  [n_slots, n_kv_heads, head_dim], strides (kv_stride_s, kv_stride_h, 1)
+ *     q_cu_lens, kv_cu_lens, block_cu_lens: [batch+1] int32;  block_table int32
+ *     alibi_slopes: [n_heads] float32 or NULL
+ *     sliding_window < 0 disables the local mask; logits_soft_cap == 0 disables it.
+ *     workspace: device scratch for split-KV partials, at least
+ *     b200_paged_attn_workspace_bytes(...) bytes, 16-byte aligned (may be NULL
+ *     when that function returns 0).
+ *     Every query token of a sequence is processed as its own work item, which is
+ *     the right shape for decode / speculative decode (max_q_len <= ~8); large
+ *     q_len (prefill) is correct but not the tuned path.
+ * ------------------------------------------------------------------------ */
+B200_API int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len,
+                                                 int64_t max_kv_len,
+                                                 int64_t n_heads,
+                                                 int64_t n_kv_heads,
+                                                 int64_t head_dim);
+
+B200_API int b200_paged_attn_decode(
+    void* out, const void* q, const void* k_cache, const void* v_cache,
+    const int32_t* q_cu_lens, const int32_t* kv_cu_lens,
+    const int32_t* block_table, const int32_t* block_cu_lens,
+    const float* alibi_slopes, int64_t batch, int64_t n_heads,
+    int64_t n_kv_heads, int64_t head_dim, int64_t n_slots, int64_t q_stride_t,
+    int64_t q_stride_h, int64_t o_stride_t, int64_t o_stride_h,
+    int64_t kv_stride_s, int64_t kv_stride_h, int block_size, int max_q_len,
+    int max_kv_len, float sm_scale, float logits_soft_cap, int sliding_window,
+    void* workspace, int64_t workspace_bytes, int dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A6/A7  int4 weight x bf16 activation matmul (W4A16)
+ *     replaces marlin::awq_repack / gptq_repack + marlin::gptq_gemm
+ *     (src/kernels/quantization/marlin.h:17-37) behind the qlinear plugins
+ *     (src/layers/quantization/qlinear_awq_marlin_impl.cpp:99-125,332-365).
+ *
+ *     C[M,N] = A[M,K] * W,   W[k,n] = bf16_mul( bf16(q[k,n]) - bf16(z[k/g,n]), s[k/g,n] )
+ *     (exact subtract, one bf16 rounding in the multiply: marlin/numeric_conversion.h:144-167,221-240),
+ *     fp32 accumulate, fp32 cross-CTA reduction, one final rounding to bf16.
+ *
+ *     Checkpoint formats accepted by the prepack calls (device pointers):
+ *       AWQ : qweight [K, N/8] int32, nibbles along N in order [0,2,4,6,1,3,5,7];
+ *             qzeros [K/g, N/8] int32 same packing; scales [K/g, N] bf16
+ *             (tests/kernels/quant_utils.py:177-197)
+ *       GPTQ: qweight [K/8, N] int32, nibbles along K in natural order
+ *             (quant_utils.py:101-115); symmetric zero point 8 when qzeros == NULL
+ *             (qlinear_gptq_marlin_impl.cpp:18-20), else qzeros [K/g, N/8] int32
+ *             natural order with the GPTQ-v1 "+1" convention applied iff
+ *             zeros_plus_one != 0 (src/layers/quantization/qlinear_impl.cpp:44,86);
+ *             g_idx (act-order) is not supported: B200_ERR_UNSUPPORTED.
+ *     group_size g in {32, 64, 128, -1(=K)};  K % 128 == 0, N % 128 == 0.
+ *
+ *     The prepacked buffer is an opaque tile-blob layout private to this
+ *     library (DESIGN.md "W4 tile blob"); size from b200_w4a16_packed_bytes.
+ * ------------------------------------------------------------------------ */
+B200_API int64_t b200_w4a16_packed_bytes(int64_t K, int64_t N, int group_size);
+
+B200_API int b200_w4a16_prepack_awq(void* packed, const int32_t* qweight,
+                                    const int32_t* qzeros, const void* scales,
+                                    int64_t K, int64_t N, int group_size,
+                                    b200_stream_t stream);
+
+B200_API int b200_w4a16_prepack_gptq(void* packed, const int32_t* qweight,
+                                     const int32_t* qzeros, const void* scales,
+                                     int64_t K, int64_t N, int group_size,
+                                     int zeros_plus_one, b200_stream_t stream);
+
+/* Inverse of the prepack (debug / parity): W_out[K,N] bf16 = dequantised weights. */
+B200_API int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K,
+                                int64_t N, int group_size, b200_stream_t stream);
+
+/* Workspace for split-K partials + tile counters.  The counter region (first
+ * B200_W4A16_COUNTER_BYTES bytes) must be zero on first use; the GEMM leaves it
+ * zeroed on return (same contract as Marlin's lock workspace, marlin.h:24). */
+#define B200_W4A16_COUNTER_BYTES 16384
+B200_API int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+/* A: [M, K] bf16 row stride lda;  C: [M, N] bf16 row stride ldc; bias: [N] bf16 or NULL. */
+B200_API int b200_w4a16_gemm(void* C, const void* A, const void* packed,
+                             const void* bias, int64_t M, int64_t N, int64_t K,
+                             int64_t lda, int64_t ldc, int group_size,
+                             void* workspace, int64_t workspace_bytes,
+                             b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * A9  Tensor-parallel all-reduce over NVLink peer memory
+ *     replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
+ *     for the <= 1 MiB row-parallel reductions of the decode step.
+ *
+ *     One communicator per GPU (one process per GPU here; one thread per GPU in
+ *     the reference).  Setup: every rank calls b200_ar_create (allocates its
+ *     symmetric buffer + flags and returns an IPC handle blob), exchanges the
+ *     blobs out of band (torch.distributed all_gather in this repo), then calls
+ *     b200_ar_open_peers with all ranks' blobs in rank order.
+ * ------------------------------------------------------------------------ */
+typedef struct b200_ar_comm b200_ar_comm;
+#define B200_AR_HANDLE_BYTES 128
+
+B200_API int b200_ar_create(b200_ar_comm** comm, int rank, int world_size,
+                            int64_t max_bytes, void* handle_out /*[B200_AR_HANDLE_BYTES]*/);
+B200_API int b200_ar_open_peers(b200_ar_comm* comm,
+                                const void* all_handles /*[world][B200_AR_HANDLE_BYTES]*/);
+/* In-place sum of data[count] (bf16/fp16/fp32) over all ranks, on `stream`. */
+B200_API int b200_ar_allreduce(b200_ar_comm* comm, void* data, int64_t count,
+                               int dtype, b200_stream_t stream);
+B200_API int b200_ar_destroy(b200_ar_comm* comm);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* B200_DECODE_H_ */

@@ -1,0 +1,242 @@
+// allreduce.cu — one-shot tensor-parallel all-reduce over NVLink peer memory.
+//
+// Replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
+// for the latency-bound <= 1 MiB row-parallel reductions of the decode step
+// (2 per layer: after o_proj and down_proj).
+//
+// One process per GPU.  Each rank owns ONE cudaMalloc'ed symmetric region
+//   [ data buffer, parity 0 | data buffer, parity 1 | flags[world][AR_MAX_BLOCKS] | epoch | done ]
+// exported through CUDA IPC and mapped by every peer (NVSwitch gives every pair
+// full NVLink bandwidth).  A call with epoch e:
+//   1. every block copies its slice of the input into the local buffer (e & 1),
+//   2. publishes flag value e into every peer's flag array (st.release.sys),
+//   3. waits until all peers' flags for the same block index reach e,
+//   4. sums the slice over ranks in rank order 0..w-1 in fp32 (identical order on
+//      every rank => bit-identical results on all ranks) and writes it in place.
+// Double buffering by epoch parity plus the flag barrier of the next call makes
+// reuse safe: nobody can overwrite buffer (e & 1) before every peer finished
+// reading it in call e (they must have entered call e+1 first).  The epoch lives
+// in device memory and is advanced by the kernel, so a captured CUDA graph can
+// be replayed (no host-side state baked into kernel arguments).
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b200 {
+constexpr int AR_MAX_WORLD = 8;
+constexpr int AR_MAX_BLOCKS = 64;
+constexpr int AR_THREADS = 512;
+}  // namespace b200
+
+struct b200_ar_comm {
+  int rank = 0, world = 1;
+  int device = 0;
+  int64_t max_bytes = 0;
+  uint8_t* local = nullptr;                 // base of the local symmetric region
+  uint8_t* peer[b200::AR_MAX_WORLD] = {};   // mapped bases, peer[rank] == local
+  bool opened = false;
+};
+
+namespace b200 {
+
+struct ArDevPtrs {
+  uint8_t* base[AR_MAX_WORLD];
+};
+
+__host__ __device__ inline int64_t ar_flags_off(int64_t max_bytes) { return 2 * max_bytes; }
+__host__ __device__ inline int64_t ar_epoch_off(int64_t max_bytes) {
+  return 2 * max_bytes + (int64_t)AR_MAX_WORLD * AR_MAX_BLOCKS * 4;
+}
+__host__ __device__ inline int64_t ar_region_bytes(int64_t max_bytes) {
+  return ar_epoch_off(max_bytes) + 256;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void accum16(float (&acc)[16 / sizeof(T)], uint4 v) {
+  const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(16 / sizeof(T)); ++i) acc[i] += Num<T>::to_f(e[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs ptrs, T* data,
+                                                                      int64_t nvec, int rank,
+                                                                      int world,
+                                                                      int64_t max_bytes) {
+  constexpr int VEC = 16 / sizeof(T);
+  uint8_t* local = ptrs.base[rank];
+  uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
+  uint32_t* done_ptr = epoch_ptr + 1;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
+  const int64_t buf_off = (e & 1) ? max_bytes : 0;
+
+  // slice of this block (in 16-byte vectors)
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = (int64_t)blockIdx.x * per;
+  const int64_t v1 = v0 + per < nvec ? v0 + per : nvec;
+
+  // 1. stage my slice
+  uint4* mine = reinterpret_cast<uint4*>(local + buf_off);
+  const uint4* src = reinterpret_cast<const uint4*>(data);
+  for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) mine[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+
+  // 2. tell every peer this slice of mine is ready; 3. wait for theirs
+  if (threadIdx.x < world) {
+    const int r = threadIdx.x;
+    uint32_t* their_flags = reinterpret_cast<uint32_t*>(ptrs.base[r] + ar_flags_off(max_bytes));
+    st_release_sys(&their_flags[rank * AR_MAX_BLOCKS + blockIdx.x], e);
+    const uint32_t* my_flags =
+        reinterpret_cast<const uint32_t*>(local + ar_flags_off(max_bytes));
+    while ((int32_t)(ld_acquire_sys(&my_flags[r * AR_MAX_BLOCKS + blockIdx.x]) - e) < 0) {
+    }
+  }
+  __syncthreads();
+
+  // 4. reduce in rank order, write back in place
+  for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
+      accum16<T>(acc, ld_volatile_v4(pb + i));
+    }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) oe[k] = Num<T>::from_f(acc[k]);
+    reinterpret_cast<uint4*>(data)[i] = o;
+  }
+
+  // advance the epoch once every block is done with it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t d = atomicAdd(done_ptr, 1u);
+    if (d == gridDim.x - 1) {
+      *done_ptr = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = e;
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_ar_create(b200_ar_comm** comm, int rank, int world_size, int64_t max_bytes,
+                   void* handle_out) {
+  B200_CHECK_ARG(comm && handle_out, "ar_create: null pointer");
+  B200_CHECK_ARG(world_size >= 1 && world_size <= AR_MAX_WORLD && rank >= 0 && rank < world_size,
+                 "ar_create: rank %d / world %d unsupported (max %d)", rank, world_size,
+                 AR_MAX_WORLD);
+  B200_CHECK_ARG(max_bytes > 0 && max_bytes % 16 == 0, "ar_create: max_bytes must be a multiple of 16");
+  auto* c = new b200_ar_comm();
+  c->rank = rank;
+  c->world = world_size;
+  c->max_bytes = max_bytes;
+  B200_CUDA_OK(cudaGetDevice(&c->device));
+  void* p = nullptr;
+  B200_CUDA_OK(cudaMalloc(&p, (size_t)ar_region_bytes(max_bytes)));
+  B200_CUDA_OK(cudaMemset(p, 0, (size_t)ar_region_bytes(max_bytes)));
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  c->local = static_cast<uint8_t*>(p);
+  c->peer[rank] = c->local;
+  memset(handle_out, 0, B200_AR_HANDLE_BYTES);
+  if (world_size > 1) {
+    cudaIpcMemHandle_t h;
+    B200_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) <= B200_AR_HANDLE_BYTES, "handle blob too small");
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  *comm = c;
+  return B200_OK;
+}
+
+int b200_ar_open_peers(b200_ar_comm* c, const void* all_handles) {
+  B200_CHECK_ARG(c && all_handles, "ar_open_peers: null pointer");
+  if (c->opened) return B200_OK;
+  const uint8_t* hs = static_cast<const uint8_t*>(all_handles);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + (size_t)r * B200_AR_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    B200_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[r] = static_cast<uint8_t*>(p);
+  }
+  c->opened = true;
+  return B200_OK;
+}
+
+int b200_ar_allreduce(b200_ar_comm* c, void* data, int64_t count, int dtype,
+                      b200_stream_t stream) {
+  B200_CHECK_ARG(c && data, "ar_allreduce: null pointer");
+  B200_CHECK_ARG(dtype >= 0 && dtype <= 2, "ar_allreduce: bad dtype");
+  if (count == 0 || c->world == 1) return B200_OK;
+  B200_CHECK_ARG(c->opened, "ar_allreduce: peers not opened");
+  const int es = dtype == B200_FP32 ? 4 : 2;
+  const int64_t bytes = count * es;
+  B200_CHECK_ARG(bytes % 16 == 0 && is_aligned(data, 16),
+                 "ar_allreduce: message must be 16-byte aligned and a multiple of 16 bytes");
+  if (bytes > c->max_bytes)
+    return set_error(B200_ERR_WORKSPACE, "ar_allreduce: %lld B exceeds the %lld B symmetric buffer",
+                     (long long)bytes, (long long)c->max_bytes);
+  const int64_t nvec = bytes / 16;
+  int blocks = (int)((nvec + 2 * AR_THREADS - 1) / (2 * AR_THREADS));
+  if (blocks < 1) blocks = 1;
+  if (blocks > AR_MAX_BLOCKS) blocks = AR_MAX_BLOCKS;
+  ArDevPtrs ptrs{};
+  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case B200_BF16:
+      allreduce_oneshot_kernel<__nv_bfloat16><<<blocks, AR_THREADS, 0, st>>>(
+          ptrs, static_cast<__nv_bfloat16*>(data), nvec, c->rank, c->world, c->max_bytes);
+      break;
+    case B200_FP16:
+      allreduce_oneshot_kernel<__half><<<blocks, AR_THREADS, 0, st>>>(
+          ptrs, static_cast<__half*>(data), nvec, c->rank, c->world, c->max_bytes);
+      break;
+    default:
+      allreduce_oneshot_kernel<float><<<blocks, AR_THREADS, 0, st>>>(
+          ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes);
+      break;
+  }
+  B200_LAUNCH_OK("allreduce_oneshot");
+  return B200_OK;
+}
+
+int b200_ar_destroy(b200_ar_comm* c) {
+  if (!c) return B200_OK;
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,597 @@
+// elementwise.cu — RMSNorm, RoPE, KV-slot write/gather, SiLU(*mul) for sm_100a.
+//
+// All of these are HBM/latency-bound byte movers.  Design
+// rules applied: 128-bit coalesced global accesses, the row held in registers so
+// the input is read exactly once, fp32 math with the reference's per-op rounding
+// reproduced exactly, and launch shapes that depend only on host scalars (CUDA
+// graph capturable).
+//
+// Reference semantics restated (never copied):
+//   RMSNorm         src/kernels/layernorm_kernels.cu:15-41,125-155
+//   RoPE            src/kernels/pos_embedding_kernels.cu:10-82
+//   KV write        src/kernels/kv_cache_kernels.cu:9-41
+//   SiLU / SiLU*mul src/kernels/activation_kernels.cu:44-50,53-95
+
+#include "common.cuh"
+
+namespace b200 {
+
+// ===========================================================================
+// RMSNorm
+// ===========================================================================
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  constexpr int NW = THREADS / 32;
+  float t = (lane < NW) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+
+// Vector path: n % VEC == 0, one CTA per row, each thread owns up to MAXV
+// 16-byte vectors of the row in registers (row read once).
+template <typename T, int THREADS, int MAXV, bool RESIDUAL>
+__global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ out,
+                                                               T* __restrict__ residual,
+                                                               const T* __restrict__ in,
+                                                               const T* __restrict__ weight,
+                                                               float eps, int n) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = n / VEC;
+  const T* in_row = in + row * n;
+  T* res_row = RESIDUAL ? residual + row * n : nullptr;
+  T* out_row = out + row * n;
+
+  float x[MAXV][VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = threadIdx.x + j * THREADS;
+    if (v < nvec) {
+      uint4 raw = ld_nc_v4(in_row + v * VEC);
+      const T* e = reinterpret_cast<const T*>(&raw);
+      if constexpr (RESIDUAL) {
+        uint4 rraw = ld_v4(res_row + v * VEC);
+        const T* r = reinterpret_cast<const T*>(&rraw);
+        uint4 sraw;
+        T* s = reinterpret_cast<T*>(&sraw);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          // x = float(r) + float(in): variance uses the UNROUNDED fp32 sum, the
+          // second pass re-reads the rounded residual (layernorm_kernels.cu:137-153)
+          const float f = Num<T>::to_f(r[i]) + Num<T>::to_f(e[i]);
+          ss += f * f;
+          s[i] = Num<T>::from_f(f);
+          x[j][i] = Num<T>::to_f(s[i]);
+        }
+        st_v4(res_row + v * VEC, sraw);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          x[j][i] = Num<T>::to_f(e[i]);
+          ss += x[j][i] * x[j][i];
+        }
+      }
+    }
+  }
+  const float total = block_sum<THREADS>(ss, red);
+  const float rstd = rsqrtf(total / n + eps);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = threadIdx.x + j * THREADS;
+    if (v < nvec) {
+      uint4 wraw = ld_v4(weight + v * VEC);
+      const T* w = reinterpret_cast<const T*>(&wraw);
+      uint4 oraw;
+      T* o = reinterpret_cast<T*>(&oraw);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        // (T)(x * rstd) * w  — two roundings (layernorm_kernels.cu:39)
+        const float y = rnd<T>(x[j][i] * rstd);
+        o[i] = Num<T>::from_f(y * Num<T>::to_f(w[i]));
+      }
+      st_v4(out_row + v * VEC, oraw);
+    }
+  }
+}
+
+// Scalar fallback: any n (the reference's own test uses n = 1038).
+template <typename T, bool RESIDUAL>
+__global__ void __launch_bounds__(1024) rms_norm_scalar_kernel(T* __restrict__ out,
+                                                               T* __restrict__ residual,
+                                                               const T* __restrict__ in,
+                                                               const T* __restrict__ weight,
+                                                               float eps, int64_t n) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  float ss = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float f = Num<T>::to_f(in[row * n + i]);
+    if constexpr (RESIDUAL) {
+      f = Num<T>::to_f(residual[row * n + i]) + f;
+      residual[row * n + i] = Num<T>::from_f(f);
+    }
+    ss += f * f;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float t = (threadIdx.x & 31) < ((blockDim.x + 31) >> 5) ? red[threadIdx.x & 31] : 0.f;
+  t = warp_sum(t);
+  const float rstd = rsqrtf(t / n + eps);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float f = RESIDUAL ? Num<T>::to_f(residual[row * n + i]) : Num<T>::to_f(in[row * n + i]);
+    const float y = rnd<T>(f * rstd);
+    out[row * n + i] = Num<T>::from_f(y * Num<T>::to_f(weight[i]));
+  }
+}
+
+template <typename T, bool RESIDUAL>
+static int launch_rms_norm(void* out, void* residual, const void* in, const void* weight,
+                           int64_t rows, int64_t n, float eps, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = (n % VEC == 0) && is_aligned(out, 16) && is_aligned(in, 16) &&
+                      is_aligned(weight, 16) && (!RESIDUAL || is_aligned(residual, 16));
+  const int64_t nvec = n / VEC;
+  T* o = static_cast<T*>(out);
+  T* r = static_cast<T*>(residual);
+  const T* i = static_cast<const T*>(in);
+  const T* w = static_cast<const T*>(weight);
+  dim3 grid(static_cast<unsigned>(rows));
+  if (vec_ok && nvec <= 128) {
+    rms_norm_vec_kernel<T, 128, 1, RESIDUAL><<<grid, 128, 0, st>>>(o, r, i, w, eps, (int)n);
+  } else if (vec_ok && nvec <= 256) {
+    rms_norm_vec_kernel<T, 256, 1, RESIDUAL><<<grid, 256, 0, st>>>(o, r, i, w, eps, (int)n);
+  } else if (vec_ok && nvec <= 512) {
+    rms_norm_vec_kernel<T, 512, 1, RESIDUAL><<<grid, 512, 0, st>>>(o, r, i, w, eps, (int)n);
+  } else if (vec_ok && nvec <= 1024) {
+    rms_norm_vec_kernel<T, 512, 2, RESIDUAL><<<grid, 512, 0, st>>>(o, r, i, w, eps, (int)n);
+  } else if (vec_ok && nvec <= 4096) {
+    rms_norm_vec_kernel<T, 1024, 4, RESIDUAL><<<grid, 1024, 0, st>>>(o, r, i, w, eps, (int)n);
+  } else {
+    const int threads = (int)((n < 1024 ? ((n + 31) / 32) * 32 : 1024));
+    rms_norm_scalar_kernel<T, RESIDUAL><<<grid, threads, 0, st>>>(o, r, i, w, eps, n);
+  }
+  B200_LAUNCH_OK("rms_norm");
+  return B200_OK;
+}
+
+// ===========================================================================
+// RoPE (+ optional fused KV-slot write)
+// ===========================================================================
+// One CTA per token.  A work item is one 16-byte vector of the x half paired
+// with the matching vector of the y half (non-interleaved), or one vector of
+// interleaved (x,y) pairs.  Every multiply and add is rounded to T.
+template <typename T>
+__device__ __forceinline__ void rope_pair(float x, float y, float c, float s, T& ox, T& oy) {
+  // x' = x*c - y*s ; y' = x*s + y*c   with per-op rounding to T
+  const float xc = rnd<T>(x * c), ys = rnd<T>(y * s);
+  const float xs = rnd<T>(x * s), yc = rnd<T>(y * c);
+  ox = Num<T>::from_f(xc - ys);
+  oy = Num<T>::from_f(xs + yc);
+}
+
+template <typename T, bool FUSE_KV>
+__global__ void __launch_bounds__(256) rope_vec_kernel(
+    T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v,
+    const int32_t* __restrict__ positions, const T* __restrict__ cos_sin,
+    const int32_t* __restrict__ slot_ids, T* __restrict__ k_cache, T* __restrict__ v_cache,
+    int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
+    int64_t k_stride, int64_t v_stride, bool interleaved) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t tok = blockIdx.x;
+  const int half = rotary_dim / 2;
+  const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
+  const T* cosp = cs;
+  const T* sinp = cs + half;
+  const int64_t slot = FUSE_KV ? static_cast<int64_t>(slot_ids[tok]) : 0;
+  T* kc_row = FUSE_KV ? k_cache + slot * n_kv_heads * head_dim : nullptr;
+  T* vc_row = FUSE_KV ? v_cache + slot * n_kv_heads * head_dim : nullptr;
+
+  // items per head: non-interleaved -> half/VEC vector pairs; interleaved -> rotary_dim/VEC vectors
+  const int items_per_head = interleaved ? rotary_dim / VEC : half / VEC;
+  const int total_heads = n_heads + n_kv_heads;
+  for (int it = threadIdx.x; it < total_heads * items_per_head; it += blockDim.x) {
+    const int h = it / items_per_head;
+    const int j = it % items_per_head;
+    const bool is_k = h >= n_heads;
+    T* base = is_k ? k + tok * k_stride + static_cast<int64_t>(h - n_heads) * head_dim
+                   : q + tok * q_stride + static_cast<int64_t>(h) * head_dim;
+    T* cdst = (FUSE_KV && is_k) ? kc_row + static_cast<int64_t>(h - n_heads) * head_dim : nullptr;
+    if (!interleaved) {
+      uint4 xr = ld_v4(base + j * VEC), yr = ld_v4(base + half + j * VEC);
+      uint4 cr = ld_v4(cosp + j * VEC), sr = ld_v4(sinp + j * VEC);
+      const T* x = reinterpret_cast<const T*>(&xr);
+      const T* y = reinterpret_cast<const T*>(&yr);
+      const T* c = reinterpret_cast<const T*>(&cr);
+      const T* s = reinterpret_cast<const T*>(&sr);
+      uint4 oxr, oyr;
+      T* ox = reinterpret_cast<T*>(&oxr);
+      T* oy = reinterpret_cast<T*>(&oyr);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        rope_pair<T>(Num<T>::to_f(x[i]), Num<T>::to_f(y[i]), Num<T>::to_f(c[i]),
+                     Num<T>::to_f(s[i]), ox[i], oy[i]);
+      st_v4(base + j * VEC, oxr);
+      st_v4(base + half + j * VEC, oyr);
+      if (cdst) {
+        st_v4(cdst + j * VEC, oxr);
+        st_v4(cdst + half + j * VEC, oyr);
+      }
+    } else {
+      uint4 pr = ld_v4(base + j * VEC);
+      const T* p = reinterpret_cast<const T*>(&pr);
+      uint4 outr;
+      T* o = reinterpret_cast<T*>(&outr);
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        const int r = j * (VEC / 2) + i;
+        rope_pair<T>(Num<T>::to_f(p[2 * i]), Num<T>::to_f(p[2 * i + 1]), Num<T>::to_f(cosp[r]),
+                     Num<T>::to_f(sinp[r]), o[2 * i], o[2 * i + 1]);
+      }
+      st_v4(base + j * VEC, outr);
+      if (cdst) st_v4(cdst + j * VEC, outr);
+    }
+  }
+  if constexpr (FUSE_KV) {
+    // un-rotated tail of K (rotary_dim < head_dim) and the whole of V
+    const int tail_vecs = (head_dim - rotary_dim) / VEC;
+    for (int it = threadIdx.x; it < n_kv_heads * tail_vecs; it += blockDim.x) {
+      const int h = it / tail_vecs, j = it % tail_vecs;
+      const int64_t off = static_cast<int64_t>(h) * head_dim + rotary_dim + j * VEC;
+      st_v4(kc_row + off, ld_v4(k + tok * k_stride + off));
+    }
+    const int v_vecs = n_kv_heads * head_dim / VEC;
+    for (int it = threadIdx.x; it < v_vecs; it += blockDim.x)
+      st_v4(vc_row + static_cast<int64_t>(it) * VEC, ld_nc_v4(v + tok * v_stride + it * VEC));
+  }
+}
+
+// Scalar fallback (any rotary_dim / alignment), optional fused KV write.
+template <typename T, bool FUSE_KV>
+__global__ void __launch_bounds__(256) rope_scalar_kernel(
+    T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v,
+    const int32_t* __restrict__ positions, const T* __restrict__ cos_sin,
+    const int32_t* __restrict__ slot_ids, T* __restrict__ k_cache, T* __restrict__ v_cache,
+    int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
+    int64_t k_stride, int64_t v_stride, bool interleaved) {
+  const int64_t tok = blockIdx.x;
+  const int half = rotary_dim / 2;
+  const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
+  const int total = (n_heads + n_kv_heads) * half;
+  for (int it = threadIdx.x; it < total; it += blockDim.x) {
+    const int h = it / half, r = it % half;
+    const bool is_k = h >= n_heads;
+    T* base = is_k ? k + tok * k_stride + static_cast<int64_t>(h - n_heads) * head_dim
+                   : q + tok * q_stride + static_cast<int64_t>(h) * head_dim;
+    const int xi = interleaved ? 2 * r : r;
+    const int yi = interleaved ? 2 * r + 1 : r + half;
+    T ox, oy;
+    rope_pair<T>(Num<T>::to_f(base[xi]), Num<T>::to_f(base[yi]), Num<T>::to_f(cs[r]),
+                 Num<T>::to_f(cs[half + r]), ox, oy);
+    base[xi] = ox;
+    base[yi] = oy;
+  }
+  if constexpr (FUSE_KV) {
+    __syncthreads();  // rotated K of this token is complete (same CTA wrote it)
+    const int64_t slot = slot_ids[tok];
+    const int nkv = n_kv_heads * head_dim;
+    for (int it = threadIdx.x; it < nkv; it += blockDim.x) {
+      k_cache[slot * nkv + it] = k[tok * k_stride + it];
+      v_cache[slot * nkv + it] = v[tok * v_stride + it];
+    }
+  }
+}
+
+template <typename T, bool FUSE_KV>
+static int launch_rope(void* q, void* k, const void* v, const int32_t* positions,
+                       const void* cos_sin, const int32_t* slot_ids, void* k_cache, void* v_cache,
+                       int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
+                       int64_t rotary_dim, int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                       int interleaved, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (n_tokens == 0) return B200_OK;
+  const int64_t half = rotary_dim / 2;
+  bool vec_ok = is_aligned(q, 16) && is_aligned(k, 16) && is_aligned(cos_sin, 16) &&
+                head_dim % VEC == 0 && q_stride % VEC == 0 && k_stride % VEC == 0 &&
+                rotary_dim % VEC == 0 && (interleaved ? true : half % VEC == 0);
+  if (FUSE_KV)
+    vec_ok = vec_ok && is_aligned(v, 16) && is_aligned(k_cache, 16) && is_aligned(v_cache, 16) &&
+             v_stride % VEC == 0;
+  dim3 grid(static_cast<unsigned>(n_tokens));
+  auto* qq = static_cast<T*>(q);
+  auto* kk = static_cast<T*>(k);
+  auto* vv = static_cast<const T*>(v);
+  auto* cs = static_cast<const T*>(cos_sin);
+  auto* kc = static_cast<T*>(k_cache);
+  auto* vc = static_cast<T*>(v_cache);
+  if (vec_ok) {
+    rope_vec_kernel<T, FUSE_KV><<<grid, 256, 0, st>>>(
+        qq, kk, vv, positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
+        (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0);
+  } else {
+    rope_scalar_kernel<T, FUSE_KV><<<grid, 256, 0, st>>>(
+        qq, kk, vv, positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
+        (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0);
+  }
+  B200_LAUNCH_OK("rope");
+  return B200_OK;
+}
+
+// ===========================================================================
+// KV slot write / gather (pure copies, bit exact)
+// ===========================================================================
+template <int ESZ, bool GATHER>
+__global__ void __launch_bounds__(256) kv_copy_kernel(const int32_t* __restrict__ slot_ids,
+                                                      const uint8_t* __restrict__ k_tok,
+                                                      const uint8_t* __restrict__ v_tok,
+                                                      uint8_t* __restrict__ k_cache,
+                                                      uint8_t* __restrict__ v_cache,
+                                                      int64_t row_bytes, int64_t k_stride_b,
+                                                      int64_t v_stride_b, bool vec) {
+  // GATHER: tok <- cache ; else cache <- tok.  (k_tok/v_tok are written when GATHER)
+  const int64_t tok = blockIdx.x;
+  const int64_t slot = slot_ids[tok];
+  uint8_t* kc = k_cache + slot * row_bytes;
+  uint8_t* vc = v_cache + slot * row_bytes;
+  uint8_t* kt = const_cast<uint8_t*>(k_tok) + tok * k_stride_b;
+  uint8_t* vt = const_cast<uint8_t*>(v_tok) + tok * v_stride_b;
+  if (vec) {
+    for (int64_t o = threadIdx.x * 16; o < row_bytes; o += blockDim.x * 16) {
+      if (GATHER) {
+        st_v4(kt + o, ld_v4(kc + o));
+        st_v4(vt + o, ld_v4(vc + o));
+      } else {
+        st_v4(kc + o, ld_nc_v4(kt + o));
+        st_v4(vc + o, ld_nc_v4(vt + o));
+      }
+    }
+  } else {
+    for (int64_t o = threadIdx.x * ESZ; o < row_bytes; o += blockDim.x * ESZ) {
+#pragma unroll
+      for (int b = 0; b < ESZ; ++b) {
+        if (GATHER) {
+          kt[o + b] = kc[o + b];
+          vt[o + b] = vc[o + b];
+        } else {
+          kc[o + b] = kt[o + b];
+          vc[o + b] = vt[o + b];
+        }
+      }
+    }
+  }
+}
+
+static int esize(int dtype) { return dtype == B200_FP32 ? 4 : 2; }
+
+// ===========================================================================
+// SiLU, SiLU*mul
+// ===========================================================================
+template <typename T>
+__device__ __forceinline__ float silu_t(float x) {
+  // (T)( x / (1 + __expf(-x)) )   (activation_kernels.cu:44-50)
+  return rnd<T>(x / (1.0f + __expf(-x)));
+}
+
+// MODE 0: out = silu(a)      MODE 1: out = silu(a) * b  (second rounding)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T* __restrict__ a,
+                                                   const T* __restrict__ b, int64_t rows,
+                                                   int64_t n, int64_t a_stride, int64_t b_stride,
+                                                   bool vec) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (vec) {
+    const int64_t nv = n / VEC;
+    const int64_t total = rows * nv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / nv, j = idx % nv;
+      uint4 ar = ld_nc_v4(a + r * a_stride + j * VEC);
+      const T* ae = reinterpret_cast<const T*>(&ar);
+      uint4 br;
+      if (MODE == 1) br = ld_nc_v4(b + r * b_stride + j * VEC);
+      const T* be = reinterpret_cast<const T*>(&br);
+      uint4 orr;
+      T* o = reinterpret_cast<T*>(&orr);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float s = silu_t<T>(Num<T>::to_f(ae[i]));
+        if (MODE == 1) s = s * Num<T>::to_f(be[i]);
+        o[i] = Num<T>::from_f(s);
+      }
+      st_v4(out + r * n + j * VEC, orr);
+    }
+  } else {
+    const int64_t total = rows * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / n, j = idx % n;
+      float s = silu_t<T>(Num<T>::to_f(a[r * a_stride + j]));
+      if (MODE == 1) s = s * Num<T>::to_f(b[r * b_stride + j]);
+      out[r * n + j] = Num<T>::from_f(s);
+    }
+  }
+}
+
+template <typename T, int MODE>
+static int launch_silu(void* out, const void* a, const void* b, int64_t rows, int64_t n,
+                       int64_t a_stride, int64_t b_stride, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (rows * n == 0) return B200_OK;
+  bool vec = n % VEC == 0 && a_stride % VEC == 0 && is_aligned(out, 16) && is_aligned(a, 16);
+  if (MODE == 1) vec = vec && b_stride % VEC == 0 && is_aligned(b, 16);
+  const int64_t work = vec ? rows * (n / VEC) : rows * n;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  silu_kernel<T, MODE><<<(unsigned)blocks, 256, 0, st>>>(
+      static_cast<T*>(out), static_cast<const T*>(a), static_cast<const T*>(b), rows, n, a_stride,
+      b_stride, vec);
+  B200_LAUNCH_OK("silu");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace b200;
+
+#define DISPATCH_DTYPE3(dtype, ...)                                    \
+  switch (dtype) {                                                     \
+    case B200_BF16: { using T = __nv_bfloat16; return __VA_ARGS__; }   \
+    case B200_FP16: { using T = __half; return __VA_ARGS__; }          \
+    case B200_FP32: { using T = float; return __VA_ARGS__; }           \
+    default: return set_error(B200_ERR_INVALID_ARG, "bad dtype %d", dtype); \
+  }
+#define DISPATCH_DTYPE2(dtype, ...)                                    \
+  switch (dtype) {                                                     \
+    case B200_BF16: { using T = __nv_bfloat16; return __VA_ARGS__; }   \
+    case B200_FP16: { using T = __half; return __VA_ARGS__; }          \
+    default: return set_error(B200_ERR_UNSUPPORTED, "dtype %d not supported here", dtype); \
+  }
+
+extern "C" {
+
+int b200_rms_norm(void* out, const void* in, const void* weight, int64_t rows, int64_t n,
+                  float eps, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in && weight, "rms_norm: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31), "rms_norm: bad shape [%lld,%lld]",
+                 (long long)rows, (long long)n);
+  if (rows == 0) return B200_OK;
+  DISPATCH_DTYPE3(dtype, (launch_rms_norm<T, false>(out, nullptr, in, weight, rows, n, eps,
+                                                    static_cast<cudaStream_t>(stream))));
+}
+
+int b200_rms_norm_residual(void* out, void* residual, const void* in, const void* weight,
+                           int64_t rows, int64_t n, float eps, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in && weight && residual, "rms_norm_residual: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31), "rms_norm_residual: bad shape");
+  if (rows == 0) return B200_OK;
+  DISPATCH_DTYPE3(dtype, (launch_rms_norm<T, true>(out, residual, in, weight, rows, n, eps,
+                                                   static_cast<cudaStream_t>(stream))));
+}
+
+int b200_rope_inplace(void* q, void* k, const int32_t* positions, const void* cos_sin,
+                      int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
+                      int64_t rotary_dim, int64_t q_stride, int64_t k_stride, int interleaved,
+                      int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(q && k && positions && cos_sin, "rope: null pointer");
+  B200_CHECK_ARG(rotary_dim > 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim,
+                 "rope: rotary_dim %lld invalid for head_dim %lld", (long long)rotary_dim,
+                 (long long)head_dim);
+  B200_CHECK_ARG(q_stride >= n_heads * head_dim && k_stride >= n_kv_heads * head_dim,
+                 "rope: heads must be dense within a token");
+  DISPATCH_DTYPE3(dtype, (launch_rope<T, false>(q, k, nullptr, positions, cos_sin, nullptr, nullptr,
+                                                nullptr, n_tokens, n_heads, n_kv_heads, head_dim,
+                                                rotary_dim, q_stride, k_stride, 0, interleaved,
+                                                static_cast<cudaStream_t>(stream))));
+}
+
+int b200_rope_kv_write(void* q, void* k, const void* v, const int32_t* positions,
+                       const void* cos_sin, const int32_t* slot_ids, void* k_cache, void* v_cache,
+                       int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
+                       int64_t rotary_dim, int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                       int interleaved, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(q && k && v && positions && cos_sin && slot_ids && k_cache && v_cache,
+                 "rope_kv_write: null pointer");
+  B200_CHECK_ARG(rotary_dim > 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim,
+                 "rope_kv_write: bad rotary_dim");
+  B200_CHECK_ARG(q_stride >= n_heads * head_dim && k_stride >= n_kv_heads * head_dim &&
+                     v_stride >= n_kv_heads * head_dim,
+                 "rope_kv_write: heads must be dense within a token");
+  DISPATCH_DTYPE3(dtype, (launch_rope<T, true>(q, k, v, positions, cos_sin, slot_ids, k_cache,
+                                               v_cache, n_tokens, n_heads, n_kv_heads, head_dim,
+                                               rotary_dim, q_stride, k_stride, v_stride,
+                                               interleaved, static_cast<cudaStream_t>(stream))));
+}
+
+static int kv_copy(bool gather, const int32_t* slot_ids, const void* k, const void* v,
+                   void* k_cache, void* v_cache, int64_t n_tokens, int64_t n_kv_heads,
+                   int64_t head_dim, int64_t k_stride, int64_t v_stride, int dtype,
+                   b200_stream_t stream) {
+  B200_CHECK_ARG(slot_ids && k && v && k_cache && v_cache, "kv copy: null pointer");
+  B200_CHECK_ARG(dtype >= 0 && dtype <= 2, "kv copy: bad dtype");
+  B200_CHECK_ARG(k_stride >= n_kv_heads * head_dim && v_stride >= n_kv_heads * head_dim,
+                 "kv copy: heads must be dense within a token");
+  if (n_tokens == 0) return B200_OK;
+  const int es = esize(dtype);
+  const int64_t row_bytes = n_kv_heads * head_dim * es;
+  const bool vec = row_bytes % 16 == 0 && (k_stride * es) % 16 == 0 && (v_stride * es) % 16 == 0 &&
+                   is_aligned(k, 16) && is_aligned(v, 16) && is_aligned(k_cache, 16) &&
+                   is_aligned(v_cache, 16);
+  auto st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)n_tokens);
+  const uint8_t* kb = static_cast<const uint8_t*>(k);
+  const uint8_t* vb = static_cast<const uint8_t*>(v);
+  uint8_t* kc = static_cast<uint8_t*>(k_cache);
+  uint8_t* vc = static_cast<uint8_t*>(v_cache);
+  if (es == 2) {
+    if (gather)
+      kv_copy_kernel<2, true><<<grid, 128, 0, st>>>(slot_ids, kb, vb, kc, vc, row_bytes,
+                                                    k_stride * es, v_stride * es, vec);
+    else
+      kv_copy_kernel<2, false><<<grid, 128, 0, st>>>(slot_ids, kb, vb, kc, vc, row_bytes,
+                                                     k_stride * es, v_stride * es, vec);
+  } else {
+    if (gather)
+      kv_copy_kernel<4, true><<<grid, 128, 0, st>>>(slot_ids, kb, vb, kc, vc, row_bytes,
+                                                    k_stride * es, v_stride * es, vec);
+    else
+      kv_copy_kernel<4, false><<<grid, 128, 0, st>>>(slot_ids, kb, vb, kc, vc, row_bytes,
+                                                     k_stride * es, v_stride * es, vec);
+  }
+  B200_LAUNCH_OK("kv_copy");
+  return B200_OK;
+}
+
+int b200_kv_write(const int32_t* slot_ids, const void* k, const void* v, void* k_cache,
+                  void* v_cache, int64_t n_tokens, int64_t n_kv_heads, int64_t head_dim,
+                  int64_t k_stride, int64_t v_stride, int dtype, b200_stream_t stream) {
+  return kv_copy(false, slot_ids, k, v, k_cache, v_cache, n_tokens, n_kv_heads, head_dim, k_stride,
+                 v_stride, dtype, stream);
+}
+
+int b200_kv_gather(const int32_t* slot_ids, const void* k_cache, const void* v_cache, void* k_out,
+                   void* v_out, int64_t n_tokens, int64_t n_kv_heads, int64_t head_dim, int dtype,
+                   b200_stream_t stream) {
+  return kv_copy(true, slot_ids, k_out, v_out, const_cast<void*>(k_cache),
+                 const_cast<void*>(v_cache), n_tokens, n_kv_heads, head_dim,
+                 n_kv_heads * head_dim, n_kv_heads * head_dim, dtype, stream);
+}
+
+int b200_silu(void* out, const void* in, int64_t rows, int64_t n, int64_t in_stride, int dtype,
+              b200_stream_t stream) {
+  B200_CHECK_ARG(out && in, "silu: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n >= 0 && in_stride >= n, "silu: bad shape");
+  DISPATCH_DTYPE3(dtype, (launch_silu<T, 0>(out, in, nullptr, rows, n, in_stride, 0,
+                                            static_cast<cudaStream_t>(stream))));
+}
+
+int b200_silu_mul(void* out, const void* in, int64_t rows, int64_t n, int dtype,
+                  b200_stream_t stream) {
+  B200_CHECK_ARG(out && in, "silu_mul: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n >= 0, "silu_mul: bad shape");
+  const int es = esize(dtype);
+  const void* up = static_cast<const uint8_t*>(in) + n * es;
+  DISPATCH_DTYPE3(dtype, (launch_silu<T, 1>(out, in, up, rows, n, 2 * n, 2 * n,
+                                            static_cast<cudaStream_t>(stream))));
+}
+
+int b200_silu_mul_strided(void* out, const void* gate, const void* up, int64_t rows, int64_t n,
+                          int64_t gate_stride, int64_t up_stride, int dtype,
+                          b200_stream_t stream) {
+  B200_CHECK_ARG(out && gate && up, "silu_mul_strided: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n >= 0 && gate_stride >= n && up_stride >= n,
+                 "silu_mul_strided: bad shape");
+  DISPATCH_DTYPE3(dtype, (launch_silu<T, 1>(out, gate, up, rows, n, gate_stride, up_stride,
+                                            static_cast<cudaStream_t>(stream))));
+}
+
+}  // extern "C"

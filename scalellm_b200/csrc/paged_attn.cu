@@ -1,0 +1,622 @@
+// paged_attn.cu — paged-KV decode attention for sm_100a.
+//
+// Replaces llm::paged_kv_varlen_mha (src/kernels/attention/attn_api.cpp:14-73)
+// for decode-shaped batches.  HBM-bound (AI = group size FLOP/B), so no tensor
+// cores: KV blocks are staged into shared memory with TMA (one 3-D tensor map
+// over the [n_slots, n_kv_heads, head_dim] cache, box = min(block_size,16) slots
+// of one kv head), each warp owns a private ring of TMA stages + mbarriers so
+// there is no CTA-wide synchronisation in the main loop, dot products and the
+// online softmax (exp2 domain) use warp shuffles, and the KV range is split
+// across CTAs (split-KV) with a second-pass LSE combine.
+//
+// Work item = (split, kv head x head-group, sequence x query token).  Slot
+// lookup is the reference's: block_table[block_cu_lens[b] + (pos >> log2 bs)]
+// + (pos & (bs-1)), where block_table holds first-slot ids
+// (src/kernels/attention/kernel/sm80_kernel_mha.cuh:148-152).
+// Mask semantics follow src/kernels/attention/common/mask.h:51-86:
+//   causal: kv_pos <= q_pos, q_pos = kv_len - q_len + qi
+//   local : q_pos - kv_pos <= sliding_window   (window >= 0)
+//   alibi : score += slope[h] * kv_pos          (after scale / soft-cap)
+//   softcap: score = cap * tanh(score * sm_scale / cap)  (mha_params.h:51-66)
+
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int ATT_WARPS = 4;
+constexpr int ATT_THREADS = ATT_WARPS * 32;
+constexpr int ATT_TILE = 16;         // kv slots per TMA stage
+constexpr int ATT_MAX_TPS = 64;      // tiles per split (bounds the smem block table)
+constexpr int ATT_TBL = ATT_MAX_TPS * ATT_TILE + 8;
+
+struct AttnParams {
+  const void* q;
+  void* out;
+  const int32_t* q_cu_lens;
+  const int32_t* kv_cu_lens;
+  const int32_t* block_table;
+  const int32_t* block_cu_lens;
+  const float* alibi;
+  float* ws_o;    // [batch*max_q_len, n_heads, n_splits, D]
+  float* ws_lse;  // [batch*max_q_len, n_heads, n_splits]
+  int64_t q_stride_t, q_stride_h, o_stride_t, o_stride_h;
+  int n_heads, n_kv_heads, group, n_hg;
+  int block_shift, block_mask, box_rows, boxes_per_tile;
+  int max_q_len, n_splits, tiles_per_split;
+  float scale_log2;   // sm_scale * log2(e)            (soft_cap == 0)
+  float cap_in;       // sm_scale / soft_cap           (soft_cap  > 0)
+  float cap_out_log2; // soft_cap * log2(e)
+  int use_cap;
+  int window;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int STAGES = D >= 256 ? 2 : 3;
+  static constexpr int CPL = D / 64;           // 16-byte chunks per lane per row
+  static constexpr int EPL = CPL * 8;          // elements per lane per row
+  static constexpr int TILE_ELEMS = ATT_TILE * D;
+};
+
+template <typename T, int D>
+constexpr size_t attn_smem_bytes() {
+  return (size_t)ATT_WARPS * AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T)  // K+V stages
+         + ATT_TBL * sizeof(int32_t) + ATT_WARPS * AttnCfg<D>::STAGES * sizeof(uint64_t) + 128;
+}
+
+template <typename T, int D, int R>
+__global__ void __launch_bounds__(ATT_THREADS, (D <= 128 ? 2 : 1))
+paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
+                         const __grid_constant__ CUtensorMap vmap, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int STAGES = Cfg::STAGES, CPL = Cfg::CPL, EPL = Cfg::EPL;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  T* stage_base = reinterpret_cast<T*>(smem_raw);
+  int32_t* tbl = reinterpret_cast<int32_t*>(smem_raw + (size_t)ATT_WARPS * STAGES * 2 *
+                                                           Cfg::TILE_ELEMS * sizeof(T));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl + ATT_TBL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, j = lane & 7;
+  const int split = blockIdx.x;
+  const int kvh = blockIdx.y / p.n_hg, hg = blockIdx.y % p.n_hg;
+  const int b = blockIdx.z / p.max_q_len, qi = blockIdx.z % p.max_q_len;
+
+  const int q_begin = p.q_cu_lens[b];
+  const int q_len = p.q_cu_lens[b + 1] - q_begin;
+  if (qi >= q_len) return;
+  const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+  const int q_pos = kv_len - q_len + qi;
+  const int kv_end = q_pos + 1;
+  const int kv_begin = p.window >= 0 ? max(0, q_pos - p.window) : 0;
+  const int64_t tok = q_begin + qi;
+  const int head0 = kvh * p.group + hg * R;
+  const int rows_valid = min(R, p.group - hg * R);
+
+  // tile range of this split, clipped to the unmasked kv range
+  int t0 = split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
+  t0 = max(t0, kv_begin / ATT_TILE);
+  t1 = min(t1, (kv_end + ATT_TILE - 1) / ATT_TILE);
+
+  const int64_t ws_row = (int64_t)blockIdx.z * p.n_heads;
+  if (t0 >= t1) {  // nothing to attend to in this split
+    if (p.n_splits > 1 && threadIdx.x < rows_valid)
+      p.ws_lse[(ws_row + head0 + threadIdx.x) * p.n_splits + split] = -INFINITY;
+    return;
+  }
+
+  // ---- stage the block-table window for this split --------------------------
+  const int blk_cu = p.block_cu_lens[b];
+  const int blk_first = (t0 * ATT_TILE) >> p.block_shift;
+  const int blk_last = (min(t1 * ATT_TILE, kv_end) - 1) >> p.block_shift;
+  for (int i = threadIdx.x; i <= blk_last - blk_first; i += ATT_THREADS)
+    tbl[i] = p.block_table[blk_cu + blk_first + i];
+  if (threadIdx.x < ATT_WARPS * STAGES) mbar_init(&bars[threadIdx.x], 1);
+  fence_mbar_init();
+  __syncthreads();
+
+  T* my_stage = stage_base + (size_t)warp * STAGES * 2 * Cfg::TILE_ELEMS;
+  uint64_t* my_bars = bars + warp * STAGES;
+  const int n_my = (t1 - t0 - warp + ATT_WARPS - 1) / ATT_WARPS;  // tiles t0+warp, +W, ...
+
+  auto issue = [&](int i) {  // lane 0 only
+    const int tile = t0 + warp + i * ATT_WARPS;
+    const int s = i % STAGES;
+    T* ks = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
+    T* vs = ks + Cfg::TILE_ELEMS;
+    const int pos0 = tile * ATT_TILE;
+    int nbox = 0;
+    for (int bx = 0; bx < p.boxes_per_tile; ++bx)
+      if (pos0 + bx * p.box_rows < kv_end) ++nbox;
+    mbar_arrive_expect_tx(&my_bars[s], (uint32_t)(nbox * 2 * p.box_rows * D * sizeof(T)));
+    for (int bx = 0; bx < nbox; ++bx) {
+      const int pos = pos0 + bx * p.box_rows;
+      const int slot0 = tbl[(pos >> p.block_shift) - blk_first] + (pos & p.block_mask);
+      tma_load_3d(ks + bx * p.box_rows * D, &kmap, &my_bars[s], 0, kvh, slot0);
+      tma_load_3d(vs + bx * p.box_rows * D, &vmap, &my_bars[s], 0, kvh, slot0);
+    }
+  };
+
+  if (lane == 0) {
+    if (warp == 0) {
+      prefetch_tensormap(&kmap);
+      prefetch_tensormap(&vmap);
+    }
+    for (int i = 0; i < STAGES && i < n_my; ++i) issue(i);
+  }
+
+  // ---- query rows of this head group -> registers (fp32) --------------------
+  float qf[R][EPL];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int h = head0 + (r < rows_valid ? r : 0);
+    const T* qrow = static_cast<const T*>(p.q) + tok * p.q_stride_t + (int64_t)h * p.q_stride_h;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      uint4 raw = ld_v4(qrow + (j + 8 * c) * 8);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = Num<T>::unpack(w[e]);
+        qf[r][c * 8 + 2 * e] = f.x;
+        qf[r][c * 8 + 2 * e + 1] = f.y;
+      }
+    }
+  }
+  float slope_log2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    slope_log2[r] = p.alibi ? p.alibi[head0 + (r < rows_valid ? r : 0)] * 1.4426950408889634f : 0.f;
+
+  float m[R], l[R], acc[R][EPL];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[r][e] = 0.f;
+  }
+
+  // ---- main loop: this warp's tiles ----------------------------------------
+  for (int i = 0; i < n_my; ++i) {
+    const int s = i % STAGES;
+    const uint32_t phase = (i / STAGES) & 1;
+    const T* ks = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
+    const T* vs = ks + Cfg::TILE_ELEMS;
+    const int pos0 = (t0 + warp + i * ATT_WARPS) * ATT_TILE;
+    mbar_wait(&my_bars[s], phase);
+
+    // scores: lane group g handles slots g, g+4, g+8, g+12 of the tile
+    float sc[4][R];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const T* krow = ks + (it * 4 + g) * D;
+      float kf[EPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        uint4 raw = ld_v4(krow + (j + 8 * c) * 8);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = Num<T>::unpack(w[e]);
+          kf[c * 8 + 2 * e] = f.x;
+          kf[c * 8 + 2 * e + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) a = fmaf(qf[r][e], kf[e], a);
+        sc[it][r] = a;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+#pragma unroll
+        for (int r = 0; r < R; ++r) sc[it][r] += __shfl_xor_sync(0xffffffffu, sc[it][r], o);
+
+    // online softmax (exp2 domain), private to the lane group
+    bool valid[4];
+    float pr[4][R];
+    bool need_rescale = false;
+    float corr[R];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int pos = pos0 + it * 4 + g;
+      valid[it] = pos >= kv_begin && pos < kv_end;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float x[4];
+      float mx = m[r];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int pos = pos0 + it * 4 + g;
+        float v = p.use_cap ? tanhf(sc[it][r] * p.cap_in) * p.cap_out_log2 : sc[it][r] * p.scale_log2;
+        v = fmaf(slope_log2[r], (float)pos, v);
+        x[it] = valid[it] ? v : -INFINITY;
+        mx = fmaxf(mx, x[it]);
+      }
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      corr[r] = exp2f(m[r] - ms);
+      float sum = 0.f;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        pr[it][r] = exp2f(x[it] - ms);
+        sum += pr[it][r];
+      }
+      l[r] = fmaf(l[r], corr[r], sum);
+      m[r] = mx;
+      need_rescale |= (corr[r] != 1.f);
+    }
+    if (__any_sync(0xffffffffu, need_rescale)) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[r][e] *= corr[r];
+    }
+
+    // acc += P V
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (valid[it]) {  // masked rows may hold stale bytes (NaN) — never touch them
+        const T* vrow = vs + (it * 4 + g) * D;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          uint4 raw = ld_v4(vrow + (j + 8 * c) * 8);
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = Num<T>::unpack(w[e]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][c * 8 + 2 * e] = fmaf(pr[it][r], f.x, acc[r][c * 8 + 2 * e]);
+              acc[r][c * 8 + 2 * e + 1] = fmaf(pr[it][r], f.y, acc[r][c * 8 + 2 * e + 1]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && i + STAGES < n_my) issue(i + STAGES);
+  }
+
+  // ---- merge the 4 lane groups of the warp ----------------------------------
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m[r], off);
+      const float lo = __shfl_xor_sync(0xffffffffu, l[r], off);
+      const float mn = fmaxf(m[r], mo);
+      const float ms = (mn == -INFINITY) ? 0.f : mn;
+      const float a = exp2f(m[r] - ms), bb = exp2f(mo - ms);
+      l[r] = l[r] * a + lo * bb;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[r][e], off);
+        acc[r][e] = acc[r][e] * a + ao * bb;
+      }
+      m[r] = mn;
+    }
+  }
+
+  // ---- merge warps through shared memory (each warp reuses its own stages) ---
+  float* red = reinterpret_cast<float*>(my_stage);  // [R][D] acc, then [R] m, [R] l
+  if (g == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[r * D + (j + 8 * c) * 8 + e] = acc[r][c * 8 + e];
+      if (j == 0) {
+        red[R * D + r] = m[r];
+        red[R * D + R + r] = l[r];
+      }
+    }
+  }
+  __syncthreads();
+  constexpr size_t WARP_STRIDE = (size_t)STAGES * 2 * Cfg::TILE_ELEMS * sizeof(T) / sizeof(float);
+  const float* red0 = reinterpret_cast<const float*>(stage_base);
+  for (int idx = threadIdx.x; idx < rows_valid * D; idx += ATT_THREADS) {
+    const int r = idx / D, d = idx % D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, red0[w * WARP_STRIDE + R * D + r]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) {
+      const float sc_w = exp2f(red0[w * WARP_STRIDE + R * D + r] - M);
+      L = fmaf(red0[w * WARP_STRIDE + R * D + R + r], sc_w, L);
+      O = fmaf(red0[w * WARP_STRIDE + r * D + d], sc_w, O);
+    }
+    const float o = O / L;
+    const int h = head0 + r;
+    if (p.n_splits == 1) {
+      static_cast<T*>(p.out)[tok * p.o_stride_t + (int64_t)h * p.o_stride_h + d] = Num<T>::from_f(o);
+    } else {
+      p.ws_o[((ws_row + h) * p.n_splits + split) * D + d] = o;
+      if (d == 0) p.ws_lse[(ws_row + h) * p.n_splits + split] = M + log2f(L);
+    }
+  }
+}
+
+// Second pass: merge split-KV partials (same maths as the reference's unwired
+// attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).
+template <typename T, int D>
+__global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
+  const int h = blockIdx.x;
+  const int b = blockIdx.y / p.max_q_len, qi = blockIdx.y % p.max_q_len;
+  const int q_begin = p.q_cu_lens[b];
+  if (qi >= p.q_cu_lens[b + 1] - q_begin) return;
+  const int64_t tok = q_begin + qi;
+  const int64_t row = (int64_t)blockIdx.y * p.n_heads + h;
+  const float* lse = p.ws_lse + row * p.n_splits;
+  float M = -INFINITY;
+  for (int s = 0; s < p.n_splits; ++s) M = fmaxf(M, lse[s]);
+  float L = 0.f;
+  for (int s = 0; s < p.n_splits; ++s) L += exp2f(lse[s] - M);
+  const float inv = 1.f / L;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float o = 0.f;
+    for (int s = 0; s < p.n_splits; ++s) {
+      const float w = exp2f(lse[s] - M);
+      if (w != 0.f) o = fmaf(p.ws_o[(row * p.n_splits + s) * D + d], w, o);
+    }
+    static_cast<T*>(p.out)[tok * p.o_stride_t + (int64_t)h * p.o_stride_h + d] =
+        Num<T>::from_f(o * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct MapKey {
+  const void* ptr;
+  int64_t n_slots, stride_s, stride_h;
+  int n_kv_heads, head_dim, box_rows, dtype;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && n_slots == o.n_slots && stride_s == o.stride_s &&
+           stride_h == o.stride_h && n_kv_heads == o.n_kv_heads && head_dim == o.head_dim &&
+           box_rows == o.box_rows && dtype == o.dtype;
+  }
+};
+struct MapEntry {
+  MapKey key;
+  CUtensorMap map;
+};
+static std::mutex g_map_mu;
+static std::vector<MapEntry> g_maps;
+
+static int get_kv_tensor_map(const MapKey& key, CUtensorMap* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    for (const auto& e : g_maps)
+      if (e.key == key) {
+        *out = e.map;
+        return B200_OK;
+      }
+  }
+  tensor_map_encode_fn enc = get_tensor_map_encode();
+  if (!enc) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int es = 2;
+  cuuint64_t dims[3] = {(cuuint64_t)key.head_dim, (cuuint64_t)key.n_kv_heads,
+                        (cuuint64_t)key.n_slots};
+  cuuint64_t strides[2] = {(cuuint64_t)key.stride_h * es, (cuuint64_t)key.stride_s * es};
+  cuuint32_t box[3] = {(cuuint32_t)key.head_dim, 1u, (cuuint32_t)key.box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m,
+                   key.dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   3, const_cast<void*>(key.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for kv cache", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.push_back({key, m});
+  }
+  *out = m;
+  return B200_OK;
+}
+
+static int ilog2(int x) {
+  int s = 0;
+  while ((1 << s) < x) ++s;
+  return s;
+}
+
+// Split-KV plan from host scalars only (CUDA-graph safe).
+static void plan_splits(int64_t base_items, int max_kv_len, int ctas_per_sm, int* n_splits,
+                        int* tiles_per_split) {
+  const int n_tiles = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
+  const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
+  int s_min = (n_tiles + ATT_MAX_TPS - 1) / ATT_MAX_TPS;
+  int s_max = std::max(s_min, std::min(64, n_tiles / 8));  // >= 8 tiles (128 slots) per split
+  int best = s_min;
+  double best_eff = -1.0;
+  const char* env = getenv("B200_ATTN_SPLITS");
+  if (env && atoi(env) > 0) {
+    best = std::max(s_min, std::min(atoi(env), n_tiles));
+  } else {
+    for (int s = s_min; s <= s_max; ++s) {
+      const double waves = (double)(base_items * s) / (double)slots;
+      double eff = waves / std::ceil(waves);
+      if (waves >= 4.0) eff = std::max(eff, 0.97);  // enough waves: tail is amortised
+      if (eff > best_eff + 0.02) {
+        best_eff = eff;
+        best = s;
+      }
+    }
+  }
+  int tps = (n_tiles + best - 1) / best;
+  *tiles_per_split = tps;
+  *n_splits = (n_tiles + tps - 1) / tps;
+}
+
+static int hg_rows(int group) { return group >= 4 ? 4 : (group >= 2 ? 2 : 1); }
+
+template <typename T, int D, int R>
+static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnParams& p,
+                       int64_t batch, cudaStream_t st) {
+  constexpr size_t smem = attn_smem_bytes<T, D>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(paged_attn_decode_kernel<T, D, R>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)p.n_splits, (unsigned)(p.n_kv_heads * p.n_hg),
+            (unsigned)(batch * p.max_q_len));
+  paged_attn_decode_kernel<T, D, R><<<grid, ATT_THREADS, smem, st>>>(kmap, vmap, p);
+  B200_LAUNCH_OK("paged_attn_decode");
+  if (p.n_splits > 1) {
+    dim3 cgrid((unsigned)p.n_heads, (unsigned)(batch * p.max_q_len));
+    paged_attn_combine_kernel<T, D><<<cgrid, 128, 0, st>>>(p);
+    B200_LAUNCH_OK("paged_attn_combine");
+  }
+  return B200_OK;
+}
+
+template <typename T, int D>
+static int launch_attn_r(int R, const CUtensorMap& kmap, const CUtensorMap& vmap,
+                         const AttnParams& p, int64_t batch, cudaStream_t st) {
+  switch (R) {
+    case 4: return launch_attn<T, D, 4>(kmap, vmap, p, batch, st);
+    case 2: return launch_attn<T, D, 2>(kmap, vmap, p, batch, st);
+    default: return launch_attn<T, D, 1>(kmap, vmap, p, batch, st);
+  }
+}
+
+template <typename T>
+static int launch_attn_d(int D, int R, const CUtensorMap& kmap, const CUtensorMap& vmap,
+                         const AttnParams& p, int64_t batch, cudaStream_t st) {
+  switch (D) {
+    case 64: return launch_attn_r<T, 64>(R, kmap, vmap, p, batch, st);
+    case 128: return launch_attn_r<T, 128>(R, kmap, vmap, p, batch, st);
+    case 256: return launch_attn_r<T, 256>(R, kmap, vmap, p, batch, st);
+    default:
+      return set_error(B200_ERR_UNSUPPORTED, "paged_attn: head_dim %d not in {64,128,256}", D);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_t max_kv_len,
+                                        int64_t n_heads, int64_t n_kv_heads, int64_t head_dim) {
+  if (batch <= 0 || max_q_len <= 0 || n_heads <= 0 || n_kv_heads <= 0) return 0;
+  const int group = (int)(n_heads / n_kv_heads);
+  const int R = hg_rows(group);
+  const int n_hg = (group + R - 1) / R;
+  int n_splits, tps;
+  plan_splits(batch * max_q_len * n_kv_heads * n_hg, (int)max_kv_len, head_dim <= 128 ? 2 : 1,
+              &n_splits, &tps);
+  if (n_splits <= 1) return 0;
+  // worst case over env overrides: size for the planned split count
+  return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
+}
+
+int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const void* v_cache,
+                           const int32_t* q_cu_lens, const int32_t* kv_cu_lens,
+                           const int32_t* block_table, const int32_t* block_cu_lens,
+                           const float* alibi_slopes, int64_t batch, int64_t n_heads,
+                           int64_t n_kv_heads, int64_t head_dim, int64_t n_slots,
+                           int64_t q_stride_t, int64_t q_stride_h, int64_t o_stride_t,
+                           int64_t o_stride_h, int64_t kv_stride_s, int64_t kv_stride_h,
+                           int block_size, int max_q_len, int max_kv_len, float sm_scale,
+                           float logits_soft_cap, int sliding_window, void* workspace,
+                           int64_t workspace_bytes, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && q && k_cache && v_cache && q_cu_lens && kv_cu_lens && block_table &&
+                     block_cu_lens,
+                 "paged_attn: null pointer");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "paged_attn: dtype must be bf16/fp16");
+  B200_CHECK_ARG(batch >= 0 && n_heads > 0 && n_kv_heads > 0 && n_heads % n_kv_heads == 0,
+                 "paged_attn: bad head counts %lld/%lld", (long long)n_heads,
+                 (long long)n_kv_heads);
+  B200_CHECK_ARG(block_size > 0 && (block_size & (block_size - 1)) == 0,
+                 "paged_attn: block_size %d must be a power of two", block_size);
+  B200_CHECK_ARG(n_slots > 0 && n_slots < (1ll << 31), "paged_attn: bad n_slots");
+  B200_CHECK_ARG(is_aligned(q, 16) && is_aligned(k_cache, 16) && is_aligned(v_cache, 16) &&
+                     q_stride_t % 8 == 0 && q_stride_h % 8 == 0 && kv_stride_s % 8 == 0 &&
+                     kv_stride_h % 8 == 0,
+                 "paged_attn: q / kv cache must be 16-byte aligned with strides %% 8 == 0");
+  if (batch == 0 || max_q_len <= 0 || max_kv_len <= 0) return B200_OK;
+
+  const int group = (int)(n_heads / n_kv_heads);
+  const int R = hg_rows(group);
+  AttnParams p{};
+  p.q = q;
+  p.out = out;
+  p.q_cu_lens = q_cu_lens;
+  p.kv_cu_lens = kv_cu_lens;
+  p.block_table = block_table;
+  p.block_cu_lens = block_cu_lens;
+  p.alibi = alibi_slopes;
+  p.q_stride_t = q_stride_t;
+  p.q_stride_h = q_stride_h;
+  p.o_stride_t = o_stride_t;
+  p.o_stride_h = o_stride_h;
+  p.n_heads = (int)n_heads;
+  p.n_kv_heads = (int)n_kv_heads;
+  p.group = group;
+  p.n_hg = (group + R - 1) / R;
+  p.block_shift = ilog2(block_size);
+  p.block_mask = block_size - 1;
+  p.box_rows = block_size < ATT_TILE ? block_size : ATT_TILE;
+  p.boxes_per_tile = ATT_TILE / p.box_rows;
+  p.max_q_len = max_q_len;
+  p.window = sliding_window;
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (logits_soft_cap > 0.f) {
+    p.use_cap = 1;
+    p.cap_in = sm_scale / logits_soft_cap;
+    p.cap_out_log2 = logits_soft_cap * LOG2E;
+  } else {
+    p.use_cap = 0;
+    p.scale_log2 = sm_scale * LOG2E;
+  }
+  plan_splits(batch * max_q_len * n_kv_heads * p.n_hg, max_kv_len, head_dim <= 128 ? 2 : 1,
+              &p.n_splits, &p.tiles_per_split);
+  if (p.n_splits > 1) {
+    const int64_t rows = batch * max_q_len * n_heads * p.n_splits;
+    const int64_t need = rows * (head_dim + 1) * (int64_t)sizeof(float);
+    if (!workspace || workspace_bytes < need)
+      return set_error(B200_ERR_WORKSPACE, "paged_attn: workspace %lld B < required %lld B",
+                       (long long)workspace_bytes, (long long)need);
+    B200_CHECK_ARG(is_aligned(workspace, 16), "paged_attn: workspace must be 16-byte aligned");
+    p.ws_o = static_cast<float*>(workspace);
+    p.ws_lse = p.ws_o + rows * head_dim;
+  }
+
+  CUtensorMap kmap, vmap;
+  MapKey key{k_cache, n_slots, kv_stride_s, kv_stride_h, (int)n_kv_heads, (int)head_dim,
+             p.box_rows, dtype};
+  int rc = get_kv_tensor_map(key, &kmap);
+  if (rc != B200_OK) return rc;
+  key.ptr = v_cache;
+  rc = get_kv_tensor_map(key, &vmap);
+  if (rc != B200_OK) return rc;
+
+  auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_BF16)
+    return launch_attn_d<__nv_bfloat16>((int)head_dim, R, kmap, vmap, p, batch, st);
+  return launch_attn_d<__half>((int)head_dim, R, kmap, vmap, p, batch, st);
+}
+
+}  // extern "C"

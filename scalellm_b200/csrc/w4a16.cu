@@ -1,0 +1,761 @@
+// w4a16.cu — int4-weight x bf16-activation matmul for sm_100a.
+//
+// Replaces marlin::{awq,gptq}_repack + marlin::gptq_gemm
+// (src/kernels/quantization/marlin.h:17-37) behind the qlinear plugins.
+//
+//   C[M,N] = A[M,K] * W,  W[k,n] = bf16_mul(bf16(q) - bf16(z), s)     (exact sub,
+//   one rounding in the multiply — marlin/numeric_conversion.h:144-167,221-240),
+//   fp32 accumulation in TMEM, fp32 cross-CTA reduction, one final rounding.
+//
+// B200 design (not Marlin's mma.sync/cp.async pipeline):
+//   * operands swapped so the WEIGHT tile is the 128-row UMMA "A" operand and the
+//     decode batch (M <= 128) is the UMMA N dimension: D[n, m] in TMEM.
+//   * weights live in HBM as self-contained "tile blobs" (128 n x 128 k: packed
+//     nibbles + that tile's scales + zero points), streamed with one bulk-async
+//     copy per blob into a deep shared-memory ring;
+//   * 8 dequant warps turn a blob into two 128x64 bf16 K-major SWIZZLE_128B UMMA
+//     tiles (lop3 magic-number int4->bf16, HSUB2 zero point, HMUL2 scale);
+//   * one thread issues tcgen05.mma (kind::f16, M=128, N=MT, K=16) with the
+//     accumulator in TMEM (double buffered), activations arrive by TMA (128B swizzle);
+//   * stream-K over (n_tile, k_tile) units so all SMs stream an equal share of
+//     the weight bytes; partial tiles meet in an fp32 workspace and the last
+//     arriving CTA reduces them in a fixed order (deterministic).
+//
+// W4 tile blob (n_tile nt, k_tile kt) at ((nt * K/128) + kt) * blob_bytes:
+//   [0, 8192)            qdata: uint4[(khalf*2+q4)*128 + n_local]; word w of that
+//                        uint4 holds k = kt*128 + (khalf*8+q4*4+w)*8 + {0..7} of
+//                        column nt*128+n_local, nibble p<4 -> k+2p, p>=4 -> k+2(p-4)+1
+//   [8192, +ngrp*256)    scales bf16 [ngrp][128]     (ngrp = 128/geff, geff = min(g,128))
+//   [.., +ngrp*128)      zero points, uint8 [ngrp][128] (0..16: GPTQ-v1 "zero+1" can reach 16)
+
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int W4_BN = 128;
+constexpr int W4_BK = 128;
+constexpr int W4_QBYTES = 8192;
+constexpr int W4_MAX_BLOB = 8192 + 4 * (256 + 128);  // 9728
+
+__host__ __device__ inline int w4_geff(int g) { return (g <= 0 || g > 128) ? 128 : g; }
+__host__ __device__ inline int w4_blob_bytes(int geff) {
+  return W4_QBYTES + (128 / geff) * (256 + 128);
+}
+
+// ===========================================================================
+// prepack: checkpoint format -> tile blobs
+// ===========================================================================
+// MODE 0 = AWQ (qweight [K, N/8], nibble order [0,2,4,6,1,3,5,7] along N)
+// MODE 1 = GPTQ (qweight [K/8, N], natural nibble order along K)
+template <int MODE>
+__device__ __forceinline__ uint32_t load_q(const int32_t* __restrict__ qweight, int64_t k,
+                                           int64_t n, int64_t N) {
+  if (MODE == 0) {
+    const uint32_t w = (uint32_t)qweight[k * (N / 8) + (n >> 3)];
+    const int c = (int)(n & 7);
+    const int pos = (c >> 1) + ((c & 1) << 2);  // inverse of [0,2,4,6,1,3,5,7]
+    return (w >> (4 * pos)) & 0xf;
+  } else {
+    const uint32_t w = (uint32_t)qweight[(k >> 3) * N + n];
+    return (w >> (4 * (int)(k & 7))) & 0xf;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t load_z(const int32_t* __restrict__ qzeros, int64_t grp,
+                                           int64_t n, int64_t N, int plus_one) {
+  if (qzeros == nullptr) return 8u;  // symmetric GPTQ (qlinear_gptq_marlin_impl.cpp:18-20)
+  const uint32_t w = (uint32_t)qzeros[grp * (N / 8) + (n >> 3)];
+  const int c = (int)(n & 7);
+  const int pos = MODE == 0 ? (c >> 1) + ((c & 1) << 2) : c;
+  return ((w >> (4 * pos)) & 0xf) + (plus_one ? 1u : 0u);  // may be 16 (qlinear_impl.cpp:44)
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) w4_prepack_kernel(uint8_t* __restrict__ packed,
+                                                         const int32_t* __restrict__ qweight,
+                                                         const int32_t* __restrict__ qzeros,
+                                                         const __nv_bfloat16* __restrict__ scales,
+                                                         int64_t K, int64_t N, int g_actual,
+                                                         int geff, int plus_one) {
+  const int kt = blockIdx.x, nt = blockIdx.y;
+  const int KT = (int)(K / W4_BK);
+  const int ngrp = 128 / geff;
+  const int blob = w4_blob_bytes(geff);
+  uint8_t* out = packed + ((int64_t)nt * KT + kt) * blob;
+  const int t = threadIdx.x;
+  const int n_local = t & 127, khalf = t >> 7;
+  const int64_t n = (int64_t)nt * 128 + n_local;
+#pragma unroll
+  for (int q4 = 0; q4 < 2; ++q4) {
+    uint32_t words[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int64_t k0 = (int64_t)kt * 128 + (khalf * 8 + q4 * 4 + w) * 8;
+      uint32_t word = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int dk = p < 4 ? 2 * p : 2 * (p - 4) + 1;
+        word |= load_q<MODE>(qweight, k0 + dk, n, N) << (4 * p);
+      }
+      words[w] = word;
+    }
+    uint4 v = make_uint4(words[0], words[1], words[2], words[3]);
+    *reinterpret_cast<uint4*>(out + ((khalf * 2 + q4) * 128 + n_local) * 16) = v;
+  }
+  __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(out + W4_QBYTES);
+  uint8_t* z_out = out + W4_QBYTES + ngrp * 256;
+  for (int i = t; i < ngrp * 128; i += 256) {
+    const int grp = i >> 7, nl = i & 127;
+    const int64_t gi = ((int64_t)kt * 128 + grp * geff) / g_actual;
+    s_out[i] = scales[gi * N + (int64_t)nt * 128 + nl];
+  }
+  for (int i = t; i < ngrp * 128; i += 256) {
+    const int grp = i >> 7, nl = i & 127;
+    const int64_t gi = ((int64_t)kt * 128 + grp * geff) / g_actual;
+    z_out[i] = (uint8_t)load_z<MODE>(qzeros, gi, (int64_t)nt * 128 + nl, N, plus_one);
+  }
+}
+
+// ===========================================================================
+// the dequant arithmetic shared by every consumer of a blob
+// ===========================================================================
+// one packed word (8 nibbles, pair-interleaved) -> 8 consecutive-k bf16 weights
+__device__ __forceinline__ uint4 w4_dequant_word(uint32_t q, __nv_bfloat162 zmagic,
+                                                 __nv_bfloat162 s2) {
+  uint32_t r[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    uint32_t v;
+    // (q & 0x000f000f) | 0x43004300  ->  bf16x2 (128 + nibble_j, 128 + nibble_{j+4})
+    asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(v) : "r"(q >> (4 * jj)));
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
+    b = __hsub2(b, zmagic);  // exact: (128+q) - (128+z)
+    b = __hmul2(b, s2);      // the single bf16 rounding
+    r[jj] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+__device__ __forceinline__ __nv_bfloat162 w4_zmagic(uint32_t z) {
+  const uint32_t m = 0x4300u | z;  // bf16(128 + z)
+  const uint32_t mm = m | (m << 16);
+  return *reinterpret_cast<const __nv_bfloat162*>(&mm);
+}
+
+// blob -> dense W[K,N] bf16 (debug / bit-exact prepack parity)
+__global__ void __launch_bounds__(256) w4_dequant_kernel(__nv_bfloat16* __restrict__ w_out,
+                                                         const uint8_t* __restrict__ packed,
+                                                         int64_t K, int64_t N, int geff) {
+  const int kt = blockIdx.x, nt = blockIdx.y;
+  const int KT = (int)(K / W4_BK);
+  const int ngrp = 128 / geff;
+  const uint8_t* blob = packed + ((int64_t)nt * KT + kt) * w4_blob_bytes(geff);
+  const __nv_bfloat16* s_in = reinterpret_cast<const __nv_bfloat16*>(blob + W4_QBYTES);
+  const uint8_t* z_in = blob + W4_QBYTES + ngrp * 256;
+  const int t = threadIdx.x, n_local = t & 127, khalf = t >> 7;
+#pragma unroll
+  for (int q4 = 0; q4 < 2; ++q4) {
+    const uint4 u = *reinterpret_cast<const uint4*>(blob + ((khalf * 2 + q4) * 128 + n_local) * 16);
+    const uint32_t words[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int kc = khalf * 8 + q4 * 4 + w;
+      const int grp = (kc * 8) / geff;
+      const __nv_bfloat16 s = s_in[grp * 128 + n_local];
+      const uint32_t z = z_in[grp * 128 + n_local];
+      const uint4 d = w4_dequant_word(words[w], w4_zmagic(z), __halves2bfloat162(s, s));
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w_out[((int64_t)kt * 128 + kc * 8 + i) * N + (int64_t)nt * 128 + n_local] = e[i];
+    }
+  }
+}
+
+// ===========================================================================
+// bring-up / debug GEMM on CUDA cores (selected only by B200_W4A16_IMPL=simt)
+// ===========================================================================
+// grid (N/128, ceil(M/8)); thread = one output column, 8 rows.
+__global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
+    __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ A,
+    const uint8_t* __restrict__ packed, const __nv_bfloat16* __restrict__ bias, int M, int N,
+    int K, int64_t lda, int64_t ldc, int geff) {
+  const int nt = blockIdx.x, m0 = blockIdx.y * 8, n_local = threadIdx.x;
+  const int KT = K / W4_BK, ngrp = 128 / geff, blob_bytes = w4_blob_bytes(geff);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int kt = 0; kt < KT; ++kt) {
+    const uint8_t* blob = packed + ((int64_t)nt * KT + kt) * blob_bytes;
+    const __nv_bfloat16* s_in = reinterpret_cast<const __nv_bfloat16*>(blob + W4_QBYTES);
+    const uint8_t* z_in = blob + W4_QBYTES + ngrp * 256;
+    for (int kc = 0; kc < 16; ++kc) {
+      const int khalf = kc >> 3, q4 = (kc >> 2) & 1, w = kc & 3;
+      const uint32_t word =
+          reinterpret_cast<const uint32_t*>(blob + ((khalf * 2 + q4) * 128 + n_local) * 16)[w];
+      const int grp = (kc * 8) / geff;
+      const __nv_bfloat16 s = s_in[grp * 128 + n_local];
+      const uint32_t z = z_in[grp * 128 + n_local];
+      const uint4 d = w4_dequant_word(word, w4_zmagic(z), __halves2bfloat162(s, s));
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&d);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (m0 + r < M) {
+          const __nv_bfloat16* a = A + (int64_t)(m0 + r) * lda + kt * 128 + kc * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            acc[r] = fmaf(__bfloat162float(a[i]), __bfloat162float(e[i]), acc[r]);
+        }
+      }
+    }
+  }
+  const int n = nt * 128 + n_local;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (m0 + r < M) {
+      __nv_bfloat16 o = __float2bfloat16_rn(acc[r]);
+      if (bias) o = __float2bfloat16_rn(__bfloat162float(o) + __bfloat162float(bias[n]));
+      C[(int64_t)(m0 + r) * ldc + n] = o;
+    }
+  }
+}
+
+// ===========================================================================
+// tcgen05 stream-K GEMM
+// ===========================================================================
+template <int MT>
+struct W4Cfg {
+  static constexpr int RAW_STAGES = MT <= 64 ? 6 : 4;
+  static constexpr int ACT_STAGES = MT <= 64 ? 3 : 2;
+  static constexpr int DEQ_STAGES = 3;
+  static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
+  static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
+  static constexpr int DEQ_ATOM = 128 * 128;      // [128 n x 64 k] bf16
+  static constexpr int DEQ_BYTES = 2 * DEQ_ATOM;
+  static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
+  static constexpr int TMEM_COLS = 2 * MT < 32 ? 32 : 2 * MT;
+  static constexpr int N_BARS = 2 * RAW_STAGES + 2 * ACT_STAGES + 2 * DEQ_STAGES + 4;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)DEQ_STAGES * DEQ_BYTES +
+                                 (size_t)ACT_STAGES * ACT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
+                                 N_BARS * 8 + 64;
+};
+
+constexpr int W4_DEQ_WARPS = 8;
+constexpr int W4_WARP_RAW = 8, W4_WARP_ACT = 9, W4_WARP_MMA = 10, W4_WARP_EPI = 11;
+constexpr int W4_THREADS = 15 * 32;
+
+struct W4Params {
+  const uint8_t* packed;
+  __nv_bfloat16* C;
+  const __nv_bfloat16* bias;
+  float* ws_partial;  // [2*P][MT][128]
+  int* counters;      // [NT]
+  int M, N, K, KT, NT, geff, ngrp, blob_bytes, units;
+  int64_t ldc;
+};
+
+struct SegIter {
+  int u, u1, KT;
+  __device__ __forceinline__ bool next(int& nt, int& kt0, int& kt1) {
+    if (u >= u1) return false;
+    nt = u / KT;
+    kt0 = u - nt * KT;
+    kt1 = min(KT, kt0 + (u1 - u));
+    u += kt1 - kt0;
+    return true;
+  }
+};
+
+__device__ __forceinline__ int w4_unit_begin(int p, int units, int P) {
+  return (int)(((int64_t)p * units) / P);
+}
+// CTA that owns unit u (largest p with begin(p) <= u)
+__device__ __forceinline__ int w4_owner(int u, int units, int P) {
+  int p = (int)min((int64_t)P - 1, ((int64_t)u * P) / units);
+  while (p > 0 && w4_unit_begin(p, units, P) > u) --p;
+  while (p + 1 < P && w4_unit_begin(p + 1, units, P) <= u) ++p;
+  return p;
+}
+
+template <int MT>
+__global__ void __launch_bounds__(W4_THREADS, 1)
+w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
+  using Cfg = W4Cfg<MT>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* deq_smem = base;
+  uint8_t* act_smem = deq_smem + Cfg::DEQ_STAGES * Cfg::DEQ_BYTES;
+  uint8_t* raw_smem = act_smem + Cfg::ACT_STAGES * Cfg::ACT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_smem + Cfg::RAW_STAGES * Cfg::RAW_BYTES);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + Cfg::RAW_STAGES;
+  uint64_t* act_full = raw_empty + Cfg::RAW_STAGES;
+  uint64_t* act_empty = act_full + Cfg::ACT_STAGES;
+  uint64_t* deq_full = act_empty + Cfg::ACT_STAGES;
+  uint64_t* deq_empty = deq_full + Cfg::DEQ_STAGES;
+  uint64_t* tmem_full = deq_empty + Cfg::DEQ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* flag_smem = tmem_holder + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = gridDim.x;
+  const int u_begin = w4_unit_begin(blockIdx.x, p.units, P);
+  const int u_end = w4_unit_begin(blockIdx.x + 1, p.units, P);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], W4_DEQ_WARPS);
+    }
+    for (int i = 0; i < Cfg::ACT_STAGES; ++i) {
+      mbar_init(&act_full[i], 1);
+      mbar_init(&act_empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::DEQ_STAGES; ++i) {
+      mbar_init(&deq_full[i], W4_DEQ_WARPS);
+      mbar_init(&deq_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W4_WARP_MMA) {
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp == W4_WARP_ACT && lane == 0) prefetch_tensormap(&amap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp < W4_DEQ_WARPS) {
+    // ===================== dequant warps =====================================
+    const int t = threadIdx.x, n_local = t & 127, khalf = t >> 7;
+    const int row_sw = n_local & 7;
+    SegIter it{u_begin, u_end, p.KT};
+    int nt, kt0, kt1, cnt = 0;
+    while (it.next(nt, kt0, kt1)) {
+      for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+        const int rs = cnt % Cfg::RAW_STAGES, ds = cnt % Cfg::DEQ_STAGES;
+        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
+        const uint8_t* raw = raw_smem + rs * Cfg::RAW_BYTES;
+        mbar_wait(&raw_full[rs], rph);
+        uint4 u[2];
+        u[0] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 0) * 128 + n_local) * 16);
+        u[1] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 1) * 128 + n_local) * 16);
+        const __nv_bfloat16* s_in = reinterpret_cast<const __nv_bfloat16*>(raw + W4_QBYTES);
+        const uint8_t* z_in = raw + W4_QBYTES + p.ngrp * 256;
+        // this thread's 64 k span 64/geff groups (1 for geff >= 64, 2 for geff == 32)
+        const int g0 = (khalf * 64) / p.geff;
+        const int g1 = (khalf * 64 + 32) / p.geff;
+        const __nv_bfloat16 s0 = s_in[g0 * 128 + n_local], s1 = s_in[g1 * 128 + n_local];
+        const uint32_t z0 = z_in[g0 * 128 + n_local];
+        const uint32_t z1 = z_in[g1 * 128 + n_local];
+        const __nv_bfloat162 s2[2] = {__halves2bfloat162(s0, s0), __halves2bfloat162(s1, s1)};
+        const __nv_bfloat162 zm[2] = {w4_zmagic(z0), w4_zmagic(z1)};
+        mbar_wait(&deq_empty[ds], dph ^ 1);
+        // this thread's 64 k all live in swizzle atom `khalf`, chunks 0..7 of row n_local
+        uint8_t* drow = deq_smem + ds * Cfg::DEQ_BYTES + khalf * Cfg::DEQ_ATOM + n_local * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const uint32_t words[4] = {u[q4].x, u[q4].y, u[q4].z, u[q4].w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int c = q4 * 4 + w;  // 16-byte chunk (8 k) within the 128-byte row
+            const uint4 d = w4_dequant_word(words[w], zm[q4], s2[q4]);
+            *reinterpret_cast<uint4*>(drow + ((c ^ row_sw) << 4)) = d;
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05 (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&deq_full[ds]);
+          mbar_arrive(&raw_empty[rs]);
+        }
+      }
+    }
+  } else if (warp == W4_WARP_RAW) {
+    // ===================== weight-blob producer ==============================
+    if (lane == 0) {
+      SegIter it{u_begin, u_end, p.KT};
+      int nt, kt0, kt1, cnt = 0;
+      while (it.next(nt, kt0, kt1)) {
+        for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+          const int rs = cnt % Cfg::RAW_STAGES;
+          const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1;
+          mbar_wait(&raw_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)p.blob_bytes);
+          bulk_load_1d(raw_smem + rs * Cfg::RAW_BYTES,
+                       p.packed + ((int64_t)nt * p.KT + kt) * p.blob_bytes, (uint32_t)p.blob_bytes,
+                       &raw_full[rs]);
+        }
+      }
+    }
+  } else if (warp == W4_WARP_ACT) {
+    // ===================== activation producer (TMA) =========================
+    if (lane == 0) {
+      SegIter it{u_begin, u_end, p.KT};
+      int nt, kt0, kt1, cnt = 0;
+      while (it.next(nt, kt0, kt1)) {
+        for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+          const int as = cnt % Cfg::ACT_STAGES;
+          const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
+          mbar_wait(&act_empty[as], aph ^ 1);
+          mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
+          uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
+          tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
+          tma_load_2d(dst + Cfg::ACT_ATOM, &amap, &act_full[as], kt * 128 + 64, 0);
+        }
+      }
+    }
+  } else if (warp == W4_WARP_MMA) {
+    // ===================== MMA issuer =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
+      SegIter it{u_begin, u_end, p.KT};
+      int nt, kt0, kt1, cnt = 0, seg = 0;
+      while (it.next(nt, kt0, kt1)) {
+        const int buf = seg & 1;
+        const uint32_t tph = (seg >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], tph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * MT;
+        for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+          const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::DEQ_STAGES;
+          const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
+          mbar_wait(&act_full[as], aph);
+          mbar_wait(&deq_full[ds], dph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(deq_smem + ds * Cfg::DEQ_BYTES);
+          const uint32_t b_addr = smem_u32(act_smem + as * Cfg::ACT_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const int atom = ks >> 2, kk = ks & 3;
+            const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr + atom * Cfg::DEQ_ATOM + kk * 32);
+            const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + atom * Cfg::ACT_ATOM + kk * 32);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kt > kt0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&deq_empty[ds]);
+          umma_commit(&act_empty[as]);
+        }
+        umma_commit(&tmem_full[buf]);
+        ++seg;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (4) =================================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may touch
+    const int n_local = quad * 32 + lane;
+    const int et = (warp - W4_WARP_EPI) * 32 + lane;  // 0..127 within the epilogue group
+    SegIter it{u_begin, u_end, p.KT};
+    int nt, kt0, kt1, seg = 0;
+    while (it.next(nt, kt0, kt1)) {
+      const int buf = seg & 1;
+      const uint32_t tph = (seg >> 1) & 1;
+      const bool full_tile = (kt0 == 0 && kt1 == p.KT);
+      const int n = nt * 128 + n_local;
+      mbar_wait(&tmem_full[buf], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * MT;
+      float* part = nullptr;
+      if (!full_tile) {
+        const int slot = 2 * blockIdx.x + (kt0 > 0 ? 0 : 1);
+        part = p.ws_partial + (int64_t)slot * MT * 128;
+      }
+      float bias_f = 0.f;
+      if (full_tile && p.bias) bias_f = __bfloat162float(p.bias[n]);
+      constexpr int CH = MT >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < MT; c0 += CH) {
+        uint32_t r[CH];
+        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r);
+        else tmem_ld_32x32b_x16(taddr + c0, r);
+        tmem_ld_wait();
+        if (full_tile) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int m = c0 + i;
+            if (m < p.M) {
+              __nv_bfloat16 o = __float2bfloat16_rn(__uint_as_float(r[i]));
+              if (p.bias) o = __float2bfloat16_rn(__bfloat162float(o) + bias_f);
+              p.C[(int64_t)m * p.ldc + n] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int m = c0 + i;
+            if (m < p.M) part[m * 128 + n_local] = __uint_as_float(r[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+
+      if (!full_tile) {
+        // ---- publish the partial; the last contributor reduces the tile -------
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int u_lo = nt * p.KT;
+        const int p_first = w4_owner(u_lo, p.units, P);
+        const int p_last = w4_owner(u_lo + p.KT - 1, p.units, P);
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[nt], 1);
+          *flag_smem = (old == p_last - p_first) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*flag_smem) {
+          __threadfence();
+          for (int idx = et; idx < p.M * 128; idx += 128) {
+            const int m = idx >> 7, nl = idx & 127;
+            float acc = 0.f;
+            for (int pc = p_first; pc <= p_last; ++pc) {
+              const int cb = max(w4_unit_begin(pc, p.units, P), u_lo);
+              const int slot = 2 * pc + (cb > u_lo ? 0 : 1);
+              acc += __ldcg(p.ws_partial + ((int64_t)slot * MT + m) * 128 + nl);
+            }
+            const int nn = nt * 128 + nl;
+            __nv_bfloat16 o = __float2bfloat16_rn(acc);
+            if (p.bias) o = __float2bfloat16_rn(__bfloat162float(o) + __bfloat162float(p.bias[nn]));
+            p.C[(int64_t)m * p.ldc + nn] = o;
+          }
+          if (et == 0) p.counters[nt] = 0;  // leave the workspace zeroed (Marlin's contract)
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_smem reuse
+      }
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W4_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct AMapKey {
+  const void* ptr;
+  int64_t M, K, lda;
+  int mt;
+  bool operator==(const AMapKey& o) const {
+    return ptr == o.ptr && M == o.M && K == o.K && lda == o.lda && mt == o.mt;
+  }
+};
+struct AMapEntry {
+  AMapKey key;
+  CUtensorMap map;
+};
+static std::mutex g_amap_mu;
+static std::vector<AMapEntry> g_amaps;
+
+static int get_act_tensor_map(const AMapKey& key, CUtensorMap* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_amap_mu);
+    for (const auto& e : g_amaps)
+      if (e.key == key) {
+        *out = e.map;
+        return B200_OK;
+      }
+  }
+  tensor_map_encode_fn enc = get_tensor_map_encode();
+  if (!enc) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)key.K, (cuuint64_t)key.M};
+  cuuint64_t strides[1] = {(cuuint64_t)key.lda * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)key.mt};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(key.ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for activations", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_amap_mu);
+    if (g_amaps.size() > 4096) g_amaps.clear();
+    g_amaps.push_back({key, m});
+  }
+  *out = m;
+  return B200_OK;
+}
+
+static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
+
+template <int MT>
+static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, int grid, cudaStream_t st) {
+  using Cfg = W4Cfg<MT>;
+  B200_CUDA_OK(cudaFuncSetAttribute(w4a16_gemm_kernel<MT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  w4a16_gemm_kernel<MT><<<grid, W4_THREADS, Cfg::SMEM, st>>>(amap, p);
+  B200_LAUNCH_OK("w4a16_gemm");
+  return B200_OK;
+}
+
+static int w4_grid(int units) {
+  int P = sm_count();
+  const char* env = getenv("B200_W4A16_CTAS");
+  if (env && atoi(env) > 0) P = atoi(env);
+  return units < P ? units : P;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int64_t b200_w4a16_packed_bytes(int64_t K, int64_t N, int group_size) {
+  if (K <= 0 || N <= 0 || K % 128 || N % 128) return -1;
+  return (K / 128) * (N / 128) * (int64_t)w4_blob_bytes(w4_geff(group_size));
+}
+
+static int check_w4_shape(const char* who, int64_t K, int64_t N, int g) {
+  B200_CHECK_ARG(K > 0 && N > 0 && K % 128 == 0 && N % 128 == 0,
+                 "%s: K=%lld and N=%lld must be positive multiples of 128", who, (long long)K,
+                 (long long)N);
+  B200_CHECK_ARG(g == -1 || g == 32 || g == 64 || g == 128 || (g > 128 && g % 128 == 0 && K % g == 0),
+                 "%s: group_size %d not in {-1,32,64,128,k*128}", who, g);
+  return B200_OK;
+}
+
+static int prepack(int mode, void* packed, const int32_t* qweight, const int32_t* qzeros,
+                   const void* scales, int64_t K, int64_t N, int g, int plus_one,
+                   b200_stream_t stream) {
+  B200_CHECK_ARG(packed && qweight && scales, "w4a16_prepack: null pointer");
+  B200_CHECK_ARG(mode == 1 || qzeros != nullptr, "w4a16_prepack_awq: qzeros required");
+  int rc = check_w4_shape("w4a16_prepack", K, N, g);
+  if (rc != B200_OK) return rc;
+  B200_CHECK_ARG(is_aligned(packed, 16), "w4a16_prepack: packed buffer must be 16-byte aligned");
+  const int g_actual = g <= 0 ? (int)K : g;
+  const int geff = w4_geff(g);
+  dim3 grid((unsigned)(K / 128), (unsigned)(N / 128));
+  auto st = static_cast<cudaStream_t>(stream);
+  if (mode == 0)
+    w4_prepack_kernel<0><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(packed), qweight, qzeros,
+                                               static_cast<const __nv_bfloat16*>(scales), K, N,
+                                               g_actual, geff, 0);
+  else
+    w4_prepack_kernel<1><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(packed), qweight, qzeros,
+                                               static_cast<const __nv_bfloat16*>(scales), K, N,
+                                               g_actual, geff, plus_one);
+  B200_LAUNCH_OK("w4a16_prepack");
+  return B200_OK;
+}
+
+int b200_w4a16_prepack_awq(void* packed, const int32_t* qweight, const int32_t* qzeros,
+                           const void* scales, int64_t K, int64_t N, int group_size,
+                           b200_stream_t stream) {
+  return prepack(0, packed, qweight, qzeros, scales, K, N, group_size, 0, stream);
+}
+
+int b200_w4a16_prepack_gptq(void* packed, const int32_t* qweight, const int32_t* qzeros,
+                            const void* scales, int64_t K, int64_t N, int group_size,
+                            int zeros_plus_one, b200_stream_t stream) {
+  return prepack(1, packed, qweight, qzeros, scales, K, N, group_size, zeros_plus_one, stream);
+}
+
+int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K, int64_t N, int group_size,
+                       b200_stream_t stream) {
+  B200_CHECK_ARG(w_out && packed, "w4a16_dequant: null pointer");
+  int rc = check_w4_shape("w4a16_dequant", K, N, group_size);
+  if (rc != B200_OK) return rc;
+  dim3 grid((unsigned)(K / 128), (unsigned)(N / 128));
+  w4_dequant_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(w_out), static_cast<const uint8_t*>(packed), K, N,
+      w4_geff(group_size));
+  B200_LAUNCH_OK("w4a16_dequant");
+  return B200_OK;
+}
+
+int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  (void)N;
+  (void)K;
+  if (M <= 0) return B200_W4A16_COUNTER_BYTES;
+  const int mt = pick_mt(M);
+  // 2 partial slots per CTA; CTAs <= 1024 covers any env override of the grid
+  return B200_W4A16_COUNTER_BYTES + 2ll * 1024 * mt * 128 * (int64_t)sizeof(float);
+}
+
+int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias, int64_t M,
+                    int64_t N, int64_t K, int64_t lda, int64_t ldc, int group_size,
+                    void* workspace, int64_t workspace_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(C && A && packed, "w4a16_gemm: null pointer");
+  int rc = check_w4_shape("w4a16_gemm", K, N, group_size);
+  if (rc != B200_OK) return rc;
+  B200_CHECK_ARG(M >= 0 && lda >= K && ldc >= N, "w4a16_gemm: bad M/lda/ldc");
+  B200_CHECK_ARG(N / 128 <= B200_W4A16_COUNTER_BYTES / 4, "w4a16_gemm: N too large");
+  if (M == 0) return B200_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int geff = w4_geff(group_size);
+
+  const char* impl = getenv("B200_W4A16_IMPL");
+  if (impl && impl[0] == 's') {  // bring-up path, never the default
+    dim3 grid((unsigned)(N / 128), (unsigned)((M + 7) / 8));
+    w4_gemm_simt_kernel<<<grid, 128, 0, st>>>(
+        static_cast<__nv_bfloat16*>(C), static_cast<const __nv_bfloat16*>(A),
+        static_cast<const uint8_t*>(packed), static_cast<const __nv_bfloat16*>(bias), (int)M,
+        (int)N, (int)K, lda, ldc, geff);
+    B200_LAUNCH_OK("w4a16_gemm_simt");
+    return B200_OK;
+  }
+
+  B200_CHECK_ARG(is_aligned(A, 16) && lda % 8 == 0 && is_aligned(packed, 16),
+                 "w4a16_gemm: A / packed must be 16-byte aligned, lda %% 8 == 0");
+  B200_CHECK_ARG(workspace && is_aligned(workspace, 16), "w4a16_gemm: workspace required");
+  // rows beyond 128 are processed in chunks of 128 (weights re-streamed; the
+  // decode path never takes more than one chunk)
+  for (int64_t m0 = 0; m0 < M; m0 += 128) {
+    const int64_t mc = (M - m0) < 128 ? (M - m0) : 128;
+    const int mt = pick_mt(mc);
+    W4Params p{};
+    p.packed = static_cast<const uint8_t*>(packed);
+    p.C = static_cast<__nv_bfloat16*>(C) + m0 * ldc;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.M = (int)mc;
+    p.N = (int)N;
+    p.K = (int)K;
+    p.KT = (int)(K / 128);
+    p.NT = (int)(N / 128);
+    p.geff = geff;
+    p.ngrp = 128 / geff;
+    p.blob_bytes = w4_blob_bytes(geff);
+    p.units = p.KT * p.NT;
+    p.ldc = ldc;
+    const int grid = w4_grid(p.units);
+    const int64_t need =
+        B200_W4A16_COUNTER_BYTES + 2ll * grid * mt * 128 * (int64_t)sizeof(float);
+    if (workspace_bytes < need)
+      return set_error(B200_ERR_WORKSPACE, "w4a16_gemm: workspace %lld B < required %lld B",
+                       (long long)workspace_bytes, (long long)need);
+    p.counters = static_cast<int*>(workspace);
+    p.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                            B200_W4A16_COUNTER_BYTES);
+    CUtensorMap amap;
+    AMapKey key{static_cast<const __nv_bfloat16*>(A) + m0 * lda, mc, K, lda, mt};
+    rc = get_act_tensor_map(key, &amap);
+    if (rc != B200_OK) return rc;
+    switch (mt) {
+      case 16: rc = launch_w4_gemm<16>(amap, p, grid, st); break;
+      case 32: rc = launch_w4_gemm<32>(amap, p, grid, st); break;
+      case 64: rc = launch_w4_gemm<64>(amap, p, grid, st); break;
+      default: rc = launch_w4_gemm<128>(amap, p, grid, st); break;
+    }
+    if (rc != B200_OK) return rc;
+  }
+  return B200_OK;
+}
+
+}  // extern "C"

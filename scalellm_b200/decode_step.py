@@ -1,0 +1,324 @@
+"""The decode step: the reference's Llama operator sequence driven through the B200 plugins.
+
+This is the caller-side glue the benchmark and the parity tests need, not a model zoo:
+  * `LlamaDecoder`  — models/meta/llama.h:61-64,123-133,170-177,220-232,281-289 restated over
+    scalellm_b200.layers (RMSNorm -> qkv -> rope+kv-write -> paged attention -> o_proj
+    -> [all-reduce] -> RMSNorm -> gate_up -> silu*up -> down -> [all-reduce]).  The two residual
+    adds per layer are folded into the following RMSNorm (kernel::rms_norm_residual semantics,
+    bit-identical to the separate torch adds of llama.h:174-176).
+  * `build_decode_batch` — the tensor contract of Batch::prepare_model_input
+    (src/engine/batch.cpp:77-270) for a synthetic decode batch: flat tokens, positions,
+    q/kv cu_seq_lens, new_cache_slots, block_tables holding FIRST-SLOT ids (:206-209),
+    cu_block_lens; block ids are a random permutation of the pool (attention_test.cpp:63-68).
+  * `GraphedStep` — CUDA-graph capture / replay of one step with static input buffers
+    (src/engine/model_runner.cpp:141-210).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import kernels
+from .layers import (Attention, B200AttnHandler, ColumnParallelLinear, ColumnParallelQLinear,
+                     InputParameters, KVCache, QuantArgs, RMSNorm, RowParallelLinear,
+                     RowParallelQLinear, apply_llama3_rope_scaling, compute_default_inv_freq)
+from .model_parallel import (ParallelArgs, gather_from_model_parallel_region, local_heads)
+
+
+@dataclass
+class LlamaArgs:
+    """The ModelArgs fields the path reads (models/meta/llama.h:341-406)."""
+    hidden_size: int = 4096
+    n_layers: int = 32
+    n_heads: int = 32
+    n_kv_heads: int = 8
+    head_dim: int = 128
+    intermediate_size: int = 14336
+    vocab_size: int = 128256
+    rope_theta: float = 500000.0
+    rms_norm_eps: float = 1e-5
+    max_position_embeddings: int = 8192
+    rope_scaling: Optional[Dict[str, float]] = field(
+        default_factory=lambda: dict(factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                                     original_max_position_embeddings=8192))
+
+    @staticmethod
+    def llama3_8b() -> "LlamaArgs":
+        return LlamaArgs()
+
+    @staticmethod
+    def llama3_70b() -> "LlamaArgs":
+        return LlamaArgs(hidden_size=8192, n_layers=80, n_heads=64, n_kv_heads=8,
+                         intermediate_size=28672)
+
+
+def _inv_freq(args: LlamaArgs) -> torch.Tensor:
+    f = compute_default_inv_freq(args.head_dim, args.rope_theta)
+    if args.rope_scaling:
+        rs = args.rope_scaling
+        f = apply_llama3_rope_scaling(f, rs["factor"], rs["low_freq_factor"],
+                                      rs["high_freq_factor"],
+                                      int(rs["original_max_position_embeddings"]))
+    return f
+
+
+class LlamaDecoder:
+    def __init__(self, args: LlamaArgs, qa: QuantArgs, pa: ParallelArgs, device,
+                 dtype: torch.dtype = torch.bfloat16):
+        self.args, self.qa, self.pa, self.device, self.dtype = args, qa, pa, device, dtype
+        w = pa.world_size
+        self.H, self.Hkv = local_heads(args.n_heads, args.n_kv_heads, w)
+        D, h, I = args.head_dim, args.hidden_size, args.intermediate_size
+        self.q_size, self.kv_size = self.H * D, self.Hkv * D
+        self.I_local = I // w
+        quant = qa.quant_method in ("awq", "gptq")
+        self.handler = B200AttnHandler.create_handler_with_rope(
+            D, D, args.max_position_embeddings, _inv_freq(args), False, dtype, device)
+        self.layers: List[Dict] = []
+        local = ParallelArgs(0, 1, None)  # shards are materialised per rank already
+        for _ in range(args.n_layers):
+            if quant:
+                qkv = ColumnParallelQLinear(h, self.q_size + 2 * self.kv_size, False, False, qa,
+                                            local, device)
+                o = RowParallelQLinear(self.q_size * w, h, False, True, qa, pa, device)
+                gate_up = ColumnParallelQLinear(h, 2 * self.I_local, False, False, qa, local, device)
+                down = RowParallelQLinear(self.I_local * w, h, False, True, qa, pa, device)
+            else:
+                qkv = ColumnParallelLinear(h, self.q_size + 2 * self.kv_size, False, local, dtype,
+                                           device)
+                o = RowParallelLinear(self.q_size * w, h, True, pa, dtype, device)
+                gate_up = ColumnParallelLinear(h, 2 * self.I_local, False, local, dtype, device)
+                down = RowParallelLinear(self.I_local * w, h, True, pa, dtype, device)
+            self.layers.append(dict(
+                input_norm=RMSNorm(h, args.rms_norm_eps, dtype, device), qkv=qkv, o=o,
+                post_norm=RMSNorm(h, args.rms_norm_eps, dtype, device), gate_up=gate_up, down=down,
+                attn=Attention(self.H, self.Hkv, D, self.handler)))
+        self.final_norm = RMSNorm(h, args.rms_norm_eps, dtype, device)
+        assert h % w == 0 and args.vocab_size % w == 0
+        self.embed = torch.empty((args.vocab_size, h // w), dtype=dtype, device=device)
+        self.lm_head = ColumnParallelLinear(h, args.vocab_size, True, pa, dtype, device)
+        self.kv_caches: List[KVCache] = []
+
+    # -- weights -----------------------------------------------------------------
+    def load_layer(self, i: int, sd: Dict[str, Dict[str, torch.Tensor]]) -> None:
+        """sd: {"qkv"|"o"|"gate_up"|"down": checkpoint tensors of THIS RANK's shard,
+        "input_norm"/"post_norm": weight}.  Row-parallel entries are given unsharded-by-K
+        local shards too (the modules were built with world=1 sharding for local tensors)."""
+        L = self.layers[i]
+        for name in ("qkv", "o", "gate_up", "down"):
+            m = L[name]
+            if isinstance(m, (ColumnParallelQLinear, RowParallelQLinear)):
+                m._set_shard(sd[name]["qweight"], sd[name].get("qzeros"), sd[name]["scales"])
+            else:
+                m.weight.copy_(sd[name]["weight"])
+        L["input_norm"].weight.copy_(sd["input_norm"])
+        L["post_norm"].weight.copy_(sd["post_norm"])
+
+    def init_random(self, seed: int = 0) -> None:
+        """Random-init weights of the architecture on the device:
+        dense N(0, 0.02); int4: q,z ~ U{0..15} (uniform random words), s = |randn| * 0.01."""
+        g = torch.Generator(device=self.device).manual_seed(seed * 1000 + self.pa.rank)
+        quant = self.qa.quant_method in ("awq", "gptq")
+        gsz = self.qa.group_size
+
+        def rand_q(K: int, N: int) -> Dict[str, torch.Tensor]:
+            ng = 1 if gsz <= 0 else K // gsz
+            ri = lambda *s: torch.randint(-2 ** 31, 2 ** 31 - 1, s, generator=g, device=self.device,
+                                          dtype=torch.int64).to(torch.int32)
+            sc = (torch.randn((ng, N), generator=g, device=self.device).abs() * 0.01 + 1e-4).to(
+                torch.bfloat16)
+            if self.qa.quant_method == "awq":
+                return dict(qweight=ri(K, N // 8), qzeros=ri(ng, N // 8), scales=sc)
+            return dict(qweight=ri(K // 8, N), qzeros=None, scales=sc)
+
+        def rand_w(N: int, K: int) -> Dict[str, torch.Tensor]:
+            return dict(weight=(torch.randn((N, K), generator=g, device=self.device) * 0.02).to(
+                self.dtype))
+
+        h = self.args.hidden_size
+        for i, L in enumerate(self.layers):
+            shapes = dict(qkv=(h, self.q_size + 2 * self.kv_size), o=(self.q_size, h),
+                          gate_up=(h, 2 * self.I_local), down=(self.I_local, h))
+            sd = {}
+            for name, (K, N) in shapes.items():
+                sd[name] = rand_q(K, N) if quant else rand_w(N, K)
+            sd["input_norm"] = torch.ones(h, dtype=self.dtype, device=self.device)
+            sd["post_norm"] = torch.ones(h, dtype=self.dtype, device=self.device)
+            self.load_layer(i, sd)
+            if quant:  # pack now and free the checkpoint-format tensors
+                for name in ("qkv", "o", "gate_up", "down"):
+                    L[name]._ensure_packed()
+        self.embed.copy_((torch.randn(self.embed.shape, generator=g, device=self.device) * 0.02).to(
+            self.dtype))
+        self.lm_head.weight.copy_((torch.randn(self.lm_head.weight.shape, generator=g,
+                                               device=self.device) * 0.02).to(self.dtype))
+
+    def alloc_kv(self, n_blocks: int, block_size: int, randomize: bool = True, seed: int = 1) -> None:
+        self.kv_caches = []
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        for _ in range(self.args.n_layers):
+            c = KVCache(n_blocks, block_size, self.Hkv, self.args.head_dim, self.dtype, self.device)
+            if randomize:
+                c.key_cache.normal_(generator=g)
+                c.value_cache.normal_(generator=g)
+            else:
+                c.key_cache.zero_()
+                c.value_cache.zero_()
+            self.kv_caches.append(c)
+
+    # -- forward -------------------------------------------------------------------
+    def forward(self, tokens: torch.Tensor, positions: torch.Tensor,
+                params: InputParameters) -> torch.Tensor:
+        """Returns logits [n_tokens, vocab] (llama.h:220-232 then :281-289)."""
+        h = self.embed.index_select(0, tokens)
+        if self.pa.world_size > 1:  # ParallelEmbedding: split on hidden + all-gather (embedding.h:74-79)
+            h = gather_from_model_parallel_region(h, self.pa)
+        I = self.I_local
+        pending = None  # output of the previous block, not yet added to the residual stream
+        for L, cache in zip(self.layers, self.kv_caches):
+            n1 = L["input_norm"](h) if pending is None else L["input_norm"].forward_residual(pending, h)
+            qkv = L["qkv"](n1)
+            q = qkv[:, : self.q_size]
+            k = qkv[:, self.q_size: self.q_size + self.kv_size]
+            v = qkv[:, self.q_size + self.kv_size:]
+            attn = L["attn"](q, k, v, positions, cache, params)
+            o = L["o"](attn)
+            n2 = L["post_norm"].forward_residual(o, h)       # h = h + o ; n2 = norm(h)
+            gu = L["gate_up"](n2)
+            act = kernels.silu_mul(gu[:, :I], gu[:, I:])
+            pending = L["down"](act)
+        hn = self.final_norm.forward_residual(pending, h) if pending is not None else self.final_norm(h)
+        return self.lm_head(hn)
+
+    __call__ = forward
+
+
+# ---------------------------------------------------------------------------
+# synthetic decode batch (host side; numpy)
+# ---------------------------------------------------------------------------
+@dataclass
+class HostBatch:
+    tokens: np.ndarray          # int32 [T]
+    positions: np.ndarray       # int32 [T]
+    q_cu_lens: np.ndarray       # int32 [B+1]
+    kv_cu_lens: np.ndarray      # int32 [B+1]
+    new_cache_slots: np.ndarray  # int32 [T]
+    block_tables: np.ndarray    # int32 [sum blocks]  (first-slot ids)
+    cu_block_lens: np.ndarray   # int32 [B+1]
+    q_max: int
+    kv_max: int
+
+
+class BlockPool:
+    """Minimal stand-in for the reference's BlockAllocator output: block ids are handed out from
+    a random permutation (src/memory/block_allocator.cpp semantics are out of scope; only the ids
+    it would produce matter to the kernels)."""
+
+    def __init__(self, n_blocks: int, block_size: int, seed: int = 2):
+        self.block_size = block_size
+        self.free = list(np.random.default_rng(seed).permutation(n_blocks).astype(np.int64))
+        self.seq_blocks: List[List[int]] = []
+
+    def add_sequence(self, n_tokens_capacity: int) -> int:
+        nb = (n_tokens_capacity + self.block_size - 1) // self.block_size
+        if nb > len(self.free):
+            raise RuntimeError("block pool exhausted")
+        self.seq_blocks.append([self.free.pop() for _ in range(nb)])
+        return len(self.seq_blocks) - 1
+
+
+def build_decode_batch(pool: BlockPool, kv_lens: List[int], q_lens: List[int], vocab: int,
+                       seed: int = 5) -> HostBatch:
+    """kv_lens INCLUDE the new tokens (kv_cu_seq_lens semantics, parameters.h:35-37)."""
+    bs = pool.block_size
+    rng = np.random.default_rng(seed)
+    B = len(kv_lens)
+    tokens, positions, slots, tables = [], [], [], []
+    q_cu, kv_cu, blk_cu = [0], [0], [0]
+    for b in range(B):
+        kv, ql = kv_lens[b], q_lens[b]
+        blocks = pool.seq_blocks[b]
+        nb = (kv + bs - 1) // bs
+        assert nb <= len(blocks), "sequence outgrew its blocks"
+        for p in range(kv - ql, kv):
+            positions.append(p)
+            slots.append(blocks[p // bs] * bs + p % bs)
+        tokens.extend(rng.integers(0, vocab, size=ql).tolist())
+        tables.extend([blk * bs for blk in blocks[:nb]])   # first-slot ids (batch.cpp:206-209)
+        q_cu.append(q_cu[-1] + ql)
+        kv_cu.append(kv_cu[-1] + kv)
+        blk_cu.append(blk_cu[-1] + nb)
+    i32 = lambda x: np.asarray(x, dtype=np.int32)
+    return HostBatch(i32(tokens), i32(positions), i32(q_cu), i32(kv_cu), i32(slots), i32(tables),
+                     i32(blk_cu), max(q_lens), max(kv_lens))
+
+
+class StepBuffers:
+    """Pinned host + device buffers for one step's inputs (worker.cpp:132-135 H2D copies)."""
+
+    def __init__(self, device, max_tokens: int, max_seqs: int, max_blocks: int):
+        def pair(n):
+            return (torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available()),
+                    torch.zeros(n, dtype=torch.int32, device=device))
+        self.device = device
+        self.tokens = pair(max_tokens)
+        self.positions = pair(max_tokens)
+        self.slots = pair(max_tokens)
+        self.q_cu = pair(max_seqs + 1)
+        self.kv_cu = pair(max_seqs + 1)
+        self.blk_cu = pair(max_seqs + 1)
+        self.tables = pair(max_blocks)
+
+    def h2d_bytes(self, hb: HostBatch) -> int:
+        return 4 * (3 * len(hb.tokens) + 3 * len(hb.q_cu_lens) + len(hb.block_tables))
+
+    def upload(self, hb: HostBatch) -> Tuple[torch.Tensor, torch.Tensor, InputParameters]:
+        """Async H2D of one step's metadata from pinned memory on the current stream."""
+        def put(pairbuf, arr):
+            h, d = pairbuf
+            n = len(arr)
+            h[:n].copy_(torch.from_numpy(arr))
+            d[:n].copy_(h[:n], non_blocking=True)
+            return d[:n]
+        T, B = len(hb.tokens), len(hb.q_cu_lens) - 1
+        tokens = put(self.tokens, hb.tokens)
+        positions = put(self.positions, hb.positions)
+        params = InputParameters(
+            num_sequences=B, q_cu_seq_lens=put(self.q_cu, hb.q_cu_lens),
+            kv_cu_seq_lens=put(self.kv_cu, hb.kv_cu_lens), kv_max_seq_len=hb.kv_max,
+            q_max_seq_len=hb.q_max, new_cache_slots=put(self.slots, hb.new_cache_slots),
+            block_tables=put(self.tables, hb.block_tables),
+            cu_block_lens=put(self.blk_cu, hb.cu_block_lens))
+        return tokens, positions, params
+
+
+class GraphedStep:
+    """Capture one decode step (fixed batch size / max kv len) and replay it.  Inputs are
+    refreshed by copying into the static buffers (model_runner.cpp:180-210)."""
+
+    def __init__(self, model: LlamaDecoder, bufs: StepBuffers, hb: HostBatch, greedy: bool = True):
+        self.model, self.bufs = model, bufs
+        self.tokens, self.positions, self.params = bufs.upload(hb)
+        self.greedy = greedy
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):      # warm-up outside capture: workspaces, tensor maps, cuBLAS
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def _run(self) -> torch.Tensor:
+        logits = self.model(self.tokens, self.positions, self.params)
+        return torch.argmax(logits, dim=-1) if self.greedy else logits
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out

@@ -1,0 +1,306 @@
+"""Operator-level face of the B200 decode path: the reference's `src/kernels` free
+functions, same names / argument order / in-place conventions, on torch CUDA tensors.
+
+    llm::kernel::rms_norm, rms_norm_residual     src/kernels/layernorm_kernels.h:6-19
+    llm::kernel::apply_rotary_pos_emb            src/kernels/pos_embedding_kernels.h:7-13
+    llm::kernel::set_kv_cache                    src/kernels/kv_cache_kernels.h:6-11
+    llm::kernel::silu, silu_with_mul             src/kernels/activation_kernels.h:6-14
+    llm::paged_kv_varlen_mha                     src/kernels/attention/attn_api.h:12-27
+    marlin::awq_repack / gptq_repack / gptq_gemm src/kernels/quantization/marlin.h:17-37
+        -> w4a16_prepack_awq / w4a16_prepack_gptq / w4a16_gemm (our own packed layout)
+
+Every call goes through the C ABI of libb200decode.so on the current CUDA stream.
+CPU tensors are rejected — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import B200Error, check  # noqa: F401
+
+_DT = {torch.bfloat16: _lib.B200_BF16, torch.float16: _lib.B200_FP16, torch.float32: _lib.B200_FP32}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}") from None
+
+
+def _cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("scalellm_b200 kernels require CUDA tensors (no CPU fallback)")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_i32(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t.dtype != torch.int32:
+            raise TypeError("index / length tensors must be int32 (reference: torch::kInt)")
+        if not t.is_contiguous():
+            raise ValueError("index / length tensors must be contiguous")
+
+
+# ---------------------------------------------------------------------------
+# workspace cache (per device).  Allocate BEFORE CUDA-graph capture by calling the
+# op once eagerly, exactly like the reference warms its kernels before capture.
+# ---------------------------------------------------------------------------
+_WS: Dict[Tuple[str, int], torch.Tensor] = {}
+
+
+def _workspace(kind: str, device: torch.device, nbytes: int, zero: bool = False) -> torch.Tensor:
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = (torch.zeros if zero else torch.empty)(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------
+# norms
+# ---------------------------------------------------------------------------
+def rms_norm(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, epsilon: float) -> None:
+    _cuda(out, input, weight)
+    assert input.is_contiguous() and out.is_contiguous(), "tensors must be contiguous"
+    n = input.shape[-1]
+    rows = input.numel() // n
+    check(_lib.load().b200_rms_norm(_p(out), _p(input), _p(weight), rows, n, epsilon, _dt(input),
+                                    _stream()))
+
+
+def rms_norm_residual(out: torch.Tensor, residual: torch.Tensor, input: torch.Tensor,
+                      weight: torch.Tensor, epsilon: float) -> None:
+    _cuda(out, residual, input, weight)
+    assert input.is_contiguous() and out.is_contiguous() and residual.is_contiguous()
+    n = input.shape[-1]
+    rows = input.numel() // n
+    check(_lib.load().b200_rms_norm_residual(_p(out), _p(residual), _p(input), _p(weight), rows, n,
+                                             epsilon, _dt(input), _stream()))
+
+
+# ---------------------------------------------------------------------------
+# rotary embedding / kv cache
+# ---------------------------------------------------------------------------
+def apply_rotary_pos_emb(querys: torch.Tensor, keys: torch.Tensor, positions: torch.Tensor,
+                         cos_sin: torch.Tensor, rotary_dim: int, interleaved: bool) -> None:
+    """In place on querys [T,H,D] and keys [T,Hkv,D] (heads dense, token stride free)."""
+    _cuda(querys, keys, positions, cos_sin)
+    _check_i32(positions)
+    assert querys.stride(-1) == 1 and querys.stride(-2) == querys.size(-1)
+    assert keys.stride(-1) == 1 and keys.stride(-2) == keys.size(-1)
+    assert cos_sin.is_contiguous() and cos_sin.dtype == querys.dtype
+    T, H, D = querys.shape[-3], querys.shape[-2], querys.shape[-1]
+    check(_lib.load().b200_rope_inplace(_p(querys), _p(keys), _p(positions), _p(cos_sin), T, H,
+                                        keys.shape[-2], D, rotary_dim, querys.stride(-3),
+                                        keys.stride(-3), int(interleaved), _dt(querys), _stream()))
+
+
+def set_kv_cache(slot_ids: torch.Tensor, keys: torch.Tensor, values: torch.Tensor,
+                 key_cache: torch.Tensor, value_cache: torch.Tensor) -> None:
+    _cuda(slot_ids, keys, values, key_cache, value_cache)
+    _check_i32(slot_ids)
+    assert keys.stride(-1) == 1 and keys.stride(-2) == keys.size(-1)
+    assert values.stride(-1) == 1 and values.stride(-2) == values.size(-1)
+    assert key_cache.is_contiguous() and value_cache.is_contiguous()
+    T, Hkv, D = keys.shape[-3], keys.shape[-2], keys.shape[-1]
+    check(_lib.load().b200_kv_write(_p(slot_ids), _p(keys), _p(values), _p(key_cache),
+                                    _p(value_cache), T, Hkv, D, keys.stride(-3), values.stride(-3),
+                                    _dt(keys), _stream()))
+
+
+def get_kv_cache(slot_ids: torch.Tensor, key_cache: torch.Tensor,
+                 value_cache: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """KVCache::get_kv_cache (src/memory/kv_cache.cpp:60-98) as a device gather."""
+    _cuda(slot_ids, key_cache, value_cache)
+    _check_i32(slot_ids)
+    T = slot_ids.numel()
+    Hkv, D = key_cache.shape[-2], key_cache.shape[-1]
+    k = torch.empty((T, Hkv, D), dtype=key_cache.dtype, device=key_cache.device)
+    v = torch.empty_like(k)
+    check(_lib.load().b200_kv_gather(_p(slot_ids), _p(key_cache), _p(value_cache), _p(k), _p(v), T,
+                                     Hkv, D, _dt(key_cache), _stream()))
+    return k, v
+
+
+def rope_and_set_kv_cache(querys: torch.Tensor, keys: torch.Tensor, values: torch.Tensor,
+                          positions: torch.Tensor, cos_sin: torch.Tensor, slot_ids: torch.Tensor,
+                          key_cache: torch.Tensor, value_cache: torch.Tensor, rotary_dim: int,
+                          interleaved: bool) -> None:
+    """Fused apply_rotary_pos_emb + set_kv_cache (bit-identical to the two calls)."""
+    _cuda(querys, keys, values, positions, cos_sin, slot_ids, key_cache, value_cache)
+    _check_i32(positions, slot_ids)
+    assert querys.stride(-1) == 1 and querys.stride(-2) == querys.size(-1)
+    assert keys.stride(-1) == 1 and keys.stride(-2) == keys.size(-1)
+    assert values.stride(-1) == 1 and values.stride(-2) == values.size(-1)
+    assert key_cache.is_contiguous() and value_cache.is_contiguous()
+    T, H, D = querys.shape[-3], querys.shape[-2], querys.shape[-1]
+    check(_lib.load().b200_rope_kv_write(_p(querys), _p(keys), _p(values), _p(positions),
+                                         _p(cos_sin), _p(slot_ids), _p(key_cache), _p(value_cache),
+                                         T, H, keys.shape[-2], D, rotary_dim, querys.stride(-3),
+                                         keys.stride(-3), values.stride(-3), int(interleaved),
+                                         _dt(querys), _stream()))
+
+
+# ---------------------------------------------------------------------------
+# activations
+# ---------------------------------------------------------------------------
+def silu(input: torch.Tensor) -> torch.Tensor:
+    _cuda(input)
+    assert input.dim() == 2 and input.stride(1) == 1
+    out = torch.empty((input.shape[0], input.shape[1]), dtype=input.dtype, device=input.device)
+    check(_lib.load().b200_silu(_p(out), _p(input), input.shape[0], input.shape[1],
+                                input.stride(0), _dt(input), _stream()))
+    return out
+
+
+def silu_with_mul(input: torch.Tensor) -> torch.Tensor:
+    _cuda(input)
+    assert input.dim() == 2 and input.is_contiguous()
+    n = input.shape[1] // 2
+    out = torch.empty((input.shape[0], n), dtype=input.dtype, device=input.device)
+    check(_lib.load().b200_silu_mul(_p(out), _p(input), input.shape[0], n, _dt(input), _stream()))
+    return out
+
+
+def silu_mul(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act_func(gate) * up on strided views of the fused gate_up output (llama.h:61-64)."""
+    _cuda(gate, up)
+    assert gate.dim() == 2 and gate.shape == up.shape and gate.stride(1) == 1 and up.stride(1) == 1
+    if out is None:
+        out = torch.empty(gate.shape, dtype=gate.dtype, device=gate.device)
+    check(_lib.load().b200_silu_mul_strided(_p(out), _p(gate), _p(up), gate.shape[0], gate.shape[1],
+                                            gate.stride(0), up.stride(0), _dt(gate), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# paged attention
+# ---------------------------------------------------------------------------
+def paged_attn_workspace_bytes(batch: int, max_q_len: int, max_kv_len: int, n_heads: int,
+                               n_kv_heads: int, head_dim: int) -> int:
+    return int(_lib.load().b200_paged_attn_workspace_bytes(batch, max_q_len, max_kv_len, n_heads,
+                                                           n_kv_heads, head_dim))
+
+
+def paged_kv_varlen_mha(out: torch.Tensor, query: torch.Tensor, key_cache: torch.Tensor,
+                        value_cache: torch.Tensor, q_cu_lens: torch.Tensor,
+                        kv_cu_lens: torch.Tensor, block_table: torch.Tensor,
+                        block_cu_lens: torch.Tensor, alibi_slopes: Optional[torch.Tensor],
+                        block_size: int, max_q_len: int, max_kv_len: int, sm_scale: float,
+                        logits_soft_cap: float, sliding_window: int,
+                        workspace: Optional[torch.Tensor] = None) -> None:
+    _cuda(out, query, key_cache, value_cache, q_cu_lens, kv_cu_lens, block_table, block_cu_lens,
+          alibi_slopes)
+    _check_i32(q_cu_lens, kv_cu_lens, block_table, block_cu_lens)
+    assert query.stride(-1) == 1 and out.stride(-1) == 1
+    assert key_cache.stride(-1) == 1 and value_cache.stride(-1) == 1
+    assert key_cache.stride() == value_cache.stride() and key_cache.shape == value_cache.shape
+    if alibi_slopes is not None:
+        assert alibi_slopes.dtype == torch.float32 and alibi_slopes.is_contiguous()
+    batch = q_cu_lens.numel() - 1
+    H, D = query.shape[-2], query.shape[-1]
+    Hkv = key_cache.shape[-2]
+    need = paged_attn_workspace_bytes(batch, max_q_len, max_kv_len, H, Hkv, D)
+    if workspace is None and need > 0:
+        workspace = _workspace("attn", query.device, need)
+    check(_lib.load().b200_paged_attn_decode(
+        _p(out), _p(query), _p(key_cache), _p(value_cache), _p(q_cu_lens), _p(kv_cu_lens),
+        _p(block_table), _p(block_cu_lens), _p(alibi_slopes), batch, H, Hkv, D,
+        key_cache.shape[0], query.stride(0), query.stride(1), out.stride(0), out.stride(1),
+        key_cache.stride(0), key_cache.stride(1), block_size, max_q_len, max_kv_len, sm_scale,
+        logits_soft_cap, sliding_window, _p(workspace),
+        0 if workspace is None else workspace.numel() * workspace.element_size(), _dt(query),
+        _stream()))
+
+
+# ---------------------------------------------------------------------------
+# W4A16
+# ---------------------------------------------------------------------------
+def w4a16_packed_bytes(K: int, N: int, group_size: int) -> int:
+    n = int(_lib.load().b200_w4a16_packed_bytes(K, N, group_size))
+    if n < 0:
+        raise ValueError(f"W4A16 needs K % 128 == 0 and N % 128 == 0, got K={K} N={N}")
+    return n
+
+
+def w4a16_prepack_awq(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
+                      group_size: int) -> torch.Tensor:
+    """AWQ checkpoint tensors -> opaque packed weight (replaces marlin::awq_repack + the
+    zero-point / scale permutations of qlinear_awq_marlin_impl.cpp:62-125)."""
+    _cuda(qweight, qzeros, scales)
+    assert qweight.dtype == torch.int32 and qzeros.dtype == torch.int32
+    assert scales.dtype == torch.bfloat16, "W4A16 path computes in bf16"
+    assert qweight.is_contiguous() and qzeros.is_contiguous() and scales.is_contiguous()
+    K, N = qweight.shape[0], qweight.shape[1] * 8
+    packed = torch.empty(w4a16_packed_bytes(K, N, group_size), dtype=torch.uint8,
+                         device=qweight.device)
+    check(_lib.load().b200_w4a16_prepack_awq(_p(packed), _p(qweight), _p(qzeros), _p(scales), K, N,
+                                             group_size, _stream()))
+    return packed
+
+
+def w4a16_prepack_gptq(qweight: torch.Tensor, qzeros: Optional[torch.Tensor], scales: torch.Tensor,
+                       group_size: int, zeros_plus_one: bool = True) -> torch.Tensor:
+    """GPTQ checkpoint tensors -> packed weight.  qzeros=None means the symmetric zero point 8
+    used by the reference's Marlin path (qlinear_gptq_marlin_impl.cpp:18-20)."""
+    _cuda(qweight, qzeros, scales)
+    assert qweight.dtype == torch.int32 and scales.dtype == torch.bfloat16
+    assert qweight.is_contiguous() and scales.is_contiguous()
+    K, N = qweight.shape[0] * 8, qweight.shape[1]
+    packed = torch.empty(w4a16_packed_bytes(K, N, group_size), dtype=torch.uint8,
+                         device=qweight.device)
+    check(_lib.load().b200_w4a16_prepack_gptq(_p(packed), _p(qweight), _p(qzeros), _p(scales), K,
+                                              N, group_size, int(zeros_plus_one), _stream()))
+    return packed
+
+
+def w4a16_dequant(packed: torch.Tensor, K: int, N: int, group_size: int) -> torch.Tensor:
+    _cuda(packed)
+    w = torch.empty((K, N), dtype=torch.bfloat16, device=packed.device)
+    check(_lib.load().b200_w4a16_dequant(_p(w), _p(packed), K, N, group_size, _stream()))
+    return w
+
+
+def w4a16_workspace(device: torch.device, M: int, N: int, K: int) -> torch.Tensor:
+    need = int(_lib.load().b200_w4a16_workspace_bytes(M, N, K))
+    return _workspace("w4a16", device, need, zero=True)
+
+
+def w4a16_gemm(a: torch.Tensor, packed: torch.Tensor, N: int, group_size: int,
+               bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M,N] = A[M,K] @ dequant(packed).  A bf16 with unit inner stride."""
+    _cuda(a, packed, bias, out)
+    assert a.dim() == 2 and a.dtype == torch.bfloat16 and a.stride(1) == 1
+    M, K = a.shape
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    assert out.dtype == torch.bfloat16 and out.stride(1) == 1 and out.shape == (M, N)
+    if workspace is None:
+        workspace = w4a16_workspace(a.device, M, N, K)
+    check(_lib.load().b200_w4a16_gemm(_p(out), _p(a), _p(packed), _p(bias), M, N, K, a.stride(0),
+                                      out.stride(0), group_size, _p(workspace),
+                                      workspace.numel(), _stream()))
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().b200_launch_count())
+
+
+def launch_count_reset() -> None:
+    _lib.load().b200_launch_count_reset()

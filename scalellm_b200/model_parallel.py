@@ -1,0 +1,152 @@
+"""Tensor-parallel plumbing: mirror of src/model_parallel/{process_group,model_parallel,parallel_args}.
+
+One process per GPU (torchrun) instead of the reference's one thread per GPU
+(src/engine/worker.h:90).  `torch.distributed` is only the plumbing (rendezvous,
+IPC-handle exchange, all-gather); the latency-critical row-parallel all-reduce
+(src/model_parallel/process_group.cpp:135-153, 2 per layer) runs through the
+NVLink peer-memory kernel of libb200decode (csrc/allreduce.cu) when the tensor is
+on CUDA and fits the symmetric buffer, else through NCCL.
+
+The sharding helpers are pure index arithmetic and are unit-tested on CPU with
+gloo (tests/test_tp_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check
+
+
+class ProcessGroup:
+    """ProcessGroup interface (src/model_parallel/process_group.h:10-60) over torch.distributed."""
+
+    def __init__(self, rank: int, world_size: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None, nvlink_max_bytes: int = 1 << 20):
+        self._rank, self._world, self._device, self._group = rank, world_size, device, group
+        self._comm = None
+        self._nvlink_max_bytes = nvlink_max_bytes
+        if device.type == "cuda" and world_size > 1:
+            self._init_nvlink()
+
+    # -- reference accessors -------------------------------------------------
+    def rank(self) -> int:
+        return self._rank
+
+    def world_size(self) -> int:
+        return self._world
+
+    def device(self) -> torch.device:
+        return self._device
+
+    # -- NVLink communicator -------------------------------------------------
+    def _init_nvlink(self) -> None:
+        lib = _lib.load()
+        comm = C.c_void_p()
+        handle = (C.c_uint8 * _lib.AR_HANDLE_BYTES)()
+        with torch.cuda.device(self._device):
+            check(lib.b200_ar_create(C.byref(comm), self._rank, self._world,
+                                     self._nvlink_max_bytes, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        if dist.get_backend(self._group) == "nccl":
+            mine = mine.to(self._device)
+        gathered = [torch.empty_like(mine) for _ in range(self._world)]
+        dist.all_gather(gathered, mine, group=self._group)
+        blob = bytes(torch.cat([g.cpu() for g in gathered]).tolist())
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self._device):
+            check(lib.b200_ar_open_peers(comm, buf))
+        dist.barrier(group=self._group)
+        self._comm = comm
+
+    # -- collectives -----------------------------------------------------------
+    def allreduce(self, input: torch.Tensor) -> None:
+        """In-place sum (process_group.cpp:135-153)."""
+        if self._world == 1:
+            return
+        nbytes = input.numel() * input.element_size()
+        if (self._comm is not None and input.is_cuda and input.is_contiguous()
+                and nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
+                and input.data_ptr() % 16 == 0
+                and input.dtype in (torch.bfloat16, torch.float16, torch.float32)):
+            dt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[input.dtype]
+            check(_lib.load().b200_ar_allreduce(self._comm, input.data_ptr(), input.numel(), dt,
+                                                torch.cuda.current_stream().cuda_stream))
+            return
+        dist.all_reduce(input, op=dist.ReduceOp.SUM, group=self._group)
+
+    def allgather(self, input: torch.Tensor, outputs: List[torch.Tensor]) -> None:
+        if self._world == 1:
+            outputs[0].copy_(input)
+            return
+        dist.all_gather(outputs, input.contiguous(), group=self._group)
+
+    def close(self) -> None:
+        if self._comm is not None:
+            _lib.load().b200_ar_destroy(self._comm)
+            self._comm = None
+
+
+@dataclass
+class ParallelArgs:
+    """src/model_parallel/parallel_args.h:10-22"""
+    rank: int = 0
+    world_size: int = 1
+    process_group: Optional[ProcessGroup] = None
+
+
+def gather_from_model_parallel_region(input: torch.Tensor, pa: ParallelArgs) -> torch.Tensor:
+    """model_parallel.cpp:13-31: all-gather then cat on the last dim."""
+    if pa.world_size == 1:
+        return input
+    outs = [torch.empty_like(input) for _ in range(pa.world_size)]
+    pa.process_group.allgather(input, outs)
+    return torch.cat(outs, dim=-1).contiguous()
+
+
+def reduce_from_model_parallel_region(input: torch.Tensor, pa: ParallelArgs) -> torch.Tensor:
+    """model_parallel.cpp:33-44"""
+    if pa.world_size == 1:
+        return input
+    pa.process_group.allreduce(input)
+    return input
+
+
+def scatter_to_model_parallel_region(input: torch.Tensor, pa: ParallelArgs) -> torch.Tensor:
+    """model_parallel.cpp:46-65"""
+    if pa.world_size == 1:
+        return input
+    last = input.size(-1)
+    assert last % pa.world_size == 0, f"last dim {last} not divisible by world {pa.world_size}"
+    return input.split(last // pa.world_size, dim=-1)[pa.rank]
+
+
+# ---------------------------------------------------------------------------
+# shard index arithmetic (host logic; CPU-testable)
+# ---------------------------------------------------------------------------
+def shard_range(total: int, rank: int, world: int) -> slice:
+    assert total % world == 0, f"{total} not divisible by world size {world}"
+    per = total // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def local_heads(n_heads: int, n_kv_heads: int, world: int):
+    """models/meta/llama.h:83-90: local q heads, local kv heads (>= 1 with replication)."""
+    assert n_heads % world == 0
+    return n_heads // world, max(1, n_kv_heads // world)
+
+
+def kv_head_for_rank(n_kv_heads: int, rank: int, world: int) -> slice:
+    """kv-head rows owned by `rank`; with n_kv_heads < world the heads are replicated
+    world/n_kv_heads times (qkv_parallel_linear.cpp:28-70)."""
+    if n_kv_heads >= world:
+        return shard_range(n_kv_heads, rank, world)
+    assert world % n_kv_heads == 0
+    rep = world // n_kv_heads
+    h = rank // rep
+    return slice(h, h + 1)

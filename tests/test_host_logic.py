@@ -1,0 +1,52 @@
+"""CPU: host-side logic of the decode step — batch metadata (Batch::prepare_model_input
+contract), block pool, head / shard arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops
+from scalellm_b200.decode_step import BlockPool, build_decode_batch
+from scalellm_b200.model_parallel import kv_head_for_rank, local_heads, shard_range
+
+
+def test_decode_batch_metadata_contract():
+    bs = 8
+    pool = BlockPool(n_blocks=64, block_size=bs, seed=2)
+    kv_lens, q_lens = [17, 8, 33], [1, 1, 1]
+    for kv in kv_lens:
+        pool.add_sequence(kv + 4)
+    hb = build_decode_batch(pool, kv_lens, q_lens, vocab=1000)
+    assert hb.q_cu_lens.tolist() == [0, 1, 2, 3]
+    assert hb.kv_cu_lens.tolist() == [0, 17, 25, 58]
+    assert hb.cu_block_lens.tolist() == [0, 3, 4, 9]
+    assert hb.positions.tolist() == [16, 7, 32]
+    assert hb.q_max == 1 and hb.kv_max == 33
+    assert all(hb.block_tables % bs == 0)                       # first-slot ids
+    assert len(set(hb.block_tables.tolist())) == len(hb.block_tables)  # blocks never shared
+    # the new token's slot is where the reference's lookup finds position kv-1
+    bt = torch.from_numpy(hb.block_tables)
+    for b, kv in enumerate(kv_lens):
+        slots = ops.slot_ids_for_sequence(bt, torch.from_numpy(hb.cu_block_lens), b, kv, bs)
+        assert int(slots[-1]) == int(hb.new_cache_slots[b])
+        assert len(set(slots.tolist())) == kv
+
+
+def test_multi_token_queries_and_pool_exhaustion():
+    pool = BlockPool(n_blocks=4, block_size=16)
+    pool.add_sequence(40)
+    hb = build_decode_batch(pool, [37], [3], vocab=10)
+    assert hb.positions.tolist() == [34, 35, 36] and hb.q_max == 3
+    with pytest.raises(RuntimeError):
+        pool.add_sequence(40)
+
+
+def test_shard_arithmetic():
+    assert shard_range(4096, 3, 8) == slice(1536, 2048)
+    with pytest.raises(AssertionError):
+        shard_range(10, 0, 4)
+    assert local_heads(64, 8, 8) == (8, 1)
+    assert local_heads(32, 8, 2) == (16, 4)
+    assert local_heads(64, 8, 16) == (4, 1)          # kv heads replicated (qkv_parallel_linear.cpp:28-38)
+    assert kv_head_for_rank(8, 5, 8) == slice(5, 6)
+    assert kv_head_for_rank(8, 5, 16) == slice(2, 3)  # ranks 4,5 share kv head 2
+    assert kv_head_for_rank(8, 1, 2) == slice(4, 8)
