@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s of the B200 decode hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W             # this repo's arm
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port) on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1: tensor parallel)
+
+Workload (config.workload): Llama-3-8B shapes, AWQ int4 g=128 decoder linears + bf16 lm_head,
+random-init weights, batch 64 sequences each with kv_len 2048 in a paged KV cache (block_size 8,
+shuffled block ids), one decode token per sequence per step.  A "step" is one full decode step
+(32 layers + final norm + lm_head + greedy argmax) = 64 tokens.
+
+`value`   : device-timed (CUDA events) CUDA-graph replays, inputs resident in HBM.
+`e2e`     : the same step driven through the public API with per-step host metadata build,
+            pinned H2D copies of that metadata and a D2H read of the 64 sampled token ids;
+            kv_len grows by one each step.
+`roofline`: the dominant kernel (paged attention) timed alone with CUDA events, rotating over
+            the 32 per-layer caches (17 GB > L2), algorithmic bytes / time vs the measured HBM peak.
+`cpu_baseline` / `--impl reference`: oracle port of the same step on the host cores, bounded
+            sample (a few layers + lm_head, extrapolated to 32 layers).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--seqlen", type=int, default=2048)
+    ap.add_argument("--block-size", type=int, default=8)
+    ap.add_argument("--quant", default="awq", choices=["awq", "gptq", "none"])
+    ap.add_argument("--layers", type=int, default=32, help="debug only; the default is the named config")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, world):
+    q = {"awq": "AWQ-int4 g128", "gptq": "GPTQ-int4 g128", "none": "bf16"}[a.quant]
+    return (f"Llama-3-8B {q} decode step, batch {a.batch}, kv_len {a.seqlen}, block_size "
+            f"{a.block_size}, TP={world}")
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        return [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    @staticmethod
+    def summarise(rows):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: oracle port of the same decode step on the host cores
+# --------------------------------------------------------------------------------------
+class CpuDecodeSample:
+    """Oracle port of the decode step at the benchmark shapes (built once, timed many times)."""
+
+    def __init__(self, a, seed: int = 0):
+        import numpy as np
+        import torch
+        from oracle import llama as ollama, ops, quant
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch, self.ollama, self.ops, self.quant = torch, ollama, ops, quant
+        cfg = self.cfg = ollama.LlamaConfig()
+        B, S, bs = a.batch, a.seqlen, a.block_size
+        self.B = B
+        g = torch.Generator().manual_seed(seed)
+        h, D, H, Hkv, I = cfg.hidden, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, cfg.inter
+
+        def lin(K, N):  # dequantised int4 weight (the CPU path multiplies dense bf16 weights)
+            q = torch.randint(0, 16, (K, N), generator=g, dtype=torch.int32).numpy()
+            z = torch.randint(0, 16, (K // 128, N), generator=g, dtype=torch.int32).numpy()
+            s = (torch.randn(K // 128, N, generator=g).abs() * 0.01 + 1e-4).bfloat16()
+            return ollama.Linear(quant.dequant(q, z, s, 128))
+
+        self.layer = dict(qkv=lin(h, (H + 2 * Hkv) * D), o=lin(H * D, h), gate_up=lin(h, 2 * I),
+                          down=lin(I, h), input_norm=torch.ones(h).bfloat16(),
+                          post_norm=torch.ones(h).bfloat16())
+        nblk = (S + bs - 1) // bs
+        n_slots = B * nblk * bs
+        self.kc = torch.randn(n_slots, Hkv, D, generator=g).bfloat16()
+        self.vc = torch.randn(n_slots, Hkv, D, generator=g).bfloat16()
+        table = (torch.randperm(B * nblk, generator=g) * bs).to(torch.int32)
+        self.meta = dict(q_cu_lens=np.arange(B + 1), kv_cu_lens=np.arange(B + 1) * S,
+                         block_table=table, block_cu_lens=np.arange(B + 1) * nblk, block_size=bs)
+        last = torch.arange(B) * nblk + (S - 1) // bs
+        self.slots = (table[last] + (S - 1) % bs).to(torch.int32)
+        self.cos_sin = ops.build_cos_sin_cache(D, 4096, ollama.inv_freq_for(cfg), torch.bfloat16)
+        self.x = (torch.randn(B, h, generator=g) * 0.5).bfloat16()
+        self.pos = torch.full((B,), S - 1, dtype=torch.int32)
+        self.lm_head = (torch.randn(h, cfg.vocab, generator=g) * 0.02).bfloat16()
+        self.fn = torch.ones(h).bfloat16()
+
+    def step(self, n_layers_sample: int):
+        """Returns (tokens_per_s extrapolated to 32 layers, seconds spent)."""
+        t0 = time.perf_counter()
+        y = self.x
+        for _ in range(n_layers_sample):
+            y = self.ollama.decoder_layer(y, self.pos, self.layer, self.cfg, self.cos_sin, self.kc,
+                                          self.vc, self.slots, self.meta)
+        t_layers = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        logits = self.quant.w4a16_gemm(self.ops.rms_norm(y, self.fn, self.cfg.rms_eps), self.lm_head)
+        _ = logits.argmax(-1)
+        t_head = time.perf_counter() - t1
+        step_s = t_layers / n_layers_sample * 32 + t_head
+        return self.B / step_s, t_layers + t_head
+
+
+def cpu_decode_sample(a, n_layers_sample: int, seed: int = 0):
+    c = CpuDecodeSample(a, seed)
+    v, secs = c.step(n_layers_sample)
+    return v, secs, c.torch.get_num_threads()
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    c = CpuDecodeSample(a, 0)
+    cores = c.torch.get_num_threads()
+    vals, secs = [], 0.0
+    for i in range(a.warmup + a.steps):
+        v, s = c.step(1)
+        if i >= a.warmup:
+            vals.append(v)
+            secs += s
+    vals.sort()
+    v = vals[len(vals) // 2]
+    sample = ("per step: 1 of 32 oracle decoder layers + final norm + bf16 lm_head at the full "
+              "batch/kv_len, extrapolated x32 layers; median over steps")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * a.batch / v,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic", "config": {"workload": workload_name(a, 1).replace("TP=1", "CPU")},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def run_b200(a, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from scalellm_b200 import kernels
+    from scalellm_b200.decode_step import (BlockPool, GraphedStep, LlamaArgs, LlamaDecoder,
+                                           StepBuffers, build_decode_batch)
+    from scalellm_b200.layers import QuantArgs
+    from scalellm_b200.model_parallel import ParallelArgs, ProcessGroup
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = ProcessGroup(rank, world, dev)
+    pa = ParallelArgs(rank, world, pg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    args = LlamaArgs.llama3_8b()
+    args.n_layers = a.layers
+    qa = QuantArgs(quant_method="" if a.quant == "none" else a.quant, bits=4, group_size=128,
+                   is_sym=(a.quant == "gptq"))
+    model = LlamaDecoder(args, qa, pa, dev)
+    model.init_random(seed=0)
+
+    B, S, bs = a.batch, a.seqlen, a.block_size
+    total_steps = a.warmup + a.steps
+    cap = S + 2 * total_steps + 8              # room for the e2e loop to grow every sequence
+    blocks_per_seq = (cap + bs - 1) // bs
+    n_blocks = B * blocks_per_seq + 16
+    pool = BlockPool(n_blocks, bs, seed=2)
+    for _ in range(B):
+        pool.add_sequence(cap)
+    model.alloc_kv(n_blocks, bs, randomize=True, seed=1)
+    bufs = StepBuffers(dev, B, B, B * blocks_per_seq)
+    hb = build_decode_batch(pool, [S] * B, [1] * B, args.vocab_size)
+    hb.kv_max = cap                            # graph is captured for the longest kv it will see
+
+    # ---- launches per step (claimed gpu_launches) --------------------------------
+    tokens, positions, params = bufs.upload(hb)
+    kernels.launch_count_reset()
+    _ = model(tokens, positions, params)
+    torch.cuda.synchronize()
+    launches_per_step = kernels.launch_count()
+
+    use_graph = not a.no_graph
+    step = None
+    if use_graph:
+        try:
+            step = GraphedStep(model, bufs, hb, greedy=True)
+        except Exception as e:  # e.g. a collective that cannot be captured
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); eager", file=sys.stderr)
+            use_graph = False
+
+    def one_step():
+        if use_graph:
+            return step.replay()
+        return torch.argmax(model(tokens, positions, params), dim=-1)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- device-timed value: inputs resident, K replays --------------------------
+    for _ in range(max(a.warmup, 3)):
+        one_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.perf_counter()
+    ev0.record()
+    for _ in range(a.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    t_w1 = time.perf_counter()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / a.steps)
+    value = B / (ms_step / 1000.0)
+
+    # ---- end-to-end: host metadata + pinned H2D + step + D2H of the sampled tokens ----
+    out_host = torch.empty(B, dtype=torch.int64, pin_memory=True)
+    kv = S
+
+    def e2e_step(kv_now):
+        hbn = build_decode_batch(pool, [kv_now] * B, [1] * B, args.vocab_size, seed=kv_now)
+        hbn.kv_max = cap
+        nonlocal tokens, positions, params
+        tokens, positions, params = bufs.upload(hbn)
+        nxt = one_step()
+        out_host.copy_(nxt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hbn
+
+    for _ in range(max(a.warmup, 3)):
+        kv += 1
+        last = e2e_step(kv)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        kv += 1
+        last = e2e_step(kv)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
+    e2e_val = B / e2e_s
+    h2d = bufs.h2d_bytes(last)
+    d2h = B * 8
+
+    # ---- roofline of the dominant kernel (paged attention), timed alone -------------
+    roof = attention_roofline(model, params, hb, a, dev, world)
+    gemm = gemm_roofline(model, a, dev) if a.quant != "none" else None
+
+    clocks = None
+    if sampler:
+        time.sleep(0.15)
+        clocks = ClockSampler.summarise(sampler.window(t_w0, t_w1))
+        sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.skip_cpu_baseline:
+        v, secs, cores = cpu_decode_sample(a, n_layers_sample=2)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2 of 32 oracle decoder layers + lm_head at the full shapes ({secs:.1f} s of CPU "
+                         "work), extrapolated to 32 layers"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": workload_name(a, world), "global_batch": B, "seq_len": S,
+                          "parallelism": f"tp{world}", "layers": a.layers,
+                          "cuda_graph": use_graph,
+                          "l2_policy": "inputs larger than L2 (17.2 GB KV + 4.7 GB weights per step)",
+                          "ttft": "not measured: prefill kernels are SURVEY §8f rank 1 (next)"},
+               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches_per_step * a.steps, "clocks": clocks, "roofline": roof,
+               "roofline_w4a16_gemm": gemm, "cpu_baseline": cpu}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        if pg:
+            pg.close()
+        dist.destroy_process_group()
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(name):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(name)
+    except Exception:
+        return None
+
+
+def attention_roofline(model, params, hb, a, dev, world):
+    import torch
+    from scalellm_b200 import kernels
+    H, Hkv, D = model.H, model.Hkv, model.args.head_dim
+    B, S = a.batch, a.seqlen
+    q = torch.randn(B, H, D, device=dev).to(torch.bfloat16)
+    out = torch.empty_like(q)
+    caches = model.kv_caches
+    sm_scale = D ** -0.5
+
+    def launch(c):
+        kernels.paged_kv_varlen_mha(out, q, c.key_cache, c.value_cache, params.q_cu_seq_lens,
+                                    params.kv_cu_seq_lens, params.block_tables,
+                                    params.cu_block_lens, None, c.block_size(), 1, hb.kv_max,
+                                    sm_scale, 0.0, -1)
+
+    for c in caches[:4]:
+        launch(c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        for c in caches:           # rotating over all layers: every launch reads cold HBM
+            launch(c)
+    e1.record()
+    torch.cuda.synchronize()
+    n = reps * len(caches)
+    ms = e0.elapsed_time(e1) / n                     # includes the split-KV combine launch
+    kv_now = int(params.kv_cu_seq_lens[1].item())
+    alg_bytes = 2 * B * kv_now * Hkv * D * 2 + 2 * B * H * D * 2   # K+V read, q read + o write
+    peak, src = _peaks()
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"kernel": "paged_attn_decode_kernel(+combine)", "bound": "hbm", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("paged_attn"),
+            "peak_source": src, "us_per_launch": ms * 1e3, "algorithmic_bytes": alg_bytes,
+            "launches_timed": n}
+
+
+def gemm_roofline(model, a, dev):
+    import torch
+    from scalellm_b200 import kernels
+    peak, src = _peaks()
+    res = {}
+    x_by_k = {}
+    layers = model.layers
+    for name in ("qkv", "o", "gate_up", "down"):
+        mods = [L[name] for L in layers]
+        K, N = mods[0].K, mods[0].N
+        x = x_by_k.setdefault(K, torch.randn(a.batch, K, device=dev).to(torch.bfloat16))
+        outb = torch.empty(a.batch, N, dtype=torch.bfloat16, device=dev)
+        for m in mods[:2]:
+            kernels.w4a16_gemm(x, m.packed, N, 128, out=outb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            for m in mods:         # rotate over layers: weights come from HBM, not L2
+                kernels.w4a16_gemm(x, m.packed, N, 128, out=outb)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (3 * len(mods))
+        alg = mods[0].packed.numel() + 2 * a.batch * (K + N)
+        ach = alg / (ms * 1e-3) / 1e9
+        res[name] = {"K": K, "N": N, "us": ms * 1e3, "achieved": ach, "frac": ach / peak,
+                     "tflops": 2.0 * a.batch * K * N / (ms * 1e-3) / 1e12}
+    tot_b = sum((model.layers[0][n].packed.numel()) for n in res)
+    tot_t = sum(v["us"] for v in res.values())
+    return {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": src, "per_proj": res,
+            "achieved": tot_b / (tot_t * 1e-6) / 1e9, "frac": tot_b / (tot_t * 1e-6) / 1e9 / peak}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        print(f"[bench] --gpus {a.gpus} needs torchrun with {a.gpus} ranks; running 1", file=sys.stderr)
+    run_b200(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -453,9 +453,8 @@ static void plan_splits(int64_t base_items, int max_kv_len, int ctas_per_sm, int
   } else {
     for (int s = s_min; s <= s_max; ++s) {
       const double waves = (double)(base_items * s) / (double)slots;
-      double eff = waves / std::ceil(waves);
-      if (waves >= 4.0) eff = std::max(eff, 0.97);  // enough waves: tail is amortised
-      if (eff > best_eff + 0.02) {
+      const double eff = waves / std::ceil(waves);  // tail-wave efficiency
+      if (eff > best_eff + 0.02) {                  // prefer fewer splits unless clearly better
         best_eff = eff;
         best = s;
       }

@@ -1,0 +1,63 @@
+#!/bin/bash
+# Runs on the B200 box (via gpurun).  Every stage is its own process under `timeout` so a hung
+# kernel cannot wedge the whole call; logs land in gpurun_out/.
+#   tools/gpu_ci.sh [tests] [probe] [smoke] [bench] [ncu]     (default: all of them)
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out
+STAGES="${*:-tests probe smoke bench ncu}"
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+echo "stages: $STAGES" | tee $OUT/summary.txt
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+
+if has probe; then
+  for impl in simt tcgen05; do
+    for t in t1 t2 t3 t4 t5 t6; do
+      if [ $impl = simt ] && [ $t != t2 ] && [ $t != t4 ]; then continue; fi
+      B200_W4A16_IMPL=$impl timeout 120 python tools/w4_probe.py $t >> $OUT/probe.log 2>&1
+      echo "probe $impl $t rc=$?" >> $OUT/summary.txt
+    done
+  done
+  grep -h "^\[" $OUT/probe.log | tee -a $OUT/summary.txt
+fi
+
+if has tests; then
+  for f in elementwise attention w4a16 decode_step; do
+    timeout 1200 python -m pytest tests/test_gpu_$f.py -m gpu -q --tb=short -p no:cacheprovider \
+        > $OUT/pytest_$f.log 2>&1
+    echo "pytest $f rc=$? : $(tail -1 $OUT/pytest_$f.log)" | tee -a $OUT/summary.txt
+  done
+fi
+
+if has smoke; then
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1
+  echo "smoke rc=$? : $(tail -1 $OUT/smoke.log)" | tee -a $OUT/summary.txt
+fi
+
+if has bench; then
+  timeout 1500 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err
+  echo "bench rc=$?" | tee -a $OUT/summary.txt
+  tail -c 3000 $OUT/bench.json | tee -a $OUT/summary.txt
+  tail -5 $OUT/bench.err >> $OUT/summary.txt
+fi
+
+if has ncu; then
+  # launch list of a short eager run (cold-cache, serialised: compare SHARES only)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --layers 4 --no-graph \
+      --skip-cpu-baseline > $OUT/ncu_bench.log 2>&1
+  echo "ncu launches rc=$?" | tee -a $OUT/summary.txt
+  # full capture of the dominant kernel
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:paged_attn_decode_kernel -s 8 -c 2 -o $OUT/prof_attn -f \
+      python bench.py --steps 1 --warmup 1 --layers 4 --no-graph --skip-cpu-baseline \
+      > $OUT/ncu_attn.log 2>&1
+  echo "ncu attn rc=$?" | tee -a $OUT/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:w4a16_gemm_kernel -s 8 -c 4 -o $OUT/prof_gemm -f \
+      python bench.py --steps 1 --warmup 1 --layers 4 --no-graph --skip-cpu-baseline \
+      > $OUT/ncu_gemm.log 2>&1
+  echo "ncu gemm rc=$?" | tee -a $OUT/summary.txt
+fi
+echo "== done" | tee -a $OUT/summary.txt
