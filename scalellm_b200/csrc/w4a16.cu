@@ -515,18 +515,57 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (*flag_smem) {
           __threadfence();
-          for (int idx = et; idx < p.M * 128; idx += 128) {
-            const int m = idx >> 7, nl = idx & 127;
-            float acc = 0.f;
+          // Vectorised fixed-order fix-up: thread -> one float4 column group, MT/4 rows, with up
+          // to 8 independent 16-byte L2 loads in flight per contributor.
+          const int n4 = et & 31, mrow0 = et >> 5;
+          constexpr int ROWS = MT / 4;
+          constexpr int RB = ROWS < 8 ? ROWS : 8;
+          const bool vec_store = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
+#pragma unroll 1
+          for (int rb = 0; rb < ROWS; rb += RB) {
+            float4 acc[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int pc = p_first; pc <= p_last; ++pc) {
               const int cb = max(w4_unit_begin(pc, p.units, P), u_lo);
               const int slot = 2 * pc + (cb > u_lo ? 0 : 1);
-              acc += __ldcg(p.ws_partial + ((int64_t)slot * MT + m) * 128 + nl);
+              const float4* src =
+                  reinterpret_cast<const float4*>(p.ws_partial + (int64_t)slot * MT * 128) + n4;
+#pragma unroll
+              for (int j = 0; j < RB; ++j) {
+                const int m = mrow0 + 4 * (rb + j);
+                if (m < p.M) {
+                  const float4 v = __ldcg(src + m * 32);
+                  acc[j].x += v.x;
+                  acc[j].y += v.y;
+                  acc[j].z += v.z;
+                  acc[j].w += v.w;
+                }
+              }
             }
-            const int nn = nt * 128 + nl;
-            __nv_bfloat16 o = __float2bfloat16_rn(acc);
-            if (p.bias) o = __float2bfloat16_rn(__bfloat162float(o) + __bfloat162float(p.bias[nn]));
-            p.C[(int64_t)m * p.ldc + nn] = o;
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+              const int m = mrow0 + 4 * (rb + j);
+              if (m < p.M) {
+                const int nn = nt * 128 + n4 * 4;
+                float f[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+                __nv_bfloat16 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  o[e] = __float2bfloat16_rn(f[e]);
+                  if (p.bias)
+                    o[e] = __float2bfloat16_rn(__bfloat162float(o[e]) +
+                                               __bfloat162float(p.bias[nn + e]));
+                }
+                __nv_bfloat16* dst = p.C + (int64_t)m * p.ldc + nn;
+                if (vec_store) {
+                  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) dst[e] = o[e];
+                }
+              }
+            }
           }
           if (et == 0) p.counters[nt] = 0;  // leave the workspace zeroed (Marlin's contract)
         }

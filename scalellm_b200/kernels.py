@@ -78,6 +78,8 @@ def rms_norm(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, epsil
     assert input.is_contiguous() and out.is_contiguous(), "tensors must be contiguous"
     n = input.shape[-1]
     rows = input.numel() // n
+    if rows == 0:
+        return
     check(_lib.load().b200_rms_norm(_p(out), _p(input), _p(weight), rows, n, epsilon, _dt(input),
                                     _stream()))
 
@@ -88,6 +90,8 @@ def rms_norm_residual(out: torch.Tensor, residual: torch.Tensor, input: torch.Te
     assert input.is_contiguous() and out.is_contiguous() and residual.is_contiguous()
     n = input.shape[-1]
     rows = input.numel() // n
+    if rows == 0:
+        return
     check(_lib.load().b200_rms_norm_residual(_p(out), _p(residual), _p(input), _p(weight), rows, n,
                                              epsilon, _dt(input), _stream()))
 

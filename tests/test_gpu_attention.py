@@ -8,7 +8,7 @@ import torch
 
 from oracle import ops
 from scalellm_b200 import kernels
-from tests.util import assert_ulp, bf16_from_bits
+from tests.util import assert_ulp_or_abs, bf16_from_bits
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -59,8 +59,12 @@ def check(out, ref, dtype, what):
     # reference bar: rtol/atol 1e-2 bf16, 1e-3 fp16 (sm80_mha_pagedkv_test.cu:225-229)
     tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
     assert torch.allclose(out.float(), ref.float(), rtol=tol, atol=tol), what
-    # our bar: fp32 softmax end to end -> within 2 ulp of the fp32 oracle, almost always equal
-    assert_ulp(out, ref, max_ulp=2, max_frac=0.03, what=what)
+    # our bar: fp32 softmax end to end -> within 2 ulp of the fp32 oracle (or, for outputs that
+    # cancel to ~0, within half a bf16 ulp of the largest output), and almost always identical
+    assert_ulp_or_abs(out, ref, max_ulp=2, abs_frac=2 ** -9 if dtype == torch.bfloat16 else 2 ** -11,
+                      what=what)
+    same = (out.view(torch.int16) == ref.view(torch.int16)).float().mean().item()
+    assert same > 0.95, f"{what}: only {same:.3f} of outputs bit-identical to the oracle"
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
@@ -176,4 +180,4 @@ def test_full_size_properties():
         slots = ops.slot_ids_for_sequence(c["table"], c["blk_cu"], b, S, bs)
         ref = ops.mha_ref(c["q"][b:b + 1], torch.nan_to_num(c["kc"][slots], nan=0.0),
                           torch.nan_to_num(c["vc"][slots], posinf=0.0), D ** -0.5, None, 0.0, -1)
-        assert_ulp(o1[b:b + 1].cpu(), ref, max_ulp=2, max_frac=0.03, what=f"full-size seq {b}")
+        assert_ulp_or_abs(o1[b:b + 1].cpu(), ref, max_ulp=2, abs_frac=2 ** -9, what=f"full-size seq {b}")

@@ -22,7 +22,8 @@ def test_rms_norm(dtype, rows, n):
     ref = ops.rms_norm(x, w, 1e-5)
     out = torch.empty_like(x, device=DEV)
     kernels.rms_norm(out, x.to(DEV), w.to(DEV), 1e-5)
-    assert_ulp(out, ref, max_ulp=1, max_frac=2e-3, what="rms_norm")
+    # two roundings ((T)(x*rstd), then *w): a 1-ulp flip of the first can show as 2 ulp
+    assert_ulp(out, ref, max_ulp=2, max_frac=2e-3, what="rms_norm")
     # reference's own bar (normalization_test.cpp:129-132)
     assert torch.allclose(out.float().cpu(), ref.float(), rtol=1e-2, atol=1e-3)
 
@@ -39,7 +40,7 @@ def test_rms_norm_residual(dtype, rows, n):
     out = torch.empty_like(x, device=DEV)
     kernels.rms_norm_residual(out, res, x.to(DEV), w.to(DEV), 1e-5)
     assert torch.equal(res.cpu(), ref_res), "residual stream must be bit exact"
-    assert_ulp(out, ref_out, max_ulp=1, max_frac=2e-3, what="rms_norm_residual")
+    assert_ulp(out, ref_out, max_ulp=2, max_frac=2e-3, what="rms_norm_residual")
 
 
 def test_rms_norm_fp32_and_empty():
@@ -151,7 +152,7 @@ def test_silu_and_silu_mul(dtype):
     if dtype == torch.float32:
         assert torch.allclose(out2.cpu(), ref2, rtol=1e-5, atol=1e-6)
     else:
-        assert_ulp(out2, ref2, max_ulp=1, max_frac=1e-3, what="silu_mul")
+        assert_ulp(out2, ref2, max_ulp=2, max_frac=1e-3, what="silu_mul")
         # the fused op equals kernel::silu followed by a torch multiply (two roundings)
         assert torch.equal(out2, out * d[:, n:])
 

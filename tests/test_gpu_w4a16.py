@@ -87,8 +87,9 @@ def check_gemm(out, a, w_ref, what):
     ref = ref32.bfloat16()
     o = out.float().cpu()
     assert not torch.isnan(o).any(), what
-    err = rel_err(o, ref32)
-    assert err < 1e-3, f"{what}: mean rel err {err:.3e}"      # marlin_gemm_test.py:104-107
+    # marlin_gemm_test.py:104-107: mean relative error of the bf16 output vs the bf16 reference
+    err = rel_err(o, ref.float())
+    assert err < 1e-3, f"{what}: mean rel err {err:.3e}"
     # element-wise: |out - fp32 ref| <= one bf16 ulp of the value + fp32 accumulation noise
     tol = ref32.abs() * 2 ** -7 + 1e-3 * ref32.abs().mean()
     bad = ((o - ref32).abs() > tol).float().mean().item()
@@ -137,7 +138,7 @@ def test_gemm_bias_strided_and_large_m():
     buf[:, 256:768] = a.to(DEV)
     out = kernels.w4a16_gemm(buf[:, 256:768], packed, 256, 128, bias=bias.to(DEV))
     ref = quant.w4a16_gemm(a, w_ref, bias)
-    assert rel_err(out, ref) < 2e-3
+    assert rel_err(out, ref) < 1e-3
     assert (out.cpu().view(torch.int16) == ref.view(torch.int16)).float().mean() > 0.85
 
 
@@ -161,4 +162,6 @@ def test_gemm_linearity_full_size():
     exact = (a1.float().cpu() @ w)
     # results are exact up to the single final bf16 rounding
     assert torch.equal(c1.cpu(), exact.bfloat16().float())
-    assert torch.allclose(c12, c1 + c2, rtol=2 ** -7, atol=0)
+    # each term carries one bf16 rounding (2^-9 relative) of its own magnitude
+    tol = 2.0 ** -8 * (c1.abs() + c2.abs() + c12.abs())
+    assert bool(((c12 - (c1 + c2)).abs() <= tol).all())

@@ -35,3 +35,16 @@ def assert_ulp(a: torch.Tensor, b: torch.Tensor, max_ulp: int = 1, max_frac: flo
 def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
     a, ref = a.float().cpu(), ref.float().cpu()
     return float((a - ref).abs().mean() / ref.abs().mean().clamp_min(1e-12))
+
+
+def assert_ulp_or_abs(a: torch.Tensor, b: torch.Tensor, max_ulp: int, abs_frac: float,
+                      what: str = ""):
+    """Every element within `max_ulp` ulps of the reference OR within abs_frac * max|ref|
+    (ulp counts explode for results that cancel to ~0, where only the absolute error matters)."""
+    a, b = a.cpu(), b.cpu()
+    d = ulp_diff(a, b)
+    err = (a.float() - b.float()).abs()
+    atol = abs_frac * float(b.float().abs().max())
+    bad = (d > max_ulp) & (err > atol)
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())} elements off by more than {max_ulp} ulp "
+                                 f"and {atol:.3e} abs (worst abs err {float(err[bad].max()):.3e})")
