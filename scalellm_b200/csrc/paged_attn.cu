@@ -48,6 +48,7 @@ struct AttnParams {
   int n_heads, n_kv_heads, group, n_hg;
   int block_shift, block_mask, box_rows, boxes_per_tile;
   int max_q_len, n_splits, tiles_per_split;
+  int n_rb;           // mma kernel: 16-row blocks of the packed (q token, group) rows
   float scale_log2;   // sm_scale * log2(e)            (soft_cap == 0)
   float cap_in;       // sm_scale / soft_cap           (soft_cap  > 0)
   float cap_out_log2; // soft_cap * log2(e)
@@ -350,6 +351,342 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   }
 }
 
+
+// ===========================================================================
+// Tensor-core variant (legacy HMMA path; M = 16 rows is the right tile for decode: tcgen05's
+// M >= 64 tiles would waste >= 94 % of the MMA on G*q_len = 4 rows, exactly the reference's
+// problem with its 64-row tile).  Rows of the MMA tile are the packed (q token, group) pairs of
+// one kv head, like the reference packs q_len x group into M (sm80_kernel_mha.cuh:208-262), so
+// speculative / multi-token decode (q_len * G <= 16) costs one KV pass.  S = Q K^T and O += P V
+// use mma.sync.m16n8k16 with fp32 accumulation; P is cast to the element type before PV like the
+// reference (sm80_collective_mha.cuh:289-290).  K/V tiles land in shared memory through a 4-D
+// tensor map {64, D/64, n_kv_heads, n_slots} with SWIZZLE_128B so ldmatrix is (nearly)
+// conflict free; the instruction count per 16-slot tile drops ~7x vs the CUDA-core kernel,
+// which leaves the warp schedulers to the memory pipeline.
+// ===========================================================================
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4],
+                                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&d)[4], const uint32_t (&a)[4],
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+// 128-byte swizzle as the TMA applies it: 16-byte chunk index ^= (address bits [7,10))
+__device__ __forceinline__ uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+
+template <typename T, int D>
+__global__ void __launch_bounds__(ATT_THREADS, (D <= 128 ? 2 : 1))
+paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
+                      const __grid_constant__ CUtensorMap vmap, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int KS = D / 16;   // k-steps of S = Q K^T
+  constexpr int NB = D / 8;    // n-blocks of O
+  constexpr int ROWB = D * (int)sizeof(T);  // bytes per slot row in a tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  T* stage_base = reinterpret_cast<T*>(smem_raw);
+  int32_t* tbl = reinterpret_cast<int32_t*>(smem_raw + (size_t)ATT_WARPS * STAGES * 2 *
+                                                           Cfg::TILE_ELEMS * sizeof(T));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl + ATT_TBL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, kvh = blockIdx.y;
+  const int b = blockIdx.z / p.n_rb, rb = blockIdx.z % p.n_rb;
+  const int G = p.group;
+
+  const int q_begin = p.q_cu_lens[b];
+  const int q_len = p.q_cu_lens[b + 1] - q_begin;
+  const int rows_total = q_len * G;
+  const int row0 = rb * 16;
+  if (row0 >= rows_total) return;
+  const int n_rows = min(16, rows_total - row0);
+  const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+  const int q_pos0 = kv_len - q_len;  // position of query token 0
+
+  // rows owned by this lane in the C / A fragments: r_lo = lane/4, r_hi = r_lo + 8
+  int row_qi[2], row_head[2], row_end[2], row_begin[2];
+  bool row_ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = (lane >> 2) + 8 * h;
+    row_ok[h] = r < n_rows;
+    const int row = row0 + (row_ok[h] ? r : 0);
+    row_qi[h] = row / G;
+    row_head[h] = kvh * G + (row - row_qi[h] * G);
+    const int qp = q_pos0 + row_qi[h];
+    row_end[h] = row_ok[h] ? qp + 1 : 0;          // invalid rows attend to nothing
+    row_begin[h] = p.window >= 0 ? max(0, qp - p.window) : 0;
+  }
+  const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
+  const int kv_end = q_pos0 + qi_max + 1;
+  const int kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
+
+  int t0 = split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
+  t0 = max(t0, kv_begin / ATT_TILE);
+  t1 = min(t1, (kv_end + ATT_TILE - 1) / ATT_TILE);
+
+  if (t0 >= t1) {
+    if (p.n_splits > 1 && threadIdx.x < n_rows) {
+      const int row = row0 + threadIdx.x, qi = row / G, head = kvh * G + (row - qi * G);
+      p.ws_lse[(((int64_t)b * p.max_q_len + qi) * p.n_heads + head) * p.n_splits + split] =
+          -INFINITY;
+    }
+    return;
+  }
+
+  const int blk_cu = p.block_cu_lens[b];
+  const int blk_first = (t0 * ATT_TILE) >> p.block_shift;
+  const int blk_last = (min(t1 * ATT_TILE, kv_end) - 1) >> p.block_shift;
+  for (int i = threadIdx.x; i <= blk_last - blk_first; i += ATT_THREADS)
+    tbl[i] = p.block_table[blk_cu + blk_first + i];
+  if (threadIdx.x < ATT_WARPS * STAGES) mbar_init(&bars[threadIdx.x], 1);
+  fence_mbar_init();
+  __syncthreads();
+
+  T* my_stage = stage_base + (size_t)warp * STAGES * 2 * Cfg::TILE_ELEMS;
+  uint64_t* my_bars = bars + warp * STAGES;
+  const int n_my = (t1 - t0 - warp + ATT_WARPS - 1) / ATT_WARPS;
+
+  auto issue = [&](int i) {  // lane 0 only
+    const int tile = t0 + warp + i * ATT_WARPS;
+    const int s = i % STAGES;
+    T* ks = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
+    T* vs = ks + Cfg::TILE_ELEMS;
+    const int pos0 = tile * ATT_TILE;
+    int nbox = 0;
+    for (int bx = 0; bx < p.boxes_per_tile; ++bx)
+      if (pos0 + bx * p.box_rows < kv_end) ++nbox;
+    mbar_arrive_expect_tx(&my_bars[s], (uint32_t)(nbox * 2 * p.box_rows * D * sizeof(T)));
+    for (int bx = 0; bx < nbox; ++bx) {
+      const int pos = pos0 + bx * p.box_rows;
+      const int slot0 = tbl[(pos >> p.block_shift) - blk_first] + (pos & p.block_mask);
+      tma_load_4d(ks + bx * p.box_rows * D, &kmap, &my_bars[s], 0, 0, kvh, slot0);
+      tma_load_4d(vs + bx * p.box_rows * D, &vmap, &my_bars[s], 0, 0, kvh, slot0);
+    }
+  };
+  if (lane == 0) {
+    if (warp == 0) {
+      prefetch_tensormap(&kmap);
+      prefetch_tensormap(&vmap);
+    }
+    for (int i = 0; i < STAGES && i < n_my; ++i) issue(i);
+  }
+
+  // ---- Q as A fragments (row-major 16 x 16 per k-step) ------------------------
+  uint32_t qa[KS][4];
+  {
+    const T* qrow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      qrow[h] = static_cast<const T*>(p.q) + (int64_t)(q_begin + row_qi[h]) * p.q_stride_t +
+                (int64_t)row_head[h] * p.q_stride_h + (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        qa[ks][h] = row_ok[h] ? *reinterpret_cast<const uint32_t*>(qrow[h] + ks * 16) : 0u;
+        qa[ks][2 + h] = row_ok[h] ? *reinterpret_cast<const uint32_t*>(qrow[h] + ks * 16 + 8) : 0u;
+      }
+    }
+  }
+  float slope_log2[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    slope_log2[h] = p.alibi ? p.alibi[row_head[h]] * 1.4426950408889634f : 0.f;
+
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float o[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
+
+  // per-lane ldmatrix row addressing (see the fragment notes above)
+  const int lm = lane >> 3, lr = lane & 7;
+
+  for (int i = 0; i < n_my; ++i) {
+    const int s = i % STAGES;
+    const uint32_t phase = (i / STAGES) & 1;
+    T* ks_t = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
+    T* vs_t = ks_t + Cfg::TILE_ELEMS;
+    const uint32_t k_base = smem_u32(ks_t), v_base = smem_u32(vs_t);
+    const int pos0 = (t0 + warp + i * ATT_WARPS) * ATT_TILE;
+    mbar_wait(&my_bars[s], phase);
+
+    // slots at or beyond kv_end may hold stale shared memory or another owner's data (possibly
+    // NaN/Inf): P is 0 there but 0 * NaN would poison the PV MMA, so zero those V rows.
+    const bool boundary = pos0 + ATT_TILE > kv_end;
+    if (boundary) {
+      const int first_bad = kv_end - pos0;  // 1..15
+      for (int c = lane; c < (ATT_TILE - first_bad) * (ROWB / 16); c += 32) {
+        const int row = first_bad + c / (ROWB / 16), ch = c % (ROWB / 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(vs_t) + row * ROWB + ch * 16) =
+            make_uint4(0, 0, 0, 0);  // zeroing a whole row: the swizzle permutes within the row
+      }
+      __syncwarp();
+    }
+
+    // ---- S = Q K^T : two n-blocks of 8 slots ------------------------------------
+    float sacc[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
+#pragma unroll
+      for (int kq = 0; kq < KS / 2; ++kq) {  // one ldmatrix.x4 = 8 slots x 32 d = two k-steps
+        uint32_t bf[4];
+        const uint32_t off = (uint32_t)((nb * 8 + lr) * ROWB + (kq * 32 + lm * 8) * (int)sizeof(T));
+        ldsm_x4(bf, swz128(k_base + off));
+        mma_16816<T>(sacc[nb], qa[2 * kq], bf[0], bf[1]);
+        mma_16816<T>(sacc[nb], qa[2 * kq + 1], bf[2], bf[3]);
+      }
+    }
+
+    // ---- mask + online softmax (exp2 domain) ------------------------------------
+    float corr[2];
+    bool need_rescale = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float x[4];
+      float mx = m[h];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int pos = pos0 + nb * 8 + (lane & 3) * 2 + e;
+          const float sc = sacc[nb][2 * h + e];
+          float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
+          v = fmaf(slope_log2[h], (float)pos, v);
+          const bool ok = pos >= row_begin[h] && pos < row_end[h];
+          x[nb * 2 + e] = ok ? v : -INFINITY;
+          mx = fmaxf(mx, x[nb * 2 + e]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      corr[h] = (mx == m[h]) ? 1.f : exp2f(m[h] - ms);  // unchanged max (or still -inf): no rescale
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        x[c] = exp2f(x[c] - ms);
+        sum += x[c];
+      }
+      l[h] = fmaf(l[h], corr[h], sum);  // per-lane partial; quad-reduced after the loop
+      m[h] = mx;
+      need_rescale |= (corr[h] != 1.f);
+      sacc[0][2 * h] = x[0];
+      sacc[0][2 * h + 1] = x[1];
+      sacc[1][2 * h] = x[2];
+      sacc[1][2 * h + 1] = x[3];
+    }
+    if (__any_sync(0xffffffffu, need_rescale)) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        o[nb][0] *= corr[0];
+        o[nb][1] *= corr[0];
+        o[nb][2] *= corr[1];
+        o[nb][3] *= corr[1];
+      }
+    }
+    // P (16 rows x 16 slots) as the A fragment of the PV MMA, cast to T
+    uint32_t pa[4];
+    pa[0] = Num<T>::pack(sacc[0][0], sacc[0][1]);
+    pa[1] = Num<T>::pack(sacc[0][2], sacc[0][3]);
+    pa[2] = Num<T>::pack(sacc[1][0], sacc[1][1]);
+    pa[3] = Num<T>::pack(sacc[1][2], sacc[1][3]);
+
+    // ---- O += P V : ldmatrix.trans gives V^T fragments, 16 d per instruction ------
+#pragma unroll
+    for (int dq = 0; dq < NB / 2; ++dq) {
+      uint32_t bf[4];
+      const uint32_t off =
+          (uint32_t)(((lm & 1) * 8 + lr) * ROWB + (dq * 16 + (lm >> 1) * 8) * (int)sizeof(T));
+      ldsm_x4_trans(bf, swz128(v_base + off));
+      mma_16816<T>(o[2 * dq], pa, bf[0], bf[1]);
+      mma_16816<T>(o[2 * dq + 1], pa, bf[2], bf[3]);
+    }
+    __syncwarp();
+    if (i + STAGES < n_my) {
+      if (boundary) fence_proxy_async_smem();  // our generic zero-stores before the next TMA write
+      if (lane == 0) issue(i + STAGES);
+    }
+  }
+
+  // ---- finish the row sums across the quad ---------------------------------------
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
+    l[h] += __shfl_xor_sync(0xffffffffu, l[h], 2);
+  }
+
+  // ---- merge the warps through shared memory (each warp reuses its own stages) -----
+  float* red = reinterpret_cast<float*>(my_stage);  // [16][D] O, then [16] m, [16] l
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = (lane >> 2) + 8 * h;
+    if (r < n_rows) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        *reinterpret_cast<float2*>(&red[r * D + nb * 8 + (lane & 3) * 2]) =
+            make_float2(o[nb][2 * h], o[nb][2 * h + 1]);
+      if ((lane & 3) == 0) {
+        red[16 * D + r] = m[h];
+        red[16 * D + 16 + r] = l[h];
+      }
+    }
+  }
+  __syncthreads();
+  constexpr size_t WARP_STRIDE = (size_t)STAGES * 2 * Cfg::TILE_ELEMS * sizeof(T) / sizeof(float);
+  const float* red0 = reinterpret_cast<const float*>(stage_base);
+  for (int idx = threadIdx.x; idx < n_rows * D; idx += ATT_THREADS) {
+    const int r = idx / D, d = idx % D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, red0[w * WARP_STRIDE + 16 * D + r]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) {
+      const float sc_w = exp2f(red0[w * WARP_STRIDE + 16 * D + r] - M);
+      L = fmaf(red0[w * WARP_STRIDE + 16 * D + 16 + r], sc_w, L);
+      O = fmaf(red0[w * WARP_STRIDE + r * D + d], sc_w, O);
+    }
+    const float ov = O / L;
+    const int row = row0 + r, qi = row / G, head = kvh * G + (row - qi * G);
+    if (p.n_splits == 1) {
+      static_cast<T*>(p.out)[(int64_t)(q_begin + qi) * p.o_stride_t + (int64_t)head * p.o_stride_h + d] =
+          Num<T>::from_f(ov);
+    } else {
+      const int64_t wrow = ((int64_t)b * p.max_q_len + qi) * p.n_heads + head;
+      p.ws_o[(wrow * p.n_splits + split) * D + d] = ov;
+      if (d == 0) p.ws_lse[wrow * p.n_splits + split] = M + log2f(L);
+    }
+  }
+}
+
 // Second pass: merge split-KV partials (same maths as the reference's unwired
 // attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).
 template <typename T, int D>
@@ -384,8 +721,9 @@ struct MapKey {
   const void* ptr;
   int64_t n_slots, stride_s, stride_h;
   int n_kv_heads, head_dim, box_rows, dtype;
+  int mode;  // 0: 3-D, no swizzle (CUDA-core kernel)   1: 4-D {64, D/64, H, slots}, SWIZZLE_128B (mma kernel)
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && n_slots == o.n_slots && stride_s == o.stride_s &&
+    return mode == o.mode && ptr == o.ptr && n_slots == o.n_slots && stride_s == o.stride_s &&
            stride_h == o.stride_h && n_kv_heads == o.n_kv_heads && head_dim == o.head_dim &&
            box_rows == o.box_rows && dtype == o.dtype;
   }
@@ -409,18 +747,29 @@ static int get_kv_tensor_map(const MapKey& key, CUtensorMap* out) {
   tensor_map_encode_fn enc = get_tensor_map_encode();
   if (!enc) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const int es = 2;
-  cuuint64_t dims[3] = {(cuuint64_t)key.head_dim, (cuuint64_t)key.n_kv_heads,
-                        (cuuint64_t)key.n_slots};
-  cuuint64_t strides[2] = {(cuuint64_t)key.stride_h * es, (cuuint64_t)key.stride_s * es};
-  cuuint32_t box[3] = {(cuuint32_t)key.head_dim, 1u, (cuuint32_t)key.box_rows};
-  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = key.dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap m;
-  CUresult r = enc(&m,
-                   key.dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                   3, const_cast<void*>(key.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (key.mode == 0) {
+    cuuint64_t dims[3] = {(cuuint64_t)key.head_dim, (cuuint64_t)key.n_kv_heads,
+                          (cuuint64_t)key.n_slots};
+    cuuint64_t strides[2] = {(cuuint64_t)key.stride_h * es, (cuuint64_t)key.stride_s * es};
+    cuuint32_t box[3] = {(cuuint32_t)key.head_dim, 1u, (cuuint32_t)key.box_rows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(&m, dt, 3, const_cast<void*>(key.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[4] = {64u, (cuuint64_t)(key.head_dim / 64), (cuuint64_t)key.n_kv_heads,
+                          (cuuint64_t)key.n_slots};
+    cuuint64_t strides[3] = {128u, (cuuint64_t)key.stride_h * es, (cuuint64_t)key.stride_s * es};
+    cuuint32_t box[4] = {64u, (cuuint32_t)(key.head_dim / 64), 1u, (cuuint32_t)key.box_rows};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = enc(&m, dt, 4, const_cast<void*>(key.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS)
     return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for kv cache", (int)r);
   {
@@ -467,20 +816,66 @@ static void plan_splits(int64_t base_items, int max_kv_len, int ctas_per_sm, int
 
 static int hg_rows(int group) { return group >= 4 ? 4 : (group >= 2 ? 2 : 1); }
 
-template <typename T, int D, int R>
-static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnParams& p,
-                       int64_t batch, cudaStream_t st) {
-  constexpr size_t smem = attn_smem_bytes<T, D>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(paged_attn_decode_kernel<T, D, R>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+// 0 = CUDA-core kernel, 1 = mma.sync kernel (default; B200_ATTN_IMPL=simt selects 0)
+static int attn_impl() {
+  const char* e = getenv("B200_ATTN_IMPL");
+  return (e && e[0] == 's') ? 0 : 1;
+}
+
+struct AttnPlan {
+  int impl, R, n_hg, n_rb, n_splits, tps;
+  int64_t grid_y, grid_z;
+};
+
+static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads,
+                          int n_kv_heads, int head_dim) {
+  AttnPlan pl{};
+  pl.impl = attn_impl();
+  const int group = n_heads / n_kv_heads;
+  const int ctas = head_dim <= 128 ? 2 : 1;
+  if (pl.impl == 0) {
+    pl.R = hg_rows(group);
+    pl.n_hg = (group + pl.R - 1) / pl.R;
+    pl.n_rb = 1;
+    pl.grid_y = (int64_t)n_kv_heads * pl.n_hg;
+    pl.grid_z = batch * max_q_len;
+  } else {
+    pl.R = 0;
+    pl.n_hg = 1;
+    pl.n_rb = (max_q_len * group + 15) / 16;
+    pl.grid_y = n_kv_heads;
+    pl.grid_z = batch * pl.n_rb;
   }
-  dim3 grid((unsigned)p.n_splits, (unsigned)(p.n_kv_heads * p.n_hg),
-            (unsigned)(batch * p.max_q_len));
-  paged_attn_decode_kernel<T, D, R><<<grid, ATT_THREADS, smem, st>>>(kmap, vmap, p);
+  plan_splits(pl.grid_y * pl.grid_z, max_kv_len, ctas, &pl.n_splits, &pl.tps);
+  return pl;
+}
+
+template <typename KernelT>
+static int launch_kernel(KernelT kernel, size_t smem, const CUtensorMap& kmap,
+                         const CUtensorMap& vmap, const AttnParams& p, const AttnPlan& pl,
+                         cudaStream_t st) {
+  B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)p.n_splits, (unsigned)pl.grid_y, (unsigned)pl.grid_z);
+  kernel<<<grid, ATT_THREADS, smem, st>>>(kmap, vmap, p);
   B200_LAUNCH_OK("paged_attn_decode");
+  return B200_OK;
+}
+
+template <typename T, int D>
+static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnParams& p,
+                       const AttnPlan& pl, int64_t batch, cudaStream_t st) {
+  constexpr size_t smem = attn_smem_bytes<T, D>();
+  int rc;
+  if (pl.impl == 1) {
+    rc = launch_kernel(paged_attn_mma_kernel<T, D>, smem, kmap, vmap, p, pl, st);
+  } else if (pl.R == 4) {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 4>, smem, kmap, vmap, p, pl, st);
+  } else if (pl.R == 2) {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 2>, smem, kmap, vmap, p, pl, st);
+  } else {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 1>, smem, kmap, vmap, p, pl, st);
+  }
+  if (rc != B200_OK) return rc;
   if (p.n_splits > 1) {
     dim3 cgrid((unsigned)p.n_heads, (unsigned)(batch * p.max_q_len));
     paged_attn_combine_kernel<T, D><<<cgrid, 128, 0, st>>>(p);
@@ -489,23 +884,13 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   return B200_OK;
 }
 
-template <typename T, int D>
-static int launch_attn_r(int R, const CUtensorMap& kmap, const CUtensorMap& vmap,
-                         const AttnParams& p, int64_t batch, cudaStream_t st) {
-  switch (R) {
-    case 4: return launch_attn<T, D, 4>(kmap, vmap, p, batch, st);
-    case 2: return launch_attn<T, D, 2>(kmap, vmap, p, batch, st);
-    default: return launch_attn<T, D, 1>(kmap, vmap, p, batch, st);
-  }
-}
-
 template <typename T>
-static int launch_attn_d(int D, int R, const CUtensorMap& kmap, const CUtensorMap& vmap,
-                         const AttnParams& p, int64_t batch, cudaStream_t st) {
+static int launch_attn_d(int D, const CUtensorMap& kmap, const CUtensorMap& vmap,
+                         const AttnParams& p, const AttnPlan& pl, int64_t batch, cudaStream_t st) {
   switch (D) {
-    case 64: return launch_attn_r<T, 64>(R, kmap, vmap, p, batch, st);
-    case 128: return launch_attn_r<T, 128>(R, kmap, vmap, p, batch, st);
-    case 256: return launch_attn_r<T, 256>(R, kmap, vmap, p, batch, st);
+    case 64: return launch_attn<T, 64>(kmap, vmap, p, pl, batch, st);
+    case 128: return launch_attn<T, 128>(kmap, vmap, p, pl, batch, st);
+    case 256: return launch_attn<T, 256>(kmap, vmap, p, pl, batch, st);
     default:
       return set_error(B200_ERR_UNSUPPORTED, "paged_attn: head_dim %d not in {64,128,256}", D);
   }
@@ -520,12 +905,10 @@ extern "C" {
 int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_t max_kv_len,
                                         int64_t n_heads, int64_t n_kv_heads, int64_t head_dim) {
   if (batch <= 0 || max_q_len <= 0 || n_heads <= 0 || n_kv_heads <= 0) return 0;
-  const int group = (int)(n_heads / n_kv_heads);
-  const int R = hg_rows(group);
-  const int n_hg = (group + R - 1) / R;
-  int n_splits, tps;
-  plan_splits(batch * max_q_len * n_kv_heads * n_hg, (int)max_kv_len, head_dim <= 128 ? 2 : 1,
-              &n_splits, &tps);
+  if (n_heads % n_kv_heads) return 0;
+  const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
+                                (int)n_kv_heads, (int)head_dim);
+  const int n_splits = pl.n_splits;
   if (n_splits <= 1) return 0;
   // worst case over env overrides: size for the planned split count
   return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
@@ -558,7 +941,8 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
   if (batch == 0 || max_q_len <= 0 || max_kv_len <= 0) return B200_OK;
 
   const int group = (int)(n_heads / n_kv_heads);
-  const int R = hg_rows(group);
+  const AttnPlan pl = make_plan(batch, max_q_len, max_kv_len, (int)n_heads, (int)n_kv_heads,
+                                (int)head_dim);
   AttnParams p{};
   p.q = q;
   p.out = out;
@@ -574,7 +958,8 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
   p.n_heads = (int)n_heads;
   p.n_kv_heads = (int)n_kv_heads;
   p.group = group;
-  p.n_hg = (group + R - 1) / R;
+  p.n_hg = pl.n_hg;
+  p.n_rb = pl.n_rb;
   p.block_shift = ilog2(block_size);
   p.block_mask = block_size - 1;
   p.box_rows = block_size < ATT_TILE ? block_size : ATT_TILE;
@@ -590,8 +975,8 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
     p.use_cap = 0;
     p.scale_log2 = sm_scale * LOG2E;
   }
-  plan_splits(batch * max_q_len * n_kv_heads * p.n_hg, max_kv_len, head_dim <= 128 ? 2 : 1,
-              &p.n_splits, &p.tiles_per_split);
+  p.n_splits = pl.n_splits;
+  p.tiles_per_split = pl.tps;
   if (p.n_splits > 1) {
     const int64_t rows = batch * max_q_len * n_heads * p.n_splits;
     const int64_t need = rows * (head_dim + 1) * (int64_t)sizeof(float);
@@ -605,7 +990,7 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
 
   CUtensorMap kmap, vmap;
   MapKey key{k_cache, n_slots, kv_stride_s, kv_stride_h, (int)n_kv_heads, (int)head_dim,
-             p.box_rows, dtype};
+             p.box_rows, dtype, pl.impl};
   int rc = get_kv_tensor_map(key, &kmap);
   if (rc != B200_OK) return rc;
   key.ptr = v_cache;
@@ -614,8 +999,8 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
 
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_BF16)
-    return launch_attn_d<__nv_bfloat16>((int)head_dim, R, kmap, vmap, p, batch, st);
-  return launch_attn_d<__half>((int)head_dim, R, kmap, vmap, p, batch, st);
+    return launch_attn_d<__nv_bfloat16>((int)head_dim, kmap, vmap, p, pl, batch, st);
+  return launch_attn_d<__half>((int)head_dim, kmap, vmap, p, pl, batch, st);
 }
 
 }  // extern "C"
