@@ -232,6 +232,10 @@ B200_API int b200_w4a16_gemm(void* C, const void* A, const void* packed,
                              void* workspace, int64_t workspace_bytes,
                              b200_stream_t stream);
 
+/* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
+ * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
+B200_API void b200_debug_set_trace(void* device_buffer);
+
 /* ------------------------------------------------------------------------ *
  * A9  Tensor-parallel all-reduce over NVLink peer memory
  *     replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)

@@ -255,7 +255,13 @@ struct W4Params {
   int* counters;      // [NT]
   int M, N, K, KT, NT, geff, ngrp, blob_bytes, units;
   int64_t ldc;
+  long long* trace;  // debug: [grid][16] clock64 milestones (null in production)
 };
+
+#define W4_TRACE(slot)                                                   \
+  do {                                                                   \
+    if (p.trace) p.trace[(int64_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
 
 struct SegIter {
   int u, u1, KT;
@@ -304,6 +310,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = gridDim.x;
+  if (threadIdx.x == 0) W4_TRACE(0);
   const int u_begin = w4_unit_begin(blockIdx.x, p.units, P);
   const int u_end = w4_unit_begin(blockIdx.x + 1, p.units, P);
 
@@ -335,6 +342,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) W4_TRACE(1);
 
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
@@ -348,6 +356,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
         const uint8_t* raw = raw_smem + rs * Cfg::RAW_BYTES;
         mbar_wait(&raw_full[rs], rph);
+        if (threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
         uint4 u[2];
         u[0] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 0) * 128 + n_local) * 16);
         u[1] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 1) * 128 + n_local) * 16);
@@ -382,6 +391,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         }
       }
     }
+    if (threadIdx.x == 0) W4_TRACE(3);
   } else if (warp == W4_WARP_RAW) {
     // ===================== weight-blob producer ==============================
     if (lane == 0) {
@@ -433,6 +443,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
           mbar_wait(&act_full[as], aph);
           mbar_wait(&deq_full[ds], dph);
+          if (cnt == 0) W4_TRACE(4);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(deq_smem + ds * Cfg::DEQ_BYTES);
           const uint32_t b_addr = smem_u32(act_smem + as * Cfg::ACT_BYTES);
@@ -449,6 +460,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         umma_commit(&tmem_full[buf]);
         ++seg;
       }
+      W4_TRACE(5);
     }
   } else {
     // ===================== epilogue warps (4) =================================
@@ -463,6 +475,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       const bool full_tile = (kt0 == 0 && kt1 == p.KT);
       const int n = nt * 128 + n_local;
       mbar_wait(&tmem_full[buf], tph);
+      if (et == 0 && seg == 0) W4_TRACE(6);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * MT;
       float* part = nullptr;
@@ -500,6 +513,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (et == 0 && seg == 0) W4_TRACE(7);
 
       if (!full_tile) {
         // ---- publish the partial; the last contributor reduces the tile -------
@@ -513,6 +527,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           *flag_smem = (old == p_last - p_first) ? 1u : 0u;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) W4_TRACE(8 + (seg > 0 ? 2 : 0));
         if (*flag_smem) {
           __threadfence();
           // Vectorised fixed-order fix-up: thread -> one float4 column group, MT/4 rows, with up
@@ -568,15 +583,18 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             }
           }
           if (et == 0) p.counters[nt] = 0;  // leave the workspace zeroed (Marlin's contract)
+          if (et == 0) W4_TRACE(9 + (seg > 0 ? 2 : 0));
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_smem reuse
       }
       ++seg;
     }
+    if (et == 0) W4_TRACE(12);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) W4_TRACE(13);
   if (warp == W4_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -630,6 +648,8 @@ static int get_act_tensor_map(const AMapKey& key, CUtensorMap* out) {
   *out = m;
   return B200_OK;
 }
+
+static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
@@ -719,6 +739,10 @@ int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K, int64_t N, in
   return B200_OK;
 }
 
+void b200_debug_set_trace(void* device_buffer) {
+  g_w4_trace = static_cast<long long*>(device_buffer);
+}
+
 int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   (void)N;
   (void)K;
@@ -773,6 +797,7 @@ int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias
     p.blob_bytes = w4_blob_bytes(geff);
     p.units = p.KT * p.NT;
     p.ldc = ldc;
+    p.trace = g_w4_trace;
     const int grid = w4_grid(p.units);
     const int64_t need =
         B200_W4A16_COUNTER_BYTES + 2ll * grid * mt * 128 * (int64_t)sizeof(float);

@@ -1,0 +1,61 @@
+"""Kernel-only timing of the paged attention decode op at the benchmark shape (B=64, S=2048,
+H=32/8, D=128), rotating over several caches so every launch streams from HBM."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from scalellm_b200 import kernels  # noqa: E402
+
+DEV = "cuda"
+
+
+def main():
+    B, S, H, Hkv, D = 64, 2048, 32, 8, 128
+    impl = os.environ.get("B200_ATTN_IMPL", "mma")
+    for bs in (8, 16, 128):
+        nblk = (S + bs - 1) // bs
+        n_blocks = B * nblk + 8
+        L = 10
+        caches = [(torch.randn(n_blocks * bs, Hkv, D, device=DEV).bfloat16(),
+                   torch.randn(n_blocks * bs, Hkv, D, device=DEV).bfloat16()) for _ in range(L)]
+        perm = torch.randperm(n_blocks)[: B * nblk]
+        table = (perm * bs).to(torch.int32).to(DEV)
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+        q_cu, kv_cu, blk_cu = i32(np.arange(B + 1)), i32(np.arange(B + 1) * S), i32(np.arange(B + 1) * nblk)
+        q = torch.randn(B, H, D, device=DEV).bfloat16()
+        out = torch.empty_like(q)
+
+        def launch(kc, vc):
+            kernels.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, 1, S,
+                                        D ** -0.5, 0.0, -1)
+        for kc, vc in caches[:3]:
+            launch(kc, vc)
+        torch.cuda.synchronize()
+        for splits in ("", "1", "2", "4", "8"):
+            if splits:
+                os.environ["B200_ATTN_SPLITS"] = splits
+            else:
+                os.environ.pop("B200_ATTN_SPLITS", None)
+            launch(*caches[0])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                for kc, vc in caches:
+                    launch(kc, vc)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (3 * L)
+            byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
+            print(f"attn impl={impl} bs={bs} splits={splits or 'auto'}: {us:7.1f} us/launch "
+                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
+                  flush=True)
+        os.environ.pop("B200_ATTN_SPLITS", None)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,23 @@ if has probe; then
   grep -h "^\[" $OUT/probe.log | tee -a $OUT/summary.txt
 fi
 
+if has trace; then
+  timeout 300 python tools/w4_trace.py > $OUT/w4_trace.log 2>&1
+  echo "trace rc=$?" | tee -a $OUT/summary.txt
+  cat $OUT/w4_trace.log >> $OUT/summary.txt
+fi
+
+if has attn2; then
+  # both attention variants through the same parity tests + a kernel-only timing
+  for impl in mma simt; do
+    B200_ATTN_IMPL=$impl timeout 900 python -m pytest tests/test_gpu_attention.py -m gpu -q --tb=short \
+        -p no:cacheprovider > $OUT/pytest_attention_$impl.log 2>&1
+    echo "pytest attention[$impl] rc=$? : $(tail -1 $OUT/pytest_attention_$impl.log)" | tee -a $OUT/summary.txt
+    B200_ATTN_IMPL=$impl timeout 600 python tools/attn_bench.py >> $OUT/attn_bench.log 2>&1
+  done
+  cat $OUT/attn_bench.log | tee -a $OUT/summary.txt
+fi
+
 if has tests; then
   for f in elementwise attention w4a16 decode_step; do
     timeout 1200 python -m pytest tests/test_gpu_$f.py -m gpu -q --tb=short -p no:cacheprovider \

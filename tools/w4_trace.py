@@ -1,0 +1,59 @@
+"""Timeline probe for the W4A16 GEMM: per-CTA clock64 milestones (see W4_TRACE in w4a16.cu)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from scalellm_b200 import _lib, kernels  # noqa: E402
+
+DEV = "cuda"
+NAMES = ["start", "setup_done", "deq_first_raw", "deq_done", "mma_first", "mma_last_commit",
+         "epi_first_full", "epi_first_seg_done", "epi_reduce0_begin", "epi_reduce0_end",
+         "epi_reduceN_begin", "epi_reduceN_end", "epi_done", "end"]
+
+
+def run(K, N, M=64, g=128):
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // g, N // 8), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    sc = (torch.randn(K // g, N, generator=gen, device=DEV).abs() * 0.01 + 1e-4).bfloat16()
+    packed = kernels.w4a16_prepack_awq(qw, qz, sc, g)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    for _ in range(3):
+        kernels.w4a16_gemm(a, packed, N, g, out=out)
+    torch.cuda.synchronize()
+    # flush L2 so the traced launch streams weights from HBM
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    flush.zero_()
+    trace = torch.zeros(1024 * 16, dtype=torch.int64, device=DEV)
+    lib = _lib.load()
+    lib.b200_debug_set_trace(trace.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    kernels.w4a16_gemm(a, packed, N, g, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.b200_debug_set_trace(None)
+    t = trace.cpu().view(-1, 16)
+    t = t[t[:, 0] != 0]
+    rel = (t - t[:, :1]).float()
+    rel[t == 0] = float("nan")
+    print(f"== K={K} N={N} M={M}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {t.shape[0]} CTAs "
+          f"(cycles; ~1.9 cycles/ns)")
+    for i, nm in enumerate(NAMES):
+        col = rel[:, i]
+        col = col[~torch.isnan(col)]
+        if col.numel() == 0:
+            continue
+        print(f"  {nm:20s} n={col.numel():4d} median={col.median():9.0f} min={col.min():9.0f} "
+              f"max={col.max():9.0f}")
+    torch.save(t, os.path.join(ROOT, "gpurun_out", f"w4_trace_{K}x{N}.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
+        run(K, N)
