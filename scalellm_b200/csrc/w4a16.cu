@@ -409,6 +409,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         }
       }
     }
+    __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_ACT) {
     // ===================== activation producer (TMA) =========================
     if (lane == 0) {
@@ -426,6 +427,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         }
       }
     }
+    __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
     if (lane == 0) {
@@ -462,6 +464,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       }
       W4_TRACE(5);
     }
+    __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else {
     // ===================== epilogue warps (4) =================================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may touch
@@ -546,16 +549,18 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
               const int slot = 2 * pc + (cb > u_lo ? 0 : 1);
               const float4* src =
                   reinterpret_cast<const float4*>(p.ws_partial + (int64_t)slot * MT * 128) + n4;
+              float4 v[RB];
+#pragma unroll
+              for (int j = 0; j < RB; ++j) {  // unconditional (row clamped): RB loads in flight
+                const int m = min(mrow0 + 4 * (rb + j), p.M - 1);
+                v[j] = __ldcg(src + m * 32);
+              }
 #pragma unroll
               for (int j = 0; j < RB; ++j) {
-                const int m = mrow0 + 4 * (rb + j);
-                if (m < p.M) {
-                  const float4 v = __ldcg(src + m * 32);
-                  acc[j].x += v.x;
-                  acc[j].y += v.y;
-                  acc[j].z += v.z;
-                  acc[j].w += v.w;
-                }
+                acc[j].x += v[j].x;
+                acc[j].y += v[j].y;
+                acc[j].z += v[j].z;
+                acc[j].w += v[j].w;
               }
             }
 #pragma unroll

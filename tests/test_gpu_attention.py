@@ -63,8 +63,11 @@ def check(out, ref, dtype, what):
     # cancel to ~0, within half a bf16 ulp of the largest output), and almost always identical
     assert_ulp_or_abs(out, ref, max_ulp=2, abs_frac=2 ** -9 if dtype == torch.bfloat16 else 2 ** -11,
                       what=what)
+    # the tensor-core kernel casts P to the element type before PV, exactly like the reference
+    # kernel (sm80_collective_mha.cuh:289-290), so fewer outputs round identically to the fp32 oracle
     same = (out.view(torch.int16) == ref.view(torch.int16)).float().mean().item()
-    assert same > 0.95, f"{what}: only {same:.3f} of outputs bit-identical to the oracle"
+    floor = 0.95 if os.environ.get("B200_ATTN_IMPL", "mma").startswith("s") else 0.6
+    assert same > floor, f"{what}: only {same:.3f} of outputs bit-identical to the oracle"
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
