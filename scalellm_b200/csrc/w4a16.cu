@@ -13,10 +13,13 @@
 //   * weights live in HBM as self-contained "tile blobs" (128 n x 128 k: packed
 //     nibbles + that tile's scales + zero points), streamed with one bulk-async
 //     copy per blob into a deep shared-memory ring;
-//   * 8 dequant warps turn a blob into two 128x64 bf16 K-major SWIZZLE_128B UMMA
-//     tiles (lop3 magic-number int4->bf16, HSUB2 zero point, HMUL2 scale);
-//   * one thread issues tcgen05.mma (kind::f16, M=128, N=MT, K=16) with the
-//     accumulator in TMEM (double buffered), activations arrive by TMA (128B swizzle);
+//   * two groups of 4 dequant warps alternate k-tiles: a thread owns one weight row (one
+//     TMEM lane), turns its 16 packed words into 128 bf16 (lop3 magic-number int4->bf16,
+//     HSUB2 zero point, HMUL2 scale) and writes them with tcgen05.st straight into TENSOR
+//     MEMORY, where they are the A operand of the UMMA — no shared-memory staging, no
+//     swizzle arithmetic and no generic->async proxy fence on the weight path;
+//   * one thread issues tcgen05.mma (kind::f16, A from TMEM, M=128, N=MT, K=16) with the
+//     accumulator in TMEM (double buffered); activations arrive by TMA (128B swizzle);
 //   * stream-K over (n_tile, k_tile) units so all SMs stream an equal share of
 //     the weight bytes; partial tiles meet in an fp32 workspace and the last
 //     arriving CTA reduces them in a fixed order (deterministic).
@@ -228,22 +231,23 @@ __global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
 // ===========================================================================
 template <int MT>
 struct W4Cfg {
-  static constexpr int RAW_STAGES = MT <= 64 ? 6 : 4;
   static constexpr int ACT_STAGES = MT <= 64 ? 3 : 2;
-  static constexpr int DEQ_STAGES = 3;
+  static constexpr int A_STAGES = 4;              // dequantised-weight stages in TMEM
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
-  static constexpr int DEQ_ATOM = 128 * 128;      // [128 n x 64 k] bf16
-  static constexpr int DEQ_BYTES = 2 * DEQ_ATOM;
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
-  static constexpr int TMEM_COLS = 2 * MT < 32 ? 32 : 2 * MT;
-  static constexpr int N_BARS = 2 * RAW_STAGES + 2 * ACT_STAGES + 2 * DEQ_STAGES + 4;
-  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)DEQ_STAGES * DEQ_BYTES +
-                                 (size_t)ACT_STAGES * ACT_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
-                                 N_BARS * 8 + 64;
+  static constexpr int RAW_STAGES = MT <= 64 ? 16 : 14;  // deep ring: ~150 KB of weights in flight
+  static constexpr int ACC_COLS = 2 * MT;         // two accumulators [128 x MT] fp32
+  static constexpr int A_COL0 = ACC_COLS;         // A ring: A_STAGES x 64 columns (128 k of bf16)
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int N_BARS = 2 * RAW_STAGES + 2 * ACT_STAGES + 2 * A_STAGES + 4;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)ACT_STAGES * ACT_BYTES +
+                                 (size_t)RAW_STAGES * RAW_BYTES + N_BARS * 8 + 64;
+  static_assert(A_COL0 + A_STAGES * 64 <= TMEM_COLS, "TMEM over-subscribed");
 };
 
 constexpr int W4_DEQ_WARPS = 8;
+constexpr int W4_DEQ_GROUPS = 2;  // groups of 4 warps (one warp per TMEM lane quadrant) alternate k-tiles
 constexpr int W4_WARP_RAW = 8, W4_WARP_ACT = 9, W4_WARP_MMA = 10, W4_WARP_EPI = 11;
 constexpr int W4_THREADS = 15 * 32;
 
@@ -293,8 +297,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* deq_smem = base;
-  uint8_t* act_smem = deq_smem + Cfg::DEQ_STAGES * Cfg::DEQ_BYTES;
+  uint8_t* act_smem = base;
   uint8_t* raw_smem = act_smem + Cfg::ACT_STAGES * Cfg::ACT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(raw_smem + Cfg::RAW_STAGES * Cfg::RAW_BYTES);
   uint64_t* raw_full = bars;
@@ -302,8 +305,8 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   uint64_t* act_full = raw_empty + Cfg::RAW_STAGES;
   uint64_t* act_empty = act_full + Cfg::ACT_STAGES;
   uint64_t* deq_full = act_empty + Cfg::ACT_STAGES;
-  uint64_t* deq_empty = deq_full + Cfg::DEQ_STAGES;
-  uint64_t* tmem_full = deq_empty + Cfg::DEQ_STAGES;
+  uint64_t* deq_empty = deq_full + Cfg::A_STAGES;
+  uint64_t* tmem_full = deq_empty + Cfg::A_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint32_t* flag_smem = tmem_holder + 1;
@@ -317,14 +320,14 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], W4_DEQ_WARPS);
+      mbar_init(&raw_empty[i], 4);
     }
     for (int i = 0; i < Cfg::ACT_STAGES; ++i) {
       mbar_init(&act_full[i], 1);
       mbar_init(&act_empty[i], 1);
     }
-    for (int i = 0; i < Cfg::DEQ_STAGES; ++i) {
-      mbar_init(&deq_full[i], W4_DEQ_WARPS);
+    for (int i = 0; i < Cfg::A_STAGES; ++i) {
+      mbar_init(&deq_full[i], 4);
       mbar_init(&deq_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -346,47 +349,61 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
-    const int t = threadIdx.x, n_local = t & 127, khalf = t >> 7;
-    const int row_sw = n_local & 7;
+    // group = warp / 4 takes k-tiles cnt % 2 == group; inside a group warp q = warp % 4 owns
+    // TMEM lanes [32q, 32q+32): thread <-> weight row n_local, all 128 k of the tile.
+    const int group = warp >> 2;
+    const int n_local = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0;
     SegIter it{u_begin, u_end, p.KT};
     int nt, kt0, kt1, cnt = 0;
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
-        const int rs = cnt % Cfg::RAW_STAGES, ds = cnt % Cfg::DEQ_STAGES;
-        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
+        if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
+        const int rs = cnt % Cfg::RAW_STAGES, as = cnt % Cfg::A_STAGES;
+        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
         const uint8_t* raw = raw_smem + rs * Cfg::RAW_BYTES;
         mbar_wait(&raw_full[rs], rph);
         if (threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
-        uint4 u[2];
-        u[0] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 0) * 128 + n_local) * 16);
-        u[1] = *reinterpret_cast<const uint4*>(raw + ((khalf * 2 + 1) * 128 + n_local) * 16);
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          u[q] = *reinterpret_cast<const uint4*>(raw + (q * 128 + n_local) * 16);
         const __nv_bfloat16* s_in = reinterpret_cast<const __nv_bfloat16*>(raw + W4_QBYTES);
         const uint8_t* z_in = raw + W4_QBYTES + p.ngrp * 256;
-        // this thread's 64 k span 64/geff groups (1 for geff >= 64, 2 for geff == 32)
-        const int g0 = (khalf * 64) / p.geff;
-        const int g1 = (khalf * 64 + 32) / p.geff;
-        const __nv_bfloat16 s0 = s_in[g0 * 128 + n_local], s1 = s_in[g1 * 128 + n_local];
-        const uint32_t z0 = z_in[g0 * 128 + n_local];
-        const uint32_t z1 = z_in[g1 * 128 + n_local];
-        const __nv_bfloat162 s2[2] = {__halves2bfloat162(s0, s0), __halves2bfloat162(s1, s1)};
-        const __nv_bfloat162 zm[2] = {w4_zmagic(z0), w4_zmagic(z1)};
-        mbar_wait(&deq_empty[ds], dph ^ 1);
-        // this thread's 64 k all live in swizzle atom `khalf`, chunks 0..7 of row n_local
-        uint8_t* drow = deq_smem + ds * Cfg::DEQ_BYTES + khalf * Cfg::DEQ_ATOM + n_local * 128;
+        // uint4 q covers k in [32q, 32q+32): its quant group is (32q)/geff (geff in {32,64,128})
+        __nv_bfloat162 s2[4], zm[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-          const uint32_t words[4] = {u[q4].x, u[q4].y, u[q4].z, u[q4].w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int c = q4 * 4 + w;  // 16-byte chunk (8 k) within the 128-byte row
-            const uint4 d = w4_dequant_word(words[w], zm[q4], s2[q4]);
-            *reinterpret_cast<uint4*>(drow + ((c ^ row_sw) << 4)) = d;
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int gq = (q * 32) / p.geff;
+          const __nv_bfloat16 sv = s_in[gq * 128 + n_local];
+          s2[q] = __halves2bfloat162(sv, sv);
+          zm[q] = w4_zmagic(z_in[gq * 128 + n_local]);
         }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05 (async proxy)
+        mbar_wait(&deq_empty[as], aph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // 64 k = 32 columns per tcgen05.st
+          uint32_t r[32];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 uu = u[hh * 2 + q];
+            const uint32_t words[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const uint4 d = w4_dequant_word(words[w], zm[hh * 2 + q], s2[hh * 2 + q]);
+              r[(q * 4 + w) * 4 + 0] = d.x;
+              r[(q * 4 + w) * 4 + 1] = d.y;
+              r[(q * 4 + w) * 4 + 2] = d.z;
+              r[(q * 4 + w) * 4 + 3] = d.w;
+            }
+          }
+          tmem_st_32x32b_x32(lane_base + as * 64 + hh * 32, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&deq_full[ds]);
+          mbar_arrive(&deq_full[as]);
           mbar_arrive(&raw_empty[rs]);
         }
       }
@@ -441,20 +458,19 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * MT;
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
-          const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::DEQ_STAGES;
-          const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::DEQ_STAGES) & 1;
+          const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::A_STAGES;
+          const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::A_STAGES) & 1;
           mbar_wait(&act_full[as], aph);
           mbar_wait(&deq_full[ds], dph);
           if (cnt == 0) W4_TRACE(4);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(deq_smem + ds * Cfg::DEQ_BYTES);
+          const uint32_t a_tmem = tmem_base + Cfg::A_COL0 + ds * 64;
           const uint32_t b_addr = smem_u32(act_smem + as * Cfg::ACT_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const int atom = ks >> 2, kk = ks & 3;
-            const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr + atom * Cfg::DEQ_ATOM + kk * 32);
             const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + atom * Cfg::ACT_ATOM + kk * 32);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kt > kt0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, (kt > kt0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(&deq_empty[ds]);
           umma_commit(&act_empty[as]);
