@@ -229,14 +229,17 @@ __global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
 // ===========================================================================
 // tcgen05 stream-K GEMM
 // ===========================================================================
-template <int MT>
+// CFG selects the shared-memory split between the activation ring (L2/TMA latency) and the
+// weight-blob ring (HBM latency); B200_W4_CFG picks one at run time while tuning.
+template <int MT, int CFG>
 struct W4Cfg {
-  static constexpr int ACT_STAGES = MT <= 64 ? 3 : 2;
+  static constexpr int ACT_STAGES = MT <= 64 ? (CFG == 0 ? 3 : CFG == 1 ? 6 : 8) : (CFG == 0 ? 2 : 3);
   static constexpr int A_STAGES = 4;              // dequantised-weight stages in TMEM
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
-  static constexpr int RAW_STAGES = MT <= 64 ? 16 : 14;  // deep ring: ~150 KB of weights in flight
+  static constexpr int RAW_STAGES =
+      MT <= 64 ? (CFG == 0 ? 16 : CFG == 1 ? 11 : 7) : (CFG == 0 ? 14 : 10);
   static constexpr int ACC_COLS = 2 * MT;         // two accumulators [128 x MT] fp32
   static constexpr int A_COL0 = ACC_COLS;         // A ring: A_STAGES x 64 columns (128 k of bf16)
   static constexpr int TMEM_COLS = 512;
@@ -259,12 +262,16 @@ struct W4Params {
   int* counters;      // [NT]
   int M, N, K, KT, NT, geff, ngrp, blob_bytes, units;
   int64_t ldc;
-  long long* trace;  // debug: [grid][16] clock64 milestones (null in production)
+  long long* trace;  // debug: [grid][32] clock64 milestones / wait totals (null in production)
 };
 
+#define W4_TRACE_ADD(slot, cyc)                                          \
+  do {                                                                   \
+    if (p.trace) p.trace[(int64_t)blockIdx.x * 32 + (slot)] += (cyc);    \
+  } while (0)
 #define W4_TRACE(slot)                                                   \
   do {                                                                   \
-    if (p.trace) p.trace[(int64_t)blockIdx.x * 16 + (slot)] = clock64(); \
+    if (p.trace) p.trace[(int64_t)blockIdx.x * 32 + (slot)] = clock64(); \
   } while (0)
 
 struct SegIter {
@@ -290,10 +297,10 @@ __device__ __forceinline__ int w4_owner(int u, int units, int P) {
   return p;
 }
 
-template <int MT>
+template <int MT, int CFG>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
-  using Cfg = W4Cfg<MT>;
+  using Cfg = W4Cfg<MT, CFG>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -356,13 +363,16 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0;
     SegIter it{u_begin, u_end, p.KT};
     int nt, kt0, kt1, cnt = 0;
+    long long w_raw = 0, w_empty = 0;
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
         if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
         const int rs = cnt % Cfg::RAW_STAGES, as = cnt % Cfg::A_STAGES;
         const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
         const uint8_t* raw = raw_smem + rs * Cfg::RAW_BYTES;
+        const long long tq0 = p.trace ? clock64() : 0;
         mbar_wait(&raw_full[rs], rph);
+        if (p.trace) w_raw += clock64() - tq0;
         if (threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
         uint4 u[4];
 #pragma unroll
@@ -379,7 +389,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           s2[q] = __halves2bfloat162(sv, sv);
           zm[q] = w4_zmagic(z_in[gq * 128 + n_local]);
         }
+        const long long tq1 = p.trace ? clock64() : 0;
         mbar_wait(&deq_empty[as], aph ^ 1);
+        if (p.trace) w_empty += clock64() - tq1;
         tc_fence_after();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {  // 64 k = 32 columns per tcgen05.st
@@ -408,23 +420,31 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         }
       }
     }
-    if (threadIdx.x == 0) W4_TRACE(3);
+    if (threadIdx.x == 0) {
+      W4_TRACE(3);
+      W4_TRACE_ADD(18, w_raw);
+      W4_TRACE_ADD(19, w_empty);
+    }
   } else if (warp == W4_WARP_RAW) {
     // ===================== weight-blob producer ==============================
     if (lane == 0) {
       SegIter it{u_begin, u_end, p.KT};
       int nt, kt0, kt1, cnt = 0;
+      long long w_wait = 0;
       while (it.next(nt, kt0, kt1)) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int rs = cnt % Cfg::RAW_STAGES;
           const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1;
+          const long long tr0 = p.trace ? clock64() : 0;
           mbar_wait(&raw_empty[rs], rph ^ 1);
+          if (p.trace) w_wait += clock64() - tr0;
           mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)p.blob_bytes);
           bulk_load_1d(raw_smem + rs * Cfg::RAW_BYTES,
                        p.packed + ((int64_t)nt * p.KT + kt) * p.blob_bytes, (uint32_t)p.blob_bytes,
                        &raw_full[rs]);
         }
       }
+      W4_TRACE_ADD(21, w_wait);
     }
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_ACT) {
@@ -432,17 +452,21 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     if (lane == 0) {
       SegIter it{u_begin, u_end, p.KT};
       int nt, kt0, kt1, cnt = 0;
+      long long w_wait = 0;
       while (it.next(nt, kt0, kt1)) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
+          const long long ta0 = p.trace ? clock64() : 0;
           mbar_wait(&act_empty[as], aph ^ 1);
+          if (p.trace) w_wait += clock64() - ta0;
           mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
           tma_load_2d(dst + Cfg::ACT_ATOM, &amap, &act_full[as], kt * 128 + 64, 0);
         }
       }
+      W4_TRACE_ADD(20, w_wait);
     }
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_MMA) {
@@ -451,17 +475,26 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
       SegIter it{u_begin, u_end, p.KT};
       int nt, kt0, kt1, cnt = 0, seg = 0;
+      long long w_act = 0, w_deq = 0, w_tmem = 0;
       while (it.next(nt, kt0, kt1)) {
         const int buf = seg & 1;
         const uint32_t tph = (seg >> 1) & 1;
+        const long long tt0 = p.trace ? clock64() : 0;
         mbar_wait(&tmem_empty[buf], tph ^ 1);
+        if (p.trace) w_tmem += clock64() - tt0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * MT;
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::A_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::A_STAGES) & 1;
+          const long long tw0 = p.trace ? clock64() : 0;
           mbar_wait(&act_full[as], aph);
+          const long long tw1 = p.trace ? clock64() : 0;
           mbar_wait(&deq_full[ds], dph);
+          if (p.trace) {
+            w_act += tw1 - tw0;
+            w_deq += clock64() - tw1;
+          }
           if (cnt == 0) W4_TRACE(4);
           tc_fence_after();
           const uint32_t a_tmem = tmem_base + Cfg::A_COL0 + ds * 64;
@@ -479,6 +512,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         ++seg;
       }
       W4_TRACE(5);
+      W4_TRACE_ADD(16, w_act);
+      W4_TRACE_ADD(17, w_deq);
+      W4_TRACE_ADD(22, w_tmem);
     }
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else {
@@ -560,24 +596,36 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             float4 acc[RB];
 #pragma unroll
             for (int j = 0; j < RB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int pc = p_first; pc <= p_last; ++pc) {
-              const int cb = max(w4_unit_begin(pc, p.units, P), u_lo);
-              const int slot = 2 * pc + (cb > u_lo ? 0 : 1);
-              const float4* src =
-                  reinterpret_cast<const float4*>(p.ws_partial + (int64_t)slot * MT * 128) + n4;
-              float4 v[RB];
+            for (int pc = p_first; pc <= p_last; pc += 2) {
+              // two contributors per round trip: 2*RB independent 16-byte L2 loads in flight
+              const float4* src[2];
+              float wgt[2];
 #pragma unroll
-              for (int j = 0; j < RB; ++j) {  // unconditional (row clamped): RB loads in flight
-                const int m = min(mrow0 + 4 * (rb + j), p.M - 1);
-                v[j] = __ldcg(src + m * 32);
+              for (int c2 = 0; c2 < 2; ++c2) {
+                const int pcc = min(pc + c2, p_last);
+                const int cb = max(w4_unit_begin(pcc, p.units, P), u_lo);
+                const int slot = 2 * pcc + (cb > u_lo ? 0 : 1);
+                src[c2] = reinterpret_cast<const float4*>(p.ws_partial + (int64_t)slot * MT * 128) + n4;
+                wgt[c2] = (pc + c2 <= p_last) ? 1.f : 0.f;
               }
+              float4 v[2][RB];
 #pragma unroll
-              for (int j = 0; j < RB; ++j) {
-                acc[j].x += v[j].x;
-                acc[j].y += v[j].y;
-                acc[j].z += v[j].z;
-                acc[j].w += v[j].w;
-              }
+              for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                  const int m = min(mrow0 + 4 * (rb + j), p.M - 1);
+                  v[c2][j] = __ldcg(src[c2] + m * 32);
+                }
+              // fixed order pc, pc+1 (the duplicate of an odd tail is multiplied by 0)
+#pragma unroll
+              for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                  acc[j].x = fmaf(v[c2][j].x, wgt[c2], acc[j].x);
+                  acc[j].y = fmaf(v[c2][j].y, wgt[c2], acc[j].y);
+                  acc[j].z = fmaf(v[c2][j].z, wgt[c2], acc[j].z);
+                  acc[j].w = fmaf(v[c2][j].w, wgt[c2], acc[j].w);
+                }
             }
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
@@ -674,14 +722,30 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-template <int MT>
-static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, int grid, cudaStream_t st) {
-  using Cfg = W4Cfg<MT>;
-  B200_CUDA_OK(cudaFuncSetAttribute(w4a16_gemm_kernel<MT>,
+template <int MT, int CFG>
+static int launch_w4_gemm_cfg(const CUtensorMap& amap, const W4Params& p, int grid,
+                              cudaStream_t st) {
+  using Cfg = W4Cfg<MT, CFG>;
+  B200_CUDA_OK(cudaFuncSetAttribute(w4a16_gemm_kernel<MT, CFG>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  w4a16_gemm_kernel<MT><<<grid, W4_THREADS, Cfg::SMEM, st>>>(amap, p);
+  w4a16_gemm_kernel<MT, CFG><<<grid, W4_THREADS, Cfg::SMEM, st>>>(amap, p);
   B200_LAUNCH_OK("w4a16_gemm");
   return B200_OK;
+}
+
+static int w4_cfg() {
+  const char* e = getenv("B200_W4_CFG");
+  const int c = e ? atoi(e) : 1;
+  return c < 0 ? 0 : (c > 2 ? 2 : c);
+}
+
+template <int MT>
+static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, int grid, cudaStream_t st) {
+  switch (w4_cfg()) {
+    case 0: return launch_w4_gemm_cfg<MT, 0>(amap, p, grid, st);
+    case 2: return launch_w4_gemm_cfg<MT, 2>(amap, p, grid, st);
+    default: return launch_w4_gemm_cfg<MT, 1>(amap, p, grid, st);
+  }
 }
 
 static int w4_grid(int units) {

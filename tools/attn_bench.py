@@ -14,9 +14,17 @@ DEV = "cuda"
 
 
 def main():
-    B, S, H, Hkv, D = 64, 2048, 32, 8, 128
+    shapes = [(64, 2048, 32, 8, 128)]
+    if len(sys.argv) > 1 and sys.argv[1] == "locality":
+        shapes = [(64, 2048, 32, 8, 128), (512, 2048, 4, 1, 128), (128, 2048, 16, 4, 128)]
+    for shp in shapes:
+        one_shape(*shp)
+
+
+def one_shape(B, S, H, Hkv, D):
     impl = os.environ.get("B200_ATTN_IMPL", "mma")
-    for bs in (8, 16, 128):
+    print(f"--- B={B} S={S} H={H} Hkv={Hkv} D={D}")
+    for bs in (8, 128):
         nblk = (S + bs - 1) // bs
         n_blocks = B * nblk + 8
         L = 10
@@ -35,7 +43,7 @@ def main():
         for kc, vc in caches[:3]:
             launch(kc, vc)
         torch.cuda.synchronize()
-        for splits in ("", "1", "2", "4", "8"):
+        for splits in ("", "1", "2", "3", "4"):
             if splits:
                 os.environ["B200_ATTN_SPLITS"] = splits
             else:

@@ -11,7 +11,10 @@ from scalellm_b200 import _lib, kernels  # noqa: E402
 DEV = "cuda"
 NAMES = ["start", "setup_done", "deq_first_raw", "deq_done", "mma_first", "mma_last_commit",
          "epi_first_full", "epi_first_seg_done", "epi_reduce0_begin", "epi_reduce0_end",
-         "epi_reduceN_begin", "epi_reduceN_end", "epi_done", "end"]
+         "epi_reduceN_begin", "epi_reduceN_end", "epi_done", "end", "-", "-",
+         "SUM mma wait act_full", "SUM mma wait deq_full", "SUM deq(g0) wait raw_full",
+         "SUM deq(g0) wait deq_empty", "SUM actprod wait act_empty", "SUM rawprod wait raw_empty",
+         "SUM mma wait tmem_empty"]
 
 
 def run(K, N, M=64, g=128):
@@ -28,7 +31,7 @@ def run(K, N, M=64, g=128):
     # flush L2 so the traced launch streams weights from HBM
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     flush.zero_()
-    trace = torch.zeros(1024 * 16, dtype=torch.int64, device=DEV)
+    trace = torch.zeros(1024 * 32, dtype=torch.int64, device=DEV)
     lib = _lib.load()
     lib.b200_debug_set_trace(trace.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,16 +40,17 @@ def run(K, N, M=64, g=128):
     e1.record()
     torch.cuda.synchronize()
     lib.b200_debug_set_trace(None)
-    t = trace.cpu().view(-1, 16)
+    t = trace.cpu().view(-1, 32)
     t = t[t[:, 0] != 0]
     rel = (t - t[:, :1]).float()
+    rel[:, 16:] = t[:, 16:].float()      # wait totals are already durations
     rel[t == 0] = float("nan")
     print(f"== K={K} N={N} M={M}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {t.shape[0]} CTAs "
           f"(cycles; ~1.9 cycles/ns)")
     for i, nm in enumerate(NAMES):
         col = rel[:, i]
         col = col[~torch.isnan(col)]
-        if col.numel() == 0:
+        if col.numel() == 0 or nm == "-":
             continue
         print(f"  {nm:20s} n={col.numel():4d} median={col.median():9.0f} min={col.min():9.0f} "
               f"max={col.max():9.0f}")
@@ -55,5 +59,8 @@ def run(K, N, M=64, g=128):
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
-        run(K, N)
+    for cfg in (sys.argv[1:] or ["1"]):
+        os.environ["B200_W4_CFG"] = cfg
+        print(f"######## B200_W4_CFG={cfg}")
+        for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
+            run(K, N)
