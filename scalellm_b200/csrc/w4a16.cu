@@ -471,8 +471,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
-    if (lane == 0) {
+    // The whole warp runs this loop converged so every operand is warp-uniform (uniform
+    // registers, no per-instruction ELECT/R2UR loop); one elected lane issues the UMMAs.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
       SegIter it{u_begin, u_end, p.KT};
       int nt, kt0, kt1, cnt = 0, seg = 0;
       long long w_act = 0, w_deq = 0, w_tmem = 0;
@@ -483,7 +487,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         mbar_wait(&tmem_empty[buf], tph ^ 1);
         if (p.trace) w_tmem += clock64() - tt0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * MT;
+        const uint32_t d_tmem = tbase + buf * MT;
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::A_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::A_STAGES) & 1;
@@ -495,26 +499,33 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             w_act += tw1 - tw0;
             w_deq += clock64() - tw1;
           }
-          if (cnt == 0) W4_TRACE(4);
+          if (cnt == 0 && lane == 0) W4_TRACE(4);
           tc_fence_after();
-          const uint32_t a_tmem = tmem_base + Cfg::A_COL0 + ds * 64;
-          const uint32_t b_addr = smem_u32(act_smem + as * Cfg::ACT_BYTES);
+          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
+          const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
+          const uint32_t first = (kt > kt0) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const int atom = ks >> 2, kk = ks & 3;
-            const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + atom * Cfg::ACT_ATOM + kk * 32);
-            umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, (kt > kt0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks) {
+              // descriptor start-address field is in 16-byte units: advance by constants
+              const uint64_t b_desc =
+                  b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
+              umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
+            }
+            umma_commit(&deq_empty[ds]);
+            umma_commit(&act_empty[as]);
+            if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
           }
-          umma_commit(&deq_empty[ds]);
-          umma_commit(&act_empty[as]);
+          __syncwarp();
         }
-        umma_commit(&tmem_full[buf]);
         ++seg;
       }
-      W4_TRACE(5);
-      W4_TRACE_ADD(16, w_act);
-      W4_TRACE_ADD(17, w_deq);
-      W4_TRACE_ADD(22, w_tmem);
+      if (lane == 0) {
+        W4_TRACE(5);
+        W4_TRACE_ADD(16, w_act);
+        W4_TRACE_ADD(17, w_deq);
+        W4_TRACE_ADD(22, w_tmem);
+      }
     }
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else {
