@@ -364,6 +364,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     SegIter it{u_begin, u_end, p.KT};
     int nt, kt0, kt1, cnt = 0;
     long long w_raw = 0, w_empty = 0;
+    int pend_as = -1, pend_rs = -1;
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
         if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
@@ -409,15 +410,29 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
               r[(q * 4 + w) * 4 + 3] = d.w;
             }
           }
+          if (hh == 0 && pend_as >= 0) {
+            // publish the PREVIOUS tile only now: its TMEM stores had half a tile of math to land
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&deq_full[pend_as]);
+              mbar_arrive(&raw_empty[pend_rs]);
+            }
+          }
           tmem_st_32x32b_x32(lane_base + as * 64 + hh * 32, r);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&deq_full[as]);
-          mbar_arrive(&raw_empty[rs]);
-        }
+        pend_as = as;
+        pend_rs = rs;
+      }
+    }
+    if (pend_as >= 0) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&deq_full[pend_as]);
+        mbar_arrive(&raw_empty[pend_rs]);
       }
     }
     if (threadIdx.x == 0) {
@@ -583,12 +598,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
       if (!full_tile) {
         // ---- publish the partial; the last contributor reduces the tile -------
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // every partial store of the CTA is issued
         const int u_lo = nt * p.KT;
         const int p_first = w4_owner(u_lo, p.units, P);
         const int p_last = w4_owner(u_lo + p.KT - 1, p.units, P);
         if (et == 0) {
+          __threadfence();  // one cumulative gpu-scope fence (grid-sync idiom), then publish
           const int old = atomicAdd(&p.counters[nt], 1);
           *flag_smem = (old == p_last - p_first) ? 1u : 0u;
         }

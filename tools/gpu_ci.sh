@@ -77,4 +77,9 @@ if has ncu; then
       > $OUT/ncu_gemm.log 2>&1
   echo "ncu gemm rc=$?" | tee -a $OUT/summary.txt
 fi
+if has ncuattn; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn_mma_kernel \
+      -s 6 -c 2 -o $OUT/prof_attn_mma -f python tools/attn_bench.py > $OUT/ncu_attn_mma.log 2>&1
+  echo "ncu attn mma rc=$?" | tee -a $OUT/summary.txt
+fi
 echo "== done" | tee -a $OUT/summary.txt
