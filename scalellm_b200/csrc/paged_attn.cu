@@ -64,6 +64,17 @@ struct AttnCfg {
   static constexpr int TILE_ELEMS = ATT_TILE * D;
 };
 
+// single-warp CTAs take at most ATT_TPS_W1 tiles, so their block-table window is small
+constexpr int ATT_TPS_W1 = 32;
+__host__ __device__ constexpr int att_tbl_entries(int warps) {
+  return warps == 1 ? ATT_TPS_W1 * ATT_TILE + 8 : ATT_TBL;
+}
+template <typename T, int D, int W>
+constexpr size_t attn_mma_smem_bytes() {
+  return (size_t)W * AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
+         att_tbl_entries(W) * sizeof(int32_t) + W * AttnCfg<D>::STAGES * sizeof(uint64_t) + 128;
+}
+
 template <typename T, int D>
 constexpr size_t attn_smem_bytes() {
   return (size_t)ATT_WARPS * AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T)  // K+V stages
@@ -398,8 +409,8 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
 // 128-byte swizzle as the TMA applies it: 16-byte chunk index ^= (address bits [7,10))
 __device__ __forceinline__ uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
-template <typename T, int D>
-__global__ void __launch_bounds__(ATT_THREADS, (D <= 128 ? 2 : 1))
+template <typename T, int D, int W>
+__global__ void __launch_bounds__(W * 32, (W == 1 ? (D <= 128 ? 6 : 2) : (D <= 128 ? 2 : 1)))
 paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
                       const __grid_constant__ CUtensorMap vmap, const AttnParams p) {
   using Cfg = AttnCfg<D>;
@@ -409,9 +420,9 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
   constexpr int ROWB = D * (int)sizeof(T);  // bytes per slot row in a tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
-  int32_t* tbl = reinterpret_cast<int32_t*>(smem_raw + (size_t)ATT_WARPS * STAGES * 2 *
+  int32_t* tbl = reinterpret_cast<int32_t*>(smem_raw + (size_t)W * STAGES * 2 *
                                                            Cfg::TILE_ELEMS * sizeof(T));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl + ATT_TBL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl + att_tbl_entries(W));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, kvh = blockIdx.y;
@@ -461,18 +472,18 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
   const int blk_cu = p.block_cu_lens[b];
   const int blk_first = (t0 * ATT_TILE) >> p.block_shift;
   const int blk_last = (min(t1 * ATT_TILE, kv_end) - 1) >> p.block_shift;
-  for (int i = threadIdx.x; i <= blk_last - blk_first; i += ATT_THREADS)
+  for (int i = threadIdx.x; i <= blk_last - blk_first; i += (W * 32))
     tbl[i] = p.block_table[blk_cu + blk_first + i];
-  if (threadIdx.x < ATT_WARPS * STAGES) mbar_init(&bars[threadIdx.x], 1);
+  if (threadIdx.x < W * STAGES) mbar_init(&bars[threadIdx.x], 1);
   fence_mbar_init();
   __syncthreads();
 
   T* my_stage = stage_base + (size_t)warp * STAGES * 2 * Cfg::TILE_ELEMS;
   uint64_t* my_bars = bars + warp * STAGES;
-  const int n_my = (t1 - t0 - warp + ATT_WARPS - 1) / ATT_WARPS;
+  const int n_my = (t1 - t0 - warp + W - 1) / W;
 
   auto issue = [&](int i) {  // lane 0 only
-    const int tile = t0 + warp + i * ATT_WARPS;
+    const int tile = t0 + warp + i * W;
     const int s = i % STAGES;
     T* ks = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
     T* vs = ks + Cfg::TILE_ELEMS;
@@ -534,7 +545,7 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
     T* ks_t = my_stage + (size_t)s * 2 * Cfg::TILE_ELEMS;
     T* vs_t = ks_t + Cfg::TILE_ELEMS;
     const uint32_t k_base = smem_u32(ks_t), v_base = smem_u32(vs_t);
-    const int pos0 = (t0 + warp + i * ATT_WARPS) * ATT_TILE;
+    const int pos0 = (t0 + warp + i * W) * ATT_TILE;
     mbar_wait(&my_bars[s], phase);
 
     // slots at or beyond kv_end may hold stale shared memory or another owner's data (possibly
@@ -662,14 +673,14 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
   __syncthreads();
   constexpr size_t WARP_STRIDE = (size_t)STAGES * 2 * Cfg::TILE_ELEMS * sizeof(T) / sizeof(float);
   const float* red0 = reinterpret_cast<const float*>(stage_base);
-  for (int idx = threadIdx.x; idx < n_rows * D; idx += ATT_THREADS) {
+  for (int idx = threadIdx.x; idx < n_rows * D; idx += (W * 32)) {
     const int r = idx / D, d = idx % D;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, red0[w * WARP_STRIDE + 16 * D + r]);
+    for (int w = 0; w < W; ++w) M = fmaxf(M, red0[w * WARP_STRIDE + 16 * D + r]);
     float L = 0.f, O = 0.f;
 #pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) {
+    for (int w = 0; w < W; ++w) {
       const float sc_w = exp2f(red0[w * WARP_STRIDE + 16 * D + r] - M);
       L = fmaf(red0[w * WARP_STRIDE + 16 * D + 16 + r], sc_w, L);
       O = fmaf(red0[w * WARP_STRIDE + r * D + d], sc_w, O);
@@ -823,7 +834,7 @@ static int attn_impl() {
 }
 
 struct AttnPlan {
-  int impl, R, n_hg, n_rb, n_splits, tps;
+  int impl, R, n_hg, n_rb, n_splits, tps, warps;
   int64_t grid_y, grid_z;
 };
 
@@ -846,17 +857,39 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     pl.grid_y = n_kv_heads;
     pl.grid_z = batch * pl.n_rb;
   }
+  pl.warps = ATT_WARPS;
+  if (pl.impl == 1) {
+    const char* e = getenv("B200_ATTN_WARPS");
+    pl.warps = (e && atoi(e) == 4) ? 4 : 1;
+  }
+  if (pl.warps == 1) {
+    // one warp per CTA: every warp is its own split; ~6 CTAs/SM run at independent phases
+    const int n_tiles = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
+    const char* e = getenv("B200_ATTN_TPS");
+    int tps = (e && atoi(e) > 0) ? atoi(e) : 16;
+    tps = std::max(1, std::min(tps, ATT_TPS_W1));
+    // keep the split count (workspace + combine cost) bounded for very long contexts
+    while ((n_tiles + tps - 1) / tps > 64 && tps < ATT_TPS_W1) tps *= 2;
+    if ((n_tiles + tps - 1) / tps > 256) tps = (n_tiles + 255) / 256;  // > 128K tokens: W=4 path
+    if (tps > ATT_TPS_W1) {
+      pl.warps = 4;
+    } else {
+      pl.tps = tps;
+      pl.n_splits = (n_tiles + tps - 1) / tps;
+      return pl;
+    }
+  }
   plan_splits(pl.grid_y * pl.grid_z, max_kv_len, ctas, &pl.n_splits, &pl.tps);
   return pl;
 }
 
 template <typename KernelT>
-static int launch_kernel(KernelT kernel, size_t smem, const CUtensorMap& kmap,
+static int launch_kernel(KernelT kernel, size_t smem, int threads, const CUtensorMap& kmap,
                          const CUtensorMap& vmap, const AttnParams& p, const AttnPlan& pl,
                          cudaStream_t st) {
   B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)p.n_splits, (unsigned)pl.grid_y, (unsigned)pl.grid_z);
-  kernel<<<grid, ATT_THREADS, smem, st>>>(kmap, vmap, p);
+  kernel<<<grid, threads, smem, st>>>(kmap, vmap, p);
   B200_LAUNCH_OK("paged_attn_decode");
   return B200_OK;
 }
@@ -866,14 +899,18 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
                        const AttnPlan& pl, int64_t batch, cudaStream_t st) {
   constexpr size_t smem = attn_smem_bytes<T, D>();
   int rc;
-  if (pl.impl == 1) {
-    rc = launch_kernel(paged_attn_mma_kernel<T, D>, smem, kmap, vmap, p, pl, st);
+  if (pl.impl == 1 && pl.warps == 1) {
+    rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,
+                       vmap, p, pl, st);
+  } else if (pl.impl == 1) {
+    rc = launch_kernel(paged_attn_mma_kernel<T, D, 4>, attn_mma_smem_bytes<T, D, 4>(), 128, kmap,
+                       vmap, p, pl, st);
   } else if (pl.R == 4) {
-    rc = launch_kernel(paged_attn_decode_kernel<T, D, 4>, smem, kmap, vmap, p, pl, st);
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 4>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
   } else if (pl.R == 2) {
-    rc = launch_kernel(paged_attn_decode_kernel<T, D, 2>, smem, kmap, vmap, p, pl, st);
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 2>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
   } else {
-    rc = launch_kernel(paged_attn_decode_kernel<T, D, 1>, smem, kmap, vmap, p, pl, st);
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 1>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
   }
   if (rc != B200_OK) return rc;
   if (p.n_splits > 1) {
