@@ -49,6 +49,7 @@ struct AttnParams {
   int block_shift, block_mask, box_rows, boxes_per_tile;
   int max_q_len, n_splits, tiles_per_split;
   int n_rb;           // mma kernel: 16-row blocks of the packed (q token, group) rows
+  int* work_counter;  // persistent kernel: global work-item counter (zeroed before each launch)
   float scale_log2;   // sm_scale * log2(e)            (soft_cap == 0)
   float cap_in;       // sm_scale / soft_cap           (soft_cap  > 0)
   float cap_out_log2; // soft_cap * log2(e)
@@ -698,6 +699,340 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
   }
 }
 
+
+// ===========================================================================
+// Persistent variant of the tensor-core kernel: one warp per CTA, each warp pulls work items
+// (sequence x row-block x kv head x kv chunk) from a global counter and keeps ONE continuous TMA
+// ring across items — while it drains item i it has already fetched item i+1's lengths, block
+// table window and query fragments and is issuing item i+1's first tiles, so there is no
+// per-item prologue bubble and no wave tail.  Every item is a split of its (sequence, head):
+// partial O / LSE go to the workspace and the combine kernel merges them.
+// ===========================================================================
+constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
+constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
+
+struct ItemMeta {
+  int b, kvh, rb, split;
+  int q_begin, q_len, kv_len;
+  int t0, n_tiles;     // first tile, number of tiles (0 = nothing to do)
+  int kv_end, kv_begin;
+  int blk_first;
+  int valid;           // 0 = no more work
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(32, (D <= 128 ? 8 : 3))
+paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
+                          const __grid_constant__ CUtensorMap vmap, const AttnParams p,
+                          int* __restrict__ work_counter, int n_items) {
+  using Cfg = AttnCfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int KS = D / 16, NB = D / 8;
+  constexpr int ROWB = D * (int)sizeof(T);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  T* stage_base = reinterpret_cast<T*>(smem_raw);
+  int32_t* tbl_base = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * 2 * Cfg::TILE_ELEMS * sizeof(T));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 2 * ATT_P_TBL);
+  const int lane = threadIdx.x;
+  const int G = p.group;
+
+  if (lane < STAGES) mbar_init(&bars[lane], 1);
+  fence_mbar_init();
+  __syncwarp();
+  if (lane == 0) {
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+  }
+
+  // ---- claim + describe a work item (all lanes compute the same values) -----------------
+  auto claim = [&](int tbl_buf) -> ItemMeta {
+    ItemMeta it{};
+    for (;;) {
+      int id = 0;
+      if (lane == 0) id = atomicAdd(work_counter, 1);
+      id = __shfl_sync(0xffffffffu, id, 0);
+      if (id >= n_items) {
+        it.valid = 0;
+        return it;
+      }
+      it.valid = 1;
+      it.split = id % p.n_splits;
+      int rest = id / p.n_splits;
+      it.kvh = rest % p.n_kv_heads;
+      rest /= p.n_kv_heads;
+      it.rb = rest % p.n_rb;
+      it.b = rest / p.n_rb;
+      it.q_begin = p.q_cu_lens[it.b];
+      it.q_len = p.q_cu_lens[it.b + 1] - it.q_begin;
+      it.kv_len = p.kv_cu_lens[it.b + 1] - p.kv_cu_lens[it.b];
+      const int rows_total = it.q_len * G, row0 = it.rb * 16;
+      if (row0 >= rows_total) continue;  // padded row block of a short sequence: nothing to write
+      const int n_rows = min(16, rows_total - row0);
+      const int q_pos0 = it.kv_len - it.q_len;
+      const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
+      it.kv_end = q_pos0 + qi_max + 1;
+      it.kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
+      int t0 = it.split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
+      t0 = max(t0, it.kv_begin / ATT_TILE);
+      t1 = min(t1, (it.kv_end + ATT_TILE - 1) / ATT_TILE);
+      if (t0 >= t1) {  // empty split: publish LSE = -inf for its rows and take the next item
+        if (p.n_splits > 1 && lane < n_rows) {
+          const int row = row0 + lane, qi = row / G, head = it.kvh * G + (row - qi * G);
+          p.ws_lse[(((int64_t)it.b * p.max_q_len + qi) * p.n_heads + head) * p.n_splits + it.split] =
+              -INFINITY;
+        }
+        continue;
+      }
+      it.t0 = t0;
+      it.n_tiles = t1 - t0;
+      it.blk_first = (t0 * ATT_TILE) >> p.block_shift;
+      const int blk_last = (min(t1 * ATT_TILE, it.kv_end) - 1) >> p.block_shift;
+      const int blk_cu = p.block_cu_lens[it.b];
+      int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
+      for (int i = lane; i <= blk_last - it.blk_first; i += 32)
+        tbl[i] = p.block_table[blk_cu + it.blk_first + i];
+      __syncwarp();
+      return it;
+    }
+  };
+
+  // TMA for tile `ti` of item `it` into ring slot of stream position `g`
+  auto issue = [&](const ItemMeta& it, int tbl_buf, int ti, int g) {  // lane 0 only
+    const int s = g % STAGES;
+    T* ks = stage_base + (size_t)s * 2 * Cfg::TILE_ELEMS;
+    T* vs = ks + Cfg::TILE_ELEMS;
+    const int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
+    const int pos0 = (it.t0 + ti) * ATT_TILE;
+    int nbox = 0;
+    for (int bx = 0; bx < p.boxes_per_tile; ++bx)
+      if (pos0 + bx * p.box_rows < it.kv_end) ++nbox;
+    mbar_arrive_expect_tx(&bars[s], (uint32_t)(nbox * 2 * p.box_rows * D * sizeof(T)));
+    for (int bx = 0; bx < nbox; ++bx) {
+      const int pos = pos0 + bx * p.box_rows;
+      const int slot0 = tbl[(pos >> p.block_shift) - it.blk_first] + (pos & p.block_mask);
+      tma_load_4d(ks + bx * p.box_rows * D, &kmap, &bars[s], 0, 0, it.kvh, slot0);
+      tma_load_4d(vs + bx * p.box_rows * D, &vmap, &bars[s], 0, 0, it.kvh, slot0);
+    }
+  };
+
+  // query fragments of an item (A operand of S = Q K^T), rows beyond the item's rows are zero
+  auto load_q = [&](const ItemMeta& it, uint32_t (&qa)[KS][4]) {
+    const int rows_total = it.q_len * G, row0 = it.rb * 16;
+    const int n_rows = min(16, rows_total - row0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (lane >> 2) + 8 * h;
+      const bool ok = r < n_rows;
+      const int row = row0 + (ok ? r : 0), qi = row / G, head = it.kvh * G + (row - qi * G);
+      const T* qrow = static_cast<const T*>(p.q) + (int64_t)(it.q_begin + qi) * p.q_stride_t +
+                      (int64_t)head * p.q_stride_h + (lane & 3) * 2;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        qa[ks][h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
+        qa[ks][2 + h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
+      }
+    }
+  };
+
+  ItemMeta cur = claim(0);
+  if (!cur.valid) return;
+  int cur_buf = 0;
+  ItemMeta nxt = claim(1);
+  uint32_t qa[KS][4], qn[KS][4];
+  load_q(cur, qa);
+  if (nxt.valid) load_q(nxt, qn);
+
+  int g_cons = 0, g_iss = 0;         // stream positions (tiles consumed / issued)
+  int cur_issued = 0, nxt_issued = 0;
+  auto issue_ahead = [&]() {          // keep the ring full: current item first, then the next one
+    while (g_iss - g_cons < STAGES) {
+      if (cur_issued < cur.n_tiles) {
+        if (lane == 0) issue(cur, cur_buf, cur_issued, g_iss);
+        ++cur_issued;
+      } else if (nxt.valid && nxt_issued < nxt.n_tiles) {
+        if (lane == 0) issue(nxt, cur_buf ^ 1, nxt_issued, g_iss);
+        ++nxt_issued;
+      } else {
+        break;
+      }
+      ++g_iss;
+    }
+  };
+  issue_ahead();
+
+  const int lm = lane >> 3, lr = lane & 7;
+  while (cur.valid) {
+    // ---- per-item row bookkeeping ------------------------------------------------------
+    const int rows_total = cur.q_len * G, row0 = cur.rb * 16;
+    const int n_rows = min(16, rows_total - row0);
+    const int q_pos0 = cur.kv_len - cur.q_len;
+    int row_end[2], row_begin[2], row_head[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (lane >> 2) + 8 * h;
+      const bool ok = r < n_rows;
+      const int row = row0 + (ok ? r : 0), qi = row / G;
+      row_head[h] = cur.kvh * G + (row - qi * G);
+      const int qp = q_pos0 + qi;
+      row_end[h] = ok ? qp + 1 : 0;
+      row_begin[h] = p.window >= 0 ? max(0, qp - p.window) : 0;
+    }
+    float slope_log2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      slope_log2[h] = p.alibi ? p.alibi[row_head[h]] * 1.4426950408889634f : 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
+
+    for (int i = 0; i < cur.n_tiles; ++i) {
+      const int s = g_cons % STAGES;
+      const uint32_t phase = (g_cons / STAGES) & 1;
+      T* ks_t = stage_base + (size_t)s * 2 * Cfg::TILE_ELEMS;
+      T* vs_t = ks_t + Cfg::TILE_ELEMS;
+      const uint32_t k_base = smem_u32(ks_t), v_base = smem_u32(vs_t);
+      const int pos0 = (cur.t0 + i) * ATT_TILE;
+      mbar_wait(&bars[s], phase);
+
+      const bool boundary = pos0 + ATT_TILE > cur.kv_end;
+      if (boundary) {  // zero V rows past the causal end (stale / foreign data, maybe NaN)
+        const int first_bad = cur.kv_end - pos0;
+        for (int c = lane; c < (ATT_TILE - first_bad) * (ROWB / 16); c += 32) {
+          const int row = first_bad + c / (ROWB / 16), ch = c % (ROWB / 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(vs_t) + row * ROWB + ch * 16) =
+              make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+      }
+
+      float sacc[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
+#pragma unroll
+        for (int kq = 0; kq < KS / 2; ++kq) {
+          uint32_t bf[4];
+          const uint32_t off = (uint32_t)((nb * 8 + lr) * ROWB + (kq * 32 + lm * 8) * (int)sizeof(T));
+          ldsm_x4(bf, swz128(k_base + off));
+          mma_16816<T>(sacc[nb], qa[2 * kq], bf[0], bf[1]);
+          mma_16816<T>(sacc[nb], qa[2 * kq + 1], bf[2], bf[3]);
+        }
+      }
+
+      float corr[2];
+      bool need_rescale = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float x[4];
+        float mx = m[h];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int pos = pos0 + nb * 8 + (lane & 3) * 2 + e;
+            const float sc = sacc[nb][2 * h + e];
+            float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
+            v = fmaf(slope_log2[h], (float)pos, v);
+            const bool ok = pos >= row_begin[h] && pos < row_end[h];
+            x[nb * 2 + e] = ok ? v : -INFINITY;
+            mx = fmaxf(mx, x[nb * 2 + e]);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float ms = (mx == -INFINITY) ? 0.f : mx;
+        corr[h] = (mx == m[h]) ? 1.f : exp2f(m[h] - ms);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          x[c] = exp2f(x[c] - ms);
+          sum += x[c];
+        }
+        l[h] = fmaf(l[h], corr[h], sum);
+        m[h] = mx;
+        need_rescale |= (corr[h] != 1.f);
+        sacc[0][2 * h] = x[0];
+        sacc[0][2 * h + 1] = x[1];
+        sacc[1][2 * h] = x[2];
+        sacc[1][2 * h + 1] = x[3];
+      }
+      if (__any_sync(0xffffffffu, need_rescale)) {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          o[nb][0] *= corr[0];
+          o[nb][1] *= corr[0];
+          o[nb][2] *= corr[1];
+          o[nb][3] *= corr[1];
+        }
+      }
+      uint32_t pa[4];
+      pa[0] = Num<T>::pack(sacc[0][0], sacc[0][1]);
+      pa[1] = Num<T>::pack(sacc[0][2], sacc[0][3]);
+      pa[2] = Num<T>::pack(sacc[1][0], sacc[1][1]);
+      pa[3] = Num<T>::pack(sacc[1][2], sacc[1][3]);
+#pragma unroll
+      for (int dq = 0; dq < NB / 2; ++dq) {
+        uint32_t bf[4];
+        const uint32_t off =
+            (uint32_t)(((lm & 1) * 8 + lr) * ROWB + (dq * 16 + (lm >> 1) * 8) * (int)sizeof(T));
+        ldsm_x4_trans(bf, swz128(v_base + off));
+        mma_16816<T>(o[2 * dq], pa, bf[0], bf[1]);
+        mma_16816<T>(o[2 * dq + 1], pa, bf[2], bf[3]);
+      }
+      __syncwarp();
+      if (boundary) fence_proxy_async_smem();
+      ++g_cons;
+      issue_ahead();
+    }
+
+    // ---- finalize the item: normalised partial O and LSE (log2 domain) ------------------
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
+      l[h] += __shfl_xor_sync(0xffffffffu, l[h], 2);
+      const int r = (lane >> 2) + 8 * h;
+      if (r < n_rows) {
+        const int row = row0 + r, qi = row / G, head = cur.kvh * G + (row - qi * G);
+        const float inv = 1.f / l[h];
+        if (p.n_splits == 1) {
+          T* dst = static_cast<T*>(p.out) + (int64_t)(cur.q_begin + qi) * p.o_stride_t +
+                   (int64_t)head * p.o_stride_h + (lane & 3) * 2;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+            *reinterpret_cast<uint32_t*>(dst + nb * 8) =
+                Num<T>::pack(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
+        } else {
+          const int64_t wrow = ((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head;
+          float* dst = p.ws_o + (wrow * p.n_splits + cur.split) * D + (lane & 3) * 2;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+            *reinterpret_cast<float2*>(dst + nb * 8) =
+                make_float2(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
+          if ((lane & 3) == 0) p.ws_lse[wrow * p.n_splits + cur.split] = m[h] + log2f(l[h]);
+        }
+      }
+    }
+
+    // ---- rotate: next becomes current, claim and prefetch a new next ----------------------
+    cur = nxt;
+    cur_buf ^= 1;
+    cur_issued = nxt_issued;
+    nxt_issued = 0;
+    if (cur.valid) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) qa[ks][e] = qn[ks][e];
+      nxt = claim(cur_buf ^ 1);
+      if (nxt.valid) load_q(nxt, qn);
+      issue_ahead();
+    }
+  }
+}
+
 // Second pass: merge split-KV partials (same maths as the reference's unwired
 // attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).
 template <typename T, int D>
@@ -827,10 +1162,13 @@ static void plan_splits(int64_t base_items, int max_kv_len, int ctas_per_sm, int
 
 static int hg_rows(int group) { return group >= 4 ? 4 : (group >= 2 ? 2 : 1); }
 
-// 0 = CUDA-core kernel, 1 = mma.sync kernel (default; B200_ATTN_IMPL=simt selects 0)
+// 0 = CUDA-core kernel ("simt"), 1 = mma.sync kernel, CTA per work item ("mma"),
+// 2 = persistent mma.sync kernel (default, "persist").  B200_ATTN_IMPL selects while tuning.
 static int attn_impl() {
   const char* e = getenv("B200_ATTN_IMPL");
-  return (e && e[0] == 's') ? 0 : 1;
+  if (e && e[0] == 's') return 0;
+  if (e && e[0] == 'm') return 1;
+  return 2;
 }
 
 struct AttnPlan {
@@ -850,7 +1188,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     pl.n_rb = 1;
     pl.grid_y = (int64_t)n_kv_heads * pl.n_hg;
     pl.grid_z = batch * max_q_len;
-  } else {
+  } else {  // both tensor-core kernels pack (q token, group) rows into 16-row blocks
     pl.R = 0;
     pl.n_hg = 1;
     pl.n_rb = (max_q_len * group + 15) / 16;
@@ -862,6 +1200,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     const char* e = getenv("B200_ATTN_WARPS");
     pl.warps = (e && atoi(e) == 4) ? 4 : 1;
   }
+  if (pl.impl == 2) pl.warps = 1;
   if (pl.warps == 1) {
     // one warp per CTA: every warp is its own split; ~6 CTAs/SM run at independent phases
     const int n_tiles = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
@@ -873,6 +1212,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     if ((n_tiles + tps - 1) / tps > 256) tps = (n_tiles + 255) / 256;  // > 128K tokens: W=4 path
     if (tps > ATT_TPS_W1) {
       pl.warps = 4;
+      if (pl.impl == 2) pl.impl = 1;  // > 128K tokens: CTA-per-item kernel with 4-warp CTAs
     } else {
       pl.tps = tps;
       pl.n_splits = (n_tiles + tps - 1) / tps;
@@ -899,7 +1239,20 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
                        const AttnPlan& pl, int64_t batch, cudaStream_t st) {
   constexpr size_t smem = attn_smem_bytes<T, D>();
   int rc;
-  if (pl.impl == 1 && pl.warps == 1) {
+  if (pl.impl == 2) {
+    constexpr size_t psmem = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
+                             2 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
+    auto kernel = paged_attn_persist_kernel<T, D>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    const int64_t n_items = (int64_t)p.n_splits * pl.grid_y * pl.grid_z;
+    const int per_sm = D <= 128 ? 7 : 3;
+    const int64_t max_ctas = (int64_t)sm_count() * per_sm;
+    const unsigned grid = (unsigned)(n_items < max_ctas ? n_items : max_ctas);
+    B200_CUDA_OK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
+    kernel<<<grid, 32, psmem, st>>>(kmap, vmap, p, p.work_counter, (int)n_items);
+    B200_LAUNCH_OK("paged_attn_persist");
+    rc = B200_OK;
+  } else if (pl.impl == 1 && pl.warps == 1) {
     rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,
                        vmap, p, pl, st);
   } else if (pl.impl == 1) {
@@ -946,7 +1299,7 @@ int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_
   const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
                                 (int)n_kv_heads, (int)head_dim);
   const int n_splits = pl.n_splits;
-  if (n_splits <= 1) return 0;
+  if (n_splits <= 1) return pl.impl == 2 ? 256 : 0;  // the persistent kernel keeps its counter here
   // worst case over env overrides: size for the planned split count
   return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
 }
@@ -1014,14 +1367,22 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
   }
   p.n_splits = pl.n_splits;
   p.tiles_per_split = pl.tps;
+  // workspace layout: [256 B: persistent kernel's work counter][split-KV partial O][partial LSE]
+  const int64_t hdr = pl.impl == 2 ? 256 : 0;
+  if (pl.impl == 2) {
+    if (!workspace || workspace_bytes < hdr)
+      return set_error(B200_ERR_WORKSPACE, "paged_attn: workspace (>= 256 B) required");
+    B200_CHECK_ARG(is_aligned(workspace, 16), "paged_attn: workspace must be 16-byte aligned");
+    p.work_counter = static_cast<int*>(workspace);
+  }
   if (p.n_splits > 1) {
     const int64_t rows = batch * max_q_len * n_heads * p.n_splits;
-    const int64_t need = rows * (head_dim + 1) * (int64_t)sizeof(float);
+    const int64_t need = hdr + rows * (head_dim + 1) * (int64_t)sizeof(float);
     if (!workspace || workspace_bytes < need)
       return set_error(B200_ERR_WORKSPACE, "paged_attn: workspace %lld B < required %lld B",
                        (long long)workspace_bytes, (long long)need);
     B200_CHECK_ARG(is_aligned(workspace, 16), "paged_attn: workspace must be 16-byte aligned");
-    p.ws_o = static_cast<float*>(workspace);
+    p.ws_o = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + hdr);
     p.ws_lse = p.ws_o + rows * head_dim;
   }
 

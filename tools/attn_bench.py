@@ -43,11 +43,13 @@ def one_shape(B, S, H, Hkv, D):
         for kc, vc in caches[:3]:
             launch(kc, vc)
         torch.cuda.synchronize()
-        configs = [("W4 auto", {"B200_ATTN_WARPS": "4"}), ("W4 s=2", {"B200_ATTN_WARPS": "4", "B200_ATTN_SPLITS": "2"}),
-                   ("W1 tps=8", {"B200_ATTN_TPS": "8"}), ("W1 tps=16", {"B200_ATTN_TPS": "16"}),
-                   ("W1 tps=32", {"B200_ATTN_TPS": "32"})]
+        configs = [("mma W4 s=2", {"B200_ATTN_IMPL": "mma", "B200_ATTN_WARPS": "4", "B200_ATTN_SPLITS": "2"}),
+                   ("mma W1 t32", {"B200_ATTN_IMPL": "mma", "B200_ATTN_TPS": "32"}),
+                   ("persist t8", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "8"}),
+                   ("persist t16", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "16"}),
+                   ("persist t32", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "32"})]
         for tag, env in configs:
-            for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS"):
+            for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             launch(*caches[0])
@@ -61,27 +63,11 @@ def one_shape(B, S, H, Hkv, D):
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (3 * L)
             byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
-            print(f"attn impl={impl} bs={bs} {tag:10s}: {us:7.1f} us/launch "
+            print(f"attn bs={bs} {tag:12s}: {us:7.1f} us/launch "
                   f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
                   flush=True)
-        for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS"):
+        for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
             os.environ.pop(k, None)
-        os.environ.pop("B200_ATTN_SPLITS", None)
-            launch(*caches[0])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                for kc, vc in caches:
-                    launch(kc, vc)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / (3 * L)
-            byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
-            print(f"attn impl={impl} bs={bs} splits={splits or 'auto'}: {us:7.1f} us/launch "
-                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
-                  flush=True)
-        os.environ.pop("B200_ATTN_SPLITS", None)
 
 
 if __name__ == "__main__":
