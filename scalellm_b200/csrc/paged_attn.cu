@@ -1205,7 +1205,17 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     // one warp per CTA: every warp is its own split; ~6 CTAs/SM run at independent phases
     const int n_tiles = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
     const char* e = getenv("B200_ATTN_TPS");
-    int tps = (e && atoi(e) > 0) ? atoi(e) : 16;
+    int tps = 8;
+    if (e && atoi(e) > 0) {
+      tps = atoi(e);
+    } else {
+      // largest chunk (fewest per-item claims) that still leaves >= 2 items per resident warp
+      const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? 7 : 3);
+      for (int cand : {32, 16, 8}) {
+        tps = cand;
+        if (pl.grid_y * pl.grid_z * ((n_tiles + cand - 1) / cand) >= 2 * warps_resident) break;
+      }
+    }
     tps = std::max(1, std::min(tps, ATT_TPS_W1));
     // keep the split count (workspace + combine cost) bounded for very long contexts
     while ((n_tiles + tps - 1) / tps > 64 && tps < ATT_TPS_W1) tps *= 2;
