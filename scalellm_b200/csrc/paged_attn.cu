@@ -711,13 +711,18 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
 
+constexpr int ATT_P_NT = 4;  // block-table entries a lane carries in registers (<= 128 per item)
+
+// One work item moving through the claim pipeline.  A stage runs once per rotation, so every
+// dependent global access (atomic -> lengths -> block table) has a whole item's duration to land.
 struct ItemMeta {
+  int valid;                       // 0 = past the end of the work list
   int b, kvh, rb, split;
-  int q_begin, q_len, kv_len;
-  int t0, n_tiles;     // first tile, number of tiles (0 = nothing to do)
-  int kv_end, kv_begin;
-  int blk_first;
-  int valid;           // 0 = no more work
+  int q_begin, q_end, kv_b0, kv_b1, blk_cu;  // stage A: raw lengths
+  int q_len, kv_len;
+  int t0, n_tiles;                 // stage B: tile range (n_tiles = 0: nothing to attend to)
+  int kv_end, kv_begin, blk_first, n_ent;
+  int32_t ent[ATT_P_NT];           // stage B: block-table window (lane-striped), stored in stage C
 };
 
 template <typename T, int D>
@@ -744,56 +749,68 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     prefetch_tensormap(&vmap);
   }
 
-  // ---- claim + describe a work item (all lanes compute the same values) -----------------
-  auto claim = [&](int tbl_buf) -> ItemMeta {
-    ItemMeta it{};
-    for (;;) {
-      int id = 0;
-      if (lane == 0) id = atomicAdd(work_counter, 1);
-      id = __shfl_sync(0xffffffffu, id, 0);
-      if (id >= n_items) {
-        it.valid = 0;
-        return it;
-      }
-      it.valid = 1;
-      it.split = id % p.n_splits;
-      int rest = id / p.n_splits;
-      it.kvh = rest % p.n_kv_heads;
-      rest /= p.n_kv_heads;
-      it.rb = rest % p.n_rb;
-      it.b = rest / p.n_rb;
-      it.q_begin = p.q_cu_lens[it.b];
-      it.q_len = p.q_cu_lens[it.b + 1] - it.q_begin;
-      it.kv_len = p.kv_cu_lens[it.b + 1] - p.kv_cu_lens[it.b];
-      const int rows_total = it.q_len * G, row0 = it.rb * 16;
-      if (row0 >= rows_total) continue;  // padded row block of a short sequence: nothing to write
-      const int n_rows = min(16, rows_total - row0);
-      const int q_pos0 = it.kv_len - it.q_len;
-      const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
-      it.kv_end = q_pos0 + qi_max + 1;
-      it.kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
-      int t0 = it.split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
-      t0 = max(t0, it.kv_begin / ATT_TILE);
-      t1 = min(t1, (it.kv_end + ATT_TILE - 1) / ATT_TILE);
-      if (t0 >= t1) {  // empty split: publish LSE = -inf for its rows and take the next item
-        if (p.n_splits > 1 && lane < n_rows) {
-          const int row = row0 + lane, qi = row / G, head = it.kvh * G + (row - qi * G);
-          p.ws_lse[(((int64_t)it.b * p.max_q_len + qi) * p.n_heads + head) * p.n_splits + it.split] =
-              -INFINITY;
-        }
-        continue;
-      }
-      it.t0 = t0;
-      it.n_tiles = t1 - t0;
-      it.blk_first = (t0 * ATT_TILE) >> p.block_shift;
-      const int blk_last = (min(t1 * ATT_TILE, it.kv_end) - 1) >> p.block_shift;
-      const int blk_cu = p.block_cu_lens[it.b];
-      int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
-      for (int i = lane; i <= blk_last - it.blk_first; i += 32)
-        tbl[i] = p.block_table[blk_cu + it.blk_first + i];
-      __syncwarp();
-      return it;
+  // ---- claim pipeline stages --------------------------------------------------------------
+  auto stage0 = [&]() -> int {  // issue the claim; the result is consumed one rotation later
+    int id = 0;
+    if (lane == 0) id = atomicAdd(work_counter, 1);
+    return id;
+  };
+  auto stageA = [&](int raw_id) -> ItemMeta {  // decode + issue the length loads
+    ItemMeta it;
+    const int id = __shfl_sync(0xffffffffu, raw_id, 0);
+    it.valid = id < n_items;
+    const int idc = it.valid ? id : 0;
+    it.split = idc % p.n_splits;
+    int rest = idc / p.n_splits;
+    it.kvh = rest % p.n_kv_heads;
+    rest /= p.n_kv_heads;
+    it.rb = rest % p.n_rb;
+    it.b = rest / p.n_rb;
+    it.q_begin = p.q_cu_lens[it.b];
+    it.q_end = p.q_cu_lens[it.b + 1];
+    it.kv_b0 = p.kv_cu_lens[it.b];
+    it.kv_b1 = p.kv_cu_lens[it.b + 1];
+    it.blk_cu = p.block_cu_lens[it.b];
+    it.n_tiles = 0;
+    return it;
+  };
+  auto stageB = [&](ItemMeta& it) {  // tile range + issue the block-table loads
+    it.q_len = it.q_end - it.q_begin;
+    it.kv_len = it.kv_b1 - it.kv_b0;
+    it.n_tiles = 0;
+    it.n_ent = 0;
+    const int rows_total = it.q_len * G, row0 = it.rb * 16;
+    if (!it.valid || row0 >= rows_total) {
+      it.q_len = it.valid ? it.q_len : 0;
+      return;
     }
+    const int n_rows = min(16, rows_total - row0);
+    const int q_pos0 = it.kv_len - it.q_len;
+    const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
+    it.kv_end = q_pos0 + qi_max + 1;
+    it.kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
+    int t0 = it.split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
+    t0 = max(t0, it.kv_begin / ATT_TILE);
+    t1 = min(t1, (it.kv_end + ATT_TILE - 1) / ATT_TILE);
+    if (t0 >= t1) return;
+    it.t0 = t0;
+    it.n_tiles = t1 - t0;
+    it.blk_first = (t0 * ATT_TILE) >> p.block_shift;
+    it.n_ent = ((min(t1 * ATT_TILE, it.kv_end) - 1) >> p.block_shift) - it.blk_first + 1;
+#pragma unroll
+    for (int j = 0; j < ATT_P_NT; ++j) {
+      const int e = lane + 32 * j;
+      it.ent[j] = e < it.n_ent ? p.block_table[it.blk_cu + it.blk_first + e] : 0;
+    }
+  };
+  auto stageC = [&](const ItemMeta& it, int tbl_buf) {  // block-table window -> shared memory
+    int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
+#pragma unroll
+    for (int j = 0; j < ATT_P_NT; ++j) {
+      const int e = lane + 32 * j;
+      if (e < it.n_ent) tbl[e] = it.ent[j];
+    }
+    __syncwarp();
   };
 
   // TMA for tile `ti` of item `it` into ring slot of stream position `g`
@@ -822,8 +839,9 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = (lane >> 2) + 8 * h;
-      const bool ok = r < n_rows;
-      const int row = row0 + (ok ? r : 0), qi = row / G, head = it.kvh * G + (row - qi * G);
+      const bool ok = it.n_tiles > 0 && r < n_rows;
+      const int row = row0 + (ok ? r : 0), qi = ok ? row / G : 0;
+      const int head = it.kvh * G + (ok ? row - qi * G : 0);
       const T* qrow = static_cast<const T*>(p.q) + (int64_t)(it.q_begin + qi) * p.q_stride_t +
                       (int64_t)head * p.q_stride_h + (lane & 3) * 2;
 #pragma unroll
@@ -834,13 +852,22 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     }
   };
 
-  ItemMeta cur = claim(0);
-  if (!cur.valid) return;
+  // ---- fill the pipeline (only here are the dependent latencies exposed) ----------------------
+  ItemMeta cur = stageA(stage0());
+  stageB(cur);
   int cur_buf = 0;
-  ItemMeta nxt = claim(1);
+  stageC(cur, cur_buf);
+  if (!cur.valid) return;
+  ItemMeta nxt = stageA(stage0());
+  stageB(nxt);
+  stageC(nxt, cur_buf ^ 1);
+  ItemMeta sB = stageA(stage0());   // lengths loaded, table not yet requested
+  stageB(sB);
+  ItemMeta sA = stageA(stage0());
+  int s0 = stage0();
   uint32_t qa[KS][4], qn[KS][4];
   load_q(cur, qa);
-  if (nxt.valid) load_q(nxt, qn);
+  load_q(nxt, qn);
 
   int g_cons = 0, g_iss = 0;         // stream positions (tiles consumed / issued)
   int cur_issued = 0, nxt_issued = 0;
@@ -880,13 +907,20 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     float slope_log2[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      slope_log2[h] = p.alibi ? p.alibi[row_head[h]] * 1.4426950408889634f : 0.f;
+      slope_log2[h] = (p.alibi && cur.n_tiles > 0) ? p.alibi[row_head[h]] * 1.4426950408889634f : 0.f;
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     float o[NB][4];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
+
+    if (cur.n_tiles == 0 && p.n_splits > 1 && n_rows > 0 && lane < n_rows) {
+      // empty split of a real row block: its rows still need an LSE the combine pass can skip
+      const int row = row0 + lane, qi = row / G, head = cur.kvh * G + (row - qi * G);
+      p.ws_lse[(((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head) * p.n_splits + cur.split] =
+          -INFINITY;
+    }
 
     for (int i = 0; i < cur.n_tiles; ++i) {
       const int s = g_cons % STAGES;
@@ -994,7 +1028,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
       l[h] += __shfl_xor_sync(0xffffffffu, l[h], 2);
       const int r = (lane >> 2) + 8 * h;
-      if (r < n_rows) {
+      if (cur.n_tiles > 0 && r < n_rows) {
         const int row = row0 + r, qi = row / G, head = cur.kvh * G + (row - qi * G);
         const float inv = 1.f / l[h];
         if (p.n_splits == 1) {
@@ -1016,7 +1050,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       }
     }
 
-    // ---- rotate: next becomes current, claim and prefetch a new next ----------------------
+    // ---- rotate: every pipeline slot advances one stage ---------------------------------------
     cur = nxt;
     cur_buf ^= 1;
     cur_issued = nxt_issued;
@@ -1026,7 +1060,12 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int e = 0; e < 4; ++e) qa[ks][e] = qn[ks][e];
-      nxt = claim(cur_buf ^ 1);
+      nxt = sB;                       // its block-table loads were issued one rotation ago
+      stageC(nxt, cur_buf ^ 1);
+      sB = sA;                        // its length loads were issued one rotation ago
+      stageB(sB);
+      sA = stageA(s0);                // its atomic was issued one rotation ago
+      s0 = stage0();
       if (nxt.valid) load_q(nxt, qn);
       issue_ahead();
     }
@@ -1177,7 +1216,7 @@ struct AttnPlan {
 };
 
 static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads,
-                          int n_kv_heads, int head_dim) {
+                          int n_kv_heads, int head_dim, int block_size) {
   AttnPlan pl{};
   pl.impl = attn_impl();
   const int group = n_heads / n_kv_heads;
@@ -1209,13 +1248,16 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     if (e && atoi(e) > 0) {
       tps = atoi(e);
     } else {
-      // largest chunk (fewest per-item claims) that still leaves >= 2 items per resident warp
+      // largest chunk that still gives every resident warp >= 8 items (dynamic balance within
+      // ~1/8 of a warp's work); claims are software pipelined, so small items are cheap
       const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? 7 : 3);
       for (int cand : {32, 16, 8}) {
         tps = cand;
-        if (pl.grid_y * pl.grid_z * ((n_tiles + cand - 1) / cand) >= 2 * warps_resident) break;
+        if (pl.grid_y * pl.grid_z * ((n_tiles + cand - 1) / cand) >= 8 * warps_resident) break;
       }
     }
+    // the persistent kernel carries <= 128 block-table entries per item in registers
+    if (pl.impl == 2) tps = std::min(tps, std::max(1, 8 * block_size));
     tps = std::max(1, std::min(tps, ATT_TPS_W1));
     // keep the split count (workspace + combine cost) bounded for very long contexts
     while ((n_tiles + tps - 1) / tps > 64 && tps < ATT_TPS_W1) tps *= 2;
@@ -1306,8 +1348,9 @@ int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_
                                         int64_t n_heads, int64_t n_kv_heads, int64_t head_dim) {
   if (batch <= 0 || max_q_len <= 0 || n_heads <= 0 || n_kv_heads <= 0) return 0;
   if (n_heads % n_kv_heads) return 0;
+  // block_size is not part of this query: assume 1 (the smallest chunks = the most splits)
   const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
-                                (int)n_kv_heads, (int)head_dim);
+                                (int)n_kv_heads, (int)head_dim, 1);
   const int n_splits = pl.n_splits;
   if (n_splits <= 1) return pl.impl == 2 ? 256 : 0;  // the persistent kernel keeps its counter here
   // worst case over env overrides: size for the planned split count
@@ -1342,7 +1385,7 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
 
   const int group = (int)(n_heads / n_kv_heads);
   const AttnPlan pl = make_plan(batch, max_q_len, max_kv_len, (int)n_heads, (int)n_kv_heads,
-                                (int)head_dim);
+                                (int)head_dim, block_size);
   AttnParams p{};
   p.q = q;
   p.out = out;

@@ -15,16 +15,22 @@ DEV = "cuda"
 
 def main():
     shapes = [(64, 2048, 32, 8, 128)]
+    if len(sys.argv) > 1 and sys.argv[1] == "ragged":
+        # bench.py's situation: kv_len not a multiple of 16 and max_kv_len > kv_len
+        one_shape(64, 2071, 32, 8, 128, max_kv=2102, bss=(8,))
+        one_shape(64, 2071, 32, 8, 128, max_kv=2071, bss=(8,))
+        one_shape(64, 2064, 32, 8, 128, max_kv=2064, bss=(8,))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "locality":
         shapes = [(64, 2048, 32, 8, 128), (512, 2048, 4, 1, 128), (128, 2048, 16, 4, 128)]
     for shp in shapes:
         one_shape(*shp)
 
 
-def one_shape(B, S, H, Hkv, D):
-    impl = os.environ.get("B200_ATTN_IMPL", "mma")
-    print(f"--- B={B} S={S} H={H} Hkv={Hkv} D={D}")
-    for bs in (8, 128):
+def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
+    max_kv = max_kv or S
+    print(f"--- B={B} S={S} max_kv={max_kv} H={H} Hkv={Hkv} D={D}")
+    for bs in bss:
         nblk = (S + bs - 1) // bs
         n_blocks = B * nblk + 8
         L = 10
@@ -38,7 +44,7 @@ def one_shape(B, S, H, Hkv, D):
         out = torch.empty_like(q)
 
         def launch(kc, vc):
-            kernels.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, 1, S,
+            kernels.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, 1, max_kv,
                                         D ** -0.5, 0.0, -1)
         for kc, vc in caches[:3]:
             launch(kc, vc)
@@ -47,7 +53,8 @@ def one_shape(B, S, H, Hkv, D):
                    ("mma W1 t32", {"B200_ATTN_IMPL": "mma", "B200_ATTN_TPS": "32"}),
                    ("persist t8", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "8"}),
                    ("persist t16", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "16"}),
-                   ("persist t32", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "32"})]
+                   ("persist t32", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "32"}),
+                   ("persist auto", {"B200_ATTN_IMPL": "persist"})]
         for tag, env in configs:
             for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
                 os.environ.pop(k, None)
