@@ -49,7 +49,10 @@ struct AttnParams {
   int block_shift, block_mask, box_rows, boxes_per_tile;
   int max_q_len, n_splits, tiles_per_split;
   int n_rb;           // mma kernel: 16-row blocks of the packed (q token, group) rows
-  int* work_counter;  // persistent kernel: global work-item counter (zeroed before each launch)
+  int* work_counter;  // (unused by the stream kernel; kept for ABI of the params block)
+  int ntm;            // stream kernel: padded tiles per (sequence, row block, kv head)
+  int tpw;            // stream kernel: tiles per warp (static partition of the padded tile stream)
+  int stream;         // 1: split index = piece of the static stream partition (combine mirrors it)
   float scale_log2;   // sm_scale * log2(e)            (soft_cap == 0)
   float cap_in;       // sm_scale / soft_cap           (soft_cap  > 0)
   float cap_out_log2; // soft_cap * log2(e)
@@ -701,12 +704,15 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 
 
 // ===========================================================================
-// Persistent variant of the tensor-core kernel: one warp per CTA, each warp pulls work items
-// (sequence x row-block x kv head x kv chunk) from a global counter and keeps ONE continuous TMA
-// ring across items — while it drains item i it has already fetched item i+1's lengths, block
-// table window and query fragments and is issuing item i+1's first tiles, so there is no
-// per-item prologue bubble and no wave tail.  Every item is a split of its (sequence, head):
-// partial O / LSE go to the workspace and the combine kernel merges them.
+// Stream variant of the tensor-core kernel (default): one warp per CTA and a STATIC, equal
+// partition of the padded tile stream — the concatenation over (sequence, row block, kv head) of
+// n_tiles_max tiles each; warp w owns stream positions [w*tpw, (w+1)*tpw).  Every warp therefore
+// streams the same number of KV tiles (stream-K for attention): no work counter, no wave tail,
+// a handful of pieces per warp.  A piece (warp range x one sequence) is a split of that sequence;
+// the warp keeps ONE continuous TMA ring across its pieces and runs the lengths -> block table
+// -> shared memory prefetch of the following pieces one stage per rotation, so the dependent
+// global accesses are off the critical path.  Partial O / LSE go to the workspace; the combine
+// pass recomputes the same partition to know which pieces exist.
 // ===========================================================================
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
@@ -721,6 +727,7 @@ struct ItemMeta {
   int q_begin, q_end, kv_b0, kv_b1, blk_cu;  // stage A: raw lengths
   int q_len, kv_len;
   int t0, n_tiles;                 // stage B: tile range (n_tiles = 0: nothing to attend to)
+  int t_hi;                        // stage A: end of this piece's window inside its sequence
   int kv_end, kv_begin, blk_first, n_ent;
   int32_t ent[ATT_P_NT];           // stage B: block-table window (lane-striped), stored in stage C
 };
@@ -729,7 +736,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(32, (D <= 128 ? 8 : 3))
 paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                           const __grid_constant__ CUtensorMap vmap, const AttnParams p,
-                          int* __restrict__ work_counter, int n_items) {
+                          int64_t total_tiles, int n_seq) {
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KS = D / 16, NB = D / 8;
@@ -737,6 +744,11 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
   int32_t* tbl_base = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * 2 * Cfg::TILE_ELEMS * sizeof(T));
+  // this warp's slice of the padded tile stream
+  const int64_t g0 = (int64_t)blockIdx.x * p.tpw;
+  const int64_t g1 = g0 + p.tpw < total_tiles ? g0 + p.tpw : total_tiles;
+  if (g0 >= g1) return;
+  const int seq_first = (int)(g0 / p.ntm), seq_last = (int)((g1 - 1) / p.ntm);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 2 * ATT_P_TBL);
   const int lane = threadIdx.x;
   const int G = p.group;
@@ -750,22 +762,21 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   }
 
   // ---- claim pipeline stages --------------------------------------------------------------
-  auto stage0 = [&]() -> int {  // issue the claim; the result is consumed one rotation later
-    int id = 0;
-    if (lane == 0) id = atomicAdd(work_counter, 1);
-    return id;
-  };
-  auto stageA = [&](int raw_id) -> ItemMeta {  // decode + issue the length loads
+  int next_seq = seq_first;
+  auto stage0 = [&]() -> int { return next_seq++; };  // pieces are the sequences the slice touches
+  auto stageA = [&](int seq) -> ItemMeta {  // decode + issue the length loads
     ItemMeta it;
-    const int id = __shfl_sync(0xffffffffu, raw_id, 0);
-    it.valid = id < n_items;
-    const int idc = it.valid ? id : 0;
-    it.split = idc % p.n_splits;
-    int rest = idc / p.n_splits;
-    it.kvh = rest % p.n_kv_heads;
-    rest /= p.n_kv_heads;
+    it.valid = seq <= seq_last;
+    const int sc = it.valid ? seq : seq_first;
+    it.kvh = sc % p.n_kv_heads;
+    int rest = sc / p.n_kv_heads;
     it.rb = rest % p.n_rb;
     it.b = rest / p.n_rb;
+    // tile window of this piece inside its sequence, and which piece of the sequence it is
+    const int64_t base = (int64_t)sc * p.ntm;
+    it.t0 = (int)((g0 > base ? g0 : base) - base);
+    it.t_hi = (int)((g1 < base + p.ntm ? g1 : base + p.ntm) - base);
+    it.split = (int)((base + it.t0) / p.tpw - base / p.tpw);
     it.q_begin = p.q_cu_lens[it.b];
     it.q_end = p.q_cu_lens[it.b + 1];
     it.kv_b0 = p.kv_cu_lens[it.b];
@@ -777,6 +788,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   auto stageB = [&](ItemMeta& it) {  // tile range + issue the block-table loads
     it.q_len = it.q_end - it.q_begin;
     it.kv_len = it.kv_b1 - it.kv_b0;
+    const int t_lo = it.t0, t_hi = it.t_hi;
     it.n_tiles = 0;
     it.n_ent = 0;
     const int rows_total = it.q_len * G, row0 = it.rb * 16;
@@ -789,9 +801,8 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
     it.kv_end = q_pos0 + qi_max + 1;
     it.kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
-    int t0 = it.split * p.tiles_per_split, t1 = t0 + p.tiles_per_split;
-    t0 = max(t0, it.kv_begin / ATT_TILE);
-    t1 = min(t1, (it.kv_end + ATT_TILE - 1) / ATT_TILE);
+    const int t0 = max(t_lo, it.kv_begin / ATT_TILE);
+    const int t1 = min(t_hi, (it.kv_end + ATT_TILE - 1) / ATT_TILE);
     if (t0 >= t1) return;
     it.t0 = t0;
     it.n_tiles = t1 - t0;
@@ -914,13 +925,6 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
-
-    if (cur.n_tiles == 0 && p.n_splits > 1 && n_rows > 0 && lane < n_rows) {
-      // empty split of a real row block: its rows still need an LSE the combine pass can skip
-      const int row = row0 + lane, qi = row / G, head = cur.kvh * G + (row - qi * G);
-      p.ws_lse[(((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head) * p.n_splits + cur.split] =
-          -INFINITY;
-    }
 
     for (int i = 0; i < cur.n_tiles; ++i) {
       const int s = g_cons % STAGES;
@@ -1079,18 +1083,46 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
   const int h = blockIdx.x;
   const int b = blockIdx.y / p.max_q_len, qi = blockIdx.y % p.max_q_len;
   const int q_begin = p.q_cu_lens[b];
-  if (qi >= p.q_cu_lens[b + 1] - q_begin) return;
+  const int q_len = p.q_cu_lens[b + 1] - q_begin;
+  if (qi >= q_len) return;
   const int64_t tok = q_begin + qi;
   const int64_t row = (int64_t)blockIdx.y * p.n_heads + h;
   const float* lse = p.ws_lse + row * p.n_splits;
+  // which split slots hold a piece?  fixed-split kernels publish every slot; the stream kernel
+  // only writes pieces that exist, so mirror its static partition here.
+  uint64_t present[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  if (p.stream) {
+    present[0] = present[1] = present[2] = present[3] = 0;
+    const int G = p.group, kvh = h / G, g = h - kvh * G;
+    const int r = qi * G + g, rb = r / 16;
+    const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+    const int rows_total = q_len * G, row0 = rb * 16, n_rows = min(16, rows_total - row0);
+    const int q_pos0 = kv_len - q_len, qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
+    const int kv_end = q_pos0 + qi_max + 1;
+    const int kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
+    const int64_t seq = ((int64_t)b * p.n_rb + rb) * p.n_kv_heads + kvh;
+    const int64_t base = seq * p.ntm, first_piece = base / p.tpw;
+    for (int s = 0; s < p.n_splits; ++s) {
+      const int64_t lo = max(base, (first_piece + s) * p.tpw);
+      const int64_t hi = min(base + p.ntm, (first_piece + s + 1) * p.tpw);
+      if (lo >= hi) continue;
+      const int t0 = max((int)(lo - base), kv_begin / ATT_TILE);
+      const int t1 = min((int)(hi - base), (kv_end + ATT_TILE - 1) / ATT_TILE);
+      if (t0 < t1) present[s >> 6] |= 1ull << (s & 63);
+    }
+  }
+  auto has = [&](int s) { return (present[s >> 6] >> (s & 63)) & 1ull; };
   float M = -INFINITY;
-  for (int s = 0; s < p.n_splits; ++s) M = fmaxf(M, lse[s]);
+  for (int s = 0; s < p.n_splits; ++s)
+    if (has(s)) M = fmaxf(M, lse[s]);
   float L = 0.f;
-  for (int s = 0; s < p.n_splits; ++s) L += exp2f(lse[s] - M);
+  for (int s = 0; s < p.n_splits; ++s)
+    if (has(s)) L += exp2f(lse[s] - M);
   const float inv = 1.f / L;
   for (int d = threadIdx.x; d < D; d += 128) {
     float o = 0.f;
     for (int s = 0; s < p.n_splits; ++s) {
+      if (!has(s)) continue;
       const float w = exp2f(lse[s] - M);
       if (w != 0.f) o = fmaf(p.ws_o[(row * p.n_splits + s) * D + d], w, o);
     }
@@ -1212,6 +1244,8 @@ static int attn_impl() {
 
 struct AttnPlan {
   int impl, R, n_hg, n_rb, n_splits, tps, warps;
+  int ntm, tpw, n_seq;       // stream kernel
+  int64_t total_tiles;
   int64_t grid_y, grid_z;
 };
 
@@ -1239,7 +1273,28 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     const char* e = getenv("B200_ATTN_WARPS");
     pl.warps = (e && atoi(e) == 4) ? 4 : 1;
   }
-  if (pl.impl == 2) pl.warps = 1;
+  if (pl.impl == 2) {
+    pl.warps = 1;
+    pl.ntm = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
+    pl.n_seq = (int)(pl.grid_y * pl.grid_z);
+    pl.total_tiles = (int64_t)pl.n_seq * pl.ntm;
+    const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? 7 : 3);
+    int64_t tpw = (pl.total_tiles + warps_resident - 1) / warps_resident;
+    const char* e = getenv("B200_ATTN_TPS");
+    if (e && atoi(e) > 0) tpw = atoi(e);
+    tpw = std::max<int64_t>(tpw, 8);                            // tiny problems: >= 128 slots per piece
+    tpw = std::min<int64_t>(tpw, std::max(1, 8 * block_size));  // <= 128 block-table entries per piece
+    tpw = std::min<int64_t>(tpw, 4096);
+    pl.tpw = (int)tpw;
+    pl.n_splits = (pl.ntm + pl.tpw - 1) / pl.tpw + 1;           // pieces one sequence can be cut into
+    if (pl.n_splits > 256) {                                    // absurdly long context with tiny blocks
+      pl.impl = 1;
+      pl.warps = 4;
+    } else {
+      pl.tps = pl.tpw;
+      return pl;
+    }
+  }
   if (pl.warps == 1) {
     // one warp per CTA: every warp is its own split; ~6 CTAs/SM run at independent phases
     const int n_tiles = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
@@ -1296,13 +1351,9 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
                              2 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
     auto kernel = paged_attn_persist_kernel<T, D>;
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    const int64_t n_items = (int64_t)p.n_splits * pl.grid_y * pl.grid_z;
-    const int per_sm = D <= 128 ? 7 : 3;
-    const int64_t max_ctas = (int64_t)sm_count() * per_sm;
-    const unsigned grid = (unsigned)(n_items < max_ctas ? n_items : max_ctas);
-    B200_CUDA_OK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
-    kernel<<<grid, 32, psmem, st>>>(kmap, vmap, p, p.work_counter, (int)n_items);
-    B200_LAUNCH_OK("paged_attn_persist");
+    const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
+    kernel<<<grid, 32, psmem, st>>>(kmap, vmap, p, pl.total_tiles, pl.n_seq);
+    B200_LAUNCH_OK("paged_attn_stream");
     rc = B200_OK;
   } else if (pl.impl == 1 && pl.warps == 1) {
     rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,
@@ -1352,7 +1403,7 @@ int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_
   const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
                                 (int)n_kv_heads, (int)head_dim, 1);
   const int n_splits = pl.n_splits;
-  if (n_splits <= 1) return pl.impl == 2 ? 256 : 0;  // the persistent kernel keeps its counter here
+  if (n_splits <= 1) return 0;
   // worst case over env overrides: size for the planned split count
   return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
 }
@@ -1420,14 +1471,11 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
   }
   p.n_splits = pl.n_splits;
   p.tiles_per_split = pl.tps;
+  p.ntm = pl.ntm;
+  p.tpw = pl.tpw;
+  p.stream = pl.impl == 2 ? 1 : 0;
   // workspace layout: [256 B: persistent kernel's work counter][split-KV partial O][partial LSE]
-  const int64_t hdr = pl.impl == 2 ? 256 : 0;
-  if (pl.impl == 2) {
-    if (!workspace || workspace_bytes < hdr)
-      return set_error(B200_ERR_WORKSPACE, "paged_attn: workspace (>= 256 B) required");
-    B200_CHECK_ARG(is_aligned(workspace, 16), "paged_attn: workspace must be 16-byte aligned");
-    p.work_counter = static_cast<int*>(workspace);
-  }
+  const int64_t hdr = 0;
   if (p.n_splits > 1) {
     const int64_t rows = batch * max_q_len * n_heads * p.n_splits;
     const int64_t need = hdr + rows * (head_dim + 1) * (int64_t)sizeof(float);

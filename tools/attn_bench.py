@@ -50,11 +50,8 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
             launch(kc, vc)
         torch.cuda.synchronize()
         configs = [("mma W4 s=2", {"B200_ATTN_IMPL": "mma", "B200_ATTN_WARPS": "4", "B200_ATTN_SPLITS": "2"}),
-                   ("mma W1 t32", {"B200_ATTN_IMPL": "mma", "B200_ATTN_TPS": "32"}),
-                   ("persist t8", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "8"}),
-                   ("persist t16", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "16"}),
-                   ("persist t32", {"B200_ATTN_IMPL": "persist", "B200_ATTN_TPS": "32"}),
-                   ("persist auto", {"B200_ATTN_IMPL": "persist"})]
+                   ("stream t32", {"B200_ATTN_TPS": "32"}),
+                   ("stream auto", {})]
         for tag, env in configs:
             for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
                 os.environ.pop(k, None)
