@@ -717,7 +717,6 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
 
-constexpr int ATT_P_NT = 4;  // block-table entries a lane carries in registers (<= 128 per item)
 
 // One work item moving through the claim pipeline.  A stage runs once per rotation, so every
 // dependent global access (atomic -> lengths -> block table) has a whole item's duration to land.
@@ -729,7 +728,7 @@ struct ItemMeta {
   int t0, n_tiles;                 // stage B: tile range (n_tiles = 0: nothing to attend to)
   int t_hi;                        // stage A: end of this piece's window inside its sequence
   int kv_end, kv_begin, blk_first, n_ent;
-  int32_t ent[ATT_P_NT];           // stage B: block-table window (lane-striped), stored in stage C
+  int tbl_buf;                     // stage B: which of the 3 table buffers holds its window
 };
 
 template <typename T, int D>
@@ -749,7 +748,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   const int64_t g1 = g0 + p.tpw < total_tiles ? g0 + p.tpw : total_tiles;
   if (g0 >= g1) return;
   const int seq_first = (int)(g0 / p.ntm), seq_last = (int)((g1 - 1) / p.ntm);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 2 * ATT_P_TBL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 3 * ATT_P_TBL);
   const int lane = threadIdx.x;
   const int G = p.group;
 
@@ -763,6 +762,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 
   // ---- claim pipeline stages --------------------------------------------------------------
   int next_seq = seq_first;
+  int tbl_rot = 0;  // rotating table buffer index (3 buffers: current, next, the one being filled)
   auto stage0 = [&]() -> int { return next_seq++; };  // pieces are the sequences the slice touches
   auto stageA = [&](int seq) -> ItemMeta {  // decode + issue the length loads
     ItemMeta it;
@@ -808,28 +808,26 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     it.n_tiles = t1 - t0;
     it.blk_first = (t0 * ATT_TILE) >> p.block_shift;
     it.n_ent = ((min(t1 * ATT_TILE, it.kv_end) - 1) >> p.block_shift) - it.blk_first + 1;
-#pragma unroll
-    for (int j = 0; j < ATT_P_NT; ++j) {
-      const int e = lane + 32 * j;
-      it.ent[j] = e < it.n_ent ? p.block_table[it.blk_cu + it.blk_first + e] : 0;
-    }
+    // asynchronous copy of the block-table window: lands while the previous pieces are processed
+    it.tbl_buf = tbl_rot;
+    tbl_rot = tbl_rot == 2 ? 0 : tbl_rot + 1;
+    const uint32_t dst = smem_u32(tbl_base + it.tbl_buf * ATT_P_TBL);
+    const int32_t* src = p.block_table + it.blk_cu + it.blk_first;
+    for (int e = lane; e < it.n_ent; e += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + e * 4), "l"(src + e)
+                   : "memory");
   };
-  auto stageC = [&](const ItemMeta& it, int tbl_buf) {  // block-table window -> shared memory
-    int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
-#pragma unroll
-    for (int j = 0; j < ATT_P_NT; ++j) {
-      const int e = lane + 32 * j;
-      if (e < it.n_ent) tbl[e] = it.ent[j];
-    }
+  auto stageC = [&]() {  // every table window requested so far has landed
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
   };
 
   // TMA for tile `ti` of item `it` into ring slot of stream position `g`
-  auto issue = [&](const ItemMeta& it, int tbl_buf, int ti, int g) {  // lane 0 only
+  auto issue = [&](const ItemMeta& it, int ti, int g) {  // lane 0 only
     const int s = g % STAGES;
     T* ks = stage_base + (size_t)s * 2 * Cfg::TILE_ELEMS;
     T* vs = ks + Cfg::TILE_ELEMS;
-    const int32_t* tbl = tbl_base + tbl_buf * ATT_P_TBL;
+    const int32_t* tbl = tbl_base + it.tbl_buf * ATT_P_TBL;
     const int pos0 = (it.t0 + ti) * ATT_TILE;
     int nbox = 0;
     for (int bx = 0; bx < p.boxes_per_tile; ++bx)
@@ -866,15 +864,12 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   // ---- fill the pipeline (only here are the dependent latencies exposed) ----------------------
   ItemMeta cur = stageA(stage0());
   stageB(cur);
-  int cur_buf = 0;
-  stageC(cur, cur_buf);
-  if (!cur.valid) return;
   ItemMeta nxt = stageA(stage0());
   stageB(nxt);
-  stageC(nxt, cur_buf ^ 1);
-  ItemMeta sB = stageA(stage0());   // lengths loaded, table not yet requested
-  stageB(sB);
-  ItemMeta sA = stageA(stage0());
+  stageC();                         // cur's and nxt's table windows are in shared memory
+  ItemMeta sB = stageA(stage0());
+  stageB(sB);                       // its table window is in flight into the third buffer
+  ItemMeta sA = stageA(stage0());   // lengths in flight
   int s0 = stage0();
   uint32_t qa[KS][4], qn[KS][4];
   load_q(cur, qa);
@@ -885,10 +880,10 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   auto issue_ahead = [&]() {          // keep the ring full: current item first, then the next one
     while (g_iss - g_cons < STAGES) {
       if (cur_issued < cur.n_tiles) {
-        if (lane == 0) issue(cur, cur_buf, cur_issued, g_iss);
+        if (lane == 0) issue(cur, cur_issued, g_iss);
         ++cur_issued;
       } else if (nxt.valid && nxt_issued < nxt.n_tiles) {
-        if (lane == 0) issue(nxt, cur_buf ^ 1, nxt_issued, g_iss);
+        if (lane == 0) issue(nxt, nxt_issued, g_iss);
         ++nxt_issued;
       } else {
         break;
@@ -1056,7 +1051,6 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 
     // ---- rotate: every pipeline slot advances one stage ---------------------------------------
     cur = nxt;
-    cur_buf ^= 1;
     cur_issued = nxt_issued;
     nxt_issued = 0;
     if (cur.valid) {
@@ -1064,11 +1058,11 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int e = 0; e < 4; ++e) qa[ks][e] = qn[ks][e];
-      nxt = sB;                       // its block-table loads were issued one rotation ago
-      stageC(nxt, cur_buf ^ 1);
-      sB = sA;                        // its length loads were issued one rotation ago
-      stageB(sB);
-      sA = stageA(s0);                // its atomic was issued one rotation ago
+      stageC();                       // sB's table window (requested one rotation ago) has landed
+      nxt = sB;
+      sB = sA;                        // its lengths were requested one rotation ago
+      stageB(sB);                     // -> tile range known: request its table window (3rd buffer)
+      sA = stageA(s0);
       s0 = stage0();
       if (nxt.valid) load_q(nxt, qn);
       issue_ahead();
@@ -1283,7 +1277,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     const char* e = getenv("B200_ATTN_TPS");
     if (e && atoi(e) > 0) tpw = atoi(e);
     tpw = std::max<int64_t>(tpw, 8);                            // tiny problems: >= 128 slots per piece
-    tpw = std::min<int64_t>(tpw, std::max(1, 8 * block_size));  // <= 128 block-table entries per piece
+    tpw = std::min<int64_t>(tpw, std::max(1, (ATT_P_TBL - 8) * block_size / ATT_TILE));  // table window
     tpw = std::min<int64_t>(tpw, 4096);
     pl.tpw = (int)tpw;
     pl.n_splits = (pl.ntm + pl.tpw - 1) / pl.tpw + 1;           // pieces one sequence can be cut into
@@ -1348,7 +1342,7 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   int rc;
   if (pl.impl == 2) {
     constexpr size_t psmem = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
-                             2 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
+                             3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
     auto kernel = paged_attn_persist_kernel<T, D>;
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
