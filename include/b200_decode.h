@@ -232,6 +232,21 @@ B200_API int b200_w4a16_gemm(void* C, const void* A, const void* packed,
                              void* workspace, int64_t workspace_bytes,
                              b200_stream_t stream);
 
+/* Split-K "partials" mode (B200-native fusion of the GEMM's cross-CTA reduction into its consumer):
+ * every CTA owns (n tile, K slice) and writes its fp32 partial to partials[split][M][N]; the
+ * consumer (b200_rms_norm_residual_splitk) sums the `splits` partials in slice order, rounds once
+ * to the element type — exactly what the GEMM epilogue would have stored — and carries on.  Replaces
+ * the o_proj / down_proj + residual add + RMSNorm sequence of models/meta/llama.h:170-177.
+ * b200_w4a16_splitk_splits recommends a split count (n_tiles * splits <= #SMs).  M <= 128. */
+B200_API int b200_w4a16_splitk_splits(int64_t M, int64_t N, int64_t K);
+B200_API int b200_w4a16_gemm_splitk(float* partials, const void* A, const void* packed, int64_t M,
+                                    int64_t N, int64_t K, int64_t lda, int group_size, int splits,
+                                    b200_stream_t stream);
+/* residual += T(sum_s partials[s]); out = rms_norm(residual) * weight.  partials: [splits, rows, n] fp32. */
+B200_API int b200_rms_norm_residual_splitk(void* out, void* residual, const float* partials,
+                                           int splits, const void* weight, int64_t rows, int64_t n,
+                                           float eps, int dtype, b200_stream_t stream);
+
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
 B200_API void b200_debug_set_trace(void* device_buffer);

@@ -161,6 +161,104 @@ static int launch_rms_norm(void* out, void* residual, const void* in, const void
   return B200_OK;
 }
 
+
+// Residual RMSNorm whose `in` operand arrives as S split-K partials in fp32 (the W4A16 GEMM's
+// partial mode): x = T(sum_s P[s][row][:]) — the single rounding the GEMM epilogue would have
+// done — then exactly rms_norm_residual.  One CTA per row, row held in registers.
+template <typename T, int THREADS, int MAXV>
+__global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
+    T* __restrict__ out, T* __restrict__ residual, const float* __restrict__ partials, int S,
+    int64_t split_stride, const T* __restrict__ weight, float eps, int n) {
+  constexpr int VEC = 16 / sizeof(T);
+  static_assert(VEC == 8, "16-bit element types only");
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = n / VEC;
+  T* res_row = residual + row * n;
+  T* out_row = out + row * n;
+  const float* p_row = partials + row * n;
+  float x[MAXV][VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = threadIdx.x + j * THREADS;
+    if (v < nvec) {
+      float a[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) a[i] = 0.f;
+      // all (<= 8) partials are requested up front: one L2 round trip instead of S
+      float4 lo[8], hi[8];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) {
+        const int spc = sp < S ? sp : S - 1;  // clamped, the duplicate is weighted 0 below
+        const float4* src = reinterpret_cast<const float4*>(p_row + spc * split_stride + v * VEC);
+        lo[sp] = __ldcg(src);
+        hi[sp] = __ldcg(src + 1);
+      }
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) {  // fixed order: deterministic
+        const float wgt = sp < S ? 1.f : 0.f;
+        a[0] = fmaf(lo[sp].x, wgt, a[0]); a[1] = fmaf(lo[sp].y, wgt, a[1]);
+        a[2] = fmaf(lo[sp].z, wgt, a[2]); a[3] = fmaf(lo[sp].w, wgt, a[3]);
+        a[4] = fmaf(hi[sp].x, wgt, a[4]); a[5] = fmaf(hi[sp].y, wgt, a[5]);
+        a[6] = fmaf(hi[sp].z, wgt, a[6]); a[7] = fmaf(hi[sp].w, wgt, a[7]);
+      }
+      uint4 rraw = ld_v4(res_row + v * VEC);
+      const T* r = reinterpret_cast<const T*>(&rraw);
+      uint4 sraw;
+      T* sv = reinterpret_cast<T*>(&sraw);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float gemm_out = rnd<T>(a[i]);  // what the GEMM would have stored
+        const float f = Num<T>::to_f(r[i]) + gemm_out;
+        ss += f * f;
+        sv[i] = Num<T>::from_f(f);
+        x[j][i] = Num<T>::to_f(sv[i]);
+      }
+      st_v4(res_row + v * VEC, sraw);
+    }
+  }
+  const float total = block_sum<THREADS>(ss, red);
+  const float rstd = rsqrtf(total / n + eps);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = threadIdx.x + j * THREADS;
+    if (v < nvec) {
+      uint4 wraw = ld_v4(weight + v * VEC);
+      const T* w = reinterpret_cast<const T*>(&wraw);
+      uint4 oraw;
+      T* o = reinterpret_cast<T*>(&oraw);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float y = rnd<T>(x[j][i] * rstd);
+        o[i] = Num<T>::from_f(y * Num<T>::to_f(w[i]));
+      }
+      st_v4(out_row + v * VEC, oraw);
+    }
+  }
+}
+
+template <typename T>
+static int launch_rms_norm_splitk(void* out, void* residual, const float* partials, int S,
+                                  int64_t split_stride, const void* weight, int64_t rows,
+                                  int64_t n, float eps, cudaStream_t st) {
+  T* o = static_cast<T*>(out);
+  T* r = static_cast<T*>(residual);
+  const T* w = static_cast<const T*>(weight);
+  const int64_t nvec = n / 8;
+  dim3 grid(static_cast<unsigned>(rows));
+  if (nvec <= 256)
+    rms_norm_residual_splitk_kernel<T, 256, 1><<<grid, 256, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+  else if (nvec <= 512)
+    rms_norm_residual_splitk_kernel<T, 512, 1><<<grid, 512, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+  else if (nvec <= 1024)
+    rms_norm_residual_splitk_kernel<T, 512, 2><<<grid, 512, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+  else
+    rms_norm_residual_splitk_kernel<T, 1024, 4><<<grid, 1024, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+  B200_LAUNCH_OK("rms_norm_residual_splitk");
+  return B200_OK;
+}
+
 // ===========================================================================
 // RoPE (+ optional fused KV-slot write)
 // ===========================================================================
@@ -476,6 +574,30 @@ int b200_rms_norm_residual(void* out, void* residual, const void* in, const void
   if (rows == 0) return B200_OK;
   DISPATCH_DTYPE3(dtype, (launch_rms_norm<T, true>(out, residual, in, weight, rows, n, eps,
                                                    static_cast<cudaStream_t>(stream))));
+}
+
+int b200_rms_norm_residual_splitk(void* out, void* residual, const float* partials, int splits,
+                                  const void* weight, int64_t rows, int64_t n, float eps, int dtype,
+                                  b200_stream_t stream) {
+  B200_CHECK_ARG(out && residual && partials && weight, "rms_norm_residual_splitk: null pointer");
+  B200_CHECK_ARG(splits >= 1 && splits <= 8 && rows >= 0 && n > 0 && n % 8 == 0 && n <= 32768,
+                 "rms_norm_residual_splitk: need n %% 8 == 0, n <= 32768, 1 <= splits <= 8");
+  B200_CHECK_ARG(is_aligned(out, 16) && is_aligned(residual, 16) && is_aligned(partials, 16) &&
+                     is_aligned(weight, 16),
+                 "rms_norm_residual_splitk: 16-byte alignment required");
+  if (rows == 0) return B200_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = rows * n;
+  switch (dtype) {
+    case B200_BF16:
+      return launch_rms_norm_splitk<__nv_bfloat16>(out, residual, partials, splits, stride, weight,
+                                                   rows, n, eps, st);
+    case B200_FP16:
+      return launch_rms_norm_splitk<__half>(out, residual, partials, splits, stride, weight, rows, n,
+                                            eps, st);
+    default:
+      return set_error(B200_ERR_UNSUPPORTED, "rms_norm_residual_splitk: bf16 / fp16 only");
+  }
 }
 
 int b200_rope_inplace(void* q, void* k, const int32_t* positions, const void* cos_sin,

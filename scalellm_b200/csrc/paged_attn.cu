@@ -1072,9 +1072,13 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 
 // Second pass: merge split-KV partials (same maths as the reference's unwired
 // attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).
+// One warp per (token, head) row; each lane owns D/32 consecutive outputs (vector loads).
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
-  const int h = blockIdx.x;
+  constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 4 + warp;
+  if (h >= p.n_heads) return;
   const int b = blockIdx.y / p.max_q_len, qi = blockIdx.y % p.max_q_len;
   const int q_begin = p.q_cu_lens[b];
   const int q_len = p.q_cu_lens[b + 1] - q_begin;
@@ -1082,47 +1086,64 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
   const int64_t tok = q_begin + qi;
   const int64_t row = (int64_t)blockIdx.y * p.n_heads + h;
   const float* lse = p.ws_lse + row * p.n_splits;
-  // which split slots hold a piece?  fixed-split kernels publish every slot; the stream kernel
-  // only writes pieces that exist, so mirror its static partition here.
-  uint64_t present[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-  if (p.stream) {
-    present[0] = present[1] = present[2] = present[3] = 0;
-    const int G = p.group, kvh = h / G, g = h - kvh * G;
-    const int r = qi * G + g, rb = r / 16;
-    const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
-    const int rows_total = q_len * G, row0 = rb * 16, n_rows = min(16, rows_total - row0);
-    const int q_pos0 = kv_len - q_len, qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
-    const int kv_end = q_pos0 + qi_max + 1;
-    const int kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
-    const int64_t seq = ((int64_t)b * p.n_rb + rb) * p.n_kv_heads + kvh;
-    const int64_t base = seq * p.ntm, first_piece = base / p.tpw;
-    for (int s = 0; s < p.n_splits; ++s) {
+  // Lane l looks at split slots l, l+32, ...: is a piece there, and what is its LSE?  Fixed-split
+  // kernels publish every slot; the stream kernel only writes pieces that exist, so its static
+  // partition is mirrored here.
+  auto slot_lse = [&](int s) -> float {
+    if (s >= p.n_splits) return -INFINITY;
+    if (p.stream) {
+      const int G = p.group, kvh = h / G, g = h - kvh * G;
+      const int r = qi * G + g, rb = r / 16;
+      const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+      const int rows_total = q_len * G, row0 = rb * 16, n_rows = min(16, rows_total - row0);
+      const int q_pos0 = kv_len - q_len, qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
+      const int kv_end = q_pos0 + qi_max + 1;
+      const int kv_begin = p.window >= 0 ? max(0, q_pos0 + qi_min - p.window) : 0;
+      const int64_t seq = ((int64_t)b * p.n_rb + rb) * p.n_kv_heads + kvh;
+      const int64_t base = seq * p.ntm, first_piece = base / p.tpw;
       const int64_t lo = max(base, (first_piece + s) * p.tpw);
       const int64_t hi = min(base + p.ntm, (first_piece + s + 1) * p.tpw);
-      if (lo >= hi) continue;
       const int t0 = max((int)(lo - base), kv_begin / ATT_TILE);
       const int t1 = min((int)(hi - base), (kv_end + ATT_TILE - 1) / ATT_TILE);
-      if (t0 < t1) present[s >> 6] |= 1ull << (s & 63);
+      if (!(lo < hi && t0 < t1)) return -INFINITY;
     }
-  }
-  auto has = [&](int s) { return (present[s >> 6] >> (s & 63)) & 1ull; };
+    return lse[s];
+  };
   float M = -INFINITY;
-  for (int s = 0; s < p.n_splits; ++s)
-    if (has(s)) M = fmaxf(M, lse[s]);
+  for (int s0 = 0; s0 < p.n_splits; s0 += 32) M = fmaxf(M, slot_lse(s0 + lane));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
   float L = 0.f;
-  for (int s = 0; s < p.n_splits; ++s)
-    if (has(s)) L += exp2f(lse[s] - M);
-  const float inv = 1.f / L;
-  for (int d = threadIdx.x; d < D; d += 128) {
-    float o = 0.f;
-    for (int s = 0; s < p.n_splits; ++s) {
-      if (!has(s)) continue;
-      const float w = exp2f(lse[s] - M);
-      if (w != 0.f) o = fmaf(p.ws_o[(row * p.n_splits + s) * D + d], w, o);
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int s0 = 0; s0 < p.n_splits; s0 += 32) {
+    const float my_w = exp2f(slot_lse(s0 + lane) - M);  // 0 for absent / empty pieces
+    L += my_w;
+    const int ns = min(p.n_splits - s0, 32);
+    for (int s = 0; s < ns; ++s) {
+      const float w = __shfl_sync(0xffffffffu, my_w, s);
+      if (w == 0.f) continue;  // its partial O may be unwritten / NaN
+      const float* src = p.ws_o + (row * p.n_splits + s0 + s) * D + lane * EPL;
+      if constexpr (EPL == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        acc[0] = fmaf(v.x, w, acc[0]);
+        acc[1] = fmaf(v.y, w, acc[1]);
+        acc[2] = fmaf(v.z, w, acc[2]);
+        acc[3] = fmaf(v.w, w, acc[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(src[e], w, acc[e]);
+      }
     }
-    static_cast<T*>(p.out)[tok * p.o_stride_t + (int64_t)h * p.o_stride_h + d] =
-        Num<T>::from_f(o * inv);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+  const float inv = 1.f / L;
+  T* dst = static_cast<T*>(p.out) + tok * p.o_stride_t + (int64_t)h * p.o_stride_h + lane * EPL;
+#pragma unroll
+  for (int e = 0; e < EPL; e += 2)
+    *reinterpret_cast<uint32_t*>(dst + e) = Num<T>::pack(acc[e] * inv, acc[e + 1] * inv);
 }
 
 // ---------------------------------------------------------------------------
@@ -1364,7 +1385,7 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   }
   if (rc != B200_OK) return rc;
   if (p.n_splits > 1) {
-    dim3 cgrid((unsigned)p.n_heads, (unsigned)(batch * p.max_q_len));
+    dim3 cgrid((unsigned)((p.n_heads + 3) / 4), (unsigned)(batch * p.max_q_len));
     paged_attn_combine_kernel<T, D><<<cgrid, 128, 0, st>>>(p);
     B200_LAUNCH_OK("paged_attn_combine");
   }

@@ -263,6 +263,8 @@ struct W4Params {
   int M, N, K, KT, NT, geff, ngrp, blob_bytes, units;
   int64_t ldc;
   long long* trace;  // debug: [grid][32] clock64 milestones / wait totals (null in production)
+  float* splitk_out;  // != null: regular split-K, every CTA writes its fp32 partial to
+  int splitk_S;       //          splitk_out[split][m][n] and the CONSUMER kernel reduces
 };
 
 #define W4_TRACE_ADD(slot, cyc)                                          \
@@ -321,8 +323,15 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = gridDim.x;
   if (threadIdx.x == 0) W4_TRACE(0);
-  const int u_begin = w4_unit_begin(blockIdx.x, p.units, P);
-  const int u_end = w4_unit_begin(blockIdx.x + 1, p.units, P);
+  int u_begin, u_end;
+  if (p.splitk_out) {  // regular split-K: CTA = (n tile, K slice), exactly one segment
+    const int nt_ = blockIdx.x / p.splitk_S, sp_ = blockIdx.x % p.splitk_S;
+    u_begin = nt_ * p.KT + (int)(((int64_t)sp_ * p.KT) / p.splitk_S);
+    u_end = nt_ * p.KT + (int)(((int64_t)(sp_ + 1) * p.KT) / p.splitk_S);
+  } else {             // stream-K: equal share of the (n tile, k tile) units
+    u_begin = w4_unit_begin(blockIdx.x, p.units, P);
+    u_end = w4_unit_begin(blockIdx.x + 1, p.units, P);
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
@@ -553,14 +562,19 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     while (it.next(nt, kt0, kt1)) {
       const int buf = seg & 1;
       const uint32_t tph = (seg >> 1) & 1;
-      const bool full_tile = (kt0 == 0 && kt1 == p.KT);
+      const bool full_tile = (kt0 == 0 && kt1 == p.KT) && !p.splitk_out;
       const int n = nt * 128 + n_local;
       mbar_wait(&tmem_full[buf], tph);
       if (et == 0 && seg == 0) W4_TRACE(6);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * MT;
       float* part = nullptr;
-      if (!full_tile) {
+      int64_t part_ld = 128;
+      if (p.splitk_out) {
+        const int sp_ = blockIdx.x % p.splitk_S;
+        part = p.splitk_out + (int64_t)sp_ * p.M * p.N + (int64_t)nt * 128;
+        part_ld = p.N;
+      } else if (!full_tile) {
         const int slot = 2 * blockIdx.x + (kt0 > 0 ? 0 : 1);
         part = p.ws_partial + (int64_t)slot * MT * 128;
       }
@@ -587,7 +601,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int m = c0 + i;
-            if (m < p.M) part[m * 128 + n_local] = __uint_as_float(r[i]);
+            if (m < p.M) part[m * part_ld + n_local] = __uint_as_float(r[i]);
           }
         }
       }
@@ -596,7 +610,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       if (et == 0 && seg == 0) W4_TRACE(7);
 
-      if (!full_tile) {
+      if (!full_tile && !p.splitk_out) {
         // ---- publish the partial; the last contributor reduces the tile -------
         asm volatile("bar.sync 1, 128;" ::: "memory");  // every partial store of the CTA is issued
         const int u_lo = nt * p.KT;
@@ -852,6 +866,58 @@ int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K, int64_t N, in
 
 void b200_debug_set_trace(void* device_buffer) {
   g_w4_trace = static_cast<long long*>(device_buffer);
+}
+
+int b200_w4a16_splitk_splits(int64_t M, int64_t N, int64_t K) {
+  (void)M;
+  if (N <= 0 || K <= 0 || N % 128 || K % 128) return 0;
+  const int NT = (int)(N / 128), KT = (int)(K / 128), sms = sm_count();
+  int best = 1;
+  for (int S = 1; S <= 8; ++S)
+    if (NT * S <= sms && KT / S >= 4) best = S;
+  return best;
+}
+
+int b200_w4a16_gemm_splitk(float* partials, const void* A, const void* packed, int64_t M,
+                           int64_t N, int64_t K, int64_t lda, int group_size, int splits,
+                           b200_stream_t stream) {
+  B200_CHECK_ARG(partials && A && packed, "w4a16_gemm_splitk: null pointer");
+  int rc = check_w4_shape("w4a16_gemm_splitk", K, N, group_size);
+  if (rc != B200_OK) return rc;
+  B200_CHECK_ARG(M > 0 && M <= 128 && lda >= K, "w4a16_gemm_splitk: 1 <= M <= 128 required");
+  B200_CHECK_ARG(splits >= 1 && splits <= K / 128, "w4a16_gemm_splitk: bad split count %d", splits);
+  B200_CHECK_ARG(is_aligned(A, 16) && lda % 8 == 0 && is_aligned(packed, 16) &&
+                     is_aligned(partials, 16),
+                 "w4a16_gemm_splitk: pointers must be 16-byte aligned, lda %% 8 == 0");
+  const int geff = w4_geff(group_size);
+  const int mt = pick_mt(M);
+  W4Params p{};
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.KT = (int)(K / 128);
+  p.NT = (int)(N / 128);
+  p.geff = geff;
+  p.ngrp = 128 / geff;
+  p.blob_bytes = w4_blob_bytes(geff);
+  p.units = p.KT * p.NT;
+  p.ldc = N;
+  p.trace = g_w4_trace;
+  p.splitk_out = partials;
+  p.splitk_S = splits;
+  CUtensorMap amap;
+  AMapKey key{A, M, K, lda, mt};
+  rc = get_act_tensor_map(key, &amap);
+  if (rc != B200_OK) return rc;
+  const int grid = p.NT * splits;
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (mt) {
+    case 16: return launch_w4_gemm<16>(amap, p, grid, st);
+    case 32: return launch_w4_gemm<32>(amap, p, grid, st);
+    case 64: return launch_w4_gemm<64>(amap, p, grid, st);
+    default: return launch_w4_gemm<128>(amap, p, grid, st);
+  }
 }
 
 int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K) {

@@ -15,6 +15,7 @@ This is the caller-side glue the benchmark and the parity tests need, not a mode
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -101,6 +102,8 @@ class LlamaDecoder:
         self.embed = torch.empty((args.vocab_size, h // w), dtype=dtype, device=device)
         self.lm_head = ColumnParallelLinear(h, args.vocab_size, True, pa, dtype, device)
         self.kv_caches: List[KVCache] = []
+        # fuse the split-K reduction of o_proj / down_proj into the following RMSNorm
+        self.fuse_splitk = os.environ.get("B200_FUSE_SPLITK", "1") != "0"
 
     # -- weights -----------------------------------------------------------------
     def load_layer(self, i: int, sd: Dict[str, Dict[str, torch.Tensor]]) -> None:
@@ -177,20 +180,36 @@ class LlamaDecoder:
         if self.pa.world_size > 1:  # ParallelEmbedding: split on hidden + all-gather (embedding.h:74-79)
             h = gather_from_model_parallel_region(h, self.pa)
         I = self.I_local
-        pending = None  # output of the previous block, not yet added to the residual stream
+        T = h.shape[0]
+        # `pending` = output of the previous block, not yet added to the residual stream; either a
+        # bf16 tensor or the producing GEMM's split-K partials (reduction fused into the norm).
+        pending, pending_is_partials = None, False
+
+        def norm_residual(norm, pend, is_partials):
+            if is_partials:
+                return norm.forward_residual_partials(pend, h)
+            return norm.forward_residual(pend, h)
+
         for L, cache in zip(self.layers, self.kv_caches):
-            n1 = L["input_norm"](h) if pending is None else L["input_norm"].forward_residual(pending, h)
+            n1 = L["input_norm"](h) if pending is None else norm_residual(L["input_norm"], pending,
+                                                                           pending_is_partials)
             qkv = L["qkv"](n1)
             q = qkv[:, : self.q_size]
             k = qkv[:, self.q_size: self.q_size + self.kv_size]
             v = qkv[:, self.q_size + self.kv_size:]
             attn = L["attn"](q, k, v, positions, cache, params)
-            o = L["o"](attn)
-            n2 = L["post_norm"].forward_residual(o, h)       # h = h + o ; n2 = norm(h)
+            fuse_o = self.fuse_splitk and hasattr(L["o"], "supports_partials") and L["o"].supports_partials(T)
+            o = L["o"].forward_partials(attn) if fuse_o else L["o"](attn)
+            n2 = norm_residual(L["post_norm"], o, fuse_o)            # h = h + o ; n2 = norm(h)
             gu = L["gate_up"](n2)
             act = kernels.silu_mul(gu[:, :I], gu[:, I:])
-            pending = L["down"](act)
-        hn = self.final_norm.forward_residual(pending, h) if pending is not None else self.final_norm(h)
+            fuse_d = self.fuse_splitk and hasattr(L["down"], "supports_partials") and L["down"].supports_partials(T)
+            pending = L["down"].forward_partials(act) if fuse_d else L["down"](act)
+            pending_is_partials = fuse_d
+        if pending is None:
+            hn = self.final_norm(h)
+        else:
+            hn = norm_residual(self.final_norm, pending, pending_is_partials)
         return self.lm_head(hn)
 
     __call__ = forward

@@ -302,6 +302,39 @@ def w4a16_gemm(a: torch.Tensor, packed: torch.Tensor, N: int, group_size: int,
     return out
 
 
+def w4a16_splitk_splits(M: int, N: int, K: int) -> int:
+    return int(_lib.load().b200_w4a16_splitk_splits(M, N, K))
+
+
+def w4a16_gemm_splitk(a: torch.Tensor, packed: torch.Tensor, N: int, group_size: int,
+                      splits: Optional[int] = None) -> torch.Tensor:
+    """Split-K partial mode: returns fp32 partials [splits, M, N]; the consumer
+    (rms_norm_residual_splitk) performs the reduction.  M <= 128."""
+    _cuda(a, packed)
+    assert a.dim() == 2 and a.dtype == torch.bfloat16 and a.stride(1) == 1
+    M, K = a.shape
+    if splits is None:
+        splits = w4a16_splitk_splits(M, N, K)
+    partials = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
+    check(_lib.load().b200_w4a16_gemm_splitk(_p(partials), _p(a), _p(packed), M, N, K, a.stride(0),
+                                             group_size, splits, _stream()))
+    return partials
+
+
+def rms_norm_residual_splitk(out: torch.Tensor, residual: torch.Tensor, partials: torch.Tensor,
+                             weight: torch.Tensor, epsilon: float) -> None:
+    """residual += T(sum_s partials[s]); out = rms_norm(residual) * weight."""
+    _cuda(out, residual, partials, weight)
+    assert partials.dtype == torch.float32 and partials.is_contiguous() and partials.dim() == 3
+    assert out.is_contiguous() and residual.is_contiguous()
+    S, rows, n = partials.shape
+    if rows == 0:
+        return
+    check(_lib.load().b200_rms_norm_residual_splitk(_p(out), _p(residual), _p(partials), S,
+                                                    _p(weight), rows, n, epsilon, _dt(out),
+                                                    _stream()))
+
+
 def launch_count() -> int:
     return int(_lib.load().b200_launch_count())
 

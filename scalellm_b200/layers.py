@@ -236,6 +236,13 @@ class RMSNorm:
         kernels.rms_norm_residual(out, residual, x, self.weight, self.eps)
         return out
 
+    def forward_residual_partials(self, partials: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        """Same, with x delivered as the producing GEMM's split-K partials [S, rows, n] fp32: the
+        cross-CTA reduction of the GEMM is fused into this kernel."""
+        out = torch.empty_like(residual)
+        kernels.rms_norm_residual_splitk(out, residual, partials, self.weight, self.eps)
+        return out
+
     __call__ = forward
 
 
@@ -370,6 +377,15 @@ class RowParallelQLinear(_QLinearBase):
         qw, qz, sc = _shard_qtensors(sd, self.qa, 0, self.pa.rank, self.pa.world_size,
                                      self.full_K, self.N)
         self._set_shard(qw, qz, sc, sd.get("bias"))
+
+    def supports_partials(self, n_rows: int) -> bool:
+        """Split-K partial output (reduction fused into the consumer norm) — single rank, no bias."""
+        return self.pa.world_size == 1 and self.bias is None and 0 < n_rows <= 128
+
+    def forward_partials(self, x: torch.Tensor) -> torch.Tensor:
+        self._ensure_packed()
+        x2 = x.reshape(-1, x.shape[-1])
+        return kernels.w4a16_gemm_splitk(x2, self.packed, self.N, self.qa.group_size)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not self.input_is_parallelized:

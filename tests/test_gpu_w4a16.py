@@ -165,3 +165,38 @@ def test_gemm_linearity_full_size():
     # each term carries one bf16 rounding (2^-9 relative) of its own magnitude
     tol = 2.0 ** -8 * (c1.abs() + c2.abs() + c12.abs())
     assert bool(((c12 - (c1 + c2)).abs() <= tol).all())
+
+
+@pytest.mark.parametrize("K,N,M", [(4096, 4096, 64), (14336, 4096, 64), (1024, 512, 17), (512, 256, 128)])
+def test_splitk_partials_fused_into_rms_norm_residual(K, N, M):
+    """W4A16 split-K partial mode + b200_rms_norm_residual_splitk == GEMM -> residual add -> RMSNorm
+    (models/meta/llama.h:174-176) with the oracle ops; the residual stream must come out within
+    one bf16 rounding flip of the unfused oracle (summation order differs), the norm within 2 ulp."""
+    from oracle import ops
+    from tests.util import assert_ulp
+    a, w_ref, packed = gemm_case(M, K, N, 128, seed=K + N)
+    gen = torch.Generator().manual_seed(1)
+    res = torch.randn(M, N, generator=gen).bfloat16()
+    wn = (1 + 0.1 * torch.randn(N, generator=gen)).bfloat16()
+    partials = kernels.w4a16_gemm_splitk(a.to(DEV), packed, N, 128)
+    S = partials.shape[0]
+    assert S == kernels.w4a16_splitk_splits(M, N, K) and 1 <= S <= 8
+    # the partials sum to the GEMM result
+    c = partials.sum(0).cpu()
+    ref32 = a.float() @ w_ref.float()
+    assert rel_err(c.bfloat16(), ref32.bfloat16().float()) < 1e-3
+    d_res = res.to(DEV).clone()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    kernels.rms_norm_residual_splitk(out, d_res, partials, wn.to(DEV), 1e-5)
+    ref_out, ref_res = ops.rms_norm_residual(ref32.bfloat16(), res, wn, 1e-5)
+    assert_ulp(d_res, ref_res, max_ulp=2, max_frac=0.1, what="residual")
+    assert_ulp(out, ref_out, max_ulp=3, max_frac=0.15, what="norm")
+    # identical to the unfused B200 path given the same rounding point: feed the rounded sum
+    gemm_bf16 = partials.sum(0).bfloat16()   # torch sums in the same s order on the same values
+    r2 = res.to(DEV).clone()
+    out2 = torch.empty_like(out)
+    kernels.rms_norm_residual(out2, r2, gemm_bf16, wn.to(DEV), 1e-5)
+    assert_ulp(d_res, r2, max_ulp=1, max_frac=2e-3, what="fused vs unfused residual")
+    # deterministic
+    p2 = kernels.w4a16_gemm_splitk(a.to(DEV), packed, N, 128)
+    assert torch.equal(partials, p2)

@@ -77,6 +77,13 @@ if has ncu; then
       > $OUT/ncu_gemm.log 2>&1
   echo "ncu gemm rc=$?" | tee -a $OUT/summary.txt
 fi
+if has ncul; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv \
+      --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --layers 8 --no-graph \
+      --skip-cpu-baseline > $OUT/ncu_bench.log 2>&1
+  echo "ncu launches rc=$?" | tee -a $OUT/summary.txt
+fi
+
 if has ncuattn; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn_mma_kernel \
       -s 6 -c 2 -o $OUT/prof_attn_mma -f python tools/attn_bench.py > $OUT/ncu_attn_mma.log 2>&1
