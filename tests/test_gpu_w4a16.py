@@ -173,7 +173,7 @@ def test_splitk_partials_fused_into_rms_norm_residual(K, N, M):
     (models/meta/llama.h:174-176) with the oracle ops; the residual stream must come out within
     one bf16 rounding flip of the unfused oracle (summation order differs), the norm within 2 ulp."""
     from oracle import ops
-    from tests.util import assert_ulp
+    from tests.util import assert_ulp_or_abs
     a, w_ref, packed = gemm_case(M, K, N, 128, seed=K + N)
     gen = torch.Generator().manual_seed(1)
     res = torch.randn(M, N, generator=gen).bfloat16()
@@ -189,14 +189,16 @@ def test_splitk_partials_fused_into_rms_norm_residual(K, N, M):
     out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
     kernels.rms_norm_residual_splitk(out, d_res, partials, wn.to(DEV), 1e-5)
     ref_out, ref_res = ops.rms_norm_residual(ref32.bfloat16(), res, wn, 1e-5)
-    assert_ulp(d_res, ref_res, max_ulp=2, max_frac=0.1, what="residual")
-    assert_ulp(out, ref_out, max_ulp=3, max_frac=0.15, what="norm")
+    # a one-ulp flip of the GEMM output (fp32 summation order) is many ulps of a residual sum that
+    # cancels towards 0, so bound the ABSOLUTE error by one bf16 ulp of the largest operand
+    assert_ulp_or_abs(d_res, ref_res, max_ulp=2, abs_frac=2 ** -7, what="residual")
+    assert_ulp_or_abs(out, ref_out, max_ulp=3, abs_frac=2 ** -6, what="norm")
     # identical to the unfused B200 path given the same rounding point: feed the rounded sum
     gemm_bf16 = partials.sum(0).bfloat16()   # torch sums in the same s order on the same values
     r2 = res.to(DEV).clone()
     out2 = torch.empty_like(out)
     kernels.rms_norm_residual(out2, r2, gemm_bf16, wn.to(DEV), 1e-5)
-    assert_ulp(d_res, r2, max_ulp=1, max_frac=2e-3, what="fused vs unfused residual")
+    assert_ulp_or_abs(d_res, r2, max_ulp=1, abs_frac=2 ** -8, what="fused vs unfused residual")
     # deterministic
     p2 = kernels.w4a16_gemm_splitk(a.to(DEV), packed, N, 128)
     assert torch.equal(partials, p2)
