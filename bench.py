@@ -354,10 +354,15 @@ def run_b200(a, rank, world, local_rank):
                "roofline_w4a16_gemm": gemm, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.barrier()
-        if pg:
-            pg.close()
-        dist.destroy_process_group()
+        # Tear-down of NCCL communicators that were captured into CUDA graphs can block for
+        # minutes; every rank has reported (rank 0 printed), so synchronise and leave hard.
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def _peaks():
