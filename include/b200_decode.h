@@ -272,6 +272,11 @@ B200_API int b200_ar_open_peers(b200_ar_comm* comm,
 /* In-place sum of data[count] (bf16/fp16/fp32) over all ranks, on `stream`. */
 B200_API int b200_ar_allreduce(b200_ar_comm* comm, void* data, int64_t count,
                                int dtype, b200_stream_t stream);
+/* Same reduction, but this rank's input is the producing GEMM's split-K partials
+ * [splits][count] fp32 (b200_w4a16_gemm_splitk): the copy-in stage sums them and rounds once,
+ * so the row-parallel GEMM needs no fix-up pass of its own.  out: [count] bf16/fp16. */
+B200_API int b200_ar_allreduce_splitk(b200_ar_comm* comm, void* out, const float* partials,
+                                      int splits, int64_t count, int dtype, b200_stream_t stream);
 B200_API int b200_ar_destroy(b200_ar_comm* comm);
 
 #ifdef __cplusplus

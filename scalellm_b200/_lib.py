@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200_ar_create": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp]),
     "b200_ar_open_peers": (_int, [_vp, _vp]),
     "b200_ar_allreduce": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "b200_ar_allreduce_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp]),
     "b200_ar_destroy": (_int, [_vp]),
 }
 

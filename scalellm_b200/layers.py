@@ -392,8 +392,16 @@ class RowParallelQLinear(_QLinearBase):
             x = scatter_to_model_parallel_region(x, self.pa)
         if self.pa.world_size == 1:
             return self._gemm(x, self.bias)
-        out = self._gemm(x, None)
-        out = reduce_from_model_parallel_region(out, self.pa)
+        x2 = x.reshape(-1, x.shape[-1])
+        pg = self.pa.process_group
+        if 0 < x2.shape[0] <= 128 and hasattr(pg, "allreduce_partials") and x2.is_cuda:
+            # split-K partials go straight into the NVLink all-reduce (no GEMM fix-up pass)
+            self._ensure_packed()
+            parts = kernels.w4a16_gemm_splitk(x2, self.packed, self.N, self.qa.group_size)
+            out = pg.allreduce_partials(parts, x.dtype).view(*x.shape[:-1], self.N)
+        else:
+            out = self._gemm(x, None)
+            out = reduce_from_model_parallel_region(out, self.pa)
         if self.bias is not None:  # bias after the reduction (:360-363)
             out = out + self.bias
         return out

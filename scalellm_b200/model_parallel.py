@@ -80,6 +80,23 @@ class ProcessGroup:
             return
         dist.all_reduce(input, op=dist.ReduceOp.SUM, group=self._group)
 
+    def allreduce_partials(self, partials: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        """Sum over ranks of sum_s partials[s] ([S, rows, n] fp32 from the split-K GEMM), one
+        rounding to `dtype` per rank before the exchange (what the GEMM epilogue would store)."""
+        S, rows, n = partials.shape
+        out = torch.empty((rows, n), dtype=dtype, device=partials.device)
+        nbytes = out.numel() * out.element_size()
+        if (self._comm is not None and nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
+                and dtype in (torch.bfloat16, torch.float16)):
+            dt = 0 if dtype == torch.bfloat16 else 1
+            check(_lib.load().b200_ar_allreduce_splitk(self._comm, out.data_ptr(), partials.data_ptr(),
+                                                       S, out.numel(), dt,
+                                                       torch.cuda.current_stream().cuda_stream))
+            return out
+        out.copy_(partials.sum(0))
+        self.allreduce(out)
+        return out
+
     def allgather(self, input: torch.Tensor, outputs: List[torch.Tensor]) -> None:
         if self._world == 1:
             outputs[0].copy_(input)

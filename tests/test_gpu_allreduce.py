@@ -51,6 +51,16 @@ def _worker(rank, world, port):
                 ys = [torch.empty_like(y) for _ in range(world)]
                 dist.all_gather(ys, y)
                 assert all(torch.equal(ys[0], t) for t in ys)
+        # split-K partials as the local operand (row-parallel GEMM fused with the reduction)
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        parts = torch.randn(4, 64, 4096, generator=g, device=dev)
+        got = pg.allreduce_partials(parts, torch.bfloat16)
+        local = parts.sum(0).bfloat16()
+        gl = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gl, local)
+        want = sum(t.float() for t in gl).bfloat16()
+        assert (got.view(torch.int16) == want.view(torch.int16)).float().mean() > 0.99
+        assert torch.allclose(got.float(), want.float(), rtol=1e-2, atol=1e-2)
         # larger than the symmetric buffer -> NCCL path, still correct
         big = torch.ones(2 << 20, device=dev)
         pg.allreduce(big)
