@@ -40,8 +40,8 @@ if has attn2; then
 fi
 
 if has tests; then
-  for f in elementwise attention w4a16 decode_step; do
-    timeout 1200 python -m pytest tests/test_gpu_$f.py -m gpu -q --tb=short -p no:cacheprovider \
+  for f in gpu_elementwise gpu_attention gpu_w4a16 gpu_decode_step shim; do
+    timeout 1200 python -m pytest tests/test_$f.py -m gpu -q --tb=short -p no:cacheprovider \
         > $OUT/pytest_$f.log 2>&1
     echo "pytest $f rc=$? : $(tail -1 $OUT/pytest_$f.log)" | tee -a $OUT/summary.txt
   done
@@ -90,3 +90,8 @@ if has ncuattn; then
   echo "ncu attn mma rc=$?" | tee -a $OUT/summary.txt
 fi
 echo "== done" | tee -a $OUT/summary.txt
+if has deq; then
+  timeout 120 tools/microbench/deq > $OUT/deq.log 2>&1
+  echo "deq rc=$?" | tee -a $OUT/summary.txt
+  cat $OUT/deq.log | tee -a $OUT/summary.txt
+fi

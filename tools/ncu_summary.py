@@ -1,0 +1,130 @@
+#!/usr/bin/env python
+"""Turn raw ncu output (gpurun_out/, scratch) into the small text summaries kept under profiles/.
+
+  ncu_summary.py launches <launches.csv> <out.md> [title]
+      per-kernel count / total / mean / share of a `--metrics gpu__time_duration.sum` launch list
+  ncu_summary.py full <report.ncu-rep> <out.md> [traffic_key]
+      key metrics of every launch in a `--set full` capture; with traffic_key also records
+      dram read+write bytes per launch in profiles/traffic.json (read by bench.py)
+"""
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+KEYS = [
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum",
+    "lts__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum",
+    "smsp__cycles_active.avg",
+    "launch__registers_per_thread",
+    "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "launch__grid_size",
+    "launch__block_size",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def short(name: str) -> str:
+    name = re.sub(r"^void\s+", "", name)
+    name = re.sub(r"\(.*$", "", name)
+    return name.replace("b200::", "")
+
+
+def launches(path, out, title):
+    rows = []
+    with open(path, newline="") as f:
+        text = f.read()
+    start = text.find('"ID"')
+    for r in csv.DictReader(io.StringIO(text[start:])):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            v = float(r["Metric Value"].replace(",", ""))
+            if r.get("Metric Unit") == "us":
+                v *= 1e3
+            rows.append((short(r["Kernel Name"]), v, r["Grid Size"], r["Block Size"]))
+    agg = OrderedDict()
+    for n, v, g, b in rows:
+        a = agg.setdefault(n, [0, 0.0, g, b])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    ours = sum(a[1] for n, a in agg.items() if not n.startswith(("at::", "cutlass", "nvjet", "void at")))
+    with open(out, "w") as f:
+        f.write(f"# {title}\n\n")
+        f.write(f"source: `{os.path.relpath(path, ROOT)}` (ncu --metrics gpu__time_duration.sum "
+                f"--clock-control none); {len(rows)} launches, {tot / 1e3:.1f} us total.\n")
+        f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+        f.write("| kernel | launches | total us | mean us | share | grid | block |\n|---|---:|---:|---:|---:|---|---|\n")
+        for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{n}` | {a[0]} | {a[1] / 1e3:.1f} | {a[1] / a[0] / 1e3:.2f} | "
+                    f"{100 * a[1] / tot:.1f}% | {a[2]} | {a[3]} |\n")
+        f.write(f"\nlibb200decode kernels: {100 * ours / tot:.1f}% of the GPU time in the list.\n")
+    print(open(out).read())
+
+
+def full(rep, out, traffic_key):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                         text=True, check=True).stdout
+    start = txt.find('"ID"')
+    rd = list(csv.reader(io.StringIO(txt[start:])))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full: `{os.path.basename(rep)}`\n\n")
+        traffic = []
+        for r in data:
+            f.write(f"## launch {r[col['ID']]}: `{short(r[col['Kernel Name']])}` grid {r[col['Grid Size']]} "
+                    f"block {r[col['Block Size']]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEYS:
+                if k in col:
+                    f.write(f"| {k} | {r[col[k]]} | {units[col[k]]} |\n")
+            try:
+                def num(k):
+                    v = float(r[col[k]].replace(",", ""))
+                    u = units[col[k]].lower()
+                    mul = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+                    return v * mul
+                rdb, wrb = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+                dur = float(r[col["gpu__time_duration.sum"]].replace(",", ""))
+                du = units[col["gpu__time_duration.sum"]].lower()
+                dur_s = dur * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}.get(du, 1e-9)
+                f.write(f"| dram read+write | {(rdb + wrb) / 1e6:.2f} | MB |\n")
+                f.write(f"| dram GB/s (under ncu) | {(rdb + wrb) / dur_s / 1e9:.0f} | GB/s |\n")
+                traffic.append(rdb + wrb)
+            except Exception as e:  # noqa: BLE001
+                f.write(f"| (traffic unavailable: {e}) | | |\n")
+            f.write("\n")
+    print(open(out).read()[:6000])
+    if traffic_key and traffic:
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        d = json.load(open(tj)) if os.path.exists(tj) else {}
+        d[traffic_key] = {"dram_bytes_per_launch": sum(traffic) / len(traffic),
+                          "launches": len(traffic), "source": os.path.basename(out)}
+        json.dump(d, open(tj, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    if mode == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "ncu launch list")
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
