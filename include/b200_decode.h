@@ -219,33 +219,43 @@ B200_API int b200_w4a16_prepack_gptq(void* packed, const int32_t* qweight,
 B200_API int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K,
                                 int64_t N, int group_size, b200_stream_t stream);
 
-/* Workspace for split-K partials + tile counters.  The counter region (first
- * B200_W4A16_COUNTER_BYTES bytes) must be zero on first use; the GEMM leaves it
- * zeroed on return (same contract as Marlin's lock workspace, marlin.h:24). */
-#define B200_W4A16_COUNTER_BYTES 16384
+/* Workspace of b200_w4a16_gemm: the fp32 stream-K partials of one chunk of <= 128 rows
+ * (slots x min(M,128) x N floats).  No initialisation contract: it is fully overwritten before
+ * it is read (unlike Marlin's zeroed lock workspace, marlin.h:24, which has no counterpart here). */
 B200_API int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K);
 
-/* A: [M, K] bf16 row stride lda;  C: [M, N] bf16 row stride ldc; bias: [N] bf16 or NULL. */
+/* A: [M, K] bf16 row stride lda;  C: [M, N] bf16 row stride ldc; bias: [N] bf16 or NULL.
+ * Two launches: the stream-K GEMM (fp32 partials into the workspace) and a reduction pass. */
 B200_API int b200_w4a16_gemm(void* C, const void* A, const void* packed,
                              const void* bias, int64_t M, int64_t N, int64_t K,
                              int64_t lda, int64_t ldc, int group_size,
                              void* workspace, int64_t workspace_bytes,
                              b200_stream_t stream);
 
-/* Split-K "partials" mode (B200-native fusion of the GEMM's cross-CTA reduction into its consumer):
- * every CTA owns (n tile, K slice) and writes its fp32 partial to partials[split][M][N]; the
- * consumer (b200_rms_norm_residual_splitk) sums the `splits` partials in slice order, rounds once
- * to the element type — exactly what the GEMM epilogue would have stored — and carries on.  Replaces
- * the o_proj / down_proj + residual add + RMSNorm sequence of models/meta/llama.h:170-177.
- * b200_w4a16_splitk_splits recommends a split count (n_tiles * splits <= #SMs).  M <= 128. */
+/* "Partials" mode (B200-native fusion of the GEMM's cross-CTA reduction into its consumer).
+ * The GEMM is stream-K: the (n tile, k tile) units are cut into equal contiguous shares, one per
+ * CTA, and every CTA writes the fp32 partial of each tile it touches to
+ * partials[slot][M][N], slot = its rank among that tile's contributors.  The consumer
+ * (b200_rms_norm_residual_splitk, b200_ar_allreduce_splitk, or the reduction pass of
+ * b200_w4a16_gemm) recomputes the same partition from (N, K), sums each tile's slots in slot
+ * order and rounds once to the element type — exactly what a GEMM epilogue would have stored.
+ * Replaces the o_proj / down_proj + residual add + RMSNorm sequence of
+ * models/meta/llama.h:170-177.  b200_w4a16_splitk_splits returns the slot count the partials
+ * buffer must have for a [K, N] weight on the current device (<= 8).  M <= 128. */
 B200_API int b200_w4a16_splitk_splits(int64_t M, int64_t N, int64_t K);
 B200_API int b200_w4a16_gemm_splitk(float* partials, const void* A, const void* packed, int64_t M,
                                     int64_t N, int64_t K, int64_t lda, int group_size, int splits,
                                     b200_stream_t stream);
-/* residual += T(sum_s partials[s]); out = rms_norm(residual) * weight.  partials: [splits, rows, n] fp32. */
+/* C[M, N] bf16 (row stride ldc) = bf16(sum_slots partials) (+ bias): the plain reduction pass. */
+B200_API int b200_w4a16_reduce_partials(void* C, const float* partials, int splits, int64_t gemm_k,
+                                        const void* bias, int64_t M, int64_t N, int64_t ldc,
+                                        b200_stream_t stream);
+/* residual += T(sum_slots partials); out = rms_norm(residual) * weight.
+ * partials: [splits, rows, n] fp32 from a GEMM with reduction dimension gemm_k. */
 B200_API int b200_rms_norm_residual_splitk(void* out, void* residual, const float* partials,
-                                           int splits, const void* weight, int64_t rows, int64_t n,
-                                           float eps, int dtype, b200_stream_t stream);
+                                           int splits, int64_t gemm_k, const void* weight,
+                                           int64_t rows, int64_t n, float eps, int dtype,
+                                           b200_stream_t stream);
 
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
@@ -272,11 +282,13 @@ B200_API int b200_ar_open_peers(b200_ar_comm* comm,
 /* In-place sum of data[count] (bf16/fp16/fp32) over all ranks, on `stream`. */
 B200_API int b200_ar_allreduce(b200_ar_comm* comm, void* data, int64_t count,
                                int dtype, b200_stream_t stream);
-/* Same reduction, but this rank's input is the producing GEMM's split-K partials
- * [splits][count] fp32 (b200_w4a16_gemm_splitk): the copy-in stage sums them and rounds once,
- * so the row-parallel GEMM needs no fix-up pass of its own.  out: [count] bf16/fp16. */
+/* Same reduction, but this rank's input is the producing GEMM's stream-K partials
+ * [splits][count] fp32 (b200_w4a16_gemm_splitk of a [gemm_k, n] weight, count = rows * n): the
+ * copy-in stage sums each tile's slots and rounds once, so the row-parallel GEMM needs no
+ * reduction pass of its own.  out: [count] bf16/fp16. */
 B200_API int b200_ar_allreduce_splitk(b200_ar_comm* comm, void* out, const float* partials,
-                                      int splits, int64_t count, int dtype, b200_stream_t stream);
+                                      int splits, int64_t gemm_k, int64_t n, int64_t count,
+                                      int dtype, b200_stream_t stream);
 B200_API int b200_ar_destroy(b200_ar_comm* comm);
 
 #ifdef __cplusplus

@@ -15,7 +15,6 @@ LIB_PATH = os.path.join(_HERE, "libb200decode.so")
 
 B200_BF16, B200_FP16, B200_FP32 = 0, 1, 2
 AR_HANDLE_BYTES = 128
-W4A16_COUNTER_BYTES = 16384
 
 
 class B200Error(RuntimeError):
@@ -60,12 +59,13 @@ SIGNATURES = {
                                _vp]),
     "b200_w4a16_splitk_splits": (_int, [_i64, _i64, _i64]),
     "b200_w4a16_gemm_splitk": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
-    "b200_rms_norm_residual_splitk": (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _f32, _int, _vp]),
+    "b200_w4a16_reduce_partials": (_int, [_vp, _vp, _int, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "b200_rms_norm_residual_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _i64, _i64, _f32, _int, _vp]),
     "b200_debug_set_trace": (None, [_vp]),
     "b200_ar_create": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp]),
     "b200_ar_open_peers": (_int, [_vp, _vp]),
     "b200_ar_allreduce": (_int, [_vp, _vp, _i64, _int, _vp]),
-    "b200_ar_allreduce_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp]),
+    "b200_ar_allreduce_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_destroy": (_int, [_vp]),
 }
 

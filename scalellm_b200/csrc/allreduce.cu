@@ -76,15 +76,17 @@ __device__ __forceinline__ void accum16(float (&acc)[16 / sizeof(T)], uint4 v) {
   for (int i = 0; i < (int)(16 / sizeof(T)); ++i) acc[i] += Num<T>::to_f(e[i]);
 }
 
-// partials != nullptr: the local input is the producing GEMM's split-K partials [S][count] fp32;
-// the copy-in stage sums them (fixed order) and rounds once to T — the GEMM epilogue's job.
+// partials != nullptr: the local input is the producing GEMM's stream-K partials [slots][count]
+// fp32 (row length row_n); the copy-in stage sums each tile's contributor slots (fixed order) and
+// rounds once to T — the GEMM epilogue's job.
 template <typename T>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs ptrs, T* data,
                                                                       int64_t nvec, int rank,
                                                                       int world,
                                                                       int64_t max_bytes,
                                                                       const float* partials,
-                                                                      int S, int64_t split_stride) {
+                                                                      W4Plan plan, int row_n,
+                                                                      int64_t split_stride) {
   constexpr int VEC = 16 / sizeof(T);
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
@@ -104,13 +106,9 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
     for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) mine[i] = src[i];
   } else if constexpr (sizeof(T) == 2) {
     for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int sp = 0; sp < S; ++sp) {
-        const float4* pp = reinterpret_cast<const float4*>(partials + sp * split_stride) + 2 * i;
-        const float4 lo = __ldcg(pp), hi = __ldcg(pp + 1);
-        a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
-        a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
-      }
+      float a[8];
+      const int col = (int)((i * 8) % row_n);  // 8 consecutive columns of one row, inside one n tile
+      w4_sum_partials8(a, partials + i * 8, split_stride, w4_contrib_col(plan, col));
       uint4 o;
       T* oe = reinterpret_cast<T*>(&o);
 #pragma unroll
@@ -214,23 +212,29 @@ int b200_ar_open_peers(b200_ar_comm* c, const void* all_handles) {
 }
 
 static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, const float* partials,
-                     int S, b200_stream_t stream);
+                     const W4Plan& plan, int64_t row_n, b200_stream_t stream);
 
 int b200_ar_allreduce(b200_ar_comm* c, void* data, int64_t count, int dtype,
                       b200_stream_t stream) {
-  return ar_launch(c, data, count, dtype, nullptr, 0, stream);
+  return ar_launch(c, data, count, dtype, nullptr, W4Plan{}, 0, stream);
 }
 
 int b200_ar_allreduce_splitk(b200_ar_comm* c, void* out, const float* partials, int splits,
-                             int64_t count, int dtype, b200_stream_t stream) {
-  B200_CHECK_ARG(partials && splits >= 1, "ar_allreduce_splitk: bad partials");
+                             int64_t gemm_k, int64_t n, int64_t count, int dtype,
+                             b200_stream_t stream) {
+  B200_CHECK_ARG(partials && n > 0 && n % 128 == 0 && gemm_k > 0 && gemm_k % 128 == 0 &&
+                     count % n == 0,
+                 "ar_allreduce_splitk: partials of a [K, N] GEMM: n %% 128 == 0, count %% n == 0");
+  const W4Plan plan = w4_get_plan(n, gemm_k, count / n);
+  B200_CHECK_ARG(splits == plan.slots, "ar_allreduce_splitk: expected %d partial slots, got %d",
+                 plan.slots, splits);
   B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "ar_allreduce_splitk: bf16 / fp16 output");
   B200_CHECK_ARG(c && c->world > 1, "ar_allreduce_splitk: needs world_size > 1");
-  return ar_launch(c, out, count, dtype, partials, splits, stream);
+  return ar_launch(c, out, count, dtype, partials, plan, n, stream);
 }
 
 static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, const float* partials,
-                     int S, b200_stream_t stream) {
+                     const W4Plan& plan, int64_t row_n, b200_stream_t stream) {
   B200_CHECK_ARG(c && data, "ar_allreduce: null pointer");
   B200_CHECK_ARG(dtype >= 0 && dtype <= 2, "ar_allreduce: bad dtype");
   if (count == 0 || c->world == 1) return B200_OK;
@@ -253,16 +257,16 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
     case B200_BF16:
       allreduce_oneshot_kernel<__nv_bfloat16><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<__nv_bfloat16*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
-          S, count);
+          plan, (int)row_n, count);
       break;
     case B200_FP16:
       allreduce_oneshot_kernel<__half><<<blocks, AR_THREADS, 0, st>>>(
-          ptrs, static_cast<__half*>(data), nvec, c->rank, c->world, c->max_bytes, partials, S,
-          count);
+          ptrs, static_cast<__half*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
+          plan, (int)row_n, count);
       break;
     default:
       allreduce_oneshot_kernel<float><<<blocks, AR_THREADS, 0, st>>>(
-          ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes, nullptr, 0, 0);
+          ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes, nullptr, W4Plan{}, 0, 0);
       break;
   }
   B200_LAUNCH_OK("allreduce_oneshot");

@@ -332,4 +332,75 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);  // m_dim
 }
 
+// ---------------------------------------------------------------------------
+// W4A16 stream-K partition, shared by the GEMM and by every kernel that consumes its fp32
+// partials.  The (n tile, k tile) units of C = A * W (k fastest) are cut into P equal contiguous
+// shares, CTA p owns [w4_unit_begin(p), w4_unit_begin(p+1)).  A tile nt is covered by the
+// consecutive CTAs first..last; CTA p writes its part of tile nt to partial slot (p - first), so
+// a consumer sums slots [0, w4_contrib(nt)) of that tile's columns — no atomics, no fix-up pass.
+// An "n tile" of the partition is 128 << nsub_log2 output columns (two weight tiles share one
+// activation stage when the batch fits 64 rows, halving the activation traffic out of L2).
+// ---------------------------------------------------------------------------
+struct W4Plan {
+  int units, P, KT, NT, slots;  // slots = max contributors of any tile (partials buffer depth)
+  int nsub_log2;                // 128-column weight tiles per n tile of the partition: 1 << nsub_log2
+};
+__host__ __device__ __forceinline__ int w4_unit_begin(int p, int units, int P) {
+  return (int)(((long long)p * units) / P);
+}
+// CTA that owns unit u (largest p with begin(p) <= u)
+__host__ __device__ __forceinline__ int w4_owner(int u, int units, int P) {
+  int p = (int)((((long long)u + 1) * P - 1) / units);
+  if (p > P - 1) p = P - 1;
+  while (p > 0 && w4_unit_begin(p, units, P) > u) --p;
+  while (p + 1 < P && w4_unit_begin(p + 1, units, P) <= u) ++p;
+  return p;
+}
+__host__ __device__ __forceinline__ int w4_first_owner(const W4Plan& pl, int nt) {
+  return w4_owner(nt * pl.KT, pl.units, pl.P);
+}
+__host__ __device__ __forceinline__ int w4_contrib(const W4Plan& pl, int nt) {
+  return w4_owner(nt * pl.KT + pl.KT - 1, pl.units, pl.P) - w4_owner(nt * pl.KT, pl.units, pl.P) + 1;
+}
+// contributors of the partition tile that holds output column `col`
+__host__ __device__ __forceinline__ int w4_contrib_col(const W4Plan& pl, int col) {
+  return w4_contrib(pl, col >> (7 + pl.nsub_log2));
+}
+constexpr int W4_MAX_SLOTS = 8;
+// The partition b200_w4a16_gemm_splitk uses for M rows x a [K, N] weight on the current device.
+W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M);
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks
+// until the predecessor has completed and its writes are visible.  pdl_launch_dependents() in
+// the predecessor allows that early start (no-ops when PDL is not in use).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// Sum of the partial slots of 8 consecutive columns (one 32-byte group inside one n tile) of
+// row `row_ptr`: all loads are issued up front (one L2 round trip), fixed summation order.
+__device__ __forceinline__ void w4_sum_partials8(float (&a)[8], const float* __restrict__ p0,
+                                                 int64_t slot_stride, int count) {
+  float4 lo[W4_MAX_SLOTS], hi[W4_MAX_SLOTS];
+#pragma unroll
+  for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
+    const int spc = sp < count ? sp : count - 1;  // clamped; the duplicate is weighted 0 below
+    const float4* src = reinterpret_cast<const float4*>(p0 + spc * slot_stride);
+    lo[sp] = __ldcg(src);
+    hi[sp] = __ldcg(src + 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+#pragma unroll
+  for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
+    const float wgt = sp < count ? 1.f : 0.f;
+    a[0] = fmaf(lo[sp].x, wgt, a[0]); a[1] = fmaf(lo[sp].y, wgt, a[1]);
+    a[2] = fmaf(lo[sp].z, wgt, a[2]); a[3] = fmaf(lo[sp].w, wgt, a[3]);
+    a[4] = fmaf(hi[sp].x, wgt, a[4]); a[5] = fmaf(hi[sp].y, wgt, a[5]);
+    a[6] = fmaf(hi[sp].z, wgt, a[6]); a[7] = fmaf(hi[sp].w, wgt, a[7]);
+  }
+}
+
 }  // namespace b200

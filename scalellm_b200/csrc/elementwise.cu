@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
                                                                float eps, int n) {
   constexpr int VEC = 16 / sizeof(T);
   __shared__ float red[32];
+  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   const T* in_row = in + row * n;
@@ -162,16 +163,17 @@ static int launch_rms_norm(void* out, void* residual, const void* in, const void
 }
 
 
-// Residual RMSNorm whose `in` operand arrives as S split-K partials in fp32 (the W4A16 GEMM's
-// partial mode): x = T(sum_s P[s][row][:]) — the single rounding the GEMM epilogue would have
-// done — then exactly rms_norm_residual.  One CTA per row, row held in registers.
+// Residual RMSNorm whose `in` operand arrives as the W4A16 GEMM's stream-K partials in fp32:
+// x = T(sum over the tile's contributor slots of P[slot][row][:]) — the single rounding a GEMM
+// epilogue would have done — then exactly rms_norm_residual.  One CTA per row, row in registers.
 template <typename T, int THREADS, int MAXV>
 __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
-    T* __restrict__ out, T* __restrict__ residual, const float* __restrict__ partials, int S,
+    T* __restrict__ out, T* __restrict__ residual, const float* __restrict__ partials, W4Plan plan,
     int64_t split_stride, const T* __restrict__ weight, float eps, int n) {
   constexpr int VEC = 16 / sizeof(T);
   static_assert(VEC == 8, "16-bit element types only");
   __shared__ float red[32];
+  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   T* res_row = residual + row * n;
@@ -184,25 +186,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
     const int v = threadIdx.x + j * THREADS;
     if (v < nvec) {
       float a[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) a[i] = 0.f;
-      // all (<= 8) partials are requested up front: one L2 round trip instead of S
-      float4 lo[8], hi[8];
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {
-        const int spc = sp < S ? sp : S - 1;  // clamped, the duplicate is weighted 0 below
-        const float4* src = reinterpret_cast<const float4*>(p_row + spc * split_stride + v * VEC);
-        lo[sp] = __ldcg(src);
-        hi[sp] = __ldcg(src + 1);
-      }
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {  // fixed order: deterministic
-        const float wgt = sp < S ? 1.f : 0.f;
-        a[0] = fmaf(lo[sp].x, wgt, a[0]); a[1] = fmaf(lo[sp].y, wgt, a[1]);
-        a[2] = fmaf(lo[sp].z, wgt, a[2]); a[3] = fmaf(lo[sp].w, wgt, a[3]);
-        a[4] = fmaf(hi[sp].x, wgt, a[4]); a[5] = fmaf(hi[sp].y, wgt, a[5]);
-        a[6] = fmaf(hi[sp].z, wgt, a[6]); a[7] = fmaf(hi[sp].w, wgt, a[7]);
-      }
+      w4_sum_partials8(a, p_row + v * VEC, split_stride, w4_contrib_col(plan, v * VEC));
       uint4 rraw = ld_v4(res_row + v * VEC);
       const T* r = reinterpret_cast<const T*>(&rraw);
       uint4 sraw;
@@ -239,7 +223,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
 }
 
 template <typename T>
-static int launch_rms_norm_splitk(void* out, void* residual, const float* partials, int S,
+static int launch_rms_norm_splitk(void* out, void* residual, const float* partials, W4Plan S,
                                   int64_t split_stride, const void* weight, int64_t rows,
                                   int64_t n, float eps, cudaStream_t st) {
   T* o = static_cast<T*>(out);
@@ -483,6 +467,7 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
                                                    int64_t n, int64_t a_stride, int64_t b_stride,
                                                    bool vec) {
   constexpr int VEC = 16 / sizeof(T);
+  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
   if (vec) {
     const int64_t nv = n / VEC;
     const int64_t total = rows * nv;
@@ -577,11 +562,15 @@ int b200_rms_norm_residual(void* out, void* residual, const void* in, const void
 }
 
 int b200_rms_norm_residual_splitk(void* out, void* residual, const float* partials, int splits,
-                                  const void* weight, int64_t rows, int64_t n, float eps, int dtype,
-                                  b200_stream_t stream) {
+                                  int64_t gemm_k, const void* weight, int64_t rows, int64_t n,
+                                  float eps, int dtype, b200_stream_t stream) {
   B200_CHECK_ARG(out && residual && partials && weight, "rms_norm_residual_splitk: null pointer");
-  B200_CHECK_ARG(splits >= 1 && splits <= 8 && rows >= 0 && n > 0 && n % 8 == 0 && n <= 32768,
-                 "rms_norm_residual_splitk: need n %% 8 == 0, n <= 32768, 1 <= splits <= 8");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n % 128 == 0 && n <= 32768 && gemm_k > 0 && gemm_k % 128 == 0,
+                 "rms_norm_residual_splitk: need n %% 128 == 0, n <= 32768, gemm_k %% 128 == 0");
+  const W4Plan plan = w4_get_plan(n, gemm_k, rows);
+  B200_CHECK_ARG(splits == plan.slots,
+                 "rms_norm_residual_splitk: partials of a [K=%lld, N=%lld] GEMM have %d slots, got %d",
+                 (long long)gemm_k, (long long)n, plan.slots, splits);
   B200_CHECK_ARG(is_aligned(out, 16) && is_aligned(residual, 16) && is_aligned(partials, 16) &&
                      is_aligned(weight, 16),
                  "rms_norm_residual_splitk: 16-byte alignment required");
@@ -590,10 +579,10 @@ int b200_rms_norm_residual_splitk(void* out, void* residual, const float* partia
   const int64_t stride = rows * n;
   switch (dtype) {
     case B200_BF16:
-      return launch_rms_norm_splitk<__nv_bfloat16>(out, residual, partials, splits, stride, weight,
+      return launch_rms_norm_splitk<__nv_bfloat16>(out, residual, partials, plan, stride, weight,
                                                    rows, n, eps, st);
     case B200_FP16:
-      return launch_rms_norm_splitk<__half>(out, residual, partials, splits, stride, weight, rows, n,
+      return launch_rms_norm_splitk<__half>(out, residual, partials, plan, stride, weight, rows, n,
                                             eps, st);
     default:
       return set_error(B200_ERR_UNSUPPORTED, "rms_norm_residual_splitk: bf16 / fp16 only");

@@ -1076,6 +1076,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
   constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8
+  pdl_launch_dependents();  // a following W4A16 GEMM (o_proj) may start prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x * 4 + warp;
   if (h >= p.n_heads) return;

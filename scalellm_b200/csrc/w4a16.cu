@@ -13,7 +13,7 @@
 //   * weights live in HBM as self-contained "tile blobs" (128 n x 128 k: packed
 //     nibbles + that tile's scales + zero points), streamed with one bulk-async
 //     copy per blob into a deep shared-memory ring;
-//   * two groups of 4 dequant warps alternate k-tiles: a thread owns one weight row (one
+//   * four groups of 4 dequant warps take k-tiles round-robin: a thread owns one weight row (one
 //     TMEM lane), turns its 16 packed words into 128 bf16 (lop3 magic-number int4->bf16,
 //     HSUB2 zero point, HMUL2 scale) and writes them with tcgen05.st straight into TENSOR
 //     MEMORY, where they are the A operand of the UMMA — no shared-memory staging, no
@@ -21,8 +21,11 @@
 //   * one thread issues tcgen05.mma (kind::f16, A from TMEM, M=128, N=MT, K=16) with the
 //     accumulator in TMEM (double buffered); activations arrive by TMA (128B swizzle);
 //   * stream-K over (n_tile, k_tile) units so all SMs stream an equal share of
-//     the weight bytes; partial tiles meet in an fp32 workspace and the last
-//     arriving CTA reduces them in a fixed order (deterministic).
+//     the weight bytes; every CTA writes the fp32 partial of each of its segments to a slot of
+//     the partials buffer (slot = its rank among the tile's contributors, common.cuh W4Plan)
+//     and the CONSUMER of the GEMM sums the slots in a fixed order (deterministic): the
+//     following RMSNorm, the TP all-reduce's copy-in, or w4_reduce_kernel for a plain bf16 C.
+//     No atomics, no fix-up tail in the GEMM.
 //
 // W4 tile blob (n_tile nt, k_tile kt) at ((nt * K/128) + kt) * blob_bytes:
 //   [0, 8192)            qdata: uint4[(khalf*2+q4)*128 + n_local]; word w of that
@@ -31,6 +34,7 @@
 //   [8192, +ngrp*256)    scales bf16 [ngrp][128]     (ngrp = 128/geff, geff = min(g,128))
 //   [.., +ngrp*128)      zero points, uint8 [ngrp][128] (0..16: GPTQ-v1 "zero+1" can reach 16)
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -227,53 +231,44 @@ __global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
 }
 
 // ===========================================================================
-// tcgen05 stream-K GEMM
+// tcgen05 stream-K GEMM (partials out)
 // ===========================================================================
-// CFG selects the shared-memory split between the activation ring (L2/TMA latency) and the
-// weight-blob ring (HBM latency); B200_W4_CFG picks one at run time while tuning.
-template <int MT, int CFG>
+template <int MT, int NSUB>
 struct W4Cfg {
-  static constexpr int ACT_STAGES = MT <= 64 ? (CFG == 0 ? 3 : CFG == 1 ? 6 : 8) : (CFG == 0 ? 2 : 3);
-  static constexpr int A_STAGES = 4;              // dequantised-weight stages in TMEM
+  static constexpr int ACT_STAGES = MT <= 64 ? 6 : 3;   // activation ring (L2 / TMA latency)
+  static constexpr int RAW_STAGES = MT <= 64 ? 11 : 10; // weight-blob ring (HBM latency)
+  static constexpr int A_STAGES = 4;              // dequantised-weight slots in TMEM, one per dequant group
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
-  static constexpr int RAW_STAGES =
-      MT <= 64 ? (CFG == 0 ? 16 : CFG == 1 ? 11 : 7) : (CFG == 0 ? 14 : 10);
-  static constexpr int ACC_COLS = 2 * MT;         // two accumulators [128 x MT] fp32
-  static constexpr int A_COL0 = ACC_COLS;         // A ring: A_STAGES x 64 columns (128 k of bf16)
+  static constexpr int ACC_COLS = 2 * NSUB * MT;  // two buffers of NSUB accumulators [128 x MT] fp32
+  static constexpr int A_COL0 = 256;              // A ring: A_STAGES x 64 columns (128 k of bf16)
   static constexpr int TMEM_COLS = 512;
   static constexpr int N_BARS = 2 * RAW_STAGES + 2 * ACT_STAGES + 2 * A_STAGES + 4;
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)ACT_STAGES * ACT_BYTES +
                                  (size_t)RAW_STAGES * RAW_BYTES + N_BARS * 8 + 64;
-  static_assert(A_COL0 + A_STAGES * 64 <= TMEM_COLS, "TMEM over-subscribed");
+  static_assert(ACC_COLS <= A_COL0 && A_COL0 + A_STAGES * 64 <= TMEM_COLS, "TMEM over-subscribed");
 };
 
-constexpr int W4_DEQ_WARPS = 8;
-constexpr int W4_DEQ_GROUPS = 2;  // groups of 4 warps (one warp per TMEM lane quadrant) alternate k-tiles
-constexpr int W4_WARP_RAW = 8, W4_WARP_ACT = 9, W4_WARP_MMA = 10, W4_WARP_EPI = 11;
-constexpr int W4_THREADS = 15 * 32;
+// warp roles: 0-15 dequant (4 groups x 4 lane quadrants), 16 weight-blob producer, 17 activation
+// producer, 18 MMA issuer, 19 idle, 20-23 epilogue (lane quadrant = warp % 4)
+constexpr int W4_DEQ_GROUPS = 4;
+constexpr int W4_DEQ_WARPS = 4 * W4_DEQ_GROUPS;
+constexpr int W4_WARP_RAW = 16, W4_WARP_ACT = 17, W4_WARP_MMA = 18, W4_WARP_EPI = 20;
+constexpr int W4_THREADS = 24 * 32;
 
 struct W4Params {
   const uint8_t* packed;
-  __nv_bfloat16* C;
-  const __nv_bfloat16* bias;
-  float* ws_partial;  // [2*P][MT][128]
-  int* counters;      // [NT]
-  int M, N, K, KT, NT, geff, ngrp, blob_bytes, units;
-  int64_t ldc;
-  long long* trace;  // debug: [grid][32] clock64 milestones / wait totals (null in production)
-  float* splitk_out;  // != null: regular split-K, every CTA writes its fp32 partial to
-  int splitk_S;       //          splitk_out[split][m][n] and the CONSUMER kernel reduces
+  float* partials;        // [slots][M][N] fp32
+  int64_t slot_stride;    // M * N
+  int M, N, KT, geff_log2, ngrp, blob_bytes;
+  W4Plan plan;
+  long long* trace;       // debug: [grid][16] clock64 milestones (null in production)
 };
 
-#define W4_TRACE_ADD(slot, cyc)                                          \
-  do {                                                                   \
-    if (p.trace) p.trace[(int64_t)blockIdx.x * 32 + (slot)] += (cyc);    \
-  } while (0)
-#define W4_TRACE(slot)                                                   \
-  do {                                                                   \
-    if (p.trace) p.trace[(int64_t)blockIdx.x * 32 + (slot)] = clock64(); \
+#define W4_TRACE(slot)                                                               \
+  do {                                                                               \
+    if constexpr (TRACE) p.trace[(int64_t)blockIdx.x * 16 + (slot)] = clock64();     \
   } while (0)
 
 struct SegIter {
@@ -288,21 +283,31 @@ struct SegIter {
   }
 };
 
-__device__ __forceinline__ int w4_unit_begin(int p, int units, int P) {
-  return (int)(((int64_t)p * units) / P);
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(addr));
+  return r;
 }
-// CTA that owns unit u (largest p with begin(p) <= u)
-__device__ __forceinline__ int w4_owner(int u, int units, int P) {
-  int p = (int)min((int64_t)P - 1, ((int64_t)u * P) / units);
-  while (p > 0 && w4_unit_begin(p, units, P) > u) --p;
-  while (p + 1 < P && w4_unit_begin(p + 1, units, P) <= u) ++p;
-  return p;
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
 }
 
-template <int MT, int CFG>
+// NSUB weight tiles (adjacent n tiles, same k tile) share one activation stage: the activation
+// bytes pulled out of L2 per weight tile drop by NSUB (the kernel is L2-bandwidth bound on them:
+// every CTA re-reads the [MT x 128] activation tile of each of its k tiles).
+template <int MT, int NSUB, bool TRACE>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
-  using Cfg = W4Cfg<MT, CFG>;
+  using Cfg = W4Cfg<MT, NSUB>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -318,20 +323,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   uint64_t* tmem_full = deq_empty + Cfg::A_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* flag_smem = tmem_holder + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = gridDim.x;
+  const int KT = p.KT;
   if (threadIdx.x == 0) W4_TRACE(0);
-  int u_begin, u_end;
-  if (p.splitk_out) {  // regular split-K: CTA = (n tile, K slice), exactly one segment
-    const int nt_ = blockIdx.x / p.splitk_S, sp_ = blockIdx.x % p.splitk_S;
-    u_begin = nt_ * p.KT + (int)(((int64_t)sp_ * p.KT) / p.splitk_S);
-    u_end = nt_ * p.KT + (int)(((int64_t)(sp_ + 1) * p.KT) / p.splitk_S);
-  } else {             // stream-K: equal share of the (n tile, k tile) units
-    u_begin = w4_unit_begin(blockIdx.x, p.units, P);
-    u_end = w4_unit_begin(blockIdx.x + 1, p.units, P);
-  }
+  const int u_begin = w4_unit_begin(blockIdx.x, p.plan.units, p.plan.P);
+  const int u_end = w4_unit_begin(blockIdx.x + 1, p.plan.units, p.plan.P);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
@@ -365,169 +362,139 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
-    // group = warp / 4 takes k-tiles cnt % 2 == group; inside a group warp q = warp % 4 owns
-    // TMEM lanes [32q, 32q+32): thread <-> weight row n_local, all 128 k of the tile.
+    // group = warp / 4 takes k-tiles cnt % 4 == group and owns TMEM slot `group`; inside a group
+    // warp q = warp % 4 owns TMEM lanes [32q, 32q+32): thread <-> weight row n_local, all 128 k.
     const int group = warp >> 2;
     const int n_local = (warp & 3) * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0;
-    SegIter it{u_begin, u_end, p.KT};
-    int nt, kt0, kt1, cnt = 0;
-    long long w_raw = 0, w_empty = 0;
-    int pend_as = -1, pend_rs = -1;
+    const uint32_t a_tmem =
+        tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0 + group * 64;
+    const uint32_t raw_u32 = smem_u32(raw_smem);
+    const uint32_t sz_off = W4_QBYTES + n_local * 2;               // this row's scale, group 0
+    const uint32_t zp_off = W4_QBYTES + p.ngrp * 256 + n_local;    // this row's zero point
+    SegIter it{u_begin, u_end, KT};
+    int nt, kt0, kt1, cnt = 0;  // cnt counts WEIGHT tiles (NSUB per unit)
     while (it.next(nt, kt0, kt1)) {
-      for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+      for (int kt = kt0; kt < kt1; ++kt)
+      for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
         if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
-        const int rs = cnt % Cfg::RAW_STAGES, as = cnt % Cfg::A_STAGES;
-        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
-        const uint8_t* raw = raw_smem + rs * Cfg::RAW_BYTES;
-        const long long tq0 = p.trace ? clock64() : 0;
+        const int rs = cnt % Cfg::RAW_STAGES;
+        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt >> 2) & 1;
+        const uint32_t raw = raw_u32 + rs * Cfg::RAW_BYTES;
         mbar_wait(&raw_full[rs], rph);
-        if (p.trace) w_raw += clock64() - tq0;
-        if (threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
-        uint4 u[4];
+        if (TRACE && threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          u[q] = *reinterpret_cast<const uint4*>(raw + (q * 128 + n_local) * 16);
-        const __nv_bfloat16* s_in = reinterpret_cast<const __nv_bfloat16*>(raw + W4_QBYTES);
-        const uint8_t* z_in = raw + W4_QBYTES + p.ngrp * 256;
-        // uint4 q covers k in [32q, 32q+32): its quant group is (32q)/geff (geff in {32,64,128})
-        __nv_bfloat162 s2[4], zm[4];
+        for (int hh = 0; hh < 2; ++hh) {  // 64 k = 32 TMEM columns per tcgen05.st
+          uint4 u[2];
+          __nv_bfloat162 s2[2], zm[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int gq = (q * 32) / p.geff;
-          const __nv_bfloat16 sv = s_in[gq * 128 + n_local];
-          s2[q] = __halves2bfloat162(sv, sv);
-          zm[q] = w4_zmagic(z_in[gq * 128 + n_local]);
-        }
-        const long long tq1 = p.trace ? clock64() : 0;
-        mbar_wait(&deq_empty[as], aph ^ 1);
-        if (p.trace) w_empty += clock64() - tq1;
-        tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {  // 64 k = 32 columns per tcgen05.st
+          for (int q = 0; q < 2; ++q) {
+            // uint4 (hh, q) covers k in [32 (2hh+q), +32): quant group (32 (2hh+q)) >> log2(geff)
+            const int qq = hh * 2 + q;
+            u[q] = lds128(raw + (qq * 128 + n_local) * 16);
+            const int gq = (qq * 32) >> p.geff_log2;
+            const uint32_t sv = lds_u16(raw + sz_off + gq * 256);
+            const uint32_t sv2 = sv | (sv << 16);
+            s2[q] = *reinterpret_cast<const __nv_bfloat162*>(&sv2);
+            zm[q] = w4_zmagic(lds_u8(raw + zp_off + gq * 128));
+          }
           uint32_t r[32];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const uint4 uu = u[hh * 2 + q];
-            const uint32_t words[4] = {uu.x, uu.y, uu.z, uu.w};
+            const uint32_t words[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              const uint4 d = w4_dequant_word(words[w], zm[hh * 2 + q], s2[hh * 2 + q]);
+              const uint4 d = w4_dequant_word(words[w], zm[q], s2[q]);
               r[(q * 4 + w) * 4 + 0] = d.x;
               r[(q * 4 + w) * 4 + 1] = d.y;
               r[(q * 4 + w) * 4 + 2] = d.z;
               r[(q * 4 + w) * 4 + 3] = d.w;
             }
           }
-          if (hh == 0 && pend_as >= 0) {
-            // publish the PREVIOUS tile only now: its TMEM stores had half a tile of math to land
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&deq_full[pend_as]);
-              mbar_arrive(&raw_empty[pend_rs]);
-            }
+          if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
+            mbar_wait(&deq_empty[group], aph ^ 1);
+            tc_fence_after();
           }
-          tmem_st_32x32b_x32(lane_base + as * 64 + hh * 32, r);
+          tmem_st_32x32b_x32(a_tmem + hh * 32, r);
         }
-        pend_as = as;
-        pend_rs = rs;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&deq_full[group]);
+          mbar_arrive(&raw_empty[rs]);
+        }
       }
     }
-    if (pend_as >= 0) {
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&deq_full[pend_as]);
-        mbar_arrive(&raw_empty[pend_rs]);
-      }
-    }
-    if (threadIdx.x == 0) {
-      W4_TRACE(3);
-      W4_TRACE_ADD(18, w_raw);
-      W4_TRACE_ADD(19, w_empty);
-    }
+    if (threadIdx.x == 0) W4_TRACE(3);
   } else if (warp == W4_WARP_RAW) {
     // ===================== weight-blob producer ==============================
+    // Weights are never written by another kernel: under programmatic dependent launch this
+    // warp starts streaming them while the predecessor kernel is still running (no pdl_wait).
     if (lane == 0) {
-      SegIter it{u_begin, u_end, p.KT};
+      SegIter it{u_begin, u_end, KT};
       int nt, kt0, kt1, cnt = 0;
-      long long w_wait = 0;
       while (it.next(nt, kt0, kt1)) {
-        for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+        for (int kt = kt0; kt < kt1; ++kt)
+        for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
           const int rs = cnt % Cfg::RAW_STAGES;
           const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1;
-          const long long tr0 = p.trace ? clock64() : 0;
           mbar_wait(&raw_empty[rs], rph ^ 1);
-          if (p.trace) w_wait += clock64() - tr0;
           mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)p.blob_bytes);
           bulk_load_1d(raw_smem + rs * Cfg::RAW_BYTES,
-                       p.packed + ((int64_t)nt * p.KT + kt) * p.blob_bytes, (uint32_t)p.blob_bytes,
-                       &raw_full[rs]);
+                       p.packed + ((int64_t)(nt * NSUB + sub) * KT + kt) * p.blob_bytes,
+                       (uint32_t)p.blob_bytes, &raw_full[rs]);
         }
       }
-      W4_TRACE_ADD(21, w_wait);
     }
     __syncwarp();  // reconverge before the CTA-wide barrier at the end
   } else if (warp == W4_WARP_ACT) {
     // ===================== activation producer (TMA) =========================
     if (lane == 0) {
-      SegIter it{u_begin, u_end, p.KT};
+      pdl_wait();  // activations are the predecessor kernel's output
+      SegIter it{u_begin, u_end, KT};
       int nt, kt0, kt1, cnt = 0;
-      long long w_wait = 0;
       while (it.next(nt, kt0, kt1)) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          const long long ta0 = p.trace ? clock64() : 0;
           mbar_wait(&act_empty[as], aph ^ 1);
-          if (p.trace) w_wait += clock64() - ta0;
           mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
           tma_load_2d(dst + Cfg::ACT_ATOM, &amap, &act_full[as], kt * 128 + 64, 0);
         }
       }
-      W4_TRACE_ADD(20, w_wait);
     }
-    __syncwarp();  // reconverge before the CTA-wide barrier at the end
+    __syncwarp();
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
     // The whole warp runs this loop converged so every operand is warp-uniform (uniform
     // registers, no per-instruction ELECT/R2UR loop); one elected lane issues the UMMAs.
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
-      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
-      SegIter it{u_begin, u_end, p.KT};
-      int nt, kt0, kt1, cnt = 0, seg = 0;
-      long long w_act = 0, w_deq = 0, w_tmem = 0;
-      while (it.next(nt, kt0, kt1)) {
-        const int buf = seg & 1;
-        const uint32_t tph = (seg >> 1) & 1;
-        const long long tt0 = p.trace ? clock64() : 0;
-        mbar_wait(&tmem_empty[buf], tph ^ 1);
-        if (p.trace) w_tmem += clock64() - tt0;
-        tc_fence_after();
-        const uint32_t d_tmem = tbase + buf * MT;
-        for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
-          const int as = cnt % Cfg::ACT_STAGES, ds = cnt % Cfg::A_STAGES;
-          const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1, dph = (cnt / Cfg::A_STAGES) & 1;
-          const long long tw0 = p.trace ? clock64() : 0;
-          mbar_wait(&act_full[as], aph);
-          const long long tw1 = p.trace ? clock64() : 0;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
+    SegIter it{u_begin, u_end, KT};
+    int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
+    while (it.next(nt, kt0, kt1)) {
+      const int buf = seg & 1;
+      const uint32_t tph = (seg >> 1) & 1;
+      mbar_wait(&tmem_empty[buf], tph ^ 1);
+      tc_fence_after();
+      for (int kt = kt0; kt < kt1; ++kt, ++ucnt) {
+        const int as = ucnt % Cfg::ACT_STAGES;
+        const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
+        mbar_wait(&act_full[as], aph);
+        const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
+        const uint32_t first = (kt > kt0) ? 1u : 0u;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
+          const int ds = cnt & (Cfg::A_STAGES - 1);
+          const uint32_t dph = (cnt >> 2) & 1;
           mbar_wait(&deq_full[ds], dph);
-          if (p.trace) {
-            w_act += tw1 - tw0;
-            w_deq += clock64() - tw1;
-          }
-          if (cnt == 0 && lane == 0) W4_TRACE(4);
+          if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
           tc_fence_after();
           const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
-          const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
-          const uint32_t first = (kt > kt0) ? 1u : 0u;
+          const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -537,176 +504,95 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
               umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
             }
             umma_commit(&deq_empty[ds]);
-            umma_commit(&act_empty[as]);
-            if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
+            if (sub == NSUB - 1) {
+              umma_commit(&act_empty[as]);
+              if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
+            }
           }
           __syncwarp();
         }
-        ++seg;
       }
-      if (lane == 0) {
-        W4_TRACE(5);
-        W4_TRACE_ADD(16, w_act);
-        W4_TRACE_ADD(17, w_deq);
-        W4_TRACE_ADD(22, w_tmem);
-      }
+      ++seg;
     }
-    __syncwarp();  // reconverge before the CTA-wide barrier at the end
-  } else {
+    if (lane == 0) W4_TRACE(5);
+    __syncwarp();
+  } else if (warp >= W4_WARP_EPI) {
     // ===================== epilogue warps (4) =================================
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may touch
+    // fp32 partial of every segment -> partials[slot][m][n]; slot = position of this CTA among
+    // the tile's contributors.  Lane <-> n, so one store instruction writes 128 contiguous bytes.
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
     const int n_local = quad * 32 + lane;
-    const int et = (warp - W4_WARP_EPI) * 32 + lane;  // 0..127 within the epilogue group
-    SegIter it{u_begin, u_end, p.KT};
+    pdl_wait();  // the partials buffer may still be read by an earlier kernel's consumer
+    SegIter it{u_begin, u_end, KT};
     int nt, kt0, kt1, seg = 0;
     while (it.next(nt, kt0, kt1)) {
       const int buf = seg & 1;
       const uint32_t tph = (seg >> 1) & 1;
-      const bool full_tile = (kt0 == 0 && kt1 == p.KT) && !p.splitk_out;
-      const int n = nt * 128 + n_local;
+      const int slot = (int)blockIdx.x - w4_first_owner(p.plan, nt);
+      float* part = p.partials + (int64_t)slot * p.slot_stride + (int64_t)nt * (128 * NSUB) + n_local;
       mbar_wait(&tmem_full[buf], tph);
-      if (et == 0 && seg == 0) W4_TRACE(6);
+      if (TRACE && warp == W4_WARP_EPI && lane == 0 && seg == 0) W4_TRACE(6);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * MT;
-      float* part = nullptr;
-      int64_t part_ld = 128;
-      if (p.splitk_out) {
-        const int sp_ = blockIdx.x % p.splitk_S;
-        part = p.splitk_out + (int64_t)sp_ * p.M * p.N + (int64_t)nt * 128;
-        part_ld = p.N;
-      } else if (!full_tile) {
-        const int slot = 2 * blockIdx.x + (kt0 > 0 ? 0 : 1);
-        part = p.ws_partial + (int64_t)slot * MT * 128;
-      }
-      float bias_f = 0.f;
-      if (full_tile && p.bias) bias_f = __bfloat162float(p.bias[n]);
       constexpr int CH = MT >= 32 ? 32 : 16;
 #pragma unroll 1
-      for (int c0 = 0; c0 < MT; c0 += CH) {
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r);
-        else tmem_ld_32x32b_x16(taddr + c0, r);
-        tmem_ld_wait();
-        if (full_tile) {
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * NSUB + sub) * MT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < MT; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r);
+          else tmem_ld_32x32b_x16(taddr + c0, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int m = c0 + i;
-            if (m < p.M) {
-              __nv_bfloat16 o = __float2bfloat16_rn(__uint_as_float(r[i]));
-              if (p.bias) o = __float2bfloat16_rn(__bfloat162float(o) + bias_f);
-              p.C[(int64_t)m * p.ldc + n] = o;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const int m = c0 + i;
-            if (m < p.M) part[m * part_ld + n_local] = __uint_as_float(r[i]);
+            if (m < p.M) part[(int64_t)m * p.N + sub * 128] = __uint_as_float(r[i]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      if (et == 0 && seg == 0) W4_TRACE(7);
-
-      if (!full_tile && !p.splitk_out) {
-        // ---- publish the partial; the last contributor reduces the tile -------
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // every partial store of the CTA is issued
-        const int u_lo = nt * p.KT;
-        const int p_first = w4_owner(u_lo, p.units, P);
-        const int p_last = w4_owner(u_lo + p.KT - 1, p.units, P);
-        if (et == 0) {
-          __threadfence();  // one cumulative gpu-scope fence (grid-sync idiom), then publish
-          const int old = atomicAdd(&p.counters[nt], 1);
-          *flag_smem = (old == p_last - p_first) ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) W4_TRACE(8 + (seg > 0 ? 2 : 0));
-        if (*flag_smem) {
-          __threadfence();
-          // Vectorised fixed-order fix-up: thread -> one float4 column group, MT/4 rows, with up
-          // to 8 independent 16-byte L2 loads in flight per contributor.
-          const int n4 = et & 31, mrow0 = et >> 5;
-          constexpr int ROWS = MT / 4;
-          constexpr int RB = ROWS < 8 ? ROWS : 8;
-          const bool vec_store = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
-#pragma unroll 1
-          for (int rb = 0; rb < ROWS; rb += RB) {
-            float4 acc[RB];
-#pragma unroll
-            for (int j = 0; j < RB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int pc = p_first; pc <= p_last; pc += 2) {
-              // two contributors per round trip: 2*RB independent 16-byte L2 loads in flight
-              const float4* src[2];
-              float wgt[2];
-#pragma unroll
-              for (int c2 = 0; c2 < 2; ++c2) {
-                const int pcc = min(pc + c2, p_last);
-                const int cb = max(w4_unit_begin(pcc, p.units, P), u_lo);
-                const int slot = 2 * pcc + (cb > u_lo ? 0 : 1);
-                src[c2] = reinterpret_cast<const float4*>(p.ws_partial + (int64_t)slot * MT * 128) + n4;
-                wgt[c2] = (pc + c2 <= p_last) ? 1.f : 0.f;
-              }
-              float4 v[2][RB];
-#pragma unroll
-              for (int c2 = 0; c2 < 2; ++c2)
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                  const int m = min(mrow0 + 4 * (rb + j), p.M - 1);
-                  v[c2][j] = __ldcg(src[c2] + m * 32);
-                }
-              // fixed order pc, pc+1 (the duplicate of an odd tail is multiplied by 0)
-#pragma unroll
-              for (int c2 = 0; c2 < 2; ++c2)
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                  acc[j].x = fmaf(v[c2][j].x, wgt[c2], acc[j].x);
-                  acc[j].y = fmaf(v[c2][j].y, wgt[c2], acc[j].y);
-                  acc[j].z = fmaf(v[c2][j].z, wgt[c2], acc[j].z);
-                  acc[j].w = fmaf(v[c2][j].w, wgt[c2], acc[j].w);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < RB; ++j) {
-              const int m = mrow0 + 4 * (rb + j);
-              if (m < p.M) {
-                const int nn = nt * 128 + n4 * 4;
-                float f[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-                __nv_bfloat16 o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  o[e] = __float2bfloat16_rn(f[e]);
-                  if (p.bias)
-                    o[e] = __float2bfloat16_rn(__bfloat162float(o[e]) +
-                                               __bfloat162float(p.bias[nn + e]));
-                }
-                __nv_bfloat16* dst = p.C + (int64_t)m * p.ldc + nn;
-                if (vec_store) {
-                  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) dst[e] = o[e];
-                }
-              }
-            }
-          }
-          if (et == 0) p.counters[nt] = 0;  // leave the workspace zeroed (Marlin's contract)
-          if (et == 0) W4_TRACE(9 + (seg > 0 ? 2 : 0));
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag_smem reuse
-      }
       ++seg;
     }
-    if (et == 0) W4_TRACE(12);
+    if (warp == W4_WARP_EPI && lane == 0) W4_TRACE(7);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) W4_TRACE(13);
+  if (threadIdx.x == 0) W4_TRACE(8);
   if (warp == W4_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// partials -> C (bf16): the reduction pass of the plain GEMM entry point (callers that can,
+// fuse this sum into their own first read instead: norm, all-reduce).
+__global__ void __launch_bounds__(256) w4_reduce_kernel(__nv_bfloat16* __restrict__ C,
+                                                        const float* __restrict__ partials,
+                                                        const __nv_bfloat16* __restrict__ bias,
+                                                        int M, int N, int64_t ldc,
+                                                        int64_t slot_stride, W4Plan plan) {
+  const int nvec = N / 8;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (int64_t)M * nvec) return;
+  const int m = (int)(idx / nvec), v = (int)(idx - (int64_t)m * nvec);
+  const int count = w4_contrib_col(plan, v * 8);
+  float a[8];
+  w4_sum_partials8(a, partials + (int64_t)m * N + v * 8, slot_stride, count);
+  __nv_bfloat16 o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] = __float2bfloat16_rn(a[i]);
+    if (bias) o[i] = __float2bfloat16_rn(__bfloat162float(o[i]) + __bfloat162float(bias[v * 8 + i]));
+  }
+  __nv_bfloat16* dst = C + (int64_t)m * ldc + v * 8;
+  if ((ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = o[i];
   }
 }
 
@@ -762,37 +648,132 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-template <int MT, int CFG>
-static int launch_w4_gemm_cfg(const CUtensorMap& amap, const W4Params& p, int grid,
-                              cudaStream_t st) {
-  using Cfg = W4Cfg<MT, CFG>;
-  B200_CUDA_OK(cudaFuncSetAttribute(w4a16_gemm_kernel<MT, CFG>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  w4a16_gemm_kernel<MT, CFG><<<grid, W4_THREADS, Cfg::SMEM, st>>>(amap, p);
+// B200_PDL=0 disables programmatic dependent launch (the GEMM then starts only after its
+// predecessor in the stream has drained, as an ordinary launch).
+static bool w4_use_pdl() {
+  static const bool on = [] {
+    const char* e = getenv("B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int MT, int NSUB, bool TRACE>
+static int launch_w4_kernel(const CUtensorMap& amap, const W4Params& p, cudaStream_t st) {
+  using Cfg = W4Cfg<MT, NSUB>;
+  auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE>;
+  B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::SMEM));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.plan.P);
+  cfg.blockDim = dim3(W4_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = w4_use_pdl() ? 1 : 0;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, amap, p));
   B200_LAUNCH_OK("w4a16_gemm");
   return B200_OK;
 }
 
-static int w4_cfg() {
-  const char* e = getenv("B200_W4_CFG");
-  const int c = e ? atoi(e) : 1;
-  return c < 0 ? 0 : (c > 2 ? 2 : c);
-}
-
 template <int MT>
-static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, int grid, cudaStream_t st) {
-  switch (w4_cfg()) {
-    case 0: return launch_w4_gemm_cfg<MT, 0>(amap, p, grid, st);
-    case 2: return launch_w4_gemm_cfg<MT, 2>(amap, p, grid, st);
-    default: return launch_w4_gemm_cfg<MT, 1>(amap, p, grid, st);
+static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream_t st) {
+  if constexpr (MT <= 64) {
+    if (p.plan.nsub_log2 == 1)
+      return p.trace ? launch_w4_kernel<MT, 2, true>(amap, p, st)
+                     : launch_w4_kernel<MT, 2, false>(amap, p, st);
   }
+  return p.trace ? launch_w4_kernel<MT, 1, true>(amap, p, st)
+                 : launch_w4_kernel<MT, 1, false>(amap, p, st);
 }
 
-static int w4_grid(int units) {
+// Stream-K partition of a [K, N] weight on this device: as many CTAs as SMs, but never so many
+// that a tile has more than W4_MAX_SLOTS contributors (share >= KT / (W4_MAX_SLOTS - 1) units).
+struct PlanKey {
+  int64_t N, K;
+  int nsub_log2, P;
+};
+static std::mutex g_plan_mu;
+static std::vector<std::pair<PlanKey, W4Plan>> g_plans;
+
+W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
   int P = sm_count();
   const char* env = getenv("B200_W4A16_CTAS");
   if (env && atoi(env) > 0) P = atoi(env);
-  return units < P ? units : P;
+  if (P < 1) P = 1;
+  const char* ens = getenv("B200_W4_NSUB");
+  const int NT128 = (int)(N / 128);
+  // two weight tiles per activation stage when the accumulators fit (M <= 64), N allows and the
+  // coarser partition still fills every SM (share >= KT/7 caps the grid at 7 CTAs per n tile)
+  const bool want2 = ens ? ens[0] == '2' : (long long)(W4_MAX_SLOTS - 1) * (NT128 / 2) >= P;
+  const int nsub_log2 = (M <= 64 && NT128 % 2 == 0 && want2) ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (const auto& e : g_plans)
+      if (e.first.N == N && e.first.K == K && e.first.nsub_log2 == nsub_log2 && e.first.P == P)
+        return e.second;
+  }
+  W4Plan pl{};
+  pl.nsub_log2 = nsub_log2;
+  pl.KT = (int)(K / 128);
+  pl.NT = NT128 >> nsub_log2;
+  pl.units = pl.KT * pl.NT;
+  const long long cap = (long long)(W4_MAX_SLOTS - 1) * pl.NT;
+  int Pc = P;
+  if (Pc > pl.units) Pc = pl.units;
+  if (Pc > cap) Pc = (int)cap;
+  if (Pc < 1) Pc = 1;
+  pl.P = Pc;
+  pl.slots = 1;
+  for (int nt = 0; nt < pl.NT; ++nt) {
+    const int c = w4_contrib(pl, nt);
+    if (c > pl.slots) pl.slots = c;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() > 256) g_plans.clear();
+    g_plans.push_back({PlanKey{N, K, nsub_log2, P}, pl});
+  }
+  return pl;
+}
+
+static int log2_int(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// partial GEMM for one chunk of <= 128 rows
+static int run_partial_gemm(float* partials, const void* A, const void* packed, int64_t M,
+                            int64_t N, int64_t K, int64_t lda, int group_size, const W4Plan& plan,
+                            cudaStream_t st) {
+  const int geff = w4_geff(group_size);
+  const int mt = pick_mt(M);
+  W4Params p{};
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.partials = partials;
+  p.slot_stride = M * N;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.KT = plan.KT;
+  p.geff_log2 = log2_int(geff);
+  p.ngrp = 128 / geff;
+  p.blob_bytes = w4_blob_bytes(geff);
+  p.plan = plan;
+  p.trace = g_w4_trace;
+  CUtensorMap amap;
+  AMapKey key{A, M, K, lda, mt};
+  int rc = get_act_tensor_map(key, &amap);
+  if (rc != B200_OK) return rc;
+  switch (mt) {
+    case 16: return launch_w4_gemm<16>(amap, p, st);
+    case 32: return launch_w4_gemm<32>(amap, p, st);
+    case 64: return launch_w4_gemm<64>(amap, p, st);
+    default: return launch_w4_gemm<128>(amap, p, st);
+  }
 }
 
 }  // namespace b200
@@ -871,11 +852,7 @@ void b200_debug_set_trace(void* device_buffer) {
 int b200_w4a16_splitk_splits(int64_t M, int64_t N, int64_t K) {
   (void)M;
   if (N <= 0 || K <= 0 || N % 128 || K % 128) return 0;
-  const int NT = (int)(N / 128), KT = (int)(K / 128), sms = sm_count();
-  int best = 1;
-  for (int S = 1; S <= 8; ++S)
-    if (NT * S <= sms && KT / S >= 4) best = S;
-  return best;
+  return w4_get_plan(N, K, M).slots;
 }
 
 int b200_w4a16_gemm_splitk(float* partials, const void* A, const void* packed, int64_t M,
@@ -885,48 +862,41 @@ int b200_w4a16_gemm_splitk(float* partials, const void* A, const void* packed, i
   int rc = check_w4_shape("w4a16_gemm_splitk", K, N, group_size);
   if (rc != B200_OK) return rc;
   B200_CHECK_ARG(M > 0 && M <= 128 && lda >= K, "w4a16_gemm_splitk: 1 <= M <= 128 required");
-  B200_CHECK_ARG(splits >= 1 && splits <= K / 128, "w4a16_gemm_splitk: bad split count %d", splits);
   B200_CHECK_ARG(is_aligned(A, 16) && lda % 8 == 0 && is_aligned(packed, 16) &&
                      is_aligned(partials, 16),
                  "w4a16_gemm_splitk: pointers must be 16-byte aligned, lda %% 8 == 0");
-  const int geff = w4_geff(group_size);
-  const int mt = pick_mt(M);
-  W4Params p{};
-  p.packed = static_cast<const uint8_t*>(packed);
-  p.M = (int)M;
-  p.N = (int)N;
-  p.K = (int)K;
-  p.KT = (int)(K / 128);
-  p.NT = (int)(N / 128);
-  p.geff = geff;
-  p.ngrp = 128 / geff;
-  p.blob_bytes = w4_blob_bytes(geff);
-  p.units = p.KT * p.NT;
-  p.ldc = N;
-  p.trace = g_w4_trace;
-  p.splitk_out = partials;
-  p.splitk_S = splits;
-  CUtensorMap amap;
-  AMapKey key{A, M, K, lda, mt};
-  rc = get_act_tensor_map(key, &amap);
-  if (rc != B200_OK) return rc;
-  const int grid = p.NT * splits;
-  auto st = static_cast<cudaStream_t>(stream);
-  switch (mt) {
-    case 16: return launch_w4_gemm<16>(amap, p, grid, st);
-    case 32: return launch_w4_gemm<32>(amap, p, grid, st);
-    case 64: return launch_w4_gemm<64>(amap, p, grid, st);
-    default: return launch_w4_gemm<128>(amap, p, grid, st);
-  }
+  const W4Plan plan = w4_get_plan(N, K, M);
+  B200_CHECK_ARG(splits == plan.slots,
+                 "w4a16_gemm_splitk: partials must have b200_w4a16_splitk_splits() = %d slots, got %d",
+                 plan.slots, splits);
+  return run_partial_gemm(partials, A, packed, M, N, K, lda, group_size, plan,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int b200_w4a16_reduce_partials(void* C, const float* partials, int splits, int64_t gemm_k,
+                               const void* bias, int64_t M, int64_t N, int64_t ldc,
+                               b200_stream_t stream) {
+  B200_CHECK_ARG(C && partials, "w4a16_reduce_partials: null pointer");
+  B200_CHECK_ARG(M >= 0 && N > 0 && N % 128 == 0 && gemm_k > 0 && gemm_k % 128 == 0 && ldc >= N,
+                 "w4a16_reduce_partials: bad shape");
+  const W4Plan plan = w4_get_plan(N, gemm_k, M);
+  B200_CHECK_ARG(splits == plan.slots, "w4a16_reduce_partials: expected %d partial slots, got %d",
+                 plan.slots, splits);
+  if (M == 0) return B200_OK;
+  const int64_t nvec = M * (N / 8);
+  w4_reduce_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(C), partials, static_cast<const __nv_bfloat16*>(bias), (int)M,
+      (int)N, ldc, M * N, plan);
+  B200_LAUNCH_OK("w4a16_reduce");
+  return B200_OK;
 }
 
 int64_t b200_w4a16_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  (void)N;
-  (void)K;
-  if (M <= 0) return B200_W4A16_COUNTER_BYTES;
-  const int mt = pick_mt(M);
-  // 2 partial slots per CTA; CTAs <= 1024 covers any env override of the grid
-  return B200_W4A16_COUNTER_BYTES + 2ll * 1024 * mt * 128 * (int64_t)sizeof(float);
+  if (M <= 0 || N <= 0 || K <= 0 || N % 128 || K % 128) return 256;
+  const int64_t mc = M < 128 ? M : 128, rem = M > 128 ? M % 128 : 0;  // chunk sizes the GEMM uses
+  int64_t rows = (int64_t)w4_get_plan(N, K, mc).slots * mc;
+  if (rem > 0) rows = std::max(rows, (int64_t)w4_get_plan(N, K, rem).slots * rem);
+  return rows * N * (int64_t)sizeof(float) + 256;
 }
 
 int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias, int64_t M,
@@ -936,7 +906,6 @@ int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias
   int rc = check_w4_shape("w4a16_gemm", K, N, group_size);
   if (rc != B200_OK) return rc;
   B200_CHECK_ARG(M >= 0 && lda >= K && ldc >= N, "w4a16_gemm: bad M/lda/ldc");
-  B200_CHECK_ARG(N / 128 <= B200_W4A16_COUNTER_BYTES / 4, "w4a16_gemm: N too large");
   if (M == 0) return B200_OK;
   auto st = static_cast<cudaStream_t>(stream);
   const int geff = w4_geff(group_size);
@@ -955,46 +924,24 @@ int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias
   B200_CHECK_ARG(is_aligned(A, 16) && lda % 8 == 0 && is_aligned(packed, 16),
                  "w4a16_gemm: A / packed must be 16-byte aligned, lda %% 8 == 0");
   B200_CHECK_ARG(workspace && is_aligned(workspace, 16), "w4a16_gemm: workspace required");
-  // rows beyond 128 are processed in chunks of 128 (weights re-streamed; the
-  // decode path never takes more than one chunk)
+  // rows beyond 128 are processed in chunks of 128 (weights re-streamed; the decode path never
+  // takes more than one chunk); chunks reuse the workspace in stream order
   for (int64_t m0 = 0; m0 < M; m0 += 128) {
     const int64_t mc = (M - m0) < 128 ? (M - m0) : 128;
-    const int mt = pick_mt(mc);
-    W4Params p{};
-    p.packed = static_cast<const uint8_t*>(packed);
-    p.C = static_cast<__nv_bfloat16*>(C) + m0 * ldc;
-    p.bias = static_cast<const __nv_bfloat16*>(bias);
-    p.M = (int)mc;
-    p.N = (int)N;
-    p.K = (int)K;
-    p.KT = (int)(K / 128);
-    p.NT = (int)(N / 128);
-    p.geff = geff;
-    p.ngrp = 128 / geff;
-    p.blob_bytes = w4_blob_bytes(geff);
-    p.units = p.KT * p.NT;
-    p.ldc = ldc;
-    p.trace = g_w4_trace;
-    const int grid = w4_grid(p.units);
-    const int64_t need =
-        B200_W4A16_COUNTER_BYTES + 2ll * grid * mt * 128 * (int64_t)sizeof(float);
+    const W4Plan plan = w4_get_plan(N, K, mc);
+    const int64_t need = (int64_t)plan.slots * mc * N * (int64_t)sizeof(float);
     if (workspace_bytes < need)
       return set_error(B200_ERR_WORKSPACE, "w4a16_gemm: workspace %lld B < required %lld B",
                        (long long)workspace_bytes, (long long)need);
-    p.counters = static_cast<int*>(workspace);
-    p.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
-                                            B200_W4A16_COUNTER_BYTES);
-    CUtensorMap amap;
-    AMapKey key{static_cast<const __nv_bfloat16*>(A) + m0 * lda, mc, K, lda, mt};
-    rc = get_act_tensor_map(key, &amap);
+    float* partials = static_cast<float*>(workspace);
+    rc = run_partial_gemm(partials, static_cast<const __nv_bfloat16*>(A) + m0 * lda, packed, mc, N,
+                          K, lda, group_size, plan, st);
     if (rc != B200_OK) return rc;
-    switch (mt) {
-      case 16: rc = launch_w4_gemm<16>(amap, p, grid, st); break;
-      case 32: rc = launch_w4_gemm<32>(amap, p, grid, st); break;
-      case 64: rc = launch_w4_gemm<64>(amap, p, grid, st); break;
-      default: rc = launch_w4_gemm<128>(amap, p, grid, st); break;
-    }
-    if (rc != B200_OK) return rc;
+    const int64_t nvec = mc * (N / 8);
+    w4_reduce_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(
+        static_cast<__nv_bfloat16*>(C) + m0 * ldc, partials,
+        static_cast<const __nv_bfloat16*>(bias), (int)mc, (int)N, ldc, mc * N, plan);
+    B200_LAUNCH_OK("w4a16_reduce");
   }
   return B200_OK;
 }

@@ -234,84 +234,108 @@ class HostBatch:
 class BlockPool:
     """Minimal stand-in for the reference's BlockAllocator output: block ids are handed out from
     a random permutation (src/memory/block_allocator.cpp semantics are out of scope; only the ids
-    it would produce matter to the kernels)."""
+    it would produce matter to the kernels).  Per-sequence block lists are kept as rows of one
+    int32 matrix of FIRST-SLOT ids (block_id * block_size, batch.cpp:206-209) so a step's metadata
+    is built with a handful of vectorised numpy calls."""
 
     def __init__(self, n_blocks: int, block_size: int, seed: int = 2):
         self.block_size = block_size
         self.free = list(np.random.default_rng(seed).permutation(n_blocks).astype(np.int64))
         self.seq_blocks: List[List[int]] = []
+        self._table = np.zeros((0, 0), dtype=np.int32)   # [n_seqs, max blocks per seq] first-slot ids
 
     def add_sequence(self, n_tokens_capacity: int) -> int:
         nb = (n_tokens_capacity + self.block_size - 1) // self.block_size
         if nb > len(self.free):
             raise RuntimeError("block pool exhausted")
-        self.seq_blocks.append([self.free.pop() for _ in range(nb)])
-        return len(self.seq_blocks) - 1
+        blocks = [self.free.pop() for _ in range(nb)]
+        self.seq_blocks.append(blocks)
+        n, w = self._table.shape
+        t = np.zeros((n + 1, max(w, nb)), dtype=np.int32)
+        t[:n, :w] = self._table
+        t[n, :nb] = np.asarray(blocks, dtype=np.int64) * self.block_size
+        self._table = t
+        return n
+
+    def n_blocks_of(self, seq: int) -> int:
+        return len(self.seq_blocks[seq])
 
 
 def build_decode_batch(pool: BlockPool, kv_lens: List[int], q_lens: List[int], vocab: int,
                        seed: int = 5) -> HostBatch:
-    """kv_lens INCLUDE the new tokens (kv_cu_seq_lens semantics, parameters.h:35-37)."""
+    """One step's InputParameters on the host (Batch::prepare_model_input, batch.cpp:77-270) for
+    sequences 0..B-1 of the pool.  kv_lens INCLUDE the new tokens (kv_cu_seq_lens semantics,
+    parameters.h:35-37)."""
     bs = pool.block_size
-    rng = np.random.default_rng(seed)
     B = len(kv_lens)
-    tokens, positions, slots, tables = [], [], [], []
-    q_cu, kv_cu, blk_cu = [0], [0], [0]
-    for b in range(B):
-        kv, ql = kv_lens[b], q_lens[b]
-        blocks = pool.seq_blocks[b]
-        nb = (kv + bs - 1) // bs
-        assert nb <= len(blocks), "sequence outgrew its blocks"
-        for p in range(kv - ql, kv):
-            positions.append(p)
-            slots.append(blocks[p // bs] * bs + p % bs)
-        tokens.extend(rng.integers(0, vocab, size=ql).tolist())
-        tables.extend([blk * bs for blk in blocks[:nb]])   # first-slot ids (batch.cpp:206-209)
-        q_cu.append(q_cu[-1] + ql)
-        kv_cu.append(kv_cu[-1] + kv)
-        blk_cu.append(blk_cu[-1] + nb)
-    i32 = lambda x: np.asarray(x, dtype=np.int32)
+    kv = np.asarray(kv_lens, dtype=np.int64)
+    ql = np.asarray(q_lens, dtype=np.int64)
+    nb = (kv + bs - 1) // bs
+    cap = np.asarray([pool.n_blocks_of(b) for b in range(B)], dtype=np.int64)
+    assert bool((nb <= cap).all()), "sequence outgrew its blocks"
+    q_cu = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(ql, out=q_cu[1:])
+    kv_cu = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(kv, out=kv_cu[1:])
+    blk_cu = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(nb, out=blk_cu[1:])
+    T = int(q_cu[-1])
+    seq_of_tok = np.repeat(np.arange(B), ql)
+    positions = np.arange(T) - q_cu[seq_of_tok] + (kv - ql)[seq_of_tok]      # kv-ql .. kv-1 per seq
+    table = pool._table[:B]
+    slots = table[seq_of_tok, positions // bs].astype(np.int64) + positions % bs
+    tables = table[np.arange(table.shape[1])[None, :] < nb[:, None]]         # row-major: per-seq order
+    tokens = np.random.default_rng(seed).integers(0, vocab, size=T)
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
     return HostBatch(i32(tokens), i32(positions), i32(q_cu), i32(kv_cu), i32(slots), i32(tables),
-                     i32(blk_cu), max(q_lens), max(kv_lens))
+                     i32(blk_cu), int(ql.max()), int(kv.max()))
 
 
 class StepBuffers:
-    """Pinned host + device buffers for one step's inputs (worker.cpp:132-135 H2D copies)."""
+    """One pinned host staging buffer + its device twin for a step's inputs (worker.cpp:132-135
+    H2D copies): the seven int32 arrays live at fixed offsets, so a step is ONE host->device copy
+    and the device views keep their addresses (CUDA-graph safe)."""
+
+    FIELDS = ("tokens", "positions", "slots", "q_cu", "kv_cu", "blk_cu", "tables")
 
     def __init__(self, device, max_tokens: int, max_seqs: int, max_blocks: int):
-        def pair(n):
-            return (torch.empty(n, dtype=torch.int32, pin_memory=torch.cuda.is_available()),
-                    torch.zeros(n, dtype=torch.int32, device=device))
+        caps = {"tokens": max_tokens, "positions": max_tokens, "slots": max_tokens,
+                "q_cu": max_seqs + 1, "kv_cu": max_seqs + 1, "blk_cu": max_seqs + 1,
+                "tables": max_blocks}
         self.device = device
-        self.tokens = pair(max_tokens)
-        self.positions = pair(max_tokens)
-        self.slots = pair(max_tokens)
-        self.q_cu = pair(max_seqs + 1)
-        self.kv_cu = pair(max_seqs + 1)
-        self.blk_cu = pair(max_seqs + 1)
-        self.tables = pair(max_blocks)
+        self.off, total = {}, 0
+        for f in self.FIELDS:
+            self.off[f] = (total, caps[f])
+            total += (caps[f] + 3) // 4 * 4          # keep every field 16-byte aligned
+        self.total = total
+        self.host = torch.zeros(total, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        self.host_np = self.host.numpy()
+        self.dev = torch.zeros(total, dtype=torch.int32, device=device)
 
     def h2d_bytes(self, hb: HostBatch) -> int:
-        return 4 * (3 * len(hb.tokens) + 3 * len(hb.q_cu_lens) + len(hb.block_tables))
+        """Bytes of the single staging copy a step performs (up to the end of the block table)."""
+        return 4 * (self.off["tables"][0] + len(hb.block_tables))
 
     def upload(self, hb: HostBatch) -> Tuple[torch.Tensor, torch.Tensor, InputParameters]:
         """Async H2D of one step's metadata from pinned memory on the current stream."""
-        def put(pairbuf, arr):
-            h, d = pairbuf
-            n = len(arr)
-            h[:n].copy_(torch.from_numpy(arr))
-            d[:n].copy_(h[:n], non_blocking=True)
-            return d[:n]
-        T, B = len(hb.tokens), len(hb.q_cu_lens) - 1
-        tokens = put(self.tokens, hb.tokens)
-        positions = put(self.positions, hb.positions)
+        arrs = {"tokens": hb.tokens, "positions": hb.positions, "slots": hb.new_cache_slots,
+                "q_cu": hb.q_cu_lens, "kv_cu": hb.kv_cu_lens, "blk_cu": hb.cu_block_lens,
+                "tables": hb.block_tables}
+        view = {}
+        for f in self.FIELDS:
+            o, cap = self.off[f]
+            n = len(arrs[f])
+            assert n <= cap, f"{f}: {n} > capacity {cap}"
+            self.host_np[o:o + n] = arrs[f]
+            view[f] = self.dev[o:o + n]
+        used = self.off["tables"][0] + len(hb.block_tables)
+        self.dev[:used].copy_(self.host[:used], non_blocking=True)
+        B = len(hb.q_cu_lens) - 1
         params = InputParameters(
-            num_sequences=B, q_cu_seq_lens=put(self.q_cu, hb.q_cu_lens),
-            kv_cu_seq_lens=put(self.kv_cu, hb.kv_cu_lens), kv_max_seq_len=hb.kv_max,
-            q_max_seq_len=hb.q_max, new_cache_slots=put(self.slots, hb.new_cache_slots),
-            block_tables=put(self.tables, hb.block_tables),
-            cu_block_lens=put(self.blk_cu, hb.cu_block_lens))
-        return tokens, positions, params
+            num_sequences=B, q_cu_seq_lens=view["q_cu"], kv_cu_seq_lens=view["kv_cu"],
+            kv_max_seq_len=hb.kv_max, q_max_seq_len=hb.q_max, new_cache_slots=view["slots"],
+            block_tables=view["tables"], cu_block_lens=view["blk_cu"])
+        return view["tokens"], view["positions"], params
 
 
 class GraphedStep:

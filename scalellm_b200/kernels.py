@@ -15,7 +15,7 @@ CPU tensors are rejected — there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+from typing import NamedTuple, Dict, Optional, Tuple
 
 import torch
 
@@ -281,7 +281,7 @@ def w4a16_dequant(packed: torch.Tensor, K: int, N: int, group_size: int) -> torc
 
 def w4a16_workspace(device: torch.device, M: int, N: int, K: int) -> torch.Tensor:
     need = int(_lib.load().b200_w4a16_workspace_bytes(M, N, K))
-    return _workspace("w4a16", device, need, zero=True)
+    return _workspace("w4a16", device, need, zero=False)
 
 
 def w4a16_gemm(a: torch.Tensor, packed: torch.Tensor, N: int, group_size: int,
@@ -306,31 +306,55 @@ def w4a16_splitk_splits(M: int, N: int, K: int) -> int:
     return int(_lib.load().b200_w4a16_splitk_splits(M, N, K))
 
 
+class W4Partials(NamedTuple):
+    """fp32 stream-K partials of a W4A16 GEMM: data [slots, M, N]; K is the GEMM's reduction
+    dimension (the consumer recomputes the tile -> contributor-slot partition from (N, K))."""
+    data: torch.Tensor
+    K: int
+
+
 def w4a16_gemm_splitk(a: torch.Tensor, packed: torch.Tensor, N: int, group_size: int,
-                      splits: Optional[int] = None) -> torch.Tensor:
-    """Split-K partial mode: returns fp32 partials [splits, M, N]; the consumer
-    (rms_norm_residual_splitk) performs the reduction.  M <= 128."""
+                      poison: bool = False) -> W4Partials:
+    """Partials mode: the GEMM writes fp32 partials [slots, M, N] and the consumer
+    (rms_norm_residual_splitk, the TP all-reduce, w4a16_reduce_partials) performs the reduction.
+    M <= 128."""
     _cuda(a, packed)
     assert a.dim() == 2 and a.dtype == torch.bfloat16 and a.stride(1) == 1
     M, K = a.shape
-    if splits is None:
-        splits = w4a16_splitk_splits(M, N, K)
-    partials = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
+    slots = w4a16_splitk_splits(M, N, K)
+    partials = torch.empty((slots, M, N), dtype=torch.float32, device=a.device)
+    if poison:  # tests: slots a tile does not use must never be read
+        partials.fill_(float("nan"))
     check(_lib.load().b200_w4a16_gemm_splitk(_p(partials), _p(a), _p(packed), M, N, K, a.stride(0),
-                                             group_size, splits, _stream()))
-    return partials
+                                             group_size, slots, _stream()))
+    return W4Partials(partials, K)
 
 
-def rms_norm_residual_splitk(out: torch.Tensor, residual: torch.Tensor, partials: torch.Tensor,
+def w4a16_reduce_partials(partials: W4Partials, out: Optional[torch.Tensor] = None,
+                          bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] (bf16) = bf16(sum over slots of partials) (+ bias)."""
+    data = partials.data
+    S, M, N = data.shape
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=data.device)
+    _cuda(data, out, bias)
+    assert out.dtype == torch.bfloat16 and out.stride(-1) == 1
+    check(_lib.load().b200_w4a16_reduce_partials(_p(out), _p(data), S, partials.K, _p(bias), M, N,
+                                                 out.stride(0), _stream()))
+    return out
+
+
+def rms_norm_residual_splitk(out: torch.Tensor, residual: torch.Tensor, partials: W4Partials,
                              weight: torch.Tensor, epsilon: float) -> None:
-    """residual += T(sum_s partials[s]); out = rms_norm(residual) * weight."""
-    _cuda(out, residual, partials, weight)
-    assert partials.dtype == torch.float32 and partials.is_contiguous() and partials.dim() == 3
+    """residual += T(sum over slots of partials); out = rms_norm(residual) * weight."""
+    data = partials.data
+    _cuda(out, residual, data, weight)
+    assert data.dtype == torch.float32 and data.is_contiguous() and data.dim() == 3
     assert out.is_contiguous() and residual.is_contiguous()
-    S, rows, n = partials.shape
+    S, rows, n = data.shape
     if rows == 0:
         return
-    check(_lib.load().b200_rms_norm_residual_splitk(_p(out), _p(residual), _p(partials), S,
+    check(_lib.load().b200_rms_norm_residual_splitk(_p(out), _p(residual), _p(data), S, partials.K,
                                                     _p(weight), rows, n, epsilon, _dt(out),
                                                     _stream()))
 

@@ -236,9 +236,9 @@ class RMSNorm:
         kernels.rms_norm_residual(out, residual, x, self.weight, self.eps)
         return out
 
-    def forward_residual_partials(self, partials: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
-        """Same, with x delivered as the producing GEMM's split-K partials [S, rows, n] fp32: the
-        cross-CTA reduction of the GEMM is fused into this kernel."""
+    def forward_residual_partials(self, partials, residual: torch.Tensor) -> torch.Tensor:
+        """Same, with x delivered as the producing GEMM's stream-K partials (kernels.W4Partials):
+        the cross-CTA reduction of the GEMM is fused into this kernel."""
         out = torch.empty_like(residual)
         kernels.rms_norm_residual_splitk(out, residual, partials, self.weight, self.eps)
         return out
@@ -379,10 +379,11 @@ class RowParallelQLinear(_QLinearBase):
         self._set_shard(qw, qz, sc, sd.get("bias"))
 
     def supports_partials(self, n_rows: int) -> bool:
-        """Split-K partial output (reduction fused into the consumer norm) — single rank, no bias."""
+        """Partials output (the GEMM's cross-CTA reduction fused into the consumer norm) — single
+        rank, no bias."""
         return self.pa.world_size == 1 and self.bias is None and 0 < n_rows <= 128
 
-    def forward_partials(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
         self._ensure_packed()
         x2 = x.reshape(-1, x.shape[-1])
         return kernels.w4a16_gemm_splitk(x2, self.packed, self.N, self.qa.group_size)

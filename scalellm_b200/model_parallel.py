@@ -80,20 +80,23 @@ class ProcessGroup:
             return
         dist.all_reduce(input, op=dist.ReduceOp.SUM, group=self._group)
 
-    def allreduce_partials(self, partials: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-        """Sum over ranks of sum_s partials[s] ([S, rows, n] fp32 from the split-K GEMM), one
-        rounding to `dtype` per rank before the exchange (what the GEMM epilogue would store)."""
-        S, rows, n = partials.shape
-        out = torch.empty((rows, n), dtype=dtype, device=partials.device)
+    def allreduce_partials(self, partials, dtype: torch.dtype) -> torch.Tensor:
+        """Sum over ranks of this rank's GEMM result delivered as stream-K partials
+        (kernels.W4Partials: data [slots, rows, n] fp32 + the GEMM's K): the all-reduce's copy-in
+        stage sums each tile's slots and rounds once to `dtype` (what a GEMM epilogue would store)."""
+        data = partials.data
+        S, rows, n = data.shape
+        out = torch.empty((rows, n), dtype=dtype, device=data.device)
         nbytes = out.numel() * out.element_size()
         if (self._comm is not None and nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
                 and dtype in (torch.bfloat16, torch.float16)):
             dt = 0 if dtype == torch.bfloat16 else 1
-            check(_lib.load().b200_ar_allreduce_splitk(self._comm, out.data_ptr(), partials.data_ptr(),
-                                                       S, out.numel(), dt,
+            check(_lib.load().b200_ar_allreduce_splitk(self._comm, out.data_ptr(), data.data_ptr(),
+                                                       S, partials.K, n, out.numel(), dt,
                                                        torch.cuda.current_stream().cuda_stream))
             return out
-        out.copy_(partials.sum(0))
+        from . import kernels
+        kernels.w4a16_reduce_partials(partials, out)
         self.allreduce(out)
         return out
 

@@ -77,7 +77,7 @@ void gptq_gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& C,
                const torch::Tensor& perm, torch::Tensor& workspace, int num_bits, bool is_k_full,
                bool has_zp, bool use_fp32_reduce);
 
-// bytes of the packed weight / of the workspace gptq_gemm needs (zero-initialised once)
+// bytes of the packed weight / of the workspace gptq_gemm needs (no initialisation needed)
 int64_t b200_packed_bytes(int64_t K, int64_t N, int64_t group_size);
 int64_t b200_workspace_bytes(int64_t M, int64_t N, int64_t K);
 

@@ -50,3 +50,44 @@ def test_shard_arithmetic():
     assert kv_head_for_rank(8, 5, 8) == slice(5, 6)
     assert kv_head_for_rank(8, 5, 16) == slice(2, 3)  # ranks 4,5 share kv head 2
     assert kv_head_for_rank(8, 1, 2) == slice(4, 8)
+
+
+def test_build_decode_batch_matches_per_token_loop():
+    """The vectorised step-metadata builder (batch.cpp:77-270 semantics) against a per-token loop:
+    ragged kv lengths, multi-token queries, block-table rows of different lengths."""
+    import numpy as np
+    import torch
+    from scalellm_b200.decode_step import BlockPool, StepBuffers, build_decode_batch
+    rng = np.random.default_rng(0)
+    pool = BlockPool(4000, 16, seed=3)
+    caps = [int(x) for x in rng.integers(20, 600, size=9)]
+    for c in caps:
+        pool.add_sequence(c)
+    kv = [int(rng.integers(5, c + 1)) for c in caps]
+    ql = [int(rng.integers(1, min(k, 5) + 1)) for k in kv]
+    hb = build_decode_batch(pool, kv, ql, 1000)
+    bs = pool.block_size
+    positions, slots, tables, q_cu, kv_cu, blk_cu = [], [], [], [0], [0], [0]
+    for b, (k, q) in enumerate(zip(kv, ql)):
+        blocks = pool.seq_blocks[b]
+        nb = (k + bs - 1) // bs
+        for p in range(k - q, k):
+            positions.append(p)
+            slots.append(blocks[p // bs] * bs + p % bs)
+        tables.extend(blk * bs for blk in blocks[:nb])       # first-slot ids (batch.cpp:206-209)
+        q_cu.append(q_cu[-1] + q)
+        kv_cu.append(kv_cu[-1] + k)
+        blk_cu.append(blk_cu[-1] + nb)
+    assert hb.positions.tolist() == positions and hb.new_cache_slots.tolist() == slots
+    assert hb.block_tables.tolist() == tables and hb.q_cu_lens.tolist() == q_cu
+    assert hb.kv_cu_lens.tolist() == kv_cu and hb.cu_block_lens.tolist() == blk_cu
+    assert hb.q_max == max(ql) and hb.kv_max == max(kv) and len(hb.tokens) == sum(ql)
+    # one staging buffer, device views at fixed offsets
+    bufs = StepBuffers(torch.device("cpu"), 64, 16, 4000)
+    tok, pos, params = bufs.upload(hb)
+    assert torch.equal(params.block_tables, torch.from_numpy(hb.block_tables))
+    assert torch.equal(params.new_cache_slots, torch.from_numpy(hb.new_cache_slots))
+    assert torch.equal(pos, torch.from_numpy(hb.positions)) and torch.equal(tok, torch.from_numpy(hb.tokens))
+    p0 = params.block_tables.data_ptr()
+    _, _, params2 = bufs.upload(hb)
+    assert params2.block_tables.data_ptr() == p0

@@ -67,7 +67,7 @@ if has ncu; then
   echo "ncu launches rc=$?" | tee -a $OUT/summary.txt
   # full capture of the dominant kernel
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:paged_attn_decode_kernel -s 8 -c 2 -o $OUT/prof_attn -f \
+      -k regex:paged_attn_persist_kernel -s 4 -c 2 -o $OUT/prof_attn -f \
       python bench.py --steps 1 --warmup 1 --layers 4 --no-graph --skip-cpu-baseline \
       > $OUT/ncu_attn.log 2>&1
   echo "ncu attn rc=$?" | tee -a $OUT/summary.txt
@@ -94,4 +94,10 @@ if has deq; then
   timeout 120 tools/microbench/deq > $OUT/deq.log 2>&1
   echo "deq rc=$?" | tee -a $OUT/summary.txt
   cat $OUT/deq.log | tee -a $OUT/summary.txt
+fi
+if has micro; then
+  for b in readbw kvbw hmma deq; do
+    timeout 120 tools/microbench/$b > $OUT/micro_$b.log 2>&1
+    echo "micro $b rc=$?" | tee -a $OUT/summary.txt
+  done
 fi

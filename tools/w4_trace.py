@@ -9,12 +9,8 @@ sys.path.insert(0, ROOT)
 from scalellm_b200 import _lib, kernels  # noqa: E402
 
 DEV = "cuda"
-NAMES = ["start", "setup_done", "deq_first_raw", "deq_done", "mma_first", "mma_last_commit",
-         "epi_first_full", "epi_first_seg_done", "epi_reduce0_begin", "epi_reduce0_end",
-         "epi_reduceN_begin", "epi_reduceN_end", "epi_done", "end", "-", "-",
-         "SUM mma wait act_full", "SUM mma wait deq_full", "SUM deq(g0) wait raw_full",
-         "SUM deq(g0) wait deq_empty", "SUM actprod wait act_empty", "SUM rawprod wait raw_empty",
-         "SUM mma wait tmem_empty"]
+NAMES = ["start", "setup_done", "deq_first_raw", "deq_g0_done", "mma_first", "mma_last_issued",
+         "epi_first_full", "epi_done", "end"]
 
 
 def run(K, N, M=64, g=128):
@@ -26,24 +22,23 @@ def run(K, N, M=64, g=128):
     a = torch.randn(M, K, device=DEV).bfloat16()
     out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     for _ in range(3):
-        kernels.w4a16_gemm(a, packed, N, g, out=out)
+        kernels.w4a16_gemm_splitk(a, packed, N, g)
     torch.cuda.synchronize()
     # flush L2 so the traced launch streams weights from HBM
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     flush.zero_()
-    trace = torch.zeros(1024 * 32, dtype=torch.int64, device=DEV)
+    trace = torch.zeros(1024 * 16, dtype=torch.int64, device=DEV)
     lib = _lib.load()
     lib.b200_debug_set_trace(trace.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kernels.w4a16_gemm(a, packed, N, g, out=out)
+    kernels.w4a16_gemm_splitk(a, packed, N, g)   # the GEMM launch alone (partials out)
     e1.record()
     torch.cuda.synchronize()
     lib.b200_debug_set_trace(None)
-    t = trace.cpu().view(-1, 32)
+    t = trace.cpu().view(-1, 16)
     t = t[t[:, 0] != 0]
     rel = (t - t[:, :1]).float()
-    rel[:, 16:] = t[:, 16:].float()      # wait totals are already durations
     rel[t == 0] = float("nan")
     print(f"== K={K} N={N} M={M}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {t.shape[0]} CTAs "
           f"(cycles; ~1.9 cycles/ns)")
@@ -59,8 +54,5 @@ def run(K, N, M=64, g=128):
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for cfg in (sys.argv[1:] or ["1"]):
-        os.environ["B200_W4_CFG"] = cfg
-        print(f"######## B200_W4_CFG={cfg}")
-        for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
-            run(K, N)
+    for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
+        run(K, N)
