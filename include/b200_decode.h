@@ -257,6 +257,22 @@ B200_API int b200_rms_norm_residual_splitk(void* out, void* residual, const floa
                                            int64_t rows, int64_t n, float eps, int dtype,
                                            b200_stream_t stream);
 
+/* Fused consumers of the qkv / gate_up GEMM partials (same partition rules as above):
+ *   b200_rope_kv_write_splitk: qkv[T, (H + 2 Hkv) D] = T(sum_slots partials), then exactly
+ *     b200_rope_kv_write on its q | k | v column blocks (q, k rotated in place, rotated k and v
+ *     scattered to their cache slots).  Replaces qkv_proj's epilogue + apply_rotary_pos_emb +
+ *     set_kv_cache (models/meta/llama.h:123-133).
+ *   b200_silu_mul_splitk: out[rows, inter] = silu(T(gate)) * T(up), gate | up the two halves of the
+ *     gate_up GEMM row (models/meta/llama.h:61-64, activation.cpp:101-103 rounding). */
+B200_API int b200_rope_kv_write_splitk(void* qkv, const float* partials, int splits, int64_t gemm_k,
+                                       const int32_t* positions, const void* cos_sin,
+                                       const int32_t* slot_ids, void* k_cache, void* v_cache,
+                                       int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads,
+                                       int64_t head_dim, int64_t rotary_dim, int interleaved,
+                                       int dtype, b200_stream_t stream);
+B200_API int b200_silu_mul_splitk(void* out, const float* partials, int splits, int64_t gemm_k,
+                                  int64_t rows, int64_t inter, int dtype, b200_stream_t stream);
+
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
 B200_API void b200_debug_set_trace(void* device_buffer);

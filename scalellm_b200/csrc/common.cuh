@@ -49,6 +49,43 @@ inline bool is_aligned(const void* p, size_t a) {
 
 int sm_count();  // cached multiProcessorCount of the current device
 
+// Programmatic dependent launch.  B200_PDL = 0: off; 1 (default): the W4A16 GEMM and the kernels
+// that consume its partials are launched with the programmatic-stream-serialization attribute:
+// the GEMM's CTAs become resident and prefetch weights while the predecessor kernel (which calls
+// pdl_launch_dependents() at its start) is still running, and the GEMM lets its consumer's CTAs
+// be scheduled when its last epilogue begins; 2: every hot kernel is launched that way.  Each
+// kernel starts with pdl_wait(), which returns once the predecessor has completed and flushed.
+int pdl_level();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int min_level, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                              size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_level() >= min_level ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// launch + check + count; `level` = the B200_PDL level from which the launch is programmatic
+#define B200_PDL_LAUNCH(name, kernel, grid, block, smem, st, ...) \
+  B200_PDL_LAUNCH_L(2, name, kernel, grid, block, smem, st, __VA_ARGS__)
+#define B200_PDL_LAUNCH_L(level, name, kernel, grid, block, smem, st, ...)                     \
+  do {                                                                                         \
+    cudaError_t _e =                                                                           \
+        ::b200::launch_pdl(level, kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__);     \
+    if (_e != cudaSuccess)                                                                     \
+      return ::b200::set_error(B200_ERR_CUDA, "launch of %s failed: %s", name,                 \
+                               cudaGetErrorString(_e));                                        \
+    ::b200::count_launch();                                                                    \
+  } while (0)
+
 // cuTensorMapEncodeTiled resolved through the runtime (no libcuda link).
 typedef CUresult (*tensor_map_encode_fn)(
     CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -370,10 +407,9 @@ constexpr int W4_MAX_SLOTS = 8;
 // The partition b200_w4a16_gemm_splitk uses for M rows x a [K, N] weight on the current device.
 W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M);
 
-// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
-// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks
-// until the predecessor has completed and its writes are visible.  pdl_launch_dependents() in
-// the predecessor allows that early start (no-ops when PDL is not in use).
+// Device side of programmatic dependent launch: pdl_wait() blocks until the predecessor kernel
+// has completed and its writes are visible; pdl_launch_dependents() allows the successor's early
+// start (both are no-ops for an ordinary launch).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

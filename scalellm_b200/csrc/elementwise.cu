@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
                                                                float eps, int n) {
   constexpr int VEC = 16 / sizeof(T);
   __shared__ float red[32];
-  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   const T* in_row = in + row * n;
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(1024) rms_norm_scalar_kernel(T* __restrict__ o
                                                                const T* __restrict__ in,
                                                                const T* __restrict__ weight,
                                                                float eps, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   float ss = 0.f;
@@ -145,20 +148,19 @@ static int launch_rms_norm(void* out, void* residual, const void* in, const void
   const T* w = static_cast<const T*>(weight);
   dim3 grid(static_cast<unsigned>(rows));
   if (vec_ok && nvec <= 128) {
-    rms_norm_vec_kernel<T, 128, 1, RESIDUAL><<<grid, 128, 0, st>>>(o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 128, 1, RESIDUAL>), grid, 128, 0, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 256) {
-    rms_norm_vec_kernel<T, 256, 1, RESIDUAL><<<grid, 256, 0, st>>>(o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 256, 1, RESIDUAL>), grid, 256, 0, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 512) {
-    rms_norm_vec_kernel<T, 512, 1, RESIDUAL><<<grid, 512, 0, st>>>(o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 1, RESIDUAL>), grid, 512, 0, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 1024) {
-    rms_norm_vec_kernel<T, 512, 2, RESIDUAL><<<grid, 512, 0, st>>>(o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 2, RESIDUAL>), grid, 512, 0, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 4096) {
-    rms_norm_vec_kernel<T, 1024, 4, RESIDUAL><<<grid, 1024, 0, st>>>(o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 1024, 4, RESIDUAL>), grid, 1024, 0, st, o, r, i, w, eps, (int)n);
   } else {
     const int threads = (int)((n < 1024 ? ((n + 31) / 32) * 32 : 1024));
-    rms_norm_scalar_kernel<T, RESIDUAL><<<grid, threads, 0, st>>>(o, r, i, w, eps, n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_scalar_kernel<T, RESIDUAL>), grid, threads, 0, st, o, r, i, w, eps, n);
   }
-  B200_LAUNCH_OK("rms_norm");
   return B200_OK;
 }
 
@@ -173,7 +175,8 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   constexpr int VEC = 16 / sizeof(T);
   static_assert(VEC == 8, "16-bit element types only");
   __shared__ float red[32];
-  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   T* res_row = residual + row * n;
@@ -232,14 +235,13 @@ static int launch_rms_norm_splitk(void* out, void* residual, const float* partia
   const int64_t nvec = n / 8;
   dim3 grid(static_cast<unsigned>(rows));
   if (nvec <= 256)
-    rms_norm_residual_splitk_kernel<T, 256, 1><<<grid, 256, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 256, 1>), grid, 256, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else if (nvec <= 512)
-    rms_norm_residual_splitk_kernel<T, 512, 1><<<grid, 512, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 1>), grid, 512, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else if (nvec <= 1024)
-    rms_norm_residual_splitk_kernel<T, 512, 2><<<grid, 512, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 2>), grid, 512, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else
-    rms_norm_residual_splitk_kernel<T, 1024, 4><<<grid, 1024, 0, st>>>(o, r, partials, S, split_stride, w, eps, (int)n);
-  B200_LAUNCH_OK("rms_norm_residual_splitk");
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 1024, 4>), grid, 1024, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
   return B200_OK;
 }
 
@@ -258,15 +260,42 @@ __device__ __forceinline__ void rope_pair(float x, float y, float c, float s, T&
   oy = Num<T>::from_f(xs + yc);
 }
 
-template <typename T, bool FUSE_KV>
+// The qkv GEMM's stream-K partials as the source of a token's [q | k | v] row (FROM_PARTIALS).
+struct RopePartials {
+  const float* data;     // [slots][n_tokens][row_n] fp32, row_n = (n_heads + 2 n_kv_heads) head_dim
+  int64_t slot_stride;
+  int row_n;
+  W4Plan plan;
+};
+
+template <typename T, bool FUSE_KV, bool FROM_PARTIALS>
 __global__ void __launch_bounds__(256) rope_vec_kernel(
     T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v,
     const int32_t* __restrict__ positions, const T* __restrict__ cos_sin,
     const int32_t* __restrict__ slot_ids, T* __restrict__ k_cache, T* __restrict__ v_cache,
     int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
-    int64_t k_stride, int64_t v_stride, bool interleaved) {
+    int64_t k_stride, int64_t v_stride, bool interleaved, RopePartials parts) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int VEC = 16 / sizeof(T);
   const int64_t tok = blockIdx.x;
+  if constexpr (FROM_PARTIALS) {
+    // Materialise this token's qkv row first: x = T(sum of the tile's partial slots), the one
+    // rounding the GEMM epilogue would have done; q, k, v are views of that row (host-checked).
+    static_assert(sizeof(T) == 2, "partials input: 16-bit element types");
+    T* row = q + tok * q_stride;
+    const float* prow = parts.data + tok * parts.row_n;
+    for (int vv = threadIdx.x; vv < parts.row_n / 8; vv += blockDim.x) {
+      float a[8];
+      w4_sum_partials8(a, prow + vv * 8, parts.slot_stride, w4_contrib_col(parts.plan, vv * 8));
+      uint4 o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) oe[i] = Num<T>::from_f(a[i]);
+      st_v4(row + vv * 8, o);
+    }
+    __syncthreads();  // the row is re-read below by other threads of this CTA
+  }
   const int half = rotary_dim / 2;
   const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
   const T* cosp = cs;
@@ -330,7 +359,9 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
     }
     const int v_vecs = n_kv_heads * head_dim / VEC;
     for (int it = threadIdx.x; it < v_vecs; it += blockDim.x)
-      st_v4(vc_row + static_cast<int64_t>(it) * VEC, ld_nc_v4(v + tok * v_stride + it * VEC));
+      st_v4(vc_row + static_cast<int64_t>(it) * VEC,
+            FROM_PARTIALS ? ld_v4(v + tok * v_stride + it * VEC)   // written above by this CTA
+                          : ld_nc_v4(v + tok * v_stride + it * VEC));
   }
 }
 
@@ -342,6 +373,8 @@ __global__ void __launch_bounds__(256) rope_scalar_kernel(
     const int32_t* __restrict__ slot_ids, T* __restrict__ k_cache, T* __restrict__ v_cache,
     int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
     int64_t k_stride, int64_t v_stride, bool interleaved) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t tok = blockIdx.x;
   const int half = rotary_dim / 2;
   const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
@@ -375,7 +408,7 @@ static int launch_rope(void* q, void* k, const void* v, const int32_t* positions
                        const void* cos_sin, const int32_t* slot_ids, void* k_cache, void* v_cache,
                        int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
                        int64_t rotary_dim, int64_t q_stride, int64_t k_stride, int64_t v_stride,
-                       int interleaved, cudaStream_t st) {
+                       int interleaved, cudaStream_t st, const RopePartials* parts = nullptr) {
   constexpr int VEC = 16 / sizeof(T);
   if (n_tokens == 0) return B200_OK;
   const int64_t half = rotary_dim / 2;
@@ -392,16 +425,27 @@ static int launch_rope(void* q, void* k, const void* v, const int32_t* positions
   auto* cs = static_cast<const T*>(cos_sin);
   auto* kc = static_cast<T*>(k_cache);
   auto* vc = static_cast<T*>(v_cache);
-  if (vec_ok) {
-    rope_vec_kernel<T, FUSE_KV><<<grid, 256, 0, st>>>(
-        qq, kk, vv, positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
-        (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0);
-  } else {
-    rope_scalar_kernel<T, FUSE_KV><<<grid, 256, 0, st>>>(
-        qq, kk, vv, positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
-        (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0);
+  if constexpr (FUSE_KV && sizeof(T) == 2) {
+    if (parts) {
+      if (!vec_ok)
+        return set_error(B200_ERR_UNSUPPORTED, "rope_kv_write_splitk: needs the vectorised layout");
+      B200_PDL_LAUNCH_L(1, "rope", (rope_vec_kernel<T, true, true>), grid, 256, 0, st, qq, kk, vv,
+                      positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads,
+                      (int)head_dim, (int)rotary_dim, q_stride, k_stride, v_stride,
+                      interleaved != 0, *parts);
+      return B200_OK;
+    }
   }
-  B200_LAUNCH_OK("rope");
+  if (vec_ok) {
+    B200_PDL_LAUNCH("rope", (rope_vec_kernel<T, FUSE_KV, false>), grid, 256, 0, st, qq, kk, vv,
+                    positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
+                    (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0,
+                    RopePartials{});
+  } else {
+    B200_PDL_LAUNCH("rope", (rope_scalar_kernel<T, FUSE_KV>), grid, 256, 0, st, qq, kk, vv,
+                    positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads, (int)head_dim,
+                    (int)rotary_dim, q_stride, k_stride, v_stride, interleaved != 0);
+  }
   return B200_OK;
 }
 
@@ -467,7 +511,8 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
                                                    int64_t n, int64_t a_stride, int64_t b_stride,
                                                    bool vec) {
   constexpr int VEC = 16 / sizeof(T);
-  pdl_launch_dependents();  // a following W4A16 GEMM may start prefetching its weights now
+  pdl_wait();
+  pdl_launch_dependents();
   if (vec) {
     const int64_t nv = n / VEC;
     const int64_t total = rows * nv;
@@ -501,6 +546,37 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
   }
 }
 
+// out = silu(gate) * up with gate | up = the two halves of the gate_up GEMM's row, delivered as
+// that GEMM's stream-K partials: each is first rounded to T (the GEMM epilogue's rounding), then
+// exactly the MODE 1 arithmetic above.
+template <typename T>
+__global__ void __launch_bounds__(256) silu_mul_splitk_kernel(T* __restrict__ out,
+                                                              const float* __restrict__ partials,
+                                                              W4Plan plan, int64_t slot_stride,
+                                                              int64_t rows, int inter) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int nv = inter / 8;
+  const int64_t total = rows * nv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / nv;
+    const int j = (int)(idx - r * nv);
+    const float* prow = partials + r * (2 * (int64_t)inter);
+    float g[8], u[8];
+    w4_sum_partials8(g, prow + j * 8, slot_stride, w4_contrib_col(plan, j * 8));
+    w4_sum_partials8(u, prow + inter + j * 8, slot_stride, w4_contrib_col(plan, inter + j * 8));
+    uint4 orr;
+    T* o = reinterpret_cast<T*>(&orr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = silu_t<T>(rnd<T>(g[i])) * rnd<T>(u[i]);
+      o[i] = Num<T>::from_f(s);
+    }
+    st_v4(out + r * inter + j * 8, orr);
+  }
+}
+
 template <typename T, int MODE>
 static int launch_silu(void* out, const void* a, const void* b, int64_t rows, int64_t n,
                        int64_t a_stride, int64_t b_stride, cudaStream_t st) {
@@ -512,10 +588,9 @@ static int launch_silu(void* out, const void* a, const void* b, int64_t rows, in
   int64_t blocks = (work + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  silu_kernel<T, MODE><<<(unsigned)blocks, 256, 0, st>>>(
-      static_cast<T*>(out), static_cast<const T*>(a), static_cast<const T*>(b), rows, n, a_stride,
-      b_stride, vec);
-  B200_LAUNCH_OK("silu");
+  B200_PDL_LAUNCH("silu", (silu_kernel<T, MODE>), (unsigned)blocks, 256, 0, st, static_cast<T*>(out),
+                  static_cast<const T*>(a), static_cast<const T*>(b), rows, n, a_stride, b_stride,
+                  vec);
   return B200_OK;
 }
 
@@ -621,6 +696,68 @@ int b200_rope_kv_write(void* q, void* k, const void* v, const int32_t* positions
                                                v_cache, n_tokens, n_heads, n_kv_heads, head_dim,
                                                rotary_dim, q_stride, k_stride, v_stride,
                                                interleaved, static_cast<cudaStream_t>(stream))));
+}
+
+int b200_rope_kv_write_splitk(void* qkv, const float* partials, int splits, int64_t gemm_k,
+                              const int32_t* positions, const void* cos_sin,
+                              const int32_t* slot_ids, void* k_cache, void* v_cache,
+                              int64_t n_tokens, int64_t n_heads, int64_t n_kv_heads,
+                              int64_t head_dim, int64_t rotary_dim, int interleaved, int dtype,
+                              b200_stream_t stream) {
+  B200_CHECK_ARG(qkv && partials && positions && cos_sin && slot_ids && k_cache && v_cache,
+                 "rope_kv_write_splitk: null pointer");
+  B200_CHECK_ARG(rotary_dim > 0 && rotary_dim % 2 == 0 && rotary_dim <= head_dim,
+                 "rope_kv_write_splitk: bad rotary_dim");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "rope_kv_write_splitk: bf16 / fp16 only");
+  const int64_t n = (n_heads + 2 * n_kv_heads) * head_dim;
+  B200_CHECK_ARG(n % 128 == 0 && gemm_k > 0 && gemm_k % 128 == 0 && n_tokens >= 0 && n_tokens <= 128,
+                 "rope_kv_write_splitk: row of %lld is not a W4A16 GEMM output", (long long)n);
+  if (n_tokens == 0) return B200_OK;
+  RopePartials parts{};
+  parts.plan = w4_get_plan(n, gemm_k, n_tokens);
+  B200_CHECK_ARG(splits == parts.plan.slots, "rope_kv_write_splitk: expected %d partial slots, got %d",
+                 parts.plan.slots, splits);
+  parts.data = partials;
+  parts.slot_stride = n_tokens * n;
+  parts.row_n = (int)n;
+  const int es = 2;
+  uint8_t* base = static_cast<uint8_t*>(qkv);
+  void* q = base;
+  void* k = base + n_heads * head_dim * es;
+  void* v = base + (n_heads + n_kv_heads) * head_dim * es;
+  if (dtype == B200_BF16)
+    return launch_rope<__nv_bfloat16, true>(q, k, v, positions, cos_sin, slot_ids, k_cache, v_cache,
+                                            n_tokens, n_heads, n_kv_heads, head_dim, rotary_dim, n, n,
+                                            n, interleaved, static_cast<cudaStream_t>(stream), &parts);
+  return launch_rope<__half, true>(q, k, v, positions, cos_sin, slot_ids, k_cache, v_cache, n_tokens,
+                                   n_heads, n_kv_heads, head_dim, rotary_dim, n, n, n, interleaved,
+                                   static_cast<cudaStream_t>(stream), &parts);
+}
+
+int b200_silu_mul_splitk(void* out, const float* partials, int splits, int64_t gemm_k, int64_t rows,
+                         int64_t inter, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && partials, "silu_mul_splitk: null pointer");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "silu_mul_splitk: bf16 / fp16 only");
+  B200_CHECK_ARG(rows >= 0 && rows <= 128 && inter > 0 && inter % 64 == 0 && gemm_k > 0 &&
+                     gemm_k % 128 == 0 && is_aligned(out, 16) && is_aligned(partials, 16),
+                 "silu_mul_splitk: bad shape / alignment");
+  if (rows == 0) return B200_OK;
+  const W4Plan plan = w4_get_plan(2 * inter, gemm_k, rows);
+  B200_CHECK_ARG(splits == plan.slots, "silu_mul_splitk: expected %d partial slots, got %d",
+                 plan.slots, splits);
+  const int64_t work = rows * (inter / 8);
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_BF16)
+    B200_PDL_LAUNCH_L(1, "silu_mul_splitk", silu_mul_splitk_kernel<__nv_bfloat16>, (unsigned)blocks, 256, 0,
+                    st, static_cast<__nv_bfloat16*>(out), partials, plan, rows * 2 * inter, rows,
+                    (int)inter);
+  else
+    B200_PDL_LAUNCH_L(1, "silu_mul_splitk", silu_mul_splitk_kernel<__half>, (unsigned)blocks, 256, 0, st,
+                    static_cast<__half*>(out), partials, plan, rows * 2 * inter, rows, (int)inter);
+  return B200_OK;
 }
 
 static int kv_copy(bool gather, const int32_t* slot_ids, const void* k, const void* v,

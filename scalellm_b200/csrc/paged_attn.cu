@@ -89,6 +89,8 @@ template <typename T, int D, int R>
 __global__ void __launch_bounds__(ATT_THREADS, (D <= 128 ? 2 : 1))
 paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
                          const __grid_constant__ CUtensorMap vmap, const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES, CPL = Cfg::CPL, EPL = Cfg::EPL;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -417,6 +419,8 @@ template <typename T, int D, int W>
 __global__ void __launch_bounds__(W * 32, (W == 1 ? (D <= 128 ? 6 : 2) : (D <= 128 ? 2 : 1)))
 paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
                       const __grid_constant__ CUtensorMap vmap, const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KS = D / 16;   // k-steps of S = Q K^T
@@ -736,6 +740,8 @@ __global__ void __launch_bounds__(32, (D <= 128 ? 8 : 3))
 paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                           const __grid_constant__ CUtensorMap vmap, const AttnParams p,
                           int64_t total_tiles, int n_seq) {
+  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KS = D / 16, NB = D / 8;
@@ -1076,13 +1082,16 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
   constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8
+  pdl_wait();
   pdl_launch_dependents();  // a following W4A16 GEMM (o_proj) may start prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x * 4 + warp;
   if (h >= p.n_heads) return;
   const int b = blockIdx.y / p.max_q_len, qi = blockIdx.y % p.max_q_len;
-  const int q_begin = p.q_cu_lens[b];
-  const int q_len = p.q_cu_lens[b + 1] - q_begin;
+  // the four length words are requested together: one L2 round trip, then LSE, then every partial
+  const int q_begin = __ldg(p.q_cu_lens + b), q_end = __ldg(p.q_cu_lens + b + 1);
+  const int kv_begin_cu = __ldg(p.kv_cu_lens + b), kv_end_cu = __ldg(p.kv_cu_lens + b + 1);
+  const int q_len = q_end - q_begin;
   if (qi >= q_len) return;
   const int64_t tok = q_begin + qi;
   const int64_t row = (int64_t)blockIdx.y * p.n_heads + h;
@@ -1095,7 +1104,7 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
     if (p.stream) {
       const int G = p.group, kvh = h / G, g = h - kvh * G;
       const int r = qi * G + g, rb = r / 16;
-      const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+      const int kv_len = kv_end_cu - kv_begin_cu;
       const int rows_total = q_len * G, row0 = rb * 16, n_rows = min(16, rows_total - row0);
       const int q_pos0 = kv_len - q_len, qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
       const int kv_end = q_pos0 + qi_max + 1;
@@ -1108,34 +1117,51 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
       const int t1 = min((int)(hi - base), (kv_end + ATT_TILE - 1) / ATT_TILE);
       if (!(lo < hi && t0 < t1)) return -INFINITY;
     }
-    return lse[s];
+    return __ldcg(lse + s);
   };
-  float M = -INFINITY;
-  for (int s0 = 0; s0 < p.n_splits; s0 += 32) M = fmaxf(M, slot_lse(s0 + lane));
+  const float lse_first = slot_lse(lane);  // kept: the usual case has <= 32 split slots
+  float M = lse_first;
+  for (int s0 = 32; s0 < p.n_splits; s0 += 32) M = fmaxf(M, slot_lse(s0 + lane));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
   float L = 0.f;
   float acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  constexpr int CHUNK = 8;  // partial rows requested per round trip
   for (int s0 = 0; s0 < p.n_splits; s0 += 32) {
-    const float my_w = exp2f(slot_lse(s0 + lane) - M);  // 0 for absent / empty pieces
+    const float my_lse = s0 == 0 ? lse_first : slot_lse(s0 + lane);
+    const float my_w = exp2f(my_lse - M);  // 0 for absent / empty pieces
     L += my_w;
     const int ns = min(p.n_splits - s0, 32);
-    for (int s = 0; s < ns; ++s) {
-      const float w = __shfl_sync(0xffffffffu, my_w, s);
-      if (w == 0.f) continue;  // its partial O may be unwritten / NaN
-      const float* src = p.ws_o + (row * p.n_splits + s0 + s) * D + lane * EPL;
-      if constexpr (EPL == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src);
-        acc[0] = fmaf(v.x, w, acc[0]);
-        acc[1] = fmaf(v.y, w, acc[1]);
-        acc[2] = fmaf(v.z, w, acc[2]);
-        acc[3] = fmaf(v.w, w, acc[3]);
-      } else {
+    for (int c0 = 0; c0 < ns; c0 += CHUNK) {
+      float w[CHUNK];
+      float v[CHUNK][EPL];
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(src[e], w, acc[e]);
+      for (int c = 0; c < CHUNK; ++c) {
+        w[c] = (c0 + c < ns) ? __shfl_sync(0xffffffffu, my_w, (c0 + c) & 31) : 0.f;
+        // an absent piece's partial O may be unwritten (NaN): never loaded, never multiplied
+        const float* src = p.ws_o + (row * p.n_splits + s0 + c0 + c) * D + lane * EPL;
+        if (w[c] != 0.f) {
+          if constexpr (EPL == 4) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src));
+            v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+          } else if constexpr (EPL == 2) {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(src));
+            v[c][0] = t.x; v[c][1] = t.y;
+          } else {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) v[c][e] = __ldcg(src + e);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) v[c][e] = 0.f;
+        }
       }
+#pragma unroll
+      for (int c = 0; c < CHUNK; ++c)  // fixed order: deterministic
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(v[c][e], w[c], acc[e]);
     }
   }
 #pragma unroll
@@ -1352,8 +1378,7 @@ static int launch_kernel(KernelT kernel, size_t smem, int threads, const CUtenso
                          cudaStream_t st) {
   B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)p.n_splits, (unsigned)pl.grid_y, (unsigned)pl.grid_z);
-  kernel<<<grid, threads, smem, st>>>(kmap, vmap, p);
-  B200_LAUNCH_OK("paged_attn_decode");
+  B200_PDL_LAUNCH("paged_attn_decode", kernel, grid, threads, smem, st, kmap, vmap, p);
   return B200_OK;
 }
 
@@ -1368,8 +1393,8 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
     auto kernel = paged_attn_persist_kernel<T, D>;
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
-    kernel<<<grid, 32, psmem, st>>>(kmap, vmap, p, pl.total_tiles, pl.n_seq);
-    B200_LAUNCH_OK("paged_attn_stream");
+    B200_PDL_LAUNCH("paged_attn_stream", kernel, grid, 32, psmem, st, kmap, vmap, p,
+                    (int64_t)pl.total_tiles, (int)pl.n_seq);
     rc = B200_OK;
   } else if (pl.impl == 1 && pl.warps == 1) {
     rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,
@@ -1387,8 +1412,7 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   if (rc != B200_OK) return rc;
   if (p.n_splits > 1) {
     dim3 cgrid((unsigned)((p.n_heads + 3) / 4), (unsigned)(batch * p.max_q_len));
-    paged_attn_combine_kernel<T, D><<<cgrid, 128, 0, st>>>(p);
-    B200_LAUNCH_OK("paged_attn_combine");
+    B200_PDL_LAUNCH("paged_attn_combine", (paged_attn_combine_kernel<T, D>), cgrid, 128, 0, st, p);
   }
   return B200_OK;
 }

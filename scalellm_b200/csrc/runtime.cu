@@ -1,5 +1,6 @@
 // runtime.cu — host-side plumbing of libb200decode: error strings, launch
 // counter, cached device properties, driver entry point for tensor maps.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -32,6 +33,14 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+int pdl_level() {
+  static const int level = [] {
+    const char* e = getenv("B200_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  return level;
 }
 
 tensor_map_encode_fn get_tensor_map_encode() {

@@ -237,17 +237,18 @@ template <int MT, int NSUB>
 struct W4Cfg {
   static constexpr int ACT_STAGES = MT <= 64 ? 6 : 3;   // activation ring (L2 / TMA latency)
   static constexpr int RAW_STAGES = MT <= 64 ? 11 : 10; // weight-blob ring (HBM latency)
-  static constexpr int A_STAGES = 4;              // dequantised-weight slots in TMEM, one per dequant group
+  static constexpr int ACC_COLS = 2 * NSUB * MT;  // two buffers of NSUB accumulators [128 x MT] fp32
+  static constexpr int A_COL0 = ACC_COLS < 128 ? 128 : ACC_COLS;
+  static constexpr int A_STAGES = (512 - A_COL0) / 64;  // dequantised-weight slots in TMEM: 6 or 4
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
-  static constexpr int ACC_COLS = 2 * NSUB * MT;  // two buffers of NSUB accumulators [128 x MT] fp32
-  static constexpr int A_COL0 = 256;              // A ring: A_STAGES x 64 columns (128 k of bf16)
   static constexpr int TMEM_COLS = 512;
   static constexpr int N_BARS = 2 * RAW_STAGES + 2 * ACT_STAGES + 2 * A_STAGES + 4;
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)ACT_STAGES * ACT_BYTES +
                                  (size_t)RAW_STAGES * RAW_BYTES + N_BARS * 8 + 64;
-  static_assert(ACC_COLS <= A_COL0 && A_COL0 + A_STAGES * 64 <= TMEM_COLS, "TMEM over-subscribed");
+  static_assert(ACC_COLS <= A_COL0 && A_COL0 + A_STAGES * 64 <= TMEM_COLS && A_STAGES >= 4,
+                "TMEM over-subscribed");
 };
 
 // warp roles: 0-15 dequant (4 groups x 4 lane quadrants), 16 weight-blob producer, 17 activation
@@ -362,12 +363,13 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
-    // group = warp / 4 takes k-tiles cnt % 4 == group and owns TMEM slot `group`; inside a group
-    // warp q = warp % 4 owns TMEM lanes [32q, 32q+32): thread <-> weight row n_local, all 128 k.
+    // group = warp / 4 takes weight tiles cnt % 4 == group; tile cnt goes to TMEM slot
+    // cnt % A_STAGES (a ring shared by the groups: with more slots than groups a group runs ahead
+    // of the tensor pipe instead of waiting for its previous tile's MMAs).  Inside a group warp
+    // q = warp % 4 owns TMEM lanes [32q, 32q+32): thread <-> weight row n_local, all 128 k.
     const int group = warp >> 2;
     const int n_local = (warp & 3) * 32 + lane;
-    const uint32_t a_tmem =
-        tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0 + group * 64;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_COL0;
     const uint32_t raw_u32 = smem_u32(raw_smem);
     const uint32_t sz_off = W4_QBYTES + n_local * 2;               // this row's scale, group 0
     const uint32_t zp_off = W4_QBYTES + p.ngrp * 256 + n_local;    // this row's zero point
@@ -378,8 +380,10 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
         if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
         const int rs = cnt % Cfg::RAW_STAGES;
-        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt >> 2) & 1;
+        const int as = cnt % Cfg::A_STAGES;
+        const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
         const uint32_t raw = raw_u32 + rs * Cfg::RAW_BYTES;
+        const uint32_t a_tmem = a_lane + as * 64;
         mbar_wait(&raw_full[rs], rph);
         if (TRACE && threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
 #pragma unroll
@@ -411,7 +415,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             }
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
-            mbar_wait(&deq_empty[group], aph ^ 1);
+            mbar_wait(&deq_empty[as], aph ^ 1);
             tc_fence_after();
           }
           tmem_st_32x32b_x32(a_tmem + hh * 32, r);
@@ -420,7 +424,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&deq_full[group]);
+          mbar_arrive(&deq_full[as]);
           mbar_arrive(&raw_empty[rs]);
         }
       }
@@ -488,13 +492,13 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         const uint32_t first = (kt > kt0) ? 1u : 0u;
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
-          const int ds = cnt & (Cfg::A_STAGES - 1);
-          const uint32_t dph = (cnt >> 2) & 1;
+          const int ds = cnt % Cfg::A_STAGES;
+          const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
+          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
+          const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
           mbar_wait(&deq_full[ds], dph);
           if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
           tc_fence_after();
-          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
-          const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -531,6 +535,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       const int slot = (int)blockIdx.x - w4_first_owner(p.plan, nt);
       float* part = p.partials + (int64_t)slot * p.slot_stride + (int64_t)nt * (128 * NSUB) + n_local;
       mbar_wait(&tmem_full[buf], tph);
+      // last segment of this CTA: let the consumer kernel's CTAs be scheduled now, so they are
+      // resident (parked in pdl_wait) when this grid drains
+      if (it.u >= it.u1 && warp == W4_WARP_EPI && lane == 0) pdl_launch_dependents();
       if (TRACE && warp == W4_WARP_EPI && lane == 0 && seg == 0) W4_TRACE(6);
       tc_fence_after();
       constexpr int CH = MT >= 32 ? 32 : 16;
@@ -574,6 +581,8 @@ __global__ void __launch_bounds__(256) w4_reduce_kernel(__nv_bfloat16* __restric
                                                         const __nv_bfloat16* __restrict__ bias,
                                                         int M, int N, int64_t ldc,
                                                         int64_t slot_stride, W4Plan plan) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int nvec = N / 8;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (int64_t)M * nvec) return;
@@ -648,34 +657,13 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-// B200_PDL=0 disables programmatic dependent launch (the GEMM then starts only after its
-// predecessor in the stream has drained, as an ordinary launch).
-static bool w4_use_pdl() {
-  static const bool on = [] {
-    const char* e = getenv("B200_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
-
 template <int MT, int NSUB, bool TRACE>
 static int launch_w4_kernel(const CUtensorMap& amap, const W4Params& p, cudaStream_t st) {
   using Cfg = W4Cfg<MT, NSUB>;
   auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE>;
   B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)Cfg::SMEM));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)p.plan.P);
-  cfg.blockDim = dim3(W4_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = w4_use_pdl() ? 1 : 0;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, amap, p));
-  B200_LAUNCH_OK("w4a16_gemm");
+  B200_PDL_LAUNCH_L(1, "w4a16_gemm", kern, (unsigned)p.plan.P, W4_THREADS, Cfg::SMEM, st, amap, p);
   return B200_OK;
 }
 
@@ -706,9 +694,10 @@ W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
   if (P < 1) P = 1;
   const char* ens = getenv("B200_W4_NSUB");
   const int NT128 = (int)(N / 128);
-  // two weight tiles per activation stage when the accumulators fit (M <= 64), N allows and the
-  // coarser partition still fills every SM (share >= KT/7 caps the grid at 7 CTAs per n tile)
-  const bool want2 = ens ? ens[0] == '2' : (long long)(W4_MAX_SLOTS - 1) * (NT128 / 2) >= P;
+  // B200_W4_NSUB=2: two weight tiles per activation stage (halves the activation traffic out of
+  // L2 but leaves only 4 TMEM slots for dequantised weights; measured slower than 1 tile with a
+  // 6-slot ring, so it is opt-in)
+  const bool want2 = ens && ens[0] == '2';
   const int nsub_log2 = (M <= 64 && NT128 % 2 == 0 && want2) ? 1 : 0;
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
@@ -884,10 +873,9 @@ int b200_w4a16_reduce_partials(void* C, const float* partials, int splits, int64
                  plan.slots, splits);
   if (M == 0) return B200_OK;
   const int64_t nvec = M * (N / 8);
-  w4_reduce_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(C), partials, static_cast<const __nv_bfloat16*>(bias), (int)M,
-      (int)N, ldc, M * N, plan);
-  B200_LAUNCH_OK("w4a16_reduce");
+  B200_PDL_LAUNCH_L(1, "w4a16_reduce", w4_reduce_kernel, (unsigned)((nvec + 255) / 256), 256, 0,
+                  static_cast<cudaStream_t>(stream), static_cast<__nv_bfloat16*>(C), partials,
+                  static_cast<const __nv_bfloat16*>(bias), (int)M, (int)N, ldc, M * N, plan);
   return B200_OK;
 }
 
@@ -938,10 +926,9 @@ int b200_w4a16_gemm(void* C, const void* A, const void* packed, const void* bias
                           K, lda, group_size, plan, st);
     if (rc != B200_OK) return rc;
     const int64_t nvec = mc * (N / 8);
-    w4_reduce_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(
-        static_cast<__nv_bfloat16*>(C) + m0 * ldc, partials,
-        static_cast<const __nv_bfloat16*>(bias), (int)mc, (int)N, ldc, mc * N, plan);
-    B200_LAUNCH_OK("w4a16_reduce");
+    B200_PDL_LAUNCH_L(1, "w4a16_reduce", w4_reduce_kernel, (unsigned)((nvec + 255) / 256), 256, 0, st,
+                    static_cast<__nv_bfloat16*>(C) + m0 * ldc, (const float*)partials,
+                    static_cast<const __nv_bfloat16*>(bias), (int)mc, (int)N, ldc, mc * N, plan);
   }
   return B200_OK;
 }

@@ -193,16 +193,27 @@ class LlamaDecoder:
         for L, cache in zip(self.layers, self.kv_caches):
             n1 = L["input_norm"](h) if pending is None else norm_residual(L["input_norm"], pending,
                                                                            pending_is_partials)
-            qkv = L["qkv"](n1)
-            q = qkv[:, : self.q_size]
-            k = qkv[:, self.q_size: self.q_size + self.kv_size]
-            v = qkv[:, self.q_size + self.kv_size:]
-            attn = L["attn"](q, k, v, positions, cache, params)
+            fuse_qkv = (self.fuse_splitk and hasattr(L["qkv"], "supports_partials")
+                        and L["qkv"].supports_partials(T) and L["attn"].supports_partials()
+                        and not cache.empty())
+            if fuse_qkv:   # GEMM partials -> (sum, RoPE, KV write) in one launch
+                attn = L["attn"].forward_partials(L["qkv"].forward_partials(n1), positions, cache,
+                                                  params, n1.dtype)
+            else:
+                qkv = L["qkv"](n1)
+                q = qkv[:, : self.q_size]
+                k = qkv[:, self.q_size: self.q_size + self.kv_size]
+                v = qkv[:, self.q_size + self.kv_size:]
+                attn = L["attn"](q, k, v, positions, cache, params)
             fuse_o = self.fuse_splitk and hasattr(L["o"], "supports_partials") and L["o"].supports_partials(T)
             o = L["o"].forward_partials(attn) if fuse_o else L["o"](attn)
             n2 = norm_residual(L["post_norm"], o, fuse_o)            # h = h + o ; n2 = norm(h)
-            gu = L["gate_up"](n2)
-            act = kernels.silu_mul(gu[:, :I], gu[:, I:])
+            if (self.fuse_splitk and hasattr(L["gate_up"], "supports_partials")
+                    and L["gate_up"].supports_partials(T)):
+                act = kernels.silu_mul_splitk(L["gate_up"].forward_partials(n2), n2.dtype)
+            else:
+                gu = L["gate_up"](n2)
+                act = kernels.silu_mul(gu[:, :I], gu[:, I:])
             fuse_d = self.fuse_splitk and hasattr(L["down"], "supports_partials") and L["down"].supports_partials(T)
             pending = L["down"].forward_partials(act) if fuse_d else L["down"](act)
             pending_is_partials = fuse_d

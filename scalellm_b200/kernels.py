@@ -344,6 +344,39 @@ def w4a16_reduce_partials(partials: W4Partials, out: Optional[torch.Tensor] = No
     return out
 
 
+def rope_and_set_kv_cache_splitk(partials: W4Partials, n_heads: int, n_kv_heads: int, head_dim: int,
+                                 positions: torch.Tensor, cos_sin: torch.Tensor,
+                                 slot_ids: torch.Tensor, key_cache: torch.Tensor,
+                                 value_cache: torch.Tensor, rotary_dim: int, interleaved: bool,
+                                 dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """qkv GEMM partials -> qkv [T, (H + 2 Hkv) D] with q, k rotated, rotated k and v written to
+    their cache slots: the GEMM's reduction + RoPE + set_kv_cache in one launch."""
+    data = partials.data
+    _cuda(data, positions, cos_sin, slot_ids, key_cache, value_cache)
+    _check_i32(positions, slot_ids)
+    S, T, n = data.shape
+    assert n == (n_heads + 2 * n_kv_heads) * head_dim and data.is_contiguous()
+    assert key_cache.is_contiguous() and value_cache.is_contiguous()
+    qkv = torch.empty((T, n), dtype=dtype, device=data.device)
+    check(_lib.load().b200_rope_kv_write_splitk(_p(qkv), _p(data), S, partials.K, _p(positions),
+                                                _p(cos_sin), _p(slot_ids), _p(key_cache),
+                                                _p(value_cache), T, n_heads, n_kv_heads, head_dim,
+                                                rotary_dim, int(interleaved), _dt(qkv), _stream()))
+    return qkv
+
+
+def silu_mul_splitk(partials: W4Partials, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """gate_up GEMM partials [slots, rows, 2*inter] -> silu(gate) * up [rows, inter]."""
+    data = partials.data
+    _cuda(data)
+    S, rows, n2 = data.shape
+    assert n2 % 2 == 0 and data.is_contiguous()
+    out = torch.empty((rows, n2 // 2), dtype=dtype, device=data.device)
+    check(_lib.load().b200_silu_mul_splitk(_p(out), _p(data), S, partials.K, rows, n2 // 2,
+                                           _dt(out), _stream()))
+    return out
+
+
 def rms_norm_residual_splitk(out: torch.Tensor, residual: torch.Tensor, partials: W4Partials,
                              weight: torch.Tensor, epsilon: float) -> None:
     """residual += T(sum over slots of partials); out = rms_norm(residual) * weight."""

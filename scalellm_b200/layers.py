@@ -214,6 +214,25 @@ class Attention:
         self.handler.batch_decode(q, kv_cache, input_params, self.sliding_window, out)
         return out.view(T, -1)
 
+    def supports_partials(self) -> bool:
+        h = self.handler
+        return (self.fuse and isinstance(h, B200AttnHandler) and h.pos_emb is not None)
+
+    def forward_partials(self, qkv_partials, positions, kv_cache: KVCache,
+                         input_params: InputParameters, dtype=torch.bfloat16) -> torch.Tensor:
+        """Same as forward, with q | k | v delivered as the qkv GEMM's stream-K partials: their
+        reduction, RoPE and the KV-slot write are one launch."""
+        h = self.handler
+        qkv = kernels.rope_and_set_kv_cache_splitk(
+            qkv_partials, self.n_heads, self.n_kv_heads, self.head_dim, positions,
+            h.pos_emb.cos_sin_cache, input_params.new_cache_slots, kv_cache.key_cache,
+            kv_cache.value_cache, h.pos_emb.rotary_dim, h.pos_emb.interleaved, dtype)
+        T = qkv.size(0)
+        q = qkv[:, : self.n_heads * self.head_dim].view(T, self.n_heads, self.head_dim)
+        out = torch.empty((T, self.n_heads, self.head_dim), dtype=qkv.dtype, device=qkv.device)
+        h.batch_decode(q, kv_cache, input_params, self.sliding_window, out)
+        return out.view(T, -1)
+
     __call__ = forward
 
 
@@ -354,6 +373,16 @@ class ColumnParallelQLinear(_QLinearBase):
         if b is not None:
             b = b[shard_range(self.full_N, self.pa.rank, self.pa.world_size)]
         self._set_shard(qw, qz, sc, b)
+
+    def supports_partials(self, n_rows: int) -> bool:
+        """Partials output for a fused consumer (rope / silu*mul): the column shard is rank-local,
+        so this also holds under tensor parallelism (no gather, no bias)."""
+        return self.bias is None and 0 < n_rows <= 128 and not (self.pa.world_size > 1 and self.gather_output)
+
+    def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
+        self._ensure_packed()
+        x2 = x.reshape(-1, x.shape[-1])
+        return kernels.w4a16_gemm_splitk(x2, self.packed, self.N, self.qa.group_size)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out = self._gemm(x, self.bias)

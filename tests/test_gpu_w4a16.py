@@ -203,3 +203,44 @@ def test_splitk_partials_fused_into_rms_norm_residual(K, N, M):
     # deterministic
     p2 = kernels.w4a16_gemm_splitk(a.to(DEV), packed, N, 128)
     assert torch.equal(c, kernels.w4a16_reduce_partials(p2).cpu())
+
+
+@pytest.mark.parametrize("K,inter,M", [(4096, 14336, 64), (512, 256, 7)])
+def test_silu_mul_splitk_matches_unfused(K, inter, M):
+    """gate_up partials -> silu(gate) * up in one launch == reduce -> silu_mul (bit-identical:
+    same slot order, same rounding points; models/meta/llama.h:61-64)."""
+    a, w_ref, packed = gemm_case(M, K, 2 * inter, 128, seed=K + inter)
+    parts = kernels.w4a16_gemm_splitk(a.to(DEV), packed, 2 * inter, 128, poison=True)
+    fused = kernels.silu_mul_splitk(parts)
+    gu = kernels.w4a16_reduce_partials(parts)
+    unfused = kernels.silu_with_mul(gu)
+    assert torch.isfinite(fused.float()).all()
+    assert torch.equal(fused, unfused)
+
+
+@pytest.mark.parametrize("M,H,Hkv,D,bs", [(64, 32, 8, 128, 8), (5, 4, 2, 64, 16)])
+def test_rope_kv_write_splitk_matches_unfused(M, H, Hkv, D, bs):
+    """qkv partials -> (sum, RoPE, KV-slot write) in one launch == reduce -> rope_and_set_kv_cache:
+    bit-identical q/k/v rows and caches (models/meta/llama.h:123-133)."""
+    from scalellm_b200.layers import RotaryEmbedding
+    K, n = 512, (H + 2 * Hkv) * D
+    a, w_ref, packed = gemm_case(M, K, n, 128, seed=n + M)
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    rope = RotaryEmbedding(D, 4096, inv_freq, False, torch.bfloat16, DEV)
+    gen = torch.Generator().manual_seed(3)
+    positions = torch.randint(0, 4096, (M,), generator=gen, dtype=torch.int32).to(DEV)
+    n_slots = 40 * bs
+    slots = torch.randperm(n_slots, generator=gen)[:M].to(torch.int32).to(DEV)
+    caches = [torch.zeros(n_slots, Hkv, D, dtype=torch.bfloat16, device=DEV) for _ in range(4)]
+    parts = kernels.w4a16_gemm_splitk(a.to(DEV), packed, n, 128, poison=True)
+    qkv_f = kernels.rope_and_set_kv_cache_splitk(parts, H, Hkv, D, positions, rope.cos_sin_cache,
+                                                 slots, caches[0], caches[1], rope.rotary_dim, False)
+    qkv_u = kernels.w4a16_reduce_partials(parts)
+    q = qkv_u[:, : H * D].view(M, H, D)
+    k = qkv_u[:, H * D: (H + Hkv) * D].view(M, Hkv, D)
+    v = qkv_u[:, (H + Hkv) * D:].view(M, Hkv, D)
+    kernels.rope_and_set_kv_cache(q, k, v, positions, rope.cos_sin_cache, slots, caches[2],
+                                  caches[3], rope.rotary_dim, False)
+    assert torch.isfinite(qkv_f.float()).all()
+    assert torch.equal(qkv_f, qkv_u)
+    assert torch.equal(caches[0], caches[2]) and torch.equal(caches[1], caches[3])
