@@ -278,6 +278,14 @@ B200_API int b200_silu_mul_splitk(void* out, const float* partials, int splits, 
 B200_API void b200_debug_set_trace(void* device_buffer);
 
 /* ------------------------------------------------------------------------ *
+ * Greedy sampling tail (the step driver's last kernel):
+ *     out[r] = argmax_j logits[r, j]   (first index of the maximum, NaN counts as the maximum:
+ *     torch.argmax semantics, which the reference's greedy path uses, src/sampling/sampler.cpp).
+ * ------------------------------------------------------------------------ */
+B200_API int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t n, int64_t stride,
+                         int dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * A9  Tensor-parallel all-reduce over NVLink peer memory
  *     replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
  *     for the <= 1 MiB row-parallel reductions of the decode step.

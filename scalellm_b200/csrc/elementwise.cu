@@ -594,6 +594,67 @@ static int launch_silu(void* out, const void* a, const void* b, int64_t rows, in
   return B200_OK;
 }
 
+// ===========================================================================
+// greedy sampling tail: argmax over the vocabulary
+// ===========================================================================
+// torch.argmax semantics: first index of the maximum, NaN counts as the maximum.
+__device__ __forceinline__ bool argmax_better(float a, int ia, float b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an != bn) return an;
+  if (an) return ia < ib;
+  return a > b || (a == b && ia < ib);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) argmax_kernel(int64_t* __restrict__ out,
+                                                     const T* __restrict__ x, int n,
+                                                     int64_t stride) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float sv[16];
+  __shared__ int si[16];
+  pdl_wait();
+  pdl_launch_dependents();
+  const T* row = x + (int64_t)blockIdx.x * stride;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  const bool vec = (stride % VEC == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int nv = vec ? n / VEC : 0;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 raw = ld_nc_v4(row + v * VEC);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float f = Num<T>::to_f(e[i]);
+      if (argmax_better(f, v * VEC + i, best, bi)) { best = f; bi = v * VEC + i; }
+    }
+  }
+  for (int j = nv * VEC + threadIdx.x; j < n; j += blockDim.x) {
+    const float f = Num<T>::to_f(row[j]);
+    if (argmax_better(f, j, best, bi)) { best = f; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (argmax_better(ob, oi, best, bi)) { best = ob; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < (int)(blockDim.x >> 5) ? sv[lane] : -INFINITY;
+    bi = lane < (int)(blockDim.x >> 5) ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (argmax_better(ob, oi, best, bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) out[blockIdx.x] = bi;
+  }
+}
+
+
 }  // namespace b200
 
 // ===========================================================================
@@ -840,6 +901,31 @@ int b200_silu_mul_strided(void* out, const void* gate, const void* up, int64_t r
                  "silu_mul_strided: bad shape");
   DISPATCH_DTYPE3(dtype, (launch_silu<T, 1>(out, gate, up, rows, n, gate_stride, up_stride,
                                             static_cast<cudaStream_t>(stream))));
+}
+
+int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t n, int64_t stride, int dtype,
+                b200_stream_t stream) {
+  B200_CHECK_ARG(out && logits, "argmax: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31) && stride >= n, "argmax: bad shape");
+  if (rows == 0) return B200_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case B200_BF16:
+      B200_PDL_LAUNCH("argmax", argmax_kernel<__nv_bfloat16>, (unsigned)rows, 512, 0, st, out,
+                      static_cast<const __nv_bfloat16*>(logits), (int)n, stride);
+      break;
+    case B200_FP16:
+      B200_PDL_LAUNCH("argmax", argmax_kernel<__half>, (unsigned)rows, 512, 0, st, out,
+                      static_cast<const __half*>(logits), (int)n, stride);
+      break;
+    case B200_FP32:
+      B200_PDL_LAUNCH("argmax", argmax_kernel<float>, (unsigned)rows, 512, 0, st, out,
+                      static_cast<const float*>(logits), (int)n, stride);
+      break;
+    default:
+      return set_error(B200_ERR_UNSUPPORTED, "argmax: unsupported dtype %d", dtype);
+  }
+  return B200_OK;
 }
 
 }  // extern "C"

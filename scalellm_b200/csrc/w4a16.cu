@@ -237,9 +237,19 @@ template <int MT, int NSUB>
 struct W4Cfg {
   static constexpr int ACT_STAGES = MT <= 64 ? 6 : 3;   // activation ring (L2 / TMA latency)
   static constexpr int RAW_STAGES = MT <= 64 ? 11 : 10; // weight-blob ring (HBM latency)
-  static constexpr int ACC_COLS = 2 * NSUB * MT;  // two buffers of NSUB accumulators [128 x MT] fp32
+  // accumulators [128 x MT] fp32: double buffered (epilogue of a segment overlaps the next
+  // segment's MMAs) for one weight tile per unit; single buffered for two, so that the
+  // dequantised-weight ring keeps 6 slots (the MMA warp then waits for the epilogue to drain at
+  // a segment boundary, which a CTA crosses at most a couple of times)
+  static constexpr int ACC_BUFS = (NSUB == 1 && MT <= 64) || MT > 64 ? 2 : 1;
+  static constexpr int ACC_COLS = ACC_BUFS * NSUB * MT;
   static constexpr int A_COL0 = ACC_COLS < 128 ? 128 : ACC_COLS;
   static constexpr int A_STAGES = (512 - A_COL0) / 64;  // dequantised-weight slots in TMEM: 6 or 4
+  // Release granularity of slots / activation stages (tiles per tcgen05.commit).  A commit costs
+  // the issuing thread ~170 cycles (tools/microbench/mix.cu), but releasing in pairs measured
+  // slower end to end (the dequant warps wait longer for slots), so it stays 1.
+  static constexpr int PAIR = 1;
+  static constexpr int ACT_PAIR = 1;
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
@@ -375,6 +385,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     const uint32_t zp_off = W4_QBYTES + p.ngrp * 256 + n_local;    // this row's zero point
     SegIter it{u_begin, u_end, KT};
     int nt, kt0, kt1, cnt = 0;  // cnt counts WEIGHT tiles (NSUB per unit)
+    long long w_raw = 0, w_slot = 0;  // TRACE: cycles spent waiting
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt)
       for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
@@ -384,7 +395,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
         const uint32_t raw = raw_u32 + rs * Cfg::RAW_BYTES;
         const uint32_t a_tmem = a_lane + as * 64;
+        long long tw = TRACE ? clock64() : 0;
         mbar_wait(&raw_full[rs], rph);
+        if (TRACE) w_raw += clock64() - tw;
         if (TRACE && threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {  // 64 k = 32 TMEM columns per tcgen05.st
@@ -415,7 +428,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             }
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
-            mbar_wait(&deq_empty[as], aph ^ 1);
+            tw = TRACE ? clock64() : 0;
+            mbar_wait(&deq_empty[as / Cfg::PAIR], aph ^ 1);
+            if (TRACE) w_slot += clock64() - tw;
             tc_fence_after();
           }
           tmem_st_32x32b_x32(a_tmem + hh * 32, r);
@@ -430,6 +445,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       }
     }
     if (threadIdx.x == 0) W4_TRACE(3);
+    if constexpr (TRACE) {
+      if (threadIdx.x == 0) {
+        p.trace[(int64_t)blockIdx.x * 16 + 12] = w_raw;
+        p.trace[(int64_t)blockIdx.x * 16 + 13] = w_slot;
+      }
+    }
   } else if (warp == W4_WARP_RAW) {
     // ===================== weight-blob producer ==============================
     // Weights are never written by another kernel: under programmatic dependent launch this
@@ -461,7 +482,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          mbar_wait(&act_empty[as], aph ^ 1);
+          mbar_wait(&act_empty[as / Cfg::ACT_PAIR], aph ^ 1);
           mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
@@ -472,22 +493,30 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     __syncwarp();
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
-    // The whole warp runs this loop converged so every operand is warp-uniform (uniform
-    // registers, no per-instruction ELECT/R2UR loop); one elected lane issues the UMMAs.
+    // The whole warp runs this loop converged so every operand is warp-uniform; one elected lane
+    // issues the UMMAs.  This one thread paces the kernel: it shares its scheduler with four
+    // dequant warps, and every tcgen05.commit / barrier wait costs it ~170 cycles
+    // (tools/microbench/mix.cu), so a weight tile takes ~600 cycles here against 256 of MMA time.
     constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
     SegIter it{u_begin, u_end, KT};
+    const int n_tiles = (u_end - u_begin) * NSUB;
     int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
+    long long w_act = 0, w_deq = 0, w_acc = 0;  // TRACE: cycles spent waiting per barrier kind
     while (it.next(nt, kt0, kt1)) {
-      const int buf = seg & 1;
-      const uint32_t tph = (seg >> 1) & 1;
+      const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
+      const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
+      long long tw = TRACE ? clock64() : 0;
       mbar_wait(&tmem_empty[buf], tph ^ 1);
+      if (TRACE) w_acc += clock64() - tw;
       tc_fence_after();
       for (int kt = kt0; kt < kt1; ++kt, ++ucnt) {
         const int as = ucnt % Cfg::ACT_STAGES;
         const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
+        tw = TRACE ? clock64() : 0;
         mbar_wait(&act_full[as], aph);
+        if (TRACE) w_act += clock64() - tw;
         const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
         const uint32_t first = (kt > kt0) ? 1u : 0u;
 #pragma unroll
@@ -496,9 +525,14 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
           const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
           const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
+          tw = TRACE ? clock64() : 0;
           mbar_wait(&deq_full[ds], dph);
+          if (TRACE) w_deq += clock64() - tw;
           if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
           tc_fence_after();
+          // end of a ring pair (or of this CTA's work): release both slots / both stages
+          const bool pair_end = Cfg::PAIR == 1 || (cnt & 1) == 1 || cnt == n_tiles - 1;
+          const bool unit_end = sub == NSUB - 1;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -507,11 +541,11 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
                   b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
               umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
             }
-            umma_commit(&deq_empty[ds]);
-            if (sub == NSUB - 1) {
-              umma_commit(&act_empty[as]);
-              if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
+            if (pair_end) {
+              umma_commit(&deq_empty[ds / Cfg::PAIR]);
+              if (unit_end) umma_commit(&act_empty[as / Cfg::ACT_PAIR]);
             }
+            if (unit_end && kt == kt1 - 1) umma_commit(&tmem_full[buf]);
           }
           __syncwarp();
         }
@@ -519,6 +553,13 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       ++seg;
     }
     if (lane == 0) W4_TRACE(5);
+    if constexpr (TRACE) {
+      if (lane == 0) {
+        p.trace[(int64_t)blockIdx.x * 16 + 9] = w_act;
+        p.trace[(int64_t)blockIdx.x * 16 + 10] = w_deq;
+        p.trace[(int64_t)blockIdx.x * 16 + 11] = w_acc;
+      }
+    }
     __syncwarp();
   } else if (warp >= W4_WARP_EPI) {
     // ===================== epilogue warps (4) =================================
@@ -530,8 +571,8 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     SegIter it{u_begin, u_end, KT};
     int nt, kt0, kt1, seg = 0;
     while (it.next(nt, kt0, kt1)) {
-      const int buf = seg & 1;
-      const uint32_t tph = (seg >> 1) & 1;
+      const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
+      const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
       const int slot = (int)blockIdx.x - w4_first_owner(p.plan, nt);
       float* part = p.partials + (int64_t)slot * p.slot_stride + (int64_t)nt * (128 * NSUB) + n_local;
       mbar_wait(&tmem_full[buf], tph);
@@ -695,8 +736,8 @@ W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
   const char* ens = getenv("B200_W4_NSUB");
   const int NT128 = (int)(N / 128);
   // B200_W4_NSUB=2: two weight tiles per activation stage (halves the activation traffic out of
-  // L2 but leaves only 4 TMEM slots for dequantised weights; measured slower than 1 tile with a
-  // 6-slot ring, so it is opt-in)
+  // L2).  Measured no faster than one tile per stage (the MMA-issuing thread, not L2, paces the
+  // kernel), so it is opt-in.
   const bool want2 = ens && ens[0] == '2';
   const int nsub_log2 = (M <= 64 && NT128 % 2 == 0 && want2) ? 1 : 0;
   {

@@ -371,7 +371,7 @@ class GraphedStep:
 
     def _run(self) -> torch.Tensor:
         logits = self.model(self.tokens, self.positions, self.params)
-        return torch.argmax(logits, dim=-1) if self.greedy else logits
+        return kernels.argmax(logits) if self.greedy else logits
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()

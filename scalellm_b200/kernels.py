@@ -392,6 +392,16 @@ def rms_norm_residual_splitk(out: torch.Tensor, residual: torch.Tensor, partials
                                                     _stream()))
 
 
+def argmax(logits: torch.Tensor) -> torch.Tensor:
+    """Greedy sampling: torch.argmax(logits, dim=-1) (first maximal index) in one launch."""
+    _cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
+    check(_lib.load().b200_argmax(_p(out), _p(logits), logits.shape[0], logits.shape[1],
+                                  logits.stride(0), _dt(logits), _stream()))
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().b200_launch_count())
 

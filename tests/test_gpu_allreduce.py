@@ -51,16 +51,24 @@ def _worker(rank, world, port):
                 ys = [torch.empty_like(y) for _ in range(world)]
                 dist.all_gather(ys, y)
                 assert all(torch.equal(ys[0], t) for t in ys)
-        # split-K partials as the local operand (row-parallel GEMM fused with the reduction)
-        g = torch.Generator(device=dev).manual_seed(7 + rank)
-        parts = torch.randn(4, 64, 4096, generator=g, device=dev)
+        # the row-parallel GEMM's stream-K partials as the local operand: the all-reduce's copy-in
+        # sums each tile's slots -> bit-identical to reduce_partials followed by the plain all-reduce
+        from scalellm_b200 import kernels
+        import numpy as np
+        K, N, M = 2048, 4096, 64
+        rng = np.random.default_rng(11 + rank)
+        qw = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, size=(K, N // 8), dtype=np.int64).astype(np.int32)).to(dev)
+        qz = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, size=(K // 128, N // 8), dtype=np.int64).astype(np.int32)).to(dev)
+        sc = (torch.rand(K // 128, N, generator=torch.Generator().manual_seed(rank)) * 0.01 + 1e-3).bfloat16().to(dev)
+        packed = kernels.w4a16_prepack_awq(qw, qz, sc, 128)
+        a = torch.randn(M, K, generator=torch.Generator().manual_seed(5 + rank)).bfloat16().to(dev)
+        parts = kernels.w4a16_gemm_splitk(a, packed, N, 128, poison=True)
         got = pg.allreduce_partials(parts, torch.bfloat16)
-        local = parts.sum(0).bfloat16()
-        gl = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gl, local)
-        want = sum(t.float() for t in gl).bfloat16()
-        assert (got.view(torch.int16) == want.view(torch.int16)).float().mean() > 0.99
-        assert torch.allclose(got.float(), want.float(), rtol=1e-2, atol=1e-2)
+        want = kernels.w4a16_reduce_partials(parts)
+        pg.allreduce(want)
+        torch.cuda.synchronize()
+        assert torch.isfinite(got.float()).all()
+        assert torch.equal(got, want)
         # larger than the symmetric buffer -> NCCL path, still correct
         big = torch.ones(2 << 20, device=dev)
         pg.allreduce(big)

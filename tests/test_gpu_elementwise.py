@@ -161,3 +161,24 @@ def test_silu_odd_width_scalar_path():
     x = torch.randn(3, 2 * 37).bfloat16()
     out = kernels.silu_with_mul(x.to(DEV))
     assert_ulp(out, ops.silu_with_mul(x), max_ulp=1, max_frac=0.05)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("rows,n", [(64, 128256), (3, 1000), (1, 7), (5, 4099)])
+def test_argmax_matches_torch(dtype, rows, n):
+    """Greedy sampling tail: first index of the maximum (ties are common in bf16 logits), NaN wins."""
+    from scalellm_b200 import kernels
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(rows, n, generator=gen).to(dtype)
+    x[0, n // 2] = x[0].max()            # a tie: the first occurrence must win
+    x[0, n - 1] = x[0].max()
+    if rows > 1:
+        x[1, min(5, n - 1)] = float("nan")
+    d = x.to(DEV)
+    got = kernels.argmax(d)
+    assert got.dtype == torch.int64
+    assert torch.equal(got.cpu(), torch.argmax(x.float(), dim=-1))
+    # a strided view (row stride > n), as the lm_head output of a padded buffer would be
+    buf = torch.zeros(rows, n + 8, dtype=dtype, device=DEV)
+    buf[:, :n] = d
+    assert torch.equal(kernels.argmax(buf[:, :n]).cpu(), got.cpu())

@@ -115,7 +115,9 @@ def test_gemm_group_sizes(g, method):
 
 
 @pytest.mark.parametrize("K,N", [(4096, 6144), (4096, 4096), (4096, 28672), (14336, 4096),
-                                 (128, 128), (256, 18944)])
+                                 (128, 128), (256, 18944),
+                                 # the same projections as TP=8 shards (column: N/8, row: K/8)
+                                 (4096, 768), (512, 4096), (4096, 3584), (1792, 4096)])
 def test_gemm_llama_shapes_m64(K, N):
     """The four Llama-3-8B decoder projections at the benchmark batch (+ edge shapes): every
     stream-K partition (full tiles, head/tail partials, multi-CTA reductions) is exercised."""

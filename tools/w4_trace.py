@@ -10,7 +10,8 @@ from scalellm_b200 import _lib, kernels  # noqa: E402
 
 DEV = "cuda"
 NAMES = ["start", "setup_done", "deq_first_raw", "deq_g0_done", "mma_first", "mma_last_issued",
-         "epi_first_full", "epi_done", "end"]
+         "epi_first_full", "epi_done", "end", "SUM mma wait act_full", "SUM mma wait deq_full",
+         "SUM mma wait acc_empty", "SUM deq(g0) wait raw_full", "SUM deq(g0) wait slot"]
 
 
 def run(K, N, M=64, g=128):
@@ -39,6 +40,7 @@ def run(K, N, M=64, g=128):
     t = trace.cpu().view(-1, 16)
     t = t[t[:, 0] != 0]
     rel = (t - t[:, :1]).float()
+    rel[:, 9:] = t[:, 9:].float()        # wait totals are already durations
     rel[t == 0] = float("nan")
     print(f"== K={K} N={N} M={M}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {t.shape[0]} CTAs "
           f"(cycles; ~1.9 cycles/ns)")
