@@ -1372,6 +1372,16 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
   return pl;
 }
 
+// B200_ATTN_PDL=1 launches the stream kernel and the combine pass programmatically already at
+// B200_PDL level 1 (experiment knob; default: only at level 2)
+static int attn_pdl_level() {
+  static const int lv = [] {
+    const char* e = getenv("B200_ATTN_PDL");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return lv;
+}
+
 template <typename KernelT>
 static int launch_kernel(KernelT kernel, size_t smem, int threads, const CUtensorMap& kmap,
                          const CUtensorMap& vmap, const AttnParams& p, const AttnPlan& pl,
@@ -1393,7 +1403,7 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
     auto kernel = paged_attn_persist_kernel<T, D>;
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
-    B200_PDL_LAUNCH("paged_attn_stream", kernel, grid, 32, psmem, st, kmap, vmap, p,
+    B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap, vmap, p,
                     (int64_t)pl.total_tiles, (int)pl.n_seq);
     rc = B200_OK;
   } else if (pl.impl == 1 && pl.warps == 1) {
@@ -1412,7 +1422,7 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   if (rc != B200_OK) return rc;
   if (p.n_splits > 1) {
     dim3 cgrid((unsigned)((p.n_heads + 3) / 4), (unsigned)(batch * p.max_q_len));
-    B200_PDL_LAUNCH("paged_attn_combine", (paged_attn_combine_kernel<T, D>), cgrid, 128, 0, st, p);
+    B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_combine", (paged_attn_combine_kernel<T, D>), cgrid, 128, 0, st, p);
   }
   return B200_OK;
 }

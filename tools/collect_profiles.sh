@@ -8,6 +8,7 @@ G=gpurun_out
 P=profiles
 mkdir -p $P
 [ -s $G/bench.json ] && tail -1 $G/bench.json > $P/${R}_bench.json
+[ -s $G/bench_ref.json ] && tail -1 $G/bench_ref.json > $P/${R}_bench_reference.json
 [ -s $G/launches.csv ] && python tools/ncu_summary.py launches $G/launches.csv $P/${R}_launches_4layers_eager.md \
     "$R: launch list of bench.py --layers 4 --no-graph (1 warm-up + 1 step)" > /dev/null
 [ -s $G/prof_attn.ncu-rep ] && python tools/ncu_summary.py full $G/prof_attn.ncu-rep $P/${R}_ncu_paged_attn.md paged_attn > /dev/null

@@ -95,8 +95,13 @@ if has deq; then
   echo "deq rc=$?" | tee -a $OUT/summary.txt
   cat $OUT/deq.log | tee -a $OUT/summary.txt
 fi
+if has ref; then
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
+  echo "bench reference rc=$?" | tee -a $OUT/summary.txt
+  tail -c 900 $OUT/bench_ref.json | tee -a $OUT/summary.txt
+fi
 if has micro; then
-  for b in readbw kvbw hmma deq; do
+  for b in readbw kvbw hmma deq umma mix; do
     timeout 120 tools/microbench/$b > $OUT/micro_$b.log 2>&1
     echo "micro $b rc=$?" | tee -a $OUT/summary.txt
   done

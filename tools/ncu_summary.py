@@ -61,6 +61,10 @@ def launches(path, out, title):
             if r.get("Metric Unit") == "us":
                 v *= 1e3
             rows.append((short(r["Kernel Name"]), v, r["Grid Size"], r["Block Size"]))
+    # drop model construction (weight init, prepack): the first decode step starts with the
+    # embedding lookup, the only gather kernel in the run
+    first = next((i for i, r in enumerate(rows) if "vectorized_gather_kernel" in r[0]), 0)
+    dropped, rows = first, rows[first:]
     agg = OrderedDict()
     for n, v, g, b in rows:
         a = agg.setdefault(n, [0, 0.0, g, b])
@@ -71,7 +75,8 @@ def launches(path, out, title):
     with open(out, "w") as f:
         f.write(f"# {title}\n\n")
         f.write(f"source: `{os.path.relpath(path, ROOT)}` (ncu --metrics gpu__time_duration.sum "
-                f"--clock-control none); {len(rows)} launches, {tot / 1e3:.1f} us total.\n")
+                f"--clock-control none); {len(rows)} launches from the first decode step on "
+                f"({dropped} model-construction launches dropped), {tot / 1e3:.1f} us total.\n")
         f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
         f.write("| kernel | launches | total us | mean us | share | grid | block |\n|---|---:|---:|---:|---:|---|---|\n")
         for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
