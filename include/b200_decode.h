@@ -273,6 +273,14 @@ B200_API int b200_rope_kv_write_splitk(void* qkv, const float* partials, int spl
 B200_API int b200_silu_mul_splitk(void* out, const float* partials, int splits, int64_t gemm_k,
                                   int64_t rows, int64_t inter, int dtype, b200_stream_t stream);
 
+/* Debug / test hook (host arithmetic only, no device): the stream-K partition the GEMM and its
+ * consumers use for a [K, N] weight split over `ctas` CTAs with `nsub` (1 or 2) weight tiles per
+ * partition tile.  plan_out[5] = {units, ctas used, k tiles, partition tiles, slots};
+ * first_owner_out / contrib_out (optional, one entry per partition tile) = first contributing CTA
+ * and number of contributors of that tile (the slot a CTA writes is its index minus first_owner). */
+B200_API int b200_debug_w4a16_plan(int64_t N, int64_t K, int ctas, int nsub, int32_t* plan_out,
+                                   int32_t* first_owner_out, int32_t* contrib_out);
+
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
 B200_API void b200_debug_set_trace(void* device_buffer);

@@ -728,6 +728,27 @@ struct PlanKey {
 static std::mutex g_plan_mu;
 static std::vector<std::pair<PlanKey, W4Plan>> g_plans;
 
+// pure arithmetic (no device, no environment): the partition for `ctas` CTAs
+static W4Plan w4_make_plan(int64_t N, int64_t K, int nsub_log2, int ctas) {
+  W4Plan pl{};
+  pl.nsub_log2 = nsub_log2;
+  pl.KT = (int)(K / 128);
+  pl.NT = (int)(N / 128) >> nsub_log2;
+  pl.units = pl.KT * pl.NT;
+  const long long cap = (long long)(W4_MAX_SLOTS - 1) * pl.NT;
+  int Pc = ctas;
+  if (Pc > pl.units) Pc = pl.units;
+  if (Pc > cap) Pc = (int)cap;
+  if (Pc < 1) Pc = 1;
+  pl.P = Pc;
+  pl.slots = 1;
+  for (int nt = 0; nt < pl.NT; ++nt) {
+    const int c = w4_contrib(pl, nt);
+    if (c > pl.slots) pl.slots = c;
+  }
+  return pl;
+}
+
 W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
   int P = sm_count();
   const char* env = getenv("B200_W4A16_CTAS");
@@ -746,22 +767,7 @@ W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
       if (e.first.N == N && e.first.K == K && e.first.nsub_log2 == nsub_log2 && e.first.P == P)
         return e.second;
   }
-  W4Plan pl{};
-  pl.nsub_log2 = nsub_log2;
-  pl.KT = (int)(K / 128);
-  pl.NT = NT128 >> nsub_log2;
-  pl.units = pl.KT * pl.NT;
-  const long long cap = (long long)(W4_MAX_SLOTS - 1) * pl.NT;
-  int Pc = P;
-  if (Pc > pl.units) Pc = pl.units;
-  if (Pc > cap) Pc = (int)cap;
-  if (Pc < 1) Pc = 1;
-  pl.P = Pc;
-  pl.slots = 1;
-  for (int nt = 0; nt < pl.NT; ++nt) {
-    const int c = w4_contrib(pl, nt);
-    if (c > pl.slots) pl.slots = c;
-  }
+  const W4Plan pl = w4_make_plan(N, K, nsub_log2, P);
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     if (g_plans.size() > 256) g_plans.clear();
@@ -872,6 +878,24 @@ int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K, int64_t N, in
       static_cast<__nv_bfloat16*>(w_out), static_cast<const uint8_t*>(packed), K, N,
       w4_geff(group_size));
   B200_LAUNCH_OK("w4a16_dequant");
+  return B200_OK;
+}
+
+int b200_debug_w4a16_plan(int64_t N, int64_t K, int ctas, int nsub, int32_t* plan_out,
+                          int32_t* first_owner_out, int32_t* contrib_out) {
+  B200_CHECK_ARG(N > 0 && K > 0 && N % 128 == 0 && K % 128 == 0 && ctas >= 1 && (nsub == 1 || nsub == 2) &&
+                     (N / 128) % nsub == 0 && plan_out,
+                 "debug_w4a16_plan: bad arguments");
+  const W4Plan pl = w4_make_plan(N, K, nsub == 2 ? 1 : 0, ctas);
+  plan_out[0] = pl.units;
+  plan_out[1] = pl.P;
+  plan_out[2] = pl.KT;
+  plan_out[3] = pl.NT;
+  plan_out[4] = pl.slots;
+  for (int nt = 0; nt < pl.NT; ++nt) {
+    if (first_owner_out) first_owner_out[nt] = w4_first_owner(pl, nt);
+    if (contrib_out) contrib_out[nt] = w4_contrib(pl, nt);
+  }
   return B200_OK;
 }
 

@@ -91,3 +91,36 @@ def test_build_decode_batch_matches_per_token_loop():
     p0 = params.block_tables.data_ptr()
     _, _, params2 = bufs.upload(hb)
     assert params2.block_tables.data_ptr() == p0
+
+
+@pytest.mark.parametrize("K,N,ctas,nsub", [(4096, 4096, 148, 1), (4096, 6144, 148, 1), (4096, 28672, 148, 1),
+                                           (14336, 4096, 148, 1), (4096, 28672, 148, 2), (128, 128, 148, 1),
+                                           (512, 256, 148, 1), (512, 4096, 148, 1), (4096, 768, 148, 1),
+                                           (1792, 4096, 132, 1), (4096, 3584, 7, 1)])
+def test_w4a16_stream_k_partition_invariants(K, N, ctas, nsub):
+    """The stream-K partition shared by the GEMM and the kernels that sum its partials (host
+    arithmetic in libb200decode, no GPU needed): equal contiguous shares, every tile's contributors
+    are consecutive CTAs, slot ranks are 0..contrib-1, and no tile needs more than 8 slots."""
+    import ctypes as C
+    import numpy as np
+    from scalellm_b200 import _lib
+    lib = _lib.load()
+    NT = N // 128 // nsub
+    plan = (C.c_int32 * 5)()
+    first = (C.c_int32 * NT)()
+    contrib = (C.c_int32 * NT)()
+    rc = lib.b200_debug_w4a16_plan(N, K, ctas, nsub, plan, first, contrib)
+    assert rc == 0, lib.b200_last_error()
+    units, P, KT, NTp, slots = list(plan)
+    assert KT == K // 128 and NTp == NT and units == KT * NT
+    assert 1 <= P <= min(ctas, units) and 1 <= slots <= 8
+    begin = [(p * units) // P for p in range(P + 1)]
+    shares = np.diff(begin)
+    assert shares.min() >= 1 and shares.max() - shares.min() <= 1      # equal, non-empty shares
+    owner = np.repeat(np.arange(P), shares)                              # unit -> CTA
+    for nt in range(NT):
+        o = owner[nt * KT:(nt + 1) * KT]
+        assert first[nt] == o[0] and contrib[nt] == o[-1] - o[0] + 1
+        assert sorted(set(o.tolist())) == list(range(o[0], o[-1] + 1))   # consecutive CTAs, no holes
+        assert contrib[nt] <= slots
+    assert max(contrib) == slots
