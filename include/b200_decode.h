@@ -321,6 +321,13 @@ B200_API int b200_ar_allreduce(b200_ar_comm* comm, void* data, int64_t count,
 B200_API int b200_ar_allreduce_splitk(b200_ar_comm* comm, void* out, const float* partials,
                                       int splits, int64_t gemm_k, int64_t n, int64_t count,
                                       int dtype, b200_stream_t stream);
+/* ... and with the consumer fused as well: residual += T(all-reduced row); out = rms_norm(residual)
+ * * weight, one launch for the row-parallel GEMM's reduction, the TP all-reduce, the residual add
+ * and the RMSNorm (models/meta/llama.h:170-177 under tensor parallelism).  rows <= 64, n <= 4096. */
+B200_API int b200_ar_allreduce_splitk_norm(b200_ar_comm* comm, void* out, void* residual,
+                                           const float* partials, int splits, int64_t gemm_k,
+                                           const void* weight, int64_t rows, int64_t n, float eps,
+                                           int dtype, b200_stream_t stream);
 B200_API int b200_ar_destroy(b200_ar_comm* comm);
 
 #ifdef __cplusplus

@@ -79,14 +79,27 @@ __device__ __forceinline__ void accum16(float (&acc)[16 / sizeof(T)], uint4 v) {
 // partials != nullptr: the local input is the producing GEMM's stream-K partials [slots][count]
 // fp32 (row length row_n); the copy-in stage sums each tile's contributor slots (fixed order) and
 // rounds once to T — the GEMM epilogue's job.
+// NORM: grid = one block per row (row_n / VEC <= AR_THREADS vectors); the reduced row is not stored
+// but consumed in place: residual += T(sum over ranks); out = rms_norm(residual) * weight — the
+// o_proj / down_proj all-reduce, the residual add and the following RMSNorm in ONE launch,
+// bit-identical to the three separate kernels (same rounding points).
 template <typename T>
+struct ArNormArgs {
+  T* residual;
+  const T* weight;
+  T* out;
+  float eps;
+};
+
+template <typename T, bool NORM>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs ptrs, T* data,
                                                                       int64_t nvec, int rank,
                                                                       int world,
                                                                       int64_t max_bytes,
                                                                       const float* partials,
                                                                       W4Plan plan, int row_n,
-                                                                      int64_t split_stride) {
+                                                                      int64_t split_stride,
+                                                                      ArNormArgs<T> na) {
   constexpr int VEC = 16 / sizeof(T);
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
@@ -131,20 +144,65 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   }
   __syncthreads();
 
-  // 4. reduce in rank order, write back in place
-  for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
-    float acc[VEC];
+  // 4. reduce in rank order, write back in place (or feed the residual + RMSNorm epilogue)
+  if constexpr (!NORM) {
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
+      float acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-    for (int r = 0; r < world; ++r) {
-      const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
-      accum16<T>(acc, ld_volatile_v4(pb + i));
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      for (int r = 0; r < world; ++r) {
+        const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
+        accum16<T>(acc, ld_volatile_v4(pb + i));
+      }
+      uint4 o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) oe[k] = Num<T>::from_f(acc[k]);
+      reinterpret_cast<uint4*>(data)[i] = o;
     }
-    uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
+  } else {
+    __shared__ float red[32];
+    const int64_t i = v0 + threadIdx.x;  // one vector per thread: the block's slice is one row
+    const bool have = i < v1;
+    float x[VEC];
+    float ss = 0.f;
+    if (have) {
+      float acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) oe[k] = Num<T>::from_f(acc[k]);
-    reinterpret_cast<uint4*>(data)[i] = o;
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      for (int r = 0; r < world; ++r) {
+        const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
+        accum16<T>(acc, ld_volatile_v4(pb + i));
+      }
+      uint4 rraw = reinterpret_cast<const uint4*>(na.residual)[i];
+      const T* rr = reinterpret_cast<const T*>(&rraw);
+      uint4 sraw;
+      T* sv = reinterpret_cast<T*>(&sraw);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float reduced = rnd<T>(acc[k]);  // what the plain all-reduce would have stored
+        const float f = Num<T>::to_f(rr[k]) + reduced;
+        ss += f * f;
+        sv[k] = Num<T>::from_f(f);
+        x[k] = Num<T>::to_f(sv[k]);
+      }
+      reinterpret_cast<uint4*>(na.residual)[i] = sraw;
+    }
+    const float total = block_sum<AR_THREADS>(ss, red);
+    const float rstd = rsqrtf(total / row_n + na.eps);
+    if (have) {
+      const int col = (int)((i * VEC) % row_n);
+      uint4 wraw = *reinterpret_cast<const uint4*>(na.weight + col);
+      const T* w = reinterpret_cast<const T*>(&wraw);
+      uint4 oraw;
+      T* o = reinterpret_cast<T*>(&oraw);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float y = rnd<T>(x[k] * rstd);
+        o[k] = Num<T>::from_f(y * Num<T>::to_f(w[k]));
+      }
+      reinterpret_cast<uint4*>(na.out)[i] = oraw;
+    }
   }
 
   // advance the epoch once every block is done with it
@@ -255,21 +313,65 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
   auto st = static_cast<cudaStream_t>(stream);
   switch (dtype) {
     case B200_BF16:
-      allreduce_oneshot_kernel<__nv_bfloat16><<<blocks, AR_THREADS, 0, st>>>(
+      allreduce_oneshot_kernel<__nv_bfloat16, false><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<__nv_bfloat16*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
-          plan, (int)row_n, count);
+          plan, (int)row_n, count, ArNormArgs<__nv_bfloat16>{});
       break;
     case B200_FP16:
-      allreduce_oneshot_kernel<__half><<<blocks, AR_THREADS, 0, st>>>(
+      allreduce_oneshot_kernel<__half, false><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<__half*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
-          plan, (int)row_n, count);
+          plan, (int)row_n, count, ArNormArgs<__half>{});
       break;
     default:
-      allreduce_oneshot_kernel<float><<<blocks, AR_THREADS, 0, st>>>(
-          ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes, nullptr, W4Plan{}, 0, 0);
+      allreduce_oneshot_kernel<float, false><<<blocks, AR_THREADS, 0, st>>>(
+          ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes, nullptr, W4Plan{}, 0, 0,
+          ArNormArgs<float>{});
       break;
   }
   B200_LAUNCH_OK("allreduce_oneshot");
+  return B200_OK;
+}
+
+int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, const float* partials,
+                                  int splits, int64_t gemm_k, const void* weight, int64_t rows,
+                                  int64_t n, float eps, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(c && out && residual && partials && weight, "ar_allreduce_splitk_norm: null pointer");
+  B200_CHECK_ARG(c->world > 1 && c->opened, "ar_allreduce_splitk_norm: needs an opened communicator, world > 1");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "ar_allreduce_splitk_norm: bf16 / fp16 only");
+  B200_CHECK_ARG(rows >= 1 && rows <= AR_MAX_BLOCKS && n > 0 && n % 128 == 0 && n / 8 <= AR_THREADS &&
+                     gemm_k > 0 && gemm_k % 128 == 0,
+                 "ar_allreduce_splitk_norm: rows <= %d, n %% 128 == 0, n <= %d", AR_MAX_BLOCKS,
+                 AR_THREADS * 8);
+  B200_CHECK_ARG(is_aligned(out, 16) && is_aligned(residual, 16) && is_aligned(weight, 16) &&
+                     is_aligned(partials, 16),
+                 "ar_allreduce_splitk_norm: 16-byte alignment required");
+  const int64_t count = rows * n, bytes = count * 2;
+  if (bytes > c->max_bytes)
+    return set_error(B200_ERR_WORKSPACE, "ar_allreduce_splitk_norm: %lld B exceeds the %lld B symmetric buffer",
+                     (long long)bytes, (long long)c->max_bytes);
+  const W4Plan plan = w4_get_plan(n, gemm_k, rows);
+  B200_CHECK_ARG(splits == plan.slots, "ar_allreduce_splitk_norm: expected %d partial slots, got %d",
+                 plan.slots, splits);
+  ArDevPtrs ptrs{};
+  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t nvec = count / 8;
+  const int blocks = (int)rows;  // one block per row: slice = ceil(nvec / blocks) = n / 8 vectors
+  if (dtype == B200_BF16) {
+    ArNormArgs<__nv_bfloat16> na{static_cast<__nv_bfloat16*>(residual),
+                                 static_cast<const __nv_bfloat16*>(weight),
+                                 static_cast<__nv_bfloat16*>(out), eps};
+    allreduce_oneshot_kernel<__nv_bfloat16, true><<<blocks, AR_THREADS, 0, st>>>(
+        ptrs, static_cast<__nv_bfloat16*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials,
+        plan, (int)n, count, na);
+  } else {
+    ArNormArgs<__half> na{static_cast<__half*>(residual), static_cast<const __half*>(weight),
+                          static_cast<__half*>(out), eps};
+    allreduce_oneshot_kernel<__half, true><<<blocks, AR_THREADS, 0, st>>>(
+        ptrs, static_cast<__half*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials, plan,
+        (int)n, count, na);
+  }
+  B200_LAUNCH_OK("allreduce_oneshot_norm");
   return B200_OK;
 }
 

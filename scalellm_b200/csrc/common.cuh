@@ -150,6 +150,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// sum over the THREADS threads of the CTA (red: 32 floats of shared memory); every thread gets it
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  constexpr int NW = THREADS / 32;
+  float t = (lane < NW) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
 
 // 128-bit streaming global access
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {

@@ -19,18 +19,6 @@ namespace b200 {
 // ===========================================================================
 // RMSNorm
 // ===========================================================================
-template <int THREADS>
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  constexpr int NW = THREADS / 32;
-  float t = (lane < NW) ? red[lane] : 0.f;
-  t = warp_sum(t);
-  return t;  // every thread holds the total
-}
-
 // Vector path: n % VEC == 0, one CTA per row, each thread owns up to MAXV
 // 16-byte vectors of the row in registers (row read once).
 template <typename T, int THREADS, int MAXV, bool RESIDUAL>

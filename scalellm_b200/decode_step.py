@@ -187,7 +187,7 @@ class LlamaDecoder:
 
         def norm_residual(norm, pend, is_partials):
             if is_partials:
-                return norm.forward_residual_partials(pend, h)
+                return norm.forward_residual_partials(pend, h, self.pa)
             return norm.forward_residual(pend, h)
 
         for L, cache in zip(self.layers, self.kv_caches):

@@ -18,6 +18,8 @@ import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -255,9 +257,13 @@ class RMSNorm:
         kernels.rms_norm_residual(out, residual, x, self.weight, self.eps)
         return out
 
-    def forward_residual_partials(self, partials, residual: torch.Tensor) -> torch.Tensor:
+    def forward_residual_partials(self, partials, residual: torch.Tensor, pa=None) -> torch.Tensor:
         """Same, with x delivered as the producing GEMM's stream-K partials (kernels.W4Partials):
-        the cross-CTA reduction of the GEMM is fused into this kernel."""
+        the cross-CTA reduction of the GEMM is fused into this kernel.  With a tensor-parallel
+        group (pa.world_size > 1) the partials are this rank's share and the TP all-reduce is
+        fused in as well."""
+        if pa is not None and pa.world_size > 1:
+            return pa.process_group.allreduce_partials_norm(partials, residual, self.weight, self.eps)
         out = torch.empty_like(residual)
         kernels.rms_norm_residual_splitk(out, residual, partials, self.weight, self.eps)
         return out
@@ -408,9 +414,15 @@ class RowParallelQLinear(_QLinearBase):
         self._set_shard(qw, qz, sc, sd.get("bias"))
 
     def supports_partials(self, n_rows: int) -> bool:
-        """Partials output (the GEMM's cross-CTA reduction fused into the consumer norm) — single
-        rank, no bias."""
-        return self.pa.world_size == 1 and self.bias is None and 0 < n_rows <= 128
+        """Partials output (the GEMM's cross-CTA reduction fused into the consumer norm; under TP
+        the all-reduce is fused into the same kernel) — no bias."""
+        if self.bias is not None or not 0 < n_rows <= 128:
+            return False
+        if self.pa.world_size == 1:
+            return True
+        pg = self.pa.process_group
+        return (os.environ.get("B200_FUSE_AR_NORM", "1") != "0" and hasattr(pg, "supports_partials_norm")
+                and pg.supports_partials_norm(n_rows, self.N, torch.bfloat16))
 
     def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
         self._ensure_packed()

@@ -100,6 +100,24 @@ class ProcessGroup:
         self.allreduce(out)
         return out
 
+    def supports_partials_norm(self, rows: int, n: int, dtype: torch.dtype) -> bool:
+        return (self._comm is not None and 0 < rows <= 64 and n % 128 == 0 and n <= 4096
+                and rows * n * 2 <= self._nvlink_max_bytes
+                and dtype in (torch.bfloat16, torch.float16))
+
+    def allreduce_partials_norm(self, partials, residual: torch.Tensor, weight: torch.Tensor,
+                                eps: float) -> torch.Tensor:
+        """residual += allreduce(partials); returns rms_norm(residual) * weight — the row-parallel
+        GEMM's reduction, the all-reduce, the residual add and the RMSNorm in one launch."""
+        data = partials.data
+        S, rows, n = data.shape
+        out = torch.empty_like(residual)
+        dt = 0 if residual.dtype == torch.bfloat16 else 1
+        check(_lib.load().b200_ar_allreduce_splitk_norm(
+            self._comm, out.data_ptr(), residual.data_ptr(), data.data_ptr(), S, partials.K,
+            weight.data_ptr(), rows, n, eps, dt, torch.cuda.current_stream().cuda_stream))
+        return out
+
     def allgather(self, input: torch.Tensor, outputs: List[torch.Tensor]) -> None:
         if self._world == 1:
             outputs[0].copy_(input)

@@ -69,6 +69,18 @@ def _worker(rank, world, port):
         torch.cuda.synchronize()
         assert torch.isfinite(got.float()).all()
         assert torch.equal(got, want)
+        # ... and with the residual add + RMSNorm fused in as well (one launch instead of three)
+        gen = torch.Generator().manual_seed(99)               # residual stream: replicated on all ranks
+        res = torch.randn(M, N, generator=gen).bfloat16().to(dev)
+        wn = (1 + 0.1 * torch.randn(N, generator=gen)).bfloat16().to(dev)
+        assert pg.supports_partials_norm(M, N, torch.bfloat16)
+        r_ref, out_ref = res.clone(), torch.empty_like(res)
+        kernels.rms_norm_residual(out_ref, r_ref, want, wn, 1e-5)
+        for _ in range(2):                                     # twice: epochs / double buffering
+            r_fused = res.clone()
+            out_fused = pg.allreduce_partials_norm(parts, r_fused, wn, 1e-5)
+        torch.cuda.synchronize()
+        assert torch.equal(r_fused, r_ref) and torch.equal(out_fused, out_ref)
         # larger than the symmetric buffer -> NCCL path, still correct
         big = torch.ones(2 << 20, device=dev)
         pg.allreduce(big)
