@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                 "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -163,10 +163,14 @@ class CpuDecodeSample:
         best, best_t = None, n
         for t in sorted({n, min(n, 32), min(n, 16), min(n, 8)}, reverse=True):
             self.torch.set_num_threads(t)
-            v, _ = self.step(1)
+            v, secs = self.step(1)
             if best is None or v > best:
-                best, best_t = v, t
+                best, best_t, self.layer_secs = v, t, secs
         self.torch.set_num_threads(best_t)
+
+    def layers_for(self, budget_s: float) -> int:
+        """How many (identical) decoder layers fit a CPU-time budget, between 2 and 32."""
+        return int(max(2, min(32, budget_s / max(self.layer_secs, 1e-3))))
 
     def step(self, n_layers_sample: int):
         """Returns (tokens_per_s extrapolated to 32 layers, seconds spent)."""
@@ -184,10 +188,11 @@ class CpuDecodeSample:
         return self.B / step_s, t_layers + t_head
 
 
-def cpu_decode_sample(a, n_layers_sample: int, seed: int = 0):
+def cpu_decode_sample(a, budget_s: float = 15.0, seed: int = 0):
     c = CpuDecodeSample(a, seed)
-    v, secs = c.step(n_layers_sample)
-    return v, secs, c.torch.get_num_threads()
+    n_layers = c.layers_for(budget_s)
+    v, secs = c.step(n_layers)
+    return v, secs, c.torch.get_num_threads(), n_layers, c.B
 
 
 def run_reference(a, rank):
@@ -350,10 +355,11 @@ def run_b200(a, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline:
-        v, secs, cores = cpu_decode_sample(a, n_layers_sample=2)
+        v, secs, cores, n_layers, n_seq = cpu_decode_sample(a)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{min(a.batch, CpuDecodeSample.SAMPLE_BATCH)} of the {a.batch} sequences through 2 of 32 oracle decoder layers + lm_head at the full kv_len ({secs:.1f} s of CPU "
-                         "work), extrapolated to 32 layers"}
+               "sample": f"{n_seq} of the {a.batch} sequences through {n_layers} oracle decoder layers + "
+                         f"lm_head at the full kv_len ({secs:.1f} s of CPU work on {cores} threads, the "
+                         "fastest of the thread counts tried), time extrapolated to 32 layers"}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -392,9 +398,11 @@ def _peaks():
 
 
 def _traffic(name):
+    """DRAM read+write bytes per launch of the kernel, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py); None if no capture is committed."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(name)
+        return float(json.load(open(p))[name]["dram_bytes_per_launch"])
     except Exception:
         return None
 
