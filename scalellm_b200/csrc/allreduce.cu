@@ -18,6 +18,14 @@
 // reading it in call e (they must have entered call e+1 first).  The epoch lives
 // in device memory and is advanced by the kernel, so a captured CUDA graph can
 // be replayed (no host-side state baked into kernel arguments).
+//
+// Fused forms (the row-parallel GEMM -> all-reduce -> residual add -> RMSNorm chain of a TP
+// decoder layer, models/meta/llama.h:170-177):
+//   * b200_ar_allreduce_splitk: step 1 reads the producing W4A16 GEMM's fp32 stream-K partials
+//     and sums each tile's contributor slots (common.cuh W4Plan) instead of copying a bf16 input;
+//   * b200_ar_allreduce_splitk_norm: additionally, one block per row, step 4 feeds the reduced row
+//     straight into residual += x; out = rms_norm(residual) * w — one launch for the whole chain,
+//     bit-identical to the separate kernels (same rounding points).
 
 #include <cstring>
 

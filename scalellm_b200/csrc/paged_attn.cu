@@ -1,16 +1,28 @@
 // paged_attn.cu — paged-KV decode attention for sm_100a.
 //
-// Replaces llm::paged_kv_varlen_mha (src/kernels/attention/attn_api.cpp:14-73)
-// for decode-shaped batches.  HBM-bound (AI = group size FLOP/B), so no tensor
-// cores: KV blocks are staged into shared memory with TMA (one 3-D tensor map
-// over the [n_slots, n_kv_heads, head_dim] cache, box = min(block_size,16) slots
-// of one kv head), each warp owns a private ring of TMA stages + mbarriers so
-// there is no CTA-wide synchronisation in the main loop, dot products and the
-// online softmax (exp2 domain) use warp shuffles, and the KV range is split
-// across CTAs (split-KV) with a second-pass LSE combine.
+// Replaces llm::paged_kv_varlen_mha (src/kernels/attention/attn_api.cpp:14-73) for
+// decode-shaped batches (q_len * group <= a few 16-row blocks).  HBM-bound: AI = group size
+// FLOP/B, so tcgen05 (M >= 64 tiles) would be >= 94 % padding — the design goal is to keep
+// ~100 KB of KV per SM in flight and stream every byte exactly once.
 //
-// Work item = (split, kv head x head-group, sequence x query token).  Slot
-// lookup is the reference's: block_table[block_cu_lens[b] + (pos >> log2 bs)]
+// Three kernels share the host side, the parameter block and the parity tests; B200_ATTN_IMPL
+// selects ("stream" is the default, the other two are the bring-up / fallback paths):
+//   * paged_attn_persist_kernel ("stream", default): one warp per CTA, 7 CTAs per SM.  The work
+//     is the padded tile stream — the concatenation over (sequence, 16-row block of packed
+//     (q token, head-in-group) rows, kv head) of ntm 16-slot KV tiles — cut into equal contiguous
+//     shares, one per warp (stream-K for attention: no atomics, no wave tail).  KV tiles arrive by
+//     TMA through a 4-D tensor map {64, D/64, n_kv_heads, n_slots} with SWIZZLE_128B into a
+//     per-warp 3-stage ring that runs continuously across the pieces of a share; S = Q K^T and
+//     O += P V use mma.sync.m16n8k16 (P rounded to the element type first, like the reference);
+//     the metadata of following pieces (lengths -> ranges -> block-table window by cp.async) is
+//     software-pipelined off the critical path.  A piece writes an fp32 partial O + LSE.
+//   * paged_attn_mma_kernel ("mma"): the same math with one CTA per (split, row block x kv head,
+//     sequence) work item and a fixed split count.
+//   * paged_attn_decode_kernel ("simt"): CUDA cores only (3-D tensor map, warp-shuffle dot
+//     products and online softmax); covers every dtype (incl. fp32) and head_dim.
+//   paged_attn_combine_kernel merges the split partials (LSE-weighted, fixed order).
+//
+// Slot lookup is the reference's: block_table[block_cu_lens[b] + (pos >> log2 bs)]
 // + (pos & (bs-1)), where block_table holds first-slot ids
 // (src/kernels/attention/kernel/sm80_kernel_mha.cuh:148-152).
 // Mask semantics follow src/kernels/attention/common/mask.h:51-86:

@@ -245,11 +245,6 @@ struct W4Cfg {
   static constexpr int ACC_COLS = ACC_BUFS * NSUB * MT;
   static constexpr int A_COL0 = ACC_COLS < 128 ? 128 : ACC_COLS;
   static constexpr int A_STAGES = (512 - A_COL0) / 64;  // dequantised-weight slots in TMEM: 6 or 4
-  // Release granularity of slots / activation stages (tiles per tcgen05.commit).  A commit costs
-  // the issuing thread ~170 cycles (tools/microbench/mix.cu), but releasing in pairs measured
-  // slower end to end (the dequant warps wait longer for slots), so it stays 1.
-  static constexpr int PAIR = 1;
-  static constexpr int ACT_PAIR = 1;
   static constexpr int ACT_ATOM = MT * 128;       // bytes of one [MT x 64] bf16 swizzle atom
   static constexpr int ACT_BYTES = 2 * ACT_ATOM;  // 128 k per stage
   static constexpr int RAW_BYTES = W4_MAX_BLOB;   // 9728 = 76 * 128
@@ -429,7 +424,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
             tw = TRACE ? clock64() : 0;
-            mbar_wait(&deq_empty[as / Cfg::PAIR], aph ^ 1);
+            mbar_wait(&deq_empty[as], aph ^ 1);
             if (TRACE) w_slot += clock64() - tw;
             tc_fence_after();
           }
@@ -482,7 +477,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          mbar_wait(&act_empty[as / Cfg::ACT_PAIR], aph ^ 1);
+          mbar_wait(&act_empty[as], aph ^ 1);
           mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
@@ -497,11 +492,13 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     // issues the UMMAs.  This one thread paces the kernel: it shares its scheduler with four
     // dequant warps, and every tcgen05.commit / barrier wait costs it ~170 cycles
     // (tools/microbench/mix.cu), so a weight tile takes ~600 cycles here against 256 of MMA time.
+    // Tried and measured no better: releasing slots in pairs (one commit per two
+    // tiles), two issuing warps with separate accumulators, loop bodies specialised on the ring
+    // position.
     constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
     SegIter it{u_begin, u_end, KT};
-    const int n_tiles = (u_end - u_begin) * NSUB;
     int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
     long long w_act = 0, w_deq = 0, w_acc = 0;  // TRACE: cycles spent waiting per barrier kind
     while (it.next(nt, kt0, kt1)) {
@@ -530,9 +527,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           if (TRACE) w_deq += clock64() - tw;
           if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
           tc_fence_after();
-          // end of a ring pair (or of this CTA's work): release both slots / both stages
-          const bool pair_end = Cfg::PAIR == 1 || (cnt & 1) == 1 || cnt == n_tiles - 1;
-          const bool unit_end = sub == NSUB - 1;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -541,11 +535,11 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
                   b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
               umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
             }
-            if (pair_end) {
-              umma_commit(&deq_empty[ds / Cfg::PAIR]);
-              if (unit_end) umma_commit(&act_empty[as / Cfg::ACT_PAIR]);
+            umma_commit(&deq_empty[ds]);
+            if (sub == NSUB - 1) {
+              umma_commit(&act_empty[as]);
+              if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
             }
-            if (unit_end && kt == kt1 - 1) umma_commit(&tmem_full[buf]);
           }
           __syncwarp();
         }
