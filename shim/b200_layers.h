@@ -1,0 +1,242 @@
+// b200_layers.h — C++ host side of the decode step above the C ABI: the reference's plugin-level
+// interfaces (same names, members and call order) implemented over libb200decode, plus the Llama
+// decoder wiring that uses the fused paths.
+//
+//   InputParameters                      src/models/parameters.h:11-56
+//   KVCache                              src/memory/kv_cache.h / kv_cache.cpp:15-98
+//   AttentionHandler (+ B200Handler)     src/layers/attention/handler.h:15-65
+//   ParallelLinearImpl (+ QLinearB200Impl)  src/layers/linear/parallel_linear.h:17-40,
+//                                        src/layers/quantization/qlinear_awq_marlin_impl.cpp:129-365
+//   RMSNormImpl                          src/layers/normalization.h:114-139
+//   LlamaDecoderStep                     src/models/meta/llama.h:61-64,123-133,170-177,220-232,281-289
+//
+// Inside ScaleLLM these classes derive from the engine's own headers; here the
+// interfaces are restated so that the library is self-contained and testable.  One tensor-parallel
+// rank (world_size 1); the TP plumbing lives in scalellm_b200/model_parallel.py this round.
+#pragma once
+
+#include <torch/torch.h>
+
+#include <memory>
+#include <optional>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+namespace llm {
+
+// ---------------------------------------------------------------------------------------------
+// fused operator-level entry points that have no counterpart in the reference's kernel API
+// ---------------------------------------------------------------------------------------------
+// fp32 stream-K partials of a W4A16 GEMM (include/b200_decode.h "partials mode"); K = the GEMM's
+// reduction dimension (a consumer recomputes the tile -> slot partition from (N, K, rows)).
+struct W4Partials {
+  torch::Tensor data;  // [slots, rows, N] fp32
+  int64_t K = 0;
+};
+
+namespace kernel {
+W4Partials w4a16_gemm_partials(const torch::Tensor& a, const torch::Tensor& packed, int64_t N,
+                               int64_t group_size);
+torch::Tensor w4a16_reduce_partials(const W4Partials& p, const std::optional<torch::Tensor>& bias);
+// residual += T(sum partials); returns rms_norm(residual) * weight
+torch::Tensor rms_norm_residual_partials(const W4Partials& p, torch::Tensor& residual,
+                                         const torch::Tensor& weight, float eps);
+// qkv partials -> qkv [T, (H + 2 Hkv) D] (q, k rotated), rotated k and v written to their slots
+torch::Tensor rope_and_set_kv_cache_partials(const W4Partials& p, int64_t n_heads,
+                                             int64_t n_kv_heads, int64_t head_dim,
+                                             const torch::Tensor& positions,
+                                             const torch::Tensor& cos_sin,
+                                             const torch::Tensor& slot_ids, torch::Tensor& key_cache,
+                                             torch::Tensor& value_cache, int rotary_dim,
+                                             bool interleaved, torch::ScalarType dtype);
+// gate_up partials [slots, rows, 2 I] -> silu(gate) * up [rows, I]
+torch::Tensor silu_mul_partials(const W4Partials& p, torch::ScalarType dtype);
+torch::Tensor argmax(const torch::Tensor& logits);
+}  // namespace kernel
+
+// ---------------------------------------------------------------------------------------------
+// step metadata and KV cache
+// ---------------------------------------------------------------------------------------------
+struct InputParameters {
+  int32_t num_sequences = 0;
+  torch::Tensor q_cu_seq_lens;    // int32 [n_seq + 1]
+  torch::Tensor kv_cu_seq_lens;   // int32 [n_seq + 1]
+  int32_t kv_max_seq_len = 0;
+  int32_t q_max_seq_len = 0;
+  torch::Tensor new_cache_slots;  // int32 [n_tokens]
+  torch::Tensor block_tables;     // int32 [n_blocks]: first-slot ids (engine/batch.cpp:206-209)
+  torch::Tensor cu_block_lens;    // int32 [n_seq + 1]
+};
+
+class KVCache {
+ public:
+  KVCache() = default;
+  KVCache(torch::Tensor key_cache, torch::Tensor value_cache, int64_t block_size)
+      : key_cache_(std::move(key_cache)), value_cache_(std::move(value_cache)),
+        block_size_(block_size) {}
+  bool empty() const { return !key_cache_.defined() || key_cache_.numel() == 0; }
+  int64_t block_size() const { return block_size_; }
+  std::tuple<torch::Tensor, torch::Tensor> get_kv_cache() const { return {key_cache_, value_cache_}; }
+  void set_kv_cache(const torch::Tensor& slot_ids, const torch::Tensor& keys,
+                    const torch::Tensor& values);
+
+ private:
+  torch::Tensor key_cache_, value_cache_;  // [n_slots, n_kv_heads, head_dim]
+  int64_t block_size_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------------------------
+class AttentionHandler {
+ public:
+  virtual ~AttentionHandler() = default;
+  virtual int64_t get_estimate_workspace_size() { return -1; }
+  virtual void set_workspace(const torch::Tensor& /*workspace*/) {}
+  virtual std::tuple<torch::Tensor, torch::Tensor> apply_pos_emb(const torch::Tensor& query,
+                                                                 const torch::Tensor& key,
+                                                                 const torch::Tensor& positions) = 0;
+  virtual void batch_decode(const torch::Tensor& query, const KVCache& kv_cache,
+                            const InputParameters& input_params, int32_t sliding_window,
+                            torch::Tensor& output) = 0;
+  virtual void append_kv_cache(KVCache& kv_cache, const torch::Tensor& key,
+                               const torch::Tensor& value, const InputParameters& input_params) = 0;
+};
+
+class B200Handler final : public AttentionHandler {
+ public:
+  // cos_sin: [max_position, rotary_dim] in the model dtype (pos_embedding.cpp:183-215)
+  B200Handler(float sm_scale, float logits_soft_cap, std::optional<torch::Tensor> alibi_slopes,
+              torch::Tensor cos_sin, int64_t rotary_dim, bool interleaved);
+
+  std::tuple<torch::Tensor, torch::Tensor> apply_pos_emb(const torch::Tensor& query,
+                                                         const torch::Tensor& key,
+                                                         const torch::Tensor& positions) override;
+  void batch_decode(const torch::Tensor& query, const KVCache& kv_cache,
+                    const InputParameters& input_params, int32_t sliding_window,
+                    torch::Tensor& output) override;
+  void append_kv_cache(KVCache& kv_cache, const torch::Tensor& key, const torch::Tensor& value,
+                       const InputParameters& input_params) override;
+
+  // B200 extensions: RoPE + KV-slot write in one launch; the same fed by the qkv GEMM's partials
+  void apply_pos_emb_and_append(torch::Tensor& query, torch::Tensor& key, const torch::Tensor& value,
+                                const torch::Tensor& positions, KVCache& kv_cache,
+                                const InputParameters& input_params);
+  torch::Tensor qkv_from_partials(const W4Partials& qkv, int64_t n_heads, int64_t n_kv_heads,
+                                  int64_t head_dim, const torch::Tensor& positions,
+                                  KVCache& kv_cache, const InputParameters& input_params,
+                                  torch::ScalarType dtype);
+  bool has_rope() const { return cos_sin_.defined(); }
+
+ private:
+  float sm_scale_, soft_cap_;
+  std::optional<torch::Tensor> alibi_;
+  torch::Tensor cos_sin_;
+  int64_t rotary_dim_;
+  bool interleaved_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// linear / norm layers
+// ---------------------------------------------------------------------------------------------
+struct QuantArgs {  // quant_args.h:10-33
+  std::string quant_method;  // "awq" | "gptq"
+  int64_t bits = 4;
+  int64_t group_size = 128;
+  bool desc_act = false;
+  bool is_sym = false;
+};
+
+using StateDict = std::unordered_map<std::string, torch::Tensor>;
+
+class ParallelLinearImpl {
+ public:
+  virtual ~ParallelLinearImpl() = default;
+  virtual torch::Tensor forward(torch::Tensor input) = 0;
+  virtual void load_state_dict(const StateDict& state_dict) = 0;
+  virtual void verify_loaded_weights() const = 0;
+};
+
+// int4 linear of one rank: checkpoint tensors in, lazy repack on first use
+// (qlinear_awq_marlin_impl.cpp:99-125,232-235), forward through the W4A16 GEMM.
+class QLinearB200Impl final : public ParallelLinearImpl {
+ public:
+  QLinearB200Impl(int64_t in_features, int64_t out_features, bool bias, const QuantArgs& quant_args,
+                  const torch::TensorOptions& options);
+  torch::Tensor forward(torch::Tensor input) override;
+  void load_state_dict(const StateDict& state_dict) override;  // qweight, qzeros (awq), scales, [bias]
+  void verify_loaded_weights() const override;
+
+  bool supports_partials(int64_t n_rows) const { return !bias_.defined() && n_rows > 0 && n_rows <= 128; }
+  W4Partials forward_partials(const torch::Tensor& input);
+  int64_t in_features() const { return K_; }
+  int64_t out_features() const { return N_; }
+
+ private:
+  void ensure_packed();
+  int64_t K_, N_;
+  QuantArgs qa_;
+  torch::TensorOptions options_;
+  bool has_bias_;
+  torch::Tensor qweight_, qzeros_, scales_, bias_, packed_, workspace_;
+};
+
+class RMSNormImpl {
+ public:
+  RMSNormImpl(int64_t dim, float eps, const torch::TensorOptions& options);
+  torch::Tensor forward(const torch::Tensor& input);
+  torch::Tensor forward_residual(const torch::Tensor& input, torch::Tensor& residual);
+  torch::Tensor forward_residual_partials(const W4Partials& input, torch::Tensor& residual);
+  void load_state_dict(const StateDict& state_dict);
+  torch::Tensor weight;
+
+ private:
+  float eps_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the decode step
+// ---------------------------------------------------------------------------------------------
+struct LlamaArgs {
+  int64_t hidden_size = 4096, n_layers = 32, n_heads = 32, n_kv_heads = 8, head_dim = 128;
+  int64_t intermediate_size = 14336, vocab_size = 128256, max_position_embeddings = 8192;
+  float rms_norm_eps = 1e-5f;
+};
+
+class LlamaDecoderStep {
+ public:
+  // inv_freq: [head_dim / 2] fp32 (after any rope scaling, pos_embedding.cpp:75-109)
+  LlamaDecoderStep(const LlamaArgs& args, const QuantArgs& quant_args, const torch::Tensor& inv_freq,
+                   const torch::TensorOptions& options);
+
+  // name -> tensor: "layers.<i>.{qkv,o,gate_up,down}.{qweight,qzeros,scales}",
+  // "layers.<i>.{input_norm,post_norm}.weight", "embed.weight", "final_norm.weight", "lm_head.weight"
+  void load_state_dict(const StateDict& state_dict);
+  void set_kv_caches(std::vector<KVCache> kv_caches) { kv_caches_ = std::move(kv_caches); }
+
+  // logits [n_tokens, vocab]
+  torch::Tensor forward(const torch::Tensor& tokens, const torch::Tensor& positions,
+                        const InputParameters& params);
+  // greedy next tokens [n_tokens] int64
+  torch::Tensor step(const torch::Tensor& tokens, const torch::Tensor& positions,
+                     const InputParameters& params);
+
+  bool fuse_partials = true;  // GEMM reductions fused into their consumers (B200_FUSE_SPLITK)
+
+ private:
+  struct Layer {
+    std::unique_ptr<RMSNormImpl> input_norm, post_norm;
+    std::unique_ptr<QLinearB200Impl> qkv, o, gate_up, down;
+  };
+  LlamaArgs args_;
+  torch::TensorOptions options_;
+  std::vector<Layer> layers_;
+  std::unique_ptr<RMSNormImpl> final_norm_;
+  std::unique_ptr<B200Handler> handler_;
+  torch::Tensor embed_, lm_head_;  // [vocab, h] each
+  std::vector<KVCache> kv_caches_;
+};
+
+}  // namespace llm

@@ -3,6 +3,7 @@
 #include <torch/extension.h>
 
 #include "b200_kernels.h"
+#include "b200_layers.h"
 
 PYBIND11_MODULE(_b200_shim, m) {
   m.def("rms_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w, double eps) {
@@ -41,4 +42,55 @@ PYBIND11_MODULE(_b200_shim, m) {
   });
   m.def("packed_bytes", &marlin::b200_packed_bytes);
   m.def("workspace_bytes", &marlin::b200_workspace_bytes);
+
+  // ---- plugin-level host side (shim/b200_layers.h) -------------------------------------------
+  namespace py = pybind11;
+  py::class_<llm::LlamaDecoderStep>(m, "LlamaDecoderStep")
+      .def(py::init([](int64_t hidden, int64_t n_layers, int64_t n_heads, int64_t n_kv_heads,
+                       int64_t head_dim, int64_t inter, int64_t vocab, int64_t max_pos, double eps,
+                       std::string quant_method, int64_t group_size, bool is_sym,
+                       torch::Tensor inv_freq, torch::Tensor like) {
+        llm::LlamaArgs a;
+        a.hidden_size = hidden;
+        a.n_layers = n_layers;
+        a.n_heads = n_heads;
+        a.n_kv_heads = n_kv_heads;
+        a.head_dim = head_dim;
+        a.intermediate_size = inter;
+        a.vocab_size = vocab;
+        a.max_position_embeddings = max_pos;
+        a.rms_norm_eps = static_cast<float>(eps);
+        llm::QuantArgs q;
+        q.quant_method = std::move(quant_method);
+        q.group_size = group_size;
+        q.is_sym = is_sym;
+        return std::make_unique<llm::LlamaDecoderStep>(a, q, inv_freq, like.options());
+      }))
+      .def("load_state_dict",
+           [](llm::LlamaDecoderStep& self, const std::unordered_map<std::string, torch::Tensor>& sd) {
+             self.load_state_dict(sd);
+           })
+      .def("set_kv_caches",
+           [](llm::LlamaDecoderStep& self, const std::vector<torch::Tensor>& k,
+              const std::vector<torch::Tensor>& v, int64_t block_size) {
+             std::vector<llm::KVCache> caches;
+             for (size_t i = 0; i < k.size(); ++i) caches.emplace_back(k[i], v[i], block_size);
+             self.set_kv_caches(std::move(caches));
+           })
+      .def_readwrite("fuse_partials", &llm::LlamaDecoderStep::fuse_partials)
+      .def("forward",
+           [](llm::LlamaDecoderStep& self, torch::Tensor tokens, torch::Tensor positions,
+              torch::Tensor q_cu, torch::Tensor kv_cu, int kv_max, int q_max, torch::Tensor slots,
+              torch::Tensor tables, torch::Tensor blk_cu) {
+             llm::InputParameters p;
+             p.num_sequences = static_cast<int32_t>(q_cu.size(0) - 1);
+             p.q_cu_seq_lens = q_cu;
+             p.kv_cu_seq_lens = kv_cu;
+             p.kv_max_seq_len = kv_max;
+             p.q_max_seq_len = q_max;
+             p.new_cache_slots = slots;
+             p.block_tables = tables;
+             p.cu_block_lens = blk_cu;
+             return self.forward(tokens, positions, p);
+           });
 }
