@@ -4,11 +4,9 @@ step, exposed through the _b200_shim pybind module.
 
 CPU: the module builds, the classes construct, load a state dict and enforce the reference's
 argument checks (qlinear_awq_marlin_impl.cpp:28-31,150-151).
-GPU: the C++ decode step must produce bit-identical logits to the Python mirror
-(scalellm_b200/decode_step.py) on the same weights, with and without the fused GEMM-partials
-consumers.  That test was written after the round's GPU budget was spent, so it only runs with
-B200_TEST_CPP_HOST=1 until it has been validated on a B200 once."""
-import os
+GPU: the C++ decode step must produce bit-identical logits (and KV-cache contents) to the Python
+mirror (scalellm_b200/decode_step.py) on the same weights, with and without the fused
+GEMM-partials consumers."""
 
 import numpy as np
 import pytest
@@ -80,8 +78,6 @@ def test_cpp_host_constructs_loads_and_checks_arguments():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B200_TEST_CPP_HOST") != "1",
-                    reason="not yet validated on a B200 (set B200_TEST_CPP_HOST=1)")
 @pytest.mark.parametrize("fuse", [True, False])
 def test_cpp_decode_step_matches_python_mirror(fuse):
     from scalellm_b200.decode_step import (BlockPool, LlamaArgs, LlamaDecoder, StepBuffers,
