@@ -40,6 +40,9 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--ttft", action="store_true",
+                    help="also measure unloaded p50 time-to-first-token (chunked prefill through "
+                         "the decode kernels; experimental, off by default)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
@@ -353,6 +356,13 @@ def run_b200(a, rank, world, local_rank):
         clocks = ClockSampler.summarise(sampler.window(t_w0, t_w1))
         sampler.stop()
 
+    ttft = "not measured: prefill kernels are SURVEY §8f rank 1 (next)"
+    if a.ttft and world == 1:
+        try:
+            ttft = measure_ttft(model, pool, args, dev)
+        except Exception as e:  # noqa: BLE001  (experimental: never cost the bench line)
+            ttft = f"failed: {type(e).__name__}: {e}"
+
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline:
         v, secs, cores, n_layers, n_seq = cpu_decode_sample(a)
@@ -369,7 +379,7 @@ def run_b200(a, rank, world, local_rank):
                           "parallelism": f"tp{world}", "layers": a.layers,
                           "cuda_graph": use_graph,
                           "l2_policy": "inputs larger than L2 (17.2 GB KV + 4.7 GB weights per step)",
-                          "ttft": "not measured: prefill kernels are SURVEY §8f rank 1 (next)"},
+                          "ttft": ttft},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h},
                "gpu_launches": launches_per_step * a.steps, "clocks": clocks, "roofline": roof,
@@ -395,6 +405,42 @@ def _peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed: int = 4):
+    """Unloaded time-to-first-token: one request at a time, prompt length ~ U[128, 2048] (SURVEY
+    §8d traffic shape), chunked prefill with a `chunk`-token budget through the SAME kernels as the
+    decode step (q_len = chunk rows per sequence: correct, not the tuned path), eager launches.
+    TTFT = host time from the request's arrival (before its first metadata build) to its first
+    generated token being on the host.  Reuses sequence 0's KV blocks of the pool."""
+    import numpy as np
+    import torch
+    from scalellm_b200 import kernels
+    from scalellm_b200.decode_step import StepBuffers, build_decode_batch, prefill_chunks
+    rng = np.random.default_rng(seed)
+    cap_tokens = pool.n_blocks_of(0) * pool.block_size
+    lens = [int(min(x, cap_tokens)) for x in rng.integers(128, 2049, size=n_req)]
+    bufs = StepBuffers(dev, chunk, 1, pool.n_blocks_of(0))
+    out_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+    times = []
+    for i, P in enumerate([lens[0]] + lens):            # first request = warm-up, not recorded
+        t0 = time.perf_counter()
+        sched = prefill_chunks(P, chunk)
+        for ci, (q_len, kv_len) in enumerate(sched):
+            hb = build_decode_batch(pool, [kv_len], [q_len], args.vocab_size, seed=seed + ci)
+            tokens, positions, params = bufs.upload(hb)
+            last = ci == len(sched) - 1
+            sel = torch.tensor([q_len - 1], device=dev) if last else torch.zeros(0, dtype=torch.int64, device=dev)
+            logits = model(tokens, positions, params, last_token_idxes=sel)
+            if last:
+                out_host.copy_(kernels.argmax(logits), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if i > 0:
+            times.append((time.perf_counter() - t0) * 1e3)
+    times.sort()
+    return {"p50_ms": times[len(times) // 2], "min_ms": times[0], "max_ms": times[-1],
+            "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
+            "load": "unloaded (one request at a time), eager launches, decode kernels"}
 
 
 def _traffic(name):

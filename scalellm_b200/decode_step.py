@@ -173,9 +173,11 @@ class LlamaDecoder:
             self.kv_caches.append(c)
 
     # -- forward -------------------------------------------------------------------
-    def forward(self, tokens: torch.Tensor, positions: torch.Tensor,
-                params: InputParameters) -> torch.Tensor:
-        """Returns logits [n_tokens, vocab] (llama.h:220-232 then :281-289)."""
+    def forward(self, tokens: torch.Tensor, positions: torch.Tensor, params: InputParameters,
+                last_token_idxes: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Returns logits [n_tokens, vocab] (llama.h:220-232 then :281-289); with
+        last_token_idxes only those rows go through the final norm's output -> lm_head
+        (the reference's `h.index_select(0, last_token_idxes)` for prefill chunks)."""
         h = self.embed.index_select(0, tokens)
         if self.pa.world_size > 1:  # ParallelEmbedding: split on hidden + all-gather (embedding.h:74-79)
             h = gather_from_model_parallel_region(h, self.pa)
@@ -221,9 +223,23 @@ class LlamaDecoder:
             hn = self.final_norm(h)
         else:
             hn = norm_residual(self.final_norm, pending, pending_is_partials)
+        if last_token_idxes is not None:
+            hn = hn.index_select(0, last_token_idxes)
         return self.lm_head(hn)
 
     __call__ = forward
+
+
+def prefill_chunks(prompt_len: int, chunk: int) -> List[Tuple[int, int]]:
+    """Chunked prefill schedule of one request (scheduler token budget, continuous_scheduler.cpp):
+    [(q_len, kv_len_after_chunk)] with q_len <= chunk, covering the prompt in order."""
+    assert prompt_len > 0 and chunk > 0
+    out, done = [], 0
+    while done < prompt_len:
+        q = min(chunk, prompt_len - done)
+        done += q
+        out.append((q, done))
+    return out
 
 
 # ---------------------------------------------------------------------------

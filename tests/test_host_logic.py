@@ -124,3 +124,14 @@ def test_w4a16_stream_k_partition_invariants(K, N, ctas, nsub):
         assert sorted(set(o.tolist())) == list(range(o[0], o[-1] + 1))   # consecutive CTAs, no holes
         assert contrib[nt] <= slots
     assert max(contrib) == slots
+
+
+def test_prefill_chunk_schedule():
+    from scalellm_b200.decode_step import prefill_chunks
+    assert prefill_chunks(1, 128) == [(1, 1)]
+    assert prefill_chunks(128, 128) == [(128, 128)]
+    assert prefill_chunks(300, 128) == [(128, 128), (128, 256), (44, 300)]
+    for P in (5, 129, 2048):
+        s = prefill_chunks(P, 128)
+        assert sum(q for q, _ in s) == P and s[-1][1] == P and all(0 < q <= 128 for q, _ in s)
+        assert all(b[1] - a[1] == b[0] for a, b in zip(s, s[1:]))
