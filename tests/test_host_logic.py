@@ -135,3 +135,27 @@ def test_prefill_chunk_schedule():
         s = prefill_chunks(P, 128)
         assert sum(q for q, _ in s) == P and s[-1][1] == P and all(0 < q <= 128 for q, _ in s)
         assert all(b[1] - a[1] == b[0] for a, b in zip(s, s[1:]))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_llama8b_tp_shard_shapes_are_valid_w4a16_shapes(world):
+    """Every per-rank projection of Llama-3-8B under TP=1/2/4/8 must be a legal W4A16 shape
+    (multiples of 128, quant groups aligned on the row-parallel K split:
+    qlinear_awq_marlin_impl.cpp:150-151,287) — the decoder constructs without a GPU."""
+    from scalellm_b200.decode_step import LlamaArgs, LlamaDecoder
+    from scalellm_b200.layers import QuantArgs
+    from scalellm_b200.model_parallel import ParallelArgs
+    args = LlamaArgs.llama3_8b()
+    args.n_layers = 1
+    m = LlamaDecoder(args, QuantArgs("awq", 4, 128), ParallelArgs(world - 1, world, None), "cpu")
+    L = m.layers[0]
+    H, Hkv = local_heads(args.n_heads, args.n_kv_heads, world)
+    assert (m.H, m.Hkv) == (H, Hkv) and H % Hkv == 0 and Hkv >= 1
+    D, h, I = args.head_dim, args.hidden_size, args.intermediate_size
+    assert (L["qkv"].K, L["qkv"].N) == (h, (H + 2 * Hkv) * D)
+    assert (L["o"].K, L["o"].N) == (H * D, h)
+    assert (L["gate_up"].K, L["gate_up"].N) == (h, 2 * I // world)
+    assert (L["down"].K, L["down"].N) == (I // world, h)
+    for name in ("qkv", "o", "gate_up", "down"):
+        assert L[name].K % 128 == 0 and L[name].N % 128 == 0, name
+    assert m.embed.shape == (args.vocab_size, h // world)
