@@ -3,6 +3,8 @@
 
   ncu_summary.py launches <launches.csv> <out.md> [title]
       per-kernel count / total / mean / share of a `--metrics gpu__time_duration.sum` launch list
+  ncu_summary.py stalls <report.ncu-rep> <out.md> [launch index] [title]
+      warp-state (stall reason) shares of one launch and its hottest instructions
   ncu_summary.py full <report.ncu-rep> <out.md> [traffic_key]
       key metrics of every launch in a `--set full` capture; with traffic_key also records
       dram read+write bytes per launch in profiles/traffic.json (read by bench.py)
@@ -46,6 +48,7 @@ KEYS = [
 
 def short(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
+    name = re.sub(r"\((?:int|bool|unsigned int)\)", "", name)   # template value casts: (int)128 -> 128
     name = re.sub(r"\(.*$", "", name)
     return name.replace("b200::", "")
 
@@ -127,9 +130,50 @@ def full(rep, out, traffic_key):
         json.dump(d, open(tj, "w"), indent=1)
 
 
+def stalls(rep, out, launch_skip="0", title=""):
+    """Warp-state sampling of one launch of a `--set full --import-source on` capture: share of
+    each stall reason over all sampled warps, and the instructions that collect the most samples."""
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
+                          "--launch-skip", str(launch_skip), "--launch-count", "1"],
+                         capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    name = next((r[1] for r in rows if r and r[0] == "Kernel Name"), "?")
+    h = rows[hdr[0]]
+    end = hdr[1] - 1 if len(hdr) > 1 else len(rows)
+    col = {n: i for i, n in enumerate(h)}
+    data = [r for r in rows[hdr[0] + 1:end] if len(r) > 10 and r[0].startswith("0x")]
+    names = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+    base = int(data[0][0], 16)
+    tot = sum(int(r[col["# Samples"]]) for r in data)
+    agg = {}
+    for r in data:
+        for n in names:
+            v = int(r[col[n]] or 0)
+            if v:
+                agg[n] = agg.get(n, 0) + v
+    with open(out, "w") as f:
+        f.write(f"# {title or 'warp-state sampling'}\n\n`{short(name)}` — launch {launch_skip} of "
+                f"`{os.path.basename(rep)}`; {len(data)} SASS instructions, {tot} warp samples.\n"
+                "`stall_selected` = the warp issued; `stall_wait` = fixed-latency dependency; "
+                "`stall_short_sb` = shared-memory / MUFU / shuffle result; `stall_long_sb` = global "
+                "memory, TMA or mbarrier result.\n\n| state | samples | share |\n|---|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            f.write(f"| {k} | {v} | {100 * v / tot:.1f}% |\n")
+        f.write("\nInstructions with the most samples:\n\n| offset | SASS | samples | executed | top states |\n|---|---|---:|---:|---|\n")
+        for r in sorted(data, key=lambda r: -int(r[col["# Samples"]]))[:20]:
+            st = sorted(((n, int(r[col[n]] or 0)) for n in names), key=lambda kv: -kv[1])[:2]
+            f.write(f"| {int(r[0], 16) - base:#x} | `{r[1].strip()[:70]}` | {r[col['# Samples']]} | "
+                    f"{r[col['Instructions Executed']]} | {', '.join(f'{n} {v}' for n, v in st if v)} |\n")
+    print(open(out).read()[:3000])
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
-    if mode == "launches":
+    if mode == "stalls":
+        stalls(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "0",
+               sys.argv[5] if len(sys.argv) > 5 else "")
+    elif mode == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "ncu launch list")
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
