@@ -732,6 +732,14 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 // ===========================================================================
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
+// High-occupancy variant (OCC = 1, B200_ATTN_OCC=1): the warp-state profile of the default
+// variant shows warps waiting on their own instruction latencies 60 % of the time and on KV data
+// 5 % (profiles/r01_ncu_paged_attn_stalls.md), i.e. it is latency bound at 7 warps per SM.  OCC
+// trades ring depth and block-table window for residency: 2 TMA stages, a 264-entry window and a
+// register cap for 11 one-warp CTAs per SM.  Same code otherwise; opt-in until measured on a B200.
+constexpr int ATT_P_TBL_OCC = 256 + 8;
+constexpr int ATT_OCC_CTAS = 11;
+__host__ __device__ constexpr int att_p_tbl(int occ) { return occ ? ATT_P_TBL_OCC : ATT_P_TBL; }
 
 
 // One work item moving through the claim pipeline.  A stage runs once per rotation, so every
@@ -747,15 +755,16 @@ struct ItemMeta {
   int tbl_buf;                     // stage B: which of the 3 table buffers holds its window
 };
 
-template <typename T, int D>
-__global__ void __launch_bounds__(32, (D <= 128 ? 8 : 3))
+template <typename T, int D, int OCC>
+__global__ void __launch_bounds__(32, (D <= 128 ? (OCC ? ATT_OCC_CTAS : 8) : 3))
 paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                           const __grid_constant__ CUtensorMap vmap, const AttnParams p,
                           int64_t total_tiles, int n_seq) {
   pdl_wait();
   pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = OCC ? 2 : Cfg::STAGES;
+  constexpr int P_TBL = att_p_tbl(OCC);
   constexpr int KS = D / 16, NB = D / 8;
   constexpr int ROWB = D * (int)sizeof(T);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -766,7 +775,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   const int64_t g1 = g0 + p.tpw < total_tiles ? g0 + p.tpw : total_tiles;
   if (g0 >= g1) return;
   const int seq_first = (int)(g0 / p.ntm), seq_last = (int)((g1 - 1) / p.ntm);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 3 * ATT_P_TBL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tbl_base + 3 * P_TBL);
   const int lane = threadIdx.x;
   const int G = p.group;
 
@@ -829,7 +838,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     // asynchronous copy of the block-table window: lands while the previous pieces are processed
     it.tbl_buf = tbl_rot;
     tbl_rot = tbl_rot == 2 ? 0 : tbl_rot + 1;
-    const uint32_t dst = smem_u32(tbl_base + it.tbl_buf * ATT_P_TBL);
+    const uint32_t dst = smem_u32(tbl_base + it.tbl_buf * P_TBL);
     const int32_t* src = p.block_table + it.blk_cu + it.blk_first;
     for (int e = lane; e < it.n_ent; e += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + e * 4), "l"(src + e)
@@ -845,7 +854,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     const int s = g % STAGES;
     T* ks = stage_base + (size_t)s * 2 * Cfg::TILE_ELEMS;
     T* vs = ks + Cfg::TILE_ELEMS;
-    const int32_t* tbl = tbl_base + it.tbl_buf * ATT_P_TBL;
+    const int32_t* tbl = tbl_base + it.tbl_buf * P_TBL;
     const int pos0 = (it.t0 + ti) * ATT_TILE;
     int nbox = 0;
     for (int bx = 0; bx < p.boxes_per_tile; ++bx)
@@ -1296,6 +1305,15 @@ static int attn_impl() {
   return 2;
 }
 
+// B200_ATTN_OCC=1: high-occupancy instantiation of the stream kernel (see ATT_P_TBL_OCC)
+static int attn_occ() {
+  static const int v = [] {
+    const char* e = getenv("B200_ATTN_OCC");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+
 struct AttnPlan {
   int impl, R, n_hg, n_rb, n_splits, tps, warps;
   int ntm, tpw, n_seq;       // stream kernel
@@ -1332,12 +1350,13 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     pl.ntm = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
     pl.n_seq = (int)(pl.grid_y * pl.grid_z);
     pl.total_tiles = (int64_t)pl.n_seq * pl.ntm;
-    const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? 7 : 3);
+    const int occ = head_dim <= 128 ? attn_occ() : 0;
+    const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? (occ ? ATT_OCC_CTAS : 7) : 3);
     int64_t tpw = (pl.total_tiles + warps_resident - 1) / warps_resident;
     const char* e = getenv("B200_ATTN_TPS");
     if (e && atoi(e) > 0) tpw = atoi(e);
     tpw = std::max<int64_t>(tpw, 8);                            // tiny problems: >= 128 slots per piece
-    tpw = std::min<int64_t>(tpw, std::max(1, (ATT_P_TBL - 8) * block_size / ATT_TILE));  // table window
+    tpw = std::min<int64_t>(tpw, std::max(1, (att_p_tbl(occ) - 8) * block_size / ATT_TILE));  // table window
     tpw = std::min<int64_t>(tpw, 4096);
     pl.tpw = (int)tpw;
     pl.n_splits = (pl.ntm + pl.tpw - 1) / pl.tpw + 1;           // pieces one sequence can be cut into
@@ -1359,7 +1378,8 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     } else {
       // largest chunk that still gives every resident warp >= 8 items (dynamic balance within
       // ~1/8 of a warp's work); claims are software pipelined, so small items are cheap
-      const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? 7 : 3);
+      const int occ = head_dim <= 128 ? attn_occ() : 0;
+    const int64_t warps_resident = (int64_t)sm_count() * (head_dim <= 128 ? (occ ? ATT_OCC_CTAS : 7) : 3);
       for (int cand : {32, 16, 8}) {
         tps = cand;
         if (pl.grid_y * pl.grid_z * ((n_tiles + cand - 1) / cand) >= 8 * warps_resident) break;
@@ -1410,13 +1430,22 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   constexpr size_t smem = attn_smem_bytes<T, D>();
   int rc;
   if (pl.impl == 2) {
-    constexpr size_t psmem = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
-                             3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
-    auto kernel = paged_attn_persist_kernel<T, D>;
-    B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
-    B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap, vmap, p,
-                    (int64_t)pl.total_tiles, (int)pl.n_seq);
+    if (D <= 128 && attn_occ()) {
+      constexpr size_t psmem = (size_t)2 * 2 * ATT_TILE * D * sizeof(T) +
+                               3 * ATT_P_TBL_OCC * sizeof(int32_t) + 2 * 8 + 128;
+      auto kernel = paged_attn_persist_kernel<T, D, 1>;
+      B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap,
+                        vmap, p, (int64_t)pl.total_tiles, (int)pl.n_seq);
+    } else {
+      constexpr size_t psmem = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
+                               3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
+      auto kernel = paged_attn_persist_kernel<T, D, 0>;
+      B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap,
+                        vmap, p, (int64_t)pl.total_tiles, (int)pl.n_seq);
+    }
     rc = B200_OK;
   } else if (pl.impl == 1 && pl.warps == 1) {
     rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,

@@ -95,6 +95,17 @@ if has deq; then
   echo "deq rc=$?" | tee -a $OUT/summary.txt
   cat $OUT/deq.log | tee -a $OUT/summary.txt
 fi
+if has occ; then
+  # opt-in high-occupancy attention instantiation (B200_ATTN_OCC=1): parity, then kernel-only timing
+  B200_ATTN_OCC=1 timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_decode_step.py \
+      -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_attention_occ.log 2>&1
+  echo "pytest attention[occ] rc=$? : $(tail -1 $OUT/pytest_attention_occ.log)" | tee -a $OUT/summary.txt
+  for v in 0 1; do
+    B200_ATTN_OCC=$v timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
+        > $OUT/bench_occ$v.json 2> $OUT/bench_occ$v.err
+    echo "bench occ=$v rc=$? $(tail -1 $OUT/bench_occ$v.json | head -c 200)" | tee -a $OUT/summary.txt
+  done
+fi
 if has ref; then
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
   echo "bench reference rc=$?" | tee -a $OUT/summary.txt
