@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -341,7 +341,8 @@ def run_b200(a, rank, world, local_rank):
         kv += 1
         last = e2e_step(kv)
     barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
+    t_e2e_end = time.perf_counter()
+    e2e_s = max_over_ranks((t_e2e_end - t0) / a.steps)
     e2e_val = B / e2e_s
     h2d = bufs.h2d_bytes(last)
     d2h = B * 8
@@ -353,7 +354,9 @@ def run_b200(a, rank, world, local_rank):
     clocks = None
     if sampler:
         time.sleep(0.15)
-        clocks = ClockSampler.summarise(sampler.window(t_w0, t_w1))
+        # under load from the first device-timed step to the last end-to-end step (same graph
+        # replayed back to back): a 100 ms nvidia-smi period needs that long for a real median
+        clocks = ClockSampler.summarise(sampler.window(t_w0, t_e2e_end))
         sampler.stop()
 
     ttft = "not measured: prefill kernels are SURVEY §8f rank 1 (next)"
