@@ -1,0 +1,46 @@
+// Python face of the reference's OWN decode kernels, compiled from /root/reference where they lie
+// (oracle/ref/Makefile; TEST INFRASTRUCTURE, never on the product path).  Nothing of the reference
+// is copied here: this file only includes its headers and re-exports the functions they declare.
+//
+//   src/kernels/layernorm_kernels.h:6-26     rms_norm, rms_norm_residual
+//   src/kernels/pos_embedding_kernels.h:7-13 apply_rotary_pos_emb
+//   src/kernels/kv_cache_kernels.h:6-11      set_kv_cache
+//   src/kernels/activation_kernels.h:6-14    silu, silu_with_mul
+//   src/kernels/attention/attn_api.h:12-27   paged_kv_varlen_mha (bf16 / fp16, head_dim 128 only:
+//                                            the other head dims are not instantiated, so the module
+//                                            must be imported with RTLD_LAZY)
+#include <torch/extension.h>
+
+#include "attn_api.h"
+#include "activation_kernels.h"
+#include "kv_cache_kernels.h"
+#include "layernorm_kernels.h"
+#include "pos_embedding_kernels.h"
+
+PYBIND11_MODULE(_ref_kernels, m) {
+  m.doc() = "vectorch-ai/ScaleLLM src/kernels compiled for sm_100a (test oracle)";
+  m.def("rms_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w, double eps) {
+    llm::kernel::rms_norm(out, x, w, static_cast<float>(eps));
+  });
+  m.def("rms_norm_residual",
+        [](torch::Tensor out, torch::Tensor res, torch::Tensor x, torch::Tensor w, double eps) {
+          llm::kernel::rms_norm_residual(out, res, x, w, static_cast<float>(eps));
+        });
+  m.def("apply_rotary_pos_emb", [](torch::Tensor q, torch::Tensor k, torch::Tensor pos,
+                                   torch::Tensor cos_sin, int rotary_dim, bool interleaved) {
+    llm::kernel::apply_rotary_pos_emb(q, k, pos, cos_sin, rotary_dim, interleaved);
+  });
+  m.def("set_kv_cache", [](torch::Tensor slots, torch::Tensor k, torch::Tensor v, torch::Tensor kc,
+                           torch::Tensor vc) { llm::kernel::set_kv_cache(slots, k, v, kc, vc); });
+  m.def("paged_kv_varlen_mha",
+        [](torch::Tensor out, torch::Tensor q, torch::Tensor kc, torch::Tensor vc, torch::Tensor q_cu,
+           torch::Tensor kv_cu, torch::Tensor table, torch::Tensor blk_cu,
+           std::optional<torch::Tensor> alibi, int bs, int max_q, int max_kv, double scale, double cap,
+           int window) {
+          TORCH_CHECK(q.size(-1) == 128, "reference attention was instantiated for head_dim 128 only");
+          llm::paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, alibi, bs, max_q, max_kv,
+                                   static_cast<float>(scale), static_cast<float>(cap), window);
+        });
+  m.def("silu", &llm::kernel::silu);
+  m.def("silu_with_mul", &llm::kernel::silu_with_mul);
+}
