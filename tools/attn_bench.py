@@ -72,6 +72,53 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
                   flush=True)
         for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
             os.environ.pop(k, None)
+        ref = load_reference_kernels()
+        if ref is not None and D == 128:
+            # GPU baseline beside ours: the reference's own sm80 mma.sync
+            # kernel, compiled for sm_100a from /root/reference (oracle/ref/Makefile), same tensors
+            def launch_ref(kc, vc):
+                ref.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, 1, max_kv,
+                                        D ** -0.5, 0.0, -1)
+            launch_ref(*caches[0])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                for kc, vc in caches:
+                    launch_ref(kc, vc)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (3 * L)
+            byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
+            print(f"attn bs={bs} {'REFERENCE':12s}: {us:7.1f} us/launch "
+                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
+                  flush=True)
+
+
+_REF = []
+
+
+def load_reference_kernels():
+    """oracle/_ref/_ref_kernels.so if it was built (imports lazily: only head_dim 128 of the
+    reference attention is instantiated); timing tool only, never the product path."""
+    if _REF:
+        return _REF[0]
+    so_dir = os.path.join(ROOT, "oracle", "_ref")
+    mod = None
+    if os.path.exists(os.path.join(so_dir, "_ref_kernels.so")):
+        sys.path.insert(0, so_dir)
+        old = sys.getdlopenflags()
+        sys.setdlopenflags(os.RTLD_LAZY | os.RTLD_LOCAL)
+        try:
+            import _ref_kernels as mod
+        except Exception as e:  # noqa: BLE001
+            print(f"(reference kernels not loadable: {e})")
+            mod = None
+        finally:
+            sys.setdlopenflags(old)
+            sys.path.pop(0)
+    _REF.append(mod)
+    return mod
 
 
 if __name__ == "__main__":

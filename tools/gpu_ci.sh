@@ -95,6 +95,14 @@ if has deq; then
   echo "deq rc=$?" | tee -a $OUT/summary.txt
   cat $OUT/deq.log | tee -a $OUT/summary.txt
 fi
+if has refk; then
+  # our kernels against the reference's own kernels (oracle/_ref), then the attention A/B timing
+  B200_TEST_REF_KERNELS=1 timeout 900 python -m pytest tests/test_gpu_vs_reference_kernels.py -m gpu -q \
+      --tb=short -p no:cacheprovider > $OUT/pytest_vs_reference.log 2>&1
+  echo "pytest vs reference kernels rc=$? : $(tail -1 $OUT/pytest_vs_reference.log)" | tee -a $OUT/summary.txt
+  timeout 600 python tools/attn_bench.py > $OUT/attn_bench.log 2>&1
+  cat $OUT/attn_bench.log | tee -a $OUT/summary.txt
+fi
 if has occ; then
   # opt-in high-occupancy attention instantiation (B200_ATTN_OCC=1): parity, then kernel-only timing
   B200_ATTN_OCC=1 timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_decode_step.py \
