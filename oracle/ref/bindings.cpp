@@ -9,9 +9,15 @@
 //   src/kernels/attention/attn_api.h:12-27   paged_kv_varlen_mha (bf16 / fp16, head_dim 128 only:
 //                                            the other head dims are not instantiated, so the module
 //                                            must be imported with RTLD_LAZY)
+//   marlin_dequant_table                     known answers of the Marlin int4 -> bf16 weight
+//                                            arithmetic (marlin_dequant_kat.cu around
+//                                            quantization/marlin/numeric_conversion.h)
+#include <ATen/cuda/CUDAContext.h>
 #include <torch/extension.h>
 
 #include "attn_api.h"
+
+extern "C" int marlin_dequant_kat(const void* scales, int S, void* out_zp, void* out_sym, void* stream);
 #include "activation_kernels.h"
 #include "kv_cache_kernels.h"
 #include "layernorm_kernels.h"
@@ -41,6 +47,16 @@ PYBIND11_MODULE(_ref_kernels, m) {
           llm::paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, alibi, bs, max_q, max_kv,
                                    static_cast<float>(scale), static_cast<float>(cap), window);
         });
+  m.def("marlin_dequant_table", [](torch::Tensor scales) {
+    TORCH_CHECK(scales.is_cuda() && scales.scalar_type() == torch::kBFloat16 && scales.is_contiguous());
+    const int S = static_cast<int>(scales.numel());
+    torch::Tensor zp = torch::empty({16, 16, S}, scales.options());   // [q][z][s]
+    torch::Tensor sym = torch::empty({16, S}, scales.options());      // [q][s], zero point 8 built in
+    const int rc = marlin_dequant_kat(scales.const_data_ptr(), S, zp.data_ptr(), sym.data_ptr(),
+                                      at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == 0, "marlin_dequant_kat launch failed: ", rc);
+    return std::make_tuple(zp, sym);
+  });
   m.def("silu", &llm::kernel::silu);
   m.def("silu_with_mul", &llm::kernel::silu_with_mul);
 }

@@ -126,3 +126,37 @@ def test_paged_attention_vs_reference_kernel(ref, case):
     d = (o_b.float() - o_r.float()).abs()
     tol = 2 * 2.0 ** -8 * o_r.float().abs() + 2e-3 * o_r.float().abs().max()
     assert bool((d <= tol).all()), float(d.max())
+
+
+def test_marlin_weight_arithmetic_known_answers(ref):
+    """Every (q, z) pair x a spread of bf16 scales through the reference's own device functions
+    (numeric_conversion.h dequant<bf16,4,has_zp> -> sub_zp -> scale, in gemm_kernel.cuh's order)
+    == the oracle's restatement (oracle/quant.py dequant) == b200_w4a16_dequant.  Pins the AWQ
+    zero-point path, for which the reference has no known-answer test of its own."""
+    from oracle import quant
+    g = torch.Generator().manual_seed(1)
+    scales = torch.cat([torch.randn(61, generator=g).abs() * 0.02 + 1e-4,
+                        torch.tensor([1.0, 0.5, 3.0]),
+                        torch.tensor([2.0 ** -20, 65280.0])]).bfloat16()
+    S = scales.numel()
+    zp_tab, sym_tab = ref.marlin_dequant_table(scales.to(DEV))
+    torch.cuda.synchronize()
+    # oracle on the same grid: K = 16 values of q as rows, one group, N = S columns per z
+    q = np.repeat(np.arange(16)[:, None], S, axis=1)
+    for z in range(16):
+        want = quant.dequant(q, z, scales[None, :], -1)            # [16, S]
+        assert torch.equal(zp_tab[:, z, :].cpu(), want), z
+    assert torch.equal(sym_tab.cpu(), quant.dequant(q, 8, scales[None, :], -1))
+    # and our prepack + dequant kernel on a weight that contains every (q, z) pair
+    K, N = 128, 256
+    qw = np.zeros((K, N), dtype=np.int64)
+    zz = np.zeros((1, N), dtype=np.int64)
+    for n in range(N):
+        zz[0, n] = n % 16
+        qw[:, n] = (np.arange(K) + n // 16) % 16
+    sc = scales[torch.arange(N) % S][None, :].contiguous()
+    packed = kernels.w4a16_prepack_awq(quant.pack_awq(qw).to(DEV), quant.pack_awq(zz).to(DEV), sc.to(DEV), 128)
+    ours = kernels.w4a16_dequant(packed, K, N, 128).cpu()
+    for n in range(N):
+        col = zp_tab[:, n % 16, n % S].cpu()                         # indexed by q
+        assert torch.equal(ours[:, n], col[torch.from_numpy(qw[:, n])]), n
