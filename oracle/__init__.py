@@ -20,12 +20,12 @@ quant_utils' ``w_ref = (q - zp) * s`` formula: parity unpinned by a reference KA
 ``oracle/_ref`` (git-ignored, built by ``oracle/ref/Makefile`` where ``/root/reference`` exists,
 shipped to the GPU box as a built file): the reference's OWN elementwise kernels
 (``src/kernels/{layernorm,pos_embedding,kv_cache,activation}_kernels.cu``) and its paged attention
-(``src/kernels/attention``: attn_api.cpp + explicit bf16/fp16 head_dim-128 instantiations) compiled
-for sm_100a from the sources where they lie, behind a pybind module written here
+(``src/kernels/attention``: attn_api.cpp + explicit bf16/fp16 head_dim-128 instantiations) and its
+Marlin GEMM (``quantization/marlin/gptq_gemm.cu`` + the instantiations selected for 17 <= M <= 64)
+compiled for sm_100a from the sources where they lie, behind a pybind module written here
 (``oracle/ref/bindings.cpp``), plus a known-answer table of the Marlin int4->bf16 weight arithmetic
 computed by the reference's own device functions (``oracle/ref/marlin_dequant_kat.cu``).
-``tests/test_gpu_vs_reference_kernels.py`` runs our kernels against them on the same inputs.  The whole engine and the Marlin GEMM (whose kernel instantiations are
-generated by the reference's cmake-driven script) are not buildable here; see DESIGN.md.
+``tests/test_gpu_vs_reference_kernels.py`` runs our kernels against them on the same inputs.  The whole engine is not buildable here; see DESIGN.md.
 """
 
 from . import ops, quant, llama, gpt2  # noqa: F401

@@ -9,6 +9,8 @@
 //   src/kernels/attention/attn_api.h:12-27   paged_kv_varlen_mha (bf16 / fp16, head_dim 128 only:
 //                                            the other head dims are not instantiated, so the module
 //                                            must be imported with RTLD_LAZY)
+//   src/kernels/quantization/marlin.h:17-28  marlin_gemm = marlin::gptq_gemm (4-bit, group 128,
+//                                            17 <= M <= 64, N % 256 == 0: the instantiations built)
 //   marlin_dequant_table                     known answers of the Marlin int4 -> bf16 weight
 //                                            arithmetic (marlin_dequant_kat.cu around
 //                                            quantization/marlin/numeric_conversion.h)
@@ -16,6 +18,7 @@
 #include <torch/extension.h>
 
 #include "attn_api.h"
+#include "marlin.h"
 
 extern "C" int marlin_dequant_kat(const void* scales, int S, void* out_zp, void* out_sym, void* stream);
 #include "activation_kernels.h"
@@ -47,6 +50,13 @@ PYBIND11_MODULE(_ref_kernels, m) {
           llm::paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, alibi, bs, max_q, max_kv,
                                    static_cast<float>(scale), static_cast<float>(cap), window);
         });
+  m.def("marlin_gemm", [](torch::Tensor A, torch::Tensor B, torch::Tensor C, torch::Tensor scales,
+                          torch::Tensor zeros, torch::Tensor g_idx, torch::Tensor perm,
+                          torch::Tensor workspace, int num_bits, bool is_k_full, bool has_zp,
+                          bool use_fp32_reduce) {
+    marlin::gptq_gemm(A, B, C, scales, zeros, g_idx, perm, workspace, num_bits, is_k_full, has_zp,
+                      use_fp32_reduce);
+  });
   m.def("marlin_dequant_table", [](torch::Tensor scales) {
     TORCH_CHECK(scales.is_cuda() && scales.scalar_type() == torch::kBFloat16 && scales.is_contiguous());
     const int S = static_cast<int>(scales.numel());

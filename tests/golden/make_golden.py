@@ -6,7 +6,7 @@ Imports, unmodified:
     /root/reference/tests/kernels/quant_utils.py            (quantize / pack AWQ, GPTQ)
     /root/reference/tests/kernels/attention/ref_attention.py (paged var-len attention reference)
 and reads /root/reference/src/layers/quantization/data/gptq_small.safetensors (real GPTQ tensors).
-Outputs (small, committed): quant_golden.npz, attn_golden.npz, gptq_small.npz,
+Outputs (small, committed): quant_golden.npz, marlin_golden.npz, attn_golden.npz, gptq_small.npz,
 llama3_rope_inv_freq.json (numbers transcribed from src/layers/pos_embedding_test.cpp:98-138).
 Nothing under tests/ or the product reads /root/reference at run time.
 """
@@ -82,6 +82,25 @@ def make_attn():
     np.savez_compressed(os.path.join(HERE, "attn_golden.npz"), **out)
 
 
+def make_marlin():
+    """Symmetric 4-bit, group 128 weights in BOTH formats from the reference's utilities: the GPTQ
+    checkpoint packing our prepack consumes and the Marlin packing + scale permutation the
+    reference's own GEMM kernel consumes (tests/kernels/marlin_gemm_test.py:82-95).  Used by
+    tests/test_gpu_vs_reference_kernels.py to run marlin::gptq_gemm and b200_w4a16_gemm on the same
+    weights.  K x N = 512 x 512 keeps the fixture small."""
+    K, N, g = 512, 512, 128
+    torch.manual_seed(77)
+    w = torch.randn(K, N, dtype=torch.float32).to(torch.bfloat16)
+    w_ref, q_w, s, _, _ = qu.quantize_weights(w, num_bits=4, group_size=g, act_order=False)
+    out = dict(shape=np.array([K, N, g]),
+               q=q_w.numpy().astype(np.int8),
+               scales_bf16=bf16_bits(s),
+               gptq_packed=qu.pack_gptq_weights(q_w, 4).numpy(),
+               marlin_packed=qu.pack_marlin_weights(q_w, num_bits=4).numpy(),
+               marlin_scales_bf16=bf16_bits(qu.permute_marlin_scales(s)))
+    np.savez_compressed(os.path.join(HERE, "marlin_golden.npz"), **out)
+
+
 def make_gptq_small():
     from safetensors.torch import load_file
     sd = load_file(os.path.join(REF, "src/layers/quantization/data/gptq_small.safetensors"))
@@ -120,6 +139,7 @@ def make_rope():
 
 if __name__ == "__main__":
     make_quant()
+    make_marlin()
     make_attn()
     make_gptq_small()
     make_rope()

@@ -160,3 +160,40 @@ def test_marlin_weight_arithmetic_known_answers(ref):
     for n in range(N):
         col = zp_tab[:, n % 16, n % S].cpu()                         # indexed by q
         assert torch.equal(ours[:, n], col[torch.from_numpy(qw[:, n])]), n
+
+
+@pytest.mark.parametrize("M", [17, 33, 64])
+def test_w4a16_gemm_vs_reference_marlin_kernel(ref, golden_dir, M):
+    """The reference's own Marlin GEMM (marlin::gptq_gemm, src/kernels/quantization/marlin.h:17-28,
+    fed exactly as tests/kernels/marlin_gemm_test.py:82-112 feeds it) and b200_w4a16_gemm on the same
+    symmetric 4-bit / group-128 weights (tests/golden/marlin_golden.npz: both packings written by the
+    reference's quant_utils) and the same activations.  Both accumulate bf16 x bf16 products in fp32
+    and round once, in different orders: each must sit within the oracle's tolerance, and they must
+    agree with each other to a bf16 ulp (or 2e-3 of the output scale where values cancel)."""
+    from oracle import quant
+    d = np.load(os.path.join(golden_dir, "marlin_golden.npz"))
+    K, N, g = (int(x) for x in d["shape"])
+    scales = torch.from_numpy(d["scales_bf16"]).view(torch.bfloat16)
+    gen = torch.Generator().manual_seed(M)
+    a = torch.randn(M, K, generator=gen).bfloat16()
+    # ours: GPTQ checkpoint packing -> tile blobs (symmetric: zero point 8)
+    packed = kernels.w4a16_prepack_gptq(torch.from_numpy(d["gptq_packed"]).to(DEV), None, scales.to(DEV), g)
+    ours = kernels.w4a16_gemm(a.to(DEV), packed, N, g)
+    # reference: Marlin packing + permuted scales, no zero points, no act-order
+    empty_i = torch.empty(0, dtype=torch.int32, device=DEV)
+    out_ref = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    workspace = torch.zeros(N // 64 * 16, dtype=torch.int32, device=DEV)
+    ref.marlin_gemm(a.to(DEV), torch.from_numpy(d["marlin_packed"]).to(DEV), out_ref,
+                    torch.from_numpy(d["marlin_scales_bf16"]).view(torch.bfloat16).to(DEV), empty_i,
+                    empty_i, empty_i, workspace, 4, True, False, True)
+    torch.cuda.synchronize()
+    assert int(workspace.abs().sum()) == 0                       # Marlin returns its locks zeroed
+    w = quant.dequant(d["q"].astype(np.int64), 8, scales, g)     # oracle weights
+    want = quant.w4a16_gemm(a, w)
+    scale = want.float().abs().max().item()
+    for name, got in (("b200", ours), ("reference", out_ref)):
+        err = (got.float().cpu() - want.float()).abs().max().item()
+        assert err <= 2e-3 * scale + 2.0 ** -8 * scale, (name, err, scale)
+    diff = (ours.float() - out_ref.float()).abs()
+    tol = 2.0 ** -8 * out_ref.float().abs() + 2e-3 * scale
+    assert bool((diff <= tol).all()), float(diff.max())

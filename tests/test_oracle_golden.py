@@ -139,3 +139,22 @@ def test_rms_norm_oracle_matches_layer_formula():
     assert torch.allclose(out.float(), ref.float(), rtol=1e-2, atol=1e-3)
     o2, r2 = ops.rms_norm_residual(x, x.clone(), w, 1e-5)
     assert torch.equal(r2, (x.float() * 2).bfloat16())
+
+
+def test_marlin_golden_fixture_is_consistent_with_oracle_packers(golden_dir):
+    """The fixture that feeds the reference's own Marlin GEMM on the GPU (marlin_golden.npz, written
+    by the reference's quant_utils): its GPTQ packing must be what our oracle packs from the same
+    integers, and the Marlin tensors must have the layout marlin::gptq_gemm expects
+    (src/kernels/quantization/marlin.h:17-28: B (k/16, n*16/8), scales (k/g, n))."""
+    import numpy as np
+    import torch
+    from oracle import quant
+    d = np.load(os.path.join(golden_dir, "marlin_golden.npz"))
+    K, N, g = (int(x) for x in d["shape"])
+    q = d["q"].astype(np.int64)
+    assert q.shape == (K, N) and q.min() >= 0 and q.max() <= 15
+    assert np.array_equal(quant.pack_gptq(q).numpy(), d["gptq_packed"])
+    assert d["marlin_packed"].shape == (K // 16, N * 16 // 8) and d["marlin_packed"].dtype == np.int32
+    assert d["marlin_scales_bf16"].shape == d["scales_bf16"].shape == (K // g, N)
+    # the permuted scales are a permutation of the original ones, row by row
+    assert np.array_equal(np.sort(d["marlin_scales_bf16"], axis=1), np.sort(d["scales_bf16"], axis=1))

@@ -102,6 +102,8 @@ if has refk; then
   echo "pytest vs reference kernels rc=$? : $(tail -1 $OUT/pytest_vs_reference.log)" | tee -a $OUT/summary.txt
   timeout 600 python tools/attn_bench.py > $OUT/attn_bench.log 2>&1
   cat $OUT/attn_bench.log | tee -a $OUT/summary.txt
+  timeout 600 python tools/w4_ref_bench.py > $OUT/w4_ref_bench.log 2>&1
+  cat $OUT/w4_ref_bench.log | tee -a $OUT/summary.txt
 fi
 if has occ; then
   # opt-in high-occupancy attention instantiation (B200_ATTN_OCC=1): parity, then kernel-only timing

@@ -1,0 +1,56 @@
+"""GPU baseline beside ours: the reference's own Marlin GEMM kernel, compiled
+for sm_100a from /root/reference into oracle/_ref (oracle/ref/Makefile), against b200_w4a16_gemm on
+the four Llama-3-8B projection shapes at M = 64.  Timing only: the weights are random words in each
+library's own layout (any word is a valid packed int4 weight), rotated over several copies so every
+launch streams from HBM.  Never on the product path."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from scalellm_b200 import kernels  # noqa: E402
+from attn_bench import load_reference_kernels  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, n_copies, reps=3):
+    fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for i in range(n_copies):
+            fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * n_copies)
+
+
+def main():
+    ref = load_reference_kernels()
+    M, g, L = 64, 128, 8
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    ri = lambda *s: torch.randint(-2 ** 31, 2 ** 31 - 1, s, generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+    for name, K, N in (("qkv", 4096, 6144), ("o", 4096, 4096), ("gate_up", 4096, 28672), ("down", 14336, 4096)):
+        a = torch.randn(M, K, device=DEV).bfloat16()
+        sc = (torch.rand(K // g, N, device=DEV) * 0.01 + 1e-3).bfloat16()
+        ours_w = [kernels.w4a16_prepack_gptq(ri(K // 8, N), None, sc, g) for _ in range(L)]
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        t_full = timeit(lambda i: kernels.w4a16_gemm(a, ours_w[i], N, g, out=out), L)
+        t_part = timeit(lambda i: kernels.w4a16_gemm_splitk(a, ours_w[i], N, g), L)
+        line = f"{name:8s} K={K:5d} N={N:5d}: b200 gemm+reduce {t_full:6.1f} us, partials only {t_part:6.1f} us"
+        if ref is not None:
+            marlin_w = [ri(K // 16, N * 16 // 8) for _ in range(L)]
+            ws = torch.zeros(N // 64 * 16, dtype=torch.int32, device=DEV)
+            e = torch.empty(0, dtype=torch.int32, device=DEV)
+            t_ref = timeit(lambda i: ref.marlin_gemm(a, marlin_w[i], out, sc, e, e, e, ws, 4, True, False, True), L)
+            line += f", reference Marlin {t_ref:6.1f} us"
+        print(line, flush=True)
+
+
+if __name__ == "__main__":
+    main()
