@@ -54,9 +54,14 @@ class Linear:
 
     def __init__(self, w: torch.Tensor):
         self.w = w
+        self._w32 = None   # fp32 copy made on first use: the CPU path computes in fp32
+                           # (llm_engine.cpp:28-31), so the conversion is not part of a step
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        return quant.w4a16_gemm(x, self.w)
+        if self._w32 is None:
+            self._w32 = self.w.to(torch.float32)
+        # == quant.w4a16_gemm(x, self.w): bf16 inputs, fp32 accumulation, one rounding
+        return (x.to(torch.float32) @ self._w32).to(x.dtype)
 
 
 def decoder_layer(x, positions, layer, cfg: LlamaConfig, cos_sin, k_cache, v_cache,
