@@ -155,7 +155,7 @@ class CpuDecodeSample:
         self.cos_sin = ops.build_cos_sin_cache(D, 4096, ollama.inv_freq_for(cfg), torch.bfloat16)
         self.x = (torch.randn(B, h, generator=g) * 0.5).bfloat16()
         self.pos = torch.full((B,), S - 1, dtype=torch.int32)
-        self.lm_head = (torch.randn(h, cfg.vocab, generator=g) * 0.02).bfloat16()
+        self.lm_head = ollama.Linear((torch.randn(h, cfg.vocab, generator=g) * 0.02).bfloat16())
         self.fn = torch.ones(h).bfloat16()
         self._pick_threads()
 
@@ -169,7 +169,7 @@ class CpuDecodeSample:
             self.torch.set_num_threads(t)
             v, secs = self.step(1)
             if best is None or v > best:
-                best, best_t, self.layer_secs = v, t, secs
+                best, best_t, self.layer_secs = v, t, self.last_layer_secs
         self.torch.set_num_threads(best_t)
 
     def layers_for(self, budget_s: float) -> int:
@@ -185,10 +185,11 @@ class CpuDecodeSample:
                                           self.vc, self.slots, self.meta)
         t_layers = time.perf_counter() - t0
         t1 = time.perf_counter()
-        logits = self.quant.w4a16_gemm(self.ops.rms_norm(y, self.fn, self.cfg.rms_eps), self.lm_head)
+        logits = self.lm_head(self.ops.rms_norm(y, self.fn, self.cfg.rms_eps))
         _ = logits.argmax(-1)
         t_head = time.perf_counter() - t1
         step_s = t_layers / n_layers_sample * 32 + t_head
+        self.last_layer_secs = t_layers / n_layers_sample
         return self.B / step_s, t_layers + t_head
 
 
