@@ -193,7 +193,7 @@ class CpuDecodeSample:
         return self.B / step_s, t_layers + t_head
 
 
-def cpu_decode_sample(a, budget_s: float = 15.0, seed: int = 0):
+def cpu_decode_sample(a, budget_s: float = 30.0, seed: int = 0):
     c = CpuDecodeSample(a, seed)
     n_layers = c.layers_for(budget_s)
     v, secs = c.step(n_layers)
