@@ -88,6 +88,12 @@ B200_API int b200_rope_inplace(void* q, void* k, const int32_t* positions,
                                int64_t q_stride, int64_t k_stride,
                                int interleaved, int dtype, b200_stream_t stream);
 
+/* Debug / test hook (host arithmetic only): the work partition b200_paged_attn_decode would use.
+ * out[8] = {impl (0 simt, 1 mma, 2 stream), n_splits, tiles per warp, padded tiles per
+ * (sequence, row block, kv head), number of those, row blocks, total tiles, block-table window}. */
+B200_API int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads,
+                                  int n_kv_heads, int head_dim, int block_size, int64_t* out);
+
 /* ------------------------------------------------------------------------ *
  * A2  KV-cache slot write           src/kernels/kv_cache_kernels.h:6-11
  *     cache[slot_ids[t], h, :] = {k,v}[t, h, :]        (bit exact)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_w4a16_splitk_splits": (_int, [_i64, _i64, _i64]),
     "b200_w4a16_gemm_splitk": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "b200_w4a16_reduce_partials": (_int, [_vp, _vp, _int, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "b200_debug_attn_plan": (_int, [_i64, _int, _int, _int, _int, _int, _int, _vp]),
     "b200_debug_w4a16_plan": (_int, [_i64, _i64, _int, _int, _vp, _vp, _vp]),
     "b200_argmax": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_rope_kv_write_splitk": (_int, [_vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64,

@@ -1499,6 +1499,23 @@ int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_
   return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
 }
 
+int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads, int n_kv_heads,
+                         int head_dim, int block_size, int64_t* out /*[8]*/) {
+  B200_CHECK_ARG(out && batch > 0 && max_q_len > 0 && max_kv_len > 0 && n_heads > 0 && n_kv_heads > 0 &&
+                     n_heads % n_kv_heads == 0 && block_size > 0,
+                 "debug_attn_plan: bad arguments");
+  const AttnPlan pl = make_plan(batch, max_q_len, max_kv_len, n_heads, n_kv_heads, head_dim, block_size);
+  out[0] = pl.impl;
+  out[1] = pl.n_splits;
+  out[2] = pl.tpw;
+  out[3] = pl.ntm;
+  out[4] = pl.n_seq;
+  out[5] = pl.n_rb;
+  out[6] = pl.total_tiles;
+  out[7] = pl.impl == 2 ? att_p_tbl(head_dim <= 128 ? attn_occ() : 0) : 0;  // table window entries
+  return B200_OK;
+}
+
 int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const void* v_cache,
                            const int32_t* q_cu_lens, const int32_t* kv_cu_lens,
                            const int32_t* block_table, const int32_t* block_cu_lens,

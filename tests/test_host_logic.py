@@ -159,3 +159,36 @@ def test_llama8b_tp_shard_shapes_are_valid_w4a16_shapes(world):
     for name in ("qkv", "o", "gate_up", "down"):
         assert L[name].K % 128 == 0 and L[name].N % 128 == 0, name
     assert m.embed.shape == (args.vocab_size, h // world)
+
+
+@pytest.mark.parametrize("heads", [(32, 8), (4, 1), (8, 8), (64, 8)])
+@pytest.mark.parametrize("batch,max_q", [(1, 1), (7, 3), (64, 1), (256, 1)])
+def test_attention_stream_partition_invariants(heads, batch, max_q):
+    """Host arithmetic of the paged-attention work partition (libb200decode, no GPU needed; the
+    SM count falls back to 148): every (sequence, row block, kv head) is cut into at most n_splits
+    pieces, a piece's block-table window fits the shared-memory table for every block size, and
+    the workspace query (which assumes block_size 1) covers every block size."""
+    import ctypes as C
+    from scalellm_b200 import _lib
+    lib = _lib.load()
+    H, Hkv = heads
+    D = 128
+    for max_kv in (1, 17, 2048, 8192, 100000):
+        plans = {}
+        for bs in (1, 8, 16, 128):
+            out = (C.c_int64 * 8)()
+            assert lib.b200_debug_attn_plan(batch, max_q, max_kv, H, Hkv, D, bs, out) == 0
+            impl, n_splits, tpw, ntm, n_seq, n_rb, total, window = list(out)
+            plans[bs] = n_splits
+            if impl != 2:       # absurdly long context with tiny blocks falls back to the mma kernel
+                continue
+            assert ntm == (max_kv + 15) // 16 and n_rb == (max_q * (H // Hkv) + 15) // 16
+            assert n_seq == batch * n_rb * Hkv and total == n_seq * ntm and tpw >= 1
+            assert tpw * 16 // bs + 8 <= window or tpw * 16 <= bs, (tpw, bs, window)
+            # pieces of the worst-placed sequence: its ntm tiles start anywhere in the stream
+            worst = max((((s * ntm) % tpw) + ntm - 1) // tpw + 1 for s in range(min(n_seq, 4096)))
+            assert worst <= n_splits, (worst, n_splits)
+        ws = lib.b200_paged_attn_workspace_bytes(batch, max_q, max_kv, H, Hkv, D)
+        need = max(plans.values())
+        if need > 1:
+            assert ws >= batch * max_q * H * need * (D + 1) * 4
