@@ -31,6 +31,7 @@
 //   alibi : score += slope[h] * kv_pos          (after scale / soft-cap)
 //   softcap: score = cap * tanh(score * sm_scale / cap)  (mha_params.h:51-66)
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -1490,10 +1491,15 @@ int64_t b200_paged_attn_workspace_bytes(int64_t batch, int64_t max_q_len, int64_
                                         int64_t n_heads, int64_t n_kv_heads, int64_t head_dim) {
   if (batch <= 0 || max_q_len <= 0 || n_heads <= 0 || n_kv_heads <= 0) return 0;
   if (n_heads % n_kv_heads) return 0;
-  // block_size is not part of this query: assume 1 (the smallest chunks = the most splits)
-  const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
-                                (int)n_kv_heads, (int)head_dim, 1);
-  const int n_splits = pl.n_splits;
+  // block_size is not part of this query: size for the block size that needs the most splits
+  // (small blocks shrink the block-table window of a piece, but very small ones can also push the
+  // plan onto the fixed-split kernel, so no single block size is the worst case)
+  int n_splits = 1;
+  for (int bs = 1; bs <= 256; bs *= 2) {
+    const AttnPlan pl = make_plan(batch, (int)max_q_len, (int)max_kv_len, (int)n_heads,
+                                  (int)n_kv_heads, (int)head_dim, bs);
+    n_splits = std::max(n_splits, pl.n_splits);
+  }
   if (n_splits <= 1) return 0;
   // worst case over env overrides: size for the planned split count
   return batch * max_q_len * n_heads * n_splits * (head_dim + 1) * (int64_t)sizeof(float) + 256;
