@@ -276,6 +276,16 @@ struct W4Params {
   do {                                                                               \
     if constexpr (TRACE) p.trace[(int64_t)blockIdx.x * 16 + (slot)] = clock64();     \
   } while (0)
+// slots 14 / 15: %globaltimer (ns, common to all SMs) at CTA entry / exit: the launch ramp and the
+// span of the whole grid, which the per-CTA clock64 milestones cannot show
+#define W4_TRACE_NS(slot)                                                            \
+  do {                                                                               \
+    if constexpr (TRACE) {                                                           \
+      unsigned long long ns_;                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_));                        \
+      p.trace[(int64_t)blockIdx.x * 16 + (slot)] = (long long)ns_;                   \
+    }                                                                                \
+  } while (0)
 
 struct SegIter {
   int u, u1, KT;
@@ -332,7 +342,10 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KT = p.KT;
-  if (threadIdx.x == 0) W4_TRACE(0);
+  if (threadIdx.x == 0) {
+    W4_TRACE(0);
+    W4_TRACE_NS(14);
+  }
   const int u_begin = w4_unit_begin(blockIdx.x, p.plan.units, p.plan.P);
   const int u_end = w4_unit_begin(blockIdx.x + 1, p.plan.units, p.plan.P);
 
@@ -602,7 +615,10 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) W4_TRACE(8);
+  if (threadIdx.x == 0) {
+    W4_TRACE(8);
+    W4_TRACE_NS(15);
+  }
   if (warp == W4_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

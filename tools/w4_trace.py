@@ -41,9 +41,14 @@ def run(K, N, M=64, g=128):
     t = t[t[:, 0] != 0]
     rel = (t - t[:, :1]).float()
     rel[:, 9:] = t[:, 9:].float()        # wait totals are already durations
+    ns0, ns1 = t[:, 14], t[:, 15]        # %globaltimer at CTA entry / exit
     rel[t == 0] = float("nan")
     print(f"== K={K} N={N} M={M}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {t.shape[0]} CTAs "
           f"(cycles; ~1.9 cycles/ns)")
+    if int(ns0.min()) > 0:
+        print(f"  grid span {(ns1.max() - ns0.min()).item() / 1e3:.2f} us (first CTA entry -> last CTA exit); "
+              f"CTA entries spread over {(ns0.max() - ns0.min()).item() / 1e3:.2f} us; "
+              f"median CTA lifetime {(ns1 - ns0).float().median().item() / 1e3:.2f} us")
     for i, nm in enumerate(NAMES):
         col = rel[:, i]
         col = col[~torch.isnan(col)]
