@@ -49,7 +49,10 @@ def parse():
     ap.add_argument("--seqlen", type=int, default=2048)
     ap.add_argument("--block-size", type=int, default=8)
     ap.add_argument("--quant", default="awq", choices=["awq", "gptq", "none"])
-    ap.add_argument("--layers", type=int, default=32, help="debug only; the default is the named config")
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"],
+                    help="llama3-70b = SURVEY §8d config 4 (run it as --gpus 8 --batch 32 --seqlen 4096 "
+                         "--quant gptq); the default is the configuration the metric is quoted on")
+    ap.add_argument("--layers", type=int, default=None, help="debug only; the default is the named config")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -57,7 +60,8 @@ def parse():
 
 def workload_name(a, world):
     q = {"awq": "AWQ-int4 g128", "gptq": "GPTQ-int4 g128", "none": "bf16"}[a.quant]
-    return (f"Llama-3-8B {q} decode step, batch {a.batch}, kv_len {a.seqlen}, block_size "
+    name = {"llama3-8b": "Llama-3-8B", "llama3-70b": "Llama-3-70B"}[a.model]
+    return (f"{name} {q} decode step, batch {a.batch}, kv_len {a.seqlen}, block_size "
             f"{a.block_size}, TP={world}")
 
 
@@ -203,6 +207,10 @@ def cpu_decode_sample(a, budget_s: float = 30.0, seed: int = 0):
 def run_reference(a, rank):
     if rank != 0:
         return
+    if a.model != "llama3-8b":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is sized for the llama3-8b "
+                          "configuration the metric is quoted on"}), flush=True)
+        return
     c = CpuDecodeSample(a, 0)
     cores = c.torch.get_num_threads()
     vals, secs = [], 0.0
@@ -261,8 +269,10 @@ def run_b200(a, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    args = LlamaArgs.llama3_8b()
-    args.n_layers = a.layers
+    args = LlamaArgs.llama3_70b() if a.model == "llama3-70b" else LlamaArgs.llama3_8b()
+    if a.layers is not None:
+        args.n_layers = a.layers
+    a.layers = args.n_layers
     qa = QuantArgs(quant_method="" if a.quant == "none" else a.quant, bits=4, group_size=128,
                    is_sym=(a.quant == "gptq"))
     model = LlamaDecoder(args, qa, pa, dev)
@@ -369,13 +379,20 @@ def run_b200(a, rank, world, local_rank):
             ttft = f"failed: {type(e).__name__}: {e}"
 
     cpu = None
-    if rank == 0 and world == 1 and not a.skip_cpu_baseline:
+    if rank == 0 and world == 1 and not a.skip_cpu_baseline and a.model == "llama3-8b":
         v, secs, cores, n_layers, n_seq = cpu_decode_sample(a)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_seq} of the {a.batch} sequences through {n_layers} passes of an oracle decoder layer + "
                          f"lm_head at the full kv_len ({secs:.1f} s of CPU work on {cores} threads, the "
                          "fastest of the thread counts tried), time extrapolated to 32 layers"}
 
+    kv_gb = 2 * B * S * max(1, args.n_kv_heads // world) * args.head_dim * 2 * args.n_layers / 1e9
+    wbytes = 0.5 + 2.5 / 128 if a.quant != "none" else 2.0      # int4 + scales + zeros @ g128
+    lin_params = args.hidden_size * ((args.n_heads + 2 * args.n_kv_heads) * args.head_dim +
+                                     args.n_heads * args.head_dim + 3 * args.intermediate_size)
+    w_gb = (args.n_layers * lin_params * wbytes + args.vocab_size * args.hidden_size * 2) / world / 1e9
+    l2_policy = f"inputs larger than L2 ({kv_gb:.1f} GB KV + {w_gb:.1f} GB weights per step" + \
+                (" and GPU)" if world > 1 else ")")
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -383,7 +400,7 @@ def run_b200(a, rank, world, local_rank):
                "config": {"workload": workload_name(a, world), "global_batch": B, "seq_len": S,
                           "parallelism": f"tp{world}", "layers": a.layers,
                           "cuda_graph": use_graph,
-                          "l2_policy": "inputs larger than L2 (17.2 GB KV + 4.7 GB weights per step)",
+                          "l2_policy": l2_policy,
                           "ttft": ttft},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h},
