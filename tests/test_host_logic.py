@@ -96,7 +96,11 @@ def test_build_decode_batch_matches_per_token_loop():
 @pytest.mark.parametrize("K,N,ctas,nsub", [(4096, 4096, 148, 1), (4096, 6144, 148, 1), (4096, 28672, 148, 1),
                                            (14336, 4096, 148, 1), (4096, 28672, 148, 2), (128, 128, 148, 1),
                                            (512, 256, 148, 1), (512, 4096, 148, 1), (4096, 768, 148, 1),
-                                           (1792, 4096, 132, 1), (4096, 3584, 7, 1)])
+                                           (1792, 4096, 132, 1), (4096, 3584, 7, 1),
+                                           # Llama-3-70B: per-rank shapes at TP=8, then TP=1
+                                           (8192, 1280, 148, 1), (1024, 8192, 148, 1), (8192, 7168, 148, 1),
+                                           (3584, 8192, 148, 1), (8192, 10240, 148, 1), (8192, 57344, 148, 1),
+                                           (28672, 8192, 148, 1)])
 def test_w4a16_stream_k_partition_invariants(K, N, ctas, nsub):
     """The stream-K partition shared by the GEMM and the kernels that sum its partials (host
     arithmetic in libb200decode, no GPU needed): equal contiguous shares, every tile's contributors
@@ -137,17 +141,19 @@ def test_prefill_chunk_schedule():
         assert all(b[1] - a[1] == b[0] for a, b in zip(s, s[1:]))
 
 
+@pytest.mark.parametrize("model", ["llama3_8b", "llama3_70b"])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_llama8b_tp_shard_shapes_are_valid_w4a16_shapes(world):
-    """Every per-rank projection of Llama-3-8B under TP=1/2/4/8 must be a legal W4A16 shape
+def test_llama_tp_shard_shapes_are_valid_w4a16_shapes(world, model):
+    """Every per-rank projection of Llama-3-8B / 70B under TP=1/2/4/8 must be a legal W4A16 shape
     (multiples of 128, quant groups aligned on the row-parallel K split:
     qlinear_awq_marlin_impl.cpp:150-151,287) — the decoder constructs without a GPU."""
     from scalellm_b200.decode_step import LlamaArgs, LlamaDecoder
     from scalellm_b200.layers import QuantArgs
     from scalellm_b200.model_parallel import ParallelArgs
-    args = LlamaArgs.llama3_8b()
+    args = getattr(LlamaArgs, model)()
     args.n_layers = 1
-    m = LlamaDecoder(args, QuantArgs("awq", 4, 128), ParallelArgs(world - 1, world, None), "cpu")
+    quant = QuantArgs("awq", 4, 128) if model == "llama3_8b" else QuantArgs("gptq", 4, 128, is_sym=True)
+    m = LlamaDecoder(args, quant, ParallelArgs(world - 1, world, None), "cpu")
     L = m.layers[0]
     H, Hkv = local_heads(args.n_heads, args.n_kv_heads, world)
     assert (m.H, m.Hkv) == (H, Hkv) and H % Hkv == 0 and Hkv >= 1
