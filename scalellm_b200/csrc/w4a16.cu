@@ -320,10 +320,20 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // NSUB weight tiles (adjacent n tiles, same k tile) share one activation stage: the activation
 // bytes pulled out of L2 per weight tile drop by NSUB (the kernel is L2-bandwidth bound on them:
 // every CTA re-reads the [MT x 128] activation tile of each of its k tiles).
-template <int MT, int NSUB, bool TRACE>
+//
+// VAR (experiments on the MMA thread's per-tile cost, B200_W4_VARIANT; 0 = default).  With one
+// weight tile per unit the activation ring and the dequantised-weight ring have the same depth, so
+// stage == slot for every tile and one barrier can release both:
+//   1: one tcgen05.commit per tile (the activation producer waits on the slot's deq_empty barrier)
+//   2: tiles are issued in aligned pairs: one tcgen05.fence + one commit per two tiles (pair
+//      barrier deq_empty[pair % 3]; both producers wait on it)
+template <int MT, int NSUB, bool TRACE, int VAR = 0>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
+  static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
+                             Cfg::ACC_BUFS == 2 && !TRACE),
+                "variants need stage == slot");
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -437,7 +447,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
             tw = TRACE ? clock64() : 0;
-            mbar_wait(&deq_empty[as], aph ^ 1);
+            if constexpr (VAR == 2) {
+              const int pr = cnt >> 1;
+              mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
+            } else {
+              mbar_wait(&deq_empty[as], aph ^ 1);
+            }
             if (TRACE) w_slot += clock64() - tw;
             tc_fence_after();
           }
@@ -490,7 +505,14 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          mbar_wait(&act_empty[as], aph ^ 1);
+          if constexpr (VAR == 0) {
+            mbar_wait(&act_empty[as], aph ^ 1);
+          } else if constexpr (VAR == 1) {
+            mbar_wait(&deq_empty[as], aph ^ 1);  // stage == slot: released by the slot's commit
+          } else {
+            const int pr = cnt >> 1;
+            mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
+          }
           mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
@@ -511,53 +533,102 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
-    SegIter it{u_begin, u_end, KT};
-    int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
     long long w_act = 0, w_deq = 0, w_acc = 0;  // TRACE: cycles spent waiting per barrier kind
-    while (it.next(nt, kt0, kt1)) {
-      const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
-      const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
-      long long tw = TRACE ? clock64() : 0;
-      mbar_wait(&tmem_empty[buf], tph ^ 1);
-      if (TRACE) w_acc += clock64() - tw;
-      tc_fence_after();
-      for (int kt = kt0; kt < kt1; ++kt, ++ucnt) {
-        const int as = ucnt % Cfg::ACT_STAGES;
-        const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
-        tw = TRACE ? clock64() : 0;
-        mbar_wait(&act_full[as], aph);
-        if (TRACE) w_act += clock64() - tw;
-        const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
-        const uint32_t first = (kt > kt0) ? 1u : 0u;
+    if constexpr (VAR == 2) {
+      // tiles in aligned pairs (cnt even): slots (cnt % 6, cnt % 6 + 1), pair barrier (cnt / 2) % 3
+      SegIter it{u_begin, u_end, KT};
+      const int total = u_end - u_begin;
+      int nt, kt0 = 0, kt1 = 0, kt = 0, seg = -1;
+      for (int cnt = 0; cnt < total; cnt += 2) {
+        const int n = min(2, total - cnt);
+        uint32_t d_tmem[2], first[2], last[2], slot[2];
 #pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
-          const int ds = cnt % Cfg::A_STAGES;
-          const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
-          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
-          const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
-          tw = TRACE ? clock64() : 0;
-          mbar_wait(&deq_full[ds], dph);
-          if (TRACE) w_deq += clock64() - tw;
-          if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              // descriptor start-address field is in 16-byte units: advance by constants
-              const uint64_t b_desc =
-                  b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
-              umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
+        for (int j = 0; j < 2; ++j) {
+          if (j < n) {
+            if (kt == kt1) {  // next segment: its accumulator buffer must have been drained
+              it.next(nt, kt0, kt1);
+              kt = kt0;
+              ++seg;
+              mbar_wait(&tmem_empty[seg & 1], ((seg >> 1) & 1) ^ 1);
             }
-            umma_commit(&deq_empty[ds]);
-            if (sub == NSUB - 1) {
-              umma_commit(&act_empty[as]);
-              if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
+            d_tmem[j] = tbase + (seg & 1) * MT;
+            first[j] = kt > kt0 ? 1u : 0u;
+            last[j] = kt == kt1 - 1 ? (uint32_t)(seg & 1) + 1u : 0u;  // 0 / buffer + 1
+            ++kt;
+            slot[j] = (uint32_t)((cnt + j) % Cfg::A_STAGES);
+            const uint32_t ph = ((cnt + j) / Cfg::A_STAGES) & 1;
+            mbar_wait(&act_full[slot[j]], ph);
+            mbar_wait(&deq_full[slot[j]], ph);
+          }
+        }
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j < n) {
+              const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + slot[j] * Cfg::ACT_BYTES);
+              const uint32_t a_tmem = tbase + Cfg::A_COL0 + slot[j] * 64;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t b_desc =
+                    b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
+                umma_bf16_ts(d_tmem[j], a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first[j]);
+              }
+              if (last[j]) umma_commit(&tmem_full[last[j] - 1]);
             }
           }
-          __syncwarp();
+          umma_commit(&deq_empty[(cnt >> 1) % 3]);
         }
+        __syncwarp();
       }
-      ++seg;
+    } else {
+      SegIter it{u_begin, u_end, KT};
+      int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
+      while (it.next(nt, kt0, kt1)) {
+        const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
+        const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
+        long long tw = TRACE ? clock64() : 0;
+        mbar_wait(&tmem_empty[buf], tph ^ 1);
+        if (TRACE) w_acc += clock64() - tw;
+        tc_fence_after();
+        for (int kt = kt0; kt < kt1; ++kt, ++ucnt) {
+          const int as = ucnt % Cfg::ACT_STAGES;
+          const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
+          tw = TRACE ? clock64() : 0;
+          mbar_wait(&act_full[as], aph);
+          if (TRACE) w_act += clock64() - tw;
+          const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
+          const uint32_t first = (kt > kt0) ? 1u : 0u;
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
+            const int ds = cnt % Cfg::A_STAGES;
+            const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
+            const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
+            const uint32_t d_tmem = tbase + (buf * NSUB + sub) * MT;
+            tw = TRACE ? clock64() : 0;
+            mbar_wait(&deq_full[ds], dph);
+            if (TRACE) w_deq += clock64() - tw;
+            if (TRACE && cnt == 0 && lane == 0) W4_TRACE(4);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                // descriptor start-address field is in 16-byte units: advance by constants
+                const uint64_t b_desc =
+                    b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
+                umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first);
+              }
+              umma_commit(&deq_empty[ds]);
+              if (sub == NSUB - 1) {
+                if constexpr (VAR == 0) umma_commit(&act_empty[as]);
+                if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        ++seg;
+      }
     }
     if (lane == 0) W4_TRACE(5);
     if constexpr (TRACE) {
@@ -708,10 +779,20 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-template <int MT, int NSUB, bool TRACE>
+// B200_W4_VARIANT = 1 | 2: experimental MMA-loop variants of the kernel (see VAR above); only for
+// batches <= 64 rows with one weight tile per unit, everything else runs the default kernel
+static int w4_variant() {
+  static const int v = [] {
+    const char* e = getenv("B200_W4_VARIANT");
+    return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : 0;
+  }();
+  return v;
+}
+
+template <int MT, int NSUB, bool TRACE, int VAR = 0>
 static int launch_w4_kernel(const CUtensorMap& amap, const W4Params& p, cudaStream_t st) {
   using Cfg = W4Cfg<MT, NSUB>;
-  auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE>;
+  auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE, VAR>;
   B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)Cfg::SMEM));
   B200_PDL_LAUNCH_L(1, "w4a16_gemm", kern, (unsigned)p.plan.P, W4_THREADS, Cfg::SMEM, st, amap, p);
@@ -724,6 +805,8 @@ static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream
     if (p.plan.nsub_log2 == 1)
       return p.trace ? launch_w4_kernel<MT, 2, true>(amap, p, st)
                      : launch_w4_kernel<MT, 2, false>(amap, p, st);
+    if (!p.trace && w4_variant() == 1) return launch_w4_kernel<MT, 1, false, 1>(amap, p, st);
+    if (!p.trace && w4_variant() == 2) return launch_w4_kernel<MT, 1, false, 2>(amap, p, st);
   }
   return p.trace ? launch_w4_kernel<MT, 1, true>(amap, p, st)
                  : launch_w4_kernel<MT, 1, false>(amap, p, st);

@@ -24,7 +24,8 @@ __device__ __forceinline__ uint4 dq_word(uint32_t q, __nv_bfloat162 zmagic, __nv
   return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-// mode bit 0: dequant warps do the math, bit 1: dequant warps do the tcgen05.st, bit 2: MMA runs
+// mode bit 0: dequant warps do the math, bit 1: dequant warps do the tcgen05.st, bit 2: MMA runs,
+// bit 3: the MMA thread skips the per-group tcgen05.fence::after_thread_sync
 __global__ void __launch_bounds__(544, 1) k_mix(int tiles, int mode, int deq_warps, int depth, int every, long long* cyc) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t holder;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(544, 1) k_mix(int tiles, int mode, int deq_war
     const int D = depth > 0 ? depth : (depth < 0 ? -depth : 1);
     for (int g = 0; g < groups; ++g) {
       if (depth > 0 && g >= D) mbar_wait(&bars[g % D], ((g / D) - 1) & 1);
-      tc_fence_after();
+      if (!(mode & 8)) tc_fence_after();
       if (elect_one()) {
         for (int t = 0; t < every; ++t) {
           const int tile = g * every + t;
@@ -134,7 +135,10 @@ int main() {
   const int tiles = 960;
   struct { int mode, warps, depth, every; const char* name; } cases[] = {
       {4, 16, 0, 1, "MMA alone, no commits"},
+      {4 | 8, 16, 0, 1, "MMA alone, no commits, no tcgen05.fence"},
       {4, 16, -4, 1, "MMA alone, commit per tile, never waits"},
+      {4 | 8, 16, -4, 1, "MMA alone, commit per tile, no fence"},
+      {4, 16, -4, 2, "MMA alone, fence+commit per 2 tiles"},
       {4, 16, 4, 1, "MMA alone, commit+wait per tile (4 deep)"},
       {4, 16, 3, 2, "MMA alone, commit+wait per 2 tiles (3 deep)"},
       {4, 16, 2, 3, "MMA alone, commit+wait per 3 tiles (2 deep)"},
