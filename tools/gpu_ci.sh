@@ -25,6 +25,8 @@ fi
 if has trace; then
   timeout 300 python tools/w4_trace.py > $OUT/w4_trace.log 2>&1
   echo "trace rc=$?" | tee -a $OUT/summary.txt
+  B200_PDL=0 timeout 300 python tools/w4_trace.py >> $OUT/w4_trace.log 2>&1
+  echo "trace (B200_PDL=0) rc=$?" | tee -a $OUT/summary.txt
   cat $OUT/w4_trace.log >> $OUT/summary.txt
 fi
 

@@ -59,7 +59,51 @@ def run(K, N, M=64, g=128):
     torch.save(t, os.path.join(ROOT, "gpurun_out", f"w4_trace_{K}x{N}.pt"))
 
 
+def back_to_back(K, N, M=64, g=128, n_launch=6):
+    """%globaltimer view of consecutive GEMM launches over distinct weights (as in a decode step):
+    how long each grid lives, and the dead time between one grid's last CTA exit and the next
+    grid's first CTA entry (negative = the next grid started early under programmatic launch)."""
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    packs = []
+    for _ in range(n_launch):
+        qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // g, N // 8), generator=gen, device=DEV, dtype=torch.int64).to(torch.int32)
+        sc = (torch.randn(K // g, N, generator=gen, device=DEV).abs() * 0.01 + 1e-4).bfloat16()
+        packs.append(kernels.w4a16_prepack_awq(qw, qz, sc, g))
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    for pk in packs[:2]:
+        kernels.w4a16_gemm_splitk(a, pk, N, g)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    flush.zero_()
+    traces = [torch.zeros(1024 * 16, dtype=torch.int64, device=DEV) for _ in packs]
+    lib = _lib.load()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for pk, tr in zip(packs, traces):
+        lib.b200_debug_set_trace(tr.data_ptr())
+        kernels.w4a16_gemm_splitk(a, pk, N, g)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.b200_debug_set_trace(None)
+    ent, ext = [], []
+    for tr in traces:
+        t = tr.cpu().view(-1, 16)
+        t = t[t[:, 14] != 0]
+        ent.append((int(t[:, 14].min()), int(t[:, 14].max())))
+        ext.append((int(t[:, 15].min()), int(t[:, 15].max())))
+    print(f"== back to back, K={K} N={N} M={M}, B200_PDL={os.environ.get('B200_PDL', 'default')}: "
+          f"{n_launch} launches in {e0.elapsed_time(e1) * 1e3:.1f} us (eager, traced kernel)")
+    for i in range(n_launch):
+        gap = (ent[i][0] - ext[i - 1][1]) / 1e3 if i else float("nan")
+        print(f"  launch {i}: grid span {(ext[i][1] - ent[i][0]) / 1e3:6.2f} us, entries spread "
+              f"{(ent[i][1] - ent[i][0]) / 1e3:5.2f} us, gap after previous grid {gap:6.2f} us")
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for K, N in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
         run(K, N)
+    for K, N in [(4096, 4096), (4096, 28672)]:
+        back_to_back(K, N)
