@@ -198,3 +198,20 @@ def test_attention_stream_partition_invariants(heads, batch, max_q):
         need = max(plans.values())
         if need > 1:
             assert ws >= batch * max_q * H * need * (D + 1) * 4
+
+
+def test_step_timeline_summary_arithmetic():
+    """tools/step_timeline.py: coverage / gap / overlap arithmetic over kernel intervals."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "step_timeline", os.path.join(os.path.dirname(__file__), "..", "tools", "step_timeline.py"))
+    st = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(st)
+    ev = [("void b200::k1<(int)3>(int)", 0.0, 10.0), ("k2", 9.0, 5.0), ("void b200::k1<(int)3>(int)", 20.0, 4.0)]
+    rows, s = st.summarise(ev[::-1], 1)
+    assert rows[0] == ("k1<3>", 2, 14.0) and rows[1] == ("k2", 1, 5.0)
+    assert s["window_us"] == 24.0 and s["covered_us"] == 18.0 and s["overlap_us"] == 1.0
+    assert s["gap_us"] == 6.0 and s["n_gaps"] == 1 and s["gap_max_us"] == 6.0
+    assert "k1<3>" in st.render(rows, s, "t")
+    assert st.summarise([], 1) == ([], {})

@@ -118,6 +118,12 @@ if has occ; then
     echo "bench occ=$v rc=$? $(tail -1 $OUT/bench_occ$v.json | head -c 200)" | tee -a $OUT/summary.txt
   done
 fi
+if has timeline; then
+  # in-graph device timeline of the decode step (CUPTI via torch.profiler): shares, gaps, overlap
+  timeout 900 python tools/step_timeline.py > $OUT/step_timeline.log 2>&1
+  echo "timeline rc=$?" | tee -a $OUT/summary.txt
+  head -40 $OUT/step_timeline.log >> $OUT/summary.txt
+fi
 if has w4var; then
   # opt-in MMA-loop variants of the W4A16 GEMM (B200_W4_VARIANT=1|2): parity, then A/B bench
   for v in 1 2; do
