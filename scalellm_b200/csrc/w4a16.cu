@@ -321,16 +321,20 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // bytes pulled out of L2 per weight tile drop by NSUB (the kernel is L2-bandwidth bound on them:
 // every CTA re-reads the [MT x 128] activation tile of each of its k tiles).
 //
-// VAR (experiments on the MMA thread's per-tile cost, B200_W4_VARIANT; 0 = default).  With one
-// weight tile per unit the activation ring and the dequantised-weight ring have the same depth, so
-// stage == slot for every tile and one barrier can release both:
+// VAR (experiments on the MMA thread's per-tile cost, B200_W4_VARIANT; 0 = default; a bit mask).
+// With one weight tile per unit the activation ring and the dequantised-weight ring have the same
+// depth, so stage == slot for every tile and one barrier can release both:
 //   1: one tcgen05.commit per tile (the activation producer waits on the slot's deq_empty barrier)
 //   2: tiles are issued in aligned pairs: one tcgen05.fence + one commit per two tiles (pair
 //      barrier deq_empty[pair % 3]; both producers wait on it)
+//   4: three dequant groups instead of four (12 warps dequantise as fast as 16,
+//      tools/microbench/deq.cu, and the MMA warp then shares its scheduler with three of them);
+//      combines with 2 as 6
 template <int MT, int NSUB, bool TRACE, int VAR = 0>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
+  static_assert((VAR & 3) != 3 && VAR < 8, "VAR: 1 and 2 are alternatives");
   static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
                              Cfg::ACC_BUFS == 2 && !TRACE),
                 "variants need stage == slot");
@@ -407,7 +411,11 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt)
       for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
-        if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
+        if constexpr (VAR & 4) {
+          if (cnt % 3 != group) continue;  // group 3 (warps 12-15) takes nothing
+        } else {
+          if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
+        }
         const int rs = cnt % Cfg::RAW_STAGES;
         const int as = cnt % Cfg::A_STAGES;
         const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
@@ -447,7 +455,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
             tw = TRACE ? clock64() : 0;
-            if constexpr (VAR == 2) {
+            if constexpr (VAR & 2) {
               const int pr = cnt >> 1;
               mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
             } else {
@@ -505,9 +513,9 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          if constexpr (VAR == 0) {
+          if constexpr ((VAR & 3) == 0) {
             mbar_wait(&act_empty[as], aph ^ 1);
-          } else if constexpr (VAR == 1) {
+          } else if constexpr ((VAR & 3) == 1) {
             mbar_wait(&deq_empty[as], aph ^ 1);  // stage == slot: released by the slot's commit
           } else {
             const int pr = cnt >> 1;
@@ -534,7 +542,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
     long long w_act = 0, w_deq = 0, w_acc = 0;  // TRACE: cycles spent waiting per barrier kind
-    if constexpr (VAR == 2) {
+    if constexpr (VAR & 2) {
       // tiles in aligned pairs (cnt even): slots (cnt % 6, cnt % 6 + 1), pair barrier (cnt / 2) % 3
       SegIter it{u_begin, u_end, KT};
       const int total = u_end - u_begin;
@@ -620,7 +628,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
               }
               umma_commit(&deq_empty[ds]);
               if (sub == NSUB - 1) {
-                if constexpr (VAR == 0) umma_commit(&act_empty[as]);
+                if constexpr ((VAR & 3) == 0) umma_commit(&act_empty[as]);
                 if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
               }
             }
@@ -779,12 +787,13 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-// B200_W4_VARIANT = 1 | 2: experimental MMA-loop variants of the kernel (see VAR above); only for
+// B200_W4_VARIANT = 1 | 2 | 4 | 6: experimental variants of the kernel (see VAR above); only for
 // batches <= 64 rows with one weight tile per unit, everything else runs the default kernel
 static int w4_variant() {
   static const int v = [] {
     const char* e = getenv("B200_W4_VARIANT");
-    return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : 0;
+    const int v = (e && e[0] >= '0' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 6) ? v : 0;
   }();
   return v;
 }
@@ -805,8 +814,15 @@ static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream
     if (p.plan.nsub_log2 == 1)
       return p.trace ? launch_w4_kernel<MT, 2, true>(amap, p, st)
                      : launch_w4_kernel<MT, 2, false>(amap, p, st);
-    if (!p.trace && w4_variant() == 1) return launch_w4_kernel<MT, 1, false, 1>(amap, p, st);
-    if (!p.trace && w4_variant() == 2) return launch_w4_kernel<MT, 1, false, 2>(amap, p, st);
+    if (!p.trace) {
+      switch (w4_variant()) {
+        case 1: return launch_w4_kernel<MT, 1, false, 1>(amap, p, st);
+        case 2: return launch_w4_kernel<MT, 1, false, 2>(amap, p, st);
+        case 4: return launch_w4_kernel<MT, 1, false, 4>(amap, p, st);
+        case 6: return launch_w4_kernel<MT, 1, false, 6>(amap, p, st);
+        default: break;
+      }
+    }
   }
   return p.trace ? launch_w4_kernel<MT, 1, true>(amap, p, st)
                  : launch_w4_kernel<MT, 1, false>(amap, p, st);
