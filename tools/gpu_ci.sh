@@ -7,6 +7,10 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
 STAGES="${*:-tests probe smoke bench ncu}"
+# "round2" = everything that was staged after round 1's GPU budget ran out, in one call
+if [[ " $STAGES " == *" round2 "* ]]; then
+  STAGES="$STAGES tests smoke bench timeline trace micro w4var occ refk"
+fi
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 echo "stages: $STAGES" | tee $OUT/summary.txt
 has() { [[ " $STAGES " == *" $1 "* ]]; }
