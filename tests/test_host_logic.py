@@ -215,3 +215,28 @@ def test_step_timeline_summary_arithmetic():
     assert s["gap_us"] == 6.0 and s["n_gaps"] == 1 and s["gap_max_us"] == 6.0
     assert "k1<3>" in st.render(rows, s, "t")
     assert st.summarise([], 1) == ([], {})
+
+
+def test_w4a16_barrier_protocol_model():
+    """tools/w4_protocol_sim.py: the GEMM's ring / barrier protocol (default and the
+    B200_W4_VARIANT experiments) under random partitions and schedules — no stale operand, no
+    overwrite under a queued MMA, no accumulator reuse before the epilogue, no deadlock."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "w4_protocol_sim", os.path.join(os.path.dirname(__file__), "..", "tools", "w4_protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    assert sim.check(trials=150, seed=1)
+    # the model must notice a broken protocol: drop the activation producer's wait
+    def racing_act_producer(self):
+        for cnt in range(self.total):
+            self.inflight.append(("act", cnt % sim.STAGES, cnt))
+            yield None
+    good = sim.Sim.act_producer
+    sim.Sim.act_producer = racing_act_producer
+    try:
+        with pytest.raises(AssertionError):
+            sim.check(variants=(0, 1), trials=100, seed=2)
+    finally:
+        sim.Sim.act_producer = good
