@@ -19,4 +19,26 @@ if ls $G/micro_*.log > /dev/null 2>&1; then
 fi
 [ -s $G/w4_trace.log ] && { echo "# $R: device-side clock64 trace of w4a16_gemm_kernel (tools/w4_trace.py)"; echo '```'; cat $G/w4_trace.log; echo '```'; } > $P/${R}_w4_trace.md
 [ -s $G/attn_bench.log ] && { echo "# $R: attention kernel-only timings (tools/attn_bench.py)"; echo '```'; cat $G/attn_bench.log; echo '```'; } > $P/${R}_attn_bench.md
+[ -s $G/step_timeline.md ] && cp $G/step_timeline.md $P/${R}_step_timeline.md
+# A/B runs of the opt-in variants: one line per run (value, ms/step, GEMM launch times)
+if ls $G/bench_w4var*.json $G/bench_occ*.json > /dev/null 2>&1; then
+  python - $G $P/${R}_variants.md "$R" <<'PY'
+import glob, json, os, sys
+g, out, r = sys.argv[1:4]
+rows = []
+for f in sorted(glob.glob(os.path.join(g, "bench_w4var*.json")) + glob.glob(os.path.join(g, "bench_occ*.json"))):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception:
+        continue
+    gm = (d.get("roofline_w4a16_gemm") or {}).get("per_proj") or {}
+    rows.append((os.path.basename(f), d["value"], d["ms_per_step"], (d.get("roofline") or {}).get("us_per_launch"),
+                 " / ".join(f"{v['us']:.1f}" for v in gm.values())))
+with open(out, "w") as fh:
+    fh.write(f"# {r}: A/B bench runs of the opt-in kernel variants (same box, back to back)\n\n"
+             "| run | tokens/s | ms/step | attention us/launch | GEMM us (qkv / o / gate_up / down) |\n|---|---:|---:|---:|---|\n")
+    for n, v, ms, au, gm in rows:
+        fh.write(f"| `{n}` | {v:.0f} | {ms:.3f} | {au if au is None else round(au, 1)} | {gm} |\n")
+PY
+fi
 ls -la $P
