@@ -21,7 +21,7 @@ fi
 [ -s $G/attn_bench.log ] && { echo "# $R: attention kernel-only timings (tools/attn_bench.py)"; echo '```'; cat $G/attn_bench.log; echo '```'; } > $P/${R}_attn_bench.md
 [ -s $G/step_timeline.md ] && cp $G/step_timeline.md $P/${R}_step_timeline.md
 # A/B runs of the opt-in variants: one line per run (value, ms/step, GEMM launch times)
-if ls $G/bench_w4var*.json $G/bench_occ*.json > /dev/null 2>&1; then
+if ls $G/bench_w4var*.json $G/bench_occ*.json 2> /dev/null | grep -q .; then
   python - $G $P/${R}_variants.md "$R" <<'PY'
 import glob, json, os, sys
 g, out, r = sys.argv[1:4]
