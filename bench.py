@@ -204,6 +204,29 @@ def cpu_decode_sample(a, budget_s: float = 30.0, seed: int = 0):
     return v, secs, c.torch.get_num_threads(), n_layers, c.B
 
 
+def cpu_config0(runs: int = 3, seed: int = 0):
+    """BASELINE.json configs[0] — the reference's only CPU-runnable case (gpt2-124M fp32, batch 1,
+    8-token prompt, 32 new tokens, greedy; examples/cpu_offline_inference.py) restated in
+    oracle/gpt2.py with random-init weights, timed on this box's host cores: median of `runs`.
+    A reported baseline beside the GPU numbers, not a target."""
+    try:
+        import torch
+        from oracle import gpt2
+        threads = torch.get_num_threads()
+        torch.set_num_threads(min(os.cpu_count() or 1, 16))    # small matrices: more threads only add sync
+        m = gpt2.init_gpt2(seed)
+        prompt = torch.randint(0, 50257, (8,), generator=torch.Generator().manual_seed(seed))
+        res = sorted((gpt2.generate(m, prompt, 32) for _ in range(runs)), key=lambda r: r["decode_tok_s"])
+        r = res[len(res) // 2]
+        out = {"workload": "gpt2-124M fp32 offline generate on CPU, batch 1, 8-token prompt, 32 new tokens",
+               "decode_tokens_per_s": r["decode_tok_s"], "ttft_ms": 1e3 * r["ttft_s"],
+               "cores": torch.get_num_threads(), "runs": runs, "kind": "port"}
+        torch.set_num_threads(threads)
+        return out
+    except Exception as e:  # noqa: BLE001  (a side figure: never cost the bench line)
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(a, rank):
     if rank != 0:
         return
@@ -229,7 +252,7 @@ def run_reference(a, rank):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic", "config": {"workload": workload_name(a, 1).replace("TP=1", "CPU")},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": sample},
+                            "sample": sample, "config0": cpu_config0()},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -384,7 +407,8 @@ def run_b200(a, rank, world, local_rank):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_seq} of the {a.batch} sequences through {n_layers} passes of an oracle decoder layer + "
                          f"lm_head at the full kv_len ({secs:.1f} s of CPU work on {cores} threads, the "
-                         "fastest of the thread counts tried), time extrapolated to 32 layers"}
+                         "fastest of the thread counts tried), time extrapolated to 32 layers",
+               "config0": cpu_config0()}
 
     kv_gb = 2 * B * S * max(1, args.n_kv_heads // world) * args.head_dim * 2 * args.n_layers / 1e9
     wbytes = 0.5 + 2.5 / 128 if a.quant != "none" else 2.0      # int4 + scales + zeros @ g128
