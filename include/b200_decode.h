@@ -317,9 +317,24 @@ B200_API int b200_ar_create(b200_ar_comm** comm, int rank, int world_size,
                             int64_t max_bytes, void* handle_out /*[B200_AR_HANDLE_BYTES]*/);
 B200_API int b200_ar_open_peers(b200_ar_comm* comm,
                                 const void* all_handles /*[world][B200_AR_HANDLE_BYTES]*/);
+/* All ranks in ONE process, one thread per GPU — the reference engine's model:
+ * ProcessGroup::create_process_groups -> ncclCommInitAll (process_group.cpp:98-118).  Creates
+ * comms[r] on devices[r] for r = 0..world_size-1 and maps every peer's region through CUDA peer
+ * access (no IPC, no handle exchange); all or nothing.  Each communicator is then used from the
+ * thread that has its device current, exactly like the IPC form. */
+B200_API int b200_ar_create_all(b200_ar_comm** comms /*[world_size] out*/, const int* devices,
+                                int world_size, int64_t max_bytes);
 /* In-place sum of data[count] (bf16/fp16/fp32) over all ranks, on `stream`. */
 B200_API int b200_ar_allreduce(b200_ar_comm* comm, void* data, int64_t count,
                                int dtype, b200_stream_t stream);
+/* All-gather along the last dimension: in [rows, row_bytes] per rank -> out [rows, world *
+ * row_bytes] with rank r's row at byte offset r * row_bytes — what
+ * gather_from_model_parallel_region builds with allgather + cat(dim=-1)
+ * (src/model_parallel/model_parallel.cpp:13-31).  Bit exact; rows * row_bytes <= max_bytes,
+ * row_bytes % 16 == 0; shares the communicator's epoch with the all-reduces (every rank must
+ * issue the same sequence of collectives). */
+B200_API int b200_ar_allgather(b200_ar_comm* comm, void* out, const void* in, int64_t rows,
+                               int64_t row_bytes, b200_stream_t stream);
 /* Same reduction, but this rank's input is the producing GEMM's stream-K partials
  * [splits][count] fp32 (b200_w4a16_gemm_splitk of a [gemm_k, n] weight, count = rows * n): the
  * copy-in stage sums each tile's slots and rounds once, so the row-parallel GEMM needs no

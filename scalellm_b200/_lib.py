@@ -70,7 +70,9 @@ SIGNATURES = {
     "b200_debug_set_trace": (None, [_vp]),
     "b200_ar_create": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp]),
     "b200_ar_open_peers": (_int, [_vp, _vp]),
+    "b200_ar_create_all": (_int, [C.POINTER(_vp), C.POINTER(C.c_int), _int, _i64]),
     "b200_ar_allreduce": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "b200_ar_allgather": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "b200_ar_allreduce_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_allreduce_splitk_norm": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _vp, _i64, _i64, _f32, _int, _vp]),
     "b200_ar_destroy": (_int, [_vp]),

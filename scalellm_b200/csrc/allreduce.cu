@@ -4,7 +4,10 @@
 // for the latency-bound <= 1 MiB row-parallel reductions of the decode step
 // (2 per layer: after o_proj and down_proj).
 //
-// One process per GPU.  Each rank owns ONE cudaMalloc'ed symmetric region
+// One process per GPU (b200_ar_create + b200_ar_open_peers, CUDA IPC), or all ranks in one
+// process with one thread per GPU like the reference's engine (b200_ar_create_all, the
+// counterpart of its ncclCommInitAll, process_group.cpp:98-118: peer access instead of IPC).
+// Each rank owns ONE cudaMalloc'ed symmetric region
 //   [ data buffer, parity 0 | data buffer, parity 1 | flags[world][AR_MAX_BLOCKS] | epoch | done ]
 // exported through CUDA IPC and mapped by every peer (NVSwitch gives every pair
 // full NVLink bandwidth).  A call with epoch e:
@@ -44,6 +47,7 @@ struct b200_ar_comm {
   uint8_t* local = nullptr;                 // base of the local symmetric region
   uint8_t* peer[b200::AR_MAX_WORLD] = {};   // mapped bases, peer[rank] == local
   bool opened = false;
+  bool ipc = true;   // peers mapped through CUDA IPC (one process per GPU); false: same process
 };
 
 namespace b200 {
@@ -226,11 +230,95 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   }
 }
 
+// All-gather with the same staging / flag protocol (and the same epoch counter, so all-reduces and
+// all-gathers of one communicator may be mixed freely as long as every rank issues the same
+// sequence): rank r's input [rows][cols_v vectors] lands in out[row][r * cols_v + c] on every
+// rank — the layout gather_from_model_parallel_region builds with allgather + cat(dim=-1)
+// (model_parallel.cpp:13-31), without the temporaries.  Pure 16-byte copies: bit exact.
+__global__ void __launch_bounds__(AR_THREADS) allgather_oneshot_kernel(ArDevPtrs ptrs,
+                                                                      const uint4* __restrict__ in,
+                                                                      uint4* __restrict__ out,
+                                                                      int64_t nvec, int64_t cols_v,
+                                                                      int rank, int world,
+                                                                      int64_t max_bytes) {
+  uint8_t* local = ptrs.base[rank];
+  uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
+  uint32_t* done_ptr = epoch_ptr + 1;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
+  const int64_t buf_off = (e & 1) ? max_bytes : 0;
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = (int64_t)blockIdx.x * per;
+  const int64_t v1 = v0 + per < nvec ? v0 + per : nvec;
+
+  uint4* mine = reinterpret_cast<uint4*>(local + buf_off);
+  for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) mine[i] = in[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int r = threadIdx.x;
+    uint32_t* their_flags = reinterpret_cast<uint32_t*>(ptrs.base[r] + ar_flags_off(max_bytes));
+    st_release_sys(&their_flags[rank * AR_MAX_BLOCKS + blockIdx.x], e);
+    const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(local + ar_flags_off(max_bytes));
+    while ((int32_t)(ld_acquire_sys(&my_flags[r * AR_MAX_BLOCKS + blockIdx.x]) - e) < 0) {
+    }
+  }
+  __syncthreads();
+  for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
+    const int64_t row = i / cols_v, c = i - row * cols_v;
+    for (int r = 0; r < world; ++r) {
+      const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
+      out[(row * world + r) * cols_v + c] = ld_volatile_v4(pb + i);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t d = atomicAdd(done_ptr, 1u);
+    if (d == gridDim.x - 1) {
+      *done_ptr = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = e;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" {
+
+int b200_ar_allgather(b200_ar_comm* c, void* out, const void* in, int64_t rows, int64_t row_bytes,
+                      b200_stream_t stream) {
+  B200_CHECK_ARG(c && out && in, "ar_allgather: null pointer");
+  B200_CHECK_ARG(rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0 && is_aligned(out, 16) &&
+                     is_aligned(in, 16),
+                 "ar_allgather: rows of a multiple of 16 bytes, 16-byte aligned buffers");
+  if (rows == 0) return B200_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (c->world == 1) {
+    if (out != in)
+      B200_CUDA_OK(cudaMemcpyAsync(out, in, (size_t)(rows * row_bytes), cudaMemcpyDeviceToDevice, st));
+    return B200_OK;
+  }
+  B200_CHECK_ARG(c->opened, "ar_allgather: peers not opened");
+  B200_CHECK_ARG(out != in, "ar_allgather: out must not alias in");
+  const int64_t bytes = rows * row_bytes;
+  if (bytes > c->max_bytes)
+    return set_error(B200_ERR_WORKSPACE, "ar_allgather: %lld B exceeds the %lld B symmetric buffer",
+                     (long long)bytes, (long long)c->max_bytes);
+  const int64_t nvec = bytes / 16;
+  int blocks = (int)((nvec + 2 * AR_THREADS - 1) / (2 * AR_THREADS));
+  if (blocks < 1) blocks = 1;
+  if (blocks > AR_MAX_BLOCKS) blocks = AR_MAX_BLOCKS;
+  ArDevPtrs ptrs{};
+  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
+  allgather_oneshot_kernel<<<blocks, AR_THREADS, 0, st>>>(
+      ptrs, static_cast<const uint4*>(in), static_cast<uint4*>(out), nvec, row_bytes / 16, c->rank,
+      c->world, c->max_bytes);
+  B200_LAUNCH_OK("allgather_oneshot");
+  return B200_OK;
+}
 
 int b200_ar_create(b200_ar_comm** comm, int rank, int world_size, int64_t max_bytes,
                    void* handle_out) {
@@ -275,6 +363,76 @@ int b200_ar_open_peers(b200_ar_comm* c, const void* all_handles) {
   }
   c->opened = true;
   return B200_OK;
+}
+
+static int ar_alloc_region(b200_ar_comm* c) {
+  void* p = nullptr;
+  B200_CUDA_OK(cudaMalloc(&p, (size_t)ar_region_bytes(c->max_bytes)));
+  c->local = static_cast<uint8_t*>(p);
+  c->peer[c->rank] = c->local;
+  B200_CUDA_OK(cudaMemset(p, 0, (size_t)ar_region_bytes(c->max_bytes)));
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  return B200_OK;
+}
+
+static int ar_create_all(b200_ar_comm** comms, const int* devices, int world, int64_t max_bytes) {
+  for (int r = 0; r < world; ++r) {
+    B200_CUDA_OK(cudaSetDevice(devices[r]));
+    auto* c = comms[r] = new b200_ar_comm();
+    c->rank = r;
+    c->world = world;
+    c->max_bytes = max_bytes;
+    c->device = devices[r];
+    c->ipc = false;
+    const int rc = ar_alloc_region(c);
+    if (rc != B200_OK) return rc;
+  }
+  for (int r = 0; r < world; ++r) {
+    B200_CUDA_OK(cudaSetDevice(devices[r]));
+    for (int q = 0; q < world; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      B200_CUDA_OK(cudaDeviceCanAccessPeer(&can, devices[r], devices[q]));
+      if (!can)
+        return set_error(B200_ERR_UNSUPPORTED, "ar_create_all: device %d cannot access device %d",
+                         devices[r], devices[q]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled)
+        (void)cudaGetLastError();  // enabled earlier (by torch or a previous group): fine
+      else
+        B200_CUDA_OK(e);
+      comms[r]->peer[q] = comms[q]->local;
+    }
+    comms[r]->opened = true;
+  }
+  return B200_OK;
+}
+
+int b200_ar_create_all(b200_ar_comm** comms, const int* devices, int world_size, int64_t max_bytes) {
+  B200_CHECK_ARG(comms && devices, "ar_create_all: null pointer");
+  B200_CHECK_ARG(world_size >= 1 && world_size <= AR_MAX_WORLD, "ar_create_all: world %d unsupported (max %d)",
+                 world_size, AR_MAX_WORLD);
+  B200_CHECK_ARG(max_bytes > 0 && max_bytes % 16 == 0, "ar_create_all: max_bytes must be a multiple of 16");
+  for (int r = 0; r < world_size; ++r) {
+    comms[r] = nullptr;
+    for (int q = 0; q < r; ++q)
+      B200_CHECK_ARG(devices[q] != devices[r], "ar_create_all: device %d listed twice", devices[r]);
+  }
+  int prev = 0;
+  B200_CUDA_OK(cudaGetDevice(&prev));
+  const int rc = ar_create_all(comms, devices, world_size, max_bytes);
+  if (rc != B200_OK) {  // all or nothing
+    for (int r = 0; r < world_size; ++r) {
+      if (comms[r]) {
+        cudaSetDevice(comms[r]->device);
+        if (comms[r]->local) cudaFree(comms[r]->local);
+        delete comms[r];
+        comms[r] = nullptr;
+      }
+    }
+  }
+  cudaSetDevice(prev);
+  return rc;
 }
 
 static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, const float* partials,
@@ -385,9 +543,17 @@ int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, co
 
 int b200_ar_destroy(b200_ar_comm* c) {
   if (!c) return B200_OK;
-  for (int r = 0; r < c->world; ++r)
-    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
-  if (c->local) cudaFree(c->local);
+  if (c->ipc) {
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->local) cudaFree(c->local);
+  } else if (c->local) {  // same-process group: the region lives on the communicator's own device
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    cudaFree(c->local);
+    cudaSetDevice(prev);
+  }
   delete c;
   return B200_OK;
 }

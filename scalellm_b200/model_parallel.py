@@ -13,6 +13,7 @@ gloo (tests/test_tp_gloo.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -27,10 +28,16 @@ class ProcessGroup:
     """ProcessGroup interface (src/model_parallel/process_group.h:10-60) over torch.distributed."""
 
     def __init__(self, rank: int, world_size: int, device: torch.device,
-                 group: Optional[dist.ProcessGroup] = None, nvlink_max_bytes: int = 1 << 20):
+                 group: Optional[dist.ProcessGroup] = None, nvlink_max_bytes: int = 1 << 20,
+                 gather_max_bytes: int = 16 << 20):
         self._rank, self._world, self._device, self._group = rank, world_size, device, group
         self._comm = None
-        self._nvlink_max_bytes = nvlink_max_bytes
+        self._nvlink_max_bytes = nvlink_max_bytes      # one-shot all-reduce: latency-bound sizes only
+        # B200_AR_GATHER=1: all-gathers go through the peer-memory kernel too (opt-in until it
+        # has run on a multi-GPU box); its messages may be larger (a one-shot gather moves no
+        # more bytes than a ring), so the symmetric buffer is sized for them
+        self._gather_max_bytes = gather_max_bytes if os.environ.get("B200_AR_GATHER") == "1" else 0
+        self._buffer_bytes = max(nvlink_max_bytes, self._gather_max_bytes)
         if device.type == "cuda" and world_size > 1:
             self._init_nvlink()
 
@@ -51,7 +58,7 @@ class ProcessGroup:
         handle = (C.c_uint8 * _lib.AR_HANDLE_BYTES)()
         with torch.cuda.device(self._device):
             check(lib.b200_ar_create(C.byref(comm), self._rank, self._world,
-                                     self._nvlink_max_bytes, handle))
+                                     self._buffer_bytes, handle))
         mine = torch.tensor(list(handle), dtype=torch.uint8)
         if dist.get_backend(self._group) == "nccl":
             mine = mine.to(self._device)
@@ -124,6 +131,22 @@ class ProcessGroup:
             return
         dist.all_gather(outputs, input.contiguous(), group=self._group)
 
+    def allgather_lastdim(self, input: torch.Tensor) -> Optional[torch.Tensor]:
+        """cat(all-gather(input), dim=-1) in one launch over peer memory (bit exact), or None when
+        the fast path does not apply (the caller then uses allgather + cat)."""
+        if self._comm is None or self._gather_max_bytes == 0 or not input.is_cuda:
+            return None
+        x = input.contiguous()
+        row_bytes = x.size(-1) * x.element_size()
+        nbytes = x.numel() * x.element_size()
+        if nbytes == 0 or row_bytes % 16 or nbytes > self._gather_max_bytes or x.data_ptr() % 16:
+            return None
+        rows = x.numel() // x.size(-1)
+        out = torch.empty((*x.shape[:-1], x.size(-1) * self._world), dtype=x.dtype, device=x.device)
+        check(_lib.load().b200_ar_allgather(self._comm, out.data_ptr(), x.data_ptr(), rows, row_bytes,
+                                            torch.cuda.current_stream().cuda_stream))
+        return out
+
     def close(self) -> None:
         if self._comm is not None:
             _lib.load().b200_ar_destroy(self._comm)
@@ -142,6 +165,11 @@ def gather_from_model_parallel_region(input: torch.Tensor, pa: ParallelArgs) -> 
     """model_parallel.cpp:13-31: all-gather then cat on the last dim."""
     if pa.world_size == 1:
         return input
+    fast = getattr(pa.process_group, "allgather_lastdim", None)
+    if fast is not None:
+        out = fast(input)
+        if out is not None:
+            return out
     outs = [torch.empty_like(input) for _ in range(pa.world_size)]
     pa.process_group.allgather(input, outs)
     return torch.cat(outs, dim=-1).contiguous()

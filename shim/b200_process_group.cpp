@@ -1,0 +1,122 @@
+// b200_process_group.cpp — see b200_process_group.h.  Host plumbing only; the collectives are
+// csrc/allreduce.cu behind the C ABI.
+#include "b200_process_group.h"
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "../include/b200_decode.h"
+
+namespace llm {
+namespace {
+
+int dtype_code(const torch::Tensor& t) {
+  switch (t.scalar_type()) {
+    case torch::kBFloat16: return B200_BF16;
+    case torch::kHalf: return B200_FP16;
+    case torch::kFloat: return B200_FP32;
+    default: TORCH_CHECK(false, "ProcessGroupB200: unsupported dtype ", t.scalar_type());
+  }
+}
+
+void ok(int rc, const char* what) {
+  TORCH_CHECK(rc == B200_OK, "b200 ", what, " failed (", rc, "): ", b200_last_error());
+}
+
+}  // namespace
+
+std::vector<std::unique_ptr<ProcessGroup>> ProcessGroup::create_process_groups(
+    const std::vector<torch::Device>& devices) {
+  TORCH_CHECK(!devices.empty(), "devices should not be empty");
+  const int world = static_cast<int>(devices.size());
+  std::vector<int> idx;
+  for (const auto& d : devices) {
+    TORCH_CHECK(d.is_cuda(), "device should be cuda device");
+    idx.push_back(d.index());
+  }
+  std::vector<b200_ar_comm*> comms(world, nullptr);
+  ok(b200_ar_create_all(comms.data(), idx.data(), world, ProcessGroupB200::kMaxBytes),
+     "ar_create_all");
+  std::vector<std::unique_ptr<ProcessGroup>> groups;
+  for (int r = 0; r < world; ++r)
+    groups.emplace_back(std::make_unique<ProcessGroupB200>(r, world, devices[r], comms[r]));
+  return groups;
+}
+
+ProcessGroupB200::~ProcessGroupB200() { b200_ar_destroy(comm_); }
+
+void ProcessGroupB200::allreduce(torch::Tensor& input) const {
+  TORCH_CHECK(input.device() == device(), "input should be on the same device as the process group");
+  if (world_size() == 1 || input.numel() == 0) return;
+  TORCH_CHECK(input.is_contiguous(), "ProcessGroupB200::allreduce: contiguous tensors only");
+  c10::cuda::CUDAGuard guard(device());
+  ok(b200_ar_allreduce(comm_, input.data_ptr(), input.numel(), dtype_code(input),
+                       at::cuda::getCurrentCUDAStream().stream()),
+     "ar_allreduce");
+}
+
+torch::Tensor ProcessGroupB200::allgather_lastdim(const torch::Tensor& input) const {
+  TORCH_CHECK(input.device() == device(), "input should be on the same device as the process group");
+  const auto x = input.contiguous();
+  auto sizes = x.sizes().vec();
+  TORCH_CHECK(!sizes.empty(), "allgather_lastdim: needs at least one dimension");
+  const int64_t cols = sizes.back();
+  sizes.back() = cols * world_size();
+  auto out = torch::empty(sizes, x.options());
+  if (x.numel() == 0) return out;
+  c10::cuda::CUDAGuard guard(device());
+  ok(b200_ar_allgather(comm_, out.data_ptr(), x.const_data_ptr(), x.numel() / cols,
+                       cols * static_cast<int64_t>(x.element_size()),
+                       at::cuda::getCurrentCUDAStream().stream()),
+     "ar_allgather");
+  return out;
+}
+
+void ProcessGroupB200::allgather(const torch::Tensor& input, torch::Tensor& outputs) const {
+  // cat along dim 0 == "last dim" gather of the flattened tensor seen as one row
+  TORCH_CHECK(outputs.is_contiguous() && outputs.numel() == input.numel() * world_size() &&
+                  outputs.scalar_type() == input.scalar_type(),
+              "allgather: outputs must be contiguous with world_size * input.numel() elements");
+  const auto x = input.contiguous();
+  if (x.numel() == 0) return;
+  c10::cuda::CUDAGuard guard(device());
+  ok(b200_ar_allgather(comm_, outputs.data_ptr(), x.const_data_ptr(), 1,
+                       x.numel() * static_cast<int64_t>(x.element_size()),
+                       at::cuda::getCurrentCUDAStream().stream()),
+     "ar_allgather");
+}
+
+void ProcessGroupB200::allgather(const torch::Tensor& input,
+                                 std::vector<torch::Tensor>& outputs) const {
+  TORCH_CHECK(static_cast<int>(outputs.size()) == world_size(),
+              "outputs should have the same size as world_size");
+  auto flat = torch::empty({world_size(), input.numel()}, input.options());
+  allgather(input, flat);
+  for (int r = 0; r < world_size(); ++r) outputs[r].copy_(flat[r].view_as(input));
+}
+
+torch::Tensor gather_from_model_parallel_region(const torch::Tensor& input, const ParallelArgs& pa) {
+  if (pa.world_size() == 1) return input;
+  auto* pg = dynamic_cast<ProcessGroupB200*>(pa.process_group());
+  if (pg != nullptr) return pg->allgather_lastdim(input);
+  std::vector<torch::Tensor> parts;
+  for (int r = 0; r < pa.world_size(); ++r) parts.push_back(torch::empty_like(input));
+  pa.process_group()->allgather(input, parts);
+  return torch::cat(parts, /*dim=*/-1).contiguous();
+}
+
+torch::Tensor reduce_from_model_parallel_region(torch::Tensor input, const ParallelArgs& pa) {
+  if (pa.world_size() == 1) return input;
+  pa.process_group()->allreduce(input);
+  return input;
+}
+
+torch::Tensor scatter_to_model_parallel_region(const torch::Tensor& input, const ParallelArgs& pa) {
+  if (pa.world_size() == 1) return input;
+  const int64_t last = input.size(-1);
+  TORCH_CHECK(last % pa.world_size() == 0, "last_dim_size ", last, " not divisible by world_size ",
+              pa.world_size());
+  return input.split(last / pa.world_size(), /*dim=*/-1)[pa.rank()];
+}
+
+}  // namespace llm

@@ -4,6 +4,7 @@
 
 #include "b200_kernels.h"
 #include "b200_layers.h"
+#include "b200_process_group.h"
 
 PYBIND11_MODULE(_b200_shim, m) {
   m.def("rms_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w, double eps) {
@@ -93,4 +94,33 @@ PYBIND11_MODULE(_b200_shim, m) {
              p.cu_block_lens = blk_cu;
              return self.forward(tokens, positions, p);
            });
+
+  // ---- tensor-parallel plumbing in the reference's threading model (shim/b200_process_group.h) --
+  py::class_<llm::ProcessGroup>(m, "ProcessGroup")
+      .def("rank", &llm::ProcessGroup::rank)
+      .def("world_size", &llm::ProcessGroup::world_size)
+      .def("allreduce", [](const llm::ProcessGroup& self, torch::Tensor t) { self.allreduce(t); })
+      .def("allgather",
+           [](const llm::ProcessGroup& self, torch::Tensor in, std::vector<torch::Tensor> outs) {
+             self.allgather(in, outs);
+           })
+      .def("gather_from_model_parallel_region",
+           [](llm::ProcessGroup& self, torch::Tensor in) {
+             return llm::gather_from_model_parallel_region(
+                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+           })
+      .def("reduce_from_model_parallel_region",
+           [](llm::ProcessGroup& self, torch::Tensor in) {
+             return llm::reduce_from_model_parallel_region(
+                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+           })
+      .def("scatter_to_model_parallel_region", [](llm::ProcessGroup& self, torch::Tensor in) {
+        return llm::scatter_to_model_parallel_region(
+            in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+      });
+  m.def("create_process_groups", [](const std::vector<int>& device_indices) {
+    std::vector<torch::Device> devices;
+    for (int i : device_indices) devices.emplace_back(torch::kCUDA, static_cast<c10::DeviceIndex>(i));
+    return llm::ProcessGroup::create_process_groups(devices);
+  });
 }

@@ -58,6 +58,14 @@ def test_argument_validation_without_gpu():
                                     4096, 128, 1024, 128, 7, 1, 16, 0.1, 0.0, -1, None, 0, 0, None)
     assert rc == -1 and b"power of two" in lib.b200_last_error()
     assert lib.b200_paged_attn_workspace_bytes(64, 1, 2048, 32, 8, 128) > 0
+    # same-process communicator group (ncclCommInitAll counterpart): checked before any CUDA call
+    import ctypes as C
+    comms = (C.c_void_p * 2)()
+    devs = (C.c_int * 2)(0, 0)
+    assert lib.b200_ar_create_all(comms, devs, 2, 1 << 20) == -1 and b"twice" in lib.b200_last_error()
+    assert lib.b200_ar_create_all(comms, devs, 9, 1 << 20) == -1
+    assert lib.b200_ar_create_all(comms, devs, 1, 24) == -1
+    assert lib.b200_ar_create_all(None, devs, 1, 1 << 20) == -1
 
 
 def test_kernels_reject_cpu_tensors():

@@ -72,3 +72,14 @@ def test_shim_matches_ctypes_path():
     kernels.paged_kv_varlen_mha(out1, *args)
     m.paged_kv_varlen_mha(out2, *args)
     assert torch.equal(out1, out2)
+
+
+def test_process_group_bindings_fail_loudly_without_gpu():
+    """The C++ ProcessGroup plumbing (shim/b200_process_group) is part of the shim; creating the
+    communicators needs GPUs and must raise, not abort, without them."""
+    import torch
+    shim = load_shim()
+    assert hasattr(shim, "ProcessGroup") and hasattr(shim, "create_process_groups")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="ar_create_all"):
+            shim.create_process_groups([0, 1])
