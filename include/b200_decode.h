@@ -304,11 +304,12 @@ B200_API int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t
  *     replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
  *     for the <= 1 MiB row-parallel reductions of the decode step.
  *
- *     One communicator per GPU (one process per GPU here; one thread per GPU in
- *     the reference).  Setup: every rank calls b200_ar_create (allocates its
- *     symmetric buffer + flags and returns an IPC handle blob), exchanges the
- *     blobs out of band (torch.distributed all_gather in this repo), then calls
- *     b200_ar_open_peers with all ranks' blobs in rank order.
+ *     One communicator per GPU.  One process per GPU: every rank calls
+ *     b200_ar_create (allocates its symmetric buffer + flags and returns an IPC
+ *     handle blob), exchanges the blobs out of band (torch.distributed
+ *     all_gather in this repo), then calls b200_ar_open_peers with all ranks'
+ *     blobs in rank order.  All ranks in one process, one thread per GPU (the
+ *     reference engine): b200_ar_create_all.
  * ------------------------------------------------------------------------ */
 typedef struct b200_ar_comm b200_ar_comm;
 #define B200_AR_HANDLE_BYTES 128
