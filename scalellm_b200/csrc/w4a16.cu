@@ -330,11 +330,14 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 //   4: three dequant groups instead of four (12 warps dequantise as fast as 16,
 //      tools/microbench/deq.cu, and the MMA warp then shares its scheduler with three of them);
 //      combines with 2 as 6
+//   8: one "full" barrier per stage: the activation TMA completes on the slot's deq_full barrier
+//      (4 dequant arrivals + the producer's expect_tx arrival + the bytes), so the MMA thread
+//      waits once per tile instead of twice; combines with 2 (10) and 2 + 4 (14)
 template <int MT, int NSUB, bool TRACE, int VAR = 0>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
-  static_assert((VAR & 3) != 3 && VAR < 8, "VAR: 1 and 2 are alternatives");
+  static_assert((VAR & 3) != 3 && VAR < 16, "VAR: 1 and 2 are alternatives");
   static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
                              Cfg::ACC_BUFS == 2 && !TRACE),
                 "variants need stage == slot");
@@ -373,7 +376,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       mbar_init(&act_empty[i], 1);
     }
     for (int i = 0; i < Cfg::A_STAGES; ++i) {
-      mbar_init(&deq_full[i], 4);
+      mbar_init(&deq_full[i], (VAR & 8) ? 5 : 4);
       mbar_init(&deq_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -521,10 +524,11 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             const int pr = cnt >> 1;
             mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
           }
-          mbar_arrive_expect_tx(&act_full[as], (uint32_t)Cfg::ACT_BYTES);
+          uint64_t* full = (VAR & 8) ? &deq_full[as] : &act_full[as];
+          mbar_arrive_expect_tx(full, (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
-          tma_load_2d(dst, &amap, &act_full[as], kt * 128, 0);
-          tma_load_2d(dst + Cfg::ACT_ATOM, &amap, &act_full[as], kt * 128 + 64, 0);
+          tma_load_2d(dst, &amap, full, kt * 128, 0);
+          tma_load_2d(dst + Cfg::ACT_ATOM, &amap, full, kt * 128 + 64, 0);
         }
       }
     }
@@ -565,7 +569,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
             ++kt;
             slot[j] = (uint32_t)((cnt + j) % Cfg::A_STAGES);
             const uint32_t ph = ((cnt + j) / Cfg::A_STAGES) & 1;
-            mbar_wait(&act_full[slot[j]], ph);
+            if constexpr (!(VAR & 8)) mbar_wait(&act_full[slot[j]], ph);
             mbar_wait(&deq_full[slot[j]], ph);
           }
         }
@@ -603,7 +607,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           const int as = ucnt % Cfg::ACT_STAGES;
           const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
           tw = TRACE ? clock64() : 0;
-          mbar_wait(&act_full[as], aph);
+          if constexpr (!(VAR & 8)) mbar_wait(&act_full[as], aph);
           if (TRACE) w_act += clock64() - tw;
           const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
           const uint32_t first = (kt > kt0) ? 1u : 0u;
@@ -787,13 +791,13 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-// B200_W4_VARIANT = 1 | 2 | 4 | 6: experimental variants of the kernel (see VAR above); only for
+// B200_W4_VARIANT = 1 | 2 | 4 | 6 | 10 | 14: experimental variants of the kernel (see VAR above); only for
 // batches <= 64 rows with one weight tile per unit, everything else runs the default kernel
 static int w4_variant() {
   static const int v = [] {
     const char* e = getenv("B200_W4_VARIANT");
-    const int v = (e && e[0] >= '0' && e[0] <= '7' && e[1] == 0) ? e[0] - '0' : 0;
-    return (v == 1 || v == 2 || v == 4 || v == 6) ? v : 0;
+    const int v = e ? atoi(e) : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 6 || v == 10 || v == 14) ? v : 0;
   }();
   return v;
 }
@@ -820,6 +824,8 @@ static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream
         case 2: return launch_w4_kernel<MT, 1, false, 2>(amap, p, st);
         case 4: return launch_w4_kernel<MT, 1, false, 4>(amap, p, st);
         case 6: return launch_w4_kernel<MT, 1, false, 6>(amap, p, st);
+        case 10: return launch_w4_kernel<MT, 1, false, 10>(amap, p, st);
+        case 14: return launch_w4_kernel<MT, 1, false, 14>(amap, p, st);
         default: break;
       }
     }

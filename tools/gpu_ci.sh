@@ -129,13 +129,13 @@ if has timeline; then
   head -40 $OUT/step_timeline.log >> $OUT/summary.txt
 fi
 if has w4var; then
-  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6): parity, then A/B bench
-  for v in 1 2 4 6; do
+  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6|10|14): parity, then A/B bench
+  for v in 1 2 4 6 10 14; do
     B200_W4_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_w4a16.py tests/test_gpu_decode_step.py \
         -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_w4var$v.log 2>&1
     echo "pytest w4a16[variant $v] rc=$? : $(tail -1 $OUT/pytest_w4var$v.log)" | tee -a $OUT/summary.txt
   done
-  for v in 0 1 2 4 6; do
+  for v in 0 1 2 4 6 10 14; do
     B200_W4_VARIANT=$v timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
         > $OUT/bench_w4var$v.json 2> $OUT/bench_w4var$v.err
     echo "bench w4 variant=$v rc=$? $(tail -1 $OUT/bench_w4var$v.json | head -c 200)" | tee -a $OUT/summary.txt

@@ -51,7 +51,9 @@ class Sim:
         self.raw_empty = [Bar(4) for _ in range(RAW_STAGES)]
         self.act_full = [Bar(1) for _ in range(STAGES)]
         self.act_empty = [Bar(1) for _ in range(STAGES)]
-        self.deq_full = [Bar(4) for _ in range(STAGES)]
+        # variant bit 8: the activation copy completes on the slot's deq_full barrier (4 dequant
+        # arrivals + the producer's expect_tx arrival + the transaction itself)
+        self.deq_full = [Bar(6 if var & 8 else 4) for _ in range(STAGES)]
         self.deq_empty = [Bar(1) for _ in range(STAGES)]
         self.tmem_full = [Bar(1), Bar(1)]
         self.tmem_empty = [Bar(4), Bar(4)]
@@ -87,6 +89,8 @@ class Sim:
             else:
                 yield self.act_empty[st], ph ^ 1
             assert not any(op[0] == "mma" and op[2] == st for op in self.pipe), "act stage overwritten under a queued MMA"
+            if self.var & 8:
+                self.deq_full[st].arrive()           # arrive.expect_tx
             self.inflight.append(("act", st, cnt))
             yield None
 
@@ -118,7 +122,8 @@ class Sim:
             yield self.tmem_empty[buf], tph ^ 1
             while cnt < self.total and self.seg_of[cnt] == seg:
                 st, ph = cnt % STAGES, (cnt // STAGES) & 1
-                yield self.act_full[st], ph
+                if not (self.var & 8):
+                    yield self.act_full[st], ph
                 yield self.deq_full[st], ph
                 self.issue(cnt, seg)
                 self.pipe.append(("commit", self.deq_empty[st]))
@@ -139,7 +144,8 @@ class Sim:
                     assert self.seg_of[cnt + j] == seg
                     yield self.tmem_empty[seg & 1], ((seg >> 1) & 1) ^ 1
                 st, ph = (cnt + j) % STAGES, ((cnt + j) // STAGES) & 1
-                yield self.act_full[st], ph
+                if not (self.var & 8):
+                    yield self.act_full[st], ph
                 yield self.deq_full[st], ph
             for j in range(n):
                 s = self.seg_of[cnt + j]
@@ -184,7 +190,7 @@ class Sim:
             self.raw_full[st].arrive()
         else:
             self.act[st] = tile
-            self.act_full[st].arrive()
+            (self.deq_full if self.var & 8 else self.act_full)[st].arrive()
 
     def run(self):
         roles = [self.raw_producer(), self.act_producer(), self.epilogue(),
@@ -232,7 +238,7 @@ def random_segments(rng):
     return segs
 
 
-def check(variants=(0, 1, 2, 4, 6), trials=300, seed=0):
+def check(variants=(0, 1, 2, 4, 6, 10, 14), trials=300, seed=0):
     rng = random.Random(seed)
     for var in variants:
         for _ in range(trials):
@@ -242,4 +248,4 @@ def check(variants=(0, 1, 2, 4, 6), trials=300, seed=0):
 
 if __name__ == "__main__":
     check(trials=int(sys.argv[1]) if len(sys.argv) > 1 else 1000)
-    print("protocol model: no hazard, no deadlock (variants 0 1 2 4 6)")
+    print("protocol model: no hazard, no deadlock (variants 0 1 2 4 6 10 14)")
