@@ -129,24 +129,29 @@ if has timeline; then
   head -40 $OUT/step_timeline.log >> $OUT/summary.txt
 fi
 if has w4var; then
-  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6|10|14): parity, then A/B bench
-  for v in 1 2 4 6 10 14; do
-    B200_W4_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_w4a16.py tests/test_gpu_decode_step.py \
-        -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_w4var$v.log 2>&1
-    echo "pytest w4a16[variant $v] rc=$? : $(tail -1 $OUT/pytest_w4var$v.log)" | tee -a $OUT/summary.txt
-  done
+  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6|10|14): parity, a GEMM-only A/B
+  # (seconds per variant), then the full bench for the default and the fastest variant
+  : > $OUT/w4_variants.jsonl
   for v in 0 1 2 4 6 10 14; do
+    if [ $v != 0 ]; then
+      B200_W4_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_w4a16.py tests/test_gpu_decode_step.py \
+          -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_w4var$v.log 2>&1
+      echo "pytest w4a16[variant $v] rc=$? : $(tail -1 $OUT/pytest_w4var$v.log)" | tee -a $OUT/summary.txt
+    fi
+    B200_W4_VARIANT=$v timeout 300 python tools/w4_variant_bench.py >> $OUT/w4_variants.jsonl 2> $OUT/w4_variant$v.err
+    echo "gemm a/b variant $v rc=$? $(tail -1 $OUT/w4_variants.jsonl)" | tee -a $OUT/summary.txt
+  done
+  BEST=$(python - $OUT/w4_variants.jsonl <<'PY'
+import json, sys
+rows = [json.loads(l) for l in open(sys.argv[1]) if l.strip().startswith("{")]
+print(min(rows, key=lambda r: r["sum_us"])["variant"] if rows else 0)
+PY
+)
+  for v in 0 $BEST; do
+    [ $v = 0 ] && [ "$BEST" = 0 ] && [ -s $OUT/bench_w4var0.json ] && continue
     B200_W4_VARIANT=$v timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
         > $OUT/bench_w4var$v.json 2> $OUT/bench_w4var$v.err
     echo "bench w4 variant=$v rc=$? $(tail -1 $OUT/bench_w4var$v.json | head -c 200)" | tee -a $OUT/summary.txt
-    python - $OUT/bench_w4var$v.json <<'PY' | tee -a $OUT/summary.txt
-import json, sys
-try:
-    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print("   ", {k: round(v["us"], 2) for k, v in d["roofline_w4a16_gemm"]["per_proj"].items()})
-except Exception as e:
-    print("    (no GEMM timings:", e, ")")
-PY
   done
 fi
 if has ref; then
