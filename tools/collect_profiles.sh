@@ -20,6 +20,7 @@ fi
 [ -s $G/w4_trace.log ] && { echo "# $R: device-side clock64 trace of w4a16_gemm_kernel (tools/w4_trace.py)"; echo '```'; cat $G/w4_trace.log; echo '```'; } > $P/${R}_w4_trace.md
 [ -s $G/attn_bench.log ] && { echo "# $R: attention kernel-only timings (tools/attn_bench.py)"; echo '```'; cat $G/attn_bench.log; echo '```'; } > $P/${R}_attn_bench.md
 [ -s $G/step_timeline.md ] && cp $G/step_timeline.md $P/${R}_step_timeline.md
+[ -s $G/w4_variants.jsonl ] && { echo "# $R: GEMM-only A/B of the W4A16 kernel variants (tools/w4_variant_bench.py; us per launch, CUDA graph replay, M = 64)"; echo '```'; cat $G/w4_variants.jsonl; echo '```'; } > $P/${R}_w4_variants.md
 # A/B runs of the opt-in variants: one line per run (value, ms/step, GEMM launch times)
 if ls $G/bench_w4var*.json $G/bench_occ*.json 2> /dev/null | grep -q .; then
   python - $G $P/${R}_variants.md "$R" <<'PY'
