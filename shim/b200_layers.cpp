@@ -4,6 +4,8 @@
 #include "b200_layers.h"
 
 #include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -406,6 +408,67 @@ torch::Tensor LlamaDecoderStep::forward(const torch::Tensor& tokens, const torch
 torch::Tensor LlamaDecoderStep::step(const torch::Tensor& tokens, const torch::Tensor& positions,
                                      const InputParameters& params) {
   return kernel::argmax(forward(tokens, positions, params));
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-graph replay of the step
+// ---------------------------------------------------------------------------------------------
+void CudaGraphStep::capture(LlamaDecoderStep* model, const torch::Tensor& tokens,
+                            const torch::Tensor& positions, const InputParameters& params,
+                            int64_t max_block_table_len, bool greedy) {
+  TORCH_CHECK(graph_ == nullptr, "graph already captured");
+  TORCH_CHECK(model != nullptr && tokens.is_cuda(), "CudaGraphStep: CUDA tensors only");
+  TORCH_CHECK(max_block_table_len >= params.block_tables.size(0), "block table capacity too small");
+  batch_size_ = params.num_sequences;
+  num_tokens_ = tokens.size(0);
+  // own the inputs: the graph reads these buffers, replay() refreshes them
+  tokens_ = tokens.clone();
+  positions_ = positions.clone();
+  params_ = params;
+  params_.q_cu_seq_lens = params.q_cu_seq_lens.clone();
+  params_.kv_cu_seq_lens = params.kv_cu_seq_lens.clone();
+  params_.new_cache_slots = params.new_cache_slots.clone();
+  params_.cu_block_lens = params.cu_block_lens.clone();
+  params_.block_tables = torch::zeros({max_block_table_len}, params.block_tables.options());
+  params_.block_tables.slice(0, 0, params.block_tables.size(0)).copy_(params.block_tables);
+
+  auto run = [&]() {
+    return greedy ? model->step(tokens_, positions_, params_) : model->forward(tokens_, positions_, params_);
+  };
+  // warm up outside the capture: workspaces, tensor maps, library handles
+  torch::cuda::synchronize();
+  run();
+  torch::cuda::synchronize();
+  {
+    at::cuda::CUDAStream capture_stream = at::cuda::getStreamFromPool();
+    at::cuda::CUDAStreamGuard stream_guard(capture_stream);
+    graph_ = std::make_unique<at::cuda::CUDAGraph>();
+    graph_->capture_begin(at::cuda::graph_pool_handle(), cudaStreamCaptureModeThreadLocal);
+    output_ = run();
+    graph_->capture_end();
+  }
+  torch::cuda::synchronize();
+}
+
+torch::Tensor CudaGraphStep::replay(const torch::Tensor& tokens, const torch::Tensor& positions,
+                                    const InputParameters& params) {
+  TORCH_CHECK(graph_ != nullptr, "graph not captured");
+  TORCH_CHECK(params.num_sequences == batch_size_, "batch size mismatch");
+  TORCH_CHECK(tokens.size(0) == num_tokens_, "num tokens mismatch");
+  const int64_t table_len = params.block_tables.size(0);
+  TORCH_CHECK(params_.block_tables.size(0) >= table_len, "block table size mismatch");
+  TORCH_CHECK(params.kv_max_seq_len <= params_.kv_max_seq_len && params.q_max_seq_len <= params_.q_max_seq_len,
+              "step exceeds the sequence lengths the graph was captured for");
+  tokens_.copy_(tokens, /*non_blocking=*/true);
+  positions_.copy_(positions, /*non_blocking=*/true);
+  params_.q_cu_seq_lens.copy_(params.q_cu_seq_lens, /*non_blocking=*/true);
+  params_.kv_cu_seq_lens.copy_(params.kv_cu_seq_lens, /*non_blocking=*/true);
+  params_.new_cache_slots.copy_(params.new_cache_slots, /*non_blocking=*/true);
+  // the block table may arrive with a different padding length
+  params_.block_tables.slice(0, 0, table_len).copy_(params.block_tables, /*non_blocking=*/true);
+  params_.cu_block_lens.copy_(params.cu_block_lens, /*non_blocking=*/true);
+  graph_->replay();
+  return output_;
 }
 
 }  // namespace llm

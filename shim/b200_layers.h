@@ -9,6 +9,7 @@
 //                                        src/layers/quantization/qlinear_awq_marlin_impl.cpp:129-365
 //   RMSNormImpl                          src/layers/normalization.h:114-139
 //   LlamaDecoderStep                     src/models/meta/llama.h:61-64,123-133,170-177,220-232,281-289
+//   CudaGraphStep                        src/engine/model_runner.cpp:141-210 (ModelRunner::CudaGraph)
 //
 // Inside ScaleLLM these classes derive from the engine's own headers; here the
 // interfaces are restated so that the library is self-contained and testable.  One tensor-parallel
@@ -16,6 +17,8 @@
 #pragma once
 
 #include <torch/torch.h>
+
+#include <ATen/cuda/CUDAGraph.h>
 
 #include <memory>
 #include <optional>
@@ -237,6 +240,29 @@ class LlamaDecoderStep {
   std::unique_ptr<B200Handler> handler_;
   torch::Tensor embed_, lm_head_;  // [vocab, h] each
   std::vector<KVCache> kv_caches_;
+};
+
+// One captured decode step for a fixed batch size and token count; replay() copies the step's
+// metadata into the captured tensors and replays (ModelRunner::CudaGraph, model_runner.cpp:141-210).
+// The host scalars of the captured launch (q_max_seq_len, kv_max_seq_len) are those of the capture:
+// capture with kv_max_seq_len = the longest context replays will see (cuda_graph_max_seq_len).
+class CudaGraphStep {
+ public:
+  // max_block_table_len: entries of the captured block table (model_runner.cpp:57-60:
+  // batch * ((max_seq_len + block_size - 1) / block_size + 1)); greedy: return next tokens
+  // (LlamaDecoderStep::step) instead of logits
+  void capture(LlamaDecoderStep* model, const torch::Tensor& tokens, const torch::Tensor& positions,
+               const InputParameters& params, int64_t max_block_table_len, bool greedy);
+  // the returned tensor is the graph's output buffer: valid until the next replay
+  torch::Tensor replay(const torch::Tensor& tokens, const torch::Tensor& positions,
+                       const InputParameters& params);
+
+ private:
+  std::unique_ptr<at::cuda::CUDAGraph> graph_;
+  int64_t batch_size_ = 0, num_tokens_ = 0;
+  torch::Tensor tokens_, positions_;
+  InputParameters params_;  // owns the captured metadata tensors
+  torch::Tensor output_;
 };
 
 }  // namespace llm

@@ -95,6 +95,39 @@ PYBIND11_MODULE(_b200_shim, m) {
              return self.forward(tokens, positions, p);
            });
 
+  py::class_<llm::CudaGraphStep>(m, "CudaGraphStep")
+      .def(py::init<>())
+      .def("capture",
+           [](llm::CudaGraphStep& self, llm::LlamaDecoderStep& model, torch::Tensor tokens,
+              torch::Tensor positions, torch::Tensor q_cu, torch::Tensor kv_cu, int kv_max, int q_max,
+              torch::Tensor slots, torch::Tensor tables, torch::Tensor blk_cu, int64_t max_table_len,
+              bool greedy) {
+             llm::InputParameters p;
+             p.num_sequences = static_cast<int32_t>(q_cu.size(0) - 1);
+             p.q_cu_seq_lens = q_cu;
+             p.kv_cu_seq_lens = kv_cu;
+             p.kv_max_seq_len = kv_max;
+             p.q_max_seq_len = q_max;
+             p.new_cache_slots = slots;
+             p.block_tables = tables;
+             p.cu_block_lens = blk_cu;
+             self.capture(&model, tokens, positions, p, max_table_len, greedy);
+           })
+      .def("replay", [](llm::CudaGraphStep& self, torch::Tensor tokens, torch::Tensor positions,
+                        torch::Tensor q_cu, torch::Tensor kv_cu, int kv_max, int q_max,
+                        torch::Tensor slots, torch::Tensor tables, torch::Tensor blk_cu) {
+        llm::InputParameters p;
+        p.num_sequences = static_cast<int32_t>(q_cu.size(0) - 1);
+        p.q_cu_seq_lens = q_cu;
+        p.kv_cu_seq_lens = kv_cu;
+        p.kv_max_seq_len = kv_max;
+        p.q_max_seq_len = q_max;
+        p.new_cache_slots = slots;
+        p.block_tables = tables;
+        p.cu_block_lens = blk_cu;
+        return self.replay(tokens, positions, p);
+      });
+
   // ---- tensor-parallel plumbing in the reference's threading model (shim/b200_process_group.h) --
   py::class_<llm::ProcessGroup>(m, "ProcessGroup")
       .def("rank", &llm::ProcessGroup::rank)

@@ -131,3 +131,60 @@ def test_cpp_decode_step_matches_python_mirror(fuse):
         assert torch.equal(a, b.key_cache)
     for a, b in zip(vc, py.kv_caches):
         assert torch.equal(a, b.value_cache)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_STAGED") != "1",
+                    reason="staged: not yet validated on a GPU box (B200_TEST_STAGED=1)")
+def test_cpp_cuda_graph_step_replays_like_eager():
+    """CudaGraphStep (ModelRunner::CudaGraph, model_runner.cpp:141-210): capture one step, replay
+    it with other metadata (different kv lengths, a shorter block table) — logits bit-identical to
+    the eager C++ step on the same inputs, and the KV writes of the replay land in the caches."""
+    from scalellm_b200.decode_step import BlockPool, StepBuffers, build_decode_batch
+    shim = _shim()
+    dev = torch.device("cuda")
+    c = CFG
+    sd = _state_dict(seed=2)
+    bs, B, n_blocks = 16, 5, 64
+
+    def fresh():
+        m = _make(shim, torch.empty(0, dtype=torch.bfloat16, device=dev))
+        m.load_state_dict(sd)
+        g = torch.Generator(device=dev).manual_seed(3)
+        kc = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g, device=dev).bfloat16()
+              for _ in range(c["n_layers"])]
+        vc = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g, device=dev).bfloat16()
+              for _ in range(c["n_layers"])]
+        m.set_kv_caches(kc, vc, bs)
+        return m, kc, vc
+
+    pool = BlockPool(n_blocks, bs, seed=1)
+    for _ in range(B):
+        pool.add_sequence(120)
+    bufs = StepBuffers(dev, 16, 8, 256)
+
+    def args_of(kv, seed):
+        hb = build_decode_batch(pool, kv, [1] * B, c["vocab"], seed=seed)
+        tokens, positions, p = bufs.upload(hb)
+        # the graph owns its copies; clone so the next upload cannot alias what we compare against
+        return [t.clone() for t in (tokens, positions, p.q_cu_seq_lens, p.kv_cu_seq_lens)] + \
+               [120, 1] + [t.clone() for t in (p.new_cache_slots, p.block_tables, p.cu_block_lens)]
+
+    graphed, g_kc, g_vc = fresh()
+    eager, e_kc, e_vc = fresh()
+    step = shim.CudaGraphStep()
+    cap = args_of([100, 64, 5, 111, 17], seed=9)
+    step.capture(graphed, *cap, B * (120 // bs + 2), False)
+    eager.forward(*cap)                                        # the capture's warm-up + capture also wrote K/V
+    for kv, seed in (([37, 64, 5, 100, 17], 4), ([1, 2, 3, 4, 5], 5), ([100, 64, 5, 111, 17], 9)):
+        a = args_of(kv, seed)
+        got = step.replay(*a).clone()
+        want = eager.forward(*a)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), kv
+        for x, y in zip(g_kc + g_vc, e_kc + e_vc):
+            assert torch.equal(x, y)
+    bad = args_of([5, 6, 7, 8, 9], 1)
+    bad[2], bad[3] = bad[2][:-1], bad[3][:-1]                  # one sequence fewer than captured
+    with pytest.raises(RuntimeError, match="batch size"):
+        step.replay(*bad)

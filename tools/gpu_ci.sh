@@ -9,7 +9,7 @@ OUT=gpurun_out
 STAGES="${*:-tests probe smoke bench ncu}"
 # "round2" = everything that was staged after round 1's GPU budget ran out, in one call
 if [[ " $STAGES " == *" round2 "* ]]; then
-  STAGES="$STAGES tests smoke bench timeline trace micro w4var occ refk"
+  STAGES="$STAGES tests smoke bench staged timeline trace micro w4var occ refk"
 fi
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 echo "stages: $STAGES" | tee $OUT/summary.txt
@@ -121,6 +121,14 @@ if has occ; then
         > $OUT/bench_occ$v.json 2> $OUT/bench_occ$v.err
     echo "bench occ=$v rc=$? $(tail -1 $OUT/bench_occ$v.json | head -c 200)" | tee -a $OUT/summary.txt
   done
+fi
+if has staged; then
+  # single-GPU tests written after round 1's GPU budget was spent (gate: B200_TEST_STAGED=1)
+  B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_cpp_host.py -m gpu -q --tb=short -p no:cacheprovider \
+      > $OUT/pytest_staged.log 2>&1
+  echo "pytest staged (cpp host incl. CudaGraphStep) rc=$? : $(tail -1 $OUT/pytest_staged.log)" | tee -a $OUT/summary.txt
+  timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --ttft > $OUT/bench_ttft.json 2> $OUT/bench_ttft.err
+  echo "bench --ttft rc=$? $(tail -1 $OUT/bench_ttft.json | python -c 'import json,sys; print(json.loads(sys.stdin.read())["config"]["ttft"])' 2>&1 | head -c 300)" | tee -a $OUT/summary.txt
 fi
 if has timeline; then
   # in-graph device timeline of the decode step (CUPTI via torch.profiler): shares, gaps, overlap
