@@ -296,14 +296,95 @@ torch::Tensor RMSNormImpl::forward_residual_partials(const W4Partials& input,
 }
 
 // ---------------------------------------------------------------------------------------------
+// tensor-parallel shards of checkpoint-format int4 linears
+//   AWQ: qweight [K, N/8] (8 columns per word), qzeros [K/g, N/8], scales [K/g, N];
+//   GPTQ: qweight [K/8, N] (8 rows per word), qzeros [K/g, N/8] (optional), scales [K/g, N]
+// ---------------------------------------------------------------------------------------------
+StateDict shard_qlinear_columns(const StateDict& t, const QuantArgs& qa, int64_t c0, int64_t c1) {
+  TORCH_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && c0 < c1, "column shard must align to 8 columns");
+  const bool awq = qa.quant_method == "awq";
+  StateDict out;
+  const auto& qw = need(t, "qweight");
+  out["qweight"] = awq ? qw.slice(1, c0 / 8, c1 / 8) : qw.slice(1, c0, c1);
+  out["scales"] = need(t, "scales").slice(1, c0, c1);
+  auto z = t.find("qzeros");
+  if (z != t.end()) out["qzeros"] = z->second.slice(1, c0 / 8, c1 / 8);
+  return out;
+}
+
+StateDict shard_qlinear_rows(const StateDict& t, const QuantArgs& qa, int64_t k0, int64_t k1) {
+  const bool awq = qa.quant_method == "awq";
+  const auto& qw = need(t, "qweight");
+  const int64_t K = awq ? qw.size(0) : qw.size(0) * 8;
+  const int64_t g = qa.group_size > 0 ? qa.group_size : K;
+  TORCH_CHECK(k0 % g == 0 && k1 % g == 0 && k0 < k1 && k1 <= K,
+              "row-parallel shard must align to quant groups");  // qlinear_awq_marlin_impl.cpp:287
+  StateDict out;
+  out["qweight"] = awq ? qw.slice(0, k0, k1) : qw.slice(0, k0 / 8, k1 / 8);
+  out["scales"] = need(t, "scales").slice(0, k0 / g, k1 / g);
+  auto z = t.find("qzeros");
+  if (z != t.end()) out["qzeros"] = z->second.slice(0, k0 / g, k1 / g);
+  return out;
+}
+
+namespace {
+StateDict cat_columns(const std::vector<StateDict>& parts) {
+  StateDict out;
+  for (const auto& kv : parts[0]) {
+    std::vector<torch::Tensor> ts;
+    for (const auto& p : parts) ts.push_back(need(p, kv.first));
+    out[kv.first] = torch::cat(ts, 1);
+  }
+  return out;
+}
+}  // namespace
+
+LlamaLayerShards shard_llama_layer(const StateDict& qkv, const StateDict& o, const StateDict& gate_up,
+                                   const StateDict& down, const LlamaArgs& args, const QuantArgs& qa,
+                                   int rank, int world) {
+  const int64_t w = world, r = rank;
+  TORCH_CHECK(w >= 1 && r >= 0 && r < w, "bad rank / world_size");
+  const int64_t D = args.head_dim, H = args.n_heads, Hkv = args.n_kv_heads, I = args.intermediate_size;
+  TORCH_CHECK(H % w == 0 && I % w == 0 && (Hkv % w == 0 || w % Hkv == 0), "sizes must divide by world_size");
+  const int64_t Hl = H / w, Hkvl = std::max<int64_t>(1, Hkv / w), Il = I / w;
+  // kv heads of this rank: a contiguous share, or one replicated head when Hkv < w
+  // (qkv_parallel_linear.cpp:28-70)
+  const int64_t kv0 = Hkv >= w ? r * (Hkv / w) : r / (w / Hkv);
+  const int64_t q0 = r * Hl * D, k_base = H * D, v_base = (H + Hkv) * D;
+  LlamaLayerShards sh;
+  sh.qkv = cat_columns({shard_qlinear_columns(qkv, qa, q0, q0 + Hl * D),
+                        shard_qlinear_columns(qkv, qa, k_base + kv0 * D, k_base + (kv0 + Hkvl) * D),
+                        shard_qlinear_columns(qkv, qa, v_base + kv0 * D, v_base + (kv0 + Hkvl) * D)});
+  sh.gate_up = cat_columns({shard_qlinear_columns(gate_up, qa, r * Il, (r + 1) * Il),
+                            shard_qlinear_columns(gate_up, qa, I + r * Il, I + (r + 1) * Il)});
+  sh.o = shard_qlinear_rows(o, qa, r * Hl * D, (r + 1) * Hl * D);
+  sh.down = shard_qlinear_rows(down, qa, r * Il, (r + 1) * Il);
+  return sh;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the decode step
 // ---------------------------------------------------------------------------------------------
 LlamaDecoderStep::LlamaDecoderStep(const LlamaArgs& args, const QuantArgs& qa,
                                    const torch::Tensor& inv_freq,
-                                   const torch::TensorOptions& options)
-    : args_(args), options_(options) {
+                                   const torch::TensorOptions& options,
+                                   const ParallelArgs& parallel_args)
+    : args_(args), quant_args_(qa), options_(options), parallel_args_(parallel_args) {
+  const int64_t w = parallel_args.world_size();
+  TORCH_CHECK(w >= 1 && args.n_heads % w == 0 && args.intermediate_size % w == 0 &&
+                  args.hidden_size % w == 0 && args.vocab_size % w == 0,
+              "heads / intermediate / hidden / vocab sizes must divide by world_size ", w);
+  TORCH_CHECK(args.n_kv_heads % w == 0 || w % args.n_kv_heads == 0,
+              "n_kv_heads ", args.n_kv_heads, " and world_size ", w, " must divide one another");
+  if (w > 1) {
+    pg_ = dynamic_cast<ProcessGroupB200*>(parallel_args.process_group());
+    TORCH_CHECK(pg_ != nullptr, "tensor parallelism needs a ProcessGroupB200");
+  }
+  n_heads_ = args.n_heads / w;                                   // llama.h:83-90
+  n_kv_heads_ = std::max<int64_t>(1, args.n_kv_heads / w);
+  inter_ = args.intermediate_size / w;
   const int64_t h = args.hidden_size, D = args.head_dim;
-  const int64_t q_size = args.n_heads * D, kv_size = args.n_kv_heads * D;
+  const int64_t q_size = n_heads_ * D, kv_size = n_kv_heads_ * D;
   const char* env = std::getenv("B200_FUSE_SPLITK");
   fuse_partials = !(env && env[0] == '0');
   // cos | sin cache in the model dtype (pos_embedding.cpp:183-215)
@@ -318,8 +399,8 @@ LlamaDecoderStep::LlamaDecoderStep(const LlamaArgs& args, const QuantArgs& qa,
     L.post_norm = std::make_unique<RMSNormImpl>(h, args.rms_norm_eps, options);
     L.qkv = std::make_unique<QLinearB200Impl>(h, q_size + 2 * kv_size, false, qa, options);
     L.o = std::make_unique<QLinearB200Impl>(q_size, h, false, qa, options);
-    L.gate_up = std::make_unique<QLinearB200Impl>(h, 2 * args.intermediate_size, false, qa, options);
-    L.down = std::make_unique<QLinearB200Impl>(args.intermediate_size, h, false, qa, options);
+    L.gate_up = std::make_unique<QLinearB200Impl>(h, 2 * inter_, false, qa, options);
+    L.down = std::make_unique<QLinearB200Impl>(inter_, h, false, qa, options);
   }
   final_norm_ = std::make_unique<RMSNormImpl>(h, args.rms_norm_eps, options);
 }
@@ -331,37 +412,62 @@ void LlamaDecoderStep::load_state_dict(const StateDict& sd) {
       if (kv.first.rfind(prefix, 0) == 0) out.emplace(kv.first.substr(prefix.size()), kv.second);
     return out;
   };
+  const int64_t w = parallel_args_.world_size(), r = parallel_args_.rank();
   for (size_t i = 0; i < layers_.size(); ++i) {
     const std::string p = "layers." + std::to_string(i) + ".";
-    layers_[i].qkv->load_state_dict(sub(p + "qkv."));
-    layers_[i].o->load_state_dict(sub(p + "o."));
-    layers_[i].gate_up->load_state_dict(sub(p + "gate_up."));
-    layers_[i].down->load_state_dict(sub(p + "down."));
+    if (w == 1) {
+      layers_[i].qkv->load_state_dict(sub(p + "qkv."));
+      layers_[i].o->load_state_dict(sub(p + "o."));
+      layers_[i].gate_up->load_state_dict(sub(p + "gate_up."));
+      layers_[i].down->load_state_dict(sub(p + "down."));
+    } else {
+      const LlamaLayerShards sh = shard_llama_layer(sub(p + "qkv."), sub(p + "o."), sub(p + "gate_up."),
+                                                    sub(p + "down."), args_, quant_args_,
+                                                    static_cast<int>(r), static_cast<int>(w));
+      layers_[i].qkv->load_state_dict(sh.qkv);
+      layers_[i].o->load_state_dict(sh.o);
+      layers_[i].gate_up->load_state_dict(sh.gate_up);
+      layers_[i].down->load_state_dict(sh.down);
+    }
     layers_[i].input_norm->load_state_dict(sub(p + "input_norm."));
     layers_[i].post_norm->load_state_dict(sub(p + "post_norm."));
   }
   final_norm_->load_state_dict(sub("final_norm."));
-  embed_ = need(sd, "embed.weight").to(options_).contiguous();
-  lm_head_ = need(sd, "lm_head.weight").to(options_).contiguous();
+  // ParallelEmbedding: split on the hidden dim + all-gather (embedding.h:74-79); lm_head: column
+  // parallel on the vocabulary + all-gather of the logits (llama.h:281-289)
+  const int64_t hs = args_.hidden_size / w, vs = args_.vocab_size / w;
+  embed_ = need(sd, "embed.weight").slice(1, r * hs, (r + 1) * hs).to(options_).contiguous();
+  lm_head_ = need(sd, "lm_head.weight").slice(0, r * vs, (r + 1) * vs).to(options_).contiguous();
 }
 
 torch::Tensor LlamaDecoderStep::forward(const torch::Tensor& tokens, const torch::Tensor& positions,
                                         const InputParameters& params) {
   TORCH_CHECK(kv_caches_.size() == layers_.size(), "set_kv_caches() first");
-  const int64_t H = args_.n_heads, Hkv = args_.n_kv_heads, D = args_.head_dim;
+  const int64_t H = n_heads_, Hkv = n_kv_heads_, D = args_.head_dim;  // this rank's heads
   const int64_t q_size = H * D, kv_size = Hkv * D;
+  const int64_t w = parallel_args_.world_size();
   torch::Tensor h = embed_.index_select(0, tokens.to(torch::kLong));  // residual stream [T, hidden]
+  if (w > 1) h = pg_->allgather_lastdim(h);
   const int64_t T = h.size(0);
   const auto dtype = h.scalar_type();
 
   // `pending` = output of the previous block, not yet added to the residual stream: a bf16 tensor
-  // or the producing GEMM's partials (llama.h:170-177 with the adds folded into the norms)
+  // or the producing GEMM's partials (llama.h:170-177 with the adds folded into the norms).  Under
+  // tensor parallelism the pending tensor is a row-parallel linear's local result: its all-reduce
+  // happens here, fused with the GEMM's reduction — and with the add + norm when the shape allows.
   bool have_pending = false, pending_is_partials = false;
   torch::Tensor pending;
   W4Partials pending_parts;
   auto norm_residual = [&](RMSNormImpl& norm) {
-    return pending_is_partials ? norm.forward_residual_partials(pending_parts, h)
-                               : norm.forward_residual(pending, h);
+    if (!pending_is_partials) {
+      if (w > 1) pg_->allreduce(pending);
+      return norm.forward_residual(pending, h);
+    }
+    if (w == 1) return norm.forward_residual_partials(pending_parts, h);
+    if (pg_->supports_partials_norm(T, h.size(1), dtype))
+      return pg_->allreduce_partials_norm(pending_parts.data, pending_parts.K, h, norm.weight, norm.eps());
+    torch::Tensor reduced = pg_->allreduce_partials(pending_parts.data, pending_parts.K, dtype);
+    return norm.forward_residual(reduced, h);
   };
 
   for (size_t li = 0; li < layers_.size(); ++li) {
@@ -402,7 +508,8 @@ torch::Tensor LlamaDecoderStep::forward(const torch::Tensor& tokens, const torch
     have_pending = true;
   }
   torch::Tensor hn = have_pending ? norm_residual(*final_norm_) : final_norm_->forward(h);
-  return torch::linear(hn, lm_head_);  // dense bf16 lm_head: library GEMM (not on this path)
+  torch::Tensor logits = torch::linear(hn, lm_head_);  // dense bf16 lm_head: library GEMM (not on this path)
+  return w > 1 ? pg_->allgather_lastdim(logits) : logits;
 }
 
 torch::Tensor LlamaDecoderStep::step(const torch::Tensor& tokens, const torch::Tensor& positions,

@@ -12,13 +12,17 @@
 //   CudaGraphStep                        src/engine/model_runner.cpp:141-210 (ModelRunner::CudaGraph)
 //
 // Inside ScaleLLM these classes derive from the engine's own headers; here the
-// interfaces are restated so that the library is self-contained and testable.  One tensor-parallel
-// rank (world_size 1); the TP plumbing lives in scalellm_b200/model_parallel.py this round.
+// interfaces are restated so that the library is self-contained and testable.  Tensor parallelism
+// follows the reference's partitioning (column split q/k/v/gate/up, row split o/down, one exchange
+// per row-parallel linear, llama.h:83-115) over shim/b200_process_group.h: one LlamaDecoderStep per
+// rank, all ranks in one process with one thread each, or one process per rank.
 #pragma once
 
 #include <torch/torch.h>
 
 #include <ATen/cuda/CUDAGraph.h>
+
+#include "b200_process_group.h"
 
 #include <memory>
 #include <optional>
@@ -186,6 +190,13 @@ class QLinearB200Impl final : public ParallelLinearImpl {
   torch::Tensor qweight_, qzeros_, scales_, bias_, packed_, workspace_;
 };
 
+// this rank's shard of a checkpoint-format int4 linear: output columns [c0, c1) of a column-
+// parallel layer / input rows [k0, k1) of a row-parallel one (views, no copies)
+StateDict shard_qlinear_columns(const StateDict& tensors, const QuantArgs& quant_args, int64_t c0,
+                                int64_t c1);
+StateDict shard_qlinear_rows(const StateDict& tensors, const QuantArgs& quant_args, int64_t k0,
+                             int64_t k1);
+
 class RMSNormImpl {
  public:
   RMSNormImpl(int64_t dim, float eps, const torch::TensorOptions& options);
@@ -193,6 +204,7 @@ class RMSNormImpl {
   torch::Tensor forward_residual(const torch::Tensor& input, torch::Tensor& residual);
   torch::Tensor forward_residual_partials(const W4Partials& input, torch::Tensor& residual);
   void load_state_dict(const StateDict& state_dict);
+  float eps() const { return eps_; }
   torch::Tensor weight;
 
  private:
@@ -208,14 +220,28 @@ struct LlamaArgs {
   float rms_norm_eps = 1e-5f;
 };
 
+// One decoder layer's four int4 linears cut for `rank` of `world` from the unsharded fused tensors
+// (qkv = q | k | v columns, gate_up = gate | up columns): llama.h:83-115 partitioning.
+struct LlamaLayerShards {
+  StateDict qkv, o, gate_up, down;
+};
+LlamaLayerShards shard_llama_layer(const StateDict& qkv, const StateDict& o, const StateDict& gate_up,
+                                   const StateDict& down, const LlamaArgs& args,
+                                   const QuantArgs& quant_args, int rank, int world);
+
 class LlamaDecoderStep {
  public:
   // inv_freq: [head_dim / 2] fp32 (after any rope scaling, pos_embedding.cpp:75-109)
   LlamaDecoderStep(const LlamaArgs& args, const QuantArgs& quant_args, const torch::Tensor& inv_freq,
-                   const torch::TensorOptions& options);
+                   const torch::TensorOptions& options,
+                   const ParallelArgs& parallel_args = ParallelArgs(0, 1, nullptr));
 
   // name -> tensor: "layers.<i>.{qkv,o,gate_up,down}.{qweight,qzeros,scales}",
   // "layers.<i>.{input_norm,post_norm}.weight", "embed.weight", "final_norm.weight", "lm_head.weight"
+  // — the UNSHARDED tensors (qkv = q | k | v columns, gate_up = gate | up columns); each rank keeps
+  // its shard: q/k/v/gate/up column ranges (kv heads replicated when n_kv_heads < world_size,
+  // qkv_parallel_linear.cpp:28-70), o/down row ranges aligned to the quant groups
+  // (qlinear_awq_marlin_impl.cpp:287), embedding split on hidden, lm_head on vocab.
   void load_state_dict(const StateDict& state_dict);
   void set_kv_caches(std::vector<KVCache> kv_caches) { kv_caches_ = std::move(kv_caches); }
 
@@ -234,7 +260,11 @@ class LlamaDecoderStep {
     std::unique_ptr<QLinearB200Impl> qkv, o, gate_up, down;
   };
   LlamaArgs args_;
+  QuantArgs quant_args_;
   torch::TensorOptions options_;
+  ParallelArgs parallel_args_;
+  ProcessGroupB200* pg_ = nullptr;          // the NVLink group, when world_size > 1
+  int64_t n_heads_, n_kv_heads_, inter_;    // per rank
   std::vector<Layer> layers_;
   std::unique_ptr<RMSNormImpl> final_norm_;
   std::unique_ptr<B200Handler> handler_;

@@ -72,6 +72,43 @@ torch::Tensor ProcessGroupB200::allgather_lastdim(const torch::Tensor& input) co
   return out;
 }
 
+torch::Tensor ProcessGroupB200::allreduce_partials(const torch::Tensor& partials, int64_t gemm_k,
+                                                   torch::ScalarType dtype) const {
+  TORCH_CHECK(partials.dim() == 3 && partials.scalar_type() == torch::kFloat && partials.is_contiguous(),
+              "allreduce_partials: fp32 [slots, rows, n]");
+  const int64_t slots = partials.size(0), rows = partials.size(1), n = partials.size(2);
+  auto out = torch::empty({rows, n}, partials.options().dtype(dtype));
+  if (rows == 0) return out;
+  c10::cuda::CUDAGuard guard(device());
+  ok(b200_ar_allreduce_splitk(comm_, out.data_ptr(), partials.const_data_ptr<float>(),
+                              static_cast<int>(slots), gemm_k, n, rows * n, dtype_code(out),
+                              at::cuda::getCurrentCUDAStream().stream()),
+     "ar_allreduce_splitk");
+  return out;
+}
+
+bool ProcessGroupB200::supports_partials_norm(int64_t rows, int64_t n, torch::ScalarType dtype) const {
+  return world_size() > 1 && rows > 0 && rows <= 64 && n % 128 == 0 && n <= 4096 &&
+         rows * n * 2 <= kMaxBytes && (dtype == torch::kBFloat16 || dtype == torch::kHalf);
+}
+
+torch::Tensor ProcessGroupB200::allreduce_partials_norm(const torch::Tensor& partials, int64_t gemm_k,
+                                                        torch::Tensor& residual,
+                                                        const torch::Tensor& weight, float eps) const {
+  TORCH_CHECK(partials.dim() == 3 && partials.scalar_type() == torch::kFloat && partials.is_contiguous() &&
+                  residual.is_contiguous(),
+              "allreduce_partials_norm: fp32 [slots, rows, n] partials, contiguous residual");
+  const int64_t slots = partials.size(0), rows = partials.size(1), n = partials.size(2);
+  auto out = torch::empty_like(residual);
+  c10::cuda::CUDAGuard guard(device());
+  ok(b200_ar_allreduce_splitk_norm(comm_, out.data_ptr(), residual.data_ptr(),
+                                   partials.const_data_ptr<float>(), static_cast<int>(slots), gemm_k,
+                                   weight.const_data_ptr(), rows, n, eps, dtype_code(residual),
+                                   at::cuda::getCurrentCUDAStream().stream()),
+     "ar_allreduce_splitk_norm");
+  return out;
+}
+
 void ProcessGroupB200::allgather(const torch::Tensor& input, torch::Tensor& outputs) const {
   // cat along dim 0 == "last dim" gather of the flattened tensor seen as one row
   TORCH_CHECK(outputs.is_contiguous() && outputs.numel() == input.numel() * world_size() &&

@@ -66,6 +66,18 @@ class ProcessGroupB200 final : public ProcessGroup {
   // cat(all-gather(input), dim=-1) in one launch (what gather_from_model_parallel_region needs)
   torch::Tensor allgather_lastdim(const torch::Tensor& input) const;
 
+  // Row-parallel W4A16 GEMM -> all-reduce without the GEMM's own reduction pass: `partials` are
+  // this rank's fp32 stream-K partials [slots, rows, n] of a [gemm_k, n] weight
+  // (include/b200_decode.h "partials mode"); returns the reduced [rows, n] in `dtype`.
+  torch::Tensor allreduce_partials(const torch::Tensor& partials, int64_t gemm_k,
+                                   torch::ScalarType dtype) const;
+  // ... with the residual add and the RMSNorm that follow fused in as well (one launch):
+  // residual += all-reduced row; returns rms_norm(residual) * weight
+  bool supports_partials_norm(int64_t rows, int64_t n, torch::ScalarType dtype) const;
+  torch::Tensor allreduce_partials_norm(const torch::Tensor& partials, int64_t gemm_k,
+                                        torch::Tensor& residual, const torch::Tensor& weight,
+                                        float eps) const;
+
   b200_ar_comm* comm() const { return comm_; }
 
  private:

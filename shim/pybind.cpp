@@ -44,13 +44,42 @@ PYBIND11_MODULE(_b200_shim, m) {
   m.def("packed_bytes", &marlin::b200_packed_bytes);
   m.def("workspace_bytes", &marlin::b200_workspace_bytes);
 
-  // ---- plugin-level host side (shim/b200_layers.h) -------------------------------------------
   namespace py = pybind11;
+  // ---- tensor-parallel plumbing in the reference's threading model (shim/b200_process_group.h) --
+  py::class_<llm::ProcessGroup>(m, "ProcessGroup")
+      .def("rank", &llm::ProcessGroup::rank)
+      .def("world_size", &llm::ProcessGroup::world_size)
+      .def("allreduce", [](const llm::ProcessGroup& self, torch::Tensor t) { self.allreduce(t); })
+      .def("allgather",
+           [](const llm::ProcessGroup& self, torch::Tensor in, std::vector<torch::Tensor> outs) {
+             self.allgather(in, outs);
+           })
+      .def("gather_from_model_parallel_region",
+           [](llm::ProcessGroup& self, torch::Tensor in) {
+             return llm::gather_from_model_parallel_region(
+                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+           })
+      .def("reduce_from_model_parallel_region",
+           [](llm::ProcessGroup& self, torch::Tensor in) {
+             return llm::reduce_from_model_parallel_region(
+                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+           })
+      .def("scatter_to_model_parallel_region", [](llm::ProcessGroup& self, torch::Tensor in) {
+        return llm::scatter_to_model_parallel_region(
+            in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
+      });
+  m.def("create_process_groups", [](const std::vector<int>& device_indices) {
+    std::vector<torch::Device> devices;
+    for (int i : device_indices) devices.emplace_back(torch::kCUDA, static_cast<c10::DeviceIndex>(i));
+    return llm::ProcessGroup::create_process_groups(devices);
+  });
+
+  // ---- plugin-level host side (shim/b200_layers.h) -------------------------------------------
   py::class_<llm::LlamaDecoderStep>(m, "LlamaDecoderStep")
       .def(py::init([](int64_t hidden, int64_t n_layers, int64_t n_heads, int64_t n_kv_heads,
                        int64_t head_dim, int64_t inter, int64_t vocab, int64_t max_pos, double eps,
                        std::string quant_method, int64_t group_size, bool is_sym,
-                       torch::Tensor inv_freq, torch::Tensor like) {
+                       torch::Tensor inv_freq, torch::Tensor like, llm::ProcessGroup* pg) {
         llm::LlamaArgs a;
         a.hidden_size = hidden;
         a.n_layers = n_layers;
@@ -65,8 +94,13 @@ PYBIND11_MODULE(_b200_shim, m) {
         q.quant_method = std::move(quant_method);
         q.group_size = group_size;
         q.is_sym = is_sym;
-        return std::make_unique<llm::LlamaDecoderStep>(a, q, inv_freq, like.options());
-      }))
+        const llm::ParallelArgs pa(pg ? pg->rank() : 0, pg ? pg->world_size() : 1, pg);
+        return std::make_unique<llm::LlamaDecoderStep>(a, q, inv_freq, like.options(), pa);
+      }),
+           py::arg("hidden"), py::arg("n_layers"), py::arg("n_heads"), py::arg("n_kv_heads"),
+           py::arg("head_dim"), py::arg("inter"), py::arg("vocab"), py::arg("max_pos"), py::arg("eps"),
+           py::arg("quant_method"), py::arg("group_size"), py::arg("is_sym"), py::arg("inv_freq"),
+           py::arg("like"), py::arg("process_group") = nullptr, py::keep_alive<1, 16>())
       .def("load_state_dict",
            [](llm::LlamaDecoderStep& self, const std::unordered_map<std::string, torch::Tensor>& sd) {
              self.load_state_dict(sd);
@@ -92,9 +126,25 @@ PYBIND11_MODULE(_b200_shim, m) {
              p.new_cache_slots = slots;
              p.block_tables = tables;
              p.cu_block_lens = blk_cu;
+             py::gil_scoped_release release;  // ranks driven from Python threads run concurrently
              return self.forward(tokens, positions, p);
            });
 
+  m.def("shard_llama_layer",
+        [](const llm::StateDict& qkv, const llm::StateDict& o, const llm::StateDict& gate_up,
+           const llm::StateDict& down, int64_t n_heads, int64_t n_kv_heads, int64_t head_dim,
+           int64_t inter, std::string quant_method, int64_t group_size, int rank, int world) {
+          llm::LlamaArgs a;
+          a.n_heads = n_heads;
+          a.n_kv_heads = n_kv_heads;
+          a.head_dim = head_dim;
+          a.intermediate_size = inter;
+          llm::QuantArgs q;
+          q.quant_method = std::move(quant_method);
+          q.group_size = group_size;
+          const auto sh = llm::shard_llama_layer(qkv, o, gate_up, down, a, q, rank, world);
+          return std::make_tuple(sh.qkv, sh.o, sh.gate_up, sh.down);
+        });
   py::class_<llm::CudaGraphStep>(m, "CudaGraphStep")
       .def(py::init<>())
       .def("capture",
@@ -128,32 +178,5 @@ PYBIND11_MODULE(_b200_shim, m) {
         return self.replay(tokens, positions, p);
       });
 
-  // ---- tensor-parallel plumbing in the reference's threading model (shim/b200_process_group.h) --
-  py::class_<llm::ProcessGroup>(m, "ProcessGroup")
-      .def("rank", &llm::ProcessGroup::rank)
-      .def("world_size", &llm::ProcessGroup::world_size)
-      .def("allreduce", [](const llm::ProcessGroup& self, torch::Tensor t) { self.allreduce(t); })
-      .def("allgather",
-           [](const llm::ProcessGroup& self, torch::Tensor in, std::vector<torch::Tensor> outs) {
-             self.allgather(in, outs);
-           })
-      .def("gather_from_model_parallel_region",
-           [](llm::ProcessGroup& self, torch::Tensor in) {
-             return llm::gather_from_model_parallel_region(
-                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
-           })
-      .def("reduce_from_model_parallel_region",
-           [](llm::ProcessGroup& self, torch::Tensor in) {
-             return llm::reduce_from_model_parallel_region(
-                 in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
-           })
-      .def("scatter_to_model_parallel_region", [](llm::ProcessGroup& self, torch::Tensor in) {
-        return llm::scatter_to_model_parallel_region(
-            in, llm::ParallelArgs(self.rank(), self.world_size(), &self));
-      });
-  m.def("create_process_groups", [](const std::vector<int>& device_indices) {
-    std::vector<torch::Device> devices;
-    for (int i : device_indices) devices.emplace_back(torch::kCUDA, static_cast<c10::DeviceIndex>(i));
-    return llm::ProcessGroup::create_process_groups(devices);
-  });
+
 }

@@ -188,3 +188,52 @@ def test_cpp_cuda_graph_step_replays_like_eager():
     bad[2], bad[3] = bad[2][:-1], bad[3][:-1]                  # one sequence fewer than captured
     with pytest.raises(RuntimeError, match="batch size"):
         step.replay(*bad)
+
+
+@pytest.mark.parametrize("method", ["awq", "gptq"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cpp_tensor_parallel_shards_are_slices_of_the_full_weight(method, world):
+    """shard_llama_layer (C++, views of the checkpoint tensors): dequantising a rank's shard gives
+    exactly the q | k | v / gate | up columns (kv heads replicated when n_kv_heads < world) or the
+    input rows that the rank owns in the dequantised unsharded weight."""
+    from oracle import quant
+    shim = _shim()
+    H, Hkv, D, I, h, g = 8, 2, 128, 1024, 512, 128
+    shapes = dict(qkv=(h, (H + 2 * Hkv) * D), o=(H * D, h), gate_up=(h, 2 * I), down=(I, h))
+    full, dense = {}, {}
+    for i, (name, (K, N)) in enumerate(shapes.items()):
+        ck = (quant.random_awq_checkpoint if method == "awq" else quant.random_gptq_checkpoint)(K, N, g, seed=i)
+        full[name] = {k: ck[k] for k in ("qweight", "qzeros", "scales") if ck.get(k) is not None}
+        dense[name] = _dequant(quant, method, full[name], g)
+
+    def kv_head(rank):
+        return rank * (Hkv // world) if Hkv >= world else rank // (world // Hkv)
+
+    for rank in range(world):
+        qkv, o, gu, down = shim.shard_llama_layer(full["qkv"], full["o"], full["gate_up"], full["down"],
+                                                  H, Hkv, D, I, method, g, rank, world)
+        Hl, Hkvl, Il = H // world, max(1, Hkv // world), I // world
+        q_cols = slice(rank * Hl * D, (rank + 1) * Hl * D)
+        k_cols = slice(H * D + kv_head(rank) * D, H * D + (kv_head(rank) + Hkvl) * D)
+        v_cols = slice((H + Hkv) * D + kv_head(rank) * D, (H + Hkv) * D + (kv_head(rank) + Hkvl) * D)
+        want_qkv = torch.cat([dense["qkv"][:, c] for c in (q_cols, k_cols, v_cols)], dim=1)
+        assert torch.equal(_dequant(quant, method, qkv, g), want_qkv)
+        want_gu = torch.cat([dense["gate_up"][:, rank * Il:(rank + 1) * Il],
+                             dense["gate_up"][:, I + rank * Il: I + (rank + 1) * Il]], dim=1)
+        assert torch.equal(_dequant(quant, method, gu, g), want_gu)
+        assert torch.equal(_dequant(quant, method, o, g), dense["o"][rank * Hl * D:(rank + 1) * Hl * D])
+        assert torch.equal(_dequant(quant, method, down, g), dense["down"][rank * Il:(rank + 1) * Il])
+    with pytest.raises(RuntimeError, match="quant groups"):     # 1024 / 16 = 64-row shards < group 128
+        shim.shard_llama_layer(full["qkv"], full["o"], full["gate_up"], full["down"], 16, Hkv, 32, I, method,
+                               g, 0, 16)
+
+
+def _dequant(quant, method, t, g):
+    """checkpoint tensors -> dense bf16 [K, N] with the oracle's unpackers."""
+    if method == "awq":
+        q, z = quant.unpack_awq(t["qweight"].contiguous()), quant.unpack_awq(t["qzeros"].contiguous())
+    else:
+        q = quant.unpack_gptq(t["qweight"].contiguous())
+        z = (quant.unpack_gptq_zeros(t["qzeros"].contiguous(), plus_one=True) if "qzeros" in t
+             else np.full((q.shape[0] // g, q.shape[1]), 8, dtype=q.dtype))
+    return quant.dequant(q, z, t["scales"].contiguous(), g)

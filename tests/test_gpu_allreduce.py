@@ -243,3 +243,77 @@ def test_cpp_process_groups_in_one_process():
     sc = pgs[1].scatter_to_model_parallel_region(xs[1])
     assert torch.equal(sc, xs[1][:, 4096 // world: 2 * 4096 // world])
     del pgs
+
+
+@_STAGED
+@pytest.mark.parametrize("fuse", [True, False])
+def test_cpp_tensor_parallel_decode_step(fuse):
+    """The C++ LlamaDecoderStep under TP=2, both ranks in this process (one Python thread each, the
+    GIL is released inside forward): every rank ends with the same logits bit for bit, and they
+    agree with the single-GPU step up to the summation order of the row-parallel reductions."""
+    import threading
+    from tests.test_cpp_host import CFG, _inv_freq, _state_dict, _shim
+    from scalellm_b200.decode_step import BlockPool, StepBuffers, build_decode_batch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    shim = _shim()
+    c, world, bs, B, n_blocks = CFG, 2, 16, 5, 64
+    sd = _state_dict(seed=4)
+    pgs = shim.create_process_groups(list(range(world)))
+
+    def make(dev, pg):
+        m = shim.LlamaDecoderStep(c["hidden"], c["n_layers"], c["n_heads"], c["n_kv_heads"], c["head_dim"],
+                                  c["inter"], c["vocab"], c["max_pos"], c["eps"], "awq", 128, False,
+                                  _inv_freq(), torch.empty(0, dtype=torch.bfloat16, device=dev), pg)
+        m.load_state_dict(sd)
+        m.fuse_partials = fuse
+        return m
+
+    g = torch.Generator().manual_seed(3)
+    full_k = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g).bfloat16()
+              for _ in range(c["n_layers"])]
+    full_v = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g).bfloat16()
+              for _ in range(c["n_layers"])]
+    single = make("cuda:0", None)
+    single.set_kv_caches([k.to("cuda:0") for k in full_k], [v.to("cuda:0") for v in full_v], bs)
+    ranks = []
+    for r in range(world):                                    # n_kv_heads == world: rank r owns kv head r
+        m = make(f"cuda:{r}", pgs[r])
+        m.set_kv_caches([k[:, r:r + 1].contiguous().to(f"cuda:{r}") for k in full_k],
+                        [v[:, r:r + 1].contiguous().to(f"cuda:{r}") for v in full_v], bs)
+        ranks.append(m)
+
+    pool = BlockPool(n_blocks, bs, seed=1)
+    kv = [37, 64, 5, 100, 17]
+    for k in kv:
+        pool.add_sequence(k + 8)
+    hb = build_decode_batch(pool, kv, [1] * B, c["vocab"], seed=9)
+
+    def args_on(dev):
+        bufs = StepBuffers(torch.device(dev), 16, 8, 256)
+        tokens, positions, p = bufs.upload(hb)
+        return (tokens, positions, p.q_cu_seq_lens, p.kv_cu_seq_lens, p.kv_max_seq_len, p.q_max_seq_len,
+                p.new_cache_slots, p.block_tables, p.cu_block_lens)
+
+    want = single.forward(*args_on("cuda:0")).float().cpu()
+    outs, errs = [None] * world, []
+
+    def run(r):
+        try:
+            with torch.cuda.device(r):
+                outs[r] = ranks[r].forward(*args_on(f"cuda:{r}"))
+                torch.cuda.synchronize(r)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs and all(not t.is_alive() for t in ts), errs
+    got = [o.float().cpu() for o in outs]
+    assert torch.equal(got[0], got[1])
+    assert got[0].shape == want.shape
+    assert torch.allclose(got[0], want, rtol=2e-2, atol=2e-2 * want.abs().max().item())
+    del ranks, pgs
