@@ -425,6 +425,13 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+// transpose of an 8x8 b16 matrix held one 32-bit register per lane (row lane / 4, columns
+// 2 (lane % 4), +1): turns an accumulator-layout pair into a B-operand-layout pair
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 // 128-byte swizzle as the TMA applies it: 16-byte chunk index ^= (address bits [7,10))
 __device__ __forceinline__ uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
@@ -756,7 +763,16 @@ struct ItemMeta {
   int tbl_buf;                     // stage B: which of the 3 table buffers holds its window
 };
 
-template <typename T, int D, int OCC>
+// TR = 1 (B200_ATTN_TR=1, decode shapes with group * max_q_len <= 8 packed rows): the transposed
+// tile.  S^T[16 keys x 8 rows] = K . Q^T and O^T[D x 8 rows] += V^T . P^T put the keys (and the
+// head dimension) on the MMA's M and the query rows on its 8-wide N: half the HMMAs per tile, 4
+// instead of 8 scores per lane in the softmax, an O accumulator of D/4 instead of D/2 registers
+// and Q fragments of half the size — the instruction chain per tile and the register count are
+// what bound the default variant (profiles/r01_ncu_paged_attn_stalls.md).  The fragment algebra
+// is modelled lane by lane in tools/attn_tr_model.py.  Row blocks are 8 rows instead of 16; the
+// plan selects TR only when all packed rows fit one block, so the work partition (and the combine
+// pass that mirrors it) is the same as the default's.
+template <typename T, int D, int OCC, int TR = 0>
 __global__ void __launch_bounds__(32, (D <= 128 ? (OCC ? ATT_OCC_CTAS : 8) : 3))
 paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                           const __grid_constant__ CUtensorMap vmap, const AttnParams p,
@@ -766,7 +782,9 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = OCC ? 2 : Cfg::STAGES;
   constexpr int P_TBL = att_p_tbl(OCC);
-  constexpr int KS = D / 16, NB = D / 8;
+  constexpr int KS = D / 16, NB = TR ? D / 16 : D / 8;  // NB: accumulator blocks of O (O^T)
+  constexpr int ROWS = TR ? 8 : 16;                      // packed (q token, head) rows per block
+  constexpr int QR = TR ? 2 : 4;                         // Q fragment registers per k-step
   constexpr int ROWB = D * (int)sizeof(T);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
@@ -819,12 +837,12 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     const int t_lo = it.t0, t_hi = it.t_hi;
     it.n_tiles = 0;
     it.n_ent = 0;
-    const int rows_total = it.q_len * G, row0 = it.rb * 16;
+    const int rows_total = it.q_len * G, row0 = it.rb * ROWS;
     if (!it.valid || row0 >= rows_total) {
       it.q_len = it.valid ? it.q_len : 0;
       return;
     }
-    const int n_rows = min(16, rows_total - row0);
+    const int n_rows = min(ROWS, rows_total - row0);
     const int q_pos0 = it.kv_len - it.q_len;
     const int qi_min = row0 / G, qi_max = (row0 + n_rows - 1) / G;
     it.kv_end = q_pos0 + qi_max + 1;
@@ -870,12 +888,12 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   };
 
   // query fragments of an item (A operand of S = Q K^T), rows beyond the item's rows are zero
-  auto load_q = [&](const ItemMeta& it, uint32_t (&qa)[KS][4]) {
-    const int rows_total = it.q_len * G, row0 = it.rb * 16;
-    const int n_rows = min(16, rows_total - row0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = (lane >> 2) + 8 * h;
+  auto load_q = [&](const ItemMeta& it, uint32_t (&qa)[KS][QR]) {
+    const int rows_total = it.q_len * G, row0 = it.rb * ROWS;
+    const int n_rows = min(ROWS, rows_total - row0);
+    if constexpr (TR) {
+      // B operand of S^T = K Q^T: lane (g, t) holds Q[row g][16 ks + 2t, +1] and [.. + 8, + 9]
+      const int r = lane >> 2;
       const bool ok = it.n_tiles > 0 && r < n_rows;
       const int row = row0 + (ok ? r : 0), qi = ok ? row / G : 0;
       const int head = it.kvh * G + (ok ? row - qi * G : 0);
@@ -883,8 +901,23 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                       (int64_t)head * p.q_stride_h + (lane & 3) * 2;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        qa[ks][h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
-        qa[ks][2 + h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
+        qa[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
+        qa[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = (lane >> 2) + 8 * h;
+        const bool ok = it.n_tiles > 0 && r < n_rows;
+        const int row = row0 + (ok ? r : 0), qi = ok ? row / G : 0;
+        const int head = it.kvh * G + (ok ? row - qi * G : 0);
+        const T* qrow = static_cast<const T*>(p.q) + (int64_t)(it.q_begin + qi) * p.q_stride_t +
+                        (int64_t)head * p.q_stride_h + (lane & 3) * 2;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          qa[ks][h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
+          qa[ks][2 + h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
+        }
       }
     }
   };
@@ -899,7 +932,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   stageB(sB);                       // its table window is in flight into the third buffer
   ItemMeta sA = stageA(stage0());   // lengths in flight
   int s0 = stage0();
-  uint32_t qa[KS][4], qn[KS][4];
+  uint32_t qa[KS][QR], qn[KS][QR];
   load_q(cur, qa);
   load_q(nxt, qn);
 
@@ -924,13 +957,14 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   const int lm = lane >> 3, lr = lane & 7;
   while (cur.valid) {
     // ---- per-item row bookkeeping ------------------------------------------------------
-    const int rows_total = cur.q_len * G, row0 = cur.rb * 16;
-    const int n_rows = min(16, rows_total - row0);
+    const int rows_total = cur.q_len * G, row0 = cur.rb * ROWS;
+    const int n_rows = min(ROWS, rows_total - row0);
     const int q_pos0 = cur.kv_len - cur.q_len;
+    // the two rows a lane works for: rows g, g + 8 of the block (TR: rows 2t, 2t + 1)
     int row_end[2], row_begin[2], row_head[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int r = (lane >> 2) + 8 * h;
+      const int r = TR ? (lane & 3) * 2 + h : (lane >> 2) + 8 * h;
       const bool ok = r < n_rows;
       const int row = row0 + (ok ? r : 0), qi = row / G;
       row_head[h] = cur.kvh * G + (row - qi * G);
@@ -969,79 +1003,144 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
         __syncwarp();
       }
 
-      float sacc[2][4];
+      if constexpr (TR) {
+        // S^T = K Q^T: A = the tile's 16 keys x 16 dims per k-step (ldmatrix), B = Q^T registers;
+        // two accumulators (even / odd k-steps) halve the dependent HMMA chain
+        float sacc[2][4];
 #pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
+        for (int e = 0; e < 4; ++e) sacc[0][e] = sacc[1][e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
-#pragma unroll
-        for (int kq = 0; kq < KS / 2; ++kq) {
-          uint32_t bf[4];
-          const uint32_t off = (uint32_t)((nb * 8 + lr) * ROWB + (kq * 32 + lm * 8) * (int)sizeof(T));
-          ldsm_x4(bf, swz128(k_base + off));
-          mma_16816<T>(sacc[nb], qa[2 * kq], bf[0], bf[1]);
-          mma_16816<T>(sacc[nb], qa[2 * kq + 1], bf[2], bf[3]);
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t af[4];
+          const uint32_t off =
+              (uint32_t)(((lm & 1) * 8 + lr) * ROWB + (ks * 16 + (lm >> 1) * 8) * (int)sizeof(T));
+          ldsm_x4(af, swz128(k_base + off));
+          mma_16816<T>(sacc[ks & 1], af, qa[ks][0], qa[ks][1]);
         }
-      }
-
-      float corr[2];
-      bool need_rescale = false;
+        // lane (g, t): keys {g, g + 8} x rows {2t, 2t + 1}; element 2 hh + h = (key g + 8 hh, row 2t + h)
+        float corr[2], pk[2][2];
+        bool need_rescale = false;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float x[4];
-        float mx = m[h];
+        for (int h = 0; h < 2; ++h) {
+          float x[2];
+          float mx = m[h];
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int pos = pos0 + nb * 8 + (lane & 3) * 2 + e;
-            const float sc = sacc[nb][2 * h + e];
+          for (int hh = 0; hh < 2; ++hh) {
+            const int pos = pos0 + (lane >> 2) + 8 * hh;
+            const float sc = sacc[0][2 * hh + h] + sacc[1][2 * hh + h];
             float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
             v = fmaf(slope_log2[h], (float)pos, v);
             const bool ok = pos >= row_begin[h] && pos < row_end[h];
-            x[nb * 2 + e] = ok ? v : -INFINITY;
-            mx = fmaxf(mx, x[nb * 2 + e]);
+            x[hh] = ok ? v : -INFINITY;
+            mx = fmaxf(mx, x[hh]);
           }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float ms = (mx == -INFINITY) ? 0.f : mx;
-        corr[h] = (mx == m[h]) ? 1.f : exp2f(m[h] - ms);
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          x[c] = exp2f(x[c] - ms);
-          sum += x[c];
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));   // over the 8 key groups g
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          const float ms = (mx == -INFINITY) ? 0.f : mx;
+          corr[h] = (mx == m[h]) ? 1.f : exp2f(m[h] - ms);
+          pk[0][h] = exp2f(x[0] - ms);
+          pk[1][h] = exp2f(x[1] - ms);
+          l[h] = fmaf(l[h], corr[h], pk[0][h] + pk[1][h]);
+          m[h] = mx;
+          need_rescale |= (corr[h] != 1.f);
         }
-        l[h] = fmaf(l[h], corr[h], sum);
-        m[h] = mx;
-        need_rescale |= (corr[h] != 1.f);
-        sacc[0][2 * h] = x[0];
-        sacc[0][2 * h + 1] = x[1];
-        sacc[1][2 * h] = x[2];
-        sacc[1][2 * h + 1] = x[3];
-      }
-      if (__any_sync(0xffffffffu, need_rescale)) {
+        if (__any_sync(0xffffffffu, need_rescale)) {
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          o[nb][0] *= corr[0];
-          o[nb][1] *= corr[0];
-          o[nb][2] *= corr[1];
-          o[nb][3] *= corr[1];
+          for (int nb = 0; nb < NB; ++nb) {
+            o[nb][0] *= corr[0];
+            o[nb][1] *= corr[1];
+            o[nb][2] *= corr[0];
+            o[nb][3] *= corr[1];
+          }
         }
-      }
-      uint32_t pa[4];
-      pa[0] = Num<T>::pack(sacc[0][0], sacc[0][1]);
-      pa[1] = Num<T>::pack(sacc[0][2], sacc[0][3]);
-      pa[2] = Num<T>::pack(sacc[1][0], sacc[1][1]);
-      pa[3] = Num<T>::pack(sacc[1][2], sacc[1][3]);
+        // P^T into the B-operand layout (keys 2t, 2t+1 | +8 of row g): transpose the two 8x8 blocks
+        const uint32_t pb0 = movmatrix_trans(Num<T>::pack(pk[0][0], pk[0][1]));
+        const uint32_t pb1 = movmatrix_trans(Num<T>::pack(pk[1][0], pk[1][1]));
+        // O^T += V^T P^T: A = 16 dims x 16 keys per block (ldmatrix.trans of V's [key][dim] rows)
 #pragma unroll
-      for (int dq = 0; dq < NB / 2; ++dq) {
-        uint32_t bf[4];
-        const uint32_t off =
-            (uint32_t)(((lm & 1) * 8 + lr) * ROWB + (dq * 16 + (lm >> 1) * 8) * (int)sizeof(T));
-        ldsm_x4_trans(bf, swz128(v_base + off));
-        mma_16816<T>(o[2 * dq], pa, bf[0], bf[1]);
-        mma_16816<T>(o[2 * dq + 1], pa, bf[2], bf[3]);
+        for (int mb = 0; mb < NB; ++mb) {
+          uint32_t af[4];
+          const uint32_t off =
+              (uint32_t)(((lm >> 1) * 8 + lr) * ROWB + (mb * 16 + (lm & 1) * 8) * (int)sizeof(T));
+          ldsm_x4_trans(af, swz128(v_base + off));
+          mma_16816<T>(o[mb], af, pb0, pb1);
+        }
+      } else {
+        float sacc[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
+#pragma unroll
+          for (int kq = 0; kq < KS / 2; ++kq) {
+            uint32_t bf[4];
+            const uint32_t off = (uint32_t)((nb * 8 + lr) * ROWB + (kq * 32 + lm * 8) * (int)sizeof(T));
+            ldsm_x4(bf, swz128(k_base + off));
+            mma_16816<T>(sacc[nb], qa[2 * kq], bf[0], bf[1]);
+            mma_16816<T>(sacc[nb], qa[2 * kq + 1], bf[2], bf[3]);
+          }
+        }
+
+        float corr[2];
+        bool need_rescale = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float x[4];
+          float mx = m[h];
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int pos = pos0 + nb * 8 + (lane & 3) * 2 + e;
+              const float sc = sacc[nb][2 * h + e];
+              float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
+              v = fmaf(slope_log2[h], (float)pos, v);
+              const bool ok = pos >= row_begin[h] && pos < row_end[h];
+              x[nb * 2 + e] = ok ? v : -INFINITY;
+              mx = fmaxf(mx, x[nb * 2 + e]);
+            }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float ms = (mx == -INFINITY) ? 0.f : mx;
+          corr[h] = (mx == m[h]) ? 1.f : exp2f(m[h] - ms);
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            x[c] = exp2f(x[c] - ms);
+            sum += x[c];
+          }
+          l[h] = fmaf(l[h], corr[h], sum);
+          m[h] = mx;
+          need_rescale |= (corr[h] != 1.f);
+          sacc[0][2 * h] = x[0];
+          sacc[0][2 * h + 1] = x[1];
+          sacc[1][2 * h] = x[2];
+          sacc[1][2 * h + 1] = x[3];
+        }
+        if (__any_sync(0xffffffffu, need_rescale)) {
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            o[nb][0] *= corr[0];
+            o[nb][1] *= corr[0];
+            o[nb][2] *= corr[1];
+            o[nb][3] *= corr[1];
+          }
+        }
+        uint32_t pa[4];
+        pa[0] = Num<T>::pack(sacc[0][0], sacc[0][1]);
+        pa[1] = Num<T>::pack(sacc[0][2], sacc[0][3]);
+        pa[2] = Num<T>::pack(sacc[1][0], sacc[1][1]);
+        pa[3] = Num<T>::pack(sacc[1][2], sacc[1][3]);
+#pragma unroll
+        for (int dq = 0; dq < NB / 2; ++dq) {
+          uint32_t bf[4];
+          const uint32_t off =
+              (uint32_t)(((lm & 1) * 8 + lr) * ROWB + (dq * 16 + (lm >> 1) * 8) * (int)sizeof(T));
+          ldsm_x4_trans(bf, swz128(v_base + off));
+          mma_16816<T>(o[2 * dq], pa, bf[0], bf[1]);
+          mma_16816<T>(o[2 * dq + 1], pa, bf[2], bf[3]);
+        }
       }
       __syncwarp();
       if (boundary) fence_proxy_async_smem();
@@ -1050,31 +1149,65 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     }
 
     // ---- finalize the item: normalised partial O and LSE (log2 domain) ------------------
+    if constexpr (TR) {
+      // lane (g, t) owns O^T[dims 16 mb + g, + 8][rows 2t, 2t + 1]
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
-      l[h] += __shfl_xor_sync(0xffffffffu, l[h], 2);
-      const int r = (lane >> 2) + 8 * h;
-      if (cur.n_tiles > 0 && r < n_rows) {
-        const int row = row0 + r, qi = row / G, head = cur.kvh * G + (row - qi * G);
-        const float inv = 1.f / l[h];
-        if (p.n_splits == 1) {
-          T* dst = static_cast<T*>(p.out) + (int64_t)(cur.q_begin + qi) * p.o_stride_t +
-                   (int64_t)head * p.o_stride_h + (lane & 3) * 2;
+      for (int h = 0; h < 2; ++h) {
+        l[h] += __shfl_xor_sync(0xffffffffu, l[h], 4);
+        l[h] += __shfl_xor_sync(0xffffffffu, l[h], 8);
+        l[h] += __shfl_xor_sync(0xffffffffu, l[h], 16);
+        const int r = (lane & 3) * 2 + h;
+        if (cur.n_tiles > 0 && r < n_rows) {
+          const int row = row0 + r, qi = row / G, head = cur.kvh * G + (row - qi * G);
+          const float inv = 1.f / l[h];
+          if (p.n_splits == 1) {
+            T* dst = static_cast<T*>(p.out) + (int64_t)(cur.q_begin + qi) * p.o_stride_t +
+                     (int64_t)head * p.o_stride_h + (lane >> 2);
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            *reinterpret_cast<uint32_t*>(dst + nb * 8) =
-                Num<T>::pack(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
-        } else {
-          const int64_t wrow = ((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head;
-          float* dst = p.ws_o + (wrow * p.n_splits + cur.split) * D + (lane & 3) * 2;
+            for (int mb = 0; mb < NB; ++mb) {
+              dst[mb * 16] = Num<T>::from_f(o[mb][h] * inv);
+              dst[mb * 16 + 8] = Num<T>::from_f(o[mb][2 + h] * inv);
+            }
+          } else {
+            const int64_t wrow = ((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head;
+            float* dst = p.ws_o + (wrow * p.n_splits + cur.split) * D + (lane >> 2);
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            *reinterpret_cast<float2*>(dst + nb * 8) =
-                make_float2(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
-          if ((lane & 3) == 0) p.ws_lse[wrow * p.n_splits + cur.split] = m[h] + log2f(l[h]);
+            for (int mb = 0; mb < NB; ++mb) {
+              dst[mb * 16] = o[mb][h] * inv;
+              dst[mb * 16 + 8] = o[mb][2 + h] * inv;
+            }
+            if ((lane >> 2) == 0) p.ws_lse[wrow * p.n_splits + cur.split] = m[h] + log2f(l[h]);
+          }
         }
       }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
+        l[h] += __shfl_xor_sync(0xffffffffu, l[h], 2);
+        const int r = (lane >> 2) + 8 * h;
+        if (cur.n_tiles > 0 && r < n_rows) {
+          const int row = row0 + r, qi = row / G, head = cur.kvh * G + (row - qi * G);
+          const float inv = 1.f / l[h];
+          if (p.n_splits == 1) {
+            T* dst = static_cast<T*>(p.out) + (int64_t)(cur.q_begin + qi) * p.o_stride_t +
+                     (int64_t)head * p.o_stride_h + (lane & 3) * 2;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+              *reinterpret_cast<uint32_t*>(dst + nb * 8) =
+                  Num<T>::pack(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
+          } else {
+            const int64_t wrow = ((int64_t)cur.b * p.max_q_len + qi) * p.n_heads + head;
+            float* dst = p.ws_o + (wrow * p.n_splits + cur.split) * D + (lane & 3) * 2;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+              *reinterpret_cast<float2*>(dst + nb * 8) =
+                  make_float2(o[nb][2 * h] * inv, o[nb][2 * h + 1] * inv);
+            if ((lane & 3) == 0) p.ws_lse[wrow * p.n_splits + cur.split] = m[h] + log2f(l[h]);
+          }
+        }
+      }
+
     }
 
     // ---- rotate: every pipeline slot advances one stage ---------------------------------------
@@ -1085,7 +1218,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) qa[ks][e] = qn[ks][e];
+        for (int e = 0; e < QR; ++e) qa[ks][e] = qn[ks][e];
       stageC();                       // sB's table window (requested one rotation ago) has landed
       nxt = sB;
       sB = sA;                        // its lengths were requested one rotation ago
@@ -1315,7 +1448,18 @@ static int attn_occ() {
   return v;
 }
 
+// B200_ATTN_TR=1: transposed-tile instantiation of the stream kernel (TR above) for shapes whose
+// packed rows fit 8: group * max_q_len <= 8 (decode), head_dim <= 128
+static int attn_tr() {
+  static const int v = [] {
+    const char* e = getenv("B200_ATTN_TR");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+
 struct AttnPlan {
+  int tr;                    // stream kernel: transposed tile, 8-row blocks
   int impl, R, n_hg, n_rb, n_splits, tps, warps;
   int ntm, tpw, n_seq;       // stream kernel
   int64_t total_tiles;
@@ -1348,6 +1492,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
   }
   if (pl.impl == 2) {
     pl.warps = 1;
+    pl.tr = attn_tr() && head_dim <= 128 && max_q_len * group <= 8;  // => one 8-row block
     pl.ntm = std::max(1, (max_kv_len + ATT_TILE - 1) / ATT_TILE);
     pl.n_seq = (int)(pl.grid_y * pl.grid_z);
     pl.total_tiles = (int64_t)pl.n_seq * pl.ntm;
@@ -1364,6 +1509,7 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
     if (pl.n_splits > 256) {                                    // absurdly long context with tiny blocks
       pl.impl = 1;
       pl.warps = 4;
+      pl.tr = 0;
     } else {
       pl.tps = pl.tpw;
       return pl;
@@ -1432,21 +1578,21 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   int rc;
   if (pl.impl == 2) {
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
-    if (D <= 128 && attn_occ()) {
-      constexpr size_t psmem = (size_t)2 * 2 * ATT_TILE * D * sizeof(T) +
-                               3 * ATT_P_TBL_OCC * sizeof(int32_t) + 2 * 8 + 128;
-      auto kernel = paged_attn_persist_kernel<T, D, 1>;
-      B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap,
-                        vmap, p, (int64_t)pl.total_tiles, (int)pl.n_seq);
-    } else {
-      constexpr size_t psmem = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
-                               3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
-      auto kernel = paged_attn_persist_kernel<T, D, 0>;
-      B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap,
-                        vmap, p, (int64_t)pl.total_tiles, (int)pl.n_seq);
+    constexpr size_t psmem_occ = (size_t)2 * 2 * ATT_TILE * D * sizeof(T) +
+                                 3 * ATT_P_TBL_OCC * sizeof(int32_t) + 2 * 8 + 128;
+    constexpr size_t psmem_def = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
+                                 3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
+    const bool occ = D <= 128 && attn_occ();
+    const size_t psmem = occ ? psmem_occ : psmem_def;
+    void (*kernel)(const CUtensorMap, const CUtensorMap, const AttnParams, int64_t, int) =
+        paged_attn_persist_kernel<T, D, 0>;
+    if constexpr (D <= 128) {
+      if (occ) kernel = pl.tr ? paged_attn_persist_kernel<T, D, 1, 1> : paged_attn_persist_kernel<T, D, 1>;
+      else if (pl.tr) kernel = paged_attn_persist_kernel<T, D, 0, 1>;
     }
+    B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_stream", kernel, grid, 32, psmem, st, kmap, vmap, p,
+                      (int64_t)pl.total_tiles, (int)pl.n_seq);
     rc = B200_OK;
   } else if (pl.impl == 1 && pl.warps == 1) {
     rc = launch_kernel(paged_attn_mma_kernel<T, D, 1>, attn_mma_smem_bytes<T, D, 1>(), 32, kmap,

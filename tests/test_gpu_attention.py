@@ -94,6 +94,22 @@ def test_variants(D, cap, alibi, win):
     check(out, ref, torch.bfloat16, f"D={D} cap={cap} alibi={alibi} win={win}")
 
 
+@pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
+                    reason="staged: written for the B200_ATTN_TR=1 variant, not yet run on a GPU")
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("H,Hkv,q_lens", [(8, 2, [2, 1, 2]), (8, 1, [1, 1, 1]), (4, 4, [5, 8, 1])])
+@pytest.mark.parametrize("cap,alibi,win", [(0.0, False, -1), (50.0, False, -1), (0.0, True, -1),
+                                           (0.0, False, 0), (0.0, False, 10), (30.0, True, 100)])
+def test_variants_with_at_most_8_packed_rows(D, H, Hkv, q_lens, cap, alibi, win):
+    """Shapes the transposed-tile instantiation takes (group * max_q_len <= 8) with every masking /
+    bias variant and a causal diagonal inside the row block; runs on whatever kernel is selected."""
+    kv_lens = [127, 1000, 40]
+    c = make_case(q_lens, kv_lens, H, Hkv, D, 8, torch.bfloat16, seed=D + H)
+    slopes = torch.rand(H) * 0.1 if alibi else None
+    out, ref = run_both(c, D ** -0.5, slopes, cap, win)
+    check(out, ref, torch.bfloat16, f"D={D} H={H}/{Hkv} q={q_lens} cap={cap} alibi={alibi} win={win}")
+
+
 def test_long_context_many_splits():
     c = make_case([1, 1], [20000, 9000], 32, 8, 128, 16, torch.bfloat16, seed=3)
     out, ref = run_both(c, 128 ** -0.5)

@@ -240,3 +240,19 @@ def test_w4a16_barrier_protocol_model():
             sim.check(variants=(0, 1), trials=100, seed=2)
     finally:
         sim.Sim.act_producer = good
+
+
+def test_attention_transposed_tile_fragment_algebra():
+    """tools/attn_tr_model.py: the transposed attention tile (S^T = K Q^T, O^T = V^T P^T with
+    ldmatrix / movmatrix fragments) restated lane by lane reproduces softmax(QK^T)V, for 1..8
+    packed rows, a ragged causal end (stale K, NaN V past the end) and head_dim 64."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "attn_tr_model", os.path.join(os.path.dirname(__file__), "..", "tools", "attn_tr_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for n_rows in (1, 4, 7, 8):
+        assert mod.check(seed=n_rows, n_rows=n_rows) < 5e-3
+    assert mod.check(seed=9, n_rows=4, n_tiles=4, kv_end=53) < 5e-3
+    assert mod.check(seed=3, D=64, n_rows=2, n_tiles=3, kv_end=40) < 5e-3

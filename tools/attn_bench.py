@@ -21,13 +21,18 @@ def main():
         one_shape(64, 2071, 32, 8, 128, max_kv=2071, bss=(8,))
         one_shape(64, 2064, 32, 8, 128, max_kv=2064, bss=(8,))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "variant":
+        # A/B of the opt-in instantiations (B200_ATTN_OCC / B200_ATTN_TR, read once per process):
+        # the default plan only, benchmark shape, block_size 8, no reference kernel
+        one_shape(64, 2048, 32, 8, 128, bss=(8,), only_auto=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "locality":
         shapes = [(64, 2048, 32, 8, 128), (512, 2048, 4, 1, 128), (128, 2048, 16, 4, 128)]
     for shp in shapes:
         one_shape(*shp)
 
 
-def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
+def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128), only_auto=False):
     max_kv = max_kv or S
     print(f"--- B={B} S={S} max_kv={max_kv} H={H} Hkv={Hkv} D={D}")
     for bs in bss:
@@ -52,6 +57,8 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
         configs = [("mma W4 s=2", {"B200_ATTN_IMPL": "mma", "B200_ATTN_WARPS": "4", "B200_ATTN_SPLITS": "2"}),
                    ("stream t32", {"B200_ATTN_TPS": "32"}),
                    ("stream auto", {})]
+        if only_auto:
+            configs = [(f"occ={os.environ.get('B200_ATTN_OCC', '0')} tr={os.environ.get('B200_ATTN_TR', '0')}", {})]
         for tag, env in configs:
             for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
                 os.environ.pop(k, None)
@@ -72,7 +79,7 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128)):
                   flush=True)
         for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
             os.environ.pop(k, None)
-        ref = load_reference_kernels()
+        ref = None if only_auto else load_reference_kernels()
         if ref is not None and D == 128:
             # GPU baseline beside ours: the reference's own sm80 mma.sync
             # kernel, compiled for sm_100a from /root/reference (oracle/ref/Makefile), same tensors

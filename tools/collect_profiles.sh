@@ -19,6 +19,7 @@ if ls $G/micro_*.log > /dev/null 2>&1; then
 fi
 [ -s $G/w4_trace.log ] && { echo "# $R: device-side clock64 trace of w4a16_gemm_kernel (tools/w4_trace.py)"; echo '```'; cat $G/w4_trace.log; echo '```'; } > $P/${R}_w4_trace.md
 [ -s $G/attn_bench.log ] && { echo "# $R: attention kernel-only timings (tools/attn_bench.py)"; echo '```'; cat $G/attn_bench.log; echo '```'; } > $P/${R}_attn_bench.md
+[ -s $G/attn_variants.log ] && { echo "# $R: kernel-only A/B of the attention stream kernel's instantiations (tools/attn_bench.py variant)"; echo '```'; grep "^attn\|^---" $G/attn_variants.log; echo '```'; } > $P/${R}_attn_variants.md
 [ -s $G/step_timeline.md ] && cp $G/step_timeline.md $P/${R}_step_timeline.md
 [ -s $G/w4_variants.jsonl ] && { echo "# $R: GEMM-only A/B of the W4A16 kernel variants (tools/w4_variant_bench.py; us per launch, CUDA graph replay, M = 64)"; echo '```'; cat $G/w4_variants.jsonl; echo '```'; } > $P/${R}_w4_variants.md
 # A/B runs of the opt-in variants: one line per run (value, ms/step, GEMM launch times)

@@ -112,14 +112,27 @@ if has refk; then
   cat $OUT/w4_ref_bench.log | tee -a $OUT/summary.txt
 fi
 if has occ; then
-  # opt-in high-occupancy attention instantiation (B200_ATTN_OCC=1): parity, then kernel-only timing
-  B200_ATTN_OCC=1 timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_decode_step.py \
-      -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_attention_occ.log 2>&1
-  echo "pytest attention[occ] rc=$? : $(tail -1 $OUT/pytest_attention_occ.log)" | tee -a $OUT/summary.txt
-  for v in 0 1; do
-    B200_ATTN_OCC=$v timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
-        > $OUT/bench_occ$v.json 2> $OUT/bench_occ$v.err
-    echo "bench occ=$v rc=$? $(tail -1 $OUT/bench_occ$v.json | head -c 200)" | tee -a $OUT/summary.txt
+  # opt-in instantiations of the attention stream kernel: B200_ATTN_OCC=1 (2 stages, 11 CTAs/SM),
+  # B200_ATTN_TR=1 (transposed tile), and both: parity (incl. the staged <= 8-row variants test),
+  # kernel-only timing, then the full bench for the default and the fastest
+  : > $OUT/attn_variants.log
+  for v in "0 0" "1 0" "0 1" "1 1"; do
+    set -- $v
+    if [ "$v" != "0 0" ]; then
+      B200_ATTN_OCC=$1 B200_ATTN_TR=$2 B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_gpu_attention.py \
+          tests/test_gpu_decode_step.py -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_attention_occ$1_tr$2.log 2>&1
+      echo "pytest attention[occ=$1 tr=$2] rc=$? : $(tail -1 $OUT/pytest_attention_occ$1_tr$2.log)" | tee -a $OUT/summary.txt
+    fi
+    B200_ATTN_OCC=$1 B200_ATTN_TR=$2 timeout 300 python tools/attn_bench.py variant >> $OUT/attn_variants.log 2>&1
+  done
+  grep "^attn" $OUT/attn_variants.log | tee -a $OUT/summary.txt
+  BEST=$(grep "^attn" $OUT/attn_variants.log | sort -t: -k2 -n | head -1 | sed 's/.*occ=\([01]\) tr=\([01]\).*/\1 \2/')
+  for v in "0 0" "$BEST"; do
+    set -- $v
+    [ "$v" = "0 0" ] && [ "$BEST" = "0 0" ] && [ -s $OUT/bench_occ0_tr0.json ] && continue
+    B200_ATTN_OCC=$1 B200_ATTN_TR=$2 timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
+        > $OUT/bench_occ$1_tr$2.json 2> $OUT/bench_occ$1_tr$2.err
+    echo "bench occ=$1 tr=$2 rc=$? $(tail -1 $OUT/bench_occ$1_tr$2.json | head -c 200)" | tee -a $OUT/summary.txt
   done
 fi
 if has staged; then
