@@ -20,3 +20,7 @@ run() {  # tag, env assignments...
 run f1 B200_FUSE_AR_NORM=1
 run f0 B200_FUSE_AR_NORM=0
 run gather B200_FUSE_AR_NORM=1 B200_AR_GATHER=1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port $((29730 + RANDOM % 200)) tools/step_timeline.py --out gpurun_out/step_timeline_tp$N.md \
+    > gpurun_out/step_timeline_tp$N.log 2>&1
+echo "timeline tp$N rc=$?"; head -12 gpurun_out/step_timeline_tp$N.md 2>/dev/null

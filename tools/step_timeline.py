@@ -7,6 +7,7 @@ plus where the step's wall time is NOT covered by any kernel (gaps) and how much
 kernels resident at once (overlap under programmatic dependent launch).
 
   python tools/step_timeline.py [--layers 32] [--batch 64] [--seqlen 2048] [--out gpurun_out/step_timeline.md]
+  torchrun --nproc-per-node N ... tools/step_timeline.py   # tensor parallel: rank 0's timeline
 
 A number printed here is taken under a tracer: use it for shares and gaps, never as a bench value.
 """
@@ -96,12 +97,20 @@ def main():
     from scalellm_b200.layers import QuantArgs
     from scalellm_b200.model_parallel import ParallelArgs
 
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        from scalellm_b200.model_parallel import ProcessGroup
+        dist.init_process_group("nccl", device_id=dev)
+        pg = ProcessGroup(rank, world, dev)
     args = LlamaArgs.llama3_8b()
     args.n_layers = a.layers
     qa = QuantArgs(quant_method=a.quant, bits=4, group_size=128, is_sym=(a.quant == "gptq"))
-    model = LlamaDecoder(args, qa, ParallelArgs(0, 1, None), dev)
+    model = LlamaDecoder(args, qa, ParallelArgs(rank, world, pg), dev)
     model.init_random(seed=0)
     B, S, bs = a.batch, a.seqlen, a.block_size
     cap = S + 16
@@ -132,16 +141,24 @@ def main():
             continue
         tr = e.time_range
         events.append((e.name, float(tr.start), float(tr.end - tr.start)))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank != 0:
+            os._exit(0)     # communicators captured into graphs can block at tear-down
     rows, st = summarise(events, a.replays)
     if not rows:
         print("no device kernel records in the trace (CUPTI unavailable?)")
         sys.exit(1)
     text = render(rows, st, f"decode-step timeline: Llama-3-8B {a.quant} int4, batch {B}, kv_len {S}, "
-                            f"block_size {bs}, {a.layers} layers, CUDA graph replay")
+                            f"block_size {bs}, {a.layers} layers, TP={world}, CUDA graph replay")
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         f.write(text)
-    print(text)
+    print(text, flush=True)
+    if world > 1:
+        os._exit(0)
 
 
 if __name__ == "__main__":
