@@ -135,6 +135,15 @@ if has occ; then
     echo "bench occ=$1 tr=$2 rc=$? $(tail -1 $OUT/bench_occ$1_tr$2.json | head -c 200)" | tee -a $OUT/summary.txt
   done
 fi
+if has pdl; then
+  # programmatic-dependent-launch knobs against the default (B200_PDL=1): off, everything, and the
+  # attention stream kernel + combine pass launched programmatically too
+  for cfg in "B200_PDL=0" "B200_PDL=2" "B200_ATTN_PDL=1"; do
+    env $cfg timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
+        > $OUT/bench_pdl_$cfg.json 2> $OUT/bench_pdl_$cfg.err
+    echo "bench $cfg rc=$? $(tail -1 $OUT/bench_pdl_$cfg.json | head -c 160)" | tee -a $OUT/summary.txt
+  done
+fi
 if has staged; then
   # single-GPU tests written after round 1's GPU budget was spent (gate: B200_TEST_STAGED=1)
   B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_cpp_host.py -m gpu -q --tb=short -p no:cacheprovider \
