@@ -256,3 +256,25 @@ def test_attention_transposed_tile_fragment_algebra():
         assert mod.check(seed=n_rows, n_rows=n_rows) < 5e-3
     assert mod.check(seed=9, n_rows=4, n_tiles=4, kv_end=53) < 5e-3
     assert mod.check(seed=3, D=64, n_rows=2, n_tiles=3, kv_end=40) < 5e-3
+
+
+def test_bench_defaults_name_the_configuration_the_metric_is_quoted_on(monkeypatch):
+    """bench.py with no flags = Llama-3-8B AWQ-int4, batch 64, kv_len 2048, block_size 8, 1 GPU
+    (BASELINE.json configs[2]); the other models / quantisations are explicit opt-ins."""
+    import importlib.util
+    import os
+    import sys
+    spec = importlib.util.spec_from_file_location(
+        "bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.gpus, a.batch, a.seqlen, a.block_size, a.quant, a.model, a.impl) == \
+           (1, 64, 2048, 8, "awq", "llama3-8b", "b200")
+    assert a.warmup >= 3 and a.steps >= 1 and not a.ttft
+    assert bench.workload_name(a, 1) == \
+        "Llama-3-8B AWQ-int4 g128 decode step, batch 64, kv_len 2048, block_size 8, TP=1"
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--model", "llama3-70b", "--quant", "gptq", "--gpus", "8"])
+    b = bench.parse()
+    assert bench.workload_name(b, 8).startswith("Llama-3-70B GPTQ-int4 g128") and bench.METRIC == "decode_tokens_per_s"
