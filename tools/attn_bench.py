@@ -8,7 +8,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from scalellm_b200 import kernels  # noqa: E402
+from _timing import time_us  # noqa: E402
 
 DEV = "cuda"
 
@@ -63,19 +65,10 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128), only_auto=False):
             for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
                 os.environ.pop(k, None)
             os.environ.update(env)
-            launch(*caches[0])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                for kc, vc in caches:
-                    launch(kc, vc)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / (3 * L)
+            us, mode = time_us(lambda: [launch(kc, vc) for kc, vc in caches], L)
             byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
             print(f"attn bs={bs} {tag:12s}: {us:7.1f} us/launch "
-                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
+                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak) [{mode}]",
                   flush=True)
         for k in ("B200_ATTN_WARPS", "B200_ATTN_SPLITS", "B200_ATTN_TPS", "B200_ATTN_IMPL"):
             os.environ.pop(k, None)
@@ -86,19 +79,10 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128), only_auto=False):
             def launch_ref(kc, vc):
                 ref.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, 1, max_kv,
                                         D ** -0.5, 0.0, -1)
-            launch_ref(*caches[0])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                for kc, vc in caches:
-                    launch_ref(kc, vc)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / (3 * L)
+            us, mode = time_us(lambda: [launch_ref(kc, vc) for kc, vc in caches], L)
             byts = 2 * B * S * Hkv * D * 2 + 2 * B * H * D * 2
             print(f"attn bs={bs} {'REFERENCE':12s}: {us:7.1f} us/launch "
-                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak)",
+                  f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak) [{mode}]",
                   flush=True)
 
 

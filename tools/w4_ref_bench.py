@@ -17,17 +17,10 @@ from attn_bench import load_reference_kernels  # noqa: E402
 DEV = "cuda"
 
 
-def timeit(fn, n_copies, reps=3):
-    fn(0)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        for i in range(n_copies):
-            fn(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (reps * n_copies)
+def timeit(fn, n_copies):
+    """us per launch over the rotating copies: >= 100 CUDA-graph replays after 10 warm-ups"""
+    from _timing import time_us
+    return time_us(lambda: [fn(i) for i in range(n_copies)], n_copies)   # (us, "graph" | "eager")
 
 
 def main():
@@ -40,15 +33,16 @@ def main():
         sc = (torch.rand(K // g, N, device=DEV) * 0.01 + 1e-3).bfloat16()
         ours_w = [kernels.w4a16_prepack_gptq(ri(K // 8, N), None, sc, g) for _ in range(L)]
         out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
-        t_full = timeit(lambda i: kernels.w4a16_gemm(a, ours_w[i], N, g, out=out), L)
-        t_part = timeit(lambda i: kernels.w4a16_gemm_splitk(a, ours_w[i], N, g), L)
-        line = f"{name:8s} K={K:5d} N={N:5d}: b200 gemm+reduce {t_full:6.1f} us, partials only {t_part:6.1f} us"
+        (t_full, m1), (t_part, m2) = (timeit(lambda i: kernels.w4a16_gemm(a, ours_w[i], N, g, out=out), L),
+                                      timeit(lambda i: kernels.w4a16_gemm_splitk(a, ours_w[i], N, g), L))
+        line = (f"{name:8s} K={K:5d} N={N:5d}: b200 gemm+reduce {t_full:6.1f} us ({m1}), "
+                f"partials only {t_part:6.1f} us ({m2})")
         if ref is not None:
             marlin_w = [ri(K // 16, N * 16 // 8) for _ in range(L)]
             ws = torch.zeros(N // 64 * 16, dtype=torch.int32, device=DEV)
             e = torch.empty(0, dtype=torch.int32, device=DEV)
-            t_ref = timeit(lambda i: ref.marlin_gemm(a, marlin_w[i], out, sc, e, e, e, ws, 4, True, False, True), L)
-            line += f", reference Marlin {t_ref:6.1f} us"
+            t_ref, m3 = timeit(lambda i: ref.marlin_gemm(a, marlin_w[i], out, sc, e, e, e, ws, 4, True, False, True), L)
+            line += f", reference Marlin {t_ref:6.1f} us ({m3})"
         print(line, flush=True)
 
 

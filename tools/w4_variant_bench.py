@@ -10,30 +10,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from scalellm_b200 import kernels  # noqa: E402
+from _timing import time_us  # noqa: E402
 
 DEV = "cuda"
-
-
-def graph_us(fn, reps=5):
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        fn()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / reps
 
 
 def main():
@@ -49,7 +30,8 @@ def main():
         def sweep():
             for w in ws:
                 kernels.w4a16_gemm_splitk(a, w, N, g)
-        res[name] = graph_us(sweep) / L
+        res[name], mode = time_us(sweep, L, replays=20, warmup=3)
+        assert mode == "graph", "GEMM launches could not be captured"
         del ws
     print(json.dumps({"variant": os.environ.get("B200_W4_VARIANT", "0"), "us": res,
                       "sum_us": sum(res.values())}), flush=True)
