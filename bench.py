@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--ttft", action="store_true",
                     help="also measure unloaded p50 time-to-first-token (chunked prefill through "
                          "the decode kernels; experimental, off by default)")
+    ap.add_argument("--ttft-chunk", type=int, default=128,
+                    help="prefill chunk (token budget per step) of the --ttft measurement; with "
+                         "B200_W4_PREFILL_DENSE=1 chunks > 256 tokens run the int4 linears as "
+                         "dequant + library bf16 GEMM")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
@@ -397,7 +401,7 @@ def run_b200(a, rank, world, local_rank):
     ttft = "not measured: prefill kernels are SURVEY §8f rank 1 (next)"
     if a.ttft and world == 1:
         try:
-            ttft = measure_ttft(model, pool, args, dev)
+            ttft = measure_ttft(model, pool, args, dev, chunk=a.ttft_chunk)
         except Exception as e:  # noqa: BLE001  (experimental: never cost the bench line)
             ttft = f"failed: {type(e).__name__}: {e}"
 
@@ -486,7 +490,9 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
     times.sort()
     return {"p50_ms": times[len(times) // 2], "min_ms": times[0], "max_ms": times[-1],
             "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
-            "load": "unloaded (one request at a time), eager launches, decode kernels"}
+            "load": "unloaded (one request at a time), eager launches, decode kernels" +
+                    (", int4 linears as dequant + library bf16 GEMM above 256 rows"
+                     if os.environ.get("B200_W4_PREFILL_DENSE") == "1" else "")}
 
 
 def _traffic(name):

@@ -284,6 +284,9 @@ class QuantArgs:
     zero_point: bool = True
 
 
+_DENSE_PREFILL_ROWS = 256   # above this many rows B200_W4_PREFILL_DENSE=1 takes the dequant + bf16 GEMM path
+
+
 def _check_quant(qa: QuantArgs, in_features: int, out_features: int) -> None:
     # qlinear_awq_marlin_impl.cpp:28-31,150-151
     if qa.bits != 4:
@@ -337,6 +340,15 @@ class _QLinearBase:
     def _gemm(self, x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
         self._ensure_packed()
         x2 = x.reshape(-1, x.shape[-1])
+        if x2.shape[0] > _DENSE_PREFILL_ROWS and os.environ.get("B200_W4_PREFILL_DENSE") == "1":
+            # Prefill-sized batches are compute bound: the streaming kernel would re-read the int4
+            # weights once per 128 rows.  Dequantise once (same bf16 values as the fused kernel,
+            # b200_w4a16_dequant) and let the library bf16 GEMM do the rest (opt-in, TTFT path).
+            w = kernels.w4a16_dequant(self.packed, self.K, self.N, self.qa.group_size)
+            out = torch.matmul(x2, w)
+            if bias is not None:
+                out = out + bias
+            return out.view(*x.shape[:-1], self.N)
         out = kernels.w4a16_gemm(x2, self.packed, self.N, self.qa.group_size, bias=bias)
         return out.view(*x.shape[:-1], self.N)
 

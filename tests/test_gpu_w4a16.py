@@ -143,6 +143,30 @@ def test_gemm_bias_strided_and_large_m():
     assert (out.cpu().view(torch.int16) == ref.view(torch.int16)).float().mean() > 0.85
 
 
+@pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
+                    reason="staged: written after the round's GPU budget, not yet run on a GPU")
+@pytest.mark.parametrize("method", ["awq", "gptq"])
+def test_dense_prefill_path_of_the_int4_linear(method, monkeypatch):
+    """B200_W4_PREFILL_DENSE=1: above 256 rows the int4 linear dequantises once (bit-exact bf16
+    weights) and runs the library bf16 GEMM — same bar as the fused kernel vs the oracle."""
+    from scalellm_b200.layers import ColumnParallelQLinear, QuantArgs
+    from scalellm_b200.model_parallel import ParallelArgs
+    K, N, M, g = 1024, 768, 300, 128
+    ck = (quant.random_awq_checkpoint if method == "awq" else quant.random_gptq_checkpoint)(K, N, g, seed=5)
+    qa = QuantArgs(method, 4, g, is_sym=(method == "gptq"))
+    lin = ColumnParallelQLinear(K, N, False, False, qa, ParallelArgs(0, 1, None), DEV)
+    lin.load_state_dict({k: ck[k] for k in ("qweight", "qzeros", "scales") if ck.get(k) is not None})
+    a = (torch.randn(M, K, generator=torch.Generator().manual_seed(6)) * 0.5).bfloat16()
+    w_ref = quant.dequant(ck["q"], ck["z"], ck["scales"], g)
+    ref = quant.w4a16_gemm(a, w_ref)
+    monkeypatch.setenv("B200_W4_PREFILL_DENSE", "1")
+    dense = lin(a.to(DEV))
+    monkeypatch.delenv("B200_W4_PREFILL_DENSE")
+    fused = lin(a.to(DEV))
+    assert rel_err(dense, ref) < 1e-3 and rel_err(fused, ref) < 1e-3
+    assert (dense.cpu().view(torch.int16) == ref.view(torch.int16)).float().mean() > 0.85
+
+
 def test_gemm_linearity_full_size():
     """Size-independent property at the benchmark shape: C(a1 + a2) == C(a1) + C(a2) when all
     terms are exactly representable (activations are small integers, weights q-z with s=2^-6)."""
