@@ -66,6 +66,8 @@ def test_argument_validation_without_gpu():
     assert lib.b200_ar_create_all(comms, devs, 9, 1 << 20) == -1
     assert lib.b200_ar_create_all(comms, devs, 1, 24) == -1
     assert lib.b200_ar_create_all(None, devs, 1, 1 << 20) == -1
+    assert lib.b200_ar_allgather(None, 16, 16, 1, 16, None) == -1 and b"null" in lib.b200_last_error()
+    assert lib.b200_ar_allgather(1, 16, 32, 1, 24, None) == -1 and b"16 bytes" in lib.b200_last_error()
 
 
 def test_kernels_reject_cpu_tensors():
