@@ -304,7 +304,7 @@ StateDict shard_qlinear_columns(const StateDict& t, const QuantArgs& qa, int64_t
   TORCH_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && c0 < c1, "column shard must align to 8 columns");
   const bool awq = qa.quant_method == "awq";
   StateDict out;
-  const auto& qw = need(t, "qweight");
+  const torch::Tensor qw = need(t, "qweight");
   out["qweight"] = awq ? qw.slice(1, c0 / 8, c1 / 8) : qw.slice(1, c0, c1);
   out["scales"] = need(t, "scales").slice(1, c0, c1);
   auto z = t.find("qzeros");
@@ -314,7 +314,7 @@ StateDict shard_qlinear_columns(const StateDict& t, const QuantArgs& qa, int64_t
 
 StateDict shard_qlinear_rows(const StateDict& t, const QuantArgs& qa, int64_t k0, int64_t k1) {
   const bool awq = qa.quant_method == "awq";
-  const auto& qw = need(t, "qweight");
+  const torch::Tensor qw = need(t, "qweight");
   const int64_t K = awq ? qw.size(0) : qw.size(0) * 8;
   const int64_t g = qa.group_size > 0 ? qa.group_size : K;
   TORCH_CHECK(k0 % g == 0 && k1 % g == 0 && k0 < k1 && k1 <= K,
