@@ -297,11 +297,14 @@ def test_cpp_tensor_parallel_decode_step(fuse):
 
     want = single.forward(*args_on("cuda:0")).float().cpu()
     outs, errs = [None] * world, []
+    rank_args = [args_on(f"cuda:{r}") for r in range(world)]   # pinned staging etc. before any rank spins
+    for r in range(world):
+        torch.cuda.synchronize(r)
 
     def run(r):
         try:
             with torch.cuda.device(r):
-                outs[r] = ranks[r].forward(*args_on(f"cuda:{r}"))
+                outs[r] = ranks[r].forward(*rank_args[r])
                 torch.cuda.synchronize(r)
         except Exception as e:  # noqa: BLE001
             errs.append(e)
