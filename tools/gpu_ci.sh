@@ -46,7 +46,7 @@ if has attn2; then
 fi
 
 if has tests; then
-  for f in gpu_elementwise gpu_attention gpu_w4a16 gpu_decode_step shim; do
+  for f in gpu_elementwise gpu_attention gpu_w4a16 gpu_decode_step shim cpp_host; do
     timeout 1200 python -m pytest tests/test_$f.py -m gpu -q --tb=short -p no:cacheprovider \
         > $OUT/pytest_$f.log 2>&1
     echo "pytest $f rc=$? : $(tail -1 $OUT/pytest_$f.log)" | tee -a $OUT/summary.txt
