@@ -157,6 +157,8 @@ B200_API int b200_silu_mul_strided(void* out, const void* gate, const void* up,
  *
  *     out, q:  [n_tokens, n_heads, head_dim], strides (q_stride_t, q_stride_h, 1)
  *     caches:  [n_slots, n_kv_heads, head_dim], strides (kv_stride_s, kv_stride_h, 1)
+ *     head_dim in {64, 128, 256} (tensor-core kernels) or {32, 96} (CUDA-core kernel; the
+ *     reference pads these into its 64 / 128 tiles, common/static_dispatch.h:16-46); bf16 / fp16
  *     q_cu_lens, kv_cu_lens, block_cu_lens: [batch+1] int32;  block_table int32
  *     alibi_slopes: [n_heads] float32 or NULL
  *     sliding_window < 0 disables the local mask; logits_soft_cap == 0 disables it.

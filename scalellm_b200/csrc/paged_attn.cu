@@ -76,7 +76,8 @@ struct AttnParams {
 template <int D>
 struct AttnCfg {
   static constexpr int STAGES = D >= 256 ? 2 : 3;
-  static constexpr int CPL = D / 64;           // 16-byte chunks per lane per row
+  static constexpr int CPL = (D + 63) / 64;    // 16-byte chunks per lane per row (the last one may
+                                               // be partly outside the row: head_dim 32 / 96)
   static constexpr int EPL = CPL * 8;          // elements per lane per row
   static constexpr int TILE_ELEMS = ATT_TILE * D;
 };
@@ -106,6 +107,10 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES, CPL = Cfg::CPL, EPL = Cfg::EPL;
+  // head_dim 32 / 96 (the reference pads them into its 64 / 128 tiles, static_dispatch.h:16-46):
+  // the row's last 64-element chunk group is only partly there; chunk (j + 8 c) exists iff
+  // (j + 8 c) * 8 < D.  For head_dim % 64 == 0 the predicate is constant true.
+  constexpr bool PARTIAL = (D % 64) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   T* stage_base = reinterpret_cast<T*>(smem_raw);
   int32_t* tbl = reinterpret_cast<int32_t*>(smem_raw + (size_t)ATT_WARPS * STAGES * 2 *
@@ -114,6 +119,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, j = lane & 7;
+  auto chunk_ok = [&](int c) { return !PARTIAL || (j + 8 * c) * 8 < D; };
   const int split = blockIdx.x;
   const int kvh = blockIdx.y / p.n_hg, hg = blockIdx.y % p.n_hg;
   const int b = blockIdx.z / p.max_q_len, qi = blockIdx.z % p.max_q_len;
@@ -189,7 +195,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     const T* qrow = static_cast<const T*>(p.q) + tok * p.q_stride_t + (int64_t)h * p.q_stride_h;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      uint4 raw = ld_v4(qrow + (j + 8 * c) * 8);
+      uint4 raw = chunk_ok(c) ? ld_v4(qrow + (j + 8 * c) * 8) : make_uint4(0, 0, 0, 0);
       const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -230,7 +236,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
       float kf[EPL];
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        uint4 raw = ld_v4(krow + (j + 8 * c) * 8);
+        uint4 raw = chunk_ok(c) ? ld_v4(krow + (j + 8 * c) * 8) : make_uint4(0, 0, 0, 0);
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -302,7 +308,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
         const T* vrow = vs + (it * 4 + g) * D;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-          uint4 raw = ld_v4(vrow + (j + 8 * c) * 8);
+          uint4 raw = chunk_ok(c) ? ld_v4(vrow + (j + 8 * c) * 8) : make_uint4(0, 0, 0, 0);
           const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -346,9 +352,11 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int c = 0; c < CPL; ++c)
+      for (int c = 0; c < CPL; ++c) {
+        if (!chunk_ok(c)) continue;
 #pragma unroll
         for (int e = 0; e < 8; ++e) red[r * D + (j + 8 * c) * 8 + e] = acc[r][c * 8 + e];
+      }
       if (j == 0) {
         red[R * D + r] = m[r];
         red[R * D + R + r] = l[r];
@@ -1236,7 +1244,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 // One warp per (token, head) row; each lane owns D/32 consecutive outputs (vector loads).
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
-  constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8
+  constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8 (1 or 3 for head_dim 32 / 96)
   pdl_wait();
   pdl_launch_dependents();  // a following W4A16 GEMM (o_proj) may start prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1323,9 +1331,14 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
   for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
   const float inv = 1.f / L;
   T* dst = static_cast<T*>(p.out) + tok * p.o_stride_t + (int64_t)h * p.o_stride_h + lane * EPL;
+  if constexpr (EPL % 2) {
 #pragma unroll
-  for (int e = 0; e < EPL; e += 2)
-    *reinterpret_cast<uint32_t*>(dst + e) = Num<T>::pack(acc[e] * inv, acc[e + 1] * inv);
+    for (int e = 0; e < EPL; ++e) dst[e] = Num<T>::from_f(acc[e] * inv);
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2)
+      *reinterpret_cast<uint32_t*>(dst + e) = Num<T>::pack(acc[e] * inv, acc[e + 1] * inv);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1469,7 +1482,7 @@ struct AttnPlan {
 static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads,
                           int n_kv_heads, int head_dim, int block_size) {
   AttnPlan pl{};
-  pl.impl = attn_impl();
+  pl.impl = head_dim % 64 ? 0 : attn_impl();  // head_dim 32 / 96: the CUDA-core kernel (no 64-wide swizzle atoms)
   const int group = n_heads / n_kv_heads;
   const int ctas = head_dim <= 128 ? 2 : 1;
   if (pl.impl == 0) {
@@ -1615,15 +1628,38 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   return B200_OK;
 }
 
+// head_dim 32 / 96: only the CUDA-core kernel (and the combine pass) are instantiated
+template <typename T, int D>
+static int launch_attn_simt(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnParams& p,
+                            const AttnPlan& pl, int64_t batch, cudaStream_t st) {
+  constexpr size_t smem = attn_smem_bytes<T, D>();
+  int rc;
+  if (pl.R == 4) {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 4>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
+  } else if (pl.R == 2) {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 2>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
+  } else {
+    rc = launch_kernel(paged_attn_decode_kernel<T, D, 1>, smem, ATT_THREADS, kmap, vmap, p, pl, st);
+  }
+  if (rc != B200_OK) return rc;
+  if (p.n_splits > 1) {
+    dim3 cgrid((unsigned)((p.n_heads + 3) / 4), (unsigned)(batch * p.max_q_len));
+    B200_PDL_LAUNCH_L(attn_pdl_level(), "paged_attn_combine", (paged_attn_combine_kernel<T, D>), cgrid, 128, 0, st, p);
+  }
+  return B200_OK;
+}
+
 template <typename T>
 static int launch_attn_d(int D, const CUtensorMap& kmap, const CUtensorMap& vmap,
                          const AttnParams& p, const AttnPlan& pl, int64_t batch, cudaStream_t st) {
   switch (D) {
+    case 32: return launch_attn_simt<T, 32>(kmap, vmap, p, pl, batch, st);
+    case 96: return launch_attn_simt<T, 96>(kmap, vmap, p, pl, batch, st);
     case 64: return launch_attn<T, 64>(kmap, vmap, p, pl, batch, st);
     case 128: return launch_attn<T, 128>(kmap, vmap, p, pl, batch, st);
     case 256: return launch_attn<T, 256>(kmap, vmap, p, pl, batch, st);
     default:
-      return set_error(B200_ERR_UNSUPPORTED, "paged_attn: head_dim %d not in {64,128,256}", D);
+      return set_error(B200_ERR_UNSUPPORTED, "paged_attn: head_dim %d not in {32,64,96,128,256}", D);
   }
 }
 
