@@ -278,3 +278,25 @@ def test_bench_defaults_name_the_configuration_the_metric_is_quoted_on(monkeypat
     monkeypatch.setattr(sys, "argv", ["bench.py", "--model", "llama3-70b", "--quant", "gptq", "--gpus", "8"])
     b = bench.parse()
     assert bench.workload_name(b, 8).startswith("Llama-3-70B GPTQ-int4 g128") and bench.METRIC == "decode_tokens_per_s"
+
+
+def test_every_environment_switch_is_documented():
+    """Each B200_* switch read anywhere in the library, the host layers, bench.py or the tests is
+    listed in DESIGN.md's table of environment switches."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(__file__), "..")
+    files = (glob.glob(os.path.join(root, "scalellm_b200", "csrc", "*.cu*")) +
+             glob.glob(os.path.join(root, "scalellm_b200", "*.py")) + glob.glob(os.path.join(root, "shim", "*.cpp")) +
+             [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] +
+             glob.glob(os.path.join(root, "tests", "*.py")))
+    used = set()
+    for f in files:
+        src = open(f).read()
+        used |= set(re.findall(r'getenv\("(B200_[A-Z0-9_]+)"\)', src))
+        used |= set(re.findall(r'environ(?:\.get)?[\[(]"(B200_[A-Z0-9_]+)"', src))
+        used |= set(re.findall(r'setenv\("(B200_[A-Z0-9_]+)"', src))
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    missing = sorted(n for n in used if n not in design)
+    assert used and not missing, missing
