@@ -578,4 +578,54 @@ torch::Tensor CudaGraphStep::replay(const torch::Tensor& tokens, const torch::Te
   return output_;
 }
 
+// ---------------------------------------------------------------------------------------------
+// graph per batch size, eager otherwise
+// ---------------------------------------------------------------------------------------------
+void ModelRunner::capture_cuda_graphs(uint32_t batch_size) {
+  TORCH_CHECK(device_.is_cuda(), "CUDA graphs need a CUDA device");
+  TORCH_CHECK(graphs_.find(batch_size) == graphs_.end(), "batch size ", batch_size, " already captured");
+  c10::cuda::CUDAGuard guard(device_);
+  const int64_t ndt = options_.num_decoding_tokens, bs = options_.block_size;
+  const int64_t n_tokens = ndt * batch_size;
+  const auto i32 = torch::dtype(torch::kInt32).device(device_);
+  // round up and add one block per sequence (speculative decoding), model_runner.cpp:57-60
+  const int64_t max_block_table_len = (options_.cuda_graph_max_seq_len + bs - 1) / bs + 1;
+  InputParameters params;
+  params.num_sequences = static_cast<int32_t>(batch_size);
+  params.q_max_seq_len = static_cast<int32_t>(ndt);
+  params.kv_max_seq_len = static_cast<int32_t>(options_.cuda_graph_max_seq_len);
+  params.q_cu_seq_lens = torch::arange(0, n_tokens + 1, ndt, i32);
+  params.kv_cu_seq_lens = torch::arange(0, n_tokens + 1, ndt, i32);
+  // placeholder sequences of kv_len = ndt, all in block 0 (first-slot id 0)
+  const int64_t nb = (ndt + bs - 1) / bs;
+  params.new_cache_slots = torch::arange(0, n_tokens, i32).remainder(std::min(ndt, bs));
+  params.block_tables = torch::zeros({static_cast<int64_t>(batch_size) * nb}, i32);
+  params.cu_block_lens = torch::arange(0, static_cast<int64_t>(batch_size) * nb + 1, nb, i32);
+  auto graph = std::make_unique<CudaGraphStep>();
+  graph->capture(model_, torch::zeros({n_tokens}, i32), torch::zeros({n_tokens}, i32), params,
+                 static_cast<int64_t>(batch_size) * max_block_table_len, options_.greedy);
+  graphs_[batch_size] = std::move(graph);
+}
+
+torch::Tensor ModelRunner::forward(const torch::Tensor& tokens, const torch::Tensor& positions,
+                                   const InputParameters& params) {
+  const uint32_t batch_size = static_cast<uint32_t>(params.num_sequences);
+  auto it = graphs_.find(batch_size);
+  if (it != graphs_.end()) {
+    const bool seq_len_supported = params.kv_max_seq_len <= options_.cuda_graph_max_seq_len;
+    const bool same_num_decoding_tokens =
+        params.q_max_seq_len == options_.num_decoding_tokens &&
+        tokens.size(0) == static_cast<int64_t>(batch_size) * options_.num_decoding_tokens;
+    if (seq_len_supported && same_num_decoding_tokens) {
+      ++n_replayed_;
+      // the graph was captured for the longest context: replay with those host scalars
+      InputParameters p = params;
+      p.kv_max_seq_len = static_cast<int32_t>(options_.cuda_graph_max_seq_len);
+      return it->second->replay(tokens, positions, p);
+    }
+  }
+  ++n_eager_;
+  return options_.greedy ? model_->step(tokens, positions, params) : model_->forward(tokens, positions, params);
+}
+
 }  // namespace llm

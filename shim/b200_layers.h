@@ -10,6 +10,7 @@
 //   RMSNormImpl                          src/layers/normalization.h:114-139
 //   LlamaDecoderStep                     src/models/meta/llama.h:61-64,123-133,170-177,220-232,281-289
 //   CudaGraphStep                        src/engine/model_runner.cpp:141-210 (ModelRunner::CudaGraph)
+//   ModelRunner                          src/engine/model_runner.cpp:25-139 (graph per batch size)
 //
 // Inside ScaleLLM these classes derive from the engine's own headers; here the
 // interfaces are restated so that the library is self-contained and testable.  Tensor parallelism
@@ -293,6 +294,39 @@ class CudaGraphStep {
   torch::Tensor tokens_, positions_;
   InputParameters params_;  // owns the captured metadata tensors
   torch::Tensor output_;
+};
+
+// Graph per captured batch size, eager otherwise (ModelRunner, model_runner.cpp:25-139): the
+// selection rule of ModelRunner::forward — a captured graph is replayed when the batch size was
+// captured, every sequence decodes num_decoding_tokens tokens and kv_max_seq_len fits
+// cuda_graph_max_seq_len; anything else (prefill, odd batch sizes, long contexts) runs eagerly.
+class ModelRunner {
+ public:
+  struct Options {
+    std::vector<uint32_t> cuda_graph_batch_sizes;
+    int64_t num_decoding_tokens = 1;
+    int64_t cuda_graph_max_seq_len = 2048;
+    int64_t block_size = 8;
+    bool greedy = false;  // return next tokens instead of logits
+  };
+  ModelRunner(LlamaDecoderStep* model, const torch::Device& device, const Options& options)
+      : model_(model), device_(device), options_(options) {}
+
+  // Captures with placeholder metadata (every sequence at kv_len = num_decoding_tokens in block 0,
+  // like model_runner.cpp:25-65): call it before the KV cache holds anything — the warm-up step
+  // writes slot 0.
+  void capture_cuda_graphs(uint32_t batch_size);
+  torch::Tensor forward(const torch::Tensor& tokens, const torch::Tensor& positions,
+                        const InputParameters& params);
+  int64_t num_cuda_graph_replayed() const { return n_replayed_; }
+  int64_t num_eager_execution() const { return n_eager_; }
+
+ private:
+  LlamaDecoderStep* model_;
+  torch::Device device_;
+  Options options_;
+  std::unordered_map<uint32_t, std::unique_ptr<CudaGraphStep>> graphs_;
+  int64_t n_replayed_ = 0, n_eager_ = 0;
 };
 
 }  // namespace llm

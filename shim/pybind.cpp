@@ -179,4 +179,35 @@ PYBIND11_MODULE(_b200_shim, m) {
       });
 
 
+
+  py::class_<llm::ModelRunner>(m, "ModelRunner")
+      .def(py::init([](llm::LlamaDecoderStep& model, int device_index, std::vector<uint32_t> batch_sizes,
+                       int64_t num_decoding_tokens, int64_t max_seq_len, int64_t block_size, bool greedy) {
+             llm::ModelRunner::Options o;
+             o.cuda_graph_batch_sizes = std::move(batch_sizes);
+             o.num_decoding_tokens = num_decoding_tokens;
+             o.cuda_graph_max_seq_len = max_seq_len;
+             o.block_size = block_size;
+             o.greedy = greedy;
+             return std::make_unique<llm::ModelRunner>(
+                 &model, torch::Device(torch::kCUDA, static_cast<c10::DeviceIndex>(device_index)), o);
+           }),
+           py::keep_alive<1, 2>())
+      .def("capture_cuda_graphs", &llm::ModelRunner::capture_cuda_graphs)
+      .def("num_cuda_graph_replayed", &llm::ModelRunner::num_cuda_graph_replayed)
+      .def("num_eager_execution", &llm::ModelRunner::num_eager_execution)
+      .def("forward", [](llm::ModelRunner& self, torch::Tensor tokens, torch::Tensor positions,
+                         torch::Tensor q_cu, torch::Tensor kv_cu, int kv_max, int q_max,
+                         torch::Tensor slots, torch::Tensor tables, torch::Tensor blk_cu) {
+        llm::InputParameters p;
+        p.num_sequences = static_cast<int32_t>(q_cu.size(0) - 1);
+        p.q_cu_seq_lens = q_cu;
+        p.kv_cu_seq_lens = kv_cu;
+        p.kv_max_seq_len = kv_max;
+        p.q_max_seq_len = q_max;
+        p.new_cache_slots = slots;
+        p.block_tables = tables;
+        p.cu_block_lens = blk_cu;
+        return self.forward(tokens, positions, p);
+      });
 }

@@ -237,3 +237,64 @@ def _dequant(quant, method, t, g):
         z = (quant.unpack_gptq_zeros(t["qzeros"].contiguous(), plus_one=True) if "qzeros" in t
              else np.full((q.shape[0] // g, q.shape[1]), 8, dtype=q.dtype))
     return quant.dequant(q, z, t["scales"].contiguous(), g)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_STAGED") != "1",
+                    reason="staged: not yet validated on a GPU box (B200_TEST_STAGED=1)")
+def test_cpp_model_runner_replays_captured_batch_sizes_and_falls_back():
+    """ModelRunner (model_runner.cpp:25-139): a decode step whose batch size was captured is a
+    graph replay, anything else (other batch size, multi-token queries, context beyond the
+    captured maximum) runs eagerly — same logits either way."""
+    from scalellm_b200.decode_step import BlockPool, StepBuffers, build_decode_batch
+    shim = _shim()
+    dev = torch.device("cuda")
+    c = CFG
+    sd = _state_dict(seed=6)
+    bs, n_blocks, max_seq = 16, 64, 120
+
+    def fresh():
+        m = _make(shim, torch.empty(0, dtype=torch.bfloat16, device=dev))
+        m.load_state_dict(sd)
+        g = torch.Generator(device=dev).manual_seed(8)
+        kc = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g, device=dev).bfloat16()
+              for _ in range(c["n_layers"])]
+        vc = [torch.randn(n_blocks * bs, c["n_kv_heads"], c["head_dim"], generator=g, device=dev).bfloat16()
+              for _ in range(c["n_layers"])]
+        m.set_kv_caches(kc, vc, bs)
+        return m, kc + vc
+
+    graphed, g_caches = fresh()
+    eager, e_caches = fresh()
+    runner = shim.ModelRunner(graphed, 0, [5], 1, max_seq, bs, False)
+    runner.capture_cuda_graphs(5)
+    for x, y in zip(g_caches, e_caches):          # the capture's warm-up step wrote slot 0
+        y.copy_(x)
+
+    pool = BlockPool(n_blocks, bs, seed=1)
+    for _ in range(6):
+        pool.add_sequence(max_seq)
+    bufs = StepBuffers(dev, 16, 8, 256)
+
+    def args_of(kv, q, seed):
+        hb = build_decode_batch(pool, kv, q, c["vocab"], seed=seed)
+        tokens, positions, p = bufs.upload(hb)
+        return [t.clone() for t in (tokens, positions, p.q_cu_seq_lens, p.kv_cu_seq_lens)] + \
+               [p.kv_max_seq_len, p.q_max_seq_len] + \
+               [t.clone() for t in (p.new_cache_slots, p.block_tables, p.cu_block_lens)]
+
+    cases = [([37, 64, 5, 100, 17], [1] * 5, True),        # captured batch size: replay
+             ([1, 2, 3, 4, 5], [1] * 5, True),
+             ([37, 64, 5, 100], [1] * 4, False),           # batch size not captured: eager
+             ([37, 64, 5, 100, 17], [2, 1, 1, 1, 1], False)]  # multi-token query: eager
+    replayed = 0
+    for i, (kv, q, graph) in enumerate(cases):
+        a = args_of(kv, q, seed=i)
+        got = runner.forward(*a).clone()
+        want = eager.forward(*a)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (kv, q)
+        replayed += int(graph)
+        assert runner.num_cuda_graph_replayed() == replayed and runner.num_eager_execution() == i + 1 - replayed
+        for x, y in zip(g_caches, e_caches):
+            assert torch.equal(x, y)

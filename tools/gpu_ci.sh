@@ -147,8 +147,8 @@ fi
 if has staged; then
   # single-GPU tests written after round 1's GPU budget was spent (gate: B200_TEST_STAGED=1)
   B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_cpp_host.py tests/test_gpu_w4a16.py -m gpu -q --tb=short \
-      -p no:cacheprovider -k "cuda_graph_step or dense_prefill or cpp_decode_step" > $OUT/pytest_staged.log 2>&1
-  echo "pytest staged (C++ CudaGraphStep, dense prefill linear) rc=$? : $(tail -1 $OUT/pytest_staged.log)" | tee -a $OUT/summary.txt
+      -p no:cacheprovider -k "cuda_graph_step or model_runner or dense_prefill or cpp_decode_step" > $OUT/pytest_staged.log 2>&1
+  echo "pytest staged (C++ CudaGraphStep / ModelRunner, dense prefill linear) rc=$? : $(tail -1 $OUT/pytest_staged.log)" | tee -a $OUT/summary.txt
   timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --ttft > $OUT/bench_ttft.json 2> $OUT/bench_ttft.err
   echo "bench --ttft rc=$? $(tail -1 $OUT/bench_ttft.json | python -c 'import json,sys; print(json.loads(sys.stdin.read())["config"]["ttft"])' 2>&1 | head -c 300)" | tee -a $OUT/summary.txt
   for ch in 512 2048; do   # bigger prefill chunks with the int4 linears as dequant + library bf16 GEMM
