@@ -278,6 +278,7 @@ def test_cpp_model_runner_replays_captured_batch_sizes_and_falls_back():
 
     def args_of(kv, q, seed):
         hb = build_decode_batch(pool, kv, q, c["vocab"], seed=seed)
+        hb.kv_max = max_seq       # the host scalar the graph was captured with: same work partition
         tokens, positions, p = bufs.upload(hb)
         return [t.clone() for t in (tokens, positions, p.q_cu_seq_lens, p.kv_cu_seq_lens)] + \
                [p.kv_max_seq_len, p.q_max_seq_len] + \
