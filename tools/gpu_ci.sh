@@ -151,6 +151,8 @@ if has staged; then
   echo "pytest staged (C++ CudaGraphStep / ModelRunner, dense prefill linear) rc=$? : $(tail -1 $OUT/pytest_staged.log)" | tee -a $OUT/summary.txt
   timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --ttft > $OUT/bench_ttft.json 2> $OUT/bench_ttft.err
   echo "bench --ttft rc=$? $(tail -1 $OUT/bench_ttft.json | python -c 'import json,sys; print(json.loads(sys.stdin.read())["config"]["ttft"])' 2>&1 | head -c 300)" | tee -a $OUT/summary.txt
+  timeout 600 scalellm_b200/decode_demo 32 64 2048 20 > $OUT/decode_demo.log 2>&1   # the step driven from C++ only
+  echo "decode_demo rc=$? $(tail -1 $OUT/decode_demo.log)" | tee -a $OUT/summary.txt
   for ch in 512 2048; do   # bigger prefill chunks with the int4 linears as dequant + library bf16 GEMM
     B200_W4_PREFILL_DENSE=1 timeout 600 python bench.py --steps 5 --warmup 3 --skip-cpu-baseline --ttft --ttft-chunk $ch \
         > $OUT/bench_ttft_dense$ch.json 2> $OUT/bench_ttft_dense$ch.err
