@@ -83,3 +83,18 @@ def test_process_group_bindings_fail_loudly_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="ar_create_all"):
             shim.create_process_groups([0, 1])
+
+
+def test_cpp_decode_demo_builds_and_refuses_to_run_without_a_gpu():
+    """shim/decode_demo.cpp: a C++ main() that links the shim + libb200decode and drives the decode
+    step; without a CUDA device it must say so and exit non-zero (no CPU path)."""
+    import os
+    import subprocess
+    import torch
+    import __graft_entry__ as g
+    g._build_shim()                                      # also links the demo next to the extension
+    exe = os.path.join(os.path.dirname(__file__), "..", "scalellm_b200", "decode_demo")
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "1", "2", "16", "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 2 and "no CUDA device" in r.stderr
