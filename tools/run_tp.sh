@@ -24,3 +24,6 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     --master-port $((29730 + RANDOM % 200)) tools/step_timeline.py --out gpurun_out/step_timeline_tp$N.md \
     > gpurun_out/step_timeline_tp$N.log 2>&1
 echo "timeline tp$N rc=$?"; head -12 gpurun_out/step_timeline_tp$N.md 2>/dev/null
+# the reference engine's model: one process, one worker thread per GPU, C++ only
+timeout 600 scalellm_b200/decode_demo 32 64 2048 20 $N > gpurun_out/decode_demo_tp$N.log 2>&1
+echo "decode_demo tp$N rc=$? $(tail -1 gpurun_out/decode_demo_tp$N.log)"
