@@ -900,6 +900,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     const int rows_total = it.q_len * G, row0 = it.rb * ROWS;
     const int n_rows = min(ROWS, rows_total - row0);
     if constexpr (TR) {
+      // [tr-emu:load_q begin]  (tools/attn_tr_emu.cpp compiles this block for the host)
       // B operand of S^T = K Q^T: lane (g, t) holds Q[row g][16 ks + 2t, +1] and [.. + 8, + 9]
       const int r = lane >> 2;
       const bool ok = it.n_tiles > 0 && r < n_rows;
@@ -912,6 +913,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
         qa[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
         qa[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
       }
+      // [tr-emu:load_q end]
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1012,6 +1014,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       }
 
       if constexpr (TR) {
+        // [tr-emu:tile begin]
         // S^T = K Q^T: A = the tile's 16 keys x 16 dims per k-step (ldmatrix), B = Q^T registers;
         // two accumulators (even / odd k-steps) halve the dependent HMMA chain
         float sacc[2][4];
@@ -1074,6 +1077,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
           ldsm_x4_trans(af, swz128(v_base + off));
           mma_16816<T>(o[mb], af, pb0, pb1);
         }
+        // [tr-emu:tile end]
       } else {
         float sacc[2][4];
 #pragma unroll
@@ -1158,6 +1162,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 
     // ---- finalize the item: normalised partial O and LSE (log2 domain) ------------------
     if constexpr (TR) {
+      // [tr-emu:finalize begin]
       // lane (g, t) owns O^T[dims 16 mb + g, + 8][rows 2t, 2t + 1]
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1188,6 +1193,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
           }
         }
       }
+      // [tr-emu:finalize end]
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

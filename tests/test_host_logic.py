@@ -300,3 +300,16 @@ def test_every_environment_switch_is_documented():
     design = open(os.path.join(root, "DESIGN.md")).read()
     missing = sorted(n for n in used if n not in design)
     assert used and not missing, missing
+
+
+def test_attention_transposed_tile_source_runs_on_the_host():
+    """tools/attn_tr_emu.py: the TR = 1 blocks of paged_attn.cu (Q fragments, the tile loop body,
+    the output scatter), cut out of the .cu file and run by 32 host threads with emulated ldmatrix /
+    mma.sync / movmatrix / shuffles over TMA-swizzled shared memory, reproduce softmax(QK^T)V —
+    ragged causal ends, split-KV partials and multi-token queries included."""
+    import os
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(__file__), "..", "tools", "attn_tr_emu.py")
+    r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
