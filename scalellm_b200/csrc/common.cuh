@@ -390,6 +390,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
 // An "n tile" of the partition is 128 << nsub_log2 output columns (two weight tiles share one
 // activation stage when the batch fits 64 rows, halving the activation traffic out of L2).
 // ---------------------------------------------------------------------------
+// [w4-emu:plan begin]
 struct W4Plan {
   int units, P, KT, NT, slots;  // slots = max contributors of any tile (partials buffer depth)
   int nsub_log2;                // 128-column weight tiles per n tile of the partition: 1 << nsub_log2
@@ -415,6 +416,7 @@ __host__ __device__ __forceinline__ int w4_contrib(const W4Plan& pl, int nt) {
 __host__ __device__ __forceinline__ int w4_contrib_col(const W4Plan& pl, int col) {
   return w4_contrib(pl, col >> (7 + pl.nsub_log2));
 }
+// [w4-emu:plan end]
 constexpr int W4_MAX_SLOTS = 8;
 // The partition b200_w4a16_gemm_splitk uses for M rows x a [K, N] weight on the current device.
 W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M);

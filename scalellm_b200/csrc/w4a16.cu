@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
 // ===========================================================================
 // tcgen05 stream-K GEMM (partials out)
 // ===========================================================================
+// [w4-emu:cfg begin]  (tools/w4_emu.cpp compiles this block, the barrier initialisation and the
+// role code of the kernel for the host)
 template <int MT, int NSUB>
 struct W4Cfg {
   static constexpr int ACT_STAGES = MT <= 64 ? 6 : 3;   // activation ring (L2 / TMA latency)
@@ -298,6 +300,7 @@ struct SegIter {
     return true;
   }
 };
+// [w4-emu:cfg end]
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 r;
@@ -367,6 +370,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   const int u_end = w4_unit_begin(blockIdx.x + 1, p.plan.units, p.plan.P);
 
   if (threadIdx.x == 0) {
+    // [w4-emu:init begin]
     for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
       mbar_init(&raw_full[i], 1);
       mbar_init(&raw_empty[i], 4);
@@ -383,6 +387,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    // [w4-emu:init end]
     fence_mbar_init();
   }
   if (warp == W4_WARP_MMA) {
@@ -396,6 +401,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   const uint32_t tmem_base = *tmem_holder;
   if (threadIdx.x == 0) W4_TRACE(1);
 
+  // [w4-emu:roles begin]
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
     // group = warp / 4 takes weight tiles cnt % 4 == group; tile cnt goes to TMEM slot
@@ -695,6 +701,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     }
     if (warp == W4_WARP_EPI && lane == 0) W4_TRACE(7);
   }
+  // [w4-emu:roles end]
 
   tc_fence_before();
   __syncthreads();

@@ -313,3 +313,17 @@ def test_attention_transposed_tile_source_runs_on_the_host():
     tool = os.path.join(os.path.dirname(__file__), "..", "tools", "attn_tr_emu.py")
     r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def test_w4a16_role_code_runs_on_the_host_for_every_variant():
+    """tools/w4_emu.py: the GEMM kernel's own role code (dequant groups, producers, MMA issuer,
+    epilogue) and barrier initialisation, cut out of w4a16.cu and run by one host thread per warp
+    over emulated mbarriers / copies / tensor memory / tensor pipe: no stale operand, no overwrite
+    under a queued MMA, exact accumulator segments, no deadlock — default kernel and every
+    B200_W4_VARIANT."""
+    import os
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(__file__), "..", "tools", "w4_emu.py")
+    r = subprocess.run([sys.executable, tool, "3"], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and r.stdout.count(", ok") == 7, r.stdout + r.stderr
