@@ -336,11 +336,17 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 //   8: one "full" barrier per stage: the activation TMA completes on the slot's deq_full barrier
 //      (4 dequant arrivals + the producer's expect_tx arrival + the bytes), so the MMA thread
 //      waits once per tile instead of twice; combines with 2 (10) and 2 + 4 (14)
+//  16: two MMA-issuing warps (18 and the otherwise idle 19): warp 18 + i takes the tiles with
+//      cnt % 2 == i and accumulates them into its own accumulator [128 x MT] (the two TMEM regions
+//      that double-buffer the default kernel's accumulator, single-buffered here, so the slot
+//      ring keeps its 6 entries); the epilogue adds the two accumulators in a fixed order.  Halves
+//      the per-tile work of an issuing thread; combines with 4 (20), 8 (24) and both (28)
 template <int MT, int NSUB, bool TRACE, int VAR = 0>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
-  static_assert((VAR & 3) != 3 && VAR < 16, "VAR: 1 and 2 are alternatives");
+  static_assert((VAR & 3) != 3 && VAR < 32 && (!(VAR & 16) || !(VAR & 3)),
+                "VAR: 1 and 2 are alternatives, and neither combines with 16");
   static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
                              Cfg::ACC_BUFS == 2 && !TRACE),
                 "variants need stage == slot");
@@ -384,7 +390,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       mbar_init(&deq_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_full[i], (VAR & 16) ? 2 : 1);
       mbar_init(&tmem_empty[i], 4);
     }
     // [w4-emu:init end]
@@ -539,6 +545,54 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       }
     }
     __syncwarp();
+  } else if ((VAR & 16) != 0 && (warp == W4_WARP_MMA || warp == W4_WARP_MMA + 1)) {
+    // ===================== two MMA issuers (VAR & 16) ==========================
+    // Issuer `me` takes the tiles with cnt % 2 == me into accumulator `me`.  Every segment both
+    // issuers first wait until the epilogue has drained the previous one (also an issuer without a
+    // tile in this segment: its arrival below must not count towards the previous segment), then
+    // each arrives once on tmem_full: through a commit behind its last MMAs, or directly if it
+    // had no tile.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
+    const int me = warp - W4_WARP_MMA;
+    const uint32_t d_tmem = tbase + me * MT;
+    SegIter it{u_begin, u_end, KT};
+    int nt, kt0, kt1, cnt = 0, seg = 0;
+    while (it.next(nt, kt0, kt1)) {
+      mbar_wait(&tmem_empty[0], (seg & 1) ^ 1);
+      tc_fence_after();
+      uint32_t started = 0;  // 0: my next MMA overwrites my accumulator
+      for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
+        if ((cnt & 1) != me) continue;
+        const int ds = cnt % Cfg::A_STAGES;  // == activation stage (one weight tile per unit)
+        const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
+        if constexpr (!(VAR & 8)) mbar_wait(&act_full[ds], dph);
+        mbar_wait(&deq_full[ds], dph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + ds * Cfg::ACT_BYTES);
+          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b_desc =
+                b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
+            umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : started);
+          }
+          umma_commit(&deq_empty[ds]);
+          umma_commit(&act_empty[ds]);
+        }
+        __syncwarp();
+        started = 1u;
+      }
+      if (started) {
+        if (elect_one()) umma_commit(&tmem_full[0]);
+      } else if (lane == 0) {
+        mbar_arrive(&tmem_full[0]);
+      }
+      __syncwarp();
+      ++seg;
+    }
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
     // The whole warp runs this loop converged so every operand is warp-uniform; one elected lane
@@ -666,6 +720,47 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     pdl_wait();  // the partials buffer may still be read by an earlier kernel's consumer
     SegIter it{u_begin, u_end, KT};
     int nt, kt0, kt1, seg = 0;
+    if constexpr (VAR & 16) {
+      // two accumulators per segment (tiles cnt even / odd), one of them unused when the segment
+      // is a single tile: partial = acc0 + acc1 in that order
+      int cnt0 = 0;  // tiles of this CTA before the segment
+      while (it.next(nt, kt0, kt1)) {
+        const int len = kt1 - kt0;
+        const bool has0 = len >= 2 || (cnt0 & 1) == 0, has1 = len >= 2 || (cnt0 & 1) == 1;
+        const int slot = (int)blockIdx.x - w4_first_owner(p.plan, nt);
+        float* part = p.partials + (int64_t)slot * p.slot_stride + (int64_t)nt * 128 + n_local;
+        mbar_wait(&tmem_full[0], seg & 1);
+        if (it.u >= it.u1 && warp == W4_WARP_EPI && lane == 0) pdl_launch_dependents();
+        tc_fence_after();
+        constexpr int CH = MT >= 32 ? 32 : 16;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < MT; c0 += CH) {
+          uint32_t r0[CH], r1[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) r0[i] = r1[i] = 0u;  // +0.0f
+          if (has0) {
+            if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r0);
+            else tmem_ld_32x32b_x16(taddr + c0, r0);
+          }
+          if (has1) {
+            if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + MT + c0, r1);
+            else tmem_ld_32x32b_x16(taddr + MT + c0, r1);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int m = c0 + i;
+            if (m < p.M) part[(int64_t)m * p.N] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[0]);
+        cnt0 += len;
+        ++seg;
+      }
+    } else
     while (it.next(nt, kt0, kt1)) {
       const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
       const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
@@ -798,13 +893,13 @@ static long long* g_w4_trace = nullptr;
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-// B200_W4_VARIANT = 1 | 2 | 4 | 6 | 10 | 14: experimental variants of the kernel (see VAR above); only for
+// B200_W4_VARIANT = 1 | 2 | 4 | 6 | 10 | 14 | 16 | 20 | 24 | 28: experimental variants of the kernel (see VAR above); only for
 // batches <= 64 rows with one weight tile per unit, everything else runs the default kernel
 static int w4_variant() {
   static const int v = [] {
     const char* e = getenv("B200_W4_VARIANT");
     const int v = e ? atoi(e) : 0;
-    return (v == 1 || v == 2 || v == 4 || v == 6 || v == 10 || v == 14) ? v : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 6 || v == 10 || v == 14 || v == 16 || v == 20 || v == 24 || v == 28) ? v : 0;
   }();
   return v;
 }
@@ -833,6 +928,10 @@ static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream
         case 6: return launch_w4_kernel<MT, 1, false, 6>(amap, p, st);
         case 10: return launch_w4_kernel<MT, 1, false, 10>(amap, p, st);
         case 14: return launch_w4_kernel<MT, 1, false, 14>(amap, p, st);
+        case 16: return launch_w4_kernel<MT, 1, false, 16>(amap, p, st);
+        case 20: return launch_w4_kernel<MT, 1, false, 20>(amap, p, st);
+        case 24: return launch_w4_kernel<MT, 1, false, 24>(amap, p, st);
+        case 28: return launch_w4_kernel<MT, 1, false, 28>(amap, p, st);
         default: break;
       }
     }

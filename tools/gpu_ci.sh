@@ -166,10 +166,10 @@ if has timeline; then
   head -40 $OUT/step_timeline.log >> $OUT/summary.txt
 fi
 if has w4var; then
-  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6|10|14): parity, a GEMM-only A/B
+  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT=1|2|4|6|10|14|16|20|24|28): parity, a GEMM-only A/B
   # (seconds per variant), then the full bench for the default and the fastest variant
   : > $OUT/w4_variants.jsonl
-  for v in 0 1 2 4 6 10 14; do
+  for v in 0 1 2 4 6 10 14 16 20 24 28; do
     if [ $v != 0 ]; then
       B200_W4_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_w4a16.py tests/test_gpu_decode_step.py \
           -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_w4var$v.log 2>&1

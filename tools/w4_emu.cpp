@@ -93,14 +93,25 @@ struct EmuBar {
 };
 static EmuBar g_eb[Cfg::N_BARS];
 static bool g_drained[2] = {true, true};
+static bool g_readable[2] = {false, false};  // accumulator holds (part of) the segment handed to the epilogue
+static int g_reads[2] = {0, 0};              // tcgen05.ld of it since the hand-over
 static inline int bar_index(const uint64_t* b) { return (int)(b - g_bars); }
+static void segment_complete(int buf);  // an accumulator segment was handed to the epilogue
 static void bar_check_complete(int i) {  // g_mu held
   EmuBar& b = g_eb[i];
   if (b.pending == 0 && b.tx == 0) {
     ++b.phase;
     b.pending = b.count;
-    const int te = bar_index(tmem_empty);
-    if (i == te || i == te + 1) g_drained[i - te] = true;  // the epilogue released the accumulator
+    const int te = bar_index(tmem_empty), tf = bar_index(tmem_full);
+    if (i == te || i == te + 1) {  // the epilogue released the accumulator(s)
+      for (int a = 0; a < 2; ++a) {
+        if (!(VAR & 16) && a != i - te) continue;
+        if (g_readable[a] && g_reads[a] == 0) fail("epilogue released an accumulator it never read", a);
+        g_readable[a] = false;
+        g_drained[a] = true;
+      }
+    }
+    if (i == tf || i == tf + 1) segment_complete(i - tf);
   }
 }
 static void mbar_init(uint64_t* bar, uint32_t count) {
@@ -231,8 +242,14 @@ static void umma_commit(uint64_t* bar) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_pipe.push_back(PipeOp{1, 0, 0, 0, 0, 0, bar_index(bar)});
 }
-static inline void tmem_ld_32x32b_x32(uint32_t, uint32_t (&r)[32]) { for (auto& x : r) x = 0; }
-static inline void tmem_ld_32x32b_x16(uint32_t, uint32_t (&r)[16]) { for (auto& x : r) x = 0; }
+static void tmem_ld_check(uint32_t taddr) {  // the epilogue may only read what was handed over to it
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int a = (int)(taddr & 0xffff) / MT;
+  if (a < 0 || a > 1 || !g_readable[a]) fail("epilogue reads an accumulator that holds no part of its segment", a);
+  else ++g_reads[a];
+}
+static inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_check(taddr); for (auto& x : r) x = 0; }
+static inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_check(taddr); for (auto& x : r) x = 0; }
 
 // ---- expected work of this CTA ---------------------------------------------------------------------------
 struct Segment {
@@ -244,21 +261,40 @@ static size_t g_seg_committed = 0;
 static std::vector<long> g_acc[2];  // weight tiles accumulated into each buffer since its last reset
 static int g_acc_ks[2] = {0, 0};    // k-steps of the tile being accumulated
 
+static bool g_fresh[2] = {false, false};  // accumulator was (re)started since the last segment hand-over
+
+static void segment_complete(int buf) {  // g_mu held: tmem_full[buf] completed a phase
+  if (g_seg_committed >= g_segments.size()) { fail("more accumulator hand-overs than segments"); return; }
+  const Segment& s = g_segments[g_seg_committed];
+  long cnt0 = 0;  // tiles of the CTA before this segment
+  for (size_t i = 0; i < g_seg_committed; ++i) cnt0 += g_segments[i].kt1 - g_segments[i].kt0;
+  if (VAR & 16) {  // two issuers: tiles with even / odd position in the CTA's tile stream
+    if (buf != 0) fail("two-issuer kernel uses tmem_full[0] only", buf);
+    std::vector<long> want[2];
+    for (int kt = s.kt0; kt < s.kt1; ++kt) want[(cnt0 + kt - s.kt0) & 1].push_back((long)s.nt * g_KT + kt);
+    for (int i = 0; i < 2; ++i) {
+      if (want[i].empty() ? g_fresh[i] : (!g_fresh[i] || g_acc[i] != want[i]) || g_acc_ks[i] != 0)
+        fail("issuer's accumulator does not hold exactly its share of the segment", (long)g_seg_committed, i,
+             (long)g_acc[i].size());
+      g_fresh[i] = false;
+      g_readable[i] = !want[i].empty();
+      g_reads[i] = 0;
+    }
+  } else {
+    if ((int)(g_seg_committed & 1) != buf) fail("segment committed from the wrong accumulator buffer", buf);
+    std::vector<long> want;
+    for (int kt = s.kt0; kt < s.kt1; ++kt) want.push_back((long)s.nt * g_KT + kt);
+    if (g_acc[buf] != want || g_acc_ks[buf] != 0)
+      fail("accumulator does not hold exactly its segment's tiles", (long)g_seg_committed, (long)g_acc[buf].size(),
+           (long)want.size());
+    g_readable[buf] = true;
+    g_reads[buf] = 0;
+  }
+  ++g_seg_committed;
+}
+
 static void pipe_execute(const PipeOp& op) {  // g_mu held
   if (op.kind == 1) {
-    const int tf = bar_index(tmem_full);
-    if (op.bar == tf || op.bar == tf + 1) {  // an accumulator segment is complete: must be the next one, exactly
-      const int buf = op.bar - tf;
-      if (g_seg_committed >= g_segments.size()) { fail("more accumulator commits than segments"); return; }
-      const Segment& s = g_segments[g_seg_committed];
-      if ((int)(g_seg_committed & 1) != buf) fail("segment committed from the wrong accumulator buffer", buf);
-      std::vector<long> want;
-      for (int kt = s.kt0; kt < s.kt1; ++kt) want.push_back((long)s.nt * g_KT + kt);
-      if (g_acc[buf] != want || g_acc_ks[buf] != 0)
-        fail("accumulator does not hold exactly its segment's tiles", (long)g_seg_committed, (long)g_acc[buf].size(),
-             (long)want.size());
-      ++g_seg_committed;
-    }
     if (--g_eb[op.bar].pending < 0) fail("more arrivals than the barrier expects", op.bar);
     bar_check_complete(op.bar);
     return;
@@ -275,6 +311,7 @@ static void pipe_execute(const PipeOp& op) {  // g_mu held
     if (!op.accumulate) {  // first MMA of a segment overwrites the accumulator
       if (!g_drained[op.buf]) fail("accumulator overwritten before the epilogue drained it", op.buf);
       g_drained[op.buf] = false;
+      g_fresh[op.buf] = true;
       acc.clear();
     } else if (acc.empty()) {
       fail("accumulating into an accumulator that was never started", op.buf);
@@ -341,6 +378,9 @@ static int run_cta(int KT, int u_begin, int u_end, uint32_t seed) {
   for (auto& a : g_acc) a.clear();
   g_acc_ks[0] = g_acc_ks[1] = 0;
   g_drained[0] = g_drained[1] = true;
+  g_fresh[0] = g_fresh[1] = false;
+  g_readable[0] = g_readable[1] = false;
+  g_reads[0] = g_reads[1] = 0;
   for (auto& x : g_raw_content) x = -1;
   for (auto& s : g_act_content) s[0] = s[1] = -1;
   for (auto& s : g_slot_content)

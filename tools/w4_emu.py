@@ -9,7 +9,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = (0, 1, 2, 4, 6, 10, 14)
+VARIANTS = (0, 1, 2, 4, 6, 10, 14, 16, 20, 24, 28)
 
 
 def extract(src: str, name: str) -> str:
