@@ -915,6 +915,8 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       }
       // [tr-emu:load_q end]
     } else {
+      // [def-emu:load_q begin]  (the default blocks run through the same host harness: they are
+      // GPU-validated, so they validate the harness's ldmatrix / mma.sync emulation)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int r = (lane >> 2) + 8 * h;
@@ -929,6 +931,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
           qa[ks][2 + h] = ok ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
         }
       }
+      // [def-emu:load_q end]
     }
   };
 
@@ -1079,6 +1082,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
         }
         // [tr-emu:tile end]
       } else {
+        // [def-emu:tile begin]
         float sacc[2][4];
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
@@ -1153,6 +1157,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
           mma_16816<T>(o[2 * dq], pa, bf[0], bf[1]);
           mma_16816<T>(o[2 * dq + 1], pa, bf[2], bf[3]);
         }
+        // [def-emu:tile end]
       }
       __syncwarp();
       if (boundary) fence_proxy_async_smem();
@@ -1195,6 +1200,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       }
       // [tr-emu:finalize end]
     } else {
+      // [def-emu:finalize begin]
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         l[h] += __shfl_xor_sync(0xffffffffu, l[h], 1);
@@ -1221,7 +1227,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
           }
         }
       }
-
+      // [def-emu:finalize end]
     }
 
     // ---- rotate: every pipeline slot advances one stage ---------------------------------------

@@ -3,7 +3,10 @@
 //
 // tools/attn_tr_emu.py cuts the three marked blocks ([tr-emu:load_q], [tr-emu:tile],
 // [tr-emu:finalize]) out of the .cu file into attn_tr_emu_*.inc and compiles this harness around
-// them: 32 host threads play the lanes of one warp and run the kernel's own statements; the warp
+// them (-DEMU_TR=1).  With -DEMU_TR=0 the default branches ([def-emu:*]) are compiled instead: they
+// are validated on the GPU, so running them here validates the emulated ldmatrix / mma.sync /
+// shuffle semantics the TR check relies on.  How it works: 32 host threads play the lanes of one
+// warp and run the kernel's own statements; the warp
 // collectives (ldmatrix, mma.sync, movmatrix, shuffles, votes) are emulated with a barrier and a
 // shared exchange area, shared memory is a byte array filled the way TMA fills it (128-byte
 // swizzle).  The result is compared with a plain softmax(QK^T)V.  This checks the CUDA source's
@@ -11,12 +14,21 @@
 // tools/attn_tr_model.py checks the algebra the source was written from.
 #include <pthread.h>
 
+#ifndef EMU_TR
+#define EMU_TR 1
+#endif
+
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+struct float2 {
+  float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 // ---- element type stand-in -------------------------------------------------------------------
 struct bf16_t {
@@ -161,7 +173,7 @@ static void* lane_main(void* arg) {
   const int lane = t_lane;
   Case& c = *g_case;
   const Params& p = c.p;
-  constexpr int KS = D / 16, NB = D / 16, QR = 2, ROWS = 8;
+  constexpr int KS = D / 16, NB = EMU_TR ? D / 16 : D / 8, QR = EMU_TR ? 2 : 4, ROWS = EMU_TR ? 8 : 16;
   constexpr int ROWB = D * (int)sizeof(T);
   const int G = c.G;
   Item cur{c.n_tiles, c.q_len, 0, 0, 0, 0, 0};
@@ -177,7 +189,7 @@ static void* lane_main(void* arg) {
   int row_end[2], row_begin[2];
   float slope_log2[2] = {0.f, 0.f};
   for (int h = 0; h < 2; ++h) {
-    const int r = (lane & 3) * 2 + h;
+    const int r = EMU_TR ? (lane & 3) * 2 + h : (lane >> 2) + 8 * h;
     const bool ok = r < n_rows;
     const int row = row0 + (ok ? r : 0), qi = row / G;
     row_end[h] = ok ? q_pos0 + qi + 1 : 0;
