@@ -41,6 +41,8 @@
 
 namespace b200 {
 
+// [attn-emu:params begin]  (tools/attn_emu.cpp compiles these definitions and the whole stream
+// kernel for the host)
 constexpr int ATT_WARPS = 4;
 constexpr int ATT_THREADS = ATT_WARPS * 32;
 constexpr int ATT_TILE = 16;         // kv slots per TMA stage
@@ -81,6 +83,7 @@ struct AttnCfg {
   static constexpr int EPL = CPL * 8;          // elements per lane per row
   static constexpr int TILE_ELEMS = ATT_TILE * D;
 };
+// [attn-emu:params end]
 
 // single-warp CTAs take at most ATT_TPS_W1 tiles, so their block-table window is small
 constexpr int ATT_TPS_W1 = 32;
@@ -746,6 +749,7 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 // global accesses are off the critical path.  Partial O / LSE go to the workspace; the combine
 // pass recomputes the same partition to know which pieces exist.
 // ===========================================================================
+// [attn-emu:persist begin]
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
 // High-occupancy variant (OCC = 1, B200_ATTN_OCC=1): the warp-state profile of the default
@@ -1250,6 +1254,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
     }
   }
 }
+// [attn-emu:persist end]
 
 // Second pass: merge split-KV partials (same maths as the reference's unwired
 // attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).

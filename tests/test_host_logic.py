@@ -328,3 +328,18 @@ def test_w4a16_role_code_runs_on_the_host_for_every_variant():
     tool = os.path.join(os.path.dirname(__file__), "..", "tools", "w4_emu.py")
     r = subprocess.run([sys.executable, tool, "3"], capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and r.stdout.count(", ok") == 11, r.stdout + r.stderr
+
+
+def test_attention_stream_kernel_runs_on_the_host_in_every_instantiation():
+    """tools/attn_emu.py: the whole paged-attention stream kernel cut out of paged_attn.cu and run
+    on the host, every CTA by 32 threads over emulated mbarriers / tensor-map loads / ldmatrix /
+    mma.sync / movmatrix, with the library's own work partition, on paged caches with shuffled
+    block ids (GQA / MHA / MQA, block sizes 1 / 8 / 16, multi-token queries, many pieces, garbage
+    past the sequence ends): the default instantiation (GPU-validated, so it validates the
+    harness) and the opt-in ones (11 CTAs/SM ring, transposed tile, both)."""
+    import os
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(__file__), "..", "tools", "attn_emu.py")
+    r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=2400)
+    assert r.returncode == 0 and r.stdout.count("\nok") == 4, r.stdout + r.stderr
