@@ -30,6 +30,9 @@
 #ifndef EMU_TR
 #define EMU_TR 0
 #endif
+#ifndef EMU_D
+#define EMU_D 128
+#endif
 
 extern "C" int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads, int n_kv_heads,
                                     int head_dim, int block_size, int64_t* out);
@@ -272,18 +275,18 @@ static void* lane_main(void* arg) {
   t_lane = (int)(intptr_t)arg;
   threadIdx.x = (unsigned)t_lane;
   Problem& P = *g_pr;
-  paged_attn_persist_kernel<bf16_t, 128, EMU_OCC, EMU_TR>(P.kmap, P.vmap, P.p, P.total_tiles, P.n_seq);
+  paged_attn_persist_kernel<bf16_t, EMU_D, EMU_OCC, EMU_TR>(P.kmap, P.vmap, P.p, P.total_tiles, P.n_seq);
   return nullptr;
 }
 
 static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>& q_lens,
                const std::vector<int>& kv_lens, uint32_t seed) {
   Problem P;
-  P.B = B; P.H = H; P.Hkv = Hkv; P.D = 128; P.bs = bs; P.max_q = max_q;
+  P.B = B; P.H = H; P.Hkv = Hkv; P.D = EMU_D; P.bs = bs; P.max_q = max_q;
   P.q_lens = q_lens; P.kv_lens = kv_lens;
   std::mt19937 rng(seed);
   auto frand = [&]() { return (float)((int)(rng() % 65536) - 32768) / 32768.0f; };
-  const int D = 128, G = H / Hkv;
+  const int D = EMU_D, G = H / Hkv;
   int max_kv = 0, n_blocks = 0;
   P.q_cu = {0}; P.kv_cu = {0}; P.blk_cu = {0};
   for (int b = 0; b < B; ++b) {

@@ -8,7 +8,8 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CONFIGS = ((0, 0), (1, 0), (0, 1), (1, 1))     # (OCC, TR)
+CONFIGS = ((0, 0, 128), (1, 0, 128), (0, 1, 128), (1, 1, 128),     # (OCC, TR, head_dim)
+           (0, 0, 64), (1, 1, 64), (0, 0, 256))
 
 
 def extract(src: str, name: str) -> str:
@@ -33,10 +34,10 @@ def main() -> int:
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "attn_emu_params.inc"), "w").write(params + "\n")
         open(os.path.join(tmp, "attn_emu_persist.inc"), "w").write(kernel + "\n")
-        for occ, tr in CONFIGS:
-            exe = os.path.join(tmp, f"attn_emu_{occ}{tr}")
+        for occ, tr, hd in CONFIGS:
+            exe = os.path.join(tmp, f"attn_emu_{occ}{tr}_{hd}")
             r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", f"-DEMU_OCC={occ}",
-                                f"-DEMU_TR={tr}", "-I", tmp, os.path.join(ROOT, "tools", "attn_emu.cpp"), "-o", exe,
+                                f"-DEMU_TR={tr}", f"-DEMU_D={hd}", "-I", tmp, os.path.join(ROOT, "tools", "attn_emu.cpp"), "-o", exe,
                                 "-L" + lib_dir, "-lb200decode", "-Wl,-rpath," + lib_dir],
                                capture_output=True, text=True)
             if r.returncode != 0:
@@ -44,7 +45,7 @@ def main() -> int:
                 return 2
             env = dict(os.environ, B200_ATTN_OCC=str(occ), B200_ATTN_TR=str(tr))
             r = subprocess.run([exe], capture_output=True, text=True, timeout=1500, env=env)
-            sys.stdout.write(f"-- OCC={occ} TR={tr}\n" + r.stdout)
+            sys.stdout.write(f"-- OCC={occ} TR={tr} head_dim={hd}\n" + r.stdout)
             sys.stderr.write(r.stderr[-2000:])
             rc |= r.returncode
     return rc
