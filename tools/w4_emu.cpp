@@ -26,6 +26,9 @@
 #ifndef EMU_VAR
 #define EMU_VAR 0
 #endif
+#ifndef EMU_MT
+#define EMU_MT 64
+#endif
 
 // ---- CUDA-isms the blocks use ----------------------------------------------------------------------
 #define __host__
@@ -57,7 +60,7 @@ constexpr int W4_MAX_BLOB = 8192 + 4 * (256 + 128);
 
 #include "w4_emu_plan.inc"
 
-constexpr int MT = 64, NSUB = 1, VAR = EMU_VAR;
+constexpr int MT = EMU_MT, NSUB = 1, VAR = EMU_VAR;
 constexpr bool TRACE = false;
 #include "w4_emu_cfg.inc"
 #undef W4_TRACE
@@ -445,6 +448,6 @@ int main(int argc, char** argv) {
       ++n;
       if (bad) break;
     }
-  std::printf("w4_emu VAR=%d: %d CTA runs, %s\n", EMU_VAR, n, bad ? "FAILED" : "ok");
+  std::printf("w4_emu VAR=%d MT=%d: %d CTA runs, %s\n", EMU_VAR, EMU_MT, n, bad ? "FAILED" : "ok");
   return bad ? 1 : 0;
 }

@@ -10,6 +10,9 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = (0, 1, 2, 4, 6, 10, 14, 16, 20, 24, 28)
+# (variant, rows-of-the-batch tile): the default kernel also at 16 and 128 rows (128: 3-stage
+# activation ring, 4 TMEM slots), two variants at 16 rows
+CONFIGS = tuple((v, 64) for v in VARIANTS) + ((0, 16), (0, 128), (2, 16), (16, 16))
 
 
 def extract(src: str, name: str) -> str:
@@ -32,10 +35,10 @@ def main(rounds: int = 12) -> int:
         for name, text in blocks.items():
             with open(os.path.join(tmp, f"w4_emu_{name}.inc"), "w") as f:
                 f.write(text + "\n")
-        for var in VARIANTS:
-            exe = os.path.join(tmp, f"w4_emu_{var}")
+        for var, mt in CONFIGS:
+            exe = os.path.join(tmp, f"w4_emu_{var}_{mt}")
             r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", f"-DEMU_VAR={var}",
-                                "-I", tmp, os.path.join(ROOT, "tools", "w4_emu.cpp"), "-o", exe],
+                                f"-DEMU_MT={mt}", "-I", tmp, os.path.join(ROOT, "tools", "w4_emu.cpp"), "-o", exe],
                                capture_output=True, text=True)
             if r.returncode != 0:
                 sys.stderr.write(r.stderr[-6000:])
