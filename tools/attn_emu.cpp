@@ -15,6 +15,7 @@
 #include <pthread.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -22,6 +23,7 @@
 #include <cstring>
 #include <mutex>
 #include <random>
+#include <thread>
 #include <vector>
 
 #ifndef EMU_OCC
@@ -220,17 +222,23 @@ static void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   bar_check(b);
 }
 static void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // wall-clock deadline (a loaded machine may not schedule lane 0 for a long while), with back-off
+  const auto t0 = std::chrono::steady_clock::now();
   for (int spin = 0;; ++spin) {
     {
       std::lock_guard<std::mutex> lk(g_mu);
       if ((uint32_t)(eb(bar).phase & 1) != parity) return;
       if (g_failed) return;
     }
-    if (spin > 2000000) {
-      fail("mbar_wait never satisfied (the ring stalled)");
-      return;
+    if (spin < 200) {
+      sched_yield();
+    } else {
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+      if ((spin & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(300)) {
+        fail("mbar_wait never satisfied (the ring stalled)");
+        return;
+      }
     }
-    sched_yield();
   }
 }
 // box {64, D/64, 1, box_rows} at (0, 0, kvh, slot0): rows slot0.. of head kvh, each D elements, land

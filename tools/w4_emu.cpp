@@ -142,13 +142,14 @@ static void bar_complete_tx(int i, long bytes) {  // g_mu held
 }
 static void mbar_wait(uint64_t* bar, uint32_t parity) {
   const int i = bar_index(bar);
-  for (;;) {
+  for (int spin = 0;; ++spin) {
     {
       std::lock_guard<std::mutex> lk(g_mu);
       if ((uint32_t)(g_eb[i].phase & 1) != parity) return;
     }
     if (g_failed.load()) return;  // let the roles run off the end so the process can report
-    std::this_thread::yield();
+    if (spin < 200) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(50));  // do not starve the other roles
   }
 }
 
@@ -366,7 +367,7 @@ static void hardware_main(uint32_t seed) {  // copies complete in any order, the
         pipe_execute(op);
       }
     }
-    std::this_thread::yield();
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
   }
 }
 
@@ -414,7 +415,7 @@ static int run_cta(int KT, int u_begin, int u_end, uint32_t seed) {
   for (int w = 0; w < W4_THREADS / 32; ++w) warps.emplace_back(role_main<MT, NSUB, TRACE, VAR>, w);
   std::atomic<int> joined{0};
   std::thread watchdog([&] {
-    for (int i = 0; i < 3000 && joined.load() == 0; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    for (int i = 0; i < 30000 && joined.load() == 0; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(10));
     if (joined.load() == 0) fail("deadlock: the roles did not finish", u_begin, u_end, KT);
   });
   for (auto& t : warps) t.join();
