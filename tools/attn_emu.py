@@ -10,6 +10,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = ((0, 0, 128), (1, 0, 128), (0, 1, 128), (1, 1, 128),     # (OCC, TR, head_dim)
            (0, 0, 64), (1, 1, 64), (0, 0, 256))
+QUICK = ((0, 0, 128), (1, 1, 128), (1, 1, 64), (0, 0, 256))  # the CPU test's subset
 
 
 def extract(src: str, name: str) -> str:
@@ -19,7 +20,7 @@ def extract(src: str, name: str) -> str:
     return m.group(1)
 
 
-def main() -> int:
+def main(quick: bool = False) -> int:
     src = open(os.path.join(ROOT, "scalellm_b200", "csrc", "paged_attn.cu")).read()
     params = re.sub(r"^// kernel for the host\)\n", "", extract(src, "params"))
     kernel = extract(src, "persist")
@@ -34,7 +35,7 @@ def main() -> int:
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "attn_emu_params.inc"), "w").write(params + "\n")
         open(os.path.join(tmp, "attn_emu_persist.inc"), "w").write(kernel + "\n")
-        for occ, tr, hd in CONFIGS:
+        for occ, tr, hd in (QUICK if quick else CONFIGS):
             exe = os.path.join(tmp, f"attn_emu_{occ}{tr}_{hd}")
             r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", f"-DEMU_OCC={occ}",
                                 f"-DEMU_TR={tr}", f"-DEMU_D={hd}", "-I", tmp, os.path.join(ROOT, "tools", "attn_emu.cpp"), "-o", exe,
@@ -52,4 +53,4 @@ def main() -> int:
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(main(quick=len(sys.argv) > 1 and sys.argv[1] == "quick"))
