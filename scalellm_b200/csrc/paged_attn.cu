@@ -1259,6 +1259,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 // Second pass: merge split-KV partials (same maths as the reference's unwired
 // attn_combine_kernel, src/kernels/attention/kernel/attn_combine_kernel.cuh:30).
 // One warp per (token, head) row; each lane owns D/32 consecutive outputs (vector loads).
+// [attn-emu:combine begin]
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
   constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8 (1 or 3 for head_dim 32 / 96)
@@ -1357,6 +1358,7 @@ __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParam
       *reinterpret_cast<uint32_t*>(dst + e) = Num<T>::pack(acc[e] * inv, acc[e + 1] * inv);
   }
 }
+// [attn-emu:combine end]
 
 // ---------------------------------------------------------------------------
 // host side

@@ -9,7 +9,9 @@
 // mbarriers, the 4-D tensor-map loads into 128-byte-swizzled shared memory (out-of-range slots
 // read as zero), cp.async, ldmatrix, mma.sync, movmatrix, shuffles and votes.  The work partition
 // comes from the library itself (b200_debug_attn_plan).  The partials are merged with the LSE
-// formula and compared with a plain softmax(QK^T)V per sequence.  The default instantiation is
+// formula and compared with a plain softmax(QK^T)V per sequence; with split KV the combine kernel
+// (cut out of the source as well, [attn-emu:combine]) runs after the stream kernel and the final
+// bf16 output is compared too.  The default instantiation is
 // validated on the GPU, so it validates this harness; the opt-in ones (OCC, TR) are then checked
 // by the same harness.
 #include <pthread.h>
@@ -52,7 +54,7 @@ extern "C" int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len
 using std::max;
 using std::min;
 struct Dim3 {
-  unsigned x;
+  unsigned x, y;
 };
 static thread_local Dim3 blockIdx, threadIdx;
 struct float2 {
@@ -261,8 +263,24 @@ static void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int, i
 static void emu_cp_async4(uint32_t dst, const void* src) { std::memcpy(smem_raw + dst, src, 4); }
 static void emu_cp_async_wait_all() {}
 
+struct float4 {
+  float x, y, z, w;
+};
+template <typename V>
+static inline V __ldg(const V* p) { return *p; }
+template <typename V>
+static inline V __ldcg(const V* p) { return *p; }
+static inline float __shfl_sync(unsigned, float v, int src) {
+  g_xf[t_lane] = v;
+  sync_warp();
+  const float r = g_xf[src & 31];
+  sync_warp();
+  return r;
+}
+
 #include "attn_emu_params.inc"
 #include "attn_emu_persist.inc"
+#include "attn_emu_combine.inc"
 
 // ---- one problem ---------------------------------------------------------------------------------------------
 struct Problem {
@@ -384,7 +402,35 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
   }
   if (g_failed) return 1;
 
-  // merge the pieces (LSE formula) and compare with the reference
+  // second pass, as launch_attn does it: grid ((n_heads + 3) / 4, batch * max_q_len), 4 warps per
+  // CTA, each warp on its own (token, head) row: the warps are run one after the other
+  if (n_splits > 1) {
+    for (unsigned by = 0; by < (unsigned)(B * max_q) && !g_failed; ++by)
+      for (unsigned bx = 0; bx < (unsigned)((H + 3) / 4); ++bx)
+        for (int w = 0; w < 4; ++w) {
+          pthread_barrier_init(&g_bar, nullptr, LANES);
+          pthread_t th[LANES];
+          struct CArg { int lane, warp; unsigned bx, by; };
+          static CArg cargs[LANES];
+          for (int i = 0; i < LANES; ++i) {
+            cargs[i] = CArg{i, w, bx, by};
+            pthread_create(&th[i], nullptr, [](void* a) -> void* {
+              CArg* x = (CArg*)a;
+              t_lane = x->lane;
+              threadIdx.x = (unsigned)(x->warp * 32 + x->lane);
+              blockIdx.x = x->bx;
+              blockIdx.y = x->by;
+              paged_attn_combine_kernel<bf16_t, EMU_D>(g_pr->p);
+              return nullptr;
+            }, &cargs[i]);
+          }
+          for (int i = 0; i < LANES; ++i) pthread_join(th[i], nullptr);
+          pthread_barrier_destroy(&g_bar);
+        }
+  }
+
+  // compare the kernel pair's output with the reference (and, for split KV, also the harness's
+  // own LSE merge of the partials)
   double worst = 0.0;
   for (int b = 0; b < B; ++b)
     for (int qi = 0; qi < q_lens[b]; ++qi)
@@ -413,10 +459,12 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
             want += s[j] * bf2f(P.vc[(slot * Hkv + kvh) * D + d]);
           }
           want /= sum;
-          double got;
-          if (n_splits == 1) {
-            got = bf2f(P.out[(tok * H + h) * D + d]);
-          } else {
+          double got = bf2f(P.out[(tok * H + h) * D + d]);  // stream kernel (+ combine pass)
+          {
+            const double err0 = std::fabs(got - want);
+            if (!(err0 <= worst)) worst = err0;
+          }
+          if (n_splits > 1) {
             double L = 0, O = 0;
             for (int sp = 0; sp < n_splits; ++sp) {
               const double lse = P.ws_lse[wrow * n_splits + sp];

@@ -24,6 +24,7 @@ def main(quick: bool = False) -> int:
     src = open(os.path.join(ROOT, "scalellm_b200", "csrc", "paged_attn.cu")).read()
     params = re.sub(r"^// kernel for the host\)\n", "", extract(src, "params"))
     kernel = extract(src, "persist")
+    combine = extract(src, "combine")
     # the two inline-asm statements of the kernel become calls into the harness
     kernel, n1 = re.subn(r'asm volatile\("cp\.async\.ca\.shared\.global \[%0\], \[%1\], 4;" ::"r"\((.*?)\), "l"\((.*?)\)\s*:\s*"memory"\);',
                          r"emu_cp_async4(\1, \2);", kernel, flags=re.S)
@@ -35,6 +36,7 @@ def main(quick: bool = False) -> int:
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "attn_emu_params.inc"), "w").write(params + "\n")
         open(os.path.join(tmp, "attn_emu_persist.inc"), "w").write(kernel + "\n")
+        open(os.path.join(tmp, "attn_emu_combine.inc"), "w").write(combine + "\n")
         for occ, tr, hd in (QUICK if quick else CONFIGS):
             exe = os.path.join(tmp, f"attn_emu_{occ}{tr}_{hd}")
             r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", f"-DEMU_OCC={occ}",
