@@ -102,6 +102,7 @@ constexpr size_t attn_smem_bytes() {
          + ATT_TBL * sizeof(int32_t) + ATT_WARPS * AttnCfg<D>::STAGES * sizeof(uint64_t) + 128;
 }
 
+// [attn-emu:simt begin]
 template <typename T, int D, int R>
 __global__ void __launch_bounds__(ATT_THREADS, (D <= 128 ? 2 : 1))
 paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
@@ -391,6 +392,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     }
   }
 }
+// [attn-emu:simt end]
 
 
 // ===========================================================================

@@ -336,10 +336,12 @@ def test_attention_stream_kernel_runs_on_the_host_in_every_instantiation():
     mma.sync / movmatrix, with the library's own work partition, on paged caches with shuffled
     block ids (GQA / MHA / MQA, block sizes 1 / 8 / 16, multi-token queries, many pieces, garbage
     past the sequence ends): the default instantiation (GPU-validated, so it validates the
-    harness) and the opt-in ones (11 CTAs/SM ring, transposed tile, both)."""
+    harness) and the opt-in ones (11 CTAs/SM ring, transposed tile, both); then the CUDA-core kernel
+    (4 warps per CTA) at head_dim 128 (GPU-validated) and at the padded head dims 96 and 32, each
+    followed by the combine kernel."""
     import os
     import subprocess
     import sys
     tool = os.path.join(os.path.dirname(__file__), "..", "tools", "attn_emu.py")
     r = subprocess.run([sys.executable, tool, "quick"], capture_output=True, text=True, timeout=2400)
-    assert r.returncode == 0 and r.stdout.count("\nok") == 4, r.stdout + r.stderr
+    assert r.returncode == 0 and r.stdout.count("\nok") == 7, r.stdout + r.stderr

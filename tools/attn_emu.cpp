@@ -37,6 +37,9 @@
 #ifndef EMU_D
 #define EMU_D 128
 #endif
+#ifndef EMU_SIMT  // 1: the CUDA-core kernel (paged_attn_decode_kernel, 4 warps per CTA) instead of the stream kernel
+#define EMU_SIMT 0
+#endif
 
 extern "C" int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len, int n_heads, int n_kv_heads,
                                     int head_dim, int block_size, int64_t* out);
@@ -54,7 +57,7 @@ extern "C" int b200_debug_attn_plan(int64_t batch, int max_q_len, int max_kv_len
 using std::max;
 using std::min;
 struct Dim3 {
-  unsigned x, y;
+  unsigned x, y, z;
 };
 static thread_local Dim3 blockIdx, threadIdx;
 struct float2 {
@@ -89,6 +92,7 @@ struct Num<bf16_t> {
   static float to_f(bf16_t x) { return bf2f(x); }
   static bf16_t from_f(float x) { return f2bf(x); }
   static uint32_t pack(float lo, float hi) { return (uint32_t)f2bf(lo).bits | ((uint32_t)f2bf(hi).bits << 16); }
+  static float2 unpack(uint32_t w) { return float2{bf2f(bf16_t{(uint16_t)(w & 0xffffu)}), bf2f(bf16_t{(uint16_t)(w >> 16)})}; }
 };
 
 // the KV cache as the tensor map describes it: [n_slots][n_kv_heads][D]
@@ -100,12 +104,17 @@ struct CUtensorMap {
 
 // ---- one warp = 32 threads -----------------------------------------------------------------------------
 constexpr int LANES = 32;
-static pthread_barrier_t g_bar;
+struct WarpCtx {  // what the lanes of one warp share to emulate a warp-collective instruction
+  pthread_barrier_t bar;
+  uint32_t x32[LANES][8];
+  float xf[LANES];
+  int xi[LANES];
+};
+static WarpCtx g_warps[4];
+static thread_local WarpCtx* t_warp = &g_warps[0];
+static pthread_barrier_t g_cta_bar;  // __syncthreads of a multi-warp CTA
 static thread_local int t_lane;
-uint8_t smem_raw[96 * 1024] __attribute__((aligned(1024)));
-static uint32_t g_x32[LANES][8];
-static float g_xf[LANES];
-static int g_xi[LANES];
+uint8_t smem_raw[160 * 1024] __attribute__((aligned(1024)));
 static std::mutex g_mu;
 static bool g_failed = false;
 static void fail(const char* what) {
@@ -113,7 +122,8 @@ static void fail(const char* what) {
   if (!g_failed) std::fprintf(stderr, "attn_emu: %s\n", what);
   g_failed = true;
 }
-static void sync_warp() { pthread_barrier_wait(&g_bar); }
+static void sync_warp() { pthread_barrier_wait(&t_warp->bar); }
+static inline void __syncthreads() { pthread_barrier_wait(&g_cta_bar); }
 static inline void __syncwarp() { sync_warp(); }
 static inline void pdl_wait() {}
 static inline void pdl_launch_dependents() {}
@@ -123,31 +133,31 @@ static inline void prefetch_tensormap(const CUtensorMap*) {}
 static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - smem_raw); }
 
 static inline float __shfl_xor_sync(unsigned, float v, int mask) {
-  g_xf[t_lane] = v;
+  t_warp->xf[t_lane] = v;
   sync_warp();
-  const float r = g_xf[t_lane ^ mask];
+  const float r = t_warp->xf[t_lane ^ mask];
   sync_warp();
   return r;
 }
 static inline bool __any_sync(unsigned, bool pred) {
-  g_xi[t_lane] = pred;
+  t_warp->xi[t_lane] = pred;
   sync_warp();
   bool r = false;
-  for (int i = 0; i < LANES; ++i) r |= g_xi[i] != 0;
+  for (int i = 0; i < LANES; ++i) r |= t_warp->xi[i] != 0;
   sync_warp();
   return r;
 }
 static inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
 static void ldsm_impl(uint32_t (&r)[4], uint32_t addr, bool trans) {
-  g_x32[t_lane][0] = addr;
+  t_warp->x32[t_lane][0] = addr;
   sync_warp();
   for (int j = 0; j < 4; ++j) {
     uint16_t e[2];
     for (int k = 0; k < 2; ++k) {
       const int row = trans ? 2 * (t_lane & 3) + k : t_lane >> 2;
       const int col = trans ? t_lane >> 2 : 2 * (t_lane & 3) + k;
-      std::memcpy(&e[k], smem_raw + g_x32[8 * j + row][0] + col * 2, 2);
+      std::memcpy(&e[k], smem_raw + t_warp->x32[8 * j + row][0] + col * 2, 2);
     }
     r[j] = (uint32_t)e[0] | ((uint32_t)e[1] << 16);
   }
@@ -156,12 +166,12 @@ static void ldsm_impl(uint32_t (&r)[4], uint32_t addr, bool trans) {
 static void ldsm_x4(uint32_t (&r)[4], uint32_t addr) { ldsm_impl(r, addr, false); }
 static void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) { ldsm_impl(r, addr, true); }
 static uint32_t movmatrix_trans(uint32_t a) {
-  g_x32[t_lane][0] = a;
+  t_warp->x32[t_lane][0] = a;
   sync_warp();
   uint16_t e[2];
   for (int k = 0; k < 2; ++k) {
     const int src_row = 2 * (t_lane & 3) + k, src_col = t_lane >> 2;
-    const uint32_t w = g_x32[src_row * 4 + src_col / 2][0];
+    const uint32_t w = t_warp->x32[src_row * 4 + src_col / 2][0];
     e[k] = (uint16_t)(src_col & 1 ? w >> 16 : w & 0xffffu);
   }
   sync_warp();
@@ -169,16 +179,16 @@ static uint32_t movmatrix_trans(uint32_t a) {
 }
 template <typename T>
 static void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  for (int i = 0; i < 4; ++i) g_x32[t_lane][i] = a[i];
-  g_x32[t_lane][4] = b0;
-  g_x32[t_lane][5] = b1;
+  for (int i = 0; i < 4; ++i) t_warp->x32[t_lane][i] = a[i];
+  t_warp->x32[t_lane][4] = b0;
+  t_warp->x32[t_lane][5] = b1;
   sync_warp();
   auto half = [](uint32_t w, int k) { return bf2f(bf16_t{(uint16_t)(k ? w >> 16 : w & 0xffffu)}); };
   auto A = [&](int row, int col) {
     const int g = row & 7, t = (col & 7) >> 1;
-    return half(g_x32[g * 4 + t][(row >> 3) + 2 * (col >> 3)], col & 1);
+    return half(t_warp->x32[g * 4 + t][(row >> 3) + 2 * (col >> 3)], col & 1);
   };
-  auto B = [&](int k, int n) { return half(g_x32[n * 4 + ((k & 7) >> 1)][4 + (k >> 3)], k & 1); };
+  auto B = [&](int k, int n) { return half(t_warp->x32[n * 4 + ((k & 7) >> 1)][4 + (k >> 3)], k & 1); };
   const int g = t_lane >> 2, t = t_lane & 3;
   const int rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
   float acc[4];
@@ -204,7 +214,7 @@ static EmuBar& eb(uint64_t* bar) {
 }
 static void mbar_init(uint64_t* bar, uint32_t count) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_bar_base || bar < g_bar_base) g_bar_base = bar - t_lane;  // lane i initialises bars[i]
+  if (!g_bar_base || bar < g_bar_base) g_bar_base = bar - threadIdx.x;  // thread i initialises bars[i]
   EmuBar& b = g_eb[bar - g_bar_base];
   b.count = b.pending = (int)count;
   b.phase = 0;
@@ -271,14 +281,36 @@ static inline V __ldg(const V* p) { return *p; }
 template <typename V>
 static inline V __ldcg(const V* p) { return *p; }
 static inline float __shfl_sync(unsigned, float v, int src) {
-  g_xf[t_lane] = v;
+  t_warp->xf[t_lane] = v;
   sync_warp();
-  const float r = g_xf[src & 31];
+  const float r = t_warp->xf[src & 31];
   sync_warp();
   return r;
 }
 
+static inline uint4 ld_v4(const void* p) {
+  uint4 r;
+  std::memcpy(&r, p, 16);
+  return r;
+}
+// box {D, 1, box_rows} at (0, kvh, slot0), no swizzle: rows land contiguously [row][D]
+static void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int, int kvh, int slot0) {
+  const int D = map->head_dim;
+  for (int r = 0; r < map->box_rows; ++r)
+    for (int d = 0; d < D; ++d) {
+      bf16_t v = f2bf(0.f);
+      const int64_t slot = (int64_t)slot0 + r;
+      if (slot >= 0 && slot < map->n_slots) v = map->base[(slot * map->n_kv_heads + kvh) * D + d];
+      std::memcpy((uint8_t*)dst + (size_t)(r * D + d) * 2, &v, 2);
+    }
+  std::lock_guard<std::mutex> lk(g_mu);
+  EmuBar& b = eb(bar);
+  b.tx -= (long)map->box_rows * D * 2;
+  bar_check(b);
+}
+
 #include "attn_emu_params.inc"
+#include "attn_emu_simt.inc"
 #include "attn_emu_persist.inc"
 #include "attn_emu_combine.inc"
 
@@ -300,8 +332,10 @@ static Problem* g_pr;
 static void* lane_main(void* arg) {
   t_lane = (int)(intptr_t)arg;
   threadIdx.x = (unsigned)t_lane;
+#if !EMU_SIMT
   Problem& P = *g_pr;
   paged_attn_persist_kernel<bf16_t, EMU_D, EMU_OCC, EMU_TR>(P.kmap, P.vmap, P.p, P.total_tiles, P.n_seq);
+#endif
   return nullptr;
 }
 
@@ -352,11 +386,15 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
   P.out.assign(P.q.size(), f2bf(-77.f));
 
   int64_t plan[8];
-  if (b200_debug_attn_plan(B, max_q, max_kv, H, Hkv, D, bs, plan) != 0 || plan[0] != 2) {
-    std::fprintf(stderr, "attn_emu: the library does not plan the stream kernel for this case\n");
+  if (b200_debug_attn_plan(B, max_q, max_kv, H, Hkv, D, bs, plan) != 0 || plan[0] != (EMU_SIMT ? 0 : 2)) {
+    std::fprintf(stderr, "attn_emu: the library does not plan the expected kernel for this case (impl %lld)\n",
+                 (long long)plan[0]);
     return 1;
   }
-  const int n_splits = (int)plan[1], tpw = (int)plan[2], ntm = (int)plan[3];
+  const int n_splits = (int)plan[1], ntm = (int)plan[3];
+  const int n_tiles_max = (max_kv + ATT_TILE - 1) / ATT_TILE;
+  // fixed-split kernel: any tiles-per-split that covers the tiles with n_splits pieces is valid
+  const int tpw = EMU_SIMT ? (n_tiles_max + n_splits - 1) / n_splits : (int)plan[2];
   P.n_seq = (int)plan[4];
   P.total_tiles = plan[6];
   P.ws_o.assign((size_t)B * max_q * H * n_splits * D, NAN);
@@ -368,25 +406,57 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
   p.block_table = P.table.data(); p.block_cu_lens = P.blk_cu.data();
   p.alibi = nullptr; p.ws_o = P.ws_o.data(); p.ws_lse = P.ws_lse.data();
   p.q_stride_t = (int64_t)H * D; p.q_stride_h = D; p.o_stride_t = (int64_t)H * D; p.o_stride_h = D;
-  p.n_heads = H; p.n_kv_heads = Hkv; p.group = G; p.n_hg = 1; p.n_rb = (int)plan[5];
+  const int R = G >= 4 ? 4 : (G >= 2 ? 2 : 1);  // hg_rows(): query heads per CTA of the CUDA-core kernel
+  p.n_heads = H; p.n_kv_heads = Hkv; p.group = G; p.n_hg = EMU_SIMT ? (G + R - 1) / R : 1; p.n_rb = (int)plan[5];
   int shift = 0;
   while ((1 << shift) < bs) ++shift;
   p.block_shift = shift; p.block_mask = bs - 1;
   p.box_rows = bs < ATT_TILE ? bs : ATT_TILE; p.boxes_per_tile = ATT_TILE / p.box_rows;
   p.max_q_len = max_q; p.window = -1; p.use_cap = 0;
   p.scale_log2 = 1.4426950408889634f / std::sqrt((float)D);
-  p.n_splits = n_splits; p.tiles_per_split = tpw; p.ntm = ntm; p.tpw = tpw; p.stream = 1;
+  p.n_splits = n_splits; p.tiles_per_split = tpw; p.ntm = ntm; p.tpw = tpw; p.stream = EMU_SIMT ? 0 : 1;
   P.kmap = CUtensorMap{P.kc.data(), P.n_slots, Hkv, D, p.box_rows};
   P.vmap = CUtensorMap{P.vc.data(), P.n_slots, Hkv, D, p.box_rows};
   g_pr = &P;
 
+#if EMU_SIMT
+  unsigned grid = 0;
+  for (unsigned bz = 0; bz < (unsigned)(B * max_q) && !g_failed; ++bz)
+    for (unsigned by = 0; by < (unsigned)(Hkv * p.n_hg); ++by)
+      for (unsigned bx = 0; bx < (unsigned)n_splits; ++bx, ++grid) {
+        g_bar_base = nullptr;
+        for (auto& b : g_eb) b = EmuBar{};
+        for (auto& w : g_warps) pthread_barrier_init(&w.bar, nullptr, LANES);
+        pthread_barrier_init(&g_cta_bar, nullptr, 4 * LANES);
+        pthread_t th[4 * LANES];
+        struct SArg { int tid; unsigned bx, by, bz; int R; };
+        static SArg sargs[4 * LANES];
+        for (int i = 0; i < 4 * LANES; ++i) {
+          sargs[i] = SArg{i, bx, by, bz, R};
+          pthread_create(&th[i], nullptr, [](void* a) -> void* {
+            SArg* x = (SArg*)a;
+            t_lane = x->tid & 31;
+            t_warp = &g_warps[x->tid >> 5];
+            threadIdx.x = (unsigned)x->tid;
+            blockIdx.x = x->bx; blockIdx.y = x->by; blockIdx.z = x->bz;
+            Problem& Q = *g_pr;
+            if (x->R == 4) paged_attn_decode_kernel<bf16_t, EMU_D, 4>(Q.kmap, Q.vmap, Q.p);
+            else if (x->R == 2) paged_attn_decode_kernel<bf16_t, EMU_D, 2>(Q.kmap, Q.vmap, Q.p);
+            else paged_attn_decode_kernel<bf16_t, EMU_D, 1>(Q.kmap, Q.vmap, Q.p);
+            return nullptr;
+          }, &sargs[i]);
+        }
+        for (int i = 0; i < 4 * LANES; ++i) pthread_join(th[i], nullptr);
+        for (auto& w : g_warps) pthread_barrier_destroy(&w.bar);
+        pthread_barrier_destroy(&g_cta_bar);
+      }
+#else
   const unsigned grid = (unsigned)((P.total_tiles + tpw - 1) / tpw);
   for (unsigned cta = 0; cta < grid && !g_failed; ++cta) {
     g_bar_base = nullptr;
     for (auto& b : g_eb) b = EmuBar{};
-    pthread_barrier_init(&g_bar, nullptr, LANES);
+    pthread_barrier_init(&g_warps[0].bar, nullptr, LANES);
     pthread_t th[LANES];
-    blockIdx.x = cta;  // (thread_local: set again in each lane below)
     struct Arg { int lane; unsigned cta; };
     static Arg args[LANES];
     for (int i = 0; i < LANES; ++i) {
@@ -394,12 +464,14 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
       pthread_create(&th[i], nullptr, [](void* a) -> void* {
         Arg* x = (Arg*)a;
         blockIdx.x = x->cta;
+        t_warp = &g_warps[0];
         return lane_main((void*)(intptr_t)x->lane);
       }, &args[i]);
     }
     for (int i = 0; i < LANES; ++i) pthread_join(th[i], nullptr);
-    pthread_barrier_destroy(&g_bar);
+    pthread_barrier_destroy(&g_warps[0].bar);
   }
+#endif
   if (g_failed) return 1;
 
   // second pass, as launch_attn does it: grid ((n_heads + 3) / 4, batch * max_q_len), 4 warps per
@@ -408,7 +480,7 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
     for (unsigned by = 0; by < (unsigned)(B * max_q) && !g_failed; ++by)
       for (unsigned bx = 0; bx < (unsigned)((H + 3) / 4); ++bx)
         for (int w = 0; w < 4; ++w) {
-          pthread_barrier_init(&g_bar, nullptr, LANES);
+          pthread_barrier_init(&g_warps[0].bar, nullptr, LANES);
           pthread_t th[LANES];
           struct CArg { int lane, warp; unsigned bx, by; };
           static CArg cargs[LANES];
@@ -417,6 +489,7 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
             pthread_create(&th[i], nullptr, [](void* a) -> void* {
               CArg* x = (CArg*)a;
               t_lane = x->lane;
+              t_warp = &g_warps[0];
               threadIdx.x = (unsigned)(x->warp * 32 + x->lane);
               blockIdx.x = x->bx;
               blockIdx.y = x->by;
@@ -425,7 +498,7 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
             }, &cargs[i]);
           }
           for (int i = 0; i < LANES; ++i) pthread_join(th[i], nullptr);
-          pthread_barrier_destroy(&g_bar);
+          pthread_barrier_destroy(&g_warps[0].bar);
         }
   }
 
@@ -489,6 +562,7 @@ int main() {
   bad += run(3, 8, 2, 8, 1, {1, 1, 1}, {127, 300, 40}, 1);         // GQA 4, decode, ragged lengths
   bad += run(2, 4, 4, 16, 1, {1, 1}, {33, 257}, 2);                 // MHA, block 16
   bad += run(2, 8, 1, 1, 1, {1, 1}, {70, 19}, 3);                   // MQA 8 rows, block size 1
+  if (EMU_SIMT) bad += run(2, 6, 3, 8, 2, {2, 1}, {100, 37}, 6);   // group 2 (two query heads per CTA)
   if (!EMU_TR) bad += run(2, 8, 2, 8, 3, {3, 2}, {100, 37}, 4);     // multi-token queries (12 rows: not a TR shape)
   else bad += run(2, 8, 2, 8, 2, {2, 1}, {100, 37}, 4);             // 8 packed rows, causal diagonal inside
   bad += run(1, 8, 2, 8, 1, {1}, {1500}, 5);                        // long: many pieces over many warps
