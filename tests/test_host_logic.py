@@ -344,4 +344,4 @@ def test_attention_stream_kernel_runs_on_the_host_in_every_instantiation():
     import sys
     tool = os.path.join(os.path.dirname(__file__), "..", "tools", "attn_emu.py")
     r = subprocess.run([sys.executable, tool, "quick"], capture_output=True, text=True, timeout=2400)
-    assert r.returncode == 0 and r.stdout.count("\nok") == 7, r.stdout + r.stderr
+    assert r.returncode == 0 and r.stdout.count("\nok") == 6, r.stdout + r.stderr
