@@ -393,6 +393,10 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       mbar_init(&tmem_full[i], (VAR & 16) ? 2 : 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    if constexpr (VAR & 16) {  // tiles issued so far by each of the two MMA issuers
+      reinterpret_cast<volatile int*>(tmem_holder + 2)[0] = 0;
+      reinterpret_cast<volatile int*>(tmem_holder + 2)[1] = 0;
+    }
     // [w4-emu:init end]
     fence_mbar_init();
   }
@@ -437,6 +441,15 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         const uint32_t raw = raw_u32 + rs * Cfg::RAW_BYTES;
         const uint32_t a_tmem = a_lane + as * 64;
         long long tw = TRACE ? clock64() : 0;
+        if constexpr (VAR & 16) {
+          // Two issuers: wait for the TMEM slot BEFORE touching the weight blob.  The raw_full wait
+          // below goes by the parity of the ring entry's use count, which is only sound if the
+          // entry's previous blob (tile cnt - 11) has landed.  With one in-order issuer the slot
+          // wait of this group's previous tile guarantees that (tile cnt - 10 consumed => cnt - 11
+          // issued); with two issuers bounded to a drift of 3 tiles it takes this tile's own slot
+          // (tile cnt - 6 consumed => the other issuer is past cnt - 9).
+          mbar_wait(&deq_empty[as], aph ^ 1);
+        }
         mbar_wait(&raw_full[rs], rph);
         if (TRACE) w_raw += clock64() - tw;
         if (TRACE && threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
@@ -552,6 +565,14 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     // tile in this segment: its arrival below must not count towards the previous segment), then
     // each arrives once on tmem_full: through a commit behind its last MMAs, or directly if it
     // had no tile.
+    // The issuers may not drift apart: a dequant group waits for its weight blob by the parity of
+    // the ring entry's use count, which is only sound while nobody gets a whole ring (11 tiles)
+    // ahead of a blob that has not landed.  One in-order issuer bounds that lead by the 6 TMEM
+    // slots; two independent ones do not (the odd tiles could run on while an even tile's blob
+    // is late — found by the host emulation, tools/w4_emu.py).  So an issuer takes tile cnt only
+    // once the other one has issued tile cnt - 3, and the dequant groups wait for their TMEM slot
+    // before they read the blob (see there): lead <= 6 + 3 < 11.
+    volatile int* issued = reinterpret_cast<volatile int*>(tmem_holder + 2);  // [2]: tiles issued + 1
     constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
@@ -565,6 +586,8 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       uint32_t started = 0;  // 0: my next MMA overwrites my accumulator
       for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
         if ((cnt & 1) != me) continue;
+        while (issued[1 - me] < cnt - 2) {  // the other issuer is more than 3 tiles behind
+        }
         const int ds = cnt % Cfg::A_STAGES;  // == activation stage (one weight tile per unit)
         const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
         if constexpr (!(VAR & 8)) mbar_wait(&act_full[ds], dph);
@@ -581,6 +604,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           }
           umma_commit(&deq_empty[ds]);
           umma_commit(&act_empty[ds]);
+          issued[me] = cnt + 1;
         }
         __syncwarp();
         started = 1u;

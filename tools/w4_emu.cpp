@@ -89,6 +89,8 @@ static uint64_t* const deq_full = act_empty + Cfg::ACT_STAGES;
 static uint64_t* const deq_empty = deq_full + Cfg::A_STAGES;
 static uint64_t* const tmem_full = deq_empty + Cfg::A_STAGES;
 static uint64_t* const tmem_empty = tmem_full + 2;
+static uint32_t g_holder[16];  // the kernel's tmem_holder word and what follows it in shared memory
+static uint32_t* const tmem_holder = g_holder;
 
 struct EmuBar {
   int count = 0, pending = 0, phase = 0;
@@ -306,7 +308,18 @@ static void pipe_execute(const PipeOp& op) {  // g_mu held
   long tile = g_slot_content[op.slot][0][0];
   for (int q = 0; q < 4; ++q)
     for (int h = 0; h < 2; ++h)
-      if (g_slot_content[op.slot][q][h] != tile) fail("TMEM slot holds pieces of different tiles", op.slot);
+      if (g_slot_content[op.slot][q][h] != tile) {
+        if (!g_failed.load()) {
+          std::fprintf(stderr, "  slot %d contents:", op.slot);
+          for (int qq = 0; qq < 4; ++qq) std::fprintf(stderr, " [%ld %ld]", g_slot_content[op.slot][qq][0], g_slot_content[op.slot][qq][1]);
+          std::fprintf(stderr, "  act stage %d: %ld %ld  ks %d buf %d acc %d\n", op.stage, g_act_content[op.stage][0],
+                       g_act_content[op.stage][1], op.ks, op.buf, op.accumulate);
+          const int df = bar_index(deq_full) + op.slot, de = bar_index(deq_empty) + op.slot;
+          std::fprintf(stderr, "  deq_full: phase %d pending %d tx %ld   deq_empty: phase %d pending %d\n", g_eb[df].phase,
+                       g_eb[df].pending, g_eb[df].tx, g_eb[de].phase, g_eb[de].pending);
+        }
+        fail("TMEM slot holds pieces of different tiles", op.slot);
+      }
   const long kt = g_act_content[op.stage][0];
   if (g_act_content[op.stage][1] != kt) fail("activation stage halves hold different k tiles", op.stage);
   if (tile < 0 || kt < 0 || tile % g_KT != kt) fail("MMA pairs a weight tile with another k tile's activations", tile, kt);
