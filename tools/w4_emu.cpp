@@ -363,12 +363,26 @@ static void role_main(int warp_id) {
 static std::atomic<bool> g_stop{false};
 static void hardware_main(uint32_t seed) {  // copies complete in any order, the pipe executes in order
   std::mt19937 rng(seed);
+  long held_tile = -1;
+  int held_for = 0;
   while (!g_stop.load()) {
     {
       std::lock_guard<std::mutex> lk(g_mu);
       const int what = (int)(rng() % 3);
+      // adversarial memory system: now and then one copy is held back for a long while (a late
+      // blob) while everything else makes progress — the ring rules must hold regardless
+      if (held_for == 0 && !g_copies.empty() && rng() % 64 == 0) {
+        held_tile = g_copies[rng() % g_copies.size()].tile;
+        held_for = 400 + (int)(rng() % 3000);
+      }
+      if (held_for > 0) --held_for;
       if (what == 0 && !g_copies.empty()) {
-        const size_t i = rng() % g_copies.size();
+        size_t i = rng() % g_copies.size();
+        if (held_for > 0 && g_copies[i].kind == 0 && g_copies[i].tile == held_tile) {
+          if (g_copies.size() == 1) continue;       // only the held copy is in flight: let time pass
+          i = (i + 1) % g_copies.size();
+          if (g_copies[i].kind == 0 && g_copies[i].tile == held_tile) continue;
+        }
         const Copy c = g_copies[i];
         g_copies.erase(g_copies.begin() + (long)i);
         if (c.kind == 0) g_raw_content[c.stage] = c.tile;
