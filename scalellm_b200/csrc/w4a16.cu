@@ -345,6 +345,10 @@ template <int MT, int NSUB, bool TRACE, int VAR = 0>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
+  // A dequant group waits for its weight blob by the parity of the ring entry's use count.  That
+  // is sound only while no group can get a whole ring ahead of a blob that has not landed; the
+  // TMEM slot ring bounds a group's lead over the in-order MMA issuer to (groups + slots) tiles.
+  static_assert(Cfg::RAW_STAGES > W4_DEQ_GROUPS + Cfg::A_STAGES, "weight ring too shallow for the slot ring");
   static_assert((VAR & 3) != 3 && VAR < 32 && (!(VAR & 16) || !(VAR & 3)),
                 "VAR: 1 and 2 are alternatives, and neither combines with 16");
   static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
