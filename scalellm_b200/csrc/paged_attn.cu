@@ -988,7 +988,9 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
       const int row = row0 + (ok ? r : 0), qi = row / G;
       row_head[h] = cur.kvh * G + (row - qi * G);
       const int qp = q_pos0 + qi;
-      row_end[h] = ok ? qp + 1 : 0;
+      // (TR: a padding row gets the first row's bounds instead of an empty range — its Q is zero and
+      // its column of O^T is never written — so that the interior-tile test below is warp-uniform)
+      row_end[h] = (ok || TR) ? qp + 1 : 0;
       row_begin[h] = p.window >= 0 ? max(0, qp - p.window) : 0;
     }
     float slope_log2[2];
@@ -1040,18 +1042,26 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
         // lane (g, t): keys {g, g + 8} x rows {2t, 2t + 1}; element 2 hh + h = (key g + 8 hh, row 2t + h)
         float corr[2], pk[2][2];
         bool need_rescale = false;
+        const bool plain = !p.use_cap && p.alibi == nullptr;  // no soft cap, no position bias
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float x[2];
           float mx = m[h];
+          // interior tile of this row (every key inside its causal / window range): the score is
+          // just the scaled dot product — the mask and bias arithmetic is skipped
+          const bool inside = plain && pos0 >= row_begin[h] && pos0 + ATT_TILE <= row_end[h];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            const int pos = pos0 + (lane >> 2) + 8 * hh;
             const float sc = sacc[0][2 * hh + h] + sacc[1][2 * hh + h];
-            float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
-            v = fmaf(slope_log2[h], (float)pos, v);
-            const bool ok = pos >= row_begin[h] && pos < row_end[h];
-            x[hh] = ok ? v : -INFINITY;
+            if (inside) {
+              x[hh] = sc * p.scale_log2;
+            } else {
+              const int pos = pos0 + (lane >> 2) + 8 * hh;
+              float v = p.use_cap ? tanhf(sc * p.cap_in) * p.cap_out_log2 : sc * p.scale_log2;
+              v = fmaf(slope_log2[h], (float)pos, v);
+              const bool ok = pos >= row_begin[h] && pos < row_end[h];
+              x[hh] = ok ? v : -INFINITY;
+            }
             mx = fmaxf(mx, x[hh]);
           }
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));   // over the 8 key groups g

@@ -340,7 +340,8 @@ static void* lane_main(void* arg) {
 }
 
 static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>& q_lens,
-               const std::vector<int>& kv_lens, uint32_t seed) {
+               const std::vector<int>& kv_lens, uint32_t seed, float soft_cap = 0.f, bool alibi = false,
+               int window = -1) {
   Problem P;
   P.B = B; P.H = H; P.Hkv = Hkv; P.D = EMU_D; P.bs = bs; P.max_q = max_q;
   P.q_lens = q_lens; P.kv_lens = kv_lens;
@@ -404,7 +405,7 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
   p.q = P.q.data(); p.out = P.out.data();
   p.q_cu_lens = P.q_cu.data(); p.kv_cu_lens = P.kv_cu.data();
   p.block_table = P.table.data(); p.block_cu_lens = P.blk_cu.data();
-  p.alibi = nullptr; p.ws_o = P.ws_o.data(); p.ws_lse = P.ws_lse.data();
+  p.ws_o = P.ws_o.data(); p.ws_lse = P.ws_lse.data();
   p.q_stride_t = (int64_t)H * D; p.q_stride_h = D; p.o_stride_t = (int64_t)H * D; p.o_stride_h = D;
   const int R = G >= 4 ? 4 : (G >= 2 ? 2 : 1);  // hg_rows(): query heads per CTA of the CUDA-core kernel
   p.n_heads = H; p.n_kv_heads = Hkv; p.group = G; p.n_hg = EMU_SIMT ? (G + R - 1) / R : 1; p.n_rb = (int)plan[5];
@@ -412,8 +413,21 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
   while ((1 << shift) < bs) ++shift;
   p.block_shift = shift; p.block_mask = bs - 1;
   p.box_rows = bs < ATT_TILE ? bs : ATT_TILE; p.boxes_per_tile = ATT_TILE / p.box_rows;
-  p.max_q_len = max_q; p.window = -1; p.use_cap = 0;
-  p.scale_log2 = 1.4426950408889634f / std::sqrt((float)D);
+  p.max_q_len = max_q; p.window = window;
+  static std::vector<float> slopes;
+  slopes.assign(H, 0.f);
+  for (int h = 0; h < H; ++h) slopes[h] = 0.02f * (float)(h + 1);
+  p.alibi = alibi ? slopes.data() : nullptr;
+  const float sm_scale = 1.0f / std::sqrt((float)D);
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (soft_cap > 0.f) {  // as b200_paged_attn_decode sets them
+    p.use_cap = 1;
+    p.cap_in = sm_scale / soft_cap;
+    p.cap_out_log2 = soft_cap * LOG2E;
+  } else {
+    p.use_cap = 0;
+    p.scale_log2 = sm_scale * LOG2E;
+  }
   p.n_splits = n_splits; p.tiles_per_split = tpw; p.ntm = ntm; p.tpw = tpw; p.stream = EMU_SIMT ? 0 : 1;
   P.kmap = CUtensorMap{P.kc.data(), P.n_slots, Hkv, D, p.box_rows};
   P.vmap = CUtensorMap{P.vc.data(), P.n_slots, Hkv, D, p.box_rows};
@@ -512,16 +526,20 @@ static int run(int B, int H, int Hkv, int bs, int max_q, const std::vector<int>&
         const int64_t tok = P.q_cu[b] + qi;
         std::vector<double> s(end);
         double mx = -1e300;
+        const int begin = window >= 0 ? std::max(0, end - 1 - window) : 0;
         for (int j = 0; j < end; ++j) {
           const int64_t slot = P.table[P.blk_cu[b] + j / bs] + j % bs;
           double a = 0;
           for (int d = 0; d < D; ++d)
             a += (double)bf2f(P.q[(tok * H + h) * D + d]) * bf2f(P.kc[(slot * Hkv + kvh) * D + d]);
-          s[j] = a / std::sqrt((double)D);
+          a /= std::sqrt((double)D);
+          if (soft_cap > 0.f) a = soft_cap * std::tanh(a / soft_cap);
+          if (alibi) a += (double)slopes[h] * j;
+          s[j] = j >= begin ? a : -1e300;
           mx = std::max(mx, s[j]);
         }
         double sum = 0;
-        for (int j = 0; j < end; ++j) sum += (s[j] = std::exp(s[j] - mx));
+        for (int j = 0; j < end; ++j) sum += (s[j] = j >= begin ? std::exp(s[j] - mx) : 0.0);
         const int64_t wrow = ((int64_t)b * max_q + qi) * H + h;
         double M = -INFINITY;
         for (int sp = 0; sp < n_splits; ++sp) M = std::max(M, (double)P.ws_lse[wrow * n_splits + sp]);
@@ -566,6 +584,8 @@ int main() {
   if (!EMU_TR) bad += run(2, 8, 2, 8, 3, {3, 2}, {100, 37}, 4);     // multi-token queries (12 rows: not a TR shape)
   else bad += run(2, 8, 2, 8, 2, {2, 1}, {100, 37}, 4);             // 8 packed rows, causal diagonal inside
   bad += run(1, 8, 2, 8, 1, {1}, {1500}, 5);                        // long: many pieces over many warps
+  bad += run(2, 8, 2, 8, 1, {1, 1}, {200, 90}, 7, 30.f, true, 40);  // soft cap + alibi + sliding window
+  bad += run(2, 4, 4, 16, 1, {1, 1}, {130, 64}, 8, 0.f, false, 0);  // window 0: only the token itself
   std::printf(bad || g_failed ? "FAILED\n" : "ok\n");
   return bad || g_failed ? 1 : 0;
 }

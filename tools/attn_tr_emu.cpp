@@ -146,6 +146,7 @@ static void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32
 struct Params {
   const void* q;
   void* out;
+  const float* alibi;
   float* ws_o;
   float* ws_lse;
   int64_t q_stride_t, q_stride_h, o_stride_t, o_stride_h;
@@ -192,7 +193,7 @@ static void* lane_main(void* arg) {
     const int r = EMU_TR ? (lane & 3) * 2 + h : (lane >> 2) + 8 * h;
     const bool ok = r < n_rows;
     const int row = row0 + (ok ? r : 0), qi = row / G;
-    row_end[h] = ok ? q_pos0 + qi + 1 : 0;
+    row_end[h] = (ok || EMU_TR) ? q_pos0 + qi + 1 : 0;
     row_begin[h] = 0;
   }
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
@@ -252,7 +253,7 @@ static int run(int G, int q_len, int kv_len, int n_splits, uint32_t seed) {
   }
   c.ws_o.assign((size_t)q_len * H * n_splits * D, -55.f);
   c.ws_lse.assign((size_t)q_len * H * n_splits, -55.f);
-  c.p = Params{c.q.data(), c.out.data(), c.ws_o.data(), c.ws_lse.data(), (int64_t)H * D, D, (int64_t)H * D, D,
+  c.p = Params{c.q.data(), c.out.data(), nullptr, c.ws_o.data(), c.ws_lse.data(), (int64_t)H * D, D, (int64_t)H * D, D,
                H, n_splits, q_len, 0, 1.4426950408889634f / std::sqrt((float)D), 0.f, 0.f};
   g_case = &c;
   pthread_barrier_init(&g_bar, nullptr, LANES);
