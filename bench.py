@@ -321,7 +321,7 @@ def run_b200(a, rank, world, local_rank):
     # ---- launches per step (claimed gpu_launches) --------------------------------
     tokens, positions, params = bufs.upload(hb)
     kernels.launch_count_reset()
-    _ = model(tokens, positions, params)
+    _ = model(tokens, positions, params, greedy=True)
     torch.cuda.synchronize()
     launches_per_step = kernels.launch_count()
 
@@ -338,7 +338,7 @@ def run_b200(a, rank, world, local_rank):
     def one_step():
         if use_graph:
             return step.replay()
-        return kernels.argmax(model(tokens, positions, params))
+        return model(tokens, positions, params, greedy=True)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
@@ -481,9 +481,9 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
             tokens, positions, params = bufs.upload(hb)
             last = ci == len(sched) - 1
             sel = torch.tensor([q_len - 1], device=dev) if last else torch.zeros(0, dtype=torch.int64, device=dev)
-            logits = model(tokens, positions, params, last_token_idxes=sel)
+            ids = model(tokens, positions, params, last_token_idxes=sel, greedy=True)
             if last:
-                out_host.copy_(kernels.argmax(logits), non_blocking=True)
+                out_host.copy_(ids, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         if i > 0:
             times.append((time.perf_counter() - t0) * 1e3)

@@ -304,7 +304,8 @@ B200_API int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t
 /* ------------------------------------------------------------------------ *
  * A9  Tensor-parallel all-reduce over NVLink peer memory
  *     replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
- *     for the <= 1 MiB row-parallel reductions of the decode step.
+ *     for the <= 1 MiB row-parallel reductions of the decode step (two-shot row-partitioned
+ *     push protocol above two ranks, one-shot pull at two; csrc/allreduce.cu).
  *
  *     One communicator per GPU.  One process per GPU: every rank calls
  *     b200_ar_create (allocates its symmetric buffer + flags and returns an IPC
@@ -347,11 +348,22 @@ B200_API int b200_ar_allreduce_splitk(b200_ar_comm* comm, void* out, const float
                                       int dtype, b200_stream_t stream);
 /* ... and with the consumer fused as well: residual += T(all-reduced row); out = rms_norm(residual)
  * * weight, one launch for the row-parallel GEMM's reduction, the TP all-reduce, the residual add
- * and the RMSNorm (models/meta/llama.h:170-177 under tensor parallelism).  rows <= 64, n <= 4096. */
+ * and the RMSNorm (models/meta/llama.h:170-177 under tensor parallelism).  Two-shot form (default
+ * above two ranks): rows <= 128, n <= 8192; one-shot form: rows <= 64, n <= 4096. */
 B200_API int b200_ar_allreduce_splitk_norm(b200_ar_comm* comm, void* out, void* residual,
                                            const float* partials, int splits, int64_t gemm_k,
                                            const void* weight, int64_t rows, int64_t n, float eps,
                                            int dtype, b200_stream_t stream);
+/* Greedy sampling over a column-parallel (vocabulary-sharded) lm_head without gathering the
+ * logits: out[r] = argmax over all ranks' columns of row r, exactly what
+ * torch.argmax(gather_from_model_parallel_region(logits), -1) gives (lm_head gather_output=true,
+ * src/models/meta/llama.h:259-265 -> model_parallel.cpp:13-31, then the greedy sampler): first
+ * index of the maximum, NaN counts as the maximum.  logits: this rank's [rows, n_local] shard
+ * (row stride `stride` elements), global column = rank * n_local + local column.  One launch: an
+ * 8-byte candidate per rank and row crosses NVLink.  rows <= 128.  Shares the communicator's
+ * epoch with the other collectives. */
+B200_API int b200_ar_argmax(b200_ar_comm* comm, int64_t* out, const void* logits, int64_t rows,
+                            int64_t n_local, int64_t stride, int dtype, b200_stream_t stream);
 B200_API int b200_ar_destroy(b200_ar_comm* comm);
 
 #ifdef __cplusplus

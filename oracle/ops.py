@@ -22,11 +22,42 @@ def _r(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # RMSNorm — src/kernels/layernorm_kernels.cu:15-41 (kernel rounding) and
 # src/layers/normalization.h:17-52 (torch formula)
 # ----------------------------------------------------------------------------
+def _sumsq_kernel_order(xf: torch.Tensor) -> torch.Tensor:
+    """Row-wise sum of squares in the reference KERNEL's order, fp32 (layernorm_kernels.cu:30-35 +
+    reduce_kernel_utils.cuh:15-64): a block of BD = min(n, 1024) threads; thread t accumulates
+    x[t], x[t+BD], ... with one fused multiply-add each (`variance += x * x` compiles to FFMA),
+    every warp of 32 consecutive threads reduces by an xor butterfly (16, 8, 4, 2, 1), and a last
+    butterfly runs over the <= 32 warp sums.  Returns [rows, 1] float32."""
+    import numpy as np
+    x = xf.detach().to(torch.float32).reshape(-1, xf.shape[-1]).numpy()
+    rows, n = x.shape
+    BD = min(n, 1024)
+    nvw = (BD + 31) // 32
+    v = np.zeros((rows, nvw * 32), dtype=np.float32)
+    for k in range((n + BD - 1) // BD):
+        seg = x[:, k * BD: min(n, (k + 1) * BD)].astype(np.longdouble)
+        w = seg.shape[1]
+        # fma: exact product (48 bits fit in the 64-bit significand), one rounding to fp32
+        v[:, :w] = (seg * seg + v[:, :w].astype(np.longdouble)).astype(np.float32)
+
+    def butterfly(a):                      # a: [..., 32] float32 -> every lane holds the total
+        lane = np.arange(32)
+        for m in (16, 8, 4, 2, 1):
+            a = (a + a[..., lane ^ m]).astype(np.float32)
+        return a
+
+    warp = butterfly(v.reshape(rows, nvw, 32))[..., 0]           # lane 0 parks the warp's sum
+    red = np.zeros((rows, 32), dtype=np.float32)
+    red[:, :nvw] = warp
+    tot = butterfly(red)[:, 0]
+    return torch.from_numpy(tot.astype(np.float32)).reshape(*xf.shape[:-1], 1)
+
+
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     dt = x.dtype
     xf = x.to(torch.float32)
-    var = (xf * xf).sum(dim=-1, keepdim=True) / x.shape[-1]
-    rstd = torch.rsqrt(var + eps)
+    var = _sumsq_kernel_order(xf) / x.shape[-1]
+    rstd = torch.rsqrt(var + eps)              # the GPU's MUFU.RSQ may differ by an ulp from this
     y = _r(xf * rstd, dt)                      # (T)(x * s_variance)   layernorm_kernels.cu:39
     return (y * weight.to(torch.float32)).to(dt)  # ... * weight[i] in T
 
@@ -38,7 +69,7 @@ def rms_norm_residual(x: torch.Tensor, residual: torch.Tensor, weight: torch.Ten
     dt = x.dtype
     s = residual.to(torch.float32) + x.to(torch.float32)
     new_res = s.to(dt)
-    var = (s * s).sum(dim=-1, keepdim=True) / x.shape[-1]
+    var = _sumsq_kernel_order(s) / x.shape[-1]
     rstd = torch.rsqrt(var + eps)
     y = _r(new_res.to(torch.float32) * rstd, dt)
     return (y * weight.to(torch.float32)).to(dt), new_res

@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_ar_allgather": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "b200_ar_allreduce_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_allreduce_splitk_norm": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _vp, _i64, _i64, _f32, _int, _vp]),
+    "b200_ar_argmax": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_destroy": (_int, [_vp]),
 }
 

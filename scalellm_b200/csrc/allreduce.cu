@@ -1,42 +1,57 @@
-// allreduce.cu — one-shot tensor-parallel all-reduce over NVLink peer memory.
+// allreduce.cu — tensor-parallel collectives over NVLink peer memory.
 //
-// Replaces ProcessGroupNCCL::allreduce (src/model_parallel/process_group.cpp:135-153)
-// for the latency-bound <= 1 MiB row-parallel reductions of the decode step
-// (2 per layer: after o_proj and down_proj).
+// Replaces ProcessGroupNCCL::allreduce / allgather (src/model_parallel/process_group.cpp:135-202)
+// for the latency-bound <= 1 MiB collectives of the decode step (2 all-reduces per layer: after
+// o_proj and down_proj; the embedding / lm_head gathers).
 //
 // One process per GPU (b200_ar_create + b200_ar_open_peers, CUDA IPC), or all ranks in one
 // process with one thread per GPU like the reference's engine (b200_ar_create_all, the
 // counterpart of its ncclCommInitAll, process_group.cpp:98-118: peer access instead of IPC).
 // Each rank owns ONE cudaMalloc'ed symmetric region
-//   [ data buffer, parity 0 | data buffer, parity 1 | flags[world][AR_MAX_BLOCKS] | epoch | done ]
-// exported through CUDA IPC and mapped by every peer (NVSwitch gives every pair
-// full NVLink bandwidth).  A call with epoch e:
-//   1. every block copies its slice of the input into the local buffer (e & 1),
-//   2. publishes flag value e into every peer's flag array (st.release.sys),
-//   3. waits until all peers' flags for the same block index reach e,
-//   4. sums the slice over ranks in rank order 0..w-1 in fp32 (identical order on
-//      every rank => bit-identical results on all ranks) and writes it in place.
-// Double buffering by epoch parity plus the flag barrier of the next call makes
-// reuse safe: nobody can overwrite buffer (e & 1) before every peer finished
-// reading it in call e (they must have entered call e+1 first).  The epoch lives
-// in device memory and is advanced by the kernel, so a captured CUDA graph can
-// be replayed (no host-side state baked into kernel arguments).
+//   [ inbox p0 | inbox p1 | result p0 | result p1 | flags1[world][128] | flags2[128] |
+//     flagsA[world][128] | cand[2][world][128] | epoch | done ]
+// exported through CUDA IPC and mapped by every peer (NVSwitch gives every pair full NVLink
+// bandwidth).  Every collective of a communicator takes the next epoch e (kept in device memory
+// and advanced by the kernel, so a captured CUDA graph replays) and uses the buffers of parity
+// e & 1; flags carry epoch values, so nothing is ever reset.  Reuse is safe because a rank can be
+// in call e+2 only after every rank has left call e: finishing call e+1 needs a flag that some
+// owner publishes only after it has seen every rank's call-e+1 contribution.
+//
+// Two algorithms for the all-reduce (B200_AR_ALGO = oneshot | twoshot; default twoshot above two ranks):
+//   * ONE-SHOT (world 2): every block stages its slice in its own buffer, publishes a flag to every
+//     peer, waits for theirs and pulls all `world` copies (all loads in flight before the first add).
+//   * TWO-SHOT, row partitioned (the form that scales to 8 ranks): the message is cut into rows
+//     (one block per row; for the decoder's [tokens, hidden] messages a row is a token).  Row t is
+//     owned by rank t / ceil(rows / world).  Every rank PUSHES its contribution of row t into the
+//     owner's inbox (slot = source rank) and publishes flags1[src][t]; the owner sums the world
+//     slots in rank order in fp32 (bit-identical to the one-shot result and to a host sum in rank
+//     order), rounds once and pushes the reduced row into every rank's result buffer, then
+//     publishes flags2[t]; every rank then consumes row t from its own memory.  Per rank and call
+//     NVLink carries (world-1)/world of the message out and the same in, twice — 0.9 MB at 8
+//     ranks instead of the one-shot's 3.7 MB pull — and the critical path is two one-way NVLink
+//     hops, not `world` dependent round trips.
 //
 // Fused forms (the row-parallel GEMM -> all-reduce -> residual add -> RMSNorm chain of a TP
 // decoder layer, models/meta/llama.h:170-177):
-//   * b200_ar_allreduce_splitk: step 1 reads the producing W4A16 GEMM's fp32 stream-K partials
-//     and sums each tile's contributor slots (common.cuh W4Plan) instead of copying a bf16 input;
-//   * b200_ar_allreduce_splitk_norm: additionally, one block per row, step 4 feeds the reduced row
-//     straight into residual += x; out = rms_norm(residual) * w — one launch for the whole chain,
-//     bit-identical to the separate kernels (same rounding points).
+//   * b200_ar_allreduce_splitk: the contribution is read from the producing W4A16 GEMM's fp32
+//     stream-K partials, summing each tile's contributor slots (common.cuh W4Plan), instead of a
+//     bf16 input;
+//   * b200_ar_allreduce_splitk_norm: additionally the reduced row is consumed in place:
+//     residual += x; out = rms_norm(residual) * w — one launch for the whole chain, bit-identical
+//     to the separate kernels (same rounding points).
+// b200_ar_argmax: greedy sampling over a vocabulary-sharded lm_head without gathering logits:
+// local argmax per row, an 8-byte candidate per rank and row exchanged through `cand`, global
+// winner picked with torch.argmax's tie rule (lm_head gather + argmax: llama.h:259-265, sampler).
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace b200 {
 constexpr int AR_MAX_WORLD = 8;
-constexpr int AR_MAX_BLOCKS = 64;
+constexpr int AR_MAX_BLOCKS = 64;   // one-shot kernels: blocks (flag slots per source rank)
+constexpr int AR_MAX_ROWS = 128;    // two-shot kernels: rows (= blocks) per call
 constexpr int AR_THREADS = 512;
 }  // namespace b200
 
@@ -56,9 +71,20 @@ struct ArDevPtrs {
   uint8_t* base[AR_MAX_WORLD];
 };
 
-__host__ __device__ inline int64_t ar_flags_off(int64_t max_bytes) { return 2 * max_bytes; }
+// region layout (byte offsets)
+__host__ __device__ inline int64_t ar_result_off(int64_t max_bytes) { return 2 * max_bytes; }
+__host__ __device__ inline int64_t ar_flags_off(int64_t max_bytes) { return 4 * max_bytes; }  // flags1
+__host__ __device__ inline int64_t ar_flags2_off(int64_t max_bytes) {
+  return ar_flags_off(max_bytes) + (int64_t)AR_MAX_WORLD * AR_MAX_ROWS * 4;
+}
+__host__ __device__ inline int64_t ar_flagsA_off(int64_t max_bytes) {
+  return ar_flags2_off(max_bytes) + (int64_t)AR_MAX_ROWS * 4;
+}
+__host__ __device__ inline int64_t ar_cand_off(int64_t max_bytes) {
+  return ar_flagsA_off(max_bytes) + (int64_t)AR_MAX_WORLD * AR_MAX_ROWS * 4;
+}
 __host__ __device__ inline int64_t ar_epoch_off(int64_t max_bytes) {
-  return 2 * max_bytes + (int64_t)AR_MAX_WORLD * AR_MAX_BLOCKS * 4;
+  return ar_cand_off(max_bytes) + 2ll * AR_MAX_WORLD * AR_MAX_ROWS * 8;
 }
 __host__ __device__ inline int64_t ar_region_bytes(int64_t max_bytes) {
   return ar_epoch_off(max_bytes) + 256;
@@ -80,12 +106,46 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
                : "memory");
   return r;
 }
+__device__ __forceinline__ void ar_wait_flag(const uint32_t* p, uint32_t e) {
+  while ((int32_t)(ld_acquire_sys(p) - e) < 0) {
+  }
+}
+// last block out advances the epoch (device-side state: graph replay safe)
+__device__ __forceinline__ void ar_finish(uint32_t* epoch_ptr, uint32_t e) {
+  uint32_t* done_ptr = epoch_ptr + 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t d = atomicAdd(done_ptr, 1u);
+    if (d == gridDim.x - 1) {
+      *done_ptr = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = e;
+    }
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ void accum16(float (&acc)[16 / sizeof(T)], uint4 v) {
   const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
   for (int i = 0; i < (int)(16 / sizeof(T)); ++i) acc[i] += Num<T>::to_f(e[i]);
+}
+
+// acc = sum over ranks 0..world-1 (that order, fp32) of vector i of every rank's buffer at
+// `off`: all loads are issued before the first add, so the NVLink round trips overlap.
+template <typename T>
+__device__ __forceinline__ void ar_pull_sum(float (&acc)[16 / sizeof(T)], const ArDevPtrs& ptrs,
+                                            int64_t off, int64_t i, int world) {
+  uint4 v[AR_MAX_WORLD];
+#pragma unroll
+  for (int r = 0; r < AR_MAX_WORLD; ++r)
+    if (r < world) v[r] = ld_volatile_v4(reinterpret_cast<const uint4*>(ptrs.base[r] + off) + i);
+#pragma unroll
+  for (int k = 0; k < (int)(16 / sizeof(T)); ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int r = 0; r < AR_MAX_WORLD; ++r)
+    if (r < world) accum16<T>(acc, v[r]);
 }
 
 // partials != nullptr: the local input is the producing GEMM's stream-K partials [slots][count]
@@ -115,7 +175,6 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   constexpr int VEC = 16 / sizeof(T);
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
-  uint32_t* done_ptr = epoch_ptr + 1;
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
   const int64_t buf_off = (e & 1) ? max_bytes : 0;
 
@@ -160,12 +219,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   if constexpr (!NORM) {
     for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
       float acc[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-      for (int r = 0; r < world; ++r) {
-        const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
-        accum16<T>(acc, ld_volatile_v4(pb + i));
-      }
+      ar_pull_sum<T>(acc, ptrs, buf_off, i, world);
       uint4 o;
       T* oe = reinterpret_cast<T*>(&o);
 #pragma unroll
@@ -174,18 +228,13 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
     }
   } else {
     __shared__ float red[32];
+    extern __shared__ float sq[];        // [row_n] fp32: the row, for the reference-ordered sum of squares
     const int64_t i = v0 + threadIdx.x;  // one vector per thread: the block's slice is one row
     const bool have = i < v1;
     float x[VEC];
-    float ss = 0.f;
     if (have) {
       float acc[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-      for (int r = 0; r < world; ++r) {
-        const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
-        accum16<T>(acc, ld_volatile_v4(pb + i));
-      }
+      ar_pull_sum<T>(acc, ptrs, buf_off, i, world);
       uint4 rraw = reinterpret_cast<const uint4*>(na.residual)[i];
       const T* rr = reinterpret_cast<const T*>(&rraw);
       uint4 sraw;
@@ -194,13 +243,13 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
       for (int k = 0; k < VEC; ++k) {
         const float reduced = rnd<T>(acc[k]);  // what the plain all-reduce would have stored
         const float f = Num<T>::to_f(rr[k]) + reduced;
-        ss += f * f;
+        sq[threadIdx.x * VEC + k] = f;
         sv[k] = Num<T>::from_f(f);
         x[k] = Num<T>::to_f(sv[k]);
       }
       reinterpret_cast<uint4*>(na.residual)[i] = sraw;
     }
-    const float total = block_sum<AR_THREADS>(ss, red);
+    const float total = row_sumsq_ref_order<AR_THREADS>(sq, red, row_n);
     const float rstd = rsqrtf(total / row_n + na.eps);
     if (have) {
       const int col = (int)((i * VEC) % row_n);
@@ -217,17 +266,262 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
     }
   }
 
-  // advance the epoch once every block is done with it
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t d = atomicAdd(done_ptr, 1u);
-    if (d == gridDim.x - 1) {
-      *done_ptr = 0;
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = e;
+  ar_finish(epoch_ptr, e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-shot, row-partitioned all-reduce (file header).  One block per row; a row is `row_vecs`
+// 16-byte vectors (the last row of a plain message may be shorter), thread t holds vectors
+// t, t + 512, ... (VPT of them).  Sources of the contribution:
+//   FROM_PARTIALS: the producing GEMM's stream-K partials (sum of the tile's slots, rounded once);
+//   else:          data_in (T).
+// NORM: the reduced row feeds residual += x; out = rms_norm(residual) * weight (ArNormArgs);
+// else it is stored to data_out.  T = float only without partials / norm.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VPT, bool FROM_PARTIALS, bool NORM>
+__global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
+    ArDevPtrs ptrs, const T* __restrict__ data_in, T* __restrict__ data_out, int64_t nvec_total,
+    int row_vecs, int rank, int world, int64_t max_bytes, const float* __restrict__ partials,
+    W4Plan plan, int row_n, int64_t split_stride, ArNormArgs<T> na) {
+  constexpr int VEC = 16 / sizeof(T);
+  pdl_wait();               // the contribution (and the residual stream) come from earlier kernels
+  pdl_launch_dependents();  // the next GEMM may start prefetching its weights while we exchange
+  uint8_t* local = ptrs.base[rank];
+  uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
+  const int64_t par_off = (e & 1) ? max_bytes : 0;
+
+  const int row = blockIdx.x, rows = gridDim.x;
+  const int R = (rows + world - 1) / world;  // rows per owner
+  const int owner = row / R, lrow = row - owner * R;
+  const int64_t row_v0 = (int64_t)row * row_vecs;
+  const int64_t left = nvec_total - row_v0;
+  const int row_len = left < row_vecs ? (int)left : row_vecs;
+
+  // ---- 1. push my contribution of this row into the owner's inbox, slot = my rank ----
+  {
+    uint4* inbox = reinterpret_cast<uint4*>(ptrs.base[owner] + par_off) +
+                   ((int64_t)rank * R + lrow) * row_vecs;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) {
+        uint4 c;
+        if constexpr (FROM_PARTIALS) {
+          float a[8];
+          const int col = j * 8;  // 8 consecutive columns of this row, inside one n tile
+          w4_sum_partials8(a, partials + (row_v0 + j) * 8, split_stride, w4_contrib_col(plan, col));
+          T* ce = reinterpret_cast<T*>(&c);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ce[q] = Num<T>::from_f(a[q]);
+        } else {
+          c = reinterpret_cast<const uint4*>(data_in)[row_v0 + j];
+        }
+        inbox[j] = c;
+      }
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* f1 = reinterpret_cast<uint32_t*>(ptrs.base[owner] + ar_flags_off(max_bytes));
+    st_release_sys(&f1[rank * AR_MAX_ROWS + row], e);
+  }
+
+  // ---- 2. the owner reduces the world slots in rank order and pushes the row to everyone ----
+  uint4 red[VPT];
+  const bool is_owner = owner == rank;
+  if (is_owner) {
+    if (threadIdx.x < world) {
+      const uint32_t* f1 = reinterpret_cast<const uint32_t*>(local + ar_flags_off(max_bytes));
+      ar_wait_flag(&f1[threadIdx.x * AR_MAX_ROWS + row], e);
+    }
+    __syncthreads();
+    const uint4* inbox = reinterpret_cast<const uint4*>(local + par_off);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) {
+        uint4 v[AR_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < AR_MAX_WORLD; ++r)
+          if (r < world) v[r] = ld_volatile_v4(inbox + ((int64_t)r * R + lrow) * row_vecs + j);
+        float acc[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < AR_MAX_WORLD; ++r)
+          if (r < world) accum16<T>(acc, v[r]);
+        T* oe = reinterpret_cast<T*>(&red[k]);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) oe[q] = Num<T>::from_f(acc[q]);
+#pragma unroll
+        for (int r = 0; r < AR_MAX_WORLD; ++r)
+          if (r < world && r != rank)
+            reinterpret_cast<uint4*>(ptrs.base[r] + ar_result_off(max_bytes) + par_off)[row_v0 + j] = red[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < world && (int)threadIdx.x != rank) {
+      uint32_t* f2 = reinterpret_cast<uint32_t*>(ptrs.base[threadIdx.x] + ar_flags2_off(max_bytes));
+      st_release_sys(&f2[row], e);
+    }
+  } else {
+    // ---- 3. everyone else picks the reduced row up from its own result buffer ----
+    if (threadIdx.x == 0) {
+      const uint32_t* f2 = reinterpret_cast<const uint32_t*>(local + ar_flags2_off(max_bytes));
+      ar_wait_flag(&f2[row], e);
+    }
+    __syncthreads();
+    const uint4* res = reinterpret_cast<const uint4*>(local + ar_result_off(max_bytes) + par_off);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) red[k] = ld_volatile_v4(res + row_v0 + j);
+    }
+  }
+
+  if constexpr (!NORM) {
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) reinterpret_cast<uint4*>(data_out)[row_v0 + j] = red[k];
+    }
+  } else {
+    __shared__ float redsm[32];
+    extern __shared__ float sq[];  // [row_n] fp32: the row, for the reference-ordered sum of squares
+    float x[VPT][VEC];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) {
+        const T* rv = reinterpret_cast<const T*>(&red[k]);  // what the plain all-reduce would store
+        uint4 rraw = reinterpret_cast<const uint4*>(na.residual)[row_v0 + j];
+        const T* rr = reinterpret_cast<const T*>(&rraw);
+        uint4 sraw;
+        T* sv = reinterpret_cast<T*>(&sraw);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          const float f = Num<T>::to_f(rr[q]) + Num<T>::to_f(rv[q]);
+          sq[j * VEC + q] = f;
+          sv[q] = Num<T>::from_f(f);
+          x[k][q] = Num<T>::to_f(sv[q]);
+        }
+        reinterpret_cast<uint4*>(na.residual)[row_v0 + j] = sraw;
+      }
+    }
+    const float total = row_sumsq_ref_order<AR_THREADS>(sq, redsm, row_n);
+    const float rstd = rsqrtf(total / row_n + na.eps);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = threadIdx.x + k * AR_THREADS;
+      if (j < row_len) {
+        uint4 wraw = *reinterpret_cast<const uint4*>(na.weight + j * VEC);
+        const T* w = reinterpret_cast<const T*>(&wraw);
+        uint4 oraw;
+        T* o = reinterpret_cast<T*>(&oraw);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          const float y = rnd<T>(x[k][q] * rstd);
+          o[q] = Num<T>::from_f(y * Num<T>::to_f(w[q]));
+        }
+        reinterpret_cast<uint4*>(na.out)[row_v0 + j] = oraw;
+      }
+    }
+  }
+  ar_finish(epoch_ptr, e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Greedy sampling over a vocabulary-sharded lm_head: out[row] = argmax over ALL ranks' columns of
+// logits[row, :], as torch.argmax(cat(all-gather(logits), -1)) would give (first index of the
+// maximum, NaN counts as the maximum) — without moving the logits.  One block per row: local
+// argmax of this rank's [n_local] shard, (value, global index) pushed to every rank's `cand`
+// table, flagsA[src][row] published, then the world candidates are compared locally.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ar_argmax_better(float a, int64_t ia, float b, int64_t ib) {
+  const bool an = a != a, bn = b != b;
+  if (an != bn) return an;
+  if (an) return ia < ib;
+  return a > b || (a == b && ia < ib);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AR_THREADS) argmax_sharded_kernel(
+    ArDevPtrs ptrs, int64_t* __restrict__ out, const T* __restrict__ x, int n, int64_t stride,
+    int rank, int world, int64_t max_bytes) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float sv[16];
+  __shared__ int si[16];
+  pdl_wait();
+  pdl_launch_dependents();
+  uint8_t* local = ptrs.base[rank];
+  uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
+  const int par = e & 1;
+  const int row = blockIdx.x;
+  const T* xr = x + (int64_t)row * stride;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  const bool vec = (stride % VEC == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int nv = vec ? n / VEC : 0;
+  for (int v = threadIdx.x; v < nv; v += AR_THREADS) {
+    const uint4 raw = ld_nc_v4(xr + v * VEC);
+    const T* el = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float f = Num<T>::to_f(el[i]);
+      if (ar_argmax_better(f, v * VEC + i, best, bi)) { best = f; bi = v * VEC + i; }
+    }
+  }
+  for (int j = nv * VEC + threadIdx.x; j < n; j += AR_THREADS) {
+    const float f = Num<T>::to_f(xr[j]);
+    if (ar_argmax_better(f, j, best, bi)) { best = f; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ar_argmax_better(ob, oi, best, bi)) { best = ob; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < AR_THREADS / 32 ? sv[lane] : -INFINITY;
+    bi = lane < AR_THREADS / 32 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ar_argmax_better(ob, oi, best, bi)) { best = ob; bi = oi; }
+    }
+    // every lane holds the local winner; lane r tells rank r, then collects rank r's candidate
+    const int gi = bi + rank * n;  // global column (shards are equal, rank-major: cat order)
+    const uint64_t mine = ((uint64_t)(uint32_t)gi << 32) | __float_as_uint(best);
+    float cv = -INFINITY;
+    int64_t ci = INT64_MAX;
+    if (lane < world) {
+      uint64_t* cand = reinterpret_cast<uint64_t*>(ptrs.base[lane] + ar_cand_off(max_bytes));
+      cand[((int64_t)par * AR_MAX_WORLD + rank) * AR_MAX_ROWS + row] = mine;
+      uint32_t* fa = reinterpret_cast<uint32_t*>(ptrs.base[lane] + ar_flagsA_off(max_bytes));
+      st_release_sys(&fa[rank * AR_MAX_ROWS + row], e);
+      const uint32_t* my_fa = reinterpret_cast<const uint32_t*>(local + ar_flagsA_off(max_bytes));
+      ar_wait_flag(&my_fa[lane * AR_MAX_ROWS + row], e);
+      const volatile uint64_t* my_cand =
+          reinterpret_cast<const volatile uint64_t*>(local + ar_cand_off(max_bytes));
+      const uint64_t c = my_cand[((int64_t)par * AR_MAX_WORLD + lane) * AR_MAX_ROWS + row];
+      cv = __uint_as_float((uint32_t)c);
+      ci = (int64_t)(uint32_t)(c >> 32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (ar_argmax_better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    if (lane == 0) out[row] = ci;
+  }
+  ar_finish(epoch_ptr, e);
 }
 
 // All-gather with the same staging / flag protocol (and the same epoch counter, so all-reduces and
@@ -243,7 +537,6 @@ __global__ void __launch_bounds__(AR_THREADS) allgather_oneshot_kernel(ArDevPtrs
                                                                       int64_t max_bytes) {
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
-  uint32_t* done_ptr = epoch_ptr + 1;
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
   const int64_t buf_off = (e & 1) ? max_bytes : 0;
   const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
@@ -265,26 +558,61 @@ __global__ void __launch_bounds__(AR_THREADS) allgather_oneshot_kernel(ArDevPtrs
   __syncthreads();
   for (int64_t i = v0 + threadIdx.x; i < v1; i += AR_THREADS) {
     const int64_t row = i / cols_v, c = i - row * cols_v;
-    for (int r = 0; r < world; ++r) {
-      const uint4* pb = reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off);
-      out[(row * world + r) * cols_v + c] = ld_volatile_v4(pb + i);
-    }
+    uint4 v[AR_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < AR_MAX_WORLD; ++r)
+      if (r < world) v[r] = ld_volatile_v4(reinterpret_cast<const uint4*>(ptrs.base[r] + buf_off) + i);
+#pragma unroll
+    for (int r = 0; r < AR_MAX_WORLD; ++r)
+      if (r < world) out[(row * world + r) * cols_v + c] = v[r];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t d = atomicAdd(done_ptr, 1u);
-    if (d == gridDim.x - 1) {
-      *done_ptr = 0;
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = e;
-    }
-  }
+  ar_finish(epoch_ptr, e);
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+// B200_AR_ALGO = oneshot | twoshot (read once); default: two-shot above two ranks
+static bool ar_use_twoshot(int world) {
+  static const int forced = [] {
+    const char* v = getenv("B200_AR_ALGO");
+    if (v && !strcmp(v, "oneshot")) return 1;
+    if (v && !strcmp(v, "twoshot")) return 2;
+    return 0;
+  }();
+  if (forced) return forced == 2;
+  return world > 2;
+}
+
+static ArDevPtrs ar_ptrs(const b200_ar_comm* c) {
+  ArDevPtrs ptrs{};
+  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
+  return ptrs;
+}
+
+// two-shot launch: `rows` rows of `row_vecs` 16-byte vectors (the last may be short: nvec total)
+template <typename T, bool FROM_PARTIALS, bool NORM>
+static int ar_launch_twoshot(b200_ar_comm* c, const T* in, T* out, int64_t nvec, int row_vecs,
+                             int rows, const float* partials, const W4Plan& plan, int row_n,
+                             int64_t split_stride, ArNormArgs<T> na, cudaStream_t st) {
+  const int R = (rows + c->world - 1) / c->world;
+  if ((int64_t)c->world * R * row_vecs * 16 > c->max_bytes || (int64_t)rows * row_vecs * 16 > c->max_bytes)
+    return set_error(B200_ERR_WORKSPACE, "ar_allreduce: %d rows of %d B exceed the %lld B symmetric buffer",
+                     rows, row_vecs * 16, (long long)c->max_bytes);
+  const ArDevPtrs ptrs = ar_ptrs(c);
+  const size_t sm = NORM ? (size_t)row_n * 4 : 0;  // the row in fp32 (<= 32 KB)
+  if (row_vecs <= AR_THREADS) {
+    B200_PDL_LAUNCH_L(1, "allreduce_twoshot", (allreduce_twoshot_kernel<T, 1, FROM_PARTIALS, NORM>),
+                      (unsigned)rows, AR_THREADS, sm, st, ptrs, in, out, nvec, row_vecs, c->rank, c->world,
+                      c->max_bytes, partials, plan, row_n, split_stride, na);
+  } else {
+    B200_PDL_LAUNCH_L(1, "allreduce_twoshot", (allreduce_twoshot_kernel<T, 2, FROM_PARTIALS, NORM>),
+                      (unsigned)rows, AR_THREADS, sm, st, ptrs, in, out, nvec, row_vecs, c->rank, c->world,
+                      c->max_bytes, partials, plan, row_n, split_stride, na);
+  }
+  return B200_OK;
+}
 
 extern "C" {
 
@@ -311,8 +639,7 @@ int b200_ar_allgather(b200_ar_comm* c, void* out, const void* in, int64_t rows, 
   int blocks = (int)((nvec + 2 * AR_THREADS - 1) / (2 * AR_THREADS));
   if (blocks < 1) blocks = 1;
   if (blocks > AR_MAX_BLOCKS) blocks = AR_MAX_BLOCKS;
-  ArDevPtrs ptrs{};
-  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
+  const ArDevPtrs ptrs = ar_ptrs(c);
   allgather_oneshot_kernel<<<blocks, AR_THREADS, 0, st>>>(
       ptrs, static_cast<const uint4*>(in), static_cast<uint4*>(out), nvec, row_bytes / 16, c->rank,
       c->world, c->max_bytes);
@@ -471,12 +798,32 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
     return set_error(B200_ERR_WORKSPACE, "ar_allreduce: %lld B exceeds the %lld B symmetric buffer",
                      (long long)bytes, (long long)c->max_bytes);
   const int64_t nvec = bytes / 16;
+  auto st = static_cast<cudaStream_t>(stream);
+  // two-shot: rows of the producing GEMM when there are partials, else 8 KiB (16 KiB) chunks
+  int row_vecs = partials ? (int)(row_n * es / 16) : AR_THREADS;
+  if (!partials && nvec > (int64_t)AR_THREADS * AR_MAX_ROWS) row_vecs = 2 * AR_THREADS;
+  const int64_t rows = (nvec + row_vecs - 1) / row_vecs;
+  if (ar_use_twoshot(c->world) && rows <= AR_MAX_ROWS && row_vecs <= 2 * AR_THREADS &&
+      (int64_t)(rows + c->world) * row_vecs * 16 <= c->max_bytes) {
+    switch (dtype) {
+      case B200_BF16: {
+        using T = __nv_bfloat16;
+        return partials ? ar_launch_twoshot<T, true, false>(c, nullptr, static_cast<T*>(data), nvec, row_vecs, (int)rows, partials, plan, (int)row_n, count, ArNormArgs<T>{}, st)
+                        : ar_launch_twoshot<T, false, false>(c, static_cast<const T*>(data), static_cast<T*>(data), nvec, row_vecs, (int)rows, nullptr, plan, 0, 0, ArNormArgs<T>{}, st);
+      }
+      case B200_FP16: {
+        using T = __half;
+        return partials ? ar_launch_twoshot<T, true, false>(c, nullptr, static_cast<T*>(data), nvec, row_vecs, (int)rows, partials, plan, (int)row_n, count, ArNormArgs<T>{}, st)
+                        : ar_launch_twoshot<T, false, false>(c, static_cast<const T*>(data), static_cast<T*>(data), nvec, row_vecs, (int)rows, nullptr, plan, 0, 0, ArNormArgs<T>{}, st);
+      }
+      default:
+        return ar_launch_twoshot<float, false, false>(c, static_cast<const float*>(data), static_cast<float*>(data), nvec, row_vecs, (int)rows, nullptr, plan, 0, 0, ArNormArgs<float>{}, st);
+    }
+  }
   int blocks = (int)((nvec + 2 * AR_THREADS - 1) / (2 * AR_THREADS));
   if (blocks < 1) blocks = 1;
   if (blocks > AR_MAX_BLOCKS) blocks = AR_MAX_BLOCKS;
-  ArDevPtrs ptrs{};
-  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
-  auto st = static_cast<cudaStream_t>(stream);
+  const ArDevPtrs ptrs = ar_ptrs(c);
   switch (dtype) {
     case B200_BF16:
       allreduce_oneshot_kernel<__nv_bfloat16, false><<<blocks, AR_THREADS, 0, st>>>(
@@ -504,10 +851,12 @@ int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, co
   B200_CHECK_ARG(c && out && residual && partials && weight, "ar_allreduce_splitk_norm: null pointer");
   B200_CHECK_ARG(c->world > 1 && c->opened, "ar_allreduce_splitk_norm: needs an opened communicator, world > 1");
   B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "ar_allreduce_splitk_norm: bf16 / fp16 only");
-  B200_CHECK_ARG(rows >= 1 && rows <= AR_MAX_BLOCKS && n > 0 && n % 128 == 0 && n / 8 <= AR_THREADS &&
+  const bool twoshot = ar_use_twoshot(c->world);
+  const int max_rows = twoshot ? AR_MAX_ROWS : AR_MAX_BLOCKS;
+  const int max_n = (twoshot ? 2 : 1) * AR_THREADS * 8;
+  B200_CHECK_ARG(rows >= 1 && rows <= max_rows && n > 0 && n % 128 == 0 && n <= max_n &&
                      gemm_k > 0 && gemm_k % 128 == 0,
-                 "ar_allreduce_splitk_norm: rows <= %d, n %% 128 == 0, n <= %d", AR_MAX_BLOCKS,
-                 AR_THREADS * 8);
+                 "ar_allreduce_splitk_norm: rows <= %d, n %% 128 == 0, n <= %d", max_rows, max_n);
   B200_CHECK_ARG(is_aligned(out, 16) && is_aligned(residual, 16) && is_aligned(weight, 16) &&
                      is_aligned(partials, 16),
                  "ar_allreduce_splitk_norm: 16-byte alignment required");
@@ -518,26 +867,69 @@ int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, co
   const W4Plan plan = w4_get_plan(n, gemm_k, rows);
   B200_CHECK_ARG(splits == plan.slots, "ar_allreduce_splitk_norm: expected %d partial slots, got %d",
                  plan.slots, splits);
-  ArDevPtrs ptrs{};
-  for (int r = 0; r < c->world; ++r) ptrs.base[r] = c->peer[r];
   auto st = static_cast<cudaStream_t>(stream);
   const int64_t nvec = count / 8;
+  if (twoshot) {
+    if (dtype == B200_BF16) {
+      using T = __nv_bfloat16;
+      ArNormArgs<T> na{static_cast<T*>(residual), static_cast<const T*>(weight), static_cast<T*>(out), eps};
+      return ar_launch_twoshot<T, true, true>(c, nullptr, nullptr, nvec, (int)(n / 8), (int)rows, partials,
+                                              plan, (int)n, count, na, st);
+    }
+    using T = __half;
+    ArNormArgs<T> na{static_cast<T*>(residual), static_cast<const T*>(weight), static_cast<T*>(out), eps};
+    return ar_launch_twoshot<T, true, true>(c, nullptr, nullptr, nvec, (int)(n / 8), (int)rows, partials,
+                                            plan, (int)n, count, na, st);
+  }
+  const ArDevPtrs ptrs = ar_ptrs(c);
   const int blocks = (int)rows;  // one block per row: slice = ceil(nvec / blocks) = n / 8 vectors
   if (dtype == B200_BF16) {
     ArNormArgs<__nv_bfloat16> na{static_cast<__nv_bfloat16*>(residual),
                                  static_cast<const __nv_bfloat16*>(weight),
                                  static_cast<__nv_bfloat16*>(out), eps};
-    allreduce_oneshot_kernel<__nv_bfloat16, true><<<blocks, AR_THREADS, 0, st>>>(
+    allreduce_oneshot_kernel<__nv_bfloat16, true><<<blocks, AR_THREADS, (size_t)n * 4, st>>>(
         ptrs, static_cast<__nv_bfloat16*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials,
         plan, (int)n, count, na);
   } else {
     ArNormArgs<__half> na{static_cast<__half*>(residual), static_cast<const __half*>(weight),
                           static_cast<__half*>(out), eps};
-    allreduce_oneshot_kernel<__half, true><<<blocks, AR_THREADS, 0, st>>>(
+    allreduce_oneshot_kernel<__half, true><<<blocks, AR_THREADS, (size_t)n * 4, st>>>(
         ptrs, static_cast<__half*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials, plan,
         (int)n, count, na);
   }
   B200_LAUNCH_OK("allreduce_oneshot_norm");
+  return B200_OK;
+}
+
+int b200_ar_argmax(b200_ar_comm* c, int64_t* out, const void* logits, int64_t rows, int64_t n_local,
+                   int64_t stride, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(c && out && logits, "ar_argmax: null pointer");
+  B200_CHECK_ARG(rows >= 0 && rows <= AR_MAX_ROWS && n_local > 0 && stride >= n_local &&
+                     n_local * (int64_t)c->world < (1ll << 31),
+                 "ar_argmax: rows <= %d, world * n_local < 2^31", AR_MAX_ROWS);
+  B200_CHECK_ARG(dtype >= 0 && dtype <= 2, "ar_argmax: bad dtype");
+  if (rows == 0) return B200_OK;
+  if (c->world == 1) return b200_argmax(out, logits, rows, n_local, stride, dtype, stream);
+  B200_CHECK_ARG(c->opened, "ar_argmax: peers not opened");
+  auto st = static_cast<cudaStream_t>(stream);
+  const ArDevPtrs ptrs = ar_ptrs(c);
+  switch (dtype) {
+    case B200_BF16:
+      B200_PDL_LAUNCH_L(1, "argmax_sharded", argmax_sharded_kernel<__nv_bfloat16>, (unsigned)rows, AR_THREADS, 0,
+                        st, ptrs, out, static_cast<const __nv_bfloat16*>(logits), (int)n_local, stride,
+                        c->rank, c->world, c->max_bytes);
+      break;
+    case B200_FP16:
+      B200_PDL_LAUNCH_L(1, "argmax_sharded", argmax_sharded_kernel<__half>, (unsigned)rows, AR_THREADS, 0, st,
+                        ptrs, out, static_cast<const __half*>(logits), (int)n_local, stride, c->rank,
+                        c->world, c->max_bytes);
+      break;
+    default:
+      B200_PDL_LAUNCH_L(1, "argmax_sharded", argmax_sharded_kernel<float>, (unsigned)rows, AR_THREADS, 0, st,
+                        ptrs, out, static_cast<const float*>(logits), (int)n_local, stride, c->rank,
+                        c->world, c->max_bytes);
+      break;
+  }
   return B200_OK;
 }
 

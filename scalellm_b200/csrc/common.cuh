@@ -163,6 +163,33 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;  // every thread holds the total
 }
 
+// Sum of squares of a row whose n fp32 values are staged in shared memory `sq`, in EXACTLY the
+// order of the reference's rms_norm kernels, so that the normalised row is bit-identical to theirs
+// for every dtype (src/kernels/layernorm_kernels.cu:30-35,137-145 + reduce_kernel_utils.cuh:15-64):
+// their block has BD = min(n, 1024) threads; thread t accumulates x[t], x[t+BD], ... with one FFMA
+// each (variance += x * x, contracted), every warp of 32 consecutive t does an xor-butterfly
+// (16, 8, 4, 2, 1), lane 0 parks the warp's sum, and one more butterfly over the <= 32 warp sums
+// (zeros for absent warps) gives the total.  Our CTA has THREADS threads whatever n is: real warp
+// w plays the reference's warps w, w + THREADS/32, ...  Every thread returns the total.
+// `red`: 32 floats of shared memory.  Contains the __syncthreads() that publish `sq`.
+template <int THREADS>
+__device__ __forceinline__ float row_sumsq_ref_order(const float* sq, float* red, int n) {
+  __syncthreads();
+  const int BD = n < 1024 ? n : 1024;
+  const int nvw = (BD + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int vw = warp; vw < nvw; vw += THREADS / 32) {
+    const int t = vw * 32 + lane;
+    float v = 0.f;
+    if (t < BD)
+      for (int i = t; i < n; i += BD) v = fmaf(sq[i], sq[i], v);
+    v = warp_sum(v);
+    if (lane == 0) red[vw] = v;
+  }
+  __syncthreads();
+  return warp_sum(lane < nvw ? red[lane] : 0.f);
+}
+
 // 128-bit streaming global access
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
                                                                float eps, int n) {
   constexpr int VEC = 16 / sizeof(T);
   __shared__ float red[32];
+  extern __shared__ float sq[];  // [n] fp32: the row, for the reference-ordered sum of squares
   pdl_wait();
   pdl_launch_dependents();
   const int64_t row = blockIdx.x;
@@ -38,7 +39,6 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
   T* out_row = out + row * n;
 
   float x[MAXV][VEC];
-  float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int v = threadIdx.x + j * THREADS;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
           // x = float(r) + float(in): variance uses the UNROUNDED fp32 sum, the
           // second pass re-reads the rounded residual (layernorm_kernels.cu:137-153)
           const float f = Num<T>::to_f(r[i]) + Num<T>::to_f(e[i]);
-          ss += f * f;
+          sq[v * VEC + i] = f;
           s[i] = Num<T>::from_f(f);
           x[j][i] = Num<T>::to_f(s[i]);
         }
@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(THREADS) rms_norm_vec_kernel(T* __restrict__ o
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           x[j][i] = Num<T>::to_f(e[i]);
-          ss += x[j][i] * x[j][i];
+          sq[v * VEC + i] = x[j][i];
         }
       }
     }
   }
-  const float total = block_sum<THREADS>(ss, red);
+  const float total = row_sumsq_ref_order<THREADS>(sq, red, n);
   const float rstd = rsqrtf(total / n + eps);
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -101,14 +101,19 @@ __global__ void __launch_bounds__(1024) rms_norm_scalar_kernel(T* __restrict__ o
   pdl_launch_dependents();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
+  // the reference's own loop shape: BD = min(n, 1024) threads stride the row, one FFMA per element
+  // (threads >= BD of our warp-rounded block idle), then its two butterflies (reduce_kernel_utils.cuh:41-64)
+  const int64_t BD = n < 1024 ? n : 1024;
   float ss = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    float f = Num<T>::to_f(in[row * n + i]);
-    if constexpr (RESIDUAL) {
-      f = Num<T>::to_f(residual[row * n + i]) + f;
-      residual[row * n + i] = Num<T>::from_f(f);
+  if ((int64_t)threadIdx.x < BD) {
+    for (int64_t i = threadIdx.x; i < n; i += BD) {
+      float f = Num<T>::to_f(in[row * n + i]);
+      if constexpr (RESIDUAL) {
+        f = Num<T>::to_f(residual[row * n + i]) + f;
+        residual[row * n + i] = Num<T>::from_f(f);
+      }
+      ss = fmaf(f, f, ss);
     }
-    ss += f * f;
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -135,16 +140,17 @@ static int launch_rms_norm(void* out, void* residual, const void* in, const void
   const T* i = static_cast<const T*>(in);
   const T* w = static_cast<const T*>(weight);
   dim3 grid(static_cast<unsigned>(rows));
+  const size_t sm = (size_t)n * 4;  // the row in fp32 (reference-ordered sum of squares)
   if (vec_ok && nvec <= 128) {
-    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 128, 1, RESIDUAL>), grid, 128, 0, st, o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 128, 1, RESIDUAL>), grid, 128, sm, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 256) {
-    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 256, 1, RESIDUAL>), grid, 256, 0, st, o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 256, 1, RESIDUAL>), grid, 256, sm, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 512) {
-    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 1, RESIDUAL>), grid, 512, 0, st, o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 1, RESIDUAL>), grid, 512, sm, st, o, r, i, w, eps, (int)n);
   } else if (vec_ok && nvec <= 1024) {
-    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 2, RESIDUAL>), grid, 512, 0, st, o, r, i, w, eps, (int)n);
-  } else if (vec_ok && nvec <= 4096) {
-    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 1024, 4, RESIDUAL>), grid, 1024, 0, st, o, r, i, w, eps, (int)n);
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 512, 2, RESIDUAL>), grid, 512, sm, st, o, r, i, w, eps, (int)n);
+  } else if (vec_ok && sm <= 48 * 1024) {   // larger rows: the strided kernel below (same order, no staging)
+    B200_PDL_LAUNCH("rms_norm", (rms_norm_vec_kernel<T, 1024, 4, RESIDUAL>), grid, 1024, sm, st, o, r, i, w, eps, (int)n);
   } else {
     const int threads = (int)((n < 1024 ? ((n + 31) / 32) * 32 : 1024));
     B200_PDL_LAUNCH("rms_norm", (rms_norm_scalar_kernel<T, RESIDUAL>), grid, threads, 0, st, o, r, i, w, eps, n);
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   constexpr int VEC = 16 / sizeof(T);
   static_assert(VEC == 8, "16-bit element types only");
   __shared__ float red[32];
+  extern __shared__ float sq[];  // [n] fp32: the row, for the reference-ordered sum of squares
   pdl_wait();
   pdl_launch_dependents();
   const int64_t row = blockIdx.x;
@@ -171,7 +178,6 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   T* out_row = out + row * n;
   const float* p_row = partials + row * n;
   float x[MAXV][VEC];
-  float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int v = threadIdx.x + j * THREADS;
@@ -186,14 +192,14 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
       for (int i = 0; i < VEC; ++i) {
         const float gemm_out = rnd<T>(a[i]);  // what the GEMM would have stored
         const float f = Num<T>::to_f(r[i]) + gemm_out;
-        ss += f * f;
+        sq[v * VEC + i] = f;
         sv[i] = Num<T>::from_f(f);
         x[j][i] = Num<T>::to_f(sv[i]);
       }
       st_v4(res_row + v * VEC, sraw);
     }
   }
-  const float total = block_sum<THREADS>(ss, red);
+  const float total = row_sumsq_ref_order<THREADS>(sq, red, n);
   const float rstd = rsqrtf(total / n + eps);
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -222,14 +228,19 @@ static int launch_rms_norm_splitk(void* out, void* residual, const float* partia
   const T* w = static_cast<const T*>(weight);
   const int64_t nvec = n / 8;
   dim3 grid(static_cast<unsigned>(rows));
+  const size_t sm = (size_t)n * 4;  // the row in fp32 (reference-ordered sum of squares)
+  if (sm > 48 * 1024) {             // n <= 32768 (checked by the caller): opt in to the larger carve-out
+    B200_CUDA_OK(cudaFuncSetAttribute(rms_norm_residual_splitk_kernel<T, 1024, 4>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  }
   if (nvec <= 256)
-    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 256, 1>), grid, 256, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 256, 1>), grid, 256, sm, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else if (nvec <= 512)
-    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 1>), grid, 512, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 1>), grid, 512, sm, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else if (nvec <= 1024)
-    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 2>), grid, 512, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 512, 2>), grid, 512, sm, st, o, r, partials, S, split_stride, w, eps, (int)n);
   else
-    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 1024, 4>), grid, 1024, 0, st, o, r, partials, S, split_stride, w, eps, (int)n);
+    B200_PDL_LAUNCH_L(1, "rms_norm_residual_splitk", (rms_norm_residual_splitk_kernel<T, 1024, 4>), grid, 1024, sm, st, o, r, partials, S, split_stride, w, eps, (int)n);
   return B200_OK;
 }
 

@@ -81,7 +81,10 @@ struct AttnCfg {
   static constexpr int CPL = (D + 63) / 64;    // 16-byte chunks per lane per row (the last one may
                                                // be partly outside the row: head_dim 32 / 96)
   static constexpr int EPL = CPL * 8;          // elements per lane per row
-  static constexpr int TILE_ELEMS = ATT_TILE * D;
+  // head_dim 32 / 96: a TMA box must land on a 128-byte boundary, so the boxes of a tile sit at a
+  // pitch rounded up to 64 elements (matters when a box is 1 row: block_size 1); the tile buffer
+  // is sized for the padded row like the reference's 64 / 128 tiles
+  static constexpr int TILE_ELEMS = ATT_TILE * ((D + 63) / 64 * 64);
 };
 // [attn-emu:params end]
 
@@ -98,7 +101,7 @@ constexpr size_t attn_mma_smem_bytes() {
 
 template <typename T, int D>
 constexpr size_t attn_smem_bytes() {
-  return (size_t)ATT_WARPS * AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T)  // K+V stages
+  return (size_t)ATT_WARPS * AttnCfg<D>::STAGES * 2 * AttnCfg<D>::TILE_ELEMS * sizeof(T)  // K+V stages
          + ATT_TBL * sizeof(int32_t) + ATT_WARPS * AttnCfg<D>::STAGES * sizeof(uint64_t) + 128;
 }
 
@@ -124,6 +127,12 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, j = lane & 7;
   auto chunk_ok = [&](int c) { return !PARTIAL || (j + 8 * c) * 8 < D; };
+  // element offset of tile row r in a stage: rows are dense inside a TMA box, boxes start on
+  // 128-byte boundaries (dense for head_dim % 64 == 0)
+  const int box_pitch = PARTIAL ? ((p.box_rows * D + 63) & ~63) : p.box_rows * D;
+  auto row_off = [&](int r) {
+    return PARTIAL ? (r / p.box_rows) * box_pitch + (r % p.box_rows) * D : r * D;
+  };
   const int split = blockIdx.x;
   const int kvh = blockIdx.y / p.n_hg, hg = blockIdx.y % p.n_hg;
   const int b = blockIdx.z / p.max_q_len, qi = blockIdx.z % p.max_q_len;
@@ -178,8 +187,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     for (int bx = 0; bx < nbox; ++bx) {
       const int pos = pos0 + bx * p.box_rows;
       const int slot0 = tbl[(pos >> p.block_shift) - blk_first] + (pos & p.block_mask);
-      tma_load_3d(ks + bx * p.box_rows * D, &kmap, &my_bars[s], 0, kvh, slot0);
-      tma_load_3d(vs + bx * p.box_rows * D, &vmap, &my_bars[s], 0, kvh, slot0);
+      tma_load_3d(ks + bx * box_pitch, &kmap, &my_bars[s], 0, kvh, slot0);
+      tma_load_3d(vs + bx * box_pitch, &vmap, &my_bars[s], 0, kvh, slot0);
     }
   };
 
@@ -236,7 +245,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     float sc[4][R];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const T* krow = ks + (it * 4 + g) * D;
+      const T* krow = ks + row_off(it * 4 + g);
       float kf[EPL];
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
@@ -309,7 +318,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       if (valid[it]) {  // masked rows may hold stale bytes (NaN) — never touch them
-        const T* vrow = vs + (it * 4 + g) * D;
+        const T* vrow = vs + row_off(it * 4 + g);
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           uint4 raw = chunk_ok(c) ? ld_v4(vrow + (j + 8 * c) * 8) : make_uint4(0, 0, 0, 0);
@@ -754,13 +763,15 @@ paged_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap,
 // [attn-emu:persist begin]
 constexpr int ATT_P_TPS_MAX = 32;                            // tiles per item (upper bound)
 constexpr int ATT_P_TBL = ATT_P_TPS_MAX * ATT_TILE + 8;      // block-table window entries (bs = 1)
-// High-occupancy variant (OCC = 1, B200_ATTN_OCC=1): the warp-state profile of the default
-// variant shows warps waiting on their own instruction latencies 60 % of the time and on KV data
-// 5 % (profiles/r01_ncu_paged_attn_stalls.md), i.e. it is latency bound at 7 warps per SM.  OCC
-// trades ring depth and block-table window for residency: 2 TMA stages, a 264-entry window and a
-// register cap for 11 one-warp CTAs per SM.  Same code otherwise; opt-in until measured on a B200.
+// Occupancy variant (OCC = 1, B200_ATTN_OCC=1): the warp-state profile of the default variant
+// shows warps waiting on their own instruction latencies 60 % of the time and on KV data 5 %
+// (profiles/r01_ncu_paged_attn_stalls.md), i.e. it is latency bound at 7 warps per SM.  Round 2
+// measured the first cut of this variant (2 TMA stages, 11 CTAs per SM): 114.8 us vs 96.6 us —
+// the shallower ring costs more than the extra warps give (profiles/r02_attn_variants.md).  What
+// is left of it: the full 3-stage ring with a 264-entry block-table window, which fits 8 instead
+// of 7 one-warp CTAs into an SM's shared memory.
 constexpr int ATT_P_TBL_OCC = 256 + 8;
-constexpr int ATT_OCC_CTAS = 11;
+constexpr int ATT_OCC_CTAS = 8;
 __host__ __device__ constexpr int att_p_tbl(int occ) { return occ ? ATT_P_TBL_OCC : ATT_P_TBL; }
 
 
@@ -794,7 +805,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   pdl_wait();
   pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
-  constexpr int STAGES = OCC ? 2 : Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES;
   constexpr int P_TBL = att_p_tbl(OCC);
   constexpr int KS = D / 16, NB = TR ? D / 16 : D / 8;  // NB: accumulator blocks of O (O^T)
   constexpr int ROWS = TR ? 8 : 16;                      // packed (q token, head) rows per block
@@ -1492,12 +1503,13 @@ static int attn_occ() {
   return v;
 }
 
-// B200_ATTN_TR=1: transposed-tile instantiation of the stream kernel (TR above) for shapes whose
-// packed rows fit 8: group * max_q_len <= 8 (decode), head_dim <= 128
+// Transposed-tile instantiation of the stream kernel (TR above) for shapes whose packed rows fit
+// 8: group * max_q_len <= 8 (decode), head_dim <= 128.  Default since round 2 (91.2 us vs 96.6 us
+// at the benchmark shape, profiles/r02_attn_variants.md); B200_ATTN_TR=0 selects the 16-row tile.
 static int attn_tr() {
   static const int v = [] {
     const char* e = getenv("B200_ATTN_TR");
-    return (e && e[0] == '1') ? 1 : 0;
+    return (e && e[0] == '0') ? 0 : 1;
   }();
   return v;
 }
@@ -1622,8 +1634,8 @@ static int launch_attn(const CUtensorMap& kmap, const CUtensorMap& vmap, const A
   int rc;
   if (pl.impl == 2) {
     const unsigned grid = (unsigned)((pl.total_tiles + pl.tpw - 1) / pl.tpw);
-    constexpr size_t psmem_occ = (size_t)2 * 2 * ATT_TILE * D * sizeof(T) +
-                                 3 * ATT_P_TBL_OCC * sizeof(int32_t) + 2 * 8 + 128;
+    constexpr size_t psmem_occ = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
+                                 3 * ATT_P_TBL_OCC * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
     constexpr size_t psmem_def = (size_t)AttnCfg<D>::STAGES * 2 * ATT_TILE * D * sizeof(T) +
                                  3 * ATT_P_TBL * sizeof(int32_t) + AttnCfg<D>::STAGES * 8 + 128;
     const bool occ = D <= 128 && attn_occ();

@@ -174,10 +174,13 @@ class LlamaDecoder:
 
     # -- forward -------------------------------------------------------------------
     def forward(self, tokens: torch.Tensor, positions: torch.Tensor, params: InputParameters,
-                last_token_idxes: Optional[torch.Tensor] = None) -> torch.Tensor:
+                last_token_idxes: Optional[torch.Tensor] = None, greedy: bool = False) -> torch.Tensor:
         """Returns logits [n_tokens, vocab] (llama.h:220-232 then :281-289); with
         last_token_idxes only those rows go through the final norm's output -> lm_head
-        (the reference's `h.index_select(0, last_token_idxes)` for prefill chunks)."""
+        (the reference's `h.index_select(0, last_token_idxes)` for prefill chunks).
+        greedy=True returns the sampled token ids [n_tokens] int64 instead (argmax of the logits);
+        under tensor parallelism the vocabulary-sharded logits are never gathered — local argmax
+        plus an 8-byte exchange per rank and row (ProcessGroup.argmax_sharded), same ids."""
         h = self.embed.index_select(0, tokens)
         if self.pa.world_size > 1:  # ParallelEmbedding: split on hidden + all-gather (embedding.h:74-79)
             h = gather_from_model_parallel_region(h, self.pa)
@@ -225,6 +228,13 @@ class LlamaDecoder:
             hn = norm_residual(self.final_norm, pending, pending_is_partials)
         if last_token_idxes is not None:
             hn = hn.index_select(0, last_token_idxes)
+        if greedy:
+            pg = self.pa.process_group
+            if self.pa.world_size > 1 and hasattr(pg, "argmax_sharded"):
+                ids = pg.argmax_sharded(self.lm_head.forward_local(hn))
+                if ids is not None:
+                    return ids
+            return kernels.argmax(self.lm_head(hn))
         return self.lm_head(hn)
 
     __call__ = forward
@@ -386,8 +396,7 @@ class GraphedStep:
             self.out = self._run()
 
     def _run(self) -> torch.Tensor:
-        logits = self.model(self.tokens, self.positions, self.params)
-        return kernels.argmax(logits) if self.greedy else logits
+        return self.model(self.tokens, self.positions, self.params, greedy=self.greedy)
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()

@@ -476,6 +476,10 @@ class ColumnParallelLinear:
         w = sd["weight"][shard_range(self.full_N, self.pa.rank, self.pa.world_size)]
         self.weight.copy_(w)
 
+    def forward_local(self, x: torch.Tensor) -> torch.Tensor:
+        """This rank's column shard of the output (no gather)."""
+        return F.linear(x, self.weight)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out = F.linear(x, self.weight)
         if self.pa.world_size > 1 and self.gather_output:

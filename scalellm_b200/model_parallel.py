@@ -29,15 +29,17 @@ class ProcessGroup:
 
     def __init__(self, rank: int, world_size: int, device: torch.device,
                  group: Optional[dist.ProcessGroup] = None, nvlink_max_bytes: int = 1 << 20,
-                 gather_max_bytes: int = 16 << 20):
+                 gather_max_bytes: int = 4 << 20):
         self._rank, self._world, self._device, self._group = rank, world_size, device, group
         self._comm = None
-        self._nvlink_max_bytes = nvlink_max_bytes      # one-shot all-reduce: latency-bound sizes only
-        # B200_AR_GATHER=1: all-gathers go through the peer-memory kernel too (opt-in until it
-        # has run on a multi-GPU box); its messages may be larger (a one-shot gather moves no
-        # more bytes than a ring), so the symmetric buffer is sized for them
-        self._gather_max_bytes = gather_max_bytes if os.environ.get("B200_AR_GATHER") == "1" else 0
+        self._nvlink_max_bytes = nvlink_max_bytes      # peer-memory all-reduce: latency-bound sizes only
+        # all-gathers go through the peer-memory kernel too (B200_AR_GATHER=0: NCCL + cat); their
+        # messages may be larger (a one-shot gather moves no more bytes than a ring), so the
+        # symmetric buffers are sized for them
+        self._gather_max_bytes = gather_max_bytes if os.environ.get("B200_AR_GATHER", "1") != "0" else 0
         self._buffer_bytes = max(nvlink_max_bytes, self._gather_max_bytes)
+        algo = os.environ.get("B200_AR_ALGO", "")
+        self._twoshot = algo == "twoshot" or (algo != "oneshot" and world_size > 2)
         if device.type == "cuda" and world_size > 1:
             self._init_nvlink()
 
@@ -77,13 +79,19 @@ class ProcessGroup:
         if self._world == 1:
             return
         nbytes = input.numel() * input.element_size()
-        if (self._comm is not None and input.is_cuda and input.is_contiguous()
-                and nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
-                and input.data_ptr() % 16 == 0
+        # the peer-memory / NCCL choice uses rank-invariant properties only (size, dtype): ranks
+        # that disagreed would dead-lock (one side spinning on flags, the other inside NCCL).  A
+        # view that is not contiguous or not 16-byte aligned is staged through a temporary.
+        if (self._comm is not None and input.is_cuda
+                and 0 < nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
                 and input.dtype in (torch.bfloat16, torch.float16, torch.float32)):
             dt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[input.dtype]
-            check(_lib.load().b200_ar_allreduce(self._comm, input.data_ptr(), input.numel(), dt,
+            direct = input.is_contiguous() and input.data_ptr() % 16 == 0
+            x = input if direct else input.contiguous().clone()
+            check(_lib.load().b200_ar_allreduce(self._comm, x.data_ptr(), x.numel(), dt,
                                                 torch.cuda.current_stream().cuda_stream))
+            if not direct:
+                input.copy_(x)
             return
         dist.all_reduce(input, op=dist.ReduceOp.SUM, group=self._group)
 
@@ -95,8 +103,8 @@ class ProcessGroup:
         S, rows, n = data.shape
         out = torch.empty((rows, n), dtype=dtype, device=data.device)
         nbytes = out.numel() * out.element_size()
-        if (self._comm is not None and nbytes <= self._nvlink_max_bytes and nbytes % 16 == 0
-                and dtype in (torch.bfloat16, torch.float16)):
+        if (self._comm is not None and (rows + self._world) * n * out.element_size() <= self._nvlink_max_bytes
+                and nbytes % 16 == 0 and dtype in (torch.bfloat16, torch.float16)):
             dt = 0 if dtype == torch.bfloat16 else 1
             check(_lib.load().b200_ar_allreduce_splitk(self._comm, out.data_ptr(), data.data_ptr(),
                                                        S, partials.K, n, out.numel(), dt,
@@ -108,8 +116,9 @@ class ProcessGroup:
         return out
 
     def supports_partials_norm(self, rows: int, n: int, dtype: torch.dtype) -> bool:
-        return (self._comm is not None and 0 < rows <= 64 and n % 128 == 0 and n <= 4096
-                and rows * n * 2 <= self._nvlink_max_bytes
+        max_rows, max_n = (128, 8192) if self._twoshot else (64, 4096)
+        return (self._comm is not None and 0 < rows <= max_rows and n % 128 == 0 and n <= max_n
+                and (rows + self._world) * n * 2 <= self._buffer_bytes
                 and dtype in (torch.bfloat16, torch.float16))
 
     def allreduce_partials_norm(self, partials, residual: torch.Tensor, weight: torch.Tensor,
@@ -136,15 +145,31 @@ class ProcessGroup:
         the fast path does not apply (the caller then uses allgather + cat)."""
         if self._comm is None or self._gather_max_bytes == 0 or not input.is_cuda:
             return None
-        x = input.contiguous()
-        row_bytes = x.size(-1) * x.element_size()
-        nbytes = x.numel() * x.element_size()
-        if nbytes == 0 or row_bytes % 16 or nbytes > self._gather_max_bytes or x.data_ptr() % 16:
+        row_bytes = input.size(-1) * input.element_size()
+        nbytes = input.numel() * input.element_size()
+        if nbytes == 0 or row_bytes % 16 or nbytes > self._gather_max_bytes:   # rank-invariant
             return None
+        x = input.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone()
         rows = x.numel() // x.size(-1)
         out = torch.empty((*x.shape[:-1], x.size(-1) * self._world), dtype=x.dtype, device=x.device)
         check(_lib.load().b200_ar_allgather(self._comm, out.data_ptr(), x.data_ptr(), rows, row_bytes,
                                             torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def argmax_sharded(self, logits: torch.Tensor) -> Optional[torch.Tensor]:
+        """Greedy sampling over a vocabulary-sharded lm_head: argmax over ALL ranks' columns of
+        each row == torch.argmax(gather_from_model_parallel_region(logits), -1), without moving
+        the logits (one launch, 8 bytes per rank and row over NVLink).  None if not applicable."""
+        if (self._comm is None or not logits.is_cuda or logits.dim() != 2 or logits.size(0) > 128
+                or logits.dtype not in (torch.bfloat16, torch.float16, torch.float32)):
+            return None
+        x = logits if logits.stride(1) == 1 else logits.contiguous()
+        out = torch.empty(x.size(0), dtype=torch.int64, device=x.device)
+        dt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[x.dtype]
+        check(_lib.load().b200_ar_argmax(self._comm, out.data_ptr(), x.data_ptr(), x.size(0), x.size(1),
+                                         x.stride(0), dt, torch.cuda.current_stream().cuda_stream))
         return out
 
     def close(self) -> None:

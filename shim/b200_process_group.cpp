@@ -2,6 +2,8 @@
 // csrc/allreduce.cu behind the C ABI.
 #include "b200_process_group.h"
 
+#include <algorithm>
+
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
@@ -48,11 +50,30 @@ ProcessGroupB200::~ProcessGroupB200() { b200_ar_destroy(comm_); }
 void ProcessGroupB200::allreduce(torch::Tensor& input) const {
   TORCH_CHECK(input.device() == device(), "input should be on the same device as the process group");
   if (world_size() == 1 || input.numel() == 0) return;
-  TORCH_CHECK(input.is_contiguous(), "ProcessGroupB200::allreduce: contiguous tensors only");
   c10::cuda::CUDAGuard guard(device());
-  ok(b200_ar_allreduce(comm_, input.data_ptr(), input.numel(), dtype_code(input),
-                       at::cuda::getCurrentCUDAStream().stream()),
-     "ar_allreduce");
+  // Any size, like the reference's NCCL group (process_group.cpp:135-153): messages larger than
+  // the symmetric buffer go through it in slices; a tensor that is not contiguous, not 16-byte
+  // aligned or not a multiple of 16 bytes is staged through a zero-padded temporary.  Every
+  // decision below depends on size / dtype only, so all ranks take the same path.
+  const int64_t es = static_cast<int64_t>(input.element_size());
+  const int64_t bytes = input.numel() * es;
+  const bool direct = input.is_contiguous() && bytes % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(input.data_ptr()) % 16 == 0;
+  torch::Tensor staged;
+  if (!direct) {
+    const int64_t padded = (bytes + 15) / 16 * 16 / es;
+    staged = torch::zeros({padded}, input.options());
+    staged.narrow(0, 0, input.numel()).copy_(input.reshape({-1}));
+  }
+  auto* base = static_cast<uint8_t*>(direct ? input.data_ptr() : staged.data_ptr());
+  const int64_t total = direct ? input.numel() : staged.numel();
+  const int64_t slice = (kMaxBytes / 2) / es;  // elements per call (a multiple of 16 bytes)
+  const auto stream = at::cuda::getCurrentCUDAStream().stream();
+  for (int64_t off = 0; off < total; off += slice) {
+    const int64_t n = std::min(slice, total - off);
+    ok(b200_ar_allreduce(comm_, base + off * es, n, dtype_code(input), stream), "ar_allreduce");
+  }
+  if (!direct) input.copy_(staged.narrow(0, 0, input.numel()).view_as(input));
 }
 
 torch::Tensor ProcessGroupB200::allgather_lastdim(const torch::Tensor& input) const {
@@ -65,10 +86,20 @@ torch::Tensor ProcessGroupB200::allgather_lastdim(const torch::Tensor& input) co
   auto out = torch::empty(sizes, x.options());
   if (x.numel() == 0) return out;
   c10::cuda::CUDAGuard guard(device());
-  ok(b200_ar_allgather(comm_, out.data_ptr(), x.const_data_ptr(), x.numel() / cols,
-                       cols * static_cast<int64_t>(x.element_size()),
-                       at::cuda::getCurrentCUDAStream().stream()),
-     "ar_allgather");
+  const int64_t row_bytes = cols * static_cast<int64_t>(x.element_size());
+  const int64_t rows = x.numel() / cols;
+  TORCH_CHECK(row_bytes % 16 == 0 && row_bytes <= kMaxBytes,
+              "allgather_lastdim: rows of a multiple of 16 bytes, at most ", kMaxBytes, " bytes");
+  // more rows than the symmetric buffer holds: gather them in groups
+  const int64_t rows_per_call = std::max<int64_t>(1, kMaxBytes / row_bytes);
+  const auto stream = at::cuda::getCurrentCUDAStream().stream();
+  for (int64_t r0 = 0; r0 < rows; r0 += rows_per_call) {
+    const int64_t nr = std::min(rows_per_call, rows - r0);
+    ok(b200_ar_allgather(comm_, static_cast<uint8_t*>(out.data_ptr()) + r0 * row_bytes * world_size(),
+                         static_cast<const uint8_t*>(x.const_data_ptr()) + r0 * row_bytes, nr, row_bytes,
+                         stream),
+       "ar_allgather");
+  }
   return out;
 }
 
@@ -88,8 +119,11 @@ torch::Tensor ProcessGroupB200::allreduce_partials(const torch::Tensor& partials
 }
 
 bool ProcessGroupB200::supports_partials_norm(int64_t rows, int64_t n, torch::ScalarType dtype) const {
-  return world_size() > 1 && rows > 0 && rows <= 64 && n % 128 == 0 && n <= 4096 &&
-         rows * n * 2 <= kMaxBytes && (dtype == torch::kBFloat16 || dtype == torch::kHalf);
+  // two-shot form above two ranks (rows <= 128, n <= 8192), one-shot at two (rows <= 64, n <= 4096)
+  const bool two = world_size() > 2;
+  return world_size() > 1 && rows > 0 && rows <= (two ? 128 : 64) && n % 128 == 0 &&
+         n <= (two ? 8192 : 4096) && (rows + world_size()) * n * 2 <= kMaxBytes &&
+         (dtype == torch::kBFloat16 || dtype == torch::kHalf);
 }
 
 torch::Tensor ProcessGroupB200::allreduce_partials_norm(const torch::Tensor& partials, int64_t gemm_k,
@@ -117,10 +151,24 @@ void ProcessGroupB200::allgather(const torch::Tensor& input, torch::Tensor& outp
   const auto x = input.contiguous();
   if (x.numel() == 0) return;
   c10::cuda::CUDAGuard guard(device());
-  ok(b200_ar_allgather(comm_, outputs.data_ptr(), x.const_data_ptr(), 1,
-                       x.numel() * static_cast<int64_t>(x.element_size()),
-                       at::cuda::getCurrentCUDAStream().stream()),
-     "ar_allgather");
+  const int64_t bytes = x.numel() * static_cast<int64_t>(x.element_size());
+  TORCH_CHECK(bytes % 16 == 0, "allgather: message must be a multiple of 16 bytes");
+  if (bytes <= kMaxBytes) {
+    ok(b200_ar_allgather(comm_, outputs.data_ptr(), x.const_data_ptr(), 1, bytes,
+                         at::cuda::getCurrentCUDAStream().stream()),
+       "ar_allgather");
+    return;
+  }
+  // larger than the symmetric buffer: slices land at [r][off .. off+n) of the [world, bytes] result
+  auto tmp = torch::empty({world_size() * kMaxBytes}, x.options().dtype(torch::kUInt8));
+  auto out_b = outputs.view({-1}).view(torch::kUInt8).view({world_size(), bytes});
+  const auto* src = static_cast<const uint8_t*>(x.const_data_ptr());
+  for (int64_t off = 0; off < bytes; off += kMaxBytes) {
+    const int64_t n = std::min<int64_t>(kMaxBytes, bytes - off);
+    ok(b200_ar_allgather(comm_, tmp.data_ptr(), src + off, 1, n, at::cuda::getCurrentCUDAStream().stream()),
+       "ar_allgather");
+    out_b.narrow(1, off, n).copy_(tmp.narrow(0, 0, world_size() * n).view({world_size(), n}));
+  }
 }
 
 void ProcessGroupB200::allgather(const torch::Tensor& input,

@@ -10,8 +10,8 @@
 //                                            src/model_parallel/model_parallel.cpp:13-65
 //
 // Inside ScaleLLM ProcessGroupB200 derives from ProcessGroupNCCL and keeps NCCL for what the
-// decode step does not use (alltoall, messages larger than the symmetric buffer; INTEGRATION.md
-// 2.4); this self-contained restatement refuses those instead.
+// decode step does not use (alltoall).  Messages of any size and layout are
+// taken: larger than the symmetric buffer -> slices, unaligned / non-contiguous -> staged.
 #pragma once
 
 #include <torch/torch.h>
@@ -52,7 +52,8 @@ class ProcessGroup {
 
 class ProcessGroupB200 final : public ProcessGroup {
  public:
-  // bytes of the largest message the peer-memory kernels take (the symmetric buffer is twice that)
+  // bytes of the largest single launch of the peer-memory kernels (the symmetric region is four
+  // times that); larger messages are sliced
   static constexpr int64_t kMaxBytes = 16 << 20;
 
   ProcessGroupB200(int rank, int world_size, const torch::Device& device, b200_ar_comm* comm)

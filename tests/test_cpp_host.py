@@ -134,8 +134,6 @@ def test_cpp_decode_step_matches_python_mirror(fuse):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_STAGED") != "1",
-                    reason="staged: not yet validated on a GPU box (B200_TEST_STAGED=1)")
 def test_cpp_cuda_graph_step_replays_like_eager():
     """CudaGraphStep (ModelRunner::CudaGraph, model_runner.cpp:141-210): capture one step, replay
     it with other metadata (different kv lengths, a shorter block table) — logits bit-identical to
@@ -240,8 +238,6 @@ def _dequant(quant, method, t, g):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_STAGED") != "1",
-                    reason="staged: not yet validated on a GPU box (B200_TEST_STAGED=1)")
 def test_cpp_model_runner_replays_captured_batch_sizes_and_falls_back():
     """ModelRunner (model_runner.cpp:25-139): a decode step whose batch size was captured is a
     graph replay, anything else (other batch size, multi-token queries, context beyond the

@@ -20,8 +20,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, algo=""):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), B200_AR_ALGO=algo)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -29,8 +29,10 @@ def _worker(rank, world, port):
     pg = ProcessGroup(rank, world, dev)
     try:
         assert pg._comm is not None, "NVLink communicator was not created"
+        assert pg._twoshot == (algo == "twoshot" or (algo == "" and world > 2))
         for dtype in (torch.bfloat16, torch.float16, torch.float32):
-            for shape in ((64, 4096), (32, 8192), (1, 8), (7, 1024), (128, 4096)):
+            # (33, 1000): last row of the two-shot partition is short; (3, 4096): fewer rows than ranks
+            for shape in ((64, 4096), (32, 8192), (1, 8), (7, 1024), (128, 4096), (33, 1000), (3, 4096)):
                 g = torch.Generator(device=dev).manual_seed(100 * rank + shape[0])
                 x = torch.randn(shape, generator=g, device=dev).to(dtype)
                 ref = x.clone()
@@ -39,8 +41,10 @@ def _worker(rank, world, port):
                 dist.all_gather(gathered, x)
                 host_sum = sum(t.float() for t in gathered)  # fp32 sum in rank order
                 y = x.clone()
-                for _ in range(3):                        # repeated calls: epochs / double buffering
+                for it in range(3):                       # repeated calls: epochs / double buffering
                     y.copy_(x)
+                    if (it + rank) % world == 0:          # rank skew: somebody always arrives late
+                        torch.cuda._sleep(2_000_000)
                     pg.allreduce(y)
                 torch.cuda.synchronize()
                 # ours == fp32 rank-order sum rounded once
@@ -81,6 +85,42 @@ def _worker(rank, world, port):
             out_fused = pg.allreduce_partials_norm(parts, r_fused, wn, 1e-5)
         torch.cuda.synchronize()
         assert torch.equal(r_fused, r_ref) and torch.equal(out_fused, out_ref)
+        # hidden 8192 (two vectors per thread in the two-shot kernel; the one-shot form stops at 4096)
+        if pg._twoshot:
+            K2, N2, M2 = 1024, 8192, 32
+            qw2 = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, size=(K2, N2 // 8), dtype=np.int64).astype(np.int32)).to(dev)
+            qz2 = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, size=(K2 // 128, N2 // 8), dtype=np.int64).astype(np.int32)).to(dev)
+            sc2 = (torch.rand(K2 // 128, N2, generator=torch.Generator().manual_seed(rank)) * 0.01 + 1e-3).bfloat16().to(dev)
+            packed2 = kernels.w4a16_prepack_awq(qw2, qz2, sc2, 128)
+            a2 = torch.randn(M2, K2, generator=torch.Generator().manual_seed(7 + rank)).bfloat16().to(dev)
+            parts2 = kernels.w4a16_gemm_splitk(a2, packed2, N2, 128, poison=True)
+            want2 = kernels.w4a16_reduce_partials(parts2)
+            pg.allreduce(want2)
+            res2 = torch.randn(M2, N2, generator=gen).bfloat16().to(dev)
+            wn2 = (1 + 0.1 * torch.randn(N2, generator=gen)).bfloat16().to(dev)
+            assert pg.supports_partials_norm(M2, N2, torch.bfloat16)
+            r_ref2, out_ref2 = res2.clone(), torch.empty_like(res2)
+            kernels.rms_norm_residual(out_ref2, r_ref2, want2, wn2, 1e-5)
+            r_f2 = res2.clone()
+            out_f2 = pg.allreduce_partials_norm(parts2, r_f2, wn2, 1e-5)
+            torch.cuda.synchronize()
+            assert torch.equal(r_f2, r_ref2) and torch.equal(out_f2, out_ref2)
+        # greedy sampling over a vocabulary-sharded lm_head == argmax of the gathered logits
+        for dtype in (torch.bfloat16, torch.float32):
+            for rows, nl in ((64, 16032), (5, 1000), (128, 264), (1, 7)):
+                gl = torch.Generator(device=dev).manual_seed(31 * rank + rows)
+                lg = torch.randn(rows, nl, generator=gl, device=dev).to(dtype)
+                lg[0, :] = 1.0                                          # ties everywhere: first index wins
+                if rows > 2:
+                    lg[1, nl - 1] = 100.0 if rank == world - 1 else lg[1, nl - 1]   # winner in the last shard
+                    lg[2, 3] = float("nan") if rank == world // 2 else lg[2, 3]    # NaN counts as the maximum
+                outs = [torch.empty_like(lg) for _ in range(world)]
+                dist.all_gather(outs, lg)
+                want_ids = torch.argmax(torch.cat(outs, dim=-1).float(), dim=-1)
+                for _ in range(2):
+                    ids = pg.argmax_sharded(lg)
+                torch.cuda.synchronize()
+                assert ids is not None and torch.equal(ids, want_ids), (dtype, rows, nl)
         # larger than the symmetric buffer -> NCCL path, still correct
         big = torch.ones(2 << 20, device=dev)
         pg.allreduce(big)
@@ -108,20 +148,15 @@ def _worker(rank, world, port):
         dist.destroy_process_group()
 
 
-def test_nvlink_allreduce_matches_nccl_and_host_sum():
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
-    mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
+@pytest.mark.parametrize("world,algo", [(2, "oneshot"), (2, "twoshot"), (4, ""), (8, ""), (8, "oneshot")])
+def test_nvlink_allreduce_matches_nccl_and_host_sum(world, algo):
+    """process_group_test.cpp:48-171 loops world_size = 1,2,4,...,device_count: so do we, with
+    both algorithms at the ends of the range."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    mp.spawn(_worker, args=(world, _free_port(), algo), nprocs=world, join=True)
 
 
-# --------------------------------------------------------------------------------------------
-# Written after round 1's GPU budget was spent: run with B200_TEST_STAGED=1 on a >= 2-GPU box
-# (tools/gpu_ci.sh tp2staged) before the gate is removed.
-# --------------------------------------------------------------------------------------------
-_STAGED = pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
-                             reason="staged: not yet validated on a multi-GPU box (B200_TEST_STAGED=1)")
 
 
 def _gather_worker(rank, world, port):
@@ -158,16 +193,13 @@ def _gather_worker(rank, world, port):
         dist.destroy_process_group()
 
 
-@_STAGED
-def test_nvlink_allgather_lastdim_is_a_bit_exact_cat():
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+@pytest.mark.parametrize("world", [2, 8])
+def test_nvlink_allgather_lastdim_is_a_bit_exact_cat(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     mp.spawn(_gather_worker, args=(world, _free_port()), nprocs=world, join=True)
 
 
-@_STAGED
 def test_same_process_group_like_ncclCommInitAll():
     """b200_ar_create_all: every rank in ONE process (the reference engine's model, one thread per
     GPU): peers mapped by peer access; launches issued from one thread, one device after the other."""
@@ -208,7 +240,6 @@ def test_same_process_group_like_ncclCommInitAll():
             lib.b200_ar_destroy(comms[r])
 
 
-@_STAGED
 def test_cpp_process_groups_in_one_process():
     """shim/b200_process_group: ProcessGroup::create_process_groups + the model-parallel region
     helpers with the reference's signatures, all ranks in this process."""
@@ -245,7 +276,6 @@ def test_cpp_process_groups_in_one_process():
     del pgs
 
 
-@_STAGED
 @pytest.mark.parametrize("fuse", [True, False])
 def test_cpp_tensor_parallel_decode_step(fuse):
     """The C++ LlamaDecoderStep under TP=2, both ranks in this process (one Python thread each, the

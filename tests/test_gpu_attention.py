@@ -94,8 +94,6 @@ def test_variants(D, cap, alibi, win):
     check(out, ref, torch.bfloat16, f"D={D} cap={cap} alibi={alibi} win={win}")
 
 
-@pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
-                    reason="staged: written for the B200_ATTN_TR=1 variant, not yet run on a GPU")
 @pytest.mark.parametrize("D", [64, 128])
 @pytest.mark.parametrize("H,Hkv,q_lens", [(8, 2, [2, 1, 2]), (8, 1, [1, 1, 1]), (4, 4, [5, 8, 1])])
 @pytest.mark.parametrize("cap,alibi,win", [(0.0, False, -1), (50.0, False, -1), (0.0, True, -1),
@@ -110,8 +108,6 @@ def test_variants_with_at_most_8_packed_rows(D, H, Hkv, q_lens, cap, alibi, win)
     check(out, ref, torch.bfloat16, f"D={D} H={H}/{Hkv} q={q_lens} cap={cap} alibi={alibi} win={win}")
 
 
-@pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
-                    reason="staged: head_dim 32 / 96 were added after the round's GPU budget")
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("D", [32, 96])
 @pytest.mark.parametrize("H,Hkv,bs", [(6, 6, 1), (6, 3, 8), (6, 1, 8), (32, 8, 16)])

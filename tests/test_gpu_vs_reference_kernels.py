@@ -10,8 +10,8 @@ parity claim can have: same inputs, the reference's kernel vs ours.
   paged_kv_varlen_mha            src/kernels/attention/attn_api.cpp:14-73            both within the
                                  fp32-restatement tolerance, and within 2 bf16 ulp of each other
 
-The module was built after the round's GPU budget was spent, so the file is skipped unless
-B200_TEST_REF_KERNELS=1 until it has run once on a B200."""
+Skipped only when oracle/_ref/_ref_kernels.so is genuinely absent (build() makes it wherever
+/root/reference exists; it travels to the GPU box)."""
 import os
 import sys
 
@@ -24,9 +24,7 @@ from scalellm_b200 import kernels
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "oracle", "_ref", "_ref_kernels.so")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref not built (needs /root/reference)"),
-              pytest.mark.skipif(os.environ.get("B200_TEST_REF_KERNELS") != "1",
-                                 reason="not yet validated on a B200 (set B200_TEST_REF_KERNELS=1)")]
+              pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref not built (needs /root/reference)")]
 DEV = "cuda"
 
 

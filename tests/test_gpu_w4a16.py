@@ -143,8 +143,6 @@ def test_gemm_bias_strided_and_large_m():
     assert (out.cpu().view(torch.int16) == ref.view(torch.int16)).float().mean() > 0.85
 
 
-@pytest.mark.skipif(os.environ.get("B200_TEST_STAGED") != "1",
-                    reason="staged: written after the round's GPU budget, not yet run on a GPU")
 @pytest.mark.parametrize("method", ["awq", "gptq"])
 def test_dense_prefill_path_of_the_int4_linear(method, monkeypatch):
     """B200_W4_PREFILL_DENSE=1: above 256 rows the int4 linear dequantises once (bit-exact bf16

@@ -148,11 +148,33 @@ def main():
         if rank != 0:
             os._exit(0)     # communicators captured into graphs can block at tear-down
     rows, st = summarise(events, a.replays)
+    # one layer in the middle of the last replay, kernel by kernel: start relative to the layer's
+    # first kernel, duration, and the gap / overlap against the previous kernel's end
+    seq = sorted(events, key=lambda e: e[1])
+    per_step = len(seq) // max(1, a.replays)
+    last = seq[-per_step:]
+    attn_idx = [i for i, e in enumerate(last) if "paged_attn_persist" in e[0] or "paged_attn_decode" in e[0]]
+    layer_txt = ""
+    if len(attn_idx) > 4:
+        mid = attn_idx[len(attn_idx) // 2]
+        nxt = attn_idx[len(attn_idx) // 2 + 1]
+        lo = mid - (nxt - mid) + 1 if mid - (nxt - mid) + 1 > 0 else 0
+        win = last[lo: nxt + 1]
+        t0 = win[0][1]
+        lines = ["", "## one layer (middle of the last replay), in start order", "",
+                 "| kernel | start us | dur us | end us | start - prev end us |", "|---|---:|---:|---:|---:|"]
+        prev_end = None
+        for name, s0, d in win:
+            gap = "" if prev_end is None else f"{s0 - prev_end:+.2f}"
+            lines.append(f"| `{short(name)}` | {s0 - t0:.2f} | {d:.2f} | {s0 - t0 + d:.2f} | {gap} |")
+            prev_end = max(prev_end or 0.0, s0 + d)
+        layer_txt = "\n".join(lines) + "\n"
     if not rows:
         print("no device kernel records in the trace (CUPTI unavailable?)")
         sys.exit(1)
     text = render(rows, st, f"decode-step timeline: Llama-3-8B {a.quant} int4, batch {B}, kv_len {S}, "
                             f"block_size {bs}, {a.layers} layers, TP={world}, CUDA graph replay")
+    text += layer_txt
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         f.write(text)
