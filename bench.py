@@ -40,9 +40,10 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--ttft", action="store_true",
-                    help="also measure unloaded p50 time-to-first-token (chunked prefill through "
-                         "the decode kernels; experimental, off by default)")
+    ap.add_argument("--ttft", action="store_true", help="(default now) kept for old command lines")
+    ap.add_argument("--no-ttft", action="store_true",
+                    help="skip the unloaded p50 time-to-first-token measurement (chunked prefill of 8 "
+                         "requests, ~1 s of GPU time)")
     ap.add_argument("--ttft-chunk", type=int, default=128,
                     help="prefill chunk (token budget per step) of the --ttft measurement; with "
                          "B200_W4_PREFILL_DENSE=1 chunks > 256 tokens run the int4 linears as "
@@ -240,21 +241,33 @@ def run_reference(a, rank):
         return
     c = CpuDecodeSample(a, 0)
     cores = c.torch.get_num_threads()
-    vals, secs = [], 0.0
+    vals, secs = [], []
     for i in range(a.warmup + a.steps):
         v, s = c.step(1)
         if i >= a.warmup:
             vals.append(v)
-            secs += s
+            secs.append(s)
     vals.sort()
+    secs.sort()
     v = vals[len(vals) // 2]
-    sample = (f"per step: {c.B} of the {a.batch} sequences (kv_len {a.seqlen}) through 1 of 32 oracle "
-              "decoder layers + final norm + bf16 lm_head, time extrapolated x32 layers; tokens/s = "
-              "sampled sequences / that time; median over steps")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = (f"EXTRAPOLATED: each timed step runs {c.B} of the {a.batch} sequences (kv_len {a.seqlen}) "
+              "through 1 of the 32 oracle decoder layers + final norm + bf16 lm_head "
+              f"({secs[len(secs) // 2]:.2f} s of CPU work per step on {cores} threads, the fastest of the "
+              "thread counts {all, 32, 16, 8} timed at start-up — the same rule as the main arm's "
+              "cpu_baseline); value = sampled sequences / (layer time x 32 + head time), i.e. the "
+              "tokens/s the CPU path would sustain on the sampled sequences; median over steps")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-           "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * a.batch / v,
+           "steps": a.steps, "warmup": a.warmup,
+           # the time a timed step of THIS arm really took (the bounded sample), not the extrapolation
+           "ms_per_step": 1000.0 * secs[len(secs) // 2],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-           "data": "synthetic", "config": {"workload": workload_name(a, 1).replace("TP=1", "CPU")},
+           "data": "synthetic",
+           "config": {"workload": workload_name(a, world), "global_batch": a.batch, "seq_len": a.seqlen,
+                      "parallelism": f"tp{world}", "layers": 32},
+           "extrapolation": {"layers_run": 1, "layers_total": 32, "sequences_run": c.B,
+                             "sequences_total": a.batch,
+                             "full_step_ms_extrapolated": 1000.0 * c.B / v},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": sample, "config0": cpu_config0()},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -398,12 +411,15 @@ def run_b200(a, rank, world, local_rank):
         clocks = ClockSampler.summarise(sampler.window(t_w0, t_e2e_end))
         sampler.stop()
 
-    ttft = "not measured: prefill kernels are SURVEY §8f rank 1 (next)"
-    if a.ttft and world == 1:
+    # p50 time to first token (the metric's second half): every rank runs the same deterministic
+    # request list (the collectives inside need all of them), rank 0 reports
+    ttft = "skipped (--no-ttft)"
+    if not a.no_ttft:
         try:
-            ttft = measure_ttft(model, pool, args, dev, chunk=a.ttft_chunk)
-        except Exception as e:  # noqa: BLE001  (experimental: never cost the bench line)
+            ttft = measure_ttft(model, pool, args, dev, chunk=a.ttft_chunk, n_req=8)
+        except Exception as e:  # noqa: BLE001  (never cost the bench line)
             ttft = f"failed: {type(e).__name__}: {e}"
+        barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline and a.model == "llama3-8b":
@@ -433,7 +449,8 @@ def run_b200(a, rank, world, local_rank):
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h},
                "gpu_launches": launches_per_step * a.steps, "clocks": clocks, "roofline": roof,
-               "roofline_w4a16_gemm": gemm, "cpu_baseline": cpu}
+               "roofline_w4a16_gemm": gemm, "vs_ref_kernel": _vs_ref_kernel(roof, gemm, a, world),
+               "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     if world > 1:
         # Tear-down of NCCL communicators that were captured into CUDA graphs can block for
@@ -490,7 +507,8 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
     times.sort()
     return {"p50_ms": times[len(times) // 2], "min_ms": times[0], "max_ms": times[-1],
             "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
-            "load": "unloaded (one request at a time), eager launches, decode kernels" +
+            "kernels": "decode path (the stream attention kernel with q_len = chunk rows; no prefill-tuned kernel yet)",
+            "load": "unloaded (one request at a time), eager launches" +
                     (", int4 linears as dequant + library bf16 GEMM above 256 rows"
                      if os.environ.get("B200_W4_PREFILL_DENSE") == "1" else "")}
 
@@ -503,6 +521,28 @@ def _traffic(name):
         return float(json.load(open(p))[name]["dram_bytes_per_launch"])
     except Exception:
         return None
+
+
+def _vs_ref_kernel(roof, gemm, a, world):
+    """Our live kernel timings beside the reference's own kernels (sm80-era, recompiled for
+    sm_100a) as measured on a B200 by tools/attn_bench.py / tools/w4_ref_bench.py on the same
+    shapes (profiles/ref_ab.json, profiles/r02_ref_ab.md).  Only for the configuration those
+    were taken on: Llama-3-8B, batch 64, kv 2048, block_size 8, one GPU."""
+    if world != 1 or a.model != "llama3-8b" or a.batch != 64 or a.seqlen != 2048 or a.block_size != 8:
+        return None
+    try:
+        ref = json.load(open(os.path.join(ROOT, "profiles", "ref_ab.json")))
+    except Exception:
+        return None
+    out = {"source": ref.get("source")}
+    if roof:
+        out["attention"] = {"reference_us": ref["attention_us"], "ours_us": roof["us_per_launch"],
+                            "speedup": ref["attention_us"] / roof["us_per_launch"]}
+    if gemm:
+        ours = sum(v["us"] for v in gemm["per_proj"].values())
+        theirs = sum(ref["marlin_us"][k] for k in gemm["per_proj"])
+        out["w4a16_gemms_per_layer"] = {"reference_us": theirs, "ours_us": ours, "speedup": theirs / ours}
+    return out
 
 
 def attention_roofline(model, params, hb, a, dev, world):
@@ -539,7 +579,9 @@ def attention_roofline(model, params, hb, a, dev, world):
     peak, src = _peaks()
     ach = alg_bytes / (ms * 1e-3) / 1e9
     return {"kernel": "paged_attn_persist_kernel(+combine)", "bound": "hbm", "achieved": ach,
-            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("paged_attn"),
+            "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            # the committed ncu capture is of the 1-GPU launch (8 kv heads): no figure for TP shards
+            "traffic": _traffic("paged_attn") if world == 1 else None,
             "peak_source": src, "us_per_launch": ms * 1e3, "algorithmic_bytes": alg_bytes,
             "launches_timed": n}
 

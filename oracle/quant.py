@@ -154,3 +154,104 @@ def random_gptq_checkpoint(K: int, N: int, group_size: int, seed: int):
     z = np.full((K // g, N), 8, dtype=np.int32)
     # stored zeros follow the v1 convention (zero - 1 = 7)
     return {"qweight": pack_gptq(q), "qzeros": pack_cols(z - 1), "scales": s, "q": q, "z": z}
+
+
+# ----------------------------------------------------------------------------
+# Marlin layouts — what the reference's own GEMM kernel (marlin::gptq_gemm) consumes.  Restated
+# from tests/kernels/quant_utils.py:178-291 (weights, scales) and
+# src/layers/quantization/qlinear_awq_marlin_impl.cpp:62-97 (zero points); pinned against
+# tests/golden/marlin_golden.npz (written by the reference's quant_utils).  Used by the GPU tests
+# that run the reference kernel beside ours, and (the inverse maps) to check the drop-in shim that
+# accepts Marlin-layout scales / zero points.  4-bit only.
+# ----------------------------------------------------------------------------
+_INTERLEAVE4 = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+
+
+def marlin_weight_perm() -> np.ndarray:
+    """quant_utils.py:201-228: element order inside a [16 k x 64 n] slab (1024 entries), then the
+    pairs-interleave of fast_conversion_interleave (:178-187)."""
+    perm = []
+    for i in range(32):
+        perm1 = []
+        col = i // 4
+        for block in (0, 1):
+            for row in (2 * (i % 4), 2 * (i % 4) + 1, 2 * (i % 4 + 4), 2 * (i % 4 + 4) + 1):
+                perm1.append(16 * row + col + 8 * block)
+        for j in range(4):
+            perm.extend(p + 256 * j for p in perm1)
+    perm = np.array(perm)
+    return perm.reshape(-1, 8)[:, _INTERLEAVE4].ravel()
+
+
+def marlin_scales_perm():
+    """quant_utils.py:231-241"""
+    scale_perm = [i + 8 * j for i in range(8) for j in range(8)]
+    scale_perm_single = [2 * i + j for i in range(4) for j in (0, 1, 8, 9, 16, 17, 24, 25)]
+    return np.array(scale_perm), np.array(scale_perm_single)
+
+
+def pack_marlin_weights(q: np.ndarray) -> torch.Tensor:
+    """[K, N] ints in 0..15 -> int32 [K/16, N*16/8] (quant_utils.py:245-278)."""
+    k, n = q.shape
+    assert k % 16 == 0 and n % 64 == 0
+    t = q.reshape(k // 16, 16, n // 16, 16).transpose(0, 2, 1, 3).reshape(k // 16, n * 16)
+    perm = marlin_weight_perm()
+    res = t.reshape(-1, perm.size)[:, perm].reshape(t.shape).astype(np.uint32)
+    packed = np.zeros((res.shape[0], res.shape[1] // 8), dtype=np.uint32)
+    for i in range(8):
+        packed |= res[:, i::8] << np.uint32(4 * i)
+    return torch.from_numpy(packed.view(np.int32).copy())
+
+
+def unpack_marlin_weights(packed: torch.Tensor, K: int, N: int) -> np.ndarray:
+    """inverse of pack_marlin_weights -> [K, N] ints"""
+    p = packed.cpu().numpy().view(np.uint32)
+    res = np.zeros((p.shape[0], p.shape[1] * 8), dtype=np.int64)
+    for i in range(8):
+        res[:, i::8] = (p >> np.uint32(4 * i)) & 0xF
+    perm = marlin_weight_perm()
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    t = res.reshape(-1, perm.size)[:, inv].reshape(K // 16, N * 16)
+    return t.reshape(K // 16, N // 16, 16, 16).transpose(0, 2, 1, 3).reshape(K, N)
+
+
+def permute_marlin_scales(s: torch.Tensor) -> torch.Tensor:
+    """[G, N] -> Marlin column order (quant_utils.py:282-291; qlinear_awq_marlin_impl.cpp:116-124)."""
+    g, n = s.shape
+    perm, single = marlin_scales_perm()
+    p = single if g == 1 else perm
+    return s.reshape(-1, len(p))[:, torch.from_numpy(p)].reshape(-1, n).contiguous()
+
+
+def unpermute_marlin_scales(s: torch.Tensor) -> torch.Tensor:
+    g, n = s.shape
+    perm, single = marlin_scales_perm()
+    p = single if g == 1 else perm
+    inv = np.empty_like(p)
+    inv[p] = np.arange(len(p))
+    return s.reshape(-1, len(p))[:, torch.from_numpy(inv)].reshape(-1, n).contiguous()
+
+
+def marlin_zero_points(z: np.ndarray) -> torch.Tensor:
+    """Natural-order zero points [G, N] (ints) -> the packed int32 [G, N/8] tensor the Marlin kernel
+    reads with has_zp=true: columns permuted like the scales, then the 4-bit interleave, then packed
+    along N (qlinear_awq_marlin_impl.cpp:84-96, after its AWQ un-interleave :64-76)."""
+    g, n = z.shape
+    perm, _ = marlin_scales_perm()
+    m = z.reshape(-1, len(perm))[:, perm]
+    m = m.reshape(-1, 8)[:, _INTERLEAVE4].reshape(g, n)
+    return pack_cols(m)
+
+
+def unpack_marlin_zero_points(packed: torch.Tensor) -> np.ndarray:
+    """inverse of marlin_zero_points -> [G, N] ints"""
+    m = unpack_cols(packed)
+    g, n = m.shape
+    inv8 = np.empty(8, dtype=np.int64)
+    inv8[_INTERLEAVE4] = np.arange(8)
+    m = m.reshape(-1, 8)[:, inv8]
+    perm, _ = marlin_scales_perm()
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    return m.reshape(-1, len(perm))[:, inv].reshape(g, n)

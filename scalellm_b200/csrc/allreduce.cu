@@ -110,6 +110,15 @@ __device__ __forceinline__ void ar_wait_flag(const uint32_t* p, uint32_t e) {
   while ((int32_t)(ld_acquire_sys(p) - e) < 0) {
   }
 }
+// debug: %globaltimer (ns, common to all SMs of a GPU; GPUs of one box agree to ~1 us) into
+// trace[block * 8 + slot] when b200_debug_set_trace installed a buffer (tools/ar_bench.py)
+__device__ __forceinline__ void ar_stamp(long long* trace, int slot) {
+  if (trace != nullptr && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    trace[(int64_t)blockIdx.x * 8 + slot] = (long long)ns;
+  }
+}
 // last block out advances the epoch (device-side state: graph replay safe)
 __device__ __forceinline__ void ar_finish(uint32_t* epoch_ptr, uint32_t e) {
   uint32_t* done_ptr = epoch_ptr + 1;
@@ -171,8 +180,10 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
                                                                       const float* partials,
                                                                       W4Plan plan, int row_n,
                                                                       int64_t split_stride,
-                                                                      ArNormArgs<T> na) {
+                                                                      ArNormArgs<T> na,
+                                                                      long long* trace) {
   constexpr int VEC = 16 / sizeof(T);
+  ar_stamp(trace, 0);
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
@@ -202,6 +213,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   }
   __threadfence_system();
   __syncthreads();
+  ar_stamp(trace, 1);
 
   // 2. tell every peer this slice of mine is ready; 3. wait for theirs
   if (threadIdx.x < world) {
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
     }
   }
   __syncthreads();
+  ar_stamp(trace, 2);
 
   // 4. reduce in rank order, write back in place (or feed the residual + RMSNorm epilogue)
   if constexpr (!NORM) {
@@ -266,6 +279,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
     }
   }
 
+  ar_stamp(trace, 5);
   ar_finish(epoch_ptr, e);
 }
 
@@ -282,9 +296,11 @@ template <typename T, int VPT, bool FROM_PARTIALS, bool NORM>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     ArDevPtrs ptrs, const T* __restrict__ data_in, T* __restrict__ data_out, int64_t nvec_total,
     int row_vecs, int rank, int world, int64_t max_bytes, const float* __restrict__ partials,
-    W4Plan plan, int row_n, int64_t split_stride, ArNormArgs<T> na) {
+    W4Plan plan, int row_n, int64_t split_stride, ArNormArgs<T> na, long long* trace) {
   constexpr int VEC = 16 / sizeof(T);
+  ar_stamp(trace, 6);
   pdl_wait();               // the contribution (and the residual stream) come from earlier kernels
+  ar_stamp(trace, 0);
   pdl_launch_dependents();  // the next GEMM may start prefetching its weights while we exchange
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
@@ -326,6 +342,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     uint32_t* f1 = reinterpret_cast<uint32_t*>(ptrs.base[owner] + ar_flags_off(max_bytes));
     st_release_sys(&f1[rank * AR_MAX_ROWS + row], e);
   }
+  ar_stamp(trace, 1);
 
   // ---- 2. the owner reduces the world slots in rank order and pushes the row to everyone ----
   uint4 red[VPT];
@@ -336,6 +353,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
       ar_wait_flag(&f1[threadIdx.x * AR_MAX_ROWS + row], e);
     }
     __syncthreads();
+    ar_stamp(trace, 2);
     const uint4* inbox = reinterpret_cast<const uint4*>(local + par_off);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
@@ -365,6 +383,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
       uint32_t* f2 = reinterpret_cast<uint32_t*>(ptrs.base[threadIdx.x] + ar_flags2_off(max_bytes));
       st_release_sys(&f2[row], e);
     }
+    ar_stamp(trace, 3);
   } else {
     // ---- 3. everyone else picks the reduced row up from its own result buffer ----
     if (threadIdx.x == 0) {
@@ -372,6 +391,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
       ar_wait_flag(&f2[row], e);
     }
     __syncthreads();
+    ar_stamp(trace, 4);
     const uint4* res = reinterpret_cast<const uint4*>(local + ar_result_off(max_bytes) + par_off);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
@@ -428,6 +448,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
       }
     }
   }
+  ar_stamp(trace, 5);
   ar_finish(epoch_ptr, e);
 }
 
@@ -605,11 +626,11 @@ static int ar_launch_twoshot(b200_ar_comm* c, const T* in, T* out, int64_t nvec,
   if (row_vecs <= AR_THREADS) {
     B200_PDL_LAUNCH_L(1, "allreduce_twoshot", (allreduce_twoshot_kernel<T, 1, FROM_PARTIALS, NORM>),
                       (unsigned)rows, AR_THREADS, sm, st, ptrs, in, out, nvec, row_vecs, c->rank, c->world,
-                      c->max_bytes, partials, plan, row_n, split_stride, na);
+                      c->max_bytes, partials, plan, row_n, split_stride, na, debug_trace_ptr());
   } else {
     B200_PDL_LAUNCH_L(1, "allreduce_twoshot", (allreduce_twoshot_kernel<T, 2, FROM_PARTIALS, NORM>),
                       (unsigned)rows, AR_THREADS, sm, st, ptrs, in, out, nvec, row_vecs, c->rank, c->world,
-                      c->max_bytes, partials, plan, row_n, split_stride, na);
+                      c->max_bytes, partials, plan, row_n, split_stride, na, debug_trace_ptr());
   }
   return B200_OK;
 }
@@ -647,6 +668,24 @@ int b200_ar_allgather(b200_ar_comm* c, void* out, const void* in, int64_t rows, 
   return B200_OK;
 }
 
+static int ar_create_one(b200_ar_comm* c, void* handle_out) {
+  B200_CUDA_OK(cudaGetDevice(&c->device));
+  void* p = nullptr;
+  B200_CUDA_OK(cudaMalloc(&p, (size_t)ar_region_bytes(c->max_bytes)));
+  c->local = static_cast<uint8_t*>(p);
+  c->peer[c->rank] = c->local;
+  B200_CUDA_OK(cudaMemset(p, 0, (size_t)ar_region_bytes(c->max_bytes)));
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  memset(handle_out, 0, B200_AR_HANDLE_BYTES);
+  if (c->world > 1) {
+    cudaIpcMemHandle_t h;
+    B200_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) <= B200_AR_HANDLE_BYTES, "handle blob too small");
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  return B200_OK;
+}
+
 int b200_ar_create(b200_ar_comm** comm, int rank, int world_size, int64_t max_bytes,
                    void* handle_out) {
   B200_CHECK_ARG(comm && handle_out, "ar_create: null pointer");
@@ -658,19 +697,12 @@ int b200_ar_create(b200_ar_comm** comm, int rank, int world_size, int64_t max_by
   c->rank = rank;
   c->world = world_size;
   c->max_bytes = max_bytes;
-  B200_CUDA_OK(cudaGetDevice(&c->device));
-  void* p = nullptr;
-  B200_CUDA_OK(cudaMalloc(&p, (size_t)ar_region_bytes(max_bytes)));
-  B200_CUDA_OK(cudaMemset(p, 0, (size_t)ar_region_bytes(max_bytes)));
-  B200_CUDA_OK(cudaDeviceSynchronize());
-  c->local = static_cast<uint8_t*>(p);
-  c->peer[rank] = c->local;
-  memset(handle_out, 0, B200_AR_HANDLE_BYTES);
-  if (world_size > 1) {
-    cudaIpcMemHandle_t h;
-    B200_CUDA_OK(cudaIpcGetMemHandle(&h, p));
-    static_assert(sizeof(h) <= B200_AR_HANDLE_BYTES, "handle blob too small");
-    memcpy(handle_out, &h, sizeof(h));
+  const int rc = ar_create_one(c, handle_out);
+  if (rc != B200_OK) {  // nothing leaks on an early error
+    if (c->local) cudaFree(c->local);
+    delete c;
+    *comm = nullptr;
+    return rc;
   }
   *comm = c;
   return B200_OK;
@@ -685,7 +717,16 @@ int b200_ar_open_peers(b200_ar_comm* c, const void* all_handles) {
     cudaIpcMemHandle_t h;
     memcpy(&h, hs + (size_t)r * B200_AR_HANDLE_BYTES, sizeof(h));
     void* p = nullptr;
-    B200_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // close what was opened so far; the communicator stays unopened
+      for (int q = 0; q < r; ++q)
+        if (q != c->rank && c->peer[q]) {
+          cudaIpcCloseMemHandle(c->peer[q]);
+          c->peer[q] = nullptr;
+        }
+      return set_error(B200_ERR_CUDA, "ar_open_peers: cudaIpcOpenMemHandle(rank %d) failed: %s", r,
+                       cudaGetErrorString(e));
+    }
     c->peer[r] = static_cast<uint8_t*>(p);
   }
   c->opened = true;
@@ -828,17 +869,17 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
     case B200_BF16:
       allreduce_oneshot_kernel<__nv_bfloat16, false><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<__nv_bfloat16*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
-          plan, (int)row_n, count, ArNormArgs<__nv_bfloat16>{});
+          plan, (int)row_n, count, ArNormArgs<__nv_bfloat16>{}, debug_trace_ptr());
       break;
     case B200_FP16:
       allreduce_oneshot_kernel<__half, false><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<__half*>(data), nvec, c->rank, c->world, c->max_bytes, partials,
-          plan, (int)row_n, count, ArNormArgs<__half>{});
+          plan, (int)row_n, count, ArNormArgs<__half>{}, debug_trace_ptr());
       break;
     default:
       allreduce_oneshot_kernel<float, false><<<blocks, AR_THREADS, 0, st>>>(
           ptrs, static_cast<float*>(data), nvec, c->rank, c->world, c->max_bytes, nullptr, W4Plan{}, 0, 0,
-          ArNormArgs<float>{});
+          ArNormArgs<float>{}, debug_trace_ptr());
       break;
   }
   B200_LAUNCH_OK("allreduce_oneshot");
@@ -889,13 +930,13 @@ int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, co
                                  static_cast<__nv_bfloat16*>(out), eps};
     allreduce_oneshot_kernel<__nv_bfloat16, true><<<blocks, AR_THREADS, (size_t)n * 4, st>>>(
         ptrs, static_cast<__nv_bfloat16*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials,
-        plan, (int)n, count, na);
+        plan, (int)n, count, na, debug_trace_ptr());
   } else {
     ArNormArgs<__half> na{static_cast<__half*>(residual), static_cast<const __half*>(weight),
                           static_cast<__half*>(out), eps};
     allreduce_oneshot_kernel<__half, true><<<blocks, AR_THREADS, (size_t)n * 4, st>>>(
         ptrs, static_cast<__half*>(nullptr), nvec, c->rank, c->world, c->max_bytes, partials, plan,
-        (int)n, count, na);
+        (int)n, count, na, debug_trace_ptr());
   }
   B200_LAUNCH_OK("allreduce_oneshot_norm");
   return B200_OK;

@@ -48,6 +48,7 @@ inline bool is_aligned(const void* p, size_t a) {
 }
 
 int sm_count();  // cached multiProcessorCount of the current device
+long long* debug_trace_ptr();  // b200_debug_set_trace buffer (nullptr = off): per-CTA timestamps
 
 // Programmatic dependent launch.  B200_PDL = 0: off; 1 (default): the W4A16 GEMM and the kernels
 // that consume its partials are launched with the programmatic-stream-serialization attribute:
@@ -417,7 +418,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
 // An "n tile" of the partition is 128 << nsub_log2 output columns (two weight tiles share one
 // activation stage when the batch fits 64 rows, halving the activation traffic out of L2).
 // ---------------------------------------------------------------------------
-// [w4-emu:plan begin]
 struct W4Plan {
   int units, P, KT, NT, slots;  // slots = max contributors of any tile (partials buffer depth)
   int nsub_log2;                // 128-column weight tiles per n tile of the partition: 1 << nsub_log2
@@ -425,13 +425,13 @@ struct W4Plan {
 __host__ __device__ __forceinline__ int w4_unit_begin(int p, int units, int P) {
   return (int)(((long long)p * units) / P);
 }
-// CTA that owns unit u (largest p with begin(p) <= u)
+// CTA that owns unit u: the largest p with begin(p) <= u.  floor(p * units / P) <= u  <=>
+// p * units < (u + 1) * P  <=>  p <= floor(((u + 1) * P - 1) / units) — exact, one division (the
+// consumers evaluate this per 32-byte group of a row: 32-bit arithmetic, units * P < 2^31 always:
+// units <= 2^16 tiles per GEMM would need a 1M x 1M weight).
 __host__ __device__ __forceinline__ int w4_owner(int u, int units, int P) {
-  int p = (int)((((long long)u + 1) * P - 1) / units);
-  if (p > P - 1) p = P - 1;
-  while (p > 0 && w4_unit_begin(p, units, P) > u) --p;
-  while (p + 1 < P && w4_unit_begin(p + 1, units, P) <= u) ++p;
-  return p;
+  const unsigned p = ((unsigned)(u + 1) * (unsigned)P - 1u) / (unsigned)units;
+  return p > (unsigned)(P - 1) ? P - 1 : (int)p;
 }
 __host__ __device__ __forceinline__ int w4_first_owner(const W4Plan& pl, int nt) {
   return w4_owner(nt * pl.KT, pl.units, pl.P);
@@ -443,7 +443,6 @@ __host__ __device__ __forceinline__ int w4_contrib(const W4Plan& pl, int nt) {
 __host__ __device__ __forceinline__ int w4_contrib_col(const W4Plan& pl, int col) {
   return w4_contrib(pl, col >> (7 + pl.nsub_log2));
 }
-// [w4-emu:plan end]
 constexpr int W4_MAX_SLOTS = 8;
 // The partition b200_w4a16_gemm_splitk uses for M rows x a [K, N] weight on the current device.
 W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M);
@@ -457,26 +456,30 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 
 // Sum of the partial slots of 8 consecutive columns (one 32-byte group inside one n tile) of
-// row `row_ptr`: all loads are issued up front (one L2 round trip), fixed summation order.
+// row `row_ptr`: the loads of the `count` contributing slots are all issued up front (one L2 round
+// trip; absent slots are neither loaded — they may hold stale NaNs — nor added), fixed summation
+// order ((p0 + p1) + p2) + ...  Round 1 loaded all 8 slots with the absent ones clamped onto the
+// last one: 4x the L2 traffic at the usual 2 contributors — the gate_up consumer spent 14.7 us
+// on it (profiles/r02_step_timeline.md).
 __device__ __forceinline__ void w4_sum_partials8(float (&a)[8], const float* __restrict__ p0,
                                                  int64_t slot_stride, int count) {
   float4 lo[W4_MAX_SLOTS], hi[W4_MAX_SLOTS];
 #pragma unroll
   for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
-    const int spc = sp < count ? sp : count - 1;  // clamped; the duplicate is weighted 0 below
-    const float4* src = reinterpret_cast<const float4*>(p0 + spc * slot_stride);
-    lo[sp] = __ldcg(src);
-    hi[sp] = __ldcg(src + 1);
+    if (sp < count) {
+      const float4* src = reinterpret_cast<const float4*>(p0 + sp * slot_stride);
+      lo[sp] = __ldcg(src);
+      hi[sp] = __ldcg(src + 1);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.f;
 #pragma unroll
   for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
-    const float wgt = sp < count ? 1.f : 0.f;
-    a[0] = fmaf(lo[sp].x, wgt, a[0]); a[1] = fmaf(lo[sp].y, wgt, a[1]);
-    a[2] = fmaf(lo[sp].z, wgt, a[2]); a[3] = fmaf(lo[sp].w, wgt, a[3]);
-    a[4] = fmaf(hi[sp].x, wgt, a[4]); a[5] = fmaf(hi[sp].y, wgt, a[5]);
-    a[6] = fmaf(hi[sp].z, wgt, a[6]); a[7] = fmaf(hi[sp].w, wgt, a[7]);
+    if (sp < count) {
+      a[0] += lo[sp].x; a[1] += lo[sp].y; a[2] += lo[sp].z; a[3] += lo[sp].w;
+      a[4] += hi[sp].x; a[5] += hi[sp].y; a[6] += hi[sp].z; a[7] += hi[sp].w;
+    }
   }
 }
 

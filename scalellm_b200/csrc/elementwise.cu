@@ -274,32 +274,56 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
     const int32_t* __restrict__ slot_ids, T* __restrict__ k_cache, T* __restrict__ v_cache,
     int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
     int64_t k_stride, int64_t v_stride, bool interleaved, RopePartials parts) {
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int VEC = 16 / sizeof(T);
   const int64_t tok = blockIdx.x;
+  // positions / slot ids / the cos|sin table are step inputs and model constants, older than the
+  // predecessor kernel: fetch them before griddepcontrol.wait so their latency overlaps its tail
+  const int half = rotary_dim / 2;
+  const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
+  const int64_t slot = FUSE_KV ? static_cast<int64_t>(slot_ids[tok]) : 0;
+  extern __shared__ __align__(16) uint8_t rope_smem[];  // FROM_PARTIALS: the token's [q|k|v] row in T
+  T* row_s = reinterpret_cast<T*>(rope_smem);
+  pdl_wait();
+  pdl_launch_dependents();
   if constexpr (FROM_PARTIALS) {
     // Materialise this token's qkv row first: x = T(sum of the tile's partial slots), the one
     // rounding the GEMM epilogue would have done; q, k, v are views of that row (host-checked).
+    // Three vectors per thread per round so that all their partial loads are in flight together;
+    // the row also stays in shared memory for the rotation below (no global re-read).
     static_assert(sizeof(T) == 2, "partials input: 16-bit element types");
     T* row = q + tok * q_stride;
     const float* prow = parts.data + tok * parts.row_n;
-    for (int vv = threadIdx.x; vv < parts.row_n / 8; vv += blockDim.x) {
-      float a[8];
-      w4_sum_partials8(a, prow + vv * 8, parts.slot_stride, w4_contrib_col(parts.plan, vv * 8));
-      uint4 o;
-      T* oe = reinterpret_cast<T*>(&o);
+    const int nv = parts.row_n / 8;
+    for (int v0 = threadIdx.x; v0 < nv; v0 += 3 * blockDim.x) {
+      float a[3][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) oe[i] = Num<T>::from_f(a[i]);
-      st_v4(row + vv * 8, o);
+      for (int u = 0; u < 3; ++u) {
+        const int vv = v0 + u * blockDim.x;
+        if (vv < nv)
+          w4_sum_partials8(a[u], prow + vv * 8, parts.slot_stride, w4_contrib_col(parts.plan, vv * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int vv = v0 + u * blockDim.x;
+        if (vv < nv) {
+          uint4 o;
+          T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) oe[i] = Num<T>::from_f(a[u][i]);
+          st_v4(row + vv * 8, o);
+          st_v4(row_s + vv * 8, o);
+        }
+      }
     }
     __syncthreads();  // the row is re-read below by other threads of this CTA
   }
-  const int half = rotary_dim / 2;
-  const T* cs = cos_sin + static_cast<int64_t>(positions[tok]) * rotary_dim;
+  // source of the un-rotated values: the row in shared memory (offsets relative to q's row start:
+  // q, k, v are views of one [q|k|v] row) or global memory
+  const T* q_src = FROM_PARTIALS ? row_s : q + tok * q_stride;
+  const T* k_src = FROM_PARTIALS ? row_s + (k - q) : k + tok * k_stride;
+  const T* v_src = FROM_PARTIALS ? row_s + (v - q) : v + tok * v_stride;
   const T* cosp = cs;
   const T* sinp = cs + half;
-  const int64_t slot = FUSE_KV ? static_cast<int64_t>(slot_ids[tok]) : 0;
   T* kc_row = FUSE_KV ? k_cache + slot * n_kv_heads * head_dim : nullptr;
   T* vc_row = FUSE_KV ? v_cache + slot * n_kv_heads * head_dim : nullptr;
 
@@ -312,9 +336,11 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
     const bool is_k = h >= n_heads;
     T* base = is_k ? k + tok * k_stride + static_cast<int64_t>(h - n_heads) * head_dim
                    : q + tok * q_stride + static_cast<int64_t>(h) * head_dim;
+    const T* src = is_k ? k_src + static_cast<int64_t>(h - n_heads) * head_dim
+                        : q_src + static_cast<int64_t>(h) * head_dim;
     T* cdst = (FUSE_KV && is_k) ? kc_row + static_cast<int64_t>(h - n_heads) * head_dim : nullptr;
     if (!interleaved) {
-      uint4 xr = ld_v4(base + j * VEC), yr = ld_v4(base + half + j * VEC);
+      uint4 xr = ld_v4(src + j * VEC), yr = ld_v4(src + half + j * VEC);
       uint4 cr = ld_v4(cosp + j * VEC), sr = ld_v4(sinp + j * VEC);
       const T* x = reinterpret_cast<const T*>(&xr);
       const T* y = reinterpret_cast<const T*>(&yr);
@@ -334,7 +360,7 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
         st_v4(cdst + half + j * VEC, oyr);
       }
     } else {
-      uint4 pr = ld_v4(base + j * VEC);
+      uint4 pr = ld_v4(src + j * VEC);
       const T* p = reinterpret_cast<const T*>(&pr);
       uint4 outr;
       T* o = reinterpret_cast<T*>(&outr);
@@ -354,13 +380,13 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
     for (int it = threadIdx.x; it < n_kv_heads * tail_vecs; it += blockDim.x) {
       const int h = it / tail_vecs, j = it % tail_vecs;
       const int64_t off = static_cast<int64_t>(h) * head_dim + rotary_dim + j * VEC;
-      st_v4(kc_row + off, ld_v4(k + tok * k_stride + off));
+      st_v4(kc_row + off, ld_v4(k_src + off));
     }
     const int v_vecs = n_kv_heads * head_dim / VEC;
     for (int it = threadIdx.x; it < v_vecs; it += blockDim.x)
       st_v4(vc_row + static_cast<int64_t>(it) * VEC,
-            FROM_PARTIALS ? ld_v4(v + tok * v_stride + it * VEC)   // written above by this CTA
-                          : ld_nc_v4(v + tok * v_stride + it * VEC));
+            FROM_PARTIALS ? ld_v4(v_src + it * VEC)               // this CTA's shared-memory row
+                          : ld_nc_v4(v_src + it * VEC));
   }
 }
 
@@ -428,7 +454,10 @@ static int launch_rope(void* q, void* k, const void* v, const int32_t* positions
     if (parts) {
       if (!vec_ok)
         return set_error(B200_ERR_UNSUPPORTED, "rope_kv_write_splitk: needs the vectorised layout");
-      B200_PDL_LAUNCH_L(1, "rope", (rope_vec_kernel<T, true, true>), grid, 256, 0, st, qq, kk, vv,
+      const size_t row_bytes = (size_t)parts->row_n * sizeof(T);   // the [q|k|v] row in shared memory
+      if (row_bytes > 48 * 1024)
+        return set_error(B200_ERR_UNSUPPORTED, "rope_kv_write_splitk: qkv row of %zu bytes exceeds 48 KB", row_bytes);
+      B200_PDL_LAUNCH_L(1, "rope", (rope_vec_kernel<T, true, true>), grid, 256, row_bytes, st, qq, kk, vv,
                       positions, cs, slot_ids, kc, vc, (int)n_heads, (int)n_kv_heads,
                       (int)head_dim, (int)rotary_dim, q_stride, k_stride, v_stride,
                       interleaved != 0, *parts);

@@ -233,8 +233,6 @@ __global__ void __launch_bounds__(128) w4_gemm_simt_kernel(
 // ===========================================================================
 // tcgen05 stream-K GEMM (partials out)
 // ===========================================================================
-// [w4-emu:cfg begin]  (tools/w4_emu.cpp compiles this block, the barrier initialisation and the
-// role code of the kernel for the host)
 template <int MT, int NSUB>
 struct W4Cfg {
   static constexpr int ACT_STAGES = MT <= 64 ? 6 : 3;   // activation ring (L2 / TMA latency)
@@ -300,7 +298,6 @@ struct SegIter {
     return true;
   }
 };
-// [w4-emu:cfg end]
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 r;
@@ -324,24 +321,10 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // bytes pulled out of L2 per weight tile drop by NSUB (the kernel is L2-bandwidth bound on them:
 // every CTA re-reads the [MT x 128] activation tile of each of its k tiles).
 //
-// VAR (experiments on the MMA thread's per-tile cost, B200_W4_VARIANT; 0 = default; a bit mask).
-// With one weight tile per unit the activation ring and the dequantised-weight ring have the same
-// depth, so stage == slot for every tile and one barrier can release both:
-//   1: one tcgen05.commit per tile (the activation producer waits on the slot's deq_empty barrier)
-//   2: tiles are issued in aligned pairs: one tcgen05.fence + one commit per two tiles (pair
-//      barrier deq_empty[pair % 3]; both producers wait on it)
-//   4: three dequant groups instead of four (12 warps dequantise as fast as 16,
-//      tools/microbench/deq.cu, and the MMA warp then shares its scheduler with three of them);
-//      combines with 2 as 6
-//   8: one "full" barrier per stage: the activation TMA completes on the slot's deq_full barrier
-//      (4 dequant arrivals + the producer's expect_tx arrival + the bytes), so the MMA thread
-//      waits once per tile instead of twice; combines with 2 (10) and 2 + 4 (14)
-//  16: two MMA-issuing warps (18 and the otherwise idle 19): warp 18 + i takes the tiles with
-//      cnt % 2 == i and accumulates them into its own accumulator [128 x MT] (the two TMEM regions
-//      that double-buffer the default kernel's accumulator, single-buffered here, so the slot
-//      ring keeps its 6 entries); the epilogue adds the two accumulators in a fixed order.  Halves
-//      the per-tile work of an issuing thread; combines with 4 (20), 8 (24) and both (28)
-template <int MT, int NSUB, bool TRACE, int VAR = 0>
+// Round 2 measured ten variants of the MMA loop (one commit per tile, tiles issued in pairs, three
+// dequant groups, one "full" barrier per stage, two issuing warps and their combinations): all
+// within 3 % of this form on every projection shape (profiles/r02_w4_variants.md), so they are gone.
+template <int MT, int NSUB, bool TRACE>
 __global__ void __launch_bounds__(W4_THREADS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   using Cfg = W4Cfg<MT, NSUB>;
@@ -349,11 +332,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   // is sound only while no group can get a whole ring ahead of a blob that has not landed; the
   // TMEM slot ring bounds a group's lead over the in-order MMA issuer to (groups + slots) tiles.
   static_assert(Cfg::RAW_STAGES > W4_DEQ_GROUPS + Cfg::A_STAGES, "weight ring too shallow for the slot ring");
-  static_assert((VAR & 3) != 3 && VAR < 32 && (!(VAR & 16) || !(VAR & 3)),
-                "VAR: 1 and 2 are alternatives, and neither combines with 16");
-  static_assert(VAR == 0 || (NSUB == 1 && Cfg::ACT_STAGES == Cfg::A_STAGES && Cfg::A_STAGES == 6 &&
-                             Cfg::ACC_BUFS == 2 && !TRACE),
-                "variants need stage == slot");
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -379,29 +357,44 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   const int u_begin = w4_unit_begin(blockIdx.x, p.plan.units, p.plan.P);
   const int u_end = w4_unit_begin(blockIdx.x + 1, p.plan.units, p.plan.P);
 
-  if (threadIdx.x == 0) {
-    // [w4-emu:init begin]
+  // The weight ring belongs to the producer warp: it initialises the ring's barriers itself and
+  // puts the first RAW_STAGES blobs in flight BEFORE the CTA-wide set-up (TMEM allocation, the
+  // other barriers, the __syncthreads below) — the first HBM request leaves at ~200 instead of
+  // ~1500 cycles after the CTA starts (profiles/r02_w4_trace.md: setup_done 1470).  Weights are
+  // never written by another kernel, so no griddepcontrol.wait either.  The dequant warps learn
+  // of the initialised barriers through the __syncthreads.
+  int raw_pre = 0;  // weight tiles already requested by the prologue (warp W4_WARP_RAW, lane 0)
+  if (warp == W4_WARP_RAW && lane == 0) {
     for (int i = 0; i < Cfg::RAW_STAGES; ++i) {
       mbar_init(&raw_full[i], 1);
       mbar_init(&raw_empty[i], 4);
     }
+    fence_mbar_init();
+    SegIter it{u_begin, u_end, KT};
+    int nt, kt0, kt1;
+    while (raw_pre < Cfg::RAW_STAGES && it.next(nt, kt0, kt1)) {
+      for (int kt = kt0; kt < kt1 && raw_pre < Cfg::RAW_STAGES; ++kt)
+        for (int sub = 0; sub < NSUB && raw_pre < Cfg::RAW_STAGES; ++sub, ++raw_pre) {
+          mbar_arrive_expect_tx(&raw_full[raw_pre], (uint32_t)p.blob_bytes);
+          bulk_load_1d(raw_smem + raw_pre * Cfg::RAW_BYTES,
+                       p.packed + ((int64_t)(nt * NSUB + sub) * KT + kt) * p.blob_bytes,
+                       (uint32_t)p.blob_bytes, &raw_full[raw_pre]);
+        }
+    }
+  }
+  if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::ACT_STAGES; ++i) {
       mbar_init(&act_full[i], 1);
       mbar_init(&act_empty[i], 1);
     }
     for (int i = 0; i < Cfg::A_STAGES; ++i) {
-      mbar_init(&deq_full[i], (VAR & 8) ? 5 : 4);
+      mbar_init(&deq_full[i], 4);
       mbar_init(&deq_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], (VAR & 16) ? 2 : 1);
+      mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
-    if constexpr (VAR & 16) {  // tiles issued so far by each of the two MMA issuers
-      reinterpret_cast<volatile int*>(tmem_holder + 2)[0] = 0;
-      reinterpret_cast<volatile int*>(tmem_holder + 2)[1] = 0;
-    }
-    // [w4-emu:init end]
     fence_mbar_init();
   }
   if (warp == W4_WARP_MMA) {
@@ -415,7 +408,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
   const uint32_t tmem_base = *tmem_holder;
   if (threadIdx.x == 0) W4_TRACE(1);
 
-  // [w4-emu:roles begin]
   if (warp < W4_DEQ_WARPS) {
     // ===================== dequant warps =====================================
     // group = warp / 4 takes weight tiles cnt % 4 == group; tile cnt goes to TMEM slot
@@ -434,26 +426,13 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     while (it.next(nt, kt0, kt1)) {
       for (int kt = kt0; kt < kt1; ++kt)
       for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
-        if constexpr (VAR & 4) {
-          if (cnt % 3 != group) continue;  // group 3 (warps 12-15) takes nothing
-        } else {
-          if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
-        }
+        if ((cnt & (W4_DEQ_GROUPS - 1)) != group) continue;
         const int rs = cnt % Cfg::RAW_STAGES;
         const int as = cnt % Cfg::A_STAGES;
         const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1, aph = (cnt / Cfg::A_STAGES) & 1;
         const uint32_t raw = raw_u32 + rs * Cfg::RAW_BYTES;
         const uint32_t a_tmem = a_lane + as * 64;
         long long tw = TRACE ? clock64() : 0;
-        if constexpr (VAR & 16) {
-          // Two issuers: wait for the TMEM slot BEFORE touching the weight blob.  The raw_full wait
-          // below goes by the parity of the ring entry's use count, which is only sound if the
-          // entry's previous blob (tile cnt - 11) has landed.  With one in-order issuer the slot
-          // wait of this group's previous tile guarantees that (tile cnt - 10 consumed => cnt - 11
-          // issued); with two issuers bounded to a drift of 3 tiles it takes this tile's own slot
-          // (tile cnt - 6 consumed => the other issuer is past cnt - 9).
-          mbar_wait(&deq_empty[as], aph ^ 1);
-        }
         mbar_wait(&raw_full[rs], rph);
         if (TRACE) w_raw += clock64() - tw;
         if (TRACE && threadIdx.x == 0 && cnt == 0) W4_TRACE(2);
@@ -487,12 +466,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           }
           if (hh == 0) {  // the MMAs that read this slot's previous tile must have drained
             tw = TRACE ? clock64() : 0;
-            if constexpr (VAR & 2) {
-              const int pr = cnt >> 1;
-              mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
-            } else {
-              mbar_wait(&deq_empty[as], aph ^ 1);
-            }
+            mbar_wait(&deq_empty[as], aph ^ 1);
             if (TRACE) w_slot += clock64() - tw;
             tc_fence_after();
           }
@@ -524,6 +498,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       while (it.next(nt, kt0, kt1)) {
         for (int kt = kt0; kt < kt1; ++kt)
         for (int sub = 0; sub < NSUB; ++sub, ++cnt) {
+          if (cnt < raw_pre) continue;  // requested by the prologue above
           const int rs = cnt % Cfg::RAW_STAGES;
           const uint32_t rph = (cnt / Cfg::RAW_STAGES) & 1;
           mbar_wait(&raw_empty[rs], rph ^ 1);
@@ -545,15 +520,8 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
         for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
           const int as = cnt % Cfg::ACT_STAGES;
           const uint32_t aph = (cnt / Cfg::ACT_STAGES) & 1;
-          if constexpr ((VAR & 3) == 0) {
-            mbar_wait(&act_empty[as], aph ^ 1);
-          } else if constexpr ((VAR & 3) == 1) {
-            mbar_wait(&deq_empty[as], aph ^ 1);  // stage == slot: released by the slot's commit
-          } else {
-            const int pr = cnt >> 1;
-            mbar_wait(&deq_empty[pr % 3], ((pr / 3) & 1) ^ 1);
-          }
-          uint64_t* full = (VAR & 8) ? &deq_full[as] : &act_full[as];
+          mbar_wait(&act_empty[as], aph ^ 1);
+          uint64_t* full = &act_full[as];
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::ACT_BYTES);
           uint8_t* dst = act_smem + as * Cfg::ACT_BYTES;
           tma_load_2d(dst, &amap, full, kt * 128, 0);
@@ -562,65 +530,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
       }
     }
     __syncwarp();
-  } else if ((VAR & 16) != 0 && (warp == W4_WARP_MMA || warp == W4_WARP_MMA + 1)) {
-    // ===================== two MMA issuers (VAR & 16) ==========================
-    // Issuer `me` takes the tiles with cnt % 2 == me into accumulator `me`.  Every segment both
-    // issuers first wait until the epilogue has drained the previous one (also an issuer without a
-    // tile in this segment: its arrival below must not count towards the previous segment), then
-    // each arrives once on tmem_full: through a commit behind its last MMAs, or directly if it
-    // had no tile.
-    // The issuers may not drift apart: a dequant group waits for its weight blob by the parity of
-    // the ring entry's use count, which is only sound while nobody gets a whole ring (11 tiles)
-    // ahead of a blob that has not landed.  One in-order issuer bounds that lead by the 6 TMEM
-    // slots; two independent ones do not (the odd tiles could run on while an even tile's blob
-    // is late — found by the host emulation, tools/w4_emu.py).  So an issuer takes tile cnt only
-    // once the other one has issued tile cnt - 3, and the dequant groups wait for their TMEM slot
-    // before they read the blob (see there): lead <= 6 + 3 < 11.
-    volatile int* issued = reinterpret_cast<volatile int*>(tmem_holder + 2);  // [2]: tiles issued + 1
-    constexpr uint32_t idesc = umma_idesc_bf16(128, MT);
-    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
-    const int me = warp - W4_WARP_MMA;
-    const uint32_t d_tmem = tbase + me * MT;
-    SegIter it{u_begin, u_end, KT};
-    int nt, kt0, kt1, cnt = 0, seg = 0;
-    while (it.next(nt, kt0, kt1)) {
-      mbar_wait(&tmem_empty[0], (seg & 1) ^ 1);
-      tc_fence_after();
-      uint32_t started = 0;  // 0: my next MMA overwrites my accumulator
-      for (int kt = kt0; kt < kt1; ++kt, ++cnt) {
-        if ((cnt & 1) != me) continue;
-        while (issued[1 - me] < cnt - 2) {  // the other issuer is more than 3 tiles behind
-        }
-        const int ds = cnt % Cfg::A_STAGES;  // == activation stage (one weight tile per unit)
-        const uint32_t dph = (cnt / Cfg::A_STAGES) & 1;
-        if constexpr (!(VAR & 8)) mbar_wait(&act_full[ds], dph);
-        mbar_wait(&deq_full[ds], dph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + ds * Cfg::ACT_BYTES);
-          const uint32_t a_tmem = tbase + Cfg::A_COL0 + ds * 64;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t b_desc =
-                b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
-            umma_bf16_ts(d_tmem, a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : started);
-          }
-          umma_commit(&deq_empty[ds]);
-          umma_commit(&act_empty[ds]);
-          issued[me] = cnt + 1;
-        }
-        __syncwarp();
-        started = 1u;
-      }
-      if (started) {
-        if (elect_one()) umma_commit(&tmem_full[0]);
-      } else if (lane == 0) {
-        mbar_arrive(&tmem_full[0]);
-      }
-      __syncwarp();
-      ++seg;
-    }
   } else if (warp == W4_WARP_MMA) {
     // ===================== MMA issuer =========================================
     // The whole warp runs this loop converged so every operand is warp-uniform; one elected lane
@@ -634,54 +543,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t act_base = __shfl_sync(0xffffffffu, smem_u32(act_smem), 0);
     long long w_act = 0, w_deq = 0, w_acc = 0;  // TRACE: cycles spent waiting per barrier kind
-    if constexpr (VAR & 2) {
-      // tiles in aligned pairs (cnt even): slots (cnt % 6, cnt % 6 + 1), pair barrier (cnt / 2) % 3
-      SegIter it{u_begin, u_end, KT};
-      const int total = u_end - u_begin;
-      int nt, kt0 = 0, kt1 = 0, kt = 0, seg = -1;
-      for (int cnt = 0; cnt < total; cnt += 2) {
-        const int n = min(2, total - cnt);
-        uint32_t d_tmem[2], first[2], last[2], slot[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (j < n) {
-            if (kt == kt1) {  // next segment: its accumulator buffer must have been drained
-              it.next(nt, kt0, kt1);
-              kt = kt0;
-              ++seg;
-              mbar_wait(&tmem_empty[seg & 1], ((seg >> 1) & 1) ^ 1);
-            }
-            d_tmem[j] = tbase + (seg & 1) * MT;
-            first[j] = kt > kt0 ? 1u : 0u;
-            last[j] = kt == kt1 - 1 ? (uint32_t)(seg & 1) + 1u : 0u;  // 0 / buffer + 1
-            ++kt;
-            slot[j] = (uint32_t)((cnt + j) % Cfg::A_STAGES);
-            const uint32_t ph = ((cnt + j) / Cfg::A_STAGES) & 1;
-            if constexpr (!(VAR & 8)) mbar_wait(&act_full[slot[j]], ph);
-            mbar_wait(&deq_full[slot[j]], ph);
-          }
-        }
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (j < n) {
-              const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + slot[j] * Cfg::ACT_BYTES);
-              const uint32_t a_tmem = tbase + Cfg::A_COL0 + slot[j] * 64;
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t b_desc =
-                    b_desc0 + (uint64_t)(((ks >> 2) * Cfg::ACT_ATOM + (ks & 3) * 32) >> 4);
-                umma_bf16_ts(d_tmem[j], a_tmem + ks * 8, b_desc, idesc, ks > 0 ? 1u : first[j]);
-              }
-              if (last[j]) umma_commit(&tmem_full[last[j] - 1]);
-            }
-          }
-          umma_commit(&deq_empty[(cnt >> 1) % 3]);
-        }
-        __syncwarp();
-      }
-    } else {
+    {
       SegIter it{u_begin, u_end, KT};
       int nt, kt0, kt1, cnt = 0, ucnt = 0, seg = 0;
       while (it.next(nt, kt0, kt1)) {
@@ -695,7 +557,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
           const int as = ucnt % Cfg::ACT_STAGES;
           const uint32_t aph = (ucnt / Cfg::ACT_STAGES) & 1;
           tw = TRACE ? clock64() : 0;
-          if constexpr (!(VAR & 8)) mbar_wait(&act_full[as], aph);
+          mbar_wait(&act_full[as], aph);
           if (TRACE) w_act += clock64() - tw;
           const uint64_t b_desc0 = umma_desc_kmajor_sw128(act_base + as * Cfg::ACT_BYTES);
           const uint32_t first = (kt > kt0) ? 1u : 0u;
@@ -720,7 +582,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
               }
               umma_commit(&deq_empty[ds]);
               if (sub == NSUB - 1) {
-                if constexpr ((VAR & 3) == 0) umma_commit(&act_empty[as]);
+                umma_commit(&act_empty[as]);
                 if (kt == kt1 - 1) umma_commit(&tmem_full[buf]);
               }
             }
@@ -748,47 +610,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     pdl_wait();  // the partials buffer may still be read by an earlier kernel's consumer
     SegIter it{u_begin, u_end, KT};
     int nt, kt0, kt1, seg = 0;
-    if constexpr (VAR & 16) {
-      // two accumulators per segment (tiles cnt even / odd), one of them unused when the segment
-      // is a single tile: partial = acc0 + acc1 in that order
-      int cnt0 = 0;  // tiles of this CTA before the segment
-      while (it.next(nt, kt0, kt1)) {
-        const int len = kt1 - kt0;
-        const bool has0 = len >= 2 || (cnt0 & 1) == 0, has1 = len >= 2 || (cnt0 & 1) == 1;
-        const int slot = (int)blockIdx.x - w4_first_owner(p.plan, nt);
-        float* part = p.partials + (int64_t)slot * p.slot_stride + (int64_t)nt * 128 + n_local;
-        mbar_wait(&tmem_full[0], seg & 1);
-        if (it.u >= it.u1 && warp == W4_WARP_EPI && lane == 0) pdl_launch_dependents();
-        tc_fence_after();
-        constexpr int CH = MT >= 32 ? 32 : 16;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < MT; c0 += CH) {
-          uint32_t r0[CH], r1[CH];
-#pragma unroll
-          for (int i = 0; i < CH; ++i) r0[i] = r1[i] = 0u;  // +0.0f
-          if (has0) {
-            if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r0);
-            else tmem_ld_32x32b_x16(taddr + c0, r0);
-          }
-          if (has1) {
-            if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + MT + c0, r1);
-            else tmem_ld_32x32b_x16(taddr + MT + c0, r1);
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const int m = c0 + i;
-            if (m < p.M) part[(int64_t)m * p.N] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[0]);
-        cnt0 += len;
-        ++seg;
-      }
-    } else
     while (it.next(nt, kt0, kt1)) {
       const int buf = Cfg::ACC_BUFS == 2 ? (seg & 1) : 0;
       const uint32_t tph = (Cfg::ACC_BUFS == 2 ? (seg >> 1) : seg) & 1;
@@ -824,7 +645,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap amap, const W4Params p) {
     }
     if (warp == W4_WARP_EPI && lane == 0) W4_TRACE(7);
   }
-  // [w4-emu:roles end]
 
   tc_fence_before();
   __syncthreads();
@@ -918,24 +738,14 @@ static int get_act_tensor_map(const AMapKey& key, CUtensorMap* out) {
 }
 
 static long long* g_w4_trace = nullptr;
+long long* debug_trace_ptr() { return g_w4_trace; }
 
 static int pick_mt(int64_t M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
 
-// B200_W4_VARIANT = 1 | 2 | 4 | 6 | 10 | 14 | 16 | 20 | 24 | 28: experimental variants of the kernel (see VAR above); only for
-// batches <= 64 rows with one weight tile per unit, everything else runs the default kernel
-static int w4_variant() {
-  static const int v = [] {
-    const char* e = getenv("B200_W4_VARIANT");
-    const int v = e ? atoi(e) : 0;
-    return (v == 1 || v == 2 || v == 4 || v == 6 || v == 10 || v == 14 || v == 16 || v == 20 || v == 24 || v == 28) ? v : 0;
-  }();
-  return v;
-}
-
-template <int MT, int NSUB, bool TRACE, int VAR = 0>
+template <int MT, int NSUB, bool TRACE>
 static int launch_w4_kernel(const CUtensorMap& amap, const W4Params& p, cudaStream_t st) {
   using Cfg = W4Cfg<MT, NSUB>;
-  auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE, VAR>;
+  auto kern = w4a16_gemm_kernel<MT, NSUB, TRACE>;
   B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)Cfg::SMEM));
   B200_PDL_LAUNCH_L(1, "w4a16_gemm", kern, (unsigned)p.plan.P, W4_THREADS, Cfg::SMEM, st, amap, p);
@@ -948,21 +758,6 @@ static int launch_w4_gemm(const CUtensorMap& amap, const W4Params& p, cudaStream
     if (p.plan.nsub_log2 == 1)
       return p.trace ? launch_w4_kernel<MT, 2, true>(amap, p, st)
                      : launch_w4_kernel<MT, 2, false>(amap, p, st);
-    if (!p.trace) {
-      switch (w4_variant()) {
-        case 1: return launch_w4_kernel<MT, 1, false, 1>(amap, p, st);
-        case 2: return launch_w4_kernel<MT, 1, false, 2>(amap, p, st);
-        case 4: return launch_w4_kernel<MT, 1, false, 4>(amap, p, st);
-        case 6: return launch_w4_kernel<MT, 1, false, 6>(amap, p, st);
-        case 10: return launch_w4_kernel<MT, 1, false, 10>(amap, p, st);
-        case 14: return launch_w4_kernel<MT, 1, false, 14>(amap, p, st);
-        case 16: return launch_w4_kernel<MT, 1, false, 16>(amap, p, st);
-        case 20: return launch_w4_kernel<MT, 1, false, 20>(amap, p, st);
-        case 24: return launch_w4_kernel<MT, 1, false, 24>(amap, p, st);
-        case 28: return launch_w4_kernel<MT, 1, false, 28>(amap, p, st);
-        default: break;
-      }
-    }
   }
   return p.trace ? launch_w4_kernel<MT, 1, true>(amap, p, st)
                  : launch_w4_kernel<MT, 1, false>(amap, p, st);
@@ -989,6 +784,7 @@ static W4Plan w4_make_plan(int64_t N, int64_t K, int nsub_log2, int ctas) {
   if (Pc > pl.units) Pc = pl.units;
   if (Pc > cap) Pc = (int)cap;
   if (Pc < 1) Pc = 1;
+  while ((long long)pl.units * Pc >= (1ll << 31)) Pc /= 2;  // w4_owner's 32-bit arithmetic (never in practice)
   pl.P = Pc;
   pl.slots = 1;
   for (int nt = 0; nt < pl.NT; ++nt) {

@@ -174,13 +174,16 @@ class LlamaDecoder:
 
     # -- forward -------------------------------------------------------------------
     def forward(self, tokens: torch.Tensor, positions: torch.Tensor, params: InputParameters,
-                last_token_idxes: Optional[torch.Tensor] = None, greedy: bool = False) -> torch.Tensor:
+                last_token_idxes: Optional[torch.Tensor] = None, greedy: bool = False,
+                return_hidden: bool = False) -> torch.Tensor:
         """Returns logits [n_tokens, vocab] (llama.h:220-232 then :281-289); with
         last_token_idxes only those rows go through the final norm's output -> lm_head
         (the reference's `h.index_select(0, last_token_idxes)` for prefill chunks).
         greedy=True returns the sampled token ids [n_tokens] int64 instead (argmax of the logits);
         under tensor parallelism the vocabulary-sharded logits are never gathered — local argmax
-        plus an 8-byte exchange per rank and row (ProcessGroup.argmax_sharded), same ids."""
+        plus an 8-byte exchange per rank and row (ProcessGroup.argmax_sharded), same ids.
+        return_hidden=True returns (logits, residual stream after the last layer) — for layer-level
+        parity tests against the reference's kernels."""
         h = self.embed.index_select(0, tokens)
         if self.pa.world_size > 1:  # ParallelEmbedding: split on hidden + all-gather (embedding.h:74-79)
             h = gather_from_model_parallel_region(h, self.pa)
@@ -226,6 +229,8 @@ class LlamaDecoder:
             hn = self.final_norm(h)
         else:
             hn = norm_residual(self.final_norm, pending, pending_is_partials)
+        if return_hidden:   # h now holds the residual stream after the last block's add
+            return self.lm_head(hn), h
         if last_token_idxes is not None:
             hn = hn.index_select(0, last_token_idxes)
         if greedy:

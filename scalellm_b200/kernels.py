@@ -59,12 +59,18 @@ def _check_i32(*ts: torch.Tensor) -> None:
 # op once eagerly, exactly like the reference warms its kernels before capture.
 # ---------------------------------------------------------------------------
 _WS: Dict[Tuple[str, int], torch.Tensor] = {}
+_WS_RETIRED: list = []   # outgrown workspaces: a captured CUDA graph may still hold their addresses
 
 
 def _workspace(kind: str, device: torch.device, nbytes: int, zero: bool = False) -> torch.Tensor:
+    """Grow-only: a larger request allocates a new buffer, but the old one is never freed — a
+    CUDA graph captured earlier (GraphedStep) has its raw pointer baked in and would otherwise
+    replay into memory the caching allocator has handed to someone else."""
     key = (kind, device.index if device.index is not None else torch.cuda.current_device())
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _WS_RETIRED.append(ws)
         ws = (torch.zeros if zero else torch.empty)(max(nbytes, 1), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws

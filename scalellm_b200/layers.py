@@ -335,6 +335,10 @@ class _QLinearBase:
             qz = None if self.qa.is_sym else c["qzeros"]
             self.packed = kernels.w4a16_prepack_gptq(c["qweight"], qz, c["scales"], g,
                                                      zeros_plus_one=True)
+        # The first GEMM follows on the same stream with the programmatic-launch attribute and its
+        # weight producer skips griddepcontrol.wait (weights are constants): make the prepack's
+        # writes visible first.  One-time, never inside a graph capture (it allocates).
+        torch.cuda.current_stream().synchronize()
         self._ckpt = {}
 
     def _gemm(self, x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

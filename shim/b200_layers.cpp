@@ -6,6 +6,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime_api.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -240,18 +241,32 @@ void QLinearB200Impl::ensure_packed() {
                                stream()),
        "prepack_gptq");
   }
+  // The first GEMM follows on the same stream with the programmatic-launch attribute and its
+  // weight producer does not execute griddepcontrol.wait (weights are constants): make the
+  // prepack's writes visible first.  One-time, never inside a graph capture (it allocates).
+  TORCH_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream())) == cudaSuccess,
+              "prepack: stream synchronize failed");
   qweight_ = qzeros_ = scales_ = torch::Tensor();  // checkpoint-format copies are no longer needed
 }
 
 torch::Tensor QLinearB200Impl::forward(torch::Tensor input) {
+  // the W4A16 kernels compute in bf16 only (activations, scales, output): an fp16 tensor would be
+  // reinterpreted silently.  The reference's Marlin path takes fp16 too; here it is refused.
+  TORCH_CHECK(input.scalar_type() == torch::kBFloat16,
+              "QLinearB200Impl: bf16 activations only, got ", input.scalar_type());
+  TORCH_CHECK(input.size(-1) == K_, "QLinearB200Impl: input features ", input.size(-1), " != ", K_);
   ensure_packed();
   torch::Tensor x = input.reshape({-1, input.size(-1)});
+  if (x.stride(-1) != 1) x = x.contiguous();
   const int64_t M = x.size(0);
   torch::Tensor out = torch::empty({M, N_}, x.options());
   if (M == 0) return out;
   const int64_t ws = b200_w4a16_workspace_bytes(M, N_, K_);
-  if (!workspace_.defined() || workspace_.numel() < ws)
+  if (!workspace_.defined() || workspace_.numel() < ws) {
+    // grow-only: a CUDA graph captured with the smaller buffer keeps replaying into it
+    if (workspace_.defined()) retired_workspaces_.push_back(workspace_);
     workspace_ = torch::empty({ws}, options_.dtype(torch::kByte));
+  }
   ok(b200_w4a16_gemm(out.data_ptr(), x.const_data_ptr(), packed_.const_data_ptr(),
                      bias_.defined() ? bias_.const_data_ptr() : nullptr, M, N_, K_, x.stride(0),
                      out.stride(0), static_cast<int>(qa_.group_size), workspace_.data_ptr(),

@@ -189,6 +189,7 @@ class QLinearB200Impl final : public ParallelLinearImpl {
   torch::TensorOptions options_;
   bool has_bias_;
   torch::Tensor qweight_, qzeros_, scales_, bias_, packed_, workspace_;
+  std::vector<torch::Tensor> retired_workspaces_;  // outgrown; captured graphs may still use them
 };
 
 // this rank's shard of a checkpoint-format int4 linear: output columns [c0, c1) of a column-

@@ -158,3 +158,29 @@ def test_marlin_golden_fixture_is_consistent_with_oracle_packers(golden_dir):
     assert d["marlin_scales_bf16"].shape == d["scales_bf16"].shape == (K // g, N)
     # the permuted scales are a permutation of the original ones, row by row
     assert np.array_equal(np.sort(d["marlin_scales_bf16"], axis=1), np.sort(d["scales_bf16"], axis=1))
+
+
+def test_marlin_layout_restatement_matches_the_reference_packers(golden_dir):
+    """oracle/quant.py's Marlin weight / scale layouts == what the reference's quant_utils wrote
+    (tests/golden/marlin_golden.npz), and the inverse maps (used to check the drop-in shim that takes
+    Marlin-layout tensors) invert them; the zero-point map (qlinear_awq_marlin_impl.cpp:62-97) is a
+    bijection over the same column order as the scales."""
+    d = np.load(os.path.join(golden_dir, "marlin_golden.npz"))
+    K, N, g = (int(x) for x in d["shape"])
+    q = d["q"].astype(np.int64)
+    mp = quant.pack_marlin_weights(q)
+    assert np.array_equal(mp.numpy(), d["marlin_packed"])
+    assert np.array_equal(quant.unpack_marlin_weights(mp, K, N), q)
+    s = torch.from_numpy(d["scales_bf16"]).view(torch.bfloat16)
+    ms = quant.permute_marlin_scales(s)
+    assert torch.equal(ms.view(torch.int16).reshape(-1),
+                       torch.from_numpy(d["marlin_scales_bf16"]).view(torch.int16).reshape(-1))
+    assert torch.equal(quant.unpermute_marlin_scales(ms), s)
+    z = np.random.default_rng(0).integers(0, 16, size=(K // g, N))
+    mz = quant.marlin_zero_points(z)
+    assert np.array_equal(quant.unpack_marlin_zero_points(mz), z)
+    # column c of the natural order lands where scale column c lands (same permutation), then the
+    # 4-bit interleave inside every group of 8: spot-check one row against the C++ recipe
+    perm, _ = quant.marlin_scales_perm()
+    want = z.reshape(-1, 64)[:, perm].reshape(-1, 8)[:, [0, 2, 4, 6, 1, 3, 5, 7]].reshape(z.shape)
+    assert np.array_equal(quant.unpack_cols(mz), want)

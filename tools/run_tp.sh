@@ -1,14 +1,14 @@
 #!/bin/bash
-# Multi-GPU stage (gpurun --gpus N -- bash tools/run_tp.sh N): the all-reduce / all-gather tests
-# (staged ones included), then bench.py under torchrun with the fused all-reduce + norm on / off
-# and with the peer-memory all-gather on.
+# Multi-GPU stage (gpurun --gpus N -- bash tools/run_tp.sh N [quick]): the all-reduce / all-gather /
+# sharded-argmax tests at every world size the box offers, then bench.py under torchrun, the in-graph
+# timeline of rank 0, and the C++-only decode demo (one process, one worker thread per GPU).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-2}
-B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_gpu_allreduce.py -m gpu -q --tb=short -p no:cacheprovider \
-    > gpurun_out/pytest_allreduce.log 2>&1
-echo "pytest allreduce (staged included) rc=$? : $(tail -3 gpurun_out/pytest_allreduce.log | tr '\n' ' ')"
-grep -E "Error|assert" gpurun_out/pytest_allreduce.log | head -10
+timeout 1500 python -m pytest tests/test_gpu_allreduce.py -m gpu -q --tb=short -p no:cacheprovider \
+    > gpurun_out/pytest_allreduce_n$N.log 2>&1
+echo "pytest allreduce rc=$? : $(tail -3 gpurun_out/pytest_allreduce_n$N.log | tr '\n' ' ')"
+grep -E "Error|assert|FAILED" gpurun_out/pytest_allreduce_n$N.log | head -10
 run() {  # tag, env assignments...
   tag=$1; shift
   env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
@@ -17,13 +17,16 @@ run() {  # tag, env assignments...
   echo "bench tp$N $tag rc=$?"
   tail -1 gpurun_out/bench_tp${N}_$tag.json | head -c 200; echo; tail -2 gpurun_out/bench_tp${N}_$tag.err
 }
-run f1 B200_FUSE_AR_NORM=1
-run f0 B200_FUSE_AR_NORM=0
-run gather B200_FUSE_AR_NORM=1 B200_AR_GATHER=1
+run default B200_FUSE_AR_NORM=1
+if [ "${2:-}" != quick ]; then
+  run oneshot B200_AR_ALGO=oneshot
+  run nccl_gather B200_AR_GATHER=0
+fi
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
     --master-port $((29730 + RANDOM % 200)) tools/step_timeline.py --out gpurun_out/step_timeline_tp$N.md \
     > gpurun_out/step_timeline_tp$N.log 2>&1
-echo "timeline tp$N rc=$?"; head -12 gpurun_out/step_timeline_tp$N.md 2>/dev/null
-# the reference engine's model: one process, one worker thread per GPU, C++ only
-timeout 600 scalellm_b200/decode_demo 32 64 2048 20 $N > gpurun_out/decode_demo_tp$N.log 2>&1
-echo "decode_demo tp$N rc=$? $(tail -1 gpurun_out/decode_demo_tp$N.log)"
+echo "timeline tp$N rc=$?"; head -60 gpurun_out/step_timeline_tp$N.md 2>/dev/null
+if [ "${2:-}" != quick ]; then
+  timeout 600 scalellm_b200/decode_demo 32 64 2048 20 $N > gpurun_out/decode_demo_tp$N.log 2>&1
+  echo "decode_demo tp$N rc=$? $(tail -1 gpurun_out/decode_demo_tp$N.log)"
+fi
