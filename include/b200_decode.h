@@ -145,6 +145,20 @@ B200_API int b200_silu_mul_strided(void* out, const void* gate, const void* up,
                                    int64_t rows, int64_t n, int64_t gate_stride,
                                    int64_t up_stride, int dtype,
                                    b200_stream_t stream);
+/* Adjacent operators of the same reference link target (:kernels), so that a link-time swap also
+ * resolves for the reference's Gemma / GPT-2 / Phi models — bit-identical to the reference kernels,
+ * not on the benchmarked path:
+ *   gemma_rms_norm  out = (T)(x * rstd * (1.0 + w))           src/kernels/layernorm_kernels.cu:66-123
+ *   layer_norm      out = (T)((x - mean) * rstd * w (+ b))     src/kernels/layernorm_kernels.cu:185-260
+ *   gelu            act 1 = gelu_new, 2 = gelu_fast (tanh.approx), optionally * up
+ *                                                             src/kernels/activation_kernels.cu:13-41,108-145 */
+B200_API int b200_gemma_rms_norm(void* out, const void* in, const void* weight, int64_t rows,
+                                 int64_t n, float eps, int dtype, b200_stream_t stream);
+B200_API int b200_layer_norm(void* out, const void* in, const void* weight, const void* bias /*nullable*/,
+                             int64_t rows, int64_t n, float eps, int dtype, b200_stream_t stream);
+B200_API int b200_gelu(void* out, const void* in, int64_t rows, int64_t n, int64_t in_stride, int act,
+                       int with_mul, int dtype, b200_stream_t stream);
+
 
 /* ------------------------------------------------------------------------ *
  * A1  Paged-KV variable-length attention (decode-shaped)
@@ -223,6 +237,36 @@ B200_API int b200_w4a16_prepack_gptq(void* packed, const int32_t* qweight,
                                      int64_t K, int64_t N, int group_size,
                                      int zeros_plus_one, b200_stream_t stream);
 
+/* GPTQ act-order (desc_act): the rows of the packed weight are the checkpoint's rows sorted by
+ * quant group — perm = argsort(g_idx), g_idx_sorted = g_idx[perm] (qlinear_gptq_marlin_impl.cpp:43-56,
+ * marlin/gptq_repack.cu:17); the caller feeds the GEMM activations with the same column order
+ * (b200_permute_cols, the reference's permute_cols_kernel marlin/gptq_gemm.cu:66-104).  Whole K
+ * only (is_k_full): every group then has exactly group_size rows. */
+B200_API int b200_w4a16_prepack_gptq_actorder(void* packed, const int32_t* qweight,
+                                              const int32_t* qzeros, const void* scales,
+                                              const int32_t* perm, const int32_t* g_idx_sorted,
+                                              int64_t K, int64_t N, int group_size,
+                                              int zeros_plus_one, b200_stream_t stream);
+/* The operator-level drop-in for marlin::awq_repack(q_weight, out, num_bits) /
+ * gptq_repack(q_weight, perm, out, num_bits) (src/kernels/quantization/marlin.h:30-37): `out` has
+ * the byte count of q_weight (K * N / 2) and receives the nibble part of every tile blob, tile
+ * (nt, kt) at byte (nt * K/128 + kt) * 8192; perm = act-order row order or NULL. */
+B200_API int b200_w4a16_repack_awq(void* out, const int32_t* qweight, int64_t K, int64_t N,
+                                   b200_stream_t stream);
+B200_API int b200_w4a16_repack_gptq(void* out, const int32_t* qweight, const int32_t* perm,
+                                    int64_t K, int64_t N, b200_stream_t stream);
+/* ... and for what marlin::gptq_gemm receives beside it (marlin.h:17-28): scales [K/g, N] and
+ * zero points [K/g, N/8] ALREADY in Marlin's column order (the layer permuted them,
+ * qlinear_awq_marlin_impl.cpp:62-124); zeros_marlin NULL = symmetric, zero point 8 (has_zp
+ * false).  Writes the full tile blobs b200_w4a16_gemm streams (b200_w4a16_packed_bytes). */
+B200_API int b200_w4a16_assemble_marlin(void* packed, const void* nibbles, const void* scales_marlin,
+                                        const int32_t* zeros_marlin, int64_t K, int64_t N,
+                                        int group_size, b200_stream_t stream);
+/* out[r, j] = in[r, perm[j]], bf16 / fp16 rows (strides in elements): the activation side of
+ * act-order, permute_cols_kernel marlin/gptq_gemm.cu:66-104. */
+B200_API int b200_permute_cols(void* out, const void* in, const int32_t* perm, int64_t rows,
+                               int64_t cols, int64_t in_stride, int64_t out_stride, int dtype,
+                               b200_stream_t stream);
 /* Inverse of the prepack (debug / parity): W_out[K,N] bf16 = dequantised weights. */
 B200_API int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K,
                                 int64_t N, int group_size, b200_stream_t stream);
@@ -300,6 +344,29 @@ B200_API void b200_debug_set_trace(void* device_buffer);
  * ------------------------------------------------------------------------ */
 B200_API int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t n, int64_t stride,
                          int dtype, b200_stream_t stream);
+
+/* The logits processors of the sampling tail, in place on logits [batch, vocab] (contiguous), with
+ * the semantics and rounding points of src/kernels/sampling/penalty_kernels.cu:9-33,52-75,107-140
+ * and softmax_kernels.cu:11-54 (declared in src/kernels/sampling/sampling_kernels.h:7-29):
+ *   temperature   logits[b, :] *= (t[b] == 0 ? 1 : 1 / t[b])
+ *   repetition    for the lens[b] unique ids of row b: x < 0 ? x * p[b] : x / p[b]
+ *   freq/presence for ids with count > 0: x -= count * freq[b]; x -= presence[b]
+ *   softmax       exp(x - max) stored in T, summed from the stored values, / (sum + 1e-6)
+ * token_ids int64 [batch, max_len], token_counts / token_ids_lens int32. */
+B200_API int b200_apply_temperature(void* logits, const void* temperatures, int64_t batch,
+                                    int64_t vocab, int dtype, b200_stream_t stream);
+B200_API int b200_apply_repetition_penalty(void* logits, const int64_t* token_ids,
+                                           const int32_t* token_ids_lens, const void* penalties,
+                                           int64_t batch, int64_t vocab, int64_t max_len, int dtype,
+                                           b200_stream_t stream);
+B200_API int b200_apply_frequency_presence_penalty(void* logits, const int64_t* token_ids,
+                                                   const int32_t* token_counts,
+                                                   const int32_t* token_ids_lens,
+                                                   const void* frequency_penalties,
+                                                   const void* presence_penalties, int64_t batch,
+                                                   int64_t vocab, int64_t max_len, int dtype,
+                                                   b200_stream_t stream);
+B200_API int b200_softmax(void* logits, int64_t batch, int64_t vocab, int dtype, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * A9  Tensor-parallel all-reduce over NVLink peer memory

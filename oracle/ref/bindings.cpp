@@ -67,6 +67,17 @@ PYBIND11_MODULE(_ref_kernels, m) {
     TORCH_CHECK(rc == 0, "marlin_dequant_kat launch failed: ", rc);
     return std::make_tuple(zp, sym);
   });
+  m.def("gemma_rms_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w, double eps) {
+    llm::kernel::gemma_rms_norm(out, x, w, static_cast<float>(eps));
+  });
+  m.def("layer_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w,
+                         std::optional<torch::Tensor> b, double eps) {
+    llm::kernel::layer_norm(out, x, w, b.has_value() ? *b : torch::Tensor(), static_cast<float>(eps));
+  });
+  m.def("gelu_new", &llm::kernel::gelu_new);
+  m.def("gelu_fast", &llm::kernel::gelu_fast);
+  m.def("gelu_new_with_mul", &llm::kernel::gelu_new_with_mul);
+  m.def("gelu_fast_with_mul", &llm::kernel::gelu_fast_with_mul);
   m.def("silu", &llm::kernel::silu);
   m.def("silu_with_mul", &llm::kernel::silu_with_mul);
 }

@@ -62,12 +62,24 @@ SIGNATURES = {
     "b200_w4a16_reduce_partials": (_int, [_vp, _vp, _int, _i64, _vp, _i64, _i64, _i64, _vp]),
     "b200_debug_attn_plan": (_int, [_i64, _int, _int, _int, _int, _int, _int, _vp]),
     "b200_debug_w4a16_plan": (_int, [_i64, _i64, _int, _int, _vp, _vp, _vp]),
+    "b200_gemma_rms_norm": (_int, [_vp, _vp, _vp, _i64, _i64, _f32, _int, _vp]),
+    "b200_layer_norm": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _int, _vp]),
+    "b200_gelu": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _int, _int, _vp]),
+    "b200_apply_temperature": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
+    "b200_apply_repetition_penalty": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "b200_apply_frequency_presence_penalty": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "b200_softmax": (_int, [_vp, _i64, _i64, _int, _vp]),
     "b200_argmax": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_rope_kv_write_splitk": (_int, [_vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64,
                                          _i64, _i64, _int, _int, _vp]),
     "b200_silu_mul_splitk": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
     "b200_rms_norm_residual_splitk": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _i64, _i64, _f32, _int, _vp]),
     "b200_debug_set_trace": (None, [_vp]),
+    "b200_w4a16_prepack_gptq_actorder": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "b200_w4a16_repack_awq": (_int, [_vp, _vp, _i64, _i64, _vp]),
+    "b200_w4a16_repack_gptq": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "b200_w4a16_assemble_marlin": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "b200_permute_cols": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_create": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp]),
     "b200_ar_open_peers": (_int, [_vp, _vp]),
     "b200_ar_create_all": (_int, [C.POINTER(_vp), C.POINTER(C.c_int), _int, _i64]),

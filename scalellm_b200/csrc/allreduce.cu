@@ -8,7 +8,7 @@
 // process with one thread per GPU like the reference's engine (b200_ar_create_all, the
 // counterpart of its ncclCommInitAll, process_group.cpp:98-118: peer access instead of IPC).
 // Each rank owns ONE cudaMalloc'ed symmetric region
-//   [ inbox p0 | inbox p1 | result p0 | result p1 | flags1[world][128] | flags2[128] |
+//   [ LL inbox p0 | p1 | LL result p0 | p1 | staging p0 | p1 | flags1[world][128] | flags2[128] |
 //     flagsA[world][128] | cand[2][world][128] | epoch | done ]
 // exported through CUDA IPC and mapped by every peer (NVSwitch gives every pair full NVLink
 // bandwidth).  Every collective of a communicator takes the next epoch e (kept in device memory
@@ -73,7 +73,10 @@ struct ArDevPtrs {
 
 // region layout (byte offsets)
 __host__ __device__ inline int64_t ar_result_off(int64_t max_bytes) { return 2 * max_bytes; }
-__host__ __device__ inline int64_t ar_flags_off(int64_t max_bytes) { return 4 * max_bytes; }  // flags1
+// staging buffers (2 parities) of the flag-synchronised kernels (one-shot all-reduce, all-gather):
+// kept apart from the LL buffers, whose stale contents must never look like a current epoch
+__host__ __device__ inline int64_t ar_stage_off(int64_t max_bytes) { return 4 * max_bytes; }
+__host__ __device__ inline int64_t ar_flags_off(int64_t max_bytes) { return 6 * max_bytes; }  // flags1
 __host__ __device__ inline int64_t ar_flags2_off(int64_t max_bytes) {
   return ar_flags_off(max_bytes) + (int64_t)AR_MAX_WORLD * AR_MAX_ROWS * 4;
 }
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
-  const int64_t buf_off = (e & 1) ? max_bytes : 0;
+  const int64_t buf_off = ar_stage_off(max_bytes) + ((e & 1) ? max_bytes : 0);
 
   // slice of this block (in 16-byte vectors)
   const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
@@ -284,14 +287,41 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
 }
 
 // ---------------------------------------------------------------------------------------------
-// Two-shot, row-partitioned all-reduce (file header).  One block per row; a row is `row_vecs`
-// 16-byte vectors (the last row of a plain message may be shorter), thread t holds vectors
-// t, t + 512, ... (VPT of them).  Sources of the contribution:
+// Two-shot, row-partitioned all-reduce (file header), LL ("low latency") transport: every 16-byte
+// store that crosses NVLink carries 8 bytes of payload and two copies of the call's epoch —
+// { data0, epoch, data1, epoch } — and the receiver polls the data itself until both epoch words
+// match (8-byte aligned stores are single-copy atomic, so a matching flag vouches for its
+// payload).  No flag arrays, no release fences, no __syncthreads on the exchange path: the two hops
+// cost two one-way NVLink latencies instead of two (remote write + system fence + flag + poll)
+// sequences — the flag form measured 15-17 us per fused call at two ranks with both ranks in
+// lock step (profiles/r02_ar_bench.md).  The price is 2x the bytes on the wire and in the buffers
+// (rows * row_bytes * 2 <= max_bytes), irrelevant at <= 1 MiB.
+//
+// One block per row; a row is `row_vecs` 16-byte payload vectors (the last row of a plain message
+// may be shorter), thread t holds vectors t, t + 512, ... (VPT of them).  Contribution source:
 //   FROM_PARTIALS: the producing GEMM's stream-K partials (sum of the tile's slots, rounded once);
 //   else:          data_in (T).
 // NORM: the reduced row feeds residual += x; out = rms_norm(residual) * weight (ArNormArgs);
 // else it is stored to data_out.  T = float only without partials / norm.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4* dst, uint32_t d0, uint32_t d1, uint32_t e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(d0), "r"(e), "r"(d1), "r"(e)
+               : "memory");
+}
+// payload vector (16 B) -> two LL lines at ll[2 * v], ll[2 * v + 1]
+__device__ __forceinline__ void ll_store_vec(uint4* ll, int64_t v, uint4 p, uint32_t e) {
+  ll_store(ll + 2 * v, p.x, p.y, e);
+  ll_store(ll + 2 * v + 1, p.z, p.w, e);
+}
+__device__ __forceinline__ uint4 ll_load_vec(const uint4* ll, int64_t v, uint32_t e) {
+  uint4 a, b;
+  do {
+    a = ld_volatile_v4(ll + 2 * v);
+    b = ld_volatile_v4(ll + 2 * v + 1);
+  } while (a.y != e || a.w != e || b.y != e || b.w != e);
+  return make_uint4(a.x, a.z, b.x, b.z);
+}
+
 template <typename T, int VPT, bool FROM_PARTIALS, bool NORM>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     ArDevPtrs ptrs, const T* __restrict__ data_in, T* __restrict__ data_out, int64_t nvec_total,
@@ -300,8 +330,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
   constexpr int VEC = 16 / sizeof(T);
   ar_stamp(trace, 6);
   pdl_wait();               // the contribution (and the residual stream) come from earlier kernels
-  ar_stamp(trace, 0);
   pdl_launch_dependents();  // the next GEMM may start prefetching its weights while we exchange
+  ar_stamp(trace, 0);
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
@@ -316,8 +346,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
 
   // ---- 1. push my contribution of this row into the owner's inbox, slot = my rank ----
   {
-    uint4* inbox = reinterpret_cast<uint4*>(ptrs.base[owner] + par_off) +
-                   ((int64_t)rank * R + lrow) * row_vecs;
+    uint4* inbox = reinterpret_cast<uint4*>(ptrs.base[owner] + par_off);
+    const int64_t slot_v0 = ((int64_t)rank * R + lrow) * row_vecs;
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int j = threadIdx.x + k * AR_THREADS;
@@ -333,27 +363,15 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
         } else {
           c = reinterpret_cast<const uint4*>(data_in)[row_v0 + j];
         }
-        inbox[j] = c;
+        ll_store_vec(inbox, slot_v0 + j, c, e);
       }
     }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t* f1 = reinterpret_cast<uint32_t*>(ptrs.base[owner] + ar_flags_off(max_bytes));
-    st_release_sys(&f1[rank * AR_MAX_ROWS + row], e);
   }
   ar_stamp(trace, 1);
 
   // ---- 2. the owner reduces the world slots in rank order and pushes the row to everyone ----
   uint4 red[VPT];
-  const bool is_owner = owner == rank;
-  if (is_owner) {
-    if (threadIdx.x < world) {
-      const uint32_t* f1 = reinterpret_cast<const uint32_t*>(local + ar_flags_off(max_bytes));
-      ar_wait_flag(&f1[threadIdx.x * AR_MAX_ROWS + row], e);
-    }
-    __syncthreads();
-    ar_stamp(trace, 2);
+  if (owner == rank) {
     const uint4* inbox = reinterpret_cast<const uint4*>(local + par_off);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
         uint4 v[AR_MAX_WORLD];
 #pragma unroll
         for (int r = 0; r < AR_MAX_WORLD; ++r)
-          if (r < world) v[r] = ld_volatile_v4(inbox + ((int64_t)r * R + lrow) * row_vecs + j);
+          if (r < world) v[r] = ll_load_vec(inbox, ((int64_t)r * R + lrow) * row_vecs + j, e);
         float acc[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
@@ -375,29 +393,20 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
 #pragma unroll
         for (int r = 0; r < AR_MAX_WORLD; ++r)
           if (r < world && r != rank)
-            reinterpret_cast<uint4*>(ptrs.base[r] + ar_result_off(max_bytes) + par_off)[row_v0 + j] = red[k];
+            ll_store_vec(reinterpret_cast<uint4*>(ptrs.base[r] + ar_result_off(max_bytes) + par_off),
+                         row_v0 + j, red[k], e);
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < world && (int)threadIdx.x != rank) {
-      uint32_t* f2 = reinterpret_cast<uint32_t*>(ptrs.base[threadIdx.x] + ar_flags2_off(max_bytes));
-      st_release_sys(&f2[row], e);
     }
     ar_stamp(trace, 3);
   } else {
     // ---- 3. everyone else picks the reduced row up from its own result buffer ----
-    if (threadIdx.x == 0) {
-      const uint32_t* f2 = reinterpret_cast<const uint32_t*>(local + ar_flags2_off(max_bytes));
-      ar_wait_flag(&f2[row], e);
-    }
-    __syncthreads();
-    ar_stamp(trace, 4);
     const uint4* res = reinterpret_cast<const uint4*>(local + ar_result_off(max_bytes) + par_off);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int j = threadIdx.x + k * AR_THREADS;
-      if (j < row_len) red[k] = ld_volatile_v4(res + row_v0 + j);
+      if (j < row_len) red[k] = ll_load_vec(res, row_v0 + j, e);
     }
+    ar_stamp(trace, 4);
   }
 
   if constexpr (!NORM) {
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(AR_THREADS) allgather_oneshot_kernel(ArDevPtrs
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
-  const int64_t buf_off = (e & 1) ? max_bytes : 0;
+  const int64_t buf_off = ar_stage_off(max_bytes) + ((e & 1) ? max_bytes : 0);
   const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
   const int64_t v0 = (int64_t)blockIdx.x * per;
   const int64_t v1 = v0 + per < nvec ? v0 + per : nvec;
@@ -594,7 +603,7 @@ __global__ void __launch_bounds__(AR_THREADS) allgather_oneshot_kernel(ArDevPtrs
 
 using namespace b200;
 
-// B200_AR_ALGO = oneshot | twoshot (read once); default: two-shot above two ranks
+// B200_AR_ALGO = oneshot | twoshot (read once); default: two-shot (LL transport)
 static bool ar_use_twoshot(int world) {
   static const int forced = [] {
     const char* v = getenv("B200_AR_ALGO");
@@ -603,7 +612,7 @@ static bool ar_use_twoshot(int world) {
     return 0;
   }();
   if (forced) return forced == 2;
-  return world > 2;
+  return world >= 2;
 }
 
 static ArDevPtrs ar_ptrs(const b200_ar_comm* c) {
@@ -618,7 +627,7 @@ static int ar_launch_twoshot(b200_ar_comm* c, const T* in, T* out, int64_t nvec,
                              int rows, const float* partials, const W4Plan& plan, int row_n,
                              int64_t split_stride, ArNormArgs<T> na, cudaStream_t st) {
   const int R = (rows + c->world - 1) / c->world;
-  if ((int64_t)c->world * R * row_vecs * 16 > c->max_bytes || (int64_t)rows * row_vecs * 16 > c->max_bytes)
+  if ((int64_t)c->world * R * row_vecs * 32 > c->max_bytes)   // LL lines: 2x the payload bytes
     return set_error(B200_ERR_WORKSPACE, "ar_allreduce: %d rows of %d B exceed the %lld B symmetric buffer",
                      rows, row_vecs * 16, (long long)c->max_bytes);
   const ArDevPtrs ptrs = ar_ptrs(c);
@@ -845,7 +854,7 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
   if (!partials && nvec > (int64_t)AR_THREADS * AR_MAX_ROWS) row_vecs = 2 * AR_THREADS;
   const int64_t rows = (nvec + row_vecs - 1) / row_vecs;
   if (ar_use_twoshot(c->world) && rows <= AR_MAX_ROWS && row_vecs <= 2 * AR_THREADS &&
-      (int64_t)(rows + c->world) * row_vecs * 16 <= c->max_bytes) {
+      (int64_t)(rows + c->world) * row_vecs * 32 <= c->max_bytes) {
     switch (dtype) {
       case B200_BF16: {
         using T = __nv_bfloat16;
@@ -944,6 +953,7 @@ int b200_ar_allreduce_splitk_norm(b200_ar_comm* c, void* out, void* residual, co
 
 int b200_ar_argmax(b200_ar_comm* c, int64_t* out, const void* logits, int64_t rows, int64_t n_local,
                    int64_t stride, int dtype, b200_stream_t stream) {
+  if (rows == 0) return B200_OK;  // an empty selection has no storage (every rank sees the same rows)
   B200_CHECK_ARG(c && out && logits, "ar_argmax: null pointer");
   B200_CHECK_ARG(rows >= 0 && rows <= AR_MAX_ROWS && n_local > 0 && stride >= n_local &&
                      n_local * (int64_t)c->world < (1ll << 31),

@@ -463,22 +463,30 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 // on it (profiles/r02_step_timeline.md).
 __device__ __forceinline__ void w4_sum_partials8(float (&a)[8], const float* __restrict__ p0,
                                                  int64_t slot_stride, int count) {
-  float4 lo[W4_MAX_SLOTS], hi[W4_MAX_SLOTS];
-#pragma unroll
-  for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
-    if (sp < count) {
-      const float4* src = reinterpret_cast<const float4*>(p0 + sp * slot_stride);
-      lo[sp] = __ldcg(src);
-      hi[sp] = __ldcg(src + 1);
-    }
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  // four slots per round: their loads are in flight together (one L2 round trip for the usual
+  // 1-4 contributors) at 32 registers instead of 64 — the SiLU*mul consumer, which sums two such
+  // groups, ran at 178 registers = one 256-thread block per SM, three waves (r02 ncu capture)
 #pragma unroll
-  for (int sp = 0; sp < W4_MAX_SLOTS; ++sp) {
-    if (sp < count) {
-      a[0] += lo[sp].x; a[1] += lo[sp].y; a[2] += lo[sp].z; a[3] += lo[sp].w;
-      a[4] += hi[sp].x; a[5] += hi[sp].y; a[6] += hi[sp].z; a[7] += hi[sp].w;
+  for (int s0 = 0; s0 < W4_MAX_SLOTS; s0 += 4) {
+    if (s0 < count) {
+      float4 lo[4], hi[4];
+#pragma unroll
+      for (int sp = 0; sp < 4; ++sp) {
+        if (s0 + sp < count) {
+          const float4* src = reinterpret_cast<const float4*>(p0 + (s0 + sp) * slot_stride);
+          lo[sp] = __ldcg(src);
+          hi[sp] = __ldcg(src + 1);
+        }
+      }
+#pragma unroll
+      for (int sp = 0; sp < 4; ++sp) {
+        if (s0 + sp < count) {
+          a[0] += lo[sp].x; a[1] += lo[sp].y; a[2] += lo[sp].z; a[3] += lo[sp].w;
+          a[4] += hi[sp].x; a[5] += hi[sp].y; a[6] += hi[sp].z; a[7] += hi[sp].w;
+        }
+      }
     }
   }
 }

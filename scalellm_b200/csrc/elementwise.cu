@@ -128,6 +128,84 @@ __global__ void __launch_bounds__(1024) rms_norm_scalar_kernel(T* __restrict__ o
   }
 }
 
+// Gemma RMSNorm and LayerNorm (layernorm_kernels.cu:66-95,185-230): adjacent to the Llama path (the
+// reference's Gemma / GPT-2 / Phi models link them from the same :kernels target).  Kept in the
+// reference's own loop shape — BD = min(n, 1024) threads stride the row, FFMA accumulation, the two
+// butterflies — so the results are bit-identical; they are not on the benchmarked path.
+// gemma: out = (T)(x * rstd * (1.0 + w)) with the (1.0 + w) factor in DOUBLE, as written there.
+template <typename T>
+__global__ void __launch_bounds__(1024) gemma_rms_norm_kernel(T* __restrict__ out,
+                                                              const T* __restrict__ in,
+                                                              const T* __restrict__ weight,
+                                                              float eps, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int64_t BD = n < 1024 ? n : 1024;
+  float ss = 0.f;
+  if ((int64_t)threadIdx.x < BD)
+    for (int64_t i = threadIdx.x; i < n; i += BD) {
+      const float f = Num<T>::to_f(in[row * n + i]);
+      ss = fmaf(f, f, ss);
+    }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float t = (threadIdx.x & 31) < ((blockDim.x + 31) >> 5) ? red[threadIdx.x & 31] : 0.f;
+  t = warp_sum(t);
+  const float rstd = rsqrtf(t / n + eps);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = Num<T>::to_f(in[row * n + i]);
+    const float w = Num<T>::to_f(weight[i]);
+    out[row * n + i] = Num<T>::from_f((float)(x * rstd * (1.0 + w)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) layer_norm_kernel(T* __restrict__ out,
+                                                          const T* __restrict__ in,
+                                                          const T* __restrict__ weight,
+                                                          const T* __restrict__ bias, float eps,
+                                                          int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[32];
+  __shared__ float s_mean;
+  const int64_t row = blockIdx.x;
+  const int64_t BD = n < 1024 ? n : 1024;
+  const int lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  float m = 0.f;
+  if ((int64_t)threadIdx.x < BD)
+    for (int64_t i = threadIdx.x; i < n; i += BD) m += Num<T>::to_f(in[row * n + i]);
+  m = warp_sum(m);
+  if (lane == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.f;
+  t = warp_sum(t);
+  if (threadIdx.x == 0) s_mean = t / n;
+  __syncthreads();
+  const float mean = s_mean;
+  float var = 0.f;
+  if ((int64_t)threadIdx.x < BD)
+    for (int64_t i = threadIdx.x; i < n; i += BD) {
+      const float x = Num<T>::to_f(in[row * n + i]) - mean;
+      var = fmaf(x, x, var);
+    }
+  var = warp_sum(var);
+  __syncthreads();  // red[] is reused
+  if (lane == 0) red[threadIdx.x >> 5] = var;
+  __syncthreads();
+  t = lane < nw ? red[lane] : 0.f;
+  t = warp_sum(t);
+  const float rstd = rsqrtf(t / n + eps);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float o = (Num<T>::to_f(in[row * n + i]) - mean) * rstd * Num<T>::to_f(weight[i]);
+    if (bias != nullptr) o += Num<T>::to_f(bias[i]);
+    out[row * n + i] = Num<T>::from_f(o);
+  }
+}
+
 template <typename T, bool RESIDUAL>
 static int launch_rms_norm(void* out, void* residual, const void* in, const void* weight,
                            int64_t rows, int64_t n, float eps, cudaStream_t st) {
@@ -531,9 +609,29 @@ __device__ __forceinline__ float silu_t(float x) {
   // (T)( x / (1 + __expf(-x)) )   (activation_kernels.cu:44-50)
   return rnd<T>(x / (1.0f + __expf(-x)));
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// ACT 0 = SiLU, 1 = GELU "new" (tanh form), 2 = GELU "fast": fp32 math on the T-typed input, one
+// rounding to T at the end; the expressions are shaped like the reference's so that the compiler
+// contracts the same multiply-adds (activation_kernels.cu:13-50)
+template <typename T, int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if constexpr (ACT == 0) {
+    return silu_t<T>(x);
+  } else if constexpr (ACT == 1) {
+    const float cdf = 0.5f * (1.0f + tanh_approx((0.7978845608028654f * (x + 0.044715f * x * x * x))));
+    return rnd<T>(x * cdf);
+  } else {
+    const float cdf = 0.5f * (1.0f + tanh_approx((0.7978845608028654f * x) * (1.0f + 0.044715f * x * x)));
+    return rnd<T>(x * cdf);
+  }
+}
 
-// MODE 0: out = silu(a)      MODE 1: out = silu(a) * b  (second rounding)
-template <typename T, int MODE>
+// MODE 0: out = act(a)      MODE 1: out = act(a) * b  (second rounding)
+template <typename T, int MODE, int ACT = 0>
 __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T* __restrict__ a,
                                                    const T* __restrict__ b, int64_t rows,
                                                    int64_t n, int64_t a_stride, int64_t b_stride,
@@ -556,7 +654,7 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
       T* o = reinterpret_cast<T*>(&orr);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        float s = silu_t<T>(Num<T>::to_f(ae[i]));
+        float s = act_t<T, ACT>(Num<T>::to_f(ae[i]));
         if (MODE == 1) s = s * Num<T>::to_f(be[i]);
         o[i] = Num<T>::from_f(s);
       }
@@ -567,7 +665,7 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
       const int64_t r = idx / n, j = idx % n;
-      float s = silu_t<T>(Num<T>::to_f(a[r * a_stride + j]));
+      float s = act_t<T, ACT>(Num<T>::to_f(a[r * a_stride + j]));
       if (MODE == 1) s = s * Num<T>::to_f(b[r * b_stride + j]);
       out[r * n + j] = Num<T>::from_f(s);
     }
@@ -578,7 +676,7 @@ __global__ void __launch_bounds__(256) silu_kernel(T* __restrict__ out, const T*
 // that GEMM's stream-K partials: each is first rounded to T (the GEMM epilogue's rounding), then
 // exactly the MODE 1 arithmetic above.
 template <typename T>
-__global__ void __launch_bounds__(256) silu_mul_splitk_kernel(T* __restrict__ out,
+__global__ void __launch_bounds__(256, 3) silu_mul_splitk_kernel(T* __restrict__ out,
                                                               const float* __restrict__ partials,
                                                               W4Plan plan, int64_t slot_stride,
                                                               int64_t rows, int inter) {
@@ -605,7 +703,7 @@ __global__ void __launch_bounds__(256) silu_mul_splitk_kernel(T* __restrict__ ou
   }
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, int ACT = 0>
 static int launch_silu(void* out, const void* a, const void* b, int64_t rows, int64_t n,
                        int64_t a_stride, int64_t b_stride, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
@@ -616,7 +714,7 @@ static int launch_silu(void* out, const void* a, const void* b, int64_t rows, in
   int64_t blocks = (work + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  B200_PDL_LAUNCH("silu", (silu_kernel<T, MODE>), (unsigned)blocks, 256, 0, st, static_cast<T*>(out),
+  B200_PDL_LAUNCH("activation", (silu_kernel<T, MODE, ACT>), (unsigned)blocks, 256, 0, st, static_cast<T*>(out),
                   static_cast<const T*>(a), static_cast<const T*>(b), rows, n, a_stride, b_stride,
                   vec);
   return B200_OK;
@@ -704,6 +802,21 @@ using namespace b200;
     default: return set_error(B200_ERR_UNSUPPORTED, "dtype %d not supported here", dtype); \
   }
 
+template <typename T>
+static int launch_row_norm(int which, void* out, const void* in, const void* weight, const void* bias,
+                           int64_t rows, int64_t n, float eps, cudaStream_t st) {
+  const int threads = (int)(n < 1024 ? ((n + 31) / 32) * 32 : 1024);
+  if (which == 0) {
+    B200_PDL_LAUNCH("gemma_rms_norm", gemma_rms_norm_kernel<T>, (unsigned)rows, threads, 0, st,
+                    static_cast<T*>(out), static_cast<const T*>(in), static_cast<const T*>(weight), eps, n);
+  } else {
+    B200_PDL_LAUNCH("layer_norm", layer_norm_kernel<T>, (unsigned)rows, threads, 0, st, static_cast<T*>(out),
+                    static_cast<const T*>(in), static_cast<const T*>(weight), static_cast<const T*>(bias),
+                    eps, n);
+  }
+  return B200_OK;
+}
+
 extern "C" {
 
 int b200_rms_norm(void* out, const void* in, const void* weight, int64_t rows, int64_t n,
@@ -714,6 +827,24 @@ int b200_rms_norm(void* out, const void* in, const void* weight, int64_t rows, i
   if (rows == 0) return B200_OK;
   DISPATCH_DTYPE3(dtype, (launch_rms_norm<T, false>(out, nullptr, in, weight, rows, n, eps,
                                                     static_cast<cudaStream_t>(stream))));
+}
+
+int b200_gemma_rms_norm(void* out, const void* in, const void* weight, int64_t rows, int64_t n,
+                        float eps, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in && weight, "gemma_rms_norm: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31), "gemma_rms_norm: bad shape");
+  if (rows == 0) return B200_OK;
+  DISPATCH_DTYPE3(dtype, (launch_row_norm<T>(0, out, in, weight, nullptr, rows, n, eps,
+                                             static_cast<cudaStream_t>(stream))));
+}
+
+int b200_layer_norm(void* out, const void* in, const void* weight, const void* bias, int64_t rows,
+                    int64_t n, float eps, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in && weight, "layer_norm: null pointer (bias may be NULL)");
+  B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31), "layer_norm: bad shape");
+  if (rows == 0) return B200_OK;
+  DISPATCH_DTYPE3(dtype, (launch_row_norm<T>(1, out, in, weight, bias, rows, n, eps,
+                                             static_cast<cudaStream_t>(stream))));
 }
 
 int b200_rms_norm_residual(void* out, void* residual, const void* in, const void* weight,
@@ -836,7 +967,7 @@ int b200_silu_mul_splitk(void* out, const float* partials, int splits, int64_t g
                  plan.slots, splits);
   const int64_t work = rows * (inter / 8);
   int64_t blocks = (work + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
+  const int64_t cap = (int64_t)sm_count() * 3;   // one wave at 3 resident blocks per SM (grid-stride loop)
   if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_BF16)
@@ -911,6 +1042,24 @@ int b200_silu(void* out, const void* in, int64_t rows, int64_t n, int64_t in_str
                                             static_cast<cudaStream_t>(stream))));
 }
 
+// act: 1 = gelu_new, 2 = gelu_fast (activation_kernels.cu:22-41,108-119,128-145); with_mul: the input is
+// [rows, 2n] and out = act(in[:, :n]) * in[:, n:] (second rounding), else in is [rows, n] with row
+// stride in_stride
+int b200_gelu(void* out, const void* in, int64_t rows, int64_t n, int64_t in_stride, int act,
+              int with_mul, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in, "gelu: null pointer");
+  B200_CHECK_ARG(rows >= 0 && n >= 0 && (act == 1 || act == 2), "gelu: bad shape / act (1 = new, 2 = fast)");
+  auto st = static_cast<cudaStream_t>(stream);
+  if (with_mul) {
+    const void* up = static_cast<const uint8_t*>(in) + n * esize(dtype);
+    if (act == 1) { DISPATCH_DTYPE3(dtype, (launch_silu<T, 1, 1>(out, in, up, rows, n, 2 * n, 2 * n, st))); }
+    DISPATCH_DTYPE3(dtype, (launch_silu<T, 1, 2>(out, in, up, rows, n, 2 * n, 2 * n, st)));
+  }
+  B200_CHECK_ARG(in_stride >= n, "gelu: bad stride");
+  if (act == 1) { DISPATCH_DTYPE3(dtype, (launch_silu<T, 0, 1>(out, in, nullptr, rows, n, in_stride, 0, st))); }
+  DISPATCH_DTYPE3(dtype, (launch_silu<T, 0, 2>(out, in, nullptr, rows, n, in_stride, 0, st)));
+}
+
 int b200_silu_mul(void* out, const void* in, int64_t rows, int64_t n, int dtype,
                   b200_stream_t stream) {
   B200_CHECK_ARG(out && in, "silu_mul: null pointer");
@@ -933,9 +1082,9 @@ int b200_silu_mul_strided(void* out, const void* gate, const void* up, int64_t r
 
 int b200_argmax(int64_t* out, const void* logits, int64_t rows, int64_t n, int64_t stride, int dtype,
                 b200_stream_t stream) {
+  if (rows == 0) return B200_OK;  // an empty selection (prefill chunks before the last) has no storage
   B200_CHECK_ARG(out && logits, "argmax: null pointer");
   B200_CHECK_ARG(rows >= 0 && n > 0 && n < (1ll << 31) && stride >= n, "argmax: bad shape");
-  if (rows == 0) return B200_OK;
   auto st = static_cast<cudaStream_t>(stream);
   switch (dtype) {
     case B200_BF16:

@@ -82,18 +82,15 @@ __device__ __forceinline__ uint32_t load_z(const int32_t* __restrict__ qzeros, i
   return ((w >> (4 * pos)) & 0xf) + (plus_one ? 1u : 0u);  // may be 16 (qlinear_impl.cpp:44)
 }
 
+// The 8192 nibble bytes of tile (nt, kt): 256 threads, thread <-> (row n_local, k half).  `perm`
+// (GPTQ act-order, else nullptr): row k of the packed weight is row perm[k] of the checkpoint —
+// the rows sorted by group (marlin/gptq_repack.cu:17 does the same gather on its way into the
+// Marlin layout; qlinear_gptq_marlin_impl.cpp:43-56 builds perm = argsort(g_idx)).
 template <int MODE>
-__global__ void __launch_bounds__(256) w4_prepack_kernel(uint8_t* __restrict__ packed,
-                                                         const int32_t* __restrict__ qweight,
-                                                         const int32_t* __restrict__ qzeros,
-                                                         const __nv_bfloat16* __restrict__ scales,
-                                                         int64_t K, int64_t N, int g_actual,
-                                                         int geff, int plus_one) {
-  const int kt = blockIdx.x, nt = blockIdx.y;
-  const int KT = (int)(K / W4_BK);
-  const int ngrp = 128 / geff;
-  const int blob = w4_blob_bytes(geff);
-  uint8_t* out = packed + ((int64_t)nt * KT + kt) * blob;
+__device__ __forceinline__ void w4_pack_tile_nibbles(uint8_t* __restrict__ out_tile,
+                                                     const int32_t* __restrict__ qweight,
+                                                     const int32_t* __restrict__ perm, int kt,
+                                                     int nt, int64_t N) {
   const int t = threadIdx.x;
   const int n_local = t & 127, khalf = t >> 7;
   const int64_t n = (int64_t)nt * 128 + n_local;
@@ -107,25 +104,124 @@ __global__ void __launch_bounds__(256) w4_prepack_kernel(uint8_t* __restrict__ p
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int dk = p < 4 ? 2 * p : 2 * (p - 4) + 1;
-        word |= load_q<MODE>(qweight, k0 + dk, n, N) << (4 * p);
+        const int64_t k = perm ? (int64_t)perm[k0 + dk] : k0 + dk;
+        word |= load_q<MODE>(qweight, k, n, N) << (4 * p);
       }
       words[w] = word;
     }
     uint4 v = make_uint4(words[0], words[1], words[2], words[3]);
-    *reinterpret_cast<uint4*>(out + ((khalf * 2 + q4) * 128 + n_local) * 16) = v;
+    *reinterpret_cast<uint4*>(out_tile + ((khalf * 2 + q4) * 128 + n_local) * 16) = v;
   }
+}
+
+// g_sorted (act-order, else nullptr): quant group of packed row k = g_sorted[k] (= g_idx[perm[k]],
+// non-decreasing; every aligned block of min(g, 128) packed rows lies inside one group because all
+// groups have exactly g rows when the whole K is present — is_k_full).
+template <int MODE>
+__global__ void __launch_bounds__(256) w4_prepack_kernel(uint8_t* __restrict__ packed,
+                                                         const int32_t* __restrict__ qweight,
+                                                         const int32_t* __restrict__ qzeros,
+                                                         const __nv_bfloat16* __restrict__ scales,
+                                                         const int32_t* __restrict__ perm,
+                                                         const int32_t* __restrict__ g_sorted,
+                                                         int64_t K, int64_t N, int g_actual,
+                                                         int geff, int plus_one) {
+  const int kt = blockIdx.x, nt = blockIdx.y;
+  const int KT = (int)(K / W4_BK);
+  const int ngrp = 128 / geff;
+  const int blob = w4_blob_bytes(geff);
+  uint8_t* out = packed + ((int64_t)nt * KT + kt) * blob;
+  const int t = threadIdx.x;
+  w4_pack_tile_nibbles<MODE>(out, qweight, perm, kt, nt, N);
   __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(out + W4_QBYTES);
   uint8_t* z_out = out + W4_QBYTES + ngrp * 256;
   for (int i = t; i < ngrp * 128; i += 256) {
     const int grp = i >> 7, nl = i & 127;
-    const int64_t gi = ((int64_t)kt * 128 + grp * geff) / g_actual;
+    const int64_t k_first = (int64_t)kt * 128 + grp * geff;
+    const int64_t gi = g_sorted ? (int64_t)g_sorted[k_first] : k_first / g_actual;
     s_out[i] = scales[gi * N + (int64_t)nt * 128 + nl];
+    z_out[i] = (uint8_t)load_z<MODE>(qzeros, gi, (int64_t)nt * 128 + nl, N, plus_one);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The operator-level drop-in (shim/b200_kernels: marlin::awq_repack / gptq_repack / gptq_gemm with
+// the reference's EXACT signatures, src/kernels/quantization/marlin.h:17-37).  There the repack
+// sees only q_weight and must fill an `out` of the same byte count ((K/16) x (N*16/8) int32 =
+// K*N/2 bytes), and scales / zero points reach gptq_gemm separately, already in Marlin's column
+// order (the layer permuted them: qlinear_awq_marlin_impl.cpp:62-124).  So:
+//   repack:   `out` = the nibble part of every tile blob, tile (nt, kt) at byte (nt*KT + kt) * 8192;
+//   assemble: nibble tiles + Marlin-order scales (+ Marlin-packed zero points, or the symmetric 8)
+//             -> the full tile blobs the GEMM streams (done once per weight, cached by the shim).
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) w4_repack_nibbles_kernel(uint8_t* __restrict__ out,
+                                                                const int32_t* __restrict__ qweight,
+                                                                const int32_t* __restrict__ perm,
+                                                                int64_t K, int64_t N) {
+  const int kt = blockIdx.x, nt = blockIdx.y;
+  const int KT = (int)(K / W4_BK);
+  w4_pack_tile_nibbles<MODE>(out + ((int64_t)nt * KT + kt) * W4_QBYTES, qweight, perm, kt, nt, N);
+}
+
+// Marlin's column order of scales / zero points (tests/kernels/quant_utils.py:231-241,282-291):
+// inside every block of 64 columns natural column c sits at position (c % 8) * 8 + c / 8; with a
+// single group, inside every block of 32 columns at ((c % 8) / 2) * 8 + 2 * (c / 8) + c % 2.
+__device__ __forceinline__ int64_t marlin_scale_pos(int64_t n, bool single_group) {
+  if (!single_group) {
+    const int c = (int)(n & 63);
+    return (n & ~63ll) + (c & 7) * 8 + (c >> 3);
+  }
+  const int c = (int)(n & 31);
+  return (n & ~31ll) + ((c & 7) >> 1) * 8 + 2 * (c >> 3) + (c & 1);
+}
+// zero points: the 64-column permutation above, then nibble t of a packed word holds position
+// [0,2,4,6,1,3,5,7][t] of its group of 8 (qlinear_awq_marlin_impl.cpp:84-96)
+__device__ __forceinline__ uint32_t marlin_zero_at(const int32_t* __restrict__ zeros, int64_t gi,
+                                                   int64_t n, int64_t N) {
+  const int64_t pos = marlin_scale_pos(n, false);
+  const uint32_t w = (uint32_t)zeros[gi * (N / 8) + (pos >> 3)];
+  const int u = (int)(pos & 7);
+  const int t = (u >> 1) + ((u & 1) << 2);  // inverse of [0,2,4,6,1,3,5,7]
+  return (w >> (4 * t)) & 0xf;
+}
+
+__global__ void __launch_bounds__(256) w4_assemble_marlin_kernel(
+    uint8_t* __restrict__ packed, const uint8_t* __restrict__ nibbles,
+    const __nv_bfloat16* __restrict__ scales_m, const int32_t* __restrict__ zeros_m, int64_t K,
+    int64_t N, int g_actual, int geff) {
+  const int kt = blockIdx.x, nt = blockIdx.y;
+  const int KT = (int)(K / W4_BK);
+  const int ngrp = 128 / geff;
+  uint8_t* out = packed + ((int64_t)nt * KT + kt) * w4_blob_bytes(geff);
+  const uint4* src = reinterpret_cast<const uint4*>(nibbles + ((int64_t)nt * KT + kt) * W4_QBYTES);
+  const int t = threadIdx.x;
+  reinterpret_cast<uint4*>(out)[t] = src[t];
+  reinterpret_cast<uint4*>(out)[t + 256] = src[t + 256];
+  __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(out + W4_QBYTES);
+  uint8_t* z_out = out + W4_QBYTES + ngrp * 256;
+  const bool single = g_actual >= K;
   for (int i = t; i < ngrp * 128; i += 256) {
     const int grp = i >> 7, nl = i & 127;
     const int64_t gi = ((int64_t)kt * 128 + grp * geff) / g_actual;
-    z_out[i] = (uint8_t)load_z<MODE>(qzeros, gi, (int64_t)nt * 128 + nl, N, plus_one);
+    const int64_t n = (int64_t)nt * 128 + nl;
+    s_out[i] = scales_m[gi * N + marlin_scale_pos(n, single)];
+    z_out[i] = zeros_m ? (uint8_t)marlin_zero_at(zeros_m, gi, n, N) : (uint8_t)8;
   }
+}
+
+// out[r, j] = in[r, perm[j]] (2-byte elements): the activation side of GPTQ act-order
+// (permute_cols_kernel, marlin/gptq_gemm.cu:66-104)
+__global__ void __launch_bounds__(256) permute_cols_kernel(uint16_t* __restrict__ out,
+                                                           const uint16_t* __restrict__ in,
+                                                           const int32_t* __restrict__ perm,
+                                                           int cols, int64_t in_stride,
+                                                           int64_t out_stride) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint16_t* src = in + (int64_t)blockIdx.x * in_stride;
+  uint16_t* dst = out + (int64_t)blockIdx.x * out_stride;
+  for (int j = threadIdx.x; j < cols; j += 256) dst[j] = src[perm[j]];
 }
 
 // ===========================================================================
@@ -879,7 +975,8 @@ static int check_w4_shape(const char* who, int64_t K, int64_t N, int g) {
 
 static int prepack(int mode, void* packed, const int32_t* qweight, const int32_t* qzeros,
                    const void* scales, int64_t K, int64_t N, int g, int plus_one,
-                   b200_stream_t stream) {
+                   b200_stream_t stream, const int32_t* perm = nullptr,
+                   const int32_t* g_sorted = nullptr) {
   B200_CHECK_ARG(packed && qweight && scales, "w4a16_prepack: null pointer");
   B200_CHECK_ARG(mode == 1 || qzeros != nullptr, "w4a16_prepack_awq: qzeros required");
   int rc = check_w4_shape("w4a16_prepack", K, N, g);
@@ -891,12 +988,12 @@ static int prepack(int mode, void* packed, const int32_t* qweight, const int32_t
   auto st = static_cast<cudaStream_t>(stream);
   if (mode == 0)
     w4_prepack_kernel<0><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(packed), qweight, qzeros,
-                                               static_cast<const __nv_bfloat16*>(scales), K, N,
-                                               g_actual, geff, 0);
+                                               static_cast<const __nv_bfloat16*>(scales), nullptr,
+                                               nullptr, K, N, g_actual, geff, 0);
   else
     w4_prepack_kernel<1><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(packed), qweight, qzeros,
-                                               static_cast<const __nv_bfloat16*>(scales), K, N,
-                                               g_actual, geff, plus_one);
+                                               static_cast<const __nv_bfloat16*>(scales), perm,
+                                               g_sorted, K, N, g_actual, geff, plus_one);
   B200_LAUNCH_OK("w4a16_prepack");
   return B200_OK;
 }
@@ -911,6 +1008,75 @@ int b200_w4a16_prepack_gptq(void* packed, const int32_t* qweight, const int32_t*
                             const void* scales, int64_t K, int64_t N, int group_size,
                             int zeros_plus_one, b200_stream_t stream) {
   return prepack(1, packed, qweight, qzeros, scales, K, N, group_size, zeros_plus_one, stream);
+}
+
+int b200_w4a16_prepack_gptq_actorder(void* packed, const int32_t* qweight, const int32_t* qzeros,
+                                     const void* scales, const int32_t* perm,
+                                     const int32_t* g_idx_sorted, int64_t K, int64_t N,
+                                     int group_size, int zeros_plus_one, b200_stream_t stream) {
+  B200_CHECK_ARG(perm && g_idx_sorted, "w4a16_prepack_gptq_actorder: perm and sorted g_idx required");
+  B200_CHECK_ARG(group_size > 0, "w4a16_prepack_gptq_actorder: act-order needs a positive group size");
+  return prepack(1, packed, qweight, qzeros, scales, K, N, group_size, zeros_plus_one, stream, perm,
+                 g_idx_sorted);
+}
+
+static int repack_nibbles(int mode, void* out, const int32_t* qweight, const int32_t* perm, int64_t K,
+                          int64_t N, b200_stream_t stream) {
+  B200_CHECK_ARG(out && qweight, "w4a16_repack: null pointer");
+  int rc = check_w4_shape("w4a16_repack", K, N, 128);
+  if (rc != B200_OK) return rc;
+  B200_CHECK_ARG(is_aligned(out, 16), "w4a16_repack: out must be 16-byte aligned");
+  dim3 grid((unsigned)(K / 128), (unsigned)(N / 128));
+  auto st = static_cast<cudaStream_t>(stream);
+  if (mode == 0)
+    w4_repack_nibbles_kernel<0><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(out), qweight, nullptr, K, N);
+  else
+    w4_repack_nibbles_kernel<1><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(out), qweight, perm, K, N);
+  B200_LAUNCH_OK("w4a16_repack");
+  return B200_OK;
+}
+
+int b200_w4a16_repack_awq(void* out, const int32_t* qweight, int64_t K, int64_t N,
+                          b200_stream_t stream) {
+  return repack_nibbles(0, out, qweight, nullptr, K, N, stream);
+}
+
+int b200_w4a16_repack_gptq(void* out, const int32_t* qweight, const int32_t* perm, int64_t K,
+                           int64_t N, b200_stream_t stream) {
+  return repack_nibbles(1, out, qweight, perm, K, N, stream);
+}
+
+int b200_w4a16_assemble_marlin(void* packed, const void* nibbles, const void* scales_marlin,
+                               const int32_t* zeros_marlin, int64_t K, int64_t N, int group_size,
+                               b200_stream_t stream) {
+  B200_CHECK_ARG(packed && nibbles && scales_marlin, "w4a16_assemble_marlin: null pointer");
+  int rc = check_w4_shape("w4a16_assemble_marlin", K, N, group_size);
+  if (rc != B200_OK) return rc;
+  B200_CHECK_ARG(is_aligned(packed, 16) && is_aligned(nibbles, 16),
+                 "w4a16_assemble_marlin: buffers must be 16-byte aligned");
+  B200_CHECK_ARG(N % 64 == 0, "w4a16_assemble_marlin: N %% 64 == 0 (Marlin's column blocks)");
+  const int g_actual = group_size <= 0 ? (int)K : group_size;
+  dim3 grid((unsigned)(K / 128), (unsigned)(N / 128));
+  w4_assemble_marlin_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint8_t*>(packed), static_cast<const uint8_t*>(nibbles),
+      static_cast<const __nv_bfloat16*>(scales_marlin), zeros_marlin, K, N, g_actual,
+      w4_geff(group_size));
+  B200_LAUNCH_OK("w4a16_assemble_marlin");
+  return B200_OK;
+}
+
+int b200_permute_cols(void* out, const void* in, const int32_t* perm, int64_t rows, int64_t cols,
+                      int64_t in_stride, int64_t out_stride, int dtype, b200_stream_t stream) {
+  B200_CHECK_ARG(out && in && perm, "permute_cols: null pointer");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "permute_cols: bf16 / fp16 only");
+  B200_CHECK_ARG(rows >= 0 && cols > 0 && cols < (1ll << 31) && in_stride >= cols && out_stride >= cols,
+                 "permute_cols: bad shape");
+  B200_CHECK_ARG(out != in, "permute_cols: out must not alias in");
+  if (rows == 0) return B200_OK;
+  B200_PDL_LAUNCH("permute_cols", permute_cols_kernel, (unsigned)rows, 256, 0,
+                  static_cast<cudaStream_t>(stream), static_cast<uint16_t*>(out),
+                  static_cast<const uint16_t*>(in), perm, (int)cols, in_stride, out_stride);
+  return B200_OK;
 }
 
 int b200_w4a16_dequant(void* w_out, const void* packed, int64_t K, int64_t N, int group_size,

@@ -186,6 +186,90 @@ def silu_with_mul(input: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ---------------------------------------------------------------------------
+# sampling tail: logits processors (src/kernels/sampling/sampling_kernels.h:7-29), in place
+# ---------------------------------------------------------------------------
+def apply_temperature_penalty(logits: torch.Tensor, temperatures: torch.Tensor) -> None:
+    _cuda(logits, temperatures)
+    assert logits.dim() == 2 and logits.is_contiguous() and temperatures.is_contiguous()
+    assert temperatures.dtype == logits.dtype and temperatures.numel() == logits.shape[0]
+    check(_lib.load().b200_apply_temperature(_p(logits), _p(temperatures), logits.shape[0], logits.shape[1],
+                                             _dt(logits), _stream()))
+
+
+def apply_repetition_penalty(logits: torch.Tensor, token_ids: torch.Tensor, token_ids_lens: torch.Tensor,
+                             penalties: torch.Tensor) -> None:
+    _cuda(logits, token_ids, token_ids_lens, penalties)
+    assert logits.dim() == 2 and logits.is_contiguous() and token_ids.is_contiguous()
+    assert token_ids.dtype == torch.int64 and token_ids_lens.dtype == torch.int32 and penalties.dtype == logits.dtype
+    check(_lib.load().b200_apply_repetition_penalty(_p(logits), _p(token_ids), _p(token_ids_lens), _p(penalties),
+                                                    logits.shape[0], logits.shape[1], token_ids.shape[1],
+                                                    _dt(logits), _stream()))
+
+
+def apply_frequency_presence_penalty(logits: torch.Tensor, token_ids: torch.Tensor, token_counts: torch.Tensor,
+                                     token_ids_lens: torch.Tensor, frequency_penalties: torch.Tensor,
+                                     presence_penalties: torch.Tensor) -> None:
+    _cuda(logits, token_ids, token_counts, token_ids_lens, frequency_penalties, presence_penalties)
+    assert logits.dim() == 2 and logits.is_contiguous() and token_ids.is_contiguous() and token_counts.is_contiguous()
+    assert token_ids.dtype == torch.int64 and token_counts.dtype == torch.int32 and token_ids_lens.dtype == torch.int32
+    check(_lib.load().b200_apply_frequency_presence_penalty(
+        _p(logits), _p(token_ids), _p(token_counts), _p(token_ids_lens), _p(frequency_penalties),
+        _p(presence_penalties), logits.shape[0], logits.shape[1], token_ids.shape[1], _dt(logits), _stream()))
+
+
+def invoke_softmax(logits: torch.Tensor) -> None:
+    _cuda(logits)
+    assert logits.dim() == 2 and logits.is_contiguous()
+    check(_lib.load().b200_softmax(_p(logits), logits.shape[0], logits.shape[1], _dt(logits), _stream()))
+
+
+def _gelu(input: torch.Tensor, act: int, with_mul: bool) -> torch.Tensor:
+    _cuda(input)
+    assert input.dim() == 2 and input.stride(1) == 1 and (not with_mul or input.is_contiguous())
+    n = input.shape[1] // 2 if with_mul else input.shape[1]
+    out = torch.empty((input.shape[0], n), dtype=input.dtype, device=input.device)
+    check(_lib.load().b200_gelu(_p(out), _p(input), input.shape[0], n, input.stride(0), act,
+                                1 if with_mul else 0, _dt(input), _stream()))
+    return out
+
+
+def gelu_new(input: torch.Tensor) -> torch.Tensor:
+    """activation_kernels.h:8 (tanh form, tanh.approx)"""
+    return _gelu(input, 1, False)
+
+
+def gelu_fast(input: torch.Tensor) -> torch.Tensor:
+    return _gelu(input, 2, False)
+
+
+def gelu_new_with_mul(input: torch.Tensor) -> torch.Tensor:
+    return _gelu(input, 1, True)
+
+
+def gelu_fast_with_mul(input: torch.Tensor) -> torch.Tensor:
+    return _gelu(input, 2, True)
+
+
+def gemma_rms_norm(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, epsilon: float) -> None:
+    """layernorm_kernels.h:11-14: out = (T)(x * rstd * (1 + w))"""
+    _cuda(out, input, weight)
+    assert input.is_contiguous() and out.is_contiguous()
+    n = input.shape[-1]
+    check(_lib.load().b200_gemma_rms_norm(_p(out), _p(input), _p(weight), input.numel() // n, n, epsilon,
+                                          _dt(input), _stream()))
+
+
+def layer_norm(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor,
+               bias: Optional[torch.Tensor], epsilon: float) -> None:
+    """layernorm_kernels.h:21-25 (bias may be None / undefined)"""
+    _cuda(out, input, weight)
+    assert input.is_contiguous() and out.is_contiguous()
+    n = input.shape[-1]
+    check(_lib.load().b200_layer_norm(_p(out), _p(input), _p(weight), None if bias is None else _p(bias),
+                                      input.numel() // n, n, epsilon, _dt(input), _stream()))
+
+
 def silu_mul(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act_func(gate) * up on strided views of the fused gate_up output (llama.h:61-64)."""
     _cuda(gate, up)
@@ -275,6 +359,64 @@ def w4a16_prepack_gptq(qweight: torch.Tensor, qzeros: Optional[torch.Tensor], sc
                          device=qweight.device)
     check(_lib.load().b200_w4a16_prepack_gptq(_p(packed), _p(qweight), _p(qzeros), _p(scales), K,
                                               N, group_size, int(zeros_plus_one), _stream()))
+    return packed
+
+
+def w4a16_prepack_gptq_actorder(qweight: torch.Tensor, qzeros: Optional[torch.Tensor], scales: torch.Tensor,
+                                g_idx: torch.Tensor, group_size: int, zeros_plus_one: bool = True):
+    """GPTQ desc_act checkpoint -> (packed weight, perm): rows sorted by quant group
+    (perm = argsort(g_idx), qlinear_gptq_marlin_impl.cpp:43-56); the caller gathers the activation
+    columns with the same perm (permute_cols) before the GEMM.  Whole K only."""
+    _cuda(qweight, qzeros, scales, g_idx)
+    assert qweight.dtype == torch.int32 and scales.dtype == torch.bfloat16 and group_size > 0
+    K, N = qweight.shape[0] * 8, qweight.shape[1]
+    assert g_idx.numel() == K
+    perm = torch.argsort(g_idx.to(torch.int64), stable=True).to(torch.int32).contiguous()
+    g_sorted = g_idx.to(torch.int32)[perm.long()].contiguous()
+    # whole K: every group has exactly group_size rows, so sorted rows fall into aligned blocks
+    want = torch.arange(K, device=g_idx.device, dtype=torch.int32) // group_size
+    if not torch.equal(g_sorted, want):
+        raise ValueError("act-order: g_idx does not cover K with groups of exactly group_size rows "
+                         "(a K-sharded act-order weight is not supported)")
+    packed = torch.empty(w4a16_packed_bytes(K, N, group_size), dtype=torch.uint8, device=qweight.device)
+    check(_lib.load().b200_w4a16_prepack_gptq_actorder(_p(packed), _p(qweight), _p(qzeros), _p(scales),
+                                                       _p(perm), _p(g_sorted), K, N, group_size,
+                                                       int(zeros_plus_one), _stream()))
+    return packed, perm
+
+
+def permute_cols(x: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[:, j] = x[:, perm[j]] (permute_cols_kernel, marlin/gptq_gemm.cu:66-104)"""
+    _cuda(x, perm)
+    assert x.dim() == 2 and x.stride(1) == 1 and perm.dtype == torch.int32 and perm.numel() == x.shape[1]
+    out = torch.empty((x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)
+    check(_lib.load().b200_permute_cols(_p(out), _p(x), _p(perm), x.shape[0], x.shape[1], x.stride(0),
+                                        out.stride(0), _dt(x), _stream()))
+    return out
+
+
+def w4a16_repack_nibbles(qweight: torch.Tensor, method: str, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The operator-level drop-in's repack (marlin::awq_repack / gptq_repack with the reference's
+    signature): nibble tiles only, [K/16, N*16/8] int32."""
+    _cuda(qweight, perm)
+    if method == "awq":
+        K, N = qweight.shape[0], qweight.shape[1] * 8
+        out = torch.empty((K // 16, N * 2), dtype=torch.int32, device=qweight.device)
+        check(_lib.load().b200_w4a16_repack_awq(_p(out), _p(qweight), K, N, _stream()))
+    else:
+        K, N = qweight.shape[0] * 8, qweight.shape[1]
+        out = torch.empty((K // 16, N * 2), dtype=torch.int32, device=qweight.device)
+        check(_lib.load().b200_w4a16_repack_gptq(_p(out), _p(qweight), _p(perm), K, N, _stream()))
+    return out
+
+
+def w4a16_assemble_marlin(nibbles: torch.Tensor, scales_marlin: torch.Tensor,
+                          zeros_marlin: Optional[torch.Tensor], K: int, N: int, group_size: int) -> torch.Tensor:
+    """nibble tiles + Marlin-order scales (+ Marlin-packed zero points; None = symmetric 8) -> tile blobs"""
+    _cuda(nibbles, scales_marlin, zeros_marlin)
+    packed = torch.empty(w4a16_packed_bytes(K, N, group_size), dtype=torch.uint8, device=nibbles.device)
+    check(_lib.load().b200_w4a16_assemble_marlin(_p(packed), _p(nibbles), _p(scales_marlin), _p(zeros_marlin),
+                                                 K, N, group_size, _stream()))
     return packed
 
 

@@ -293,8 +293,6 @@ def _check_quant(qa: QuantArgs, in_features: int, out_features: int) -> None:
         raise NotImplementedError("B200 W4A16 path supports 4-bit weights only")
     if qa.group_size not in (-1, 32, 64, 128):
         raise NotImplementedError(f"group_size {qa.group_size} not in (-1, 32, 64, 128)")
-    if qa.desc_act:
-        raise NotImplementedError("act-order (desc_act) checkpoints are not supported")
     if in_features % 128 or out_features % 128:
         raise ValueError("W4A16 needs in_features % 128 == 0 and out_features % 128 == 0 per shard")
 
@@ -305,17 +303,19 @@ class _QLinearBase:
         _check_quant(qa, in_features, out_features)
         self.K, self.N, self.qa, self.device = in_features, out_features, qa, device
         self.packed: Optional[torch.Tensor] = None
+        self.perm: Optional[torch.Tensor] = None     # GPTQ act-order: activation column order
         self.bias: Optional[torch.Tensor] = None
         self._has_bias = bias
         self._ckpt: Dict[str, torch.Tensor] = {}
 
     # weights arrive in checkpoint format; packing is lazy like repack_weight
     # (qlinear_awq_marlin_impl.cpp:99-125,232-235)
-    def _set_shard(self, qweight, qzeros, scales, bias=None) -> None:
+    def _set_shard(self, qweight, qzeros, scales, bias=None, g_idx=None) -> None:
         self._ckpt = dict(qweight=qweight.contiguous().to(self.device),
                           qzeros=None if qzeros is None else qzeros.contiguous().to(self.device),
-                          scales=scales.contiguous().to(self.device).to(torch.bfloat16))
-        self.packed = None
+                          scales=scales.contiguous().to(self.device).to(torch.bfloat16),
+                          g_idx=None if g_idx is None else g_idx.contiguous().to(self.device))
+        self.packed, self.perm = None, None
         if bias is not None:
             self.bias = bias.to(self.device).to(torch.bfloat16)
 
@@ -333,8 +333,14 @@ class _QLinearBase:
             self.packed = kernels.w4a16_prepack_awq(c["qweight"], c["qzeros"], c["scales"], g)
         else:
             qz = None if self.qa.is_sym else c["qzeros"]
-            self.packed = kernels.w4a16_prepack_gptq(c["qweight"], qz, c["scales"], g,
-                                                     zeros_plus_one=True)
+            if self.qa.desc_act and c.get("g_idx") is not None:
+                # act-order: rows sorted by group at pack time, activation columns gathered with the
+                # same perm at run time (qlinear_gptq_marlin_impl.cpp:43-56, gptq_gemm.cu:66-104)
+                self.packed, self.perm = kernels.w4a16_prepack_gptq_actorder(
+                    c["qweight"], qz, c["scales"], c["g_idx"], g, zeros_plus_one=True)
+            else:
+                self.packed = kernels.w4a16_prepack_gptq(c["qweight"], qz, c["scales"], g,
+                                                         zeros_plus_one=True)
         # The first GEMM follows on the same stream with the programmatic-launch attribute and its
         # weight producer skips griddepcontrol.wait (weights are constants): make the prepack's
         # writes visible first.  One-time, never inside a graph capture (it allocates).
@@ -344,6 +350,8 @@ class _QLinearBase:
     def _gemm(self, x: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
         self._ensure_packed()
         x2 = x.reshape(-1, x.shape[-1])
+        if self.perm is not None:
+            x2 = kernels.permute_cols(x2, self.perm)
         if x2.shape[0] > _DENSE_PREFILL_ROWS and os.environ.get("B200_W4_PREFILL_DENSE") == "1":
             # Prefill-sized batches are compute bound: the streaming kernel would re-read the int4
             # weights once per 128 rows.  Dequantise once (same bf16 values as the fused kernel,
@@ -393,12 +401,13 @@ class ColumnParallelQLinear(_QLinearBase):
         b = sd.get("bias")
         if b is not None:
             b = b[shard_range(self.full_N, self.pa.rank, self.pa.world_size)]
-        self._set_shard(qw, qz, sc, b)
+        self._set_shard(qw, qz, sc, b, sd.get("g_idx") if self.qa.desc_act else None)
 
     def supports_partials(self, n_rows: int) -> bool:
         """Partials output for a fused consumer (rope / silu*mul): the column shard is rank-local,
         so this also holds under tensor parallelism (no gather, no bias)."""
-        return self.bias is None and 0 < n_rows <= 128 and not (self.pa.world_size > 1 and self.gather_output)
+        return (self.bias is None and 0 < n_rows <= 128 and not self.qa.desc_act
+                and not (self.pa.world_size > 1 and self.gather_output))
 
     def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
         self._ensure_packed()
@@ -426,12 +435,16 @@ class RowParallelQLinear(_QLinearBase):
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         qw, qz, sc = _shard_qtensors(sd, self.qa, 0, self.pa.rank, self.pa.world_size,
                                      self.full_K, self.N)
-        self._set_shard(qw, qz, sc, sd.get("bias"))
+        g_idx = sd.get("g_idx") if self.qa.desc_act else None
+        if g_idx is not None and self.pa.world_size > 1:
+            raise NotImplementedError("act-order (desc_act) on a K-sharded (row-parallel, TP > 1) weight: "
+                                      "its groups are split across ranks (is_k_full = false)")
+        self._set_shard(qw, qz, sc, sd.get("bias"), g_idx)
 
     def supports_partials(self, n_rows: int) -> bool:
         """Partials output (the GEMM's cross-CTA reduction fused into the consumer norm; under TP
         the all-reduce is fused into the same kernel) — no bias."""
-        if self.bias is not None or not 0 < n_rows <= 128:
+        if self.bias is not None or not 0 < n_rows <= 128 or self.qa.desc_act:
             return False
         if self.pa.world_size == 1:
             return True

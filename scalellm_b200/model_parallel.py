@@ -29,7 +29,7 @@ class ProcessGroup:
 
     def __init__(self, rank: int, world_size: int, device: torch.device,
                  group: Optional[dist.ProcessGroup] = None, nvlink_max_bytes: int = 1 << 20,
-                 gather_max_bytes: int = 4 << 20):
+                 gather_max_bytes: int = 8 << 20):
         self._rank, self._world, self._device, self._group = rank, world_size, device, group
         self._comm = None
         self._nvlink_max_bytes = nvlink_max_bytes      # peer-memory all-reduce: latency-bound sizes only
@@ -39,7 +39,7 @@ class ProcessGroup:
         self._gather_max_bytes = gather_max_bytes if os.environ.get("B200_AR_GATHER", "1") != "0" else 0
         self._buffer_bytes = max(nvlink_max_bytes, self._gather_max_bytes)
         algo = os.environ.get("B200_AR_ALGO", "")
-        self._twoshot = algo == "twoshot" or (algo != "oneshot" and world_size > 2)
+        self._twoshot = algo != "oneshot"      # two-shot over LL lines is the default at every world size
         if device.type == "cuda" and world_size > 1:
             self._init_nvlink()
 
@@ -103,7 +103,7 @@ class ProcessGroup:
         S, rows, n = data.shape
         out = torch.empty((rows, n), dtype=dtype, device=data.device)
         nbytes = out.numel() * out.element_size()
-        if (self._comm is not None and (rows + self._world) * n * out.element_size() <= self._nvlink_max_bytes
+        if (self._comm is not None and nbytes <= self._nvlink_max_bytes and self._fits(rows, n * out.element_size())
                 and nbytes % 16 == 0 and dtype in (torch.bfloat16, torch.float16)):
             dt = 0 if dtype == torch.bfloat16 else 1
             check(_lib.load().b200_ar_allreduce_splitk(self._comm, out.data_ptr(), data.data_ptr(),
@@ -118,8 +118,14 @@ class ProcessGroup:
     def supports_partials_norm(self, rows: int, n: int, dtype: torch.dtype) -> bool:
         max_rows, max_n = (128, 8192) if self._twoshot else (64, 4096)
         return (self._comm is not None and 0 < rows <= max_rows and n % 128 == 0 and n <= max_n
-                and (rows + self._world) * n * 2 <= self._buffer_bytes
-                and dtype in (torch.bfloat16, torch.float16))
+                and self._fits(rows, n * 2) and dtype in (torch.bfloat16, torch.float16))
+
+    def _fits(self, rows: int, row_bytes: int) -> bool:
+        """A message of `rows` rows fits the symmetric buffers (the two-shot form ships LL lines:
+        twice the payload, one extra row per rank of slack)."""
+        if self._twoshot:
+            return (rows + self._world) * row_bytes * 2 <= self._buffer_bytes
+        return rows * row_bytes <= self._buffer_bytes
 
     def allreduce_partials_norm(self, partials, residual: torch.Tensor, weight: torch.Tensor,
                                 eps: float) -> torch.Tensor:

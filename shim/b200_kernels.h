@@ -1,8 +1,9 @@
 // b200_kernels.h — C++ drop-in for ScaleLLM's operator-level kernel API.
 //
-// Same namespaces, names, argument order, borrowing and in-place conventions as the reference
-// headers these replace (link this translation unit instead of the reference's :kernels,
-// :attention.kernels and :marlin.kernels targets):
+// Same namespaces, names, signatures, borrowing and in-place conventions as the reference headers
+// these replace (link this translation unit instead of the reference's :kernels,
+// :attention.kernels and :marlin.kernels targets; tests/test_shim.py compiles a translation unit
+// against the reference's OWN headers and links it with this library):
 //
 //   llm::kernel::rms_norm / rms_norm_residual      src/kernels/layernorm_kernels.h:6-19
 //   llm::kernel::apply_rotary_pos_emb              src/kernels/pos_embedding_kernels.h:7-13
@@ -38,6 +39,16 @@ void set_kv_cache(const torch::Tensor& slot_ids, const torch::Tensor& keys,
 torch::Tensor silu(torch::Tensor input);
 torch::Tensor silu_with_mul(torch::Tensor input);
 
+// the rest of the reference's :kernels surface (adjacent to the Llama path: Gemma, GPT-2, Phi):
+// src/kernels/layernorm_kernels.h:11-25, src/kernels/activation_kernels.h:8-13
+void gemma_rms_norm(torch::Tensor& out, torch::Tensor input, torch::Tensor weight, float epsilon);
+void layer_norm(torch::Tensor& out, torch::Tensor input, torch::Tensor weight, torch::Tensor bias,
+                float epsilon);
+torch::Tensor gelu_new(torch::Tensor input);
+torch::Tensor gelu_fast(torch::Tensor input);
+torch::Tensor gelu_new_with_mul(torch::Tensor input);
+torch::Tensor gelu_fast_with_mul(torch::Tensor input);
+
 // B200 extension used by B200AttnHandler: rope + cache write in one launch
 // (bit-identical to apply_rotary_pos_emb followed by set_kv_cache).
 void rope_and_set_kv_cache(torch::Tensor& querys, torch::Tensor& keys, const torch::Tensor& values,
@@ -61,24 +72,43 @@ void paged_kv_varlen_mha(torch::Tensor& out, const torch::Tensor& query,
 
 namespace marlin {
 
-// The repack output is this library's tile-blob layout, not Marlin's fragment layout; it is
-// opaque to the callers (qlinear_*_marlin_impl.cpp only hands it back to gptq_gemm), but it is
-// (K/128)*(N/128)*(8192+groups) bytes — callers must size `out` with b200_w4a16_packed_bytes
-// (the scales / zero points travel inside the blob, so the permuted scale and zero-point
-// tensors of the Marlin path are no longer read).
-void awq_repack(const torch::Tensor& q_weight, const torch::Tensor& q_zeros,
-                const torch::Tensor& scales, torch::Tensor& out, int64_t group_size);
+// ---- the reference's EXACT signatures (src/kernels/quantization/marlin.h:17-37) ----------------
+// A ScaleLLM build that links this library instead of :marlin.kernels needs no source edit in
+// qlinear_awq_marlin_impl.cpp / qlinear_gptq_marlin_impl.cpp:
+//   * awq_repack / gptq_repack fill `out` — (K/16, N*16/8) int32, the byte count of q_weight — with
+//     the nibble part of this library's tile blobs (opaque to the caller, who only hands it back);
+//     gptq_repack's `perm` (act-order row order, may be empty) is honoured;
+//   * gptq_gemm takes the scales [K/g, N] and zero points [K/g, N/8] the layer permuted into
+//     Marlin's column order, assembles the full tile blobs once per weight (cached by the identity
+//     of B / scales / zeros) and runs b200_w4a16_gemm; `zeros` is read iff has_zp (else the
+//     symmetric zero point 8), g_idx / perm select act-order (activation columns are gathered by
+//     `perm` first; whole-K only: is_k_full must be true), `workspace` is left zeroed as Marlin
+//     promises, use_fp32_reduce is what this library always does.  num_bits must be 4; A, C and
+//     scales must be bf16 (the reference also takes fp16: refused here, not reinterpreted).
+void awq_repack(const torch::Tensor& q_weight, torch::Tensor& out, int64_t num_bits);
 
-void gptq_repack(const torch::Tensor& q_weight, const torch::Tensor& scales, torch::Tensor& out,
-                 int64_t group_size);
+void gptq_repack(const torch::Tensor& q_weight, const torch::Tensor& perm, torch::Tensor& out,
+                 int64_t num_bits);
 
 void gptq_gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& C,
                const torch::Tensor& scales, const torch::Tensor& zeros, const torch::Tensor& g_idx,
                const torch::Tensor& perm, torch::Tensor& workspace, int num_bits, bool is_k_full,
                bool has_zp, bool use_fp32_reduce);
 
-// bytes of the packed weight / of the workspace gptq_gemm needs (no initialisation needed)
+// ---- B200 extensions (not in the reference): one-step repack into the full tile blobs ----------
+// `out` must hold b200_packed_bytes(K, N, group_size) bytes; checkpoint-order scales / zero points
+// travel inside the blob.  gptq_gemm recognises such a B by its size and then ignores its
+// scales / zeros arguments.
+void b200_awq_repack(const torch::Tensor& q_weight, const torch::Tensor& q_zeros,
+                     const torch::Tensor& scales, torch::Tensor& out, int64_t group_size);
+
+void b200_gptq_repack(const torch::Tensor& q_weight, const torch::Tensor& scales,
+                      torch::Tensor& out, int64_t group_size);
+
+// bytes of the full tile blobs / of the workspace b200_w4a16_gemm needs
 int64_t b200_packed_bytes(int64_t K, int64_t N, int64_t group_size);
 int64_t b200_workspace_bytes(int64_t M, int64_t N, int64_t K);
+// blobs assembled by gptq_gemm so far (tests)
+int64_t b200_assembled_weights();
 
 }  // namespace marlin

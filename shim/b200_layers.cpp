@@ -420,6 +420,12 @@ LlamaDecoderStep::LlamaDecoderStep(const LlamaArgs& args, const QuantArgs& qa,
   final_norm_ = std::make_unique<RMSNormImpl>(h, args.rms_norm_eps, options);
 }
 
+void LlamaDecoderStep::prepack() {
+  for (auto& l : layers_)
+    for (QLinearB200Impl* m : {l.qkv.get(), l.o.get(), l.gate_up.get(), l.down.get()})
+      if (m != nullptr) m->ensure_packed();
+}
+
 void LlamaDecoderStep::load_state_dict(const StateDict& sd) {
   auto sub = [&](const std::string& prefix) {
     StateDict out;

@@ -181,9 +181,9 @@ class QLinearB200Impl final : public ParallelLinearImpl {
   W4Partials forward_partials(const torch::Tensor& input);
   int64_t in_features() const { return K_; }
   int64_t out_features() const { return N_; }
+  void ensure_packed();  // repack now (otherwise lazily at the first forward)
 
  private:
-  void ensure_packed();
   int64_t K_, N_;
   QuantArgs qa_;
   torch::TensorOptions options_;
@@ -246,6 +246,11 @@ class LlamaDecoderStep {
   // (qlinear_awq_marlin_impl.cpp:287), embedding split on hidden, lm_head on vocab.
   void load_state_dict(const StateDict& state_dict);
   void set_kv_caches(std::vector<KVCache> kv_caches) { kv_caches_ = std::move(kv_caches); }
+  // Repack every int4 weight now (otherwise lazily at the first forward).  With all ranks in one
+  // process (one thread per GPU) call this, and have the caching allocator hold enough memory,
+  // BEFORE the first collective: a cudaMalloc by one rank synchronises with its peer-mapped
+  // devices, so it dead-locks against another rank's all-reduce kernel spinning for it.
+  void prepack();
 
   // logits [n_tokens, vocab]
   torch::Tensor forward(const torch::Tensor& tokens, const torch::Tensor& positions,

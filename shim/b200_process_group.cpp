@@ -3,6 +3,8 @@
 #include "b200_process_group.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -119,10 +121,12 @@ torch::Tensor ProcessGroupB200::allreduce_partials(const torch::Tensor& partials
 }
 
 bool ProcessGroupB200::supports_partials_norm(int64_t rows, int64_t n, torch::ScalarType dtype) const {
-  // two-shot form above two ranks (rows <= 128, n <= 8192), one-shot at two (rows <= 64, n <= 4096)
-  const bool two = world_size() > 2;
+  // two-shot form (default; LL lines: twice the payload in the buffers): rows <= 128, n <= 8192;
+  // one-shot (B200_AR_ALGO=oneshot): rows <= 64, n <= 4096
+  const char* algo = std::getenv("B200_AR_ALGO");
+  const bool two = !(algo && std::string(algo) == "oneshot");
   return world_size() > 1 && rows > 0 && rows <= (two ? 128 : 64) && n % 128 == 0 &&
-         n <= (two ? 8192 : 4096) && (rows + world_size()) * n * 2 <= kMaxBytes &&
+         n <= (two ? 8192 : 4096) && (rows + world_size()) * n * 2 * (two ? 2 : 1) <= kMaxBytes &&
          (dtype == torch::kBFloat16 || dtype == torch::kHalf);
 }
 

@@ -72,6 +72,11 @@ void worker(int rank, const Config& cfg, const llm::LlamaArgs& args, const llm::
   qa.quant_method = "awq";
   llm::LlamaDecoderStep model(args, qa, inv_freq, bf16, llm::ParallelArgs(rank, cfg.world, pg));
   model.load_state_dict(sd);  // keeps this rank's shard (copied to its device)
+  // One process, one thread per GPU: every cudaMalloc synchronises with the peer-mapped devices, so
+  // none may happen while another rank's all-reduce kernel spins for this rank.  Repack the weights
+  // now and leave the caching allocator a block large enough for the step's temporaries.
+  model.prepack();
+  { auto reserve = torch::empty({int64_t(1) << 30}, torch::dtype(torch::kByte).device(dev)); }
 
   // paged KV cache: block_size 8, every sequence at kv_len S with room to grow; this rank's kv heads
   const int64_t bs = 8, cap = S + steps + 8, blocks_per_seq = (cap + bs - 1) / bs;

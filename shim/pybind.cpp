@@ -32,15 +32,23 @@ PYBIND11_MODULE(_b200_shim, m) {
                                    window);
         });
   m.def("marlin_awq_repack", [](torch::Tensor qw, torch::Tensor qz, torch::Tensor s,
-                                torch::Tensor out, int64_t g) { marlin::awq_repack(qw, qz, s, out, g); });
+                                torch::Tensor out, int64_t g) { marlin::b200_awq_repack(qw, qz, s, out, g); });
   m.def("marlin_gptq_repack", [](torch::Tensor qw, torch::Tensor s, torch::Tensor out, int64_t g) {
-    marlin::gptq_repack(qw, s, out, g);
+    marlin::b200_gptq_repack(qw, s, out, g);
   });
   m.def("marlin_gemm", [](torch::Tensor A, torch::Tensor B, torch::Tensor C, torch::Tensor scales,
                           torch::Tensor zeros, torch::Tensor g_idx, torch::Tensor perm,
                           torch::Tensor ws, int bits, bool k_full, bool has_zp, bool fp32r) {
     marlin::gptq_gemm(A, B, C, scales, zeros, g_idx, perm, ws, bits, k_full, has_zp, fp32r);
   });
+  // the reference's exact signatures (scalellm/csrc/kernels.cu:9-55 exposes the same three)
+  m.def("marlin_awq_repack_ref", [](torch::Tensor qw, torch::Tensor out, int64_t bits) {
+    marlin::awq_repack(qw, out, bits);
+  });
+  m.def("marlin_gptq_repack_ref", [](torch::Tensor qw, torch::Tensor perm, torch::Tensor out, int64_t bits) {
+    marlin::gptq_repack(qw, perm, out, bits);
+  });
+  m.def("assembled_weights", &marlin::b200_assembled_weights);
   m.def("packed_bytes", &marlin::b200_packed_bytes);
   m.def("workspace_bytes", &marlin::b200_workspace_bytes);
 

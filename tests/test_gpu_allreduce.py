@@ -29,7 +29,7 @@ def _worker(rank, world, port, algo=""):
     pg = ProcessGroup(rank, world, dev)
     try:
         assert pg._comm is not None, "NVLink communicator was not created"
-        assert pg._twoshot == (algo == "twoshot" or (algo == "" and world > 2))
+        assert pg._twoshot == (algo != "oneshot")
         for dtype in (torch.bfloat16, torch.float16, torch.float32):
             # (33, 1000): last row of the two-shot partition is short; (3, 4096): fewer rows than ranks
             for shape in ((64, 4096), (32, 8192), (1, 8), (7, 1024), (128, 4096), (33, 1000), (3, 4096)):
@@ -151,7 +151,7 @@ def _worker(rank, world, port, algo=""):
 @pytest.mark.parametrize("world,algo", [(2, "oneshot"), (2, "twoshot"), (4, ""), (8, ""), (8, "oneshot")])
 def test_nvlink_allreduce_matches_nccl_and_host_sum(world, algo):
     """process_group_test.cpp:48-171 loops world_size = 1,2,4,...,device_count: so do we, with
-    both algorithms at the ends of the range."""
+    both algorithms (two-shot over LL lines = default, one-shot pull) at the ends of the range."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs >= {world} GPUs")
     mp.spawn(_worker, args=(world, _free_port(), algo), nprocs=world, join=True)

@@ -195,3 +195,36 @@ def test_w4a16_gemm_vs_reference_marlin_kernel(ref, golden_dir, M):
     diff = (ours.float() - out_ref.float()).abs()
     tol = 2.0 ** -8 * out_ref.float().abs() + 2e-3 * scale
     assert bool((diff <= tol).all()), float(diff.max())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("rows,n", [(64, 4096), (7, 1024), (5, 2304), (3, 320)])
+def test_gemma_rms_norm_and_layer_norm_bit_exact_vs_reference_kernel(ref, dtype, rows, n):
+    """The rest of the reference's :kernels norm surface (layernorm_kernels.cu:66-123,185-260):
+    same loop shape, same FFMA accumulation, the (1.0 + w) factor in double for Gemma."""
+    g = torch.Generator().manual_seed(rows + n)
+    x = (torch.randn(rows, n, generator=g) * 2 + 0.3).to(dtype).to(DEV)
+    w = (0.2 * torch.randn(n, generator=g)).to(dtype).to(DEV)
+    b = (0.1 * torch.randn(n, generator=g)).to(dtype).to(DEV)
+    o_ref, o_b = torch.empty_like(x), torch.empty_like(x)
+    ref.gemma_rms_norm(o_ref, x, w, 1e-6)
+    kernels.gemma_rms_norm(o_b, x, w, 1e-6)
+    assert torch.equal(o_b, o_ref)
+    for bias in (b, None):
+        ref.layer_norm(o_ref, x, w, bias, 1e-5)
+        kernels.layer_norm(o_b, x, w, bias, 1e-5)
+        assert torch.equal(o_b, o_ref), bias is None
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_gelu_bit_exact_vs_reference_kernel(ref, dtype):
+    """gelu_new / gelu_fast (+ fused multiply), activation_kernels.cu:13-41,84-145"""
+    g = torch.Generator().manual_seed(17)
+    x = (torch.randn(33, 2 * 3072, generator=g) * 3).to(dtype).to(DEV)
+    half = x[:, :3072].contiguous()
+    assert torch.equal(kernels.gelu_new(half), ref.gelu_new(half))
+    assert torch.equal(kernels.gelu_fast(half), ref.gelu_fast(half))
+    assert torch.equal(kernels.gelu_new_with_mul(x), ref.gelu_new_with_mul(x))
+    assert torch.equal(kernels.gelu_fast_with_mul(x), ref.gelu_fast_with_mul(x))
+    view = x[:, 1000:1512]                                   # row stride != n (activation_kernel's `stride`)
+    assert torch.equal(kernels.gelu_new(view), ref.gelu_new(view))

@@ -268,3 +268,88 @@ def test_rope_kv_write_splitk_matches_unfused(M, H, Hkv, D, bs):
     assert torch.isfinite(qkv_f.float()).all()
     assert torch.equal(qkv_f, qkv_u)
     assert torch.equal(caches[0], caches[2]) and torch.equal(caches[1], caches[3])
+
+
+# ---------------------------------------------------------------------------------------------
+# GPTQ act-order (desc_act) and the operator-level drop-in layouts
+# ---------------------------------------------------------------------------------------------
+def _actorder_checkpoint(K, N, g, seed):
+    """A GPTQ desc_act checkpoint as AutoGPTQ writes it: the rows of the original order carry the
+    group of their position in a random permutation (every group has exactly g rows)."""
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 16, size=(K, N))
+    order = rng.permutation(K)                      # quantisation order
+    g_idx = np.empty(K, dtype=np.int32)
+    g_idx[order] = np.arange(K) // g                # row order[i] was quantised in group i // g
+    z = rng.integers(0, 15, size=(K // g, N))       # stored minus one (GPTQ v1): <= 14 keeps z + 1 <= 15
+    s = (torch.randn(K // g, N, generator=torch.Generator().manual_seed(seed)).abs() * 0.01 + 1e-3).bfloat16()
+    return dict(q=q, qweight=quant.pack_gptq(q), qzeros=quant.pack_cols(z), scales=s,
+                g_idx=torch.from_numpy(g_idx))
+
+
+@pytest.mark.parametrize("K,N,M", [(1024, 512, 48), (256, 256, 5)])
+def test_gptq_act_order_matches_construct_weights(K, N, M):
+    """desc_act through the plugin layer: packed rows sorted by group + activation columns gathered
+    by the same perm == x @ construct_weights(qweight, qzeros, scales, g_idx) (qlinear_impl.cpp:21-56,
+    the reference's own definition of the dequantised act-order weight)."""
+    from scalellm_b200.layers import ColumnParallelQLinear, QuantArgs
+    from scalellm_b200.model_parallel import ParallelArgs
+    ck = _actorder_checkpoint(K, N, 128, seed=K + N)
+    w_ref = quant.construct_gptq_weights(ck["qweight"], ck["qzeros"], ck["scales"], ck["g_idx"])   # bf16 [K, N]
+    qa = QuantArgs(quant_method="gptq", bits=4, group_size=128, desc_act=True, is_sym=False)
+    lin = ColumnParallelQLinear(K, N, False, False, qa, ParallelArgs(0, 1, None), torch.device(DEV))
+    lin.load_state_dict({k: ck[k] for k in ("qweight", "qzeros", "scales", "g_idx")})
+    a = torch.randn(M, K, generator=torch.Generator().manual_seed(3)).bfloat16()
+    out = lin(a.to(DEV))
+    assert lin.perm is not None and not lin.supports_partials(M)
+    # dequantised weights are bit-identical to the reference definition, row for row after the perm
+    w_ours = kernels.w4a16_dequant(lin.packed, K, N, 128).cpu()
+    assert torch.equal(w_ours, w_ref[lin.perm.cpu().long()])
+    want = quant.w4a16_gemm(a, w_ref)
+    assert rel_err(out, want) < 1e-3
+    # without g_idx the same tensors mean a different weight: the perm matters
+    lin2 = ColumnParallelQLinear(K, N, False, False, QuantArgs("gptq", 4, 128, False, False),
+                                 ParallelArgs(0, 1, None), torch.device(DEV))
+    lin2.load_state_dict({k: ck[k] for k in ("qweight", "qzeros", "scales")})
+    assert rel_err(lin2(a.to(DEV)), want) > 1e-2
+
+
+def test_real_gptq_fixture_with_g_idx(golden_dir):
+    """src/layers/quantization/data/gptq_small.safetensors (K = N = 256, g128, carries g_idx): the
+    reference's own checkpoint tensors through the act-order path."""
+    from scalellm_b200.layers import ColumnParallelQLinear, QuantArgs
+    from scalellm_b200.model_parallel import ParallelArgs
+    d = np.load(os.path.join(golden_dir, "gptq_small.npz"))
+    qweight, qzeros = torch.from_numpy(d["qweight"]), torch.from_numpy(d["qzeros"])
+    scales = torch.from_numpy(d["scales"]).view(torch.float16).to(torch.bfloat16)
+    g_idx = torch.from_numpy(d["g_idx"])
+    K, N = qweight.shape[0] * 8, qweight.shape[1]
+    w_ref = quant.construct_gptq_weights(qweight, qzeros, scales, g_idx)
+    qa = QuantArgs(quant_method="gptq", bits=4, group_size=128, desc_act=True, is_sym=False)
+    lin = ColumnParallelQLinear(K, N, False, False, qa, ParallelArgs(0, 1, None), torch.device(DEV))
+    lin.load_state_dict(dict(qweight=qweight, qzeros=qzeros, scales=scales, g_idx=g_idx))
+    a = torch.randn(16, K, generator=torch.Generator().manual_seed(1)).bfloat16()
+    out = lin(a.to(DEV))
+    assert torch.equal(kernels.w4a16_dequant(lin.packed, K, N, 128).cpu(), w_ref[lin.perm.cpu().long()])
+    assert rel_err(out, quant.w4a16_gemm(a, w_ref)) < 1e-3
+
+
+@pytest.mark.parametrize("method,g", [("awq", 128), ("gptq", 128), ("awq", -1), ("gptq", 64)])
+def test_nibble_repack_plus_marlin_order_scales_assemble_to_the_same_blobs(method, g):
+    """The operator-level drop-in's two steps — repack(q_weight) -> nibble tiles, then
+    assemble(nibbles, Marlin-order scales, Marlin-packed zero points) — give byte for byte the blobs
+    the one-step prepack builds from the checkpoint tensors."""
+    K, N = 512, 384 if g != -1 else 256
+    ck = quant.random_awq_checkpoint(K, N, g, seed=5) if method == "awq" else quant.random_gptq_checkpoint(K, N, g, seed=5)
+    sc = ck["scales"]
+    nib = kernels.w4a16_repack_nibbles(ck["qweight"].to(DEV), method)
+    assert nib.shape == (K // 16, N * 2) and nib.dtype == torch.int32
+    if method == "awq":
+        z = quant.unpack_awq(ck["qzeros"])
+        want = kernels.w4a16_prepack_awq(ck["qweight"].to(DEV), ck["qzeros"].to(DEV), sc.to(DEV), g)
+        mz = quant.marlin_zero_points(z).to(DEV)
+    else:
+        want = kernels.w4a16_prepack_gptq(ck["qweight"].to(DEV), None, sc.to(DEV), g)
+        mz = None                                                      # symmetric: zero point 8
+    got = kernels.w4a16_assemble_marlin(nib, quant.permute_marlin_scales(sc).to(DEV), mz, K, N, g)
+    assert torch.equal(got, want)

@@ -98,3 +98,127 @@ def test_cpp_decode_demo_builds_and_refuses_to_run_without_a_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "1", "2", "16", "1"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+_REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(_REF, "src", "kernels")),
+                    reason="needs the reference tree (dev container only)")
+def test_a_translation_unit_against_the_references_own_headers_links_with_the_shim(tmp_path):
+    """SURVEY 8b "operator-level signatures": a caller compiled against the REFERENCE's headers
+    (layernorm_kernels.h, pos_embedding_kernels.h, kv_cache_kernels.h, activation_kernels.h,
+    attention/attn_api.h, quantization/marlin.h — untouched, from /root/reference) links against
+    _b200_shim.so with every symbol it uses resolved: the link-time swap of :kernels,
+    :attention.kernels and :marlin.kernels needs no source edit."""
+    import subprocess
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    import __graft_entry__ as g
+    g._build_shim()
+    src = tmp_path / "caller.cpp"
+    src.write_text(r'''
+#include "layernorm_kernels.h"
+#include "pos_embedding_kernels.h"
+#include "kv_cache_kernels.h"
+#include "activation_kernels.h"
+#include "attention/attn_api.h"
+#include "quantization/marlin.h"
+// take the address of every function the reference's layers call, with the reference's types
+void* table[] = {
+  (void*)static_cast<void (*)(torch::Tensor&, torch::Tensor, torch::Tensor, float)>(&llm::kernel::rms_norm),
+  (void*)static_cast<void (*)(torch::Tensor&, torch::Tensor, torch::Tensor, float)>(&llm::kernel::gemma_rms_norm),
+  (void*)static_cast<void (*)(torch::Tensor&, torch::Tensor&, torch::Tensor, torch::Tensor, float)>(&llm::kernel::rms_norm_residual),
+  (void*)static_cast<void (*)(torch::Tensor&, torch::Tensor, torch::Tensor, torch::Tensor, float)>(&llm::kernel::layer_norm),
+  (void*)static_cast<void (*)(torch::Tensor&, torch::Tensor&, const torch::Tensor&, const torch::Tensor&, int, bool)>(&llm::kernel::apply_rotary_pos_emb),
+  (void*)static_cast<void (*)(const torch::Tensor&, const torch::Tensor&, const torch::Tensor&, torch::Tensor&, torch::Tensor&)>(&llm::kernel::set_kv_cache),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::gelu_new),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::gelu_fast),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::silu),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::gelu_new_with_mul),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::gelu_fast_with_mul),
+  (void*)static_cast<torch::Tensor (*)(torch::Tensor)>(&llm::kernel::silu_with_mul),
+  (void*)&llm::paged_kv_varlen_mha,
+  (void*)&marlin::gptq_gemm,
+  (void*)&marlin::gptq_repack,
+  (void*)&marlin::awq_repack,
+};
+int main() { return table[0] == nullptr; }
+''')
+    try:
+        inc = ce.include_paths(device_type="cuda")
+    except TypeError:
+        inc = ce.include_paths(cuda=True)
+    tl = os.path.join(os.path.dirname(torch.__file__), "lib")
+    so_dir = os.path.join(ROOT, "scalellm_b200")
+    cmd = (["g++", "-std=c++17", "-O0", str(src), "-o", str(tmp_path / "caller"),
+            "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI)),
+            "-I" + os.path.join(_REF, "src", "kernels")] + ["-I" + i for i in inc] +
+           ["-I" + sysconfig.get_paths()["include"], "-I/usr/local/cuda/include",
+            os.path.join(so_dir, "_b200_shim.so"), "-L" + so_dir, "-lb200decode",
+            "-L" + tl, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+            "-L" + sysconfig.get_config_var("LIBDIR"), "-lpython" + sysconfig.get_config_var("LDVERSION"),
+            "-Wl,-rpath," + so_dir, "-Wl,-rpath," + tl, "-Wl,--no-undefined"])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_marlin_drop_in_with_the_references_exact_signatures():
+    """marlin::awq_repack(q_weight, out, num_bits) / gptq_repack(q_weight, perm, out, num_bits) /
+    gptq_gemm(..., scales and zeros in Marlin's order, has_zp, g_idx, perm ...) exactly as
+    qlinear_awq_marlin_impl.cpp:99-125,332-365 and qlinear_gptq_marlin_impl.cpp:43-72 call them:
+    results bit-identical to the one-step B200 prepack path, zeros honoured, act-order honoured,
+    fp16 refused instead of reinterpreted, the weight assembled once."""
+    import numpy as np
+    from scalellm_b200 import kernels
+    from oracle import quant
+    m = load_shim()
+    dev = "cuda"
+    K, N, M, g = 1024, 512, 48, 128
+    e = torch.empty(0, dtype=torch.int32, device=dev)
+    ws = torch.zeros(N // 64 * 16, dtype=torch.int32, device=dev)      # Marlin's lock workspace
+    a = torch.randn(M, K, device=dev).bfloat16()
+    # ---- AWQ: has_zp = true ----
+    ck = quant.random_awq_checkpoint(K, N, g, seed=11)
+    qw, qz, sc = ck["qweight"].to(dev), ck["qzeros"].to(dev), ck["scales"].to(dev)
+    want = kernels.w4a16_gemm(a, kernels.w4a16_prepack_awq(qw, qz, sc, g), N, g)
+    out = torch.empty(K // 16, N * 2, dtype=torch.int32, device=dev)
+    m.marlin_awq_repack_ref(qw, out, 4)
+    ms = quant.permute_marlin_scales(ck["scales"]).to(dev)
+    mz = quant.marlin_zero_points(quant.unpack_awq(ck["qzeros"])).to(dev)
+    n0 = m.assembled_weights()
+    c = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        m.marlin_gemm(a, out, c, ms, mz, e, e, ws, 4, True, True, True)
+    assert torch.equal(c, want) and m.assembled_weights() == n0 + 1 and int(ws.abs().sum()) == 0
+    # the zero points are really read: has_zp = false means the symmetric 8
+    m.marlin_gemm(a, out, c, ms, e, e, e, ws, 4, True, False, True)
+    sym = kernels.w4a16_gemm(a, kernels.w4a16_prepack_awq(
+        qw, quant.pack_awq(np.full((K // g, N), 8)).to(dev), sc, g), N, g)
+    assert torch.equal(c, sym) and not torch.equal(c, want)
+    # fp16 activations are refused, not reinterpreted
+    with pytest.raises(RuntimeError, match="bf16"):
+        m.marlin_gemm(a.half(), out, c, ms, mz, e, e, ws, 4, True, True, True)
+    # ---- GPTQ act-order: gptq_repack(perm) + gptq_gemm(g_idx sorted, perm) ----
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 16, size=(K, N))
+    order = rng.permutation(K)
+    g_idx = np.empty(K, dtype=np.int32)
+    g_idx[order] = np.arange(K) // g
+    s2 = (torch.randn(K // g, N).abs() * 0.01 + 1e-3).bfloat16()
+    perm = torch.argsort(torch.from_numpy(g_idx).long(), stable=True).to(torch.int32)
+    # the act-order weight by definition: row k uses the scale of group g_idx[k], zero point 8
+    w_ref = (s2[torch.from_numpy(g_idx).long()].float() * torch.from_numpy(q - 8).float()).bfloat16()
+    out2 = torch.empty(K // 16, N * 2, dtype=torch.int32, device=dev)
+    m.marlin_gptq_repack_ref(quant.pack_gptq(q).to(dev), perm.to(dev), out2, 4)
+    g_sorted = torch.from_numpy(g_idx)[perm.long()].to(torch.int32).to(dev)
+    m.marlin_gemm(a, out2, c, quant.permute_marlin_scales(s2).to(dev), e, g_sorted, perm.to(dev), ws, 4,
+                  True, False, True)
+    want2 = quant.w4a16_gemm(a.cpu(), w_ref)
+    from tests.util import rel_err
+    assert rel_err(c, want2) < 1e-3
+    with pytest.raises(RuntimeError, match="K-sharded"):
+        m.marlin_gemm(a, out2, c, quant.permute_marlin_scales(s2).to(dev), e, g_sorted, perm.to(dev), ws, 4,
+                      False, False, True)

@@ -24,18 +24,35 @@ from scalellm_b200.model_parallel import ProcessGroup  # noqa: E402
 
 
 def timed(fn, iters=200, warm=20):
+    """us per call: `inner` calls captured into one CUDA graph, replayed; device-timed, max over
+    ranks.  (Issued eagerly from Python these 5-20 us kernels measure the host's launch rate.)"""
+    inner = 20
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     dist.barrier()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(inner):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    reps = max(1, iters // inner)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e3 / iters], device="cuda")
+    t = torch.tensor([e0.elapsed_time(e1) * 1e3 / (reps * inner)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 

@@ -5,10 +5,12 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-2}
-timeout 1500 python -m pytest tests/test_gpu_allreduce.py -m gpu -q --tb=short -p no:cacheprovider \
-    > gpurun_out/pytest_allreduce_n$N.log 2>&1
-echo "pytest allreduce rc=$? : $(tail -3 gpurun_out/pytest_allreduce_n$N.log | tr '\n' ' ')"
-grep -E "Error|assert|FAILED" gpurun_out/pytest_allreduce_n$N.log | head -10
+if [ "${SKIP_TESTS:-0}" != 1 ]; then
+  timeout 1500 python -m pytest tests/test_gpu_allreduce.py -m gpu -q --tb=short -p no:cacheprovider \
+      > gpurun_out/pytest_allreduce_n$N.log 2>&1
+  echo "pytest allreduce rc=$? : $(tail -3 gpurun_out/pytest_allreduce_n$N.log | tr '\n' ' ')"
+  grep -E "Error|assert|FAILED" gpurun_out/pytest_allreduce_n$N.log | head -10
+fi
 run() {  # tag, env assignments...
   tag=$1; shift
   env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
