@@ -241,3 +241,68 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
         outs.append(mha_ref(q[qs:qe], k_cache[slots], v_cache[slots], sm_scale, alibi_slopes,
                             logits_soft_cap, sliding_window))
     return torch.cat(outs, dim=0) if outs else q.new_zeros(q.shape)
+
+
+# ----------------------------------------------------------------------------
+# Sampling tail: logits processors — src/kernels/sampling/penalty_kernels.cu:9-33,52-75,107-140,
+# src/kernels/sampling/softmax_kernels.cu:11-54 (kernel semantics: every store rounds to T)
+# ----------------------------------------------------------------------------
+def apply_temperature_penalty(logits: torch.Tensor, temperatures: torch.Tensor) -> torch.Tensor:
+    t = temperatures.to(torch.float32)
+    inv = torch.where(t == 0, torch.ones_like(t), 1.0 / t)
+    return (logits.to(torch.float32) * inv[:, None]).to(logits.dtype)
+
+
+def apply_repetition_penalty(logits: torch.Tensor, token_ids: torch.Tensor, lens: torch.Tensor,
+                             penalties: torch.Tensor) -> torch.Tensor:
+    out = logits.clone()
+    for b in range(logits.shape[0]):
+        ids = token_ids[b, : int(lens[b])].long()
+        x = out[b, ids].to(torch.float32)
+        p = float(penalties[b].to(torch.float32))
+        out[b, ids] = torch.where(x < 0, x * p, x / p).to(logits.dtype)
+    return out
+
+
+def apply_frequency_presence_penalty(logits: torch.Tensor, token_ids: torch.Tensor, counts: torch.Tensor,
+                                     lens: torch.Tensor, freq: torch.Tensor, pres: torch.Tensor) -> torch.Tensor:
+    out = logits.clone()
+    for b in range(logits.shape[0]):
+        n = int(lens[b])
+        ids, c = token_ids[b, :n].long(), counts[b, :n]
+        keep = c > 0
+        ids, c = ids[keep], c[keep].to(torch.float32)
+        x = out[b, ids].to(torch.float32)
+        x = x - c * float(freq[b].to(torch.float32))       # two separately rounded fp32 steps
+        x = x - float(pres[b].to(torch.float32))
+        out[b, ids] = x.to(logits.dtype)
+    return out
+
+
+def softmax_inplace_semantics(logits: torch.Tensor) -> torch.Tensor:
+    """exp(x - max) is STORED in T and read back for the sum; sum + 1e-6 divides (softmax_kernels.cu:30-53).
+    The sum's order is the kernel's (strided by min(vocab, 1024) threads, then two butterflies)."""
+    import numpy as np
+    dt = logits.dtype
+    x = logits.to(torch.float32)
+    e = torch.exp(x - x.max(dim=-1, keepdim=True).values).to(dt)
+    ef = e.to(torch.float32).numpy()
+    rows, n = ef.shape
+    BD = min(n, 1024)
+    nvw = (BD + 31) // 32
+    v = np.zeros((rows, nvw * 32), dtype=np.float32)
+    for k in range((n + BD - 1) // BD):
+        seg = ef[:, k * BD: min(n, (k + 1) * BD)]
+        v[:, : seg.shape[1]] = (v[:, : seg.shape[1]] + seg).astype(np.float32)
+    lane = np.arange(32)
+
+    def butterfly(a):
+        for m in (16, 8, 4, 2, 1):
+            a = (a + a[..., lane ^ m]).astype(np.float32)
+        return a
+
+    warp = butterfly(v.reshape(rows, nvw, 32))[..., 0]
+    red = np.zeros((rows, 32), dtype=np.float32)
+    red[:, :nvw] = warp
+    denom = torch.from_numpy((butterfly(red)[:, 0] + np.float32(1e-6)).astype(np.float32))
+    return (e.to(torch.float32) / denom[:, None]).to(dt)

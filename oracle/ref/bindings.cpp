@@ -26,6 +26,19 @@ extern "C" int marlin_dequant_kat(const void* scales, int S, void* out_zp, void*
 #include "layernorm_kernels.h"
 #include "pos_embedding_kernels.h"
 
+// src/kernels/sampling/sampling_kernels.h:7-29 (declared here: that header also pulls in curand for
+// the top-k sampler, which is not part of this build)
+namespace llm::kernel {
+void apply_temperature_penalty(torch::Tensor& logits, const torch::Tensor& temperatures);
+void apply_repetition_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                              const torch::Tensor& token_ids_lens, const torch::Tensor& penalities);
+void apply_frequency_presence_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                                      const torch::Tensor& token_counts, const torch::Tensor& token_ids_lens,
+                                      const torch::Tensor& frequency_penalties,
+                                      const torch::Tensor& presence_penalties);
+void invoke_softmax(torch::Tensor& logits);
+}  // namespace llm::kernel
+
 PYBIND11_MODULE(_ref_kernels, m) {
   m.doc() = "vectorch-ai/ScaleLLM src/kernels compiled for sm_100a (test oracle)";
   m.def("rms_norm", [](torch::Tensor out, torch::Tensor x, torch::Tensor w, double eps) {
@@ -78,6 +91,17 @@ PYBIND11_MODULE(_ref_kernels, m) {
   m.def("gelu_fast", &llm::kernel::gelu_fast);
   m.def("gelu_new_with_mul", &llm::kernel::gelu_new_with_mul);
   m.def("gelu_fast_with_mul", &llm::kernel::gelu_fast_with_mul);
+  m.def("apply_temperature_penalty", [](torch::Tensor logits, torch::Tensor t) {
+    llm::kernel::apply_temperature_penalty(logits, t);
+  });
+  m.def("apply_repetition_penalty", [](torch::Tensor logits, torch::Tensor ids, torch::Tensor lens, torch::Tensor p) {
+    llm::kernel::apply_repetition_penalty(logits, ids, lens, p);
+  });
+  m.def("apply_frequency_presence_penalty", [](torch::Tensor logits, torch::Tensor ids, torch::Tensor counts,
+                                               torch::Tensor lens, torch::Tensor f, torch::Tensor p) {
+    llm::kernel::apply_frequency_presence_penalty(logits, ids, counts, lens, f, p);
+  });
+  m.def("invoke_softmax", [](torch::Tensor logits) { llm::kernel::invoke_softmax(logits); });
   m.def("silu", &llm::kernel::silu);
   m.def("silu_with_mul", &llm::kernel::silu_with_mul);
 }

@@ -142,6 +142,48 @@ torch::Tensor gelu_impl(const torch::Tensor& input, int act, bool with_mul) {
   return out;
 }
 }  // namespace
+void apply_temperature_penalty(torch::Tensor& logits, const torch::Tensor& temperatures) {
+  TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && temperatures.is_contiguous() &&
+                  temperatures.scalar_type() == logits.scalar_type(),
+              "apply_temperature_penalty: contiguous [batch, vocab] logits, temperatures of the same dtype");
+  ok(b200_apply_temperature(logits.data_ptr(), temperatures.const_data_ptr(), logits.size(0), logits.size(1),
+                            dtype_of(logits), stream()),
+     "apply_temperature_penalty");
+}
+
+void apply_repetition_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                              const torch::Tensor& token_ids_lens, const torch::Tensor& penalities) {
+  TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && token_ids.is_contiguous() &&
+                  token_ids.scalar_type() == torch::kLong && token_ids_lens.scalar_type() == torch::kInt,
+              "apply_repetition_penalty: int64 token_ids [batch, max_len], int32 lens");
+  ok(b200_apply_repetition_penalty(logits.data_ptr(), token_ids.const_data_ptr<int64_t>(),
+                                   token_ids_lens.const_data_ptr<int32_t>(), penalities.const_data_ptr(),
+                                   logits.size(0), logits.size(1), token_ids.size(1), dtype_of(logits), stream()),
+     "apply_repetition_penalty");
+}
+
+void apply_frequency_presence_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                                      const torch::Tensor& token_counts,
+                                      const torch::Tensor& token_ids_lens,
+                                      const torch::Tensor& frequency_penalties,
+                                      const torch::Tensor& presence_penalties) {
+  TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && token_ids.is_contiguous() &&
+                  token_counts.is_contiguous() && token_ids.scalar_type() == torch::kLong &&
+                  token_counts.scalar_type() == torch::kInt && token_ids_lens.scalar_type() == torch::kInt,
+              "apply_frequency_presence_penalty: int64 ids, int32 counts / lens");
+  ok(b200_apply_frequency_presence_penalty(
+         logits.data_ptr(), token_ids.const_data_ptr<int64_t>(), token_counts.const_data_ptr<int32_t>(),
+         token_ids_lens.const_data_ptr<int32_t>(), frequency_penalties.const_data_ptr(),
+         presence_penalties.const_data_ptr(), logits.size(0), logits.size(1), token_ids.size(1),
+         dtype_of(logits), stream()),
+     "apply_frequency_presence_penalty");
+}
+
+void invoke_softmax(torch::Tensor& logits) {
+  TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous(), "invoke_softmax: contiguous [batch, vocab]");
+  ok(b200_softmax(logits.data_ptr(), logits.size(0), logits.size(1), dtype_of(logits), stream()), "softmax");
+}
+
 torch::Tensor gelu_new(torch::Tensor input) { return gelu_impl(input, 1, false); }
 torch::Tensor gelu_fast(torch::Tensor input) { return gelu_impl(input, 2, false); }
 torch::Tensor gelu_new_with_mul(torch::Tensor input) { return gelu_impl(input, 1, true); }

@@ -49,6 +49,18 @@ torch::Tensor gelu_fast(torch::Tensor input);
 torch::Tensor gelu_new_with_mul(torch::Tensor input);
 torch::Tensor gelu_fast_with_mul(torch::Tensor input);
 
+// the sampling tail's logits processors, in place (src/kernels/sampling/sampling_kernels.h:7-29;
+// the top-k / top-p sampler of that header is not replaced: greedy selection is b200_argmax)
+void apply_temperature_penalty(torch::Tensor& logits, const torch::Tensor& temperatures);
+void apply_repetition_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                              const torch::Tensor& token_ids_lens, const torch::Tensor& penalities);
+void apply_frequency_presence_penalty(torch::Tensor& logits, const torch::Tensor& token_ids,
+                                      const torch::Tensor& token_counts,
+                                      const torch::Tensor& token_ids_lens,
+                                      const torch::Tensor& frequency_penalties,
+                                      const torch::Tensor& presence_penalties);
+void invoke_softmax(torch::Tensor& logits);
+
 // B200 extension used by B200AttnHandler: rope + cache write in one launch
 // (bit-identical to apply_rotary_pos_emb followed by set_kv_cache).
 void rope_and_set_kv_cache(torch::Tensor& querys, torch::Tensor& keys, const torch::Tensor& values,

@@ -49,7 +49,9 @@ def _worker(rank, world, port, algo=""):
                 torch.cuda.synchronize()
                 # ours == fp32 rank-order sum rounded once
                 assert torch.equal(y, host_sum.to(dtype)), (dtype, shape)
-                tol = 1e-2 if dtype != torch.float32 else 1e-5
+                # NCCL rounds its partial sums to the element type in its own order: only a sanity
+                # bound against it (the exact statement is the host sum above)
+                tol = 1e-2 * world if dtype != torch.float32 else 1e-5 * world
                 assert torch.allclose(y.float(), ref.float(), rtol=tol, atol=tol)
                 # every rank holds the same bits
                 ys = [torch.empty_like(y) for _ in range(world)]
