@@ -416,7 +416,7 @@ def run_b200(a, rank, world, local_rank):
     ttft = "skipped (--no-ttft)"
     if not a.no_ttft:
         try:
-            ttft = measure_ttft(model, pool, args, dev, chunk=a.ttft_chunk, n_req=8)
+            ttft = measure_ttft(model, pool, args, dev, chunk=a.ttft_chunk, n_req=8, use_graph=use_graph)
         except Exception as e:  # noqa: BLE001  (never cost the bench line)
             ttft = f"failed: {type(e).__name__}: {e}"
         barrier()
@@ -474,7 +474,8 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed: int = 4):
+def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed: int = 4,
+                 use_graph: bool = True):
     """Unloaded time-to-first-token: one request at a time, prompt length ~ U[128, 2048] (SURVEY
     §8d traffic shape), chunked prefill with a `chunk`-token budget through the SAME kernels as the
     decode step (q_len = chunk rows per sequence: correct, not the tuned path), eager launches.
@@ -484,11 +485,21 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
     import torch
     from scalellm_b200 import kernels
     from scalellm_b200.decode_step import StepBuffers, build_decode_batch, prefill_chunks
+    from scalellm_b200.decode_step import GraphedStep
     rng = np.random.default_rng(seed)
     cap_tokens = pool.n_blocks_of(0) * pool.block_size
     lens = [int(min(x, cap_tokens)) for x in rng.integers(128, 2049, size=n_req)]
     bufs = StepBuffers(dev, chunk, 1, pool.n_blocks_of(0))
     out_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+    # full chunks replay ONE captured graph (the reference captures its decode batch sizes the same
+    # way, model_runner.cpp:141-210; the metadata lives in the static buffers, the scalars baked in
+    # are the chunk length and the largest kv_len); the ragged last chunk runs eagerly
+    graph = None
+    if use_graph:
+        hb0 = build_decode_batch(pool, [chunk], [chunk], args.vocab_size, seed=seed)
+        hb0.kv_max = cap_tokens
+        sel_last = torch.tensor([chunk - 1], device=dev)
+        graph = GraphedStep(model, bufs, hb0, greedy=True, last_token_idxes=sel_last)
     times = []
     for i, P in enumerate([lens[0]] + lens):            # first request = warm-up, not recorded
         t0 = time.perf_counter()
@@ -497,8 +508,11 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
             hb = build_decode_batch(pool, [kv_len], [q_len], args.vocab_size, seed=seed + ci)
             tokens, positions, params = bufs.upload(hb)
             last = ci == len(sched) - 1
-            sel = torch.tensor([q_len - 1], device=dev) if last else torch.zeros(0, dtype=torch.int64, device=dev)
-            ids = model(tokens, positions, params, last_token_idxes=sel, greedy=True)
+            if graph is not None and q_len == chunk:
+                ids = graph.replay()
+            else:
+                sel = torch.tensor([q_len - 1], device=dev) if last else torch.zeros(0, dtype=torch.int64, device=dev)
+                ids = model(tokens, positions, params, last_token_idxes=sel, greedy=True)
             if last:
                 out_host.copy_(ids, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -508,7 +522,7 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
     return {"p50_ms": times[len(times) // 2], "min_ms": times[0], "max_ms": times[-1],
             "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
             "kernels": "decode path (the stream attention kernel with q_len = chunk rows; no prefill-tuned kernel yet)",
-            "load": "unloaded (one request at a time), eager launches" +
+            "load": "unloaded (one request at a time); full chunks replay a CUDA graph, the ragged last chunk is eager" +
                     (", int4 linears as dequant + library bf16 GEMM above 256 rows"
                      if os.environ.get("B200_W4_PREFILL_DENSE") == "1" else "")}
 

@@ -250,6 +250,8 @@ def paged_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
 def apply_temperature_penalty(logits: torch.Tensor, temperatures: torch.Tensor) -> torch.Tensor:
     t = temperatures.to(torch.float32)
     inv = torch.where(t == 0, torch.ones_like(t), 1.0 / t)
+    # `logits[i] *= inv` is c10's operator*=(T&, const T&): the float inverse is converted to T first
+    inv = inv.to(logits.dtype).to(torch.float32)
     return (logits.to(torch.float32) * inv[:, None]).to(logits.dtype)
 
 
@@ -271,9 +273,11 @@ def apply_frequency_presence_penalty(logits: torch.Tensor, token_ids: torch.Tens
         n = int(lens[b])
         ids, c = token_ids[b, :n].long(), counts[b, :n]
         keep = c > 0
-        ids, c = ids[keep], c[keep].to(torch.float32)
-        x = out[b, ids].to(torch.float32)
-        x = x - c * float(freq[b].to(torch.float32))       # two separately rounded fp32 steps
+        ids, c = ids[keep], c[keep].to(torch.float64)
+        x = out[b, ids].to(torch.float64)
+        # `logit -= count * freq` compiles to one fused multiply-add (exact product, one rounding):
+        # evaluated in double and rounded to fp32; then the presence term, a plain fp32 subtract
+        x = (x - c * float(freq[b].to(torch.float32))).to(torch.float32)
         x = x - float(pres[b].to(torch.float32))
         out[b, ids] = x.to(logits.dtype)
     return out
@@ -305,4 +309,5 @@ def softmax_inplace_semantics(logits: torch.Tensor) -> torch.Tensor:
     red = np.zeros((rows, 32), dtype=np.float32)
     red[:, :nvw] = warp
     denom = torch.from_numpy((butterfly(red)[:, 0] + np.float32(1e-6)).astype(np.float32))
+    denom = denom.to(dt).to(torch.float32)     # `logits[i] /= sum` is operator/=(T&, const T&): the divisor is rounded to T
     return (e.to(torch.float32) / denom[:, None]).to(dt)

@@ -329,9 +329,10 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     W4Plan plan, int row_n, int64_t split_stride, ArNormArgs<T> na, long long* trace) {
   constexpr int VEC = 16 / sizeof(T);
   ar_stamp(trace, 6);
-  pdl_wait();               // the contribution (and the residual stream) come from earlier kernels
   pdl_launch_dependents();  // the next GEMM may start prefetching its weights while we exchange
-  ar_stamp(trace, 0);
+  // Before griddepcontrol.wait: whatever does not depend on the producing GEMM.  When this kernel
+  // starts, that GEMM has passed its own wait, so everything older — the previous collective (the
+  // epoch), the previous norm (the residual stream) — is complete and visible.
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
@@ -343,6 +344,21 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
   const int64_t row_v0 = (int64_t)row * row_vecs;
   const int64_t left = nvec_total - row_v0;
   const int row_len = left < row_vecs ? (int)left : row_vecs;
+  uint4 res_pre[VPT], w_pre[VPT];
+  int cnt_pre[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int j = threadIdx.x + k * AR_THREADS;
+    if (j < row_len) {
+      if constexpr (NORM) {
+        res_pre[k] = reinterpret_cast<const uint4*>(na.residual)[row_v0 + j];
+        w_pre[k] = *reinterpret_cast<const uint4*>(na.weight + j * VEC);
+      }
+      if constexpr (FROM_PARTIALS) cnt_pre[k] = w4_contrib_col(plan, j * 8);
+    }
+  }
+  pdl_wait();               // the contribution comes from the producing GEMM
+  ar_stamp(trace, 0);
 
   // ---- 1. push my contribution of this row into the owner's inbox, slot = my rank ----
   {
@@ -355,8 +371,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
         uint4 c;
         if constexpr (FROM_PARTIALS) {
           float a[8];
-          const int col = j * 8;  // 8 consecutive columns of this row, inside one n tile
-          w4_sum_partials8(a, partials + (row_v0 + j) * 8, split_stride, w4_contrib_col(plan, col));
+          // 8 consecutive columns of this row, inside one n tile
+          w4_sum_partials8(a, partials + (row_v0 + j) * 8, split_stride, cnt_pre[k]);
           T* ce = reinterpret_cast<T*>(&c);
 #pragma unroll
           for (int q = 0; q < 8; ++q) ce[q] = Num<T>::from_f(a[q]);
@@ -424,8 +440,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
       const int j = threadIdx.x + k * AR_THREADS;
       if (j < row_len) {
         const T* rv = reinterpret_cast<const T*>(&red[k]);  // what the plain all-reduce would store
-        uint4 rraw = reinterpret_cast<const uint4*>(na.residual)[row_v0 + j];
-        const T* rr = reinterpret_cast<const T*>(&rraw);
+        const T* rr = reinterpret_cast<const T*>(&res_pre[k]);
         uint4 sraw;
         T* sv = reinterpret_cast<T*>(&sraw);
 #pragma unroll
@@ -444,8 +459,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     for (int k = 0; k < VPT; ++k) {
       const int j = threadIdx.x + k * AR_THREADS;
       if (j < row_len) {
-        uint4 wraw = *reinterpret_cast<const uint4*>(na.weight + j * VEC);
-        const T* w = reinterpret_cast<const T*>(&wraw);
+        const T* w = reinterpret_cast<const T*>(&w_pre[k]);
         uint4 oraw;
         T* o = reinterpret_cast<T*>(&oraw);
 #pragma unroll

@@ -248,22 +248,35 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   static_assert(VEC == 8, "16-bit element types only");
   __shared__ float red[32];
   extern __shared__ float sq[];  // [n] fp32: the row, for the reference-ordered sum of squares
-  pdl_wait();
-  pdl_launch_dependents();
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   T* res_row = residual + row * n;
   T* out_row = out + row * n;
   const float* p_row = partials + row * n;
+  // Before griddepcontrol.wait: everything that does not depend on the producing GEMM — the
+  // residual row (last written by the previous norm kernel, several launches back), the norm
+  // weights and the stream-K contributor counts; their latency overlaps the GEMM's tail.
+  uint4 rraw[MAXV], wraw[MAXV];
+  int cnt[MAXV];
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = threadIdx.x + j * THREADS;
+    if (v < nvec) {
+      rraw[j] = ld_v4(res_row + v * VEC);
+      wraw[j] = ld_v4(weight + v * VEC);
+      cnt[j] = w4_contrib_col(plan, v * VEC);
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   float x[MAXV][VEC];
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int v = threadIdx.x + j * THREADS;
     if (v < nvec) {
       float a[VEC];
-      w4_sum_partials8(a, p_row + v * VEC, split_stride, w4_contrib_col(plan, v * VEC));
-      uint4 rraw = ld_v4(res_row + v * VEC);
-      const T* r = reinterpret_cast<const T*>(&rraw);
+      w4_sum_partials8(a, p_row + v * VEC, split_stride, cnt[j]);
+      const T* r = reinterpret_cast<const T*>(&rraw[j]);
       uint4 sraw;
       T* sv = reinterpret_cast<T*>(&sraw);
 #pragma unroll
@@ -283,8 +296,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   for (int j = 0; j < MAXV; ++j) {
     const int v = threadIdx.x + j * THREADS;
     if (v < nvec) {
-      uint4 wraw = ld_v4(weight + v * VEC);
-      const T* w = reinterpret_cast<const T*>(&wraw);
+      const T* w = reinterpret_cast<const T*>(&wraw[j]);
       uint4 oraw;
       T* o = reinterpret_cast<T*>(&oraw);
 #pragma unroll
@@ -680,18 +692,22 @@ __global__ void __launch_bounds__(256, 3) silu_mul_splitk_kernel(T* __restrict__
                                                               const float* __restrict__ partials,
                                                               W4Plan plan, int64_t slot_stride,
                                                               int64_t rows, int inter) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int nv = inter / 8;
   const int64_t total = rows * nv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
+  // the first item's index arithmetic and contributor counts do not depend on the GEMM: before the wait
+  const int64_t idx0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int j0 = (int)(idx0 % nv);
+  const int cg0 = w4_contrib_col(plan, j0 * 8), cu0 = w4_contrib_col(plan, inter + j0 * 8);
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t idx = idx0; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / nv;
     const int j = (int)(idx - r * nv);
     const float* prow = partials + r * (2 * (int64_t)inter);
     float g[8], u[8];
-    w4_sum_partials8(g, prow + j * 8, slot_stride, w4_contrib_col(plan, j * 8));
-    w4_sum_partials8(u, prow + inter + j * 8, slot_stride, w4_contrib_col(plan, inter + j * 8));
+    const bool first = idx == idx0;
+    w4_sum_partials8(g, prow + j * 8, slot_stride, first ? cg0 : w4_contrib_col(plan, j * 8));
+    w4_sum_partials8(u, prow + inter + j * 8, slot_stride, first ? cu0 : w4_contrib_col(plan, inter + j * 8));
     uint4 orr;
     T* o = reinterpret_cast<T*>(&orr);
 #pragma unroll

@@ -802,7 +802,11 @@ __global__ void __launch_bounds__(32, (D <= 128 ? (OCC ? ATT_OCC_CTAS : 8) : 3))
 paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
                           const __grid_constant__ CUtensorMap vmap, const AttnParams p,
                           int64_t total_tiles, int n_seq) {
-  pdl_wait();
+  // Under programmatic dependent launch this kernel becomes resident while its predecessor (the
+  // RoPE + KV-write consumer) still runs.  Everything up to the first Q / KV access depends only on
+  // the step's metadata (lengths, block tables: inputs of the step, older than any kernel of it), so
+  // the pipeline fill below — three dependent global round trips — runs in the predecessor's
+  // shadow; griddepcontrol.wait sits just before the first query load.
   pdl_launch_dependents();
   using Cfg = AttnCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
@@ -963,6 +967,7 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
   ItemMeta sA = stageA(stage0());   // lengths in flight
   int s0 = stage0();
   uint32_t qa[KS][QR], qn[KS][QR];
+  pdl_wait();  // q and the newest KV slots are the predecessor's output
   load_q(cur, qa);
   load_q(nxt, qn);
 
@@ -1607,12 +1612,12 @@ static AttnPlan make_plan(int64_t batch, int max_q_len, int max_kv_len, int n_he
   return pl;
 }
 
-// B200_ATTN_PDL=1 launches the stream kernel and the combine pass programmatically already at
-// B200_PDL level 1 (experiment knob; default: only at level 2)
+// The stream kernel and the combine pass are launched programmatically at B200_PDL level 1 (their
+// metadata prologue overlaps the predecessor's tail); B200_ATTN_PDL=0: only at level 2
 static int attn_pdl_level() {
   static const int lv = [] {
     const char* e = getenv("B200_ATTN_PDL");
-    return (e && e[0] == '1') ? 1 : 2;
+    return (e && e[0] == '0') ? 2 : 1;
   }();
   return lv;
 }

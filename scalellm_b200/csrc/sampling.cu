@@ -8,7 +8,10 @@
 
 namespace b200 {
 
-// logits[b, :] *= (t[b] == 0 ? 1 : 1 / t[b]), the product rounded to T (penalty_kernels.cu:9-33)
+// logits[b, :] *= (t[b] == 0 ? 1 : 1 / t[b]) (penalty_kernels.cu:9-33).  The reference writes
+// `logits[i] *= inv` with logits of type T and inv a float: c10's compound assignment converts the
+// float to T FIRST (operator*=(T&, const T&)), so the inverse temperature is rounded to T, then the
+// product is rounded to T.
 template <typename T>
 __global__ void __launch_bounds__(256) temperature_kernel(T* __restrict__ logits,
                                                           const T* __restrict__ temperatures,
@@ -19,7 +22,7 @@ __global__ void __launch_bounds__(256) temperature_kernel(T* __restrict__ logits
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float t = Num<T>::to_f(temperatures[i / vocab]);
-    const float inv = t == 0.f ? 1.0f : 1.0f / t;
+    const float inv = rnd<T>(t == 0.f ? 1.0f : 1.0f / t);
     logits[i] = Num<T>::from_f(Num<T>::to_f(logits[i]) * inv);
   }
 }
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(256) frequency_presence_penalty_kernel(
 // In-place softmax in the reference's loop shape (softmax_kernels.cu:11-54): BD = min(vocab, 1024)
 // threads stride the row; the exponentials are stored to the row in T and READ BACK for the sum
 // (so the sum is over rounded values); the sum's butterflies are those of reduce_kernel_utils.cuh;
-// the divisor gets + 1e-6.
+// the divisor gets + 1e-6 and — `logits[i] /= s_sum_val` being operator/=(T&, const T&) — is
+// rounded to T before the division.
 template <typename T>
 __global__ void __launch_bounds__(1024) softmax_kernel(T* __restrict__ logits, int64_t vocab) {
   pdl_wait();
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(1024) softmax_kernel(T* __restrict__ logits, i
   if (lane == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
   t = lane < nw ? red[lane] : 0.f;
-  const float denom = warp_sum(t) + 1e-6f;
+  const float denom = rnd<T>(warp_sum(t) + 1e-6f);
   if (active)
     for (int64_t i = threadIdx.x; i < vocab; i += BD) row[i] = Num<T>::from_f(Num<T>::to_f(row[i]) / denom);
 }

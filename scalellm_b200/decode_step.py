@@ -384,10 +384,13 @@ class GraphedStep:
     """Capture one decode step (fixed batch size / max kv len) and replay it.  Inputs are
     refreshed by copying into the static buffers (model_runner.cpp:180-210)."""
 
-    def __init__(self, model: LlamaDecoder, bufs: StepBuffers, hb: HostBatch, greedy: bool = True):
+    def __init__(self, model: LlamaDecoder, bufs: StepBuffers, hb: HostBatch, greedy: bool = True,
+                 last_token_idxes: Optional[torch.Tensor] = None):
+        """last_token_idxes (a static device tensor): only those rows reach lm_head — a captured
+        prefill chunk needs the logits of its last token only (llama.h:281-289)."""
         self.model, self.bufs = model, bufs
         self.tokens, self.positions, self.params = bufs.upload(hb)
-        self.greedy = greedy
+        self.greedy, self.last = greedy, last_token_idxes
         torch.cuda.synchronize()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -401,7 +404,8 @@ class GraphedStep:
             self.out = self._run()
 
     def _run(self) -> torch.Tensor:
-        return self.model(self.tokens, self.positions, self.params, greedy=self.greedy)
+        return self.model(self.tokens, self.positions, self.params, last_token_idxes=self.last,
+                          greedy=self.greedy)
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()

@@ -81,14 +81,15 @@ def test_logits_processors_match_the_oracle_and_the_reference_kernels(dtype, B, 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("B,V", [(64, 128256), (5, 1000), (2, 50257)])
 def test_softmax_in_place(dtype, B, V):
-    """The GPU's __expf differs from the host's exp by an ulp here and there, so the oracle comparison
-    carries 2 ulp of T; against the reference's own kernel (same instruction) it is bit for bit."""
+    """The GPU's __expf (ex2.approx of x * log2 e) differs from the host's exp by up to ~2e-5 relative
+    at the arguments met here (|x - max| up to ~25), so the oracle comparison carries 2 ulp of T plus
+    that; against the reference's own kernel (same instruction) it is bit for bit."""
     logits = (torch.randn(B, V, generator=torch.Generator().manual_seed(V)) * 3).to(dtype)
     x = logits.to(DEV).clone()
     kernels.invoke_softmax(x)
     want = ops.softmax_inplace_semantics(logits)
     ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11, torch.float32: 2.0 ** -22}[dtype]
-    assert bool(((x.cpu().float() - want.float()).abs() <= 2 * ulp * want.float().abs() + 1e-12).all())
+    assert bool(((x.cpu().float() - want.float()).abs() <= (2 * ulp + 4e-5) * want.float().abs() + 1e-12).all())
     assert abs(float(x.float().sum(-1).mean()) - 1.0) < 2e-2
     ref = _ref()
     if ref is not None:
