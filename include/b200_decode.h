@@ -333,6 +333,20 @@ B200_API int b200_silu_mul_splitk(void* out, const float* partials, int splits, 
 B200_API int b200_debug_w4a16_plan(int64_t N, int64_t K, int ctas, int nsub, int32_t* plan_out,
                                    int32_t* first_owner_out, int32_t* contrib_out);
 
+/* ------------------------------------------------------------------------ *
+ * A8  Dense bf16 linear, decode-sized batches
+ *     replaces F::linear -> cuBLASLt of ColumnParallelLinearImpl / RowParallelLinearImpl::forward
+ *     (src/layers/linear/parallel_linear.cpp:256-263,294-308) and lm_head
+ *     (src/models/meta/llama.h:259-265): C[M, N] = A[M, K] W[N, K]^T (+ bias), bf16 in / out,
+ *     fp32 accumulation, one rounding.  W is the nn.Linear weight as the checkpoint stores it
+ *     ([N, K] row-major, row stride ldw elements); N %% 8 == 0, K %% 64 == 0; any M (one pass over
+ *     W per 128 rows).  workspace: b200_dense_workspace_bytes (fp32 stream-K partials).
+ * ------------------------------------------------------------------------ */
+B200_API int64_t b200_dense_workspace_bytes(int64_t M, int64_t N, int64_t K);
+B200_API int b200_dense_gemm(void* C, const void* A, const void* W, const void* bias /*nullable [N]*/,
+                             int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw, int64_t ldc,
+                             void* workspace, int64_t workspace_bytes, b200_stream_t stream);
+
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */
 B200_API void b200_debug_set_trace(void* device_buffer);

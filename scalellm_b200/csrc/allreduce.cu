@@ -20,16 +20,18 @@
 // Two algorithms for the all-reduce (B200_AR_ALGO = oneshot | twoshot; default twoshot above two ranks):
 //   * ONE-SHOT (world 2): every block stages its slice in its own buffer, publishes a flag to every
 //     peer, waits for theirs and pulls all `world` copies (all loads in flight before the first add).
-//   * TWO-SHOT, row partitioned (the form that scales to 8 ranks): the message is cut into rows
-//     (one block per row; for the decoder's [tokens, hidden] messages a row is a token).  Row t is
-//     owned by rank t / ceil(rows / world).  Every rank PUSHES its contribution of row t into the
-//     owner's inbox (slot = source rank) and publishes flags1[src][t]; the owner sums the world
-//     slots in rank order in fp32 (bit-identical to the one-shot result and to a host sum in rank
-//     order), rounds once and pushes the reduced row into every rank's result buffer, then
-//     publishes flags2[t]; every rank then consumes row t from its own memory.  Per rank and call
-//     NVLink carries (world-1)/world of the message out and the same in, twice — 0.9 MB at 8
-//     ranks instead of the one-shot's 3.7 MB pull — and the critical path is two one-way NVLink
-//     hops, not `world` dependent round trips.
+//   * TWO-SHOT, column partitioned (the form that scales to 8 ranks): the message is cut into rows
+//     (one block per row; for the decoder's [tokens, hidden] messages a row is a token) and every
+//     row into `world` column chunks; chunk o of every row is owned by rank o.  Every rank PUSHES
+//     its contribution of a chunk into the owner's inbox (slot = source rank); the owner sums the
+//     world slots in rank order in fp32 (bit-identical to the one-shot result and to a host sum in
+//     rank order), rounds once and pushes the reduced chunk into every rank's result buffer; every
+//     rank then consumes the row from its own memory.  Every block of every rank sends and reduces
+//     the same amount (the first cut of this round partitioned by rows: 8 of a rank's 64 blocks did
+//     all of its reducing and 7x the sending, 15.9 us per fused call at 8 ranks against 9.6 at 2).
+//     Per rank and call NVLink carries (world-1)/world of the message out and the same in, twice —
+//     0.9 MB at 8 ranks instead of the one-shot's 3.7 MB pull — and the critical path is two
+//     one-way NVLink hops, not `world` dependent round trips.
 //
 // Fused forms (the row-parallel GEMM -> all-reduce -> residual add -> RMSNorm chain of a TP
 // decoder layer, models/meta/llama.h:170-177):
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(ArDevPtrs
 }
 
 // ---------------------------------------------------------------------------------------------
-// Two-shot, row-partitioned all-reduce (file header), LL ("low latency") transport: every 16-byte
+// Two-shot, column-partitioned all-reduce (file header), LL ("low latency") transport: every 16-byte
 // store that crosses NVLink carries 8 bytes of payload and two copies of the call's epoch —
 // { data0, epoch, data1, epoch } — and the receiver polls the data itself until both epoch words
 // match (8-byte aligned stores are single-copy atomic, so a matching flag vouches for its
@@ -339,8 +341,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
   const int64_t par_off = (e & 1) ? max_bytes : 0;
 
   const int row = blockIdx.x, rows = gridDim.x;
-  const int R = (rows + world - 1) / world;  // rows per owner
-  const int owner = row / R, lrow = row - owner * R;
+  const int C = (row_vecs + world - 1) / world;  // vectors of a row per owner (column partition)
   const int64_t row_v0 = (int64_t)row * row_vecs;
   const int64_t left = nvec_total - row_v0;
   const int row_len = left < row_vecs ? (int)left : row_vecs;
@@ -360,14 +361,15 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
   pdl_wait();               // the contribution comes from the producing GEMM
   ar_stamp(trace, 0);
 
-  // ---- 1. push my contribution of this row into the owner's inbox, slot = my rank ----
+  // ---- 1. push my contribution of every vector into its owner's inbox, slot = my rank ----
   {
-    uint4* inbox = reinterpret_cast<uint4*>(ptrs.base[owner] + par_off);
-    const int64_t slot_v0 = ((int64_t)rank * R + lrow) * row_vecs;
+    const int64_t slot_v0 = ((int64_t)rank * rows + row) * C;
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int j = threadIdx.x + k * AR_THREADS;
       if (j < row_len) {
+        const int owner = j / C;
+        uint4* inbox = reinterpret_cast<uint4*>(ptrs.base[owner] + par_off);
         uint4 c;
         if constexpr (FROM_PARTIALS) {
           float a[8];
@@ -379,24 +381,28 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
         } else {
           c = reinterpret_cast<const uint4*>(data_in)[row_v0 + j];
         }
-        ll_store_vec(inbox, slot_v0 + j, c, e);
+        ll_store_vec(inbox, slot_v0 + (j - owner * C), c, e);
       }
     }
   }
   ar_stamp(trace, 1);
 
-  // ---- 2. the owner reduces the world slots in rank order and pushes the row to everyone ----
+  // ---- 2. the owner of a vector reduces its world slots in rank order and pushes the result to
+  //         everyone; 3. everyone else picks the reduced vector up from its own result buffer ----
   uint4 red[VPT];
-  if (owner == rank) {
+  {
     const uint4* inbox = reinterpret_cast<const uint4*>(local + par_off);
+    const uint4* res = reinterpret_cast<const uint4*>(local + ar_result_off(max_bytes) + par_off);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int j = threadIdx.x + k * AR_THREADS;
-      if (j < row_len) {
+      if (j >= row_len) continue;
+      const int owner = j / C;
+      if (owner == rank) {
         uint4 v[AR_MAX_WORLD];
 #pragma unroll
         for (int r = 0; r < AR_MAX_WORLD; ++r)
-          if (r < world) v[r] = ll_load_vec(inbox, ((int64_t)r * R + lrow) * row_vecs + j, e);
+          if (r < world) v[r] = ll_load_vec(inbox, ((int64_t)r * rows + row) * C + (j - owner * C), e);
         float acc[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
@@ -411,16 +417,9 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
           if (r < world && r != rank)
             ll_store_vec(reinterpret_cast<uint4*>(ptrs.base[r] + ar_result_off(max_bytes) + par_off),
                          row_v0 + j, red[k], e);
+      } else {
+        red[k] = ll_load_vec(res, row_v0 + j, e);
       }
-    }
-    ar_stamp(trace, 3);
-  } else {
-    // ---- 3. everyone else picks the reduced row up from its own result buffer ----
-    const uint4* res = reinterpret_cast<const uint4*>(local + ar_result_off(max_bytes) + par_off);
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      const int j = threadIdx.x + k * AR_THREADS;
-      if (j < row_len) red[k] = ll_load_vec(res, row_v0 + j, e);
     }
     ar_stamp(trace, 4);
   }
@@ -640,8 +639,8 @@ template <typename T, bool FROM_PARTIALS, bool NORM>
 static int ar_launch_twoshot(b200_ar_comm* c, const T* in, T* out, int64_t nvec, int row_vecs,
                              int rows, const float* partials, const W4Plan& plan, int row_n,
                              int64_t split_stride, ArNormArgs<T> na, cudaStream_t st) {
-  const int R = (rows + c->world - 1) / c->world;
-  if ((int64_t)c->world * R * row_vecs * 32 > c->max_bytes)   // LL lines: 2x the payload bytes
+  const int C = (row_vecs + c->world - 1) / c->world;        // vectors of a row per owner
+  if ((int64_t)c->world * C * rows * 32 > c->max_bytes)      // LL lines: 2x the payload bytes
     return set_error(B200_ERR_WORKSPACE, "ar_allreduce: %d rows of %d B exceed the %lld B symmetric buffer",
                      rows, row_vecs * 16, (long long)c->max_bytes);
   const ArDevPtrs ptrs = ar_ptrs(c);
@@ -868,7 +867,7 @@ static int ar_launch(b200_ar_comm* c, void* data, int64_t count, int dtype, cons
   if (!partials && nvec > (int64_t)AR_THREADS * AR_MAX_ROWS) row_vecs = 2 * AR_THREADS;
   const int64_t rows = (nvec + row_vecs - 1) / row_vecs;
   if (ar_use_twoshot(c->world) && rows <= AR_MAX_ROWS && row_vecs <= 2 * AR_THREADS &&
-      (int64_t)(rows + c->world) * row_vecs * 32 <= c->max_bytes) {
+      (int64_t)rows * (row_vecs + c->world) * 32 <= c->max_bytes) {
     switch (dtype) {
       case B200_BF16: {
         using T = __nv_bfloat16;

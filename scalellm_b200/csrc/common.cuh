@@ -446,6 +446,21 @@ __host__ __device__ __forceinline__ int w4_contrib_col(const W4Plan& pl, int col
 constexpr int W4_MAX_SLOTS = 8;
 // The partition b200_w4a16_gemm_splitk uses for M rows x a [K, N] weight on the current device.
 W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M);
+// partials [slots][M][N] -> C (bf16, + bias): the reduction pass of the plain GEMM entry points
+// (w4a16.cu; N % 8 == 0, the partition's tiles may overhang N)
+int w4_launch_reduce(__nv_bfloat16* C, const float* partials, const __nv_bfloat16* bias, int M, int N,
+                     int64_t ldc, int64_t slot_stride, const W4Plan& plan, cudaStream_t st);
+
+// prefill_attn.cu: the tcgen05 prefill / chunked-prefill attention kernel behind
+// b200_paged_attn_decode (taken for >= 64 packed query rows at head_dim 128)
+bool prefill_attn_eligible(int max_q_len, int group, int head_dim, int block_size);
+int launch_prefill_attn(void* out, const void* q, const void* k_cache, const void* v_cache,
+                        const int32_t* q_cu_lens, const int32_t* kv_cu_lens, const int32_t* block_table,
+                        const int32_t* block_cu_lens, const float* alibi, int64_t batch, int64_t n_tokens_bound,
+                        int n_heads, int n_kv_heads, int64_t n_slots, int64_t q_stride_t, int64_t q_stride_h,
+                        int64_t o_stride_t, int64_t o_stride_h, int64_t kv_stride_s, int64_t kv_stride_h,
+                        int block_size, int max_q_len, float sm_scale, float soft_cap, int window, int dtype,
+                        cudaStream_t st);
 
 // Device side of programmatic dependent launch: pdl_wait() blocks until the predecessor kernel
 // has completed and its writes are visible; pdl_launch_dependents() allows the successor's early

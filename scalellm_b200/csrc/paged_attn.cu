@@ -1779,6 +1779,15 @@ int b200_paged_attn_decode(void* out, const void* q, const void* k_cache, const 
   if (batch == 0 || max_q_len <= 0 || max_kv_len <= 0) return B200_OK;
 
   const int group = (int)(n_heads / n_kv_heads);
+  // prefill / chunked prefill (>= 64 packed query rows per block): the tcgen05 flash kernel of
+  // prefill_attn.cu — same operator, no workspace
+  if (prefill_attn_eligible(max_q_len, group, (int)head_dim, block_size) && is_aligned(out, 16) &&
+      o_stride_t % 8 == 0 && o_stride_h % 8 == 0)
+    return launch_prefill_attn(out, q, k_cache, v_cache, q_cu_lens, kv_cu_lens, block_table, block_cu_lens,
+                               alibi_slopes, batch, batch * (int64_t)max_q_len, (int)n_heads, (int)n_kv_heads,
+                               n_slots, q_stride_t, q_stride_h, o_stride_t, o_stride_h, kv_stride_s,
+                               kv_stride_h, block_size, max_q_len, sm_scale, logits_soft_cap, sliding_window,
+                               dtype, static_cast<cudaStream_t>(stream));
   const AttnPlan pl = make_plan(batch, max_q_len, max_kv_len, (int)n_heads, (int)n_kv_heads,
                                 (int)head_dim, block_size);
   AttnParams p{};

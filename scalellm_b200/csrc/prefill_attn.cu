@@ -1,0 +1,451 @@
+// prefill_attn.cu — prefill / chunked-prefill paged attention on the 5th-generation tensor cores
+// (same operator as the decode kernel: llm::paged_kv_varlen_mha,
+// src/kernels/attention/attn_api.cpp:14-73, whose one kernel — Sm80CollectiveMha,
+// collective/sm80_collective_mha.cuh:131-402, mma.sync — serves prefill in the reference).
+//
+// Taken for query blocks of >= 64 packed rows (rows = (query token, head of the kv head's group),
+// the reference's own packing of q_len x group into M, sm80_kernel_mha.cuh:208-262), head_dim 128.
+// One CTA per (sequence, kv head, block of 128 packed rows); flash-attention over 128-key tiles:
+//   * warp 4 — producer: Q block once (3-D TMA {64 d, G heads, 128/G tokens} x 2, SWIZZLE_128B), then
+//     per tile the paged K and V rows as TMA boxes {64 d, min(block_size, 8) slots} through the block
+//     table (first-slot ids, sm80_kernel_mha.cuh:148-152) into a 2-stage ring; a tile lands as the
+//     tcgen05 canonical layouts directly: K = B operand, K-major atoms [8 keys x 64 d]; V = B operand
+//     of the second GEMM, MN-major atoms [8 keys x 64 d] — the same bytes, described differently;
+//   * warp 5 — MMA issuer: S = Q K^T (M 128 rows x N 128 keys x K 128) and PV = P V (M 128 x N 128 d
+//     x K 128 keys), tcgen05.mma.kind::f16, fp32 in TMEM (S and PV: 128 columns each);
+//   * warps 0-3 — softmax, thread <-> row (TMEM lane): two passes over S in TMEM (row max, then
+//     exp2 / sum), P rounded to T like the reference (sm80_collective_mha.cuh:289-290) and stored to
+//     shared memory as the K-major A operand of the second GEMM; O kept in registers, rescaled by
+//     exp2(m_old - m_new) and advanced by each tile's PV read back from TMEM.  Online softmax in
+//     the exp2 domain, masks (causal diagonal kv_len - q_len, sliding window, alibi, soft cap)
+//     exactly as the decode kernel.
+// No split-KV (a prefill block has enough CTAs), no workspace.
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int PF_ROWS = 128, PF_KEYS = 128, PF_D = 128;
+constexpr int PF_THREADS = 6 * 32;
+constexpr int PF_WARP_TMA = 4, PF_WARP_MMA = 5;
+constexpr int PF_ATOM = 1024;               // 8 rows x 128 B
+constexpr int PF_CHUNK = 16 * PF_ATOM;      // 128 rows x 64 elements: 16 KB
+constexpr int PF_TILE = 2 * PF_CHUNK;       // 128 x 128 elements: 32 KB
+constexpr size_t PF_SMEM = 1024 + (size_t)PF_TILE * (1 /*Q*/ + 2 /*K*/ + 2 /*V*/ + 1 /*P*/) + 16 * 8 + 64;
+
+struct PrefillParams {
+  void* out;
+  const int32_t* q_cu_lens;
+  const int32_t* kv_cu_lens;
+  const int32_t* block_table;
+  const int32_t* block_cu_lens;
+  const float* alibi;
+  int64_t o_stride_t, o_stride_h;
+  int n_kv_heads, group, tokens_per_block;  // tokens_per_block = 128 / group
+  int block_shift, block_mask, box_rows;
+  float scale_log2, cap_in, cap_out_log2;
+  int use_cap, window;
+};
+
+// kind::f16 instruction descriptor: D = f32, A / B of format fmt (0 = f16, 1 = bf16), A K-major,
+// B K-major (b_mn = 0) or MN-major (b_mn = 1)
+__host__ __device__ constexpr uint32_t pf_idesc(uint32_t M, uint32_t N, uint32_t fmt, uint32_t b_mn) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// MN-major, 128-byte swizzle: atoms [8 k x 64 mn]; LBO = bytes between 64-element blocks along MN,
+// SBO = bytes between 8-row groups along K (cute::UMMA::make_umma_desc<Major::MN>)
+__device__ __forceinline__ uint64_t pf_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PF_THREADS, 1)
+prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap1,
+                    const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                    const PrefillParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* q_smem = base;
+  uint8_t* k_smem = q_smem + PF_TILE;        // 2 stages
+  uint8_t* v_smem = k_smem + 2 * PF_TILE;    // 2 stages
+  uint8_t* p_smem = v_smem + 2 * PF_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + PF_TILE);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* kv_full = bars + 1;      // 2
+  uint64_t* kv_empty = bars + 3;     // 2
+  uint64_t* s_full = bars + 5;       // 1
+  uint64_t* p_full = bars + 6;       // 1
+  uint64_t* pv_full = bars + 7;      // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int G = p.group, TPB = p.tokens_per_block;
+  // geometry from the step's metadata (inputs of the step: readable before griddepcontrol.wait)
+  const int q_begin = p.q_cu_lens[b], q_len = p.q_cu_lens[b + 1] - q_begin;
+  const int kv_len = p.kv_cu_lens[b + 1] - p.kv_cu_lens[b];
+  const int tok0 = rb * TPB;
+  if (tok0 >= q_len) return;  // this sequence has fewer row blocks than the longest one
+  const int n_tok = min(TPB, q_len - tok0);
+  const int q_pos0 = kv_len - q_len;                       // causal diagonal (sm80_kernel_mha.cuh:258-262)
+  const int kv_end = q_pos0 + tok0 + n_tok;                // last row's keys end here
+  const int kv_begin = p.window >= 0 ? max(0, q_pos0 + tok0 - p.window) : 0;
+  const int t_begin = kv_begin / PF_KEYS, t_end = (kv_end + PF_KEYS - 1) / PF_KEYS;
+  const int n_tiles = t_end - t_begin;
+  const int blk_cu = p.block_cu_lens[b];
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, PF_ROWS);
+    mbar_init(pv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == PF_WARP_MMA) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  if (warp == PF_WARP_TMA && lane == 0) {
+    prefetch_tensormap(&qmap);
+    prefetch_tensormap(&qmap1);
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t s_tmem = tmem_base, pv_tmem = tmem_base + 128;
+  pdl_launch_dependents();
+  constexpr uint32_t FMT = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;  // tcgen05 kind::f16 input format
+
+  if (warp == PF_WARP_TMA) {
+    // ===================== producer =====================
+    pdl_wait();  // q and the newest KV slots are the predecessor's output
+    if (lane == 0) {
+      if (n_tok == TPB) {   // one box per 64-d chunk: {64 d, G heads, 128 / G tokens}
+        mbar_arrive_expect_tx(q_full, PF_TILE);
+        tma_load_3d(q_smem, &qmap, q_full, 0, kvh * G, q_begin + tok0);
+        tma_load_3d(q_smem + PF_CHUNK, &qmap, q_full, 64, kvh * G, q_begin + tok0);
+      } else {              // ragged last block of a sequence: token by token, never past its tokens
+        mbar_arrive_expect_tx(q_full, (uint32_t)(n_tok * G * 128 * 2));
+        for (int t = 0; t < n_tok; ++t) {
+          tma_load_3d(q_smem + t * G * 128, &qmap1, q_full, 0, kvh * G, q_begin + tok0 + t);
+          tma_load_3d(q_smem + PF_CHUNK + t * G * 128, &qmap1, q_full, 64, kvh * G, q_begin + tok0 + t);
+        }
+      }
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      const int pos0 = (t_begin + i) * PF_KEYS;
+      const int valid = min(PF_KEYS, kv_end - pos0);                       // keys of this tile that exist
+      const int boxes = (valid + p.box_rows - 1) / p.box_rows;             // TMA boxes per chunk per tensor
+      if (lane == 0) {
+        mbar_wait(&kv_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], (uint32_t)(boxes * p.box_rows * 128 * 4));
+      }
+      __syncwarp();
+      for (int bx = lane; bx < boxes; bx += 32) {
+        const int pos = pos0 + bx * p.box_rows;
+        const int slot0 = p.block_table[blk_cu + (pos >> p.block_shift)] + (pos & p.block_mask);
+        uint8_t* kd = k_smem + s * PF_TILE + bx * p.box_rows * 128;
+        uint8_t* vd = v_smem + s * PF_TILE + bx * p.box_rows * 128;
+        tma_load_4d(kd, &kmap, &kv_full[s], 0, 0, kvh, slot0);
+        tma_load_4d(kd + PF_CHUNK, &kmap, &kv_full[s], 0, 1, kvh, slot0);
+        tma_load_4d(vd, &vmap, &kv_full[s], 0, 0, kvh, slot0);
+        tma_load_4d(vd + PF_CHUNK, &vmap, &kv_full[s], 0, 1, kvh, slot0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == PF_WARP_MMA) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = pf_idesc(PF_ROWS, PF_KEYS, FMT, 0);
+    constexpr uint32_t idesc_pv = pf_idesc(PF_ROWS, PF_D, FMT, 1);
+    const uint32_t q_a = smem_u32(q_smem), k_a = smem_u32(k_smem), v_a = smem_u32(v_smem),
+                   p_a = smem_u32(p_smem);
+    mbar_wait(q_full, 0);
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      mbar_wait(&kv_full[s], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // S = Q K^T over d: 16 per step, 4 steps per 64-d chunk
+          const uint32_t off = (ks >> 2) * PF_CHUNK + (ks & 3) * 32;
+          umma_bf16(s_tmem, umma_desc_kmajor_sw128(q_a + off), umma_desc_kmajor_sw128(k_a + s * PF_TILE + off),
+                    idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, i & 1);  // P(i) is in shared memory (and PV(i-1) has been read back)
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // PV = P V over keys: 16 per step = two 8-key atoms of V
+          const uint32_t p_off = (ks >> 2) * PF_CHUNK + (ks & 3) * 32;
+          umma_bf16(pv_tmem, umma_desc_kmajor_sw128(p_a + p_off),
+                    pf_desc_mnmajor_sw128(v_a + s * PF_TILE + ks * 2 * PF_ATOM, PF_CHUNK, PF_ATOM), idesc_pv,
+                    ks > 0 ? 1u : 0u);
+        }
+        umma_commit(pv_full);
+        umma_commit(&kv_empty[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / output: thread <-> packed row =====================
+    const int r = threadIdx.x;                     // 0..127 = TMEM lane
+    const int qi = r / G, g = r - qi * G;          // token inside the block, head inside the group
+    const bool row_ok = qi < n_tok;
+    const int head = kvh * G + g;
+    const int row_end = row_ok ? q_pos0 + tok0 + qi + 1 : 0;               // keys [row_begin, row_end)
+    const int row_begin = p.window >= 0 ? max(0, q_pos0 + tok0 + qi - p.window) : 0;
+    const float slope_log2 = p.alibi ? p.alibi[head] * 1.4426950408889634f : 0.f;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    float o[PF_D];
+#pragma unroll
+    for (int i = 0; i < PF_D; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, corr = 1.f;
+    auto score = [&](uint32_t raw, int pos) -> float {
+      const float acc = __uint_as_float(raw);
+      float v = p.use_cap ? tanhf(acc * p.cap_in) * p.cap_out_log2 : acc * p.scale_log2;
+      v = fmaf(slope_log2, (float)pos, v);
+      return (pos >= row_begin && pos < row_end) ? v : -INFINITY;
+    };
+    auto add_pv = [&](float c) {   // o = o * c + PV (the tile whose PV is in TMEM)
+#pragma unroll
+      for (int c0 = 0; c0 < PF_D; c0 += 32) {
+        uint32_t x[32];
+        tmem_ld_32x32b_x32(pv_tmem + lane_addr + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], c, __uint_as_float(x[i]));
+      }
+    };
+    for (int i = 0; i < n_tiles; ++i) {
+      const int pos0 = (t_begin + i) * PF_KEYS;
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the tile
+      float mx = m;
+#pragma unroll 1
+      for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
+        uint32_t x[32];
+        tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score(x[j], pos0 + c0 + j));
+      }
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      const float corr_new = exp2f(m - ms);         // rescales everything accumulated so far
+      // the previous tile's PV must be folded in (and P's buffer released by its MMAs) before P is rewritten
+      if (i > 0) {
+        mbar_wait(pv_full, (i - 1) & 1);
+        tc_fence_after();
+        add_pv(corr);
+      }
+      corr = corr_new;
+      // pass 2: p = exp2(s - m), row sum, P -> T -> shared memory (K-major, 128-byte swizzle)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
+        uint32_t x[32];
+        tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = exp2f(score(x[j], pos0 + c0 + j) - ms);
+          const float p1 = exp2f(score(x[j + 1], pos0 + c0 + j + 1) - ms);
+          pk[j >> 1] = Num<T>::pack(p0, p1);   // P rounded to T for the second GEMM ...
+          sum += p0 + p1;                       // ... the row sum stays fp32 (online_softmax.cuh:39-162)
+        }
+        // 32 keys = four 16-byte units of row r inside chunk (c0 / 64)
+        uint8_t* prow = p_smem + (c0 >> 6) * PF_CHUNK + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = ((c0 & 63) >> 3) + u;
+          *reinterpret_cast<uint4*>(prow + ((unit ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      }
+      l = fmaf(l, corr_new, sum);
+      m = mx;
+      // keys of the tile that do not exist: their V rows hold whatever the ring held (maybe NaN) and
+      // 0 * NaN is NaN — zero them (their P columns are exactly 0 already)
+      const int valid = min(PF_KEYS, kv_end - pos0);
+      if (r >= valid) {
+        uint8_t* vrow = v_smem + (i & 1) * PF_TILE + (r >> 3) * PF_ATOM + (r & 7) * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          *reinterpret_cast<uint4*>(vrow + u * 16) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(vrow + PF_CHUNK + u * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_full, (n_tiles - 1) & 1);
+    tc_fence_after();
+    add_pv(corr);
+    if (row_ok) {
+      const float inv = 1.f / l;
+      T* dst = static_cast<T*>(p.out) + (int64_t)(q_begin + tok0 + qi) * p.o_stride_t + (int64_t)head * p.o_stride_h;
+#pragma unroll
+      for (int c0 = 0; c0 < PF_D; c0 += 8) {
+        uint4 v;
+        v.x = Num<T>::pack(o[c0] * inv, o[c0 + 1] * inv);
+        v.y = Num<T>::pack(o[c0 + 2] * inv, o[c0 + 3] * inv);
+        v.z = Num<T>::pack(o[c0 + 4] * inv, o[c0 + 5] * inv);
+        v.w = Num<T>::pack(o[c0 + 6] * inv, o[c0 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c0) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PF_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+struct PfMapKey {
+  const void* ptr;
+  int64_t d0, d1, d2, s1, s2;   // dims / strides (elements) of the 3-D or 4-D view
+  int box1, box2, dtype, kind;  // kind 0: q {D, H, T} box {64, box1, box2}; 1: kv {64, D/64, H, slots} box {64,1,1,box2}
+  bool operator==(const PfMapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 &&
+           box1 == o.box1 && box2 == o.box2 && dtype == o.dtype && kind == o.kind;
+  }
+};
+static std::mutex g_pf_mu;
+static std::vector<std::pair<PfMapKey, CUtensorMap>> g_pf_maps;
+
+static int pf_get_map(const PfMapKey& k, CUtensorMap* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_pf_mu);
+    for (const auto& e : g_pf_maps)
+      if (e.first == k) {
+        *out = e.second;
+        return B200_OK;
+      }
+  }
+  tensor_map_encode_fn enc = get_tensor_map_encode();
+  if (!enc) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const CUtensorMapDataType dt = k.dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap m;
+  CUresult r;
+  if (k.kind == 0) {   // q [T, H, D]: dims {D, H, T}, strides {s1 = head stride, s2 = token stride}
+    cuuint64_t dims[3] = {(cuuint64_t)k.d0, (cuuint64_t)k.d1, (cuuint64_t)k.d2};
+    cuuint64_t strides[2] = {(cuuint64_t)k.s1 * 2, (cuuint64_t)k.s2 * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)k.box1, (cuuint32_t)k.box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(&m, dt, 3, const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {             // kv cache [slots, Hkv, D] as {64, D/64, Hkv, slots}: one 64-wide chunk per box
+    cuuint64_t dims[4] = {64u, (cuuint64_t)(k.d0 / 64), (cuuint64_t)k.d1, (cuuint64_t)k.d2};
+    cuuint64_t strides[3] = {128u, (cuuint64_t)k.s1 * 2, (cuuint64_t)k.s2 * 2};
+    cuuint32_t box[4] = {64u, 1u, 1u, (cuuint32_t)k.box2};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = enc(&m, dt, 4, const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for prefill attention", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_pf_mu);
+    if (g_pf_maps.size() > 4096) g_pf_maps.clear();
+    g_pf_maps.push_back({k, m});
+  }
+  *out = m;
+  return B200_OK;
+}
+
+bool prefill_attn_eligible(int max_q_len, int group, int head_dim, int block_size) {
+  static const bool off = [] {
+    const char* e = getenv("B200_ATTN_PREFILL");
+    return e && e[0] == '0';
+  }();
+  return !off && head_dim == PF_D && group >= 1 && group <= PF_ROWS && (PF_ROWS % group) == 0 &&
+         (int64_t)max_q_len * group >= 64 && block_size >= 1;
+}
+
+int launch_prefill_attn(void* out, const void* q, const void* k_cache, const void* v_cache,
+                        const int32_t* q_cu_lens, const int32_t* kv_cu_lens, const int32_t* block_table,
+                        const int32_t* block_cu_lens, const float* alibi, int64_t batch, int64_t n_tokens_bound,
+                        int n_heads, int n_kv_heads, int64_t n_slots, int64_t q_stride_t, int64_t q_stride_h,
+                        int64_t o_stride_t, int64_t o_stride_h, int64_t kv_stride_s, int64_t kv_stride_h,
+                        int block_size, int max_q_len, float sm_scale, float soft_cap, int window, int dtype,
+                        cudaStream_t st) {
+  const int G = n_heads / n_kv_heads;
+  PrefillParams p{};
+  p.out = out;
+  p.q_cu_lens = q_cu_lens;
+  p.kv_cu_lens = kv_cu_lens;
+  p.block_table = block_table;
+  p.block_cu_lens = block_cu_lens;
+  p.alibi = alibi;
+  p.o_stride_t = o_stride_t;
+  p.o_stride_h = o_stride_h;
+  p.n_kv_heads = n_kv_heads;
+  p.group = G;
+  p.tokens_per_block = PF_ROWS / G;
+  int sh = 0;
+  while ((1 << sh) < block_size) ++sh;
+  p.block_shift = sh;
+  p.block_mask = block_size - 1;
+  p.box_rows = block_size < 8 ? block_size : 8;
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (soft_cap > 0.f) {
+    p.use_cap = 1;
+    p.cap_in = sm_scale / soft_cap;
+    p.cap_out_log2 = soft_cap * LOG2E;
+  } else {
+    p.scale_log2 = sm_scale * LOG2E;
+  }
+  p.window = window;
+  CUtensorMap qmap, qmap1, kmap, vmap;
+  // q: the extent is an upper bound of the token count (batch * max_q_len); no box ever reaches past
+  // a sequence's own tokens (full blocks use the block-sized box, ragged ones the one-token box)
+  int rc = pf_get_map(PfMapKey{q, PF_D, n_heads, n_tokens_bound, q_stride_h, q_stride_t, G, p.tokens_per_block, dtype, 0}, &qmap);
+  if (rc != B200_OK) return rc;
+  rc = pf_get_map(PfMapKey{q, PF_D, n_heads, n_tokens_bound, q_stride_h, q_stride_t, G, 1, dtype, 0}, &qmap1);
+  if (rc != B200_OK) return rc;
+  rc = pf_get_map(PfMapKey{k_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &kmap);
+  if (rc != B200_OK) return rc;
+  rc = pf_get_map(PfMapKey{v_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &vmap);
+  if (rc != B200_OK) return rc;
+  const unsigned n_rb = (unsigned)(((int64_t)max_q_len + p.tokens_per_block - 1) / p.tokens_per_block);
+  dim3 grid(n_rb, (unsigned)n_kv_heads, (unsigned)batch);
+  if (dtype == B200_BF16) {
+    auto kern = prefill_attn_kernel<__nv_bfloat16>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p);
+  } else {
+    auto kern = prefill_attn_kernel<__half>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p);
+  }
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -917,6 +917,14 @@ W4Plan w4_get_plan(int64_t N, int64_t K, int64_t M) {
   return pl;
 }
 
+int w4_launch_reduce(__nv_bfloat16* C, const float* partials, const __nv_bfloat16* bias, int M, int N,
+                     int64_t ldc, int64_t slot_stride, const W4Plan& plan, cudaStream_t st) {
+  const int64_t nvec = (int64_t)M * (N / 8);
+  B200_PDL_LAUNCH_L(1, "w4a16_reduce", w4_reduce_kernel, (unsigned)((nvec + 255) / 256), 256, 0, st, C,
+                    partials, bias, M, N, ldc, slot_stride, plan);
+  return B200_OK;
+}
+
 static int log2_int(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

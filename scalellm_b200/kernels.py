@@ -187,6 +187,37 @@ def silu_with_mul(input: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------
+# dense bf16 linear (A8): F::linear -> cuBLASLt of the reference, parallel_linear.cpp:256-263,294-308
+# ---------------------------------------------------------------------------
+def dense_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes / dtypes the tcgen05 dense kernel takes (rank-invariant: sizes, dtypes and strides of
+    freshly allocated activations only)."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+            and x.dim() >= 2 and x.shape[-1] % 64 == 0 and weight.shape[0] % 8 == 0
+            and weight.stride(1) == 1 and weight.stride(0) % 8 == 0)
+
+
+def dense_gemm(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ W^T (+ bias): A [M, K] bf16 (rows dense in K), W [N, K] bf16 as nn.Linear stores it."""
+    _cuda(a, weight, bias)
+    assert a.dim() == 2 and a.stride(1) == 1 and weight.dim() == 2 and weight.stride(1) == 1
+    M, K = a.shape
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    if a.stride(0) % 8 or a.data_ptr() % 16:
+        a = a.contiguous()
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if M == 0:
+        return out
+    ws = _workspace("dense", a.device, int(_lib.load().b200_dense_workspace_bytes(M, N, K)))
+    check(_lib.load().b200_dense_gemm(_p(out), _p(a), _p(weight), _p(bias), M, N, K, a.stride(0),
+                                      weight.stride(0), out.stride(0), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # sampling tail: logits processors (src/kernels/sampling/sampling_kernels.h:7-29), in place
 # ---------------------------------------------------------------------------
 def apply_temperature_penalty(logits: torch.Tensor, temperatures: torch.Tensor) -> None:

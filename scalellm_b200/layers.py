@@ -479,8 +479,17 @@ class RowParallelQLinear(_QLinearBase):
     __call__ = forward
 
 
+def _dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """F::linear of the reference's dense layers (parallel_linear.cpp:258,299): the tcgen05 stream
+    kernel of csrc/dense.cu for bf16 on CUDA (B200_DENSE_IMPL=cublas: the library GEMM, for A/B)."""
+    if os.environ.get("B200_DENSE_IMPL") != "cublas" and kernels.dense_supported(x, weight):
+        x2 = x.reshape(-1, x.shape[-1])
+        return kernels.dense_gemm(x2, weight).view(*x.shape[:-1], weight.shape[0])
+    return F.linear(x, weight)
+
+
 class ColumnParallelLinear:
-    """Dense bf16 column-parallel linear -> F.linear / cuBLASLt (parallel_linear.cpp:221-263)."""
+    """Dense bf16 column-parallel linear (parallel_linear.cpp:221-263): csrc/dense.cu."""
 
     def __init__(self, in_features: int, out_features: int, gather_output: bool, pa: ParallelArgs,
                  dtype, device):
@@ -495,10 +504,10 @@ class ColumnParallelLinear:
 
     def forward_local(self, x: torch.Tensor) -> torch.Tensor:
         """This rank's column shard of the output (no gather)."""
-        return F.linear(x, self.weight)
+        return _dense_linear(x, self.weight)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = F.linear(x, self.weight)
+        out = _dense_linear(x, self.weight)
         if self.pa.world_size > 1 and self.gather_output:
             out = gather_from_model_parallel_region(out, self.pa)
         return out
@@ -523,7 +532,7 @@ class RowParallelLinear:
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not self.input_is_parallelized:
             x = scatter_to_model_parallel_region(x, self.pa)
-        out = F.linear(x, self.weight)
+        out = _dense_linear(x, self.weight)
         return reduce_from_model_parallel_region(out, self.pa)
 
     __call__ = forward

@@ -122,9 +122,9 @@ class ProcessGroup:
 
     def _fits(self, rows: int, row_bytes: int) -> bool:
         """A message of `rows` rows fits the symmetric buffers (the two-shot form ships LL lines:
-        twice the payload, one extra row per rank of slack)."""
-        if self._twoshot:
-            return (rows + self._world) * row_bytes * 2 <= self._buffer_bytes
+        twice the payload, one extra vector per rank and row of slack)."""
+        if self._twoshot:   # column chunks are rounded up to whole 16-byte vectors per owner
+            return rows * (row_bytes + 16 * self._world) * 2 <= self._buffer_bytes
         return rows * row_bytes <= self._buffer_bytes
 
     def allreduce_partials_norm(self, partials, residual: torch.Tensor, weight: torch.Tensor,

@@ -121,6 +121,26 @@ torch::Tensor argmax(const torch::Tensor& logits) {
   return out;
 }
 
+// dense bf16 linear, F::linear(x, W[N, K]) of the reference's dense layers and lm_head
+// (parallel_linear.cpp:258,299; llama.h:259-265): csrc/dense.cu
+torch::Tensor dense_linear(const torch::Tensor& x, const torch::Tensor& w) {
+  TORCH_CHECK(x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16 && w.dim() == 2 &&
+                  x.size(-1) == w.size(1) && w.stride(1) == 1,
+              "dense_linear: bf16 x [.., K] and W [N, K]");
+  torch::Tensor x2 = x.reshape({-1, x.size(-1)});
+  if (x2.stride(1) != 1 || x2.stride(0) % 8 != 0) x2 = x2.contiguous();
+  const int64_t M = x2.size(0), K = x2.size(1), N = w.size(0);
+  torch::Tensor out = torch::empty({M, N}, x.options());
+  if (M == 0) return out;
+  torch::Tensor ws = torch::empty({b200_dense_workspace_bytes(M, N, K)}, x.options().dtype(torch::kByte));
+  ok(b200_dense_gemm(out.data_ptr(), x2.const_data_ptr(), w.const_data_ptr(), nullptr, M, N, K, x2.stride(0),
+                     w.stride(0), out.stride(0), ws.data_ptr(), ws.numel(), stream()),
+     "dense_gemm");
+  auto shape = x.sizes().vec();
+  shape.back() = N;
+  return out.view(shape);
+}
+
 }  // namespace kernel
 
 // ---------------------------------------------------------------------------------------------
@@ -529,7 +549,10 @@ torch::Tensor LlamaDecoderStep::forward(const torch::Tensor& tokens, const torch
     have_pending = true;
   }
   torch::Tensor hn = have_pending ? norm_residual(*final_norm_) : final_norm_->forward(h);
-  torch::Tensor logits = torch::linear(hn, lm_head_);  // dense bf16 lm_head: library GEMM (not on this path)
+  // dense bf16 lm_head: csrc/dense.cu where its shape allows (K % 64 == 0, N % 8 == 0), else the library GEMM
+  torch::Tensor logits = (lm_head_.size(1) % 64 == 0 && lm_head_.size(0) % 8 == 0)
+                             ? kernel::dense_linear(hn, lm_head_)
+                             : torch::linear(hn, lm_head_);
   return w > 1 ? pg_->allgather_lastdim(logits) : logits;
 }
 

@@ -61,6 +61,7 @@ torch::Tensor rope_and_set_kv_cache_partials(const W4Partials& p, int64_t n_head
                                              bool interleaved, torch::ScalarType dtype);
 // gate_up partials [slots, rows, 2 I] -> silu(gate) * up [rows, I]
 torch::Tensor silu_mul_partials(const W4Partials& p, torch::ScalarType dtype);
+torch::Tensor dense_linear(const torch::Tensor& x, const torch::Tensor& w);  // csrc/dense.cu
 torch::Tensor argmax(const torch::Tensor& logits);
 }  // namespace kernel
 
