@@ -477,8 +477,8 @@ def _peaks():
 def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed: int = 4,
                  use_graph: bool = True):
     """Unloaded time-to-first-token: one request at a time, prompt length ~ U[128, 2048] (SURVEY
-    §8d traffic shape), chunked prefill with a `chunk`-token budget through the SAME kernels as the
-    decode step (q_len = chunk rows per sequence: correct, not the tuned path), eager launches.
+    §8d traffic shape), chunked prefill with a `chunk`-token budget through the same operator entry
+    points as the decode step (attention: the tcgen05 prefill kernel for q_len * group >= 64 rows).
     TTFT = host time from the request's arrival (before its first metadata build) to its first
     generated token being on the host.  Reuses sequence 0's KV blocks of the pool."""
     import numpy as np
@@ -521,7 +521,9 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
     times.sort()
     return {"p50_ms": times[len(times) // 2], "min_ms": times[0], "max_ms": times[-1],
             "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
-            "kernels": "decode path (the stream attention kernel with q_len = chunk rows; no prefill-tuned kernel yet)",
+            "kernels": ("decode path (the stream attention kernel with q_len = chunk rows; B200_ATTN_PREFILL=0)"
+                        if os.environ.get("B200_ATTN_PREFILL") == "0" else
+                        "tcgen05 prefill attention (csrc/prefill_attn.cu) + the step's own GEMM / consumer kernels at M = chunk"),
             "load": "unloaded (one request at a time); full chunks replay a CUDA graph, the ragged last chunk is eager" +
                     (", int4 linears as dequant + library bf16 GEMM above 256 rows"
                      if os.environ.get("B200_W4_PREFILL_DENSE") == "1" else "")}

@@ -346,6 +346,14 @@ B200_API int64_t b200_dense_workspace_bytes(int64_t M, int64_t N, int64_t K);
 B200_API int b200_dense_gemm(void* C, const void* A, const void* W, const void* bias /*nullable [N]*/,
                              int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw, int64_t ldc,
                              void* workspace, int64_t workspace_bytes, b200_stream_t stream);
+/* Partials mode, same contract as b200_w4a16_gemm_splitk (the reduction, and whatever follows it in
+ * the layer — RoPE + KV write, residual + RMSNorm, SiLU*mul, the TP all-reduce — runs in the
+ * consumer): partials [b200_dense_splitk_splits()][M][N] fp32, M <= 128, N and K multiples of 128;
+ * the stream-K partition is the int4 GEMM's for the same (N, K), so every b200_*_splitk consumer
+ * takes these partials unchanged. */
+B200_API int b200_dense_splitk_splits(int64_t M, int64_t N, int64_t K);
+B200_API int b200_dense_gemm_splitk(float* partials, const void* A, const void* W, int64_t M, int64_t N,
+                                    int64_t K, int64_t lda, int64_t ldw, int splits, b200_stream_t stream);
 
 /* Debug hook: when non-NULL, every b200_w4a16_gemm CTA records clock64() milestones into
  * device_buffer[blockIdx.x * 16 + slot] (long long).  Pass NULL to disable (default). */

@@ -82,6 +82,8 @@ SIGNATURES = {
     "b200_permute_cols": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "b200_dense_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "b200_dense_gemm": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "b200_dense_splitk_splits": (_int, [_i64, _i64, _i64]),
+    "b200_dense_gemm_splitk": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
     "b200_ar_create": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp]),
     "b200_ar_open_peers": (_int, [_vp, _vp]),
     "b200_ar_create_all": (_int, [C.POINTER(_vp), C.POINTER(C.c_int), _int, _i64]),

@@ -339,4 +339,43 @@ int b200_dense_gemm(void* C, const void* A, const void* W, const void* bias, int
   return B200_OK;
 }
 
+int b200_dense_splitk_splits(int64_t M, int64_t N, int64_t K) {
+  (void)M;
+  if (N <= 0 || K <= 0 || N % 128 || K % 128) return 0;
+  return w4_get_plan(N, K, 128).slots;
+}
+
+int b200_dense_gemm_splitk(float* partials, const void* A, const void* W, int64_t M, int64_t N,
+                           int64_t K, int64_t lda, int64_t ldw, int splits, b200_stream_t stream) {
+  B200_CHECK_ARG(partials && A && W, "dense_gemm_splitk: null pointer");
+  B200_CHECK_ARG(M > 0 && M <= 128 && N > 0 && K > 0 && N % 128 == 0 && K % 128 == 0,
+                 "dense_gemm_splitk: 1 <= M <= 128, N %% 128 == 0, K %% 128 == 0 required");
+  B200_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0 && is_aligned(A, 16) &&
+                     is_aligned(W, 16) && is_aligned(partials, 16),
+                 "dense_gemm_splitk: rows of A and W must be 16-byte aligned and dense in K");
+  const W4Plan plan = w4_get_plan(N, K, 128);
+  B200_CHECK_ARG(splits == plan.slots, "dense_gemm_splitk: partials must have b200_dense_splitk_splits() = %d slots, got %d",
+                 plan.slots, splits);
+  auto st = static_cast<cudaStream_t>(stream);
+  CUtensorMap wmap, amap;
+  int rc = get_kmajor_map(DMapKey{W, N, K, ldw, 128}, &wmap);
+  if (rc != B200_OK) return rc;
+  const int mt = dn_pick_mt(M);
+  rc = get_kmajor_map(DMapKey{A, M, K, lda, mt}, &amap);
+  if (rc != B200_OK) return rc;
+  DenseParams p{};
+  p.partials = partials;
+  p.slot_stride = M * N;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.KT = plan.KT;
+  p.plan = plan;
+  switch (mt) {
+    case 16: return launch_dense<16>(wmap, amap, p, st);
+    case 32: return launch_dense<32>(wmap, amap, p, st);
+    case 64: return launch_dense<64>(wmap, amap, p, st);
+    default: return launch_dense<128>(wmap, amap, p, st);
+  }
+}
+
 }  // extern "C"

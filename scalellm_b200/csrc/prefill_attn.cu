@@ -71,7 +71,7 @@ template <typename T>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap1,
                     const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
-                    const PrefillParams p) {
+                    const PrefillParams p, long long* trace) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -90,6 +90,14 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  // debug trace (b200_debug_set_trace, tools/prefill_trace.py): clock64 totals per role, 16 slots per CTA
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* tr = (trace != nullptr && cta_lin < 1024) ? trace + cta_lin * 16 : nullptr;
+  long long tacc[4] = {0, 0, 0, 0};
+  long long tt = 0;
+  const long long t_start = tr ? clock64() : 0;
+#define PF_T0() do { if (tr) tt = clock64(); } while (0)
+#define PF_T1(k) do { if (tr) { const long long _n = clock64(); tacc[k] += _n - tt; tt = _n; } } while (0)
   const int G = p.group, TPB = p.tokens_per_block;
   // geometry from the step's metadata (inputs of the step: readable before griddepcontrol.wait)
   const int q_begin = p.q_cu_lens[b], q_len = p.q_cu_lens[b + 1] - q_begin;
@@ -154,11 +162,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       const int pos0 = (t_begin + i) * PF_KEYS;
       const int valid = min(PF_KEYS, kv_end - pos0);                       // keys of this tile that exist
       const int boxes = (valid + p.box_rows - 1) / p.box_rows;             // TMA boxes per chunk per tensor
+      PF_T0();
       if (lane == 0) {
         mbar_wait(&kv_empty[s], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], (uint32_t)(boxes * p.box_rows * 128 * 4));
       }
       __syncwarp();
+      PF_T1(0);
       for (int bx = lane; bx < boxes; bx += 32) {
         const int pos = pos0 + bx * p.box_rows;
         const int slot0 = p.block_table[blk_cu + (pos >> p.block_shift)] + (pos & p.block_mask);
@@ -170,6 +180,11 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         tma_load_4d(vd + PF_CHUNK, &vmap, &kv_full[s], 0, 1, kvh, slot0);
       }
       __syncwarp();
+      PF_T1(1);
+    }
+    if (tr && lane == 0) {
+      tr[8] = tacc[0];
+      tr[9] = tacc[1];
     }
   } else if (warp == PF_WARP_MMA) {
     // ===================== MMA issuer =====================
@@ -177,10 +192,14 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     constexpr uint32_t idesc_pv = pf_idesc(PF_ROWS, PF_D, FMT, 1);
     const uint32_t q_a = smem_u32(q_smem), k_a = smem_u32(k_smem), v_a = smem_u32(v_smem),
                    p_a = smem_u32(p_smem);
+    PF_T0();
     mbar_wait(q_full, 0);
+    PF_T1(3);
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i & 1;
+      PF_T0();
       mbar_wait(&kv_full[s], (i >> 1) & 1);
+      PF_T1(0);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -192,7 +211,9 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         umma_commit(s_full);
       }
       __syncwarp();
+      PF_T1(2);
       mbar_wait(p_full, i & 1);  // P(i) is in shared memory (and PV(i-1) has been read back)
+      PF_T1(1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -206,6 +227,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         umma_commit(&kv_empty[s]);
       }
       __syncwarp();
+      PF_T1(2);
+    }
+    if (tr && lane == 0) {
+      tr[6] = tacc[0];
+      tr[7] = tacc[1];
+      tr[10] = tacc[3];
+      tr[11] = tacc[2];
     }
   } else {
     // ===================== softmax / output: thread <-> packed row =====================
@@ -239,7 +267,9 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     };
     for (int i = 0; i < n_tiles; ++i) {
       const int pos0 = (t_begin + i) * PF_KEYS;
+      PF_T0();
       mbar_wait(s_full, i & 1);
+      PF_T1(0);
       tc_fence_after();
       // pass 1: row maximum of the tile
       float mx = m;
@@ -251,6 +281,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score(x[j], pos0 + c0 + j));
       }
+      PF_T1(1);
       const float ms = (mx == -INFINITY) ? 0.f : mx;
       const float corr_new = exp2f(m - ms);         // rescales everything accumulated so far
       // the previous tile's PV must be folded in (and P's buffer released by its MMAs) before P is rewritten
@@ -260,6 +291,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         add_pv(corr);
       }
       corr = corr_new;
+      PF_T1(2);
       // pass 2: p = exp2(s - m), row sum, P -> T -> shared memory (K-major, 128-byte swizzle)
       float sum = 0.f;
 #pragma unroll 1
@@ -300,6 +332,14 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(p_full);
+      PF_T1(3);
+    }
+    if (tr && r == 0) {
+      tr[1] = n_tiles;
+      tr[2] = tacc[0];
+      tr[3] = tacc[1];
+      tr[4] = tacc[2];
+      tr[5] = tacc[3];
     }
     mbar_wait(pv_full, (n_tiles - 1) & 1);
     tc_fence_after();
@@ -320,10 +360,13 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
   if (warp == PF_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+#undef PF_T0
+#undef PF_T1
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,11 +482,11 @@ int launch_prefill_attn(void* out, const void* q, const void* k_cache, const voi
   if (dtype == B200_BF16) {
     auto kern = prefill_attn_kernel<__nv_bfloat16>;
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
-    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p);
+    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   } else {
     auto kern = prefill_attn_kernel<__half>;
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
-    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p);
+    B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   }
   return B200_OK;
 }

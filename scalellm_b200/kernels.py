@@ -217,6 +217,26 @@ def dense_gemm(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
+def dense_gemm_splitk(a: torch.Tensor, weight: torch.Tensor, poison: bool = False) -> "W4Partials":
+    """Partials mode of the dense GEMM: fp32 partials [slots, M, N] in the int4 GEMM's stream-K
+    format, for the same fused consumers.  M <= 128, N and K multiples of 128."""
+    _cuda(a, weight)
+    assert a.dim() == 2 and a.dtype == torch.bfloat16 and a.stride(1) == 1
+    assert weight.dim() == 2 and weight.dtype == torch.bfloat16 and weight.stride(1) == 1
+    M, K = a.shape
+    N = weight.shape[0]
+    if a.stride(0) % 8 or a.data_ptr() % 16:
+        a = a.contiguous()
+    slots = int(_lib.load().b200_dense_splitk_splits(M, N, K))
+    assert slots > 0, "dense_gemm_splitk: N and K must be multiples of 128"
+    partials = torch.empty((slots, M, N), dtype=torch.float32, device=a.device)
+    if poison:
+        partials.fill_(float("nan"))
+    check(_lib.load().b200_dense_gemm_splitk(_p(partials), _p(a), _p(weight), M, N, K, a.stride(0),
+                                             weight.stride(0), slots, _stream()))
+    return W4Partials(partials, K)
+
+
 # ---------------------------------------------------------------------------
 # sampling tail: logits processors (src/kernels/sampling/sampling_kernels.h:7-29), in place
 # ---------------------------------------------------------------------------

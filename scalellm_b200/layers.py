@@ -488,6 +488,12 @@ def _dense_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return F.linear(x, weight)
 
 
+def _dense_partials_ok(x_rows: int, weight: torch.Tensor) -> bool:
+    return (os.environ.get("B200_DENSE_IMPL") != "cublas" and weight.is_cuda
+            and weight.dtype == torch.bfloat16 and 0 < x_rows <= 128
+            and weight.shape[0] % 128 == 0 and weight.shape[1] % 128 == 0)
+
+
 class ColumnParallelLinear:
     """Dense bf16 column-parallel linear (parallel_linear.cpp:221-263): csrc/dense.cu."""
 
@@ -505,6 +511,13 @@ class ColumnParallelLinear:
     def forward_local(self, x: torch.Tensor) -> torch.Tensor:
         """This rank's column shard of the output (no gather)."""
         return _dense_linear(x, self.weight)
+
+    def supports_partials(self, n_rows: int) -> bool:
+        """Partials for a fused consumer (rope / silu*mul), like ColumnParallelQLinear."""
+        return _dense_partials_ok(n_rows, self.weight) and not (self.pa.world_size > 1 and self.gather_output)
+
+    def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
+        return kernels.dense_gemm_splitk(x.reshape(-1, x.shape[-1]), self.weight)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out = _dense_linear(x, self.weight)
@@ -528,6 +541,20 @@ class RowParallelLinear:
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         w = sd["weight"][:, shard_range(self.full_K, self.pa.rank, self.pa.world_size)]
         self.weight.copy_(w)
+
+    def supports_partials(self, n_rows: int) -> bool:
+        """Partials for the fused residual + RMSNorm consumer (under TP: fused into the all-reduce),
+        like RowParallelQLinear."""
+        if not _dense_partials_ok(n_rows, self.weight):
+            return False
+        if self.pa.world_size == 1:
+            return True
+        pg = self.pa.process_group
+        return (os.environ.get("B200_FUSE_AR_NORM", "1") != "0" and hasattr(pg, "supports_partials_norm")
+                and pg.supports_partials_norm(n_rows, self.weight.shape[0], torch.bfloat16))
+
+    def forward_partials(self, x: torch.Tensor) -> "kernels.W4Partials":
+        return kernels.dense_gemm_splitk(x.reshape(-1, x.shape[-1]), self.weight)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not self.input_is_parallelized:

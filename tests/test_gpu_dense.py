@@ -74,3 +74,32 @@ def test_dense_layers_use_the_kernel_and_match_the_library(monkeypatch):
     y_lib = row(col(x))
     d = (y.float() - y_lib.float()).abs()
     assert bool((d <= 4 * 2.0 ** -8 * y_lib.float().abs() + 4e-3 * y_lib.float().abs().max()).all())
+
+
+@pytest.mark.parametrize("M", [1, 64, 128])
+def test_dense_partials_feed_the_int4_gemms_consumers(M):
+    """b200_dense_gemm_splitk writes the int4 GEMM's stream-K partials format: the plain reduction
+    gives the bf16 result of b200_dense_gemm bit for bit, and the fused consumers (sum + residual +
+    RMSNorm, sum + SiLU*mul) equal "reduce, then the unfused kernel" with the unused slots poisoned."""
+    g = torch.Generator(device=DEV).manual_seed(11 + M)
+    a = torch.randn(M, 4096, generator=g, device=DEV).bfloat16()
+    w = (torch.randn(4096, 4096, generator=g, device=DEV) * 0.03).bfloat16()
+    parts = kernels.dense_gemm_splitk(a, w, poison=True)
+    full = kernels.dense_gemm(a, w)
+    assert torch.equal(kernels.w4a16_reduce_partials(parts), full)
+    # residual + RMSNorm consumer
+    res = torch.randn(M, 4096, generator=g, device=DEV).bfloat16()
+    wn = torch.randn(4096, generator=g, device=DEV).bfloat16()
+    r1, r2 = res.clone(), res.clone()
+    o1 = torch.empty_like(res)
+    kernels.rms_norm_residual_splitk(o1, r1, parts, wn, 1e-5)
+    o2 = torch.empty_like(res)
+    kernels.rms_norm_residual(o2, r2, full, wn, 1e-5)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2)
+    # SiLU * mul consumer over a gate_up-shaped weight
+    w2 = (torch.randn(2048, 4096, generator=g, device=DEV) * 0.03).bfloat16()
+    p2 = kernels.dense_gemm_splitk(a, w2, poison=True)
+    f2 = kernels.dense_gemm(a, w2)
+    got = kernels.silu_mul_splitk(p2, torch.bfloat16)
+    want = kernels.silu_mul(f2[:, :1024], f2[:, 1024:])
+    assert torch.equal(got, want)

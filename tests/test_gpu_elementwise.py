@@ -164,7 +164,7 @@ def test_silu_odd_width_scalar_path():
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
-@pytest.mark.parametrize("rows,n", [(64, 128256), (3, 1000), (1, 7), (5, 4099)])
+@pytest.mark.parametrize("rows,n", [(64, 128256), (3, 1000), (1, 7), (5, 4099), (2, 16387), (7, 50264)])
 def test_argmax_matches_torch(dtype, rows, n):
     """Greedy sampling tail: first index of the maximum (ties are common in bf16 logits), NaN wins."""
     from scalellm_b200 import kernels

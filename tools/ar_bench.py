@@ -102,8 +102,9 @@ def main():
         t = trace.cpu().view(-1, 8)[:M].double()
         t0 = t[:, 0].min()
         names = {0: "entry (after griddepcontrol.wait)", 1: "contribution stored + flag sent",
-                 2: "owner: all contributions arrived", 3: "owner: reduced row pushed + flag sent",
-                 4: "non-owner: reduced row arrived", 5: "row done (residual + norm written)"}
+                 2: "one-shot: all contributions arrived",
+                 4: "reduced row complete (own chunk reduced + pushed, the others arrived)",
+                 5: "row done (residual + norm written)"}
         for r in range(world):
             if rank == r:
                 print(f"   rank {r} phases, us since the first block's entry (median / max over the {M} blocks):", flush=True)

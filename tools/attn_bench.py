@@ -28,6 +28,12 @@ def main():
         # the default plan only, benchmark shape, block_size 8, no reference kernel
         one_shape(64, 2048, 32, 8, 128, bss=(8,), only_auto=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "prefill":
+        # prefill / chunked-prefill shapes (csrc/prefill_attn.cu; B200_ATTN_PREFILL=0 in the
+        # environment times the decode stream kernel on the same problem), the reference's kernel beside
+        for B, q_len, kv_len in ((1, 128, 2048), (1, 512, 2048), (1, 2048, 2048), (8, 512, 2048), (4, 2048, 2048)):
+            prefill_shape(B, q_len, kv_len, 32, 8, 128)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "locality":
         shapes = [(64, 2048, 32, 8, 128), (512, 2048, 4, 1, 128), (128, 2048, 16, 4, 128)]
     for shp in shapes:
@@ -84,6 +90,40 @@ def one_shape(B, S, H, Hkv, D, max_kv=None, bss=(8, 128), only_auto=False):
             print(f"attn bs={bs} {'REFERENCE':12s}: {us:7.1f} us/launch "
                   f"{byts / us / 1e3:7.1f} GB/s ({byts / us / 1e3 / 6576.4:.3f} of measured HBM peak) [{mode}]",
                   flush=True)
+
+
+def prefill_shape(B, q_len, kv_len, H, Hkv, D, bs=8):
+    nblk = (kv_len + bs - 1) // bs
+    n_blocks = B * nblk + 8
+    L = 4
+    caches = [(torch.randn(n_blocks * bs, Hkv, D, device=DEV).bfloat16(),
+               torch.randn(n_blocks * bs, Hkv, D, device=DEV).bfloat16()) for _ in range(L)]
+    table = (torch.randperm(n_blocks)[: B * nblk] * bs).to(torch.int32).to(DEV)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    q_cu, kv_cu, blk_cu = i32(np.arange(B + 1) * q_len), i32(np.arange(B + 1) * kv_len), i32(np.arange(B + 1) * nblk)
+    q = torch.randn(B * q_len, H, D, device=DEV).bfloat16()
+    out = torch.empty_like(q)
+    # causal: query i of the chunk sees kv_len - q_len + i + 1 keys
+    keys = q_len * (kv_len - q_len) + q_len * (q_len + 1) // 2
+    flops = 4.0 * B * keys * H * D
+    tag = "decode stream kernel" if os.environ.get("B200_ATTN_PREFILL") == "0" else "tcgen05 prefill kernel"
+
+    def run(mod):
+        def launch(kc, vc):
+            mod.paged_kv_varlen_mha(out, q, kc, vc, q_cu, kv_cu, table, blk_cu, None, bs, q_len, kv_len,
+                                    D ** -0.5, 0.0, -1)
+        for kc, vc in caches[:2]:
+            launch(kc, vc)
+        torch.cuda.synchronize()
+        us, mode = time_us(lambda: [launch(kc, vc) for kc, vc in caches], L)
+        return us, mode
+    us, mode = run(kernels)
+    print(f"prefill B={B} q={q_len} kv={kv_len} ours ({tag}): {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s [{mode}]", flush=True)
+    ref = load_reference_kernels()
+    if ref is not None:
+        us_r, mode = run(ref)
+        print(f"prefill B={B} q={q_len} kv={kv_len} REFERENCE kernel (sm80 mma.sync, built for sm_100a): "
+              f"{us_r:8.1f} us  {flops / us_r / 1e6:7.1f} TFLOP/s  -> ours {us_r / us:.2f}x [{mode}]", flush=True)
 
 
 _REF = []
