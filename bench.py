@@ -44,10 +44,10 @@ def parse():
     ap.add_argument("--no-ttft", action="store_true",
                     help="skip the unloaded p50 time-to-first-token measurement (chunked prefill of 8 "
                          "requests, ~1 s of GPU time)")
-    ap.add_argument("--ttft-chunk", type=int, default=128,
-                    help="prefill chunk (token budget per step) of the --ttft measurement; with "
-                         "B200_W4_PREFILL_DENSE=1 chunks > 256 tokens run the int4 linears as "
-                         "dequant + library bf16 GEMM")
+    ap.add_argument("--ttft-chunk", type=int, default=2048,
+                    help="prefill chunk (token budget per step) of the TTFT measurement (default: the whole "
+                         "prompt in one step, as an unloaded server would schedule it); chunks > 256 tokens "
+                         "run the int4 linears as dequant + library bf16 GEMM unless B200_W4_PREFILL_DENSE=0")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
@@ -523,10 +523,12 @@ def measure_ttft(model, pool, args, dev, n_req: int = 16, chunk: int = 128, seed
             "requests": n_req, "prompt_len": "U[128,2048]", "chunk_tokens": chunk,
             "kernels": ("decode path (the stream attention kernel with q_len = chunk rows; B200_ATTN_PREFILL=0)"
                         if os.environ.get("B200_ATTN_PREFILL") == "0" else
-                        "tcgen05 prefill attention (csrc/prefill_attn.cu) + the step's own GEMM / consumer kernels at M = chunk"),
-            "load": "unloaded (one request at a time); full chunks replay a CUDA graph, the ragged last chunk is eager" +
-                    (", int4 linears as dequant + library bf16 GEMM above 256 rows"
-                     if os.environ.get("B200_W4_PREFILL_DENSE") == "1" else "")}
+                        "tcgen05 prefill attention (csrc/prefill_attn.cu); linears: " +
+                        ("the streaming int4 kernel in 128-row passes"
+                         if chunk <= 256 or os.environ.get("B200_W4_PREFILL_DENSE", "1") == "0" else
+                         "int4 -> bf16 dequant (ours, bit-exact) + library bf16 GEMM above 256 rows, the streaming "
+                         "int4 kernel below")),
+            "load": "unloaded (one request at a time); full chunks replay a CUDA graph, the ragged last chunk is eager"}
 
 
 def _traffic(name):

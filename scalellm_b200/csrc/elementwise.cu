@@ -248,12 +248,6 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
   static_assert(VEC == 8, "16-bit element types only");
   __shared__ float red[32];
   extern __shared__ float sq[];  // [n] fp32: the row, for the reference-ordered sum of squares
-  // Dependents first: the next kernel of the layer is a GEMM (or the attention kernel) whose only work
-  // before its own griddepcontrol.wait is constant weights / step inputs; letting it become resident
-  // now puts its set-up and first weight blobs behind this kernel instead of after it.  Its trigger
-  // comes after its own wait, so "a started kernel's predecessor has passed its wait" still holds
-  // for every kernel that relies on it.
-  pdl_launch_dependents();
   const int64_t row = blockIdx.x;
   const int nvec = n / VEC;
   T* res_row = residual + row * n;
@@ -274,6 +268,7 @@ __global__ void __launch_bounds__(THREADS) rms_norm_residual_splitk_kernel(
     }
   }
   pdl_wait();
+  pdl_launch_dependents();
   float x[MAXV][VEC];
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -370,7 +365,6 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
     int n_heads, int n_kv_heads, int head_dim, int rotary_dim, int64_t q_stride,
     int64_t k_stride, int64_t v_stride, bool interleaved, RopePartials parts) {
   constexpr int VEC = 16 / sizeof(T);
-  pdl_launch_dependents();  // see rms_norm_residual_splitk_kernel: the attention kernel's prologue reads step inputs only
   const int64_t tok = blockIdx.x;
   // positions / slot ids / the cos|sin table are step inputs and model constants, older than the
   // predecessor kernel: fetch them before griddepcontrol.wait so their latency overlaps its tail
@@ -380,6 +374,7 @@ __global__ void __launch_bounds__(256) rope_vec_kernel(
   extern __shared__ __align__(16) uint8_t rope_smem[];  // FROM_PARTIALS: the token's [q|k|v] row in T
   T* row_s = reinterpret_cast<T*>(rope_smem);
   pdl_wait();
+  pdl_launch_dependents();
   if constexpr (FROM_PARTIALS) {
     // Materialise this token's qkv row first: x = T(sum of the tile's partial slots), the one
     // rounding the GEMM epilogue would have done; q, k, v are views of that row (host-checked).
@@ -697,7 +692,6 @@ __global__ void __launch_bounds__(256, 3) silu_mul_splitk_kernel(T* __restrict__
                                                               const float* __restrict__ partials,
                                                               W4Plan plan, int64_t slot_stride,
                                                               int64_t rows, int inter) {
-  pdl_launch_dependents();  // see rms_norm_residual_splitk_kernel: the down GEMM streams weights meanwhile
   const int nv = inter / 8;
   const int64_t total = rows * nv;
   // the first item's index arithmetic and contributor counts do not depend on the GEMM: before the wait
@@ -705,6 +699,7 @@ __global__ void __launch_bounds__(256, 3) silu_mul_splitk_kernel(T* __restrict__
   const int j0 = (int)(idx0 % nv);
   const int cg0 = w4_contrib_col(plan, j0 * 8), cu0 = w4_contrib_col(plan, inter + j0 * 8);
   pdl_wait();
+  pdl_launch_dependents();
   for (int64_t idx = idx0; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / nv;
     const int j = (int)(idx - r * nv);

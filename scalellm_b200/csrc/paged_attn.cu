@@ -1291,8 +1291,8 @@ paged_attn_persist_kernel(const __grid_constant__ CUtensorMap kmap,
 template <typename T, int D>
 __global__ void __launch_bounds__(128) paged_attn_combine_kernel(const AttnParams p) {
   constexpr int EPL = D / 32;  // elements per lane: 2, 4 or 8 (1 or 3 for head_dim 32 / 96)
-  pdl_launch_dependents();  // the o_proj GEMM becomes resident as the stream kernel's CTAs leave and prefetches its weights
   pdl_wait();
+  pdl_launch_dependents();  // a following W4A16 GEMM (o_proj) may start prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x * 4 + warp;
   if (h >= p.n_heads) return;

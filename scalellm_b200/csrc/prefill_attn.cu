@@ -46,6 +46,9 @@ struct PrefillParams {
   int64_t o_stride_t, o_stride_h;
   int n_kv_heads, group, tokens_per_block;  // tokens_per_block = 128 / group
   int block_shift, block_mask, box_rows;
+  int dual;                 // 1: one TMA box carries both 64-d chunks of 8 slots ([chunk][slot][64])
+  uint32_t kv_sbo;          // bytes between 8-key groups of a K / V tile (1024, dual: 2048)
+  uint32_t kv_chunk;        // bytes from a group's d 0..63 atom to its d 64..127 atom (PF_CHUNK, dual: 1024)
   float scale_log2, cap_in, cap_out_log2;
   int use_cap, window;
 };
@@ -54,6 +57,16 @@ struct PrefillParams {
 // B K-major (b_mn = 0) or MN-major (b_mn = 1)
 __host__ __device__ constexpr uint32_t pf_idesc(uint32_t M, uint32_t N, uint32_t fmt, uint32_t b_mn) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// K-major, 128-byte swizzle, 8-row groups `sbo` bytes apart
+__device__ __forceinline__ uint64_t pf_desc_kmajor_sw128(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
 // MN-major, 128-byte swizzle: atoms [8 k x 64 mn]; LBO = bytes between 64-element blocks along MN,
 // SBO = bytes between 8-row groups along K (cute::UMMA::make_umma_desc<Major::MN>)
@@ -67,7 +80,13 @@ __device__ __forceinline__ uint64_t pf_desc_mnmajor_sw128(uint32_t smem_addr, ui
   return d;
 }
 
-template <typename T>
+__device__ __forceinline__ float pf_ex2(float x) {   // 2^x, one MUFU; 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T, bool TRACE>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap1,
                     const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
@@ -81,23 +100,25 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   uint8_t* p_smem = v_smem + 2 * PF_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + PF_TILE);
   uint64_t* q_full = bars;           // 1
-  uint64_t* kv_full = bars + 1;      // 2
-  uint64_t* kv_empty = bars + 3;     // 2
-  uint64_t* s_full = bars + 5;       // 1
-  uint64_t* p_full = bars + 6;       // 1
-  uint64_t* pv_full = bars + 7;      // 1
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;       // 2
+  uint64_t* v_full = bars + 3;       // 2
+  uint64_t* k_empty = bars + 5;      // 2   (S(i) has read K(i))
+  uint64_t* v_empty = bars + 7;      // 2   (PV(i) has read V(i))
+  uint64_t* s_full = bars + 9;       // 2   (S double buffered in TMEM)
+  uint64_t* p_full = bars + 11;      // 1
+  uint64_t* pv_full = bars + 12;     // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   // debug trace (b200_debug_set_trace, tools/prefill_trace.py): clock64 totals per role, 16 slots per CTA
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  long long* tr = (trace != nullptr && cta_lin < 1024) ? trace + cta_lin * 16 : nullptr;
+  long long* tr = (TRACE && trace != nullptr && cta_lin < 1024) ? trace + cta_lin * 16 : nullptr;
   long long tacc[4] = {0, 0, 0, 0};
   long long tt = 0;
-  const long long t_start = tr ? clock64() : 0;
-#define PF_T0() do { if (tr) tt = clock64(); } while (0)
-#define PF_T1(k) do { if (tr) { const long long _n = clock64(); tacc[k] += _n - tt; tt = _n; } } while (0)
+  const long long t_start = (TRACE && tr) ? clock64() : 0;
+#define PF_T0() do { if (TRACE && tr) tt = clock64(); } while (0)
+#define PF_T1(k) do { if (TRACE && tr) { const long long _n = clock64(); tacc[k] += _n - tt; tt = _n; } } while (0)
   const int G = p.group, TPB = p.tokens_per_block;
   // geometry from the step's metadata (inputs of the step: readable before griddepcontrol.wait)
   const int q_begin = p.q_cu_lens[b], q_len = p.q_cu_lens[b + 1] - q_begin;
@@ -115,16 +136,18 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
     }
-    mbar_init(s_full, 1);
     mbar_init(p_full, PF_ROWS);
     mbar_init(pv_full, 1);
     fence_mbar_init();
   }
   if (warp == PF_WARP_MMA) {
-    tmem_alloc(tmem_holder, 256);
+    tmem_alloc(tmem_holder, 512);
     tmem_relinquish();
   }
   if (warp == PF_WARP_TMA && lane == 0) {
@@ -137,7 +160,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t s_tmem = tmem_base, pv_tmem = tmem_base + 128;
+  const uint32_t pv_tmem = tmem_base + 256;   // S(i) at tmem_base + (i & 1) * 128
   pdl_launch_dependents();
   constexpr uint32_t FMT = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;  // tcgen05 kind::f16 input format
 
@@ -157,32 +180,66 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         }
       }
     }
+    // K(i) may be overwritten once S(i-2) has read it, V(i) once PV(i-2) has: separate rings, so that
+    // the K tile of the next S GEMM is on its way while the softmax of the current tile runs.
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i & 1;
       const int pos0 = (t_begin + i) * PF_KEYS;
       const int valid = min(PF_KEYS, kv_end - pos0);                       // keys of this tile that exist
       const int boxes = (valid + p.box_rows - 1) / p.box_rows;             // TMA boxes per chunk per tensor
+      const uint32_t bytes = (uint32_t)(boxes * p.box_rows * 128 * 2);     // both 64-d chunks of one tensor
+      int slot0[4];                                                        // <= 128 boxes: 4 per lane
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bx = lane + 32 * j;
+        const int pos = pos0 + bx * p.box_rows;
+        slot0[j] = bx < boxes ? p.block_table[blk_cu + (pos >> p.block_shift)] + (pos & p.block_mask) : 0;
+      }
       PF_T0();
       if (lane == 0) {
-        mbar_wait(&kv_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], (uint32_t)(boxes * p.box_rows * 128 * 4));
+        mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], bytes);
       }
       __syncwarp();
       PF_T1(0);
-      for (int bx = lane; bx < boxes; bx += 32) {
-        const int pos = pos0 + bx * p.box_rows;
-        const int slot0 = p.block_table[blk_cu + (pos >> p.block_shift)] + (pos & p.block_mask);
-        uint8_t* kd = k_smem + s * PF_TILE + bx * p.box_rows * 128;
-        uint8_t* vd = v_smem + s * PF_TILE + bx * p.box_rows * 128;
-        tma_load_4d(kd, &kmap, &kv_full[s], 0, 0, kvh, slot0);
-        tma_load_4d(kd + PF_CHUNK, &kmap, &kv_full[s], 0, 1, kvh, slot0);
-        tma_load_4d(vd, &vmap, &kv_full[s], 0, 0, kvh, slot0);
-        tma_load_4d(vd + PF_CHUNK, &vmap, &kv_full[s], 0, 1, kvh, slot0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bx = lane + 32 * j;
+        if (bx < boxes) {
+          uint8_t* kd = k_smem + s * PF_TILE + (bx * p.box_rows >> 3) * p.kv_sbo + ((bx * p.box_rows) & 7) * 128;
+          if (p.dual) {   // one box = both chunks of 8 slots: [chunk][slot][64]
+            tma_load_4d(kd, &kmap, &k_full[s], 0, slot0[j], 0, kvh);
+          } else {
+            tma_load_4d(kd, &kmap, &k_full[s], 0, 0, kvh, slot0[j]);
+            tma_load_4d(kd + p.kv_chunk, &kmap, &k_full[s], 0, 1, kvh, slot0[j]);
+          }
+        }
+      }
+      __syncwarp();
+      PF_T1(1);
+      if (lane == 0) {
+        mbar_wait(&v_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], bytes);
+      }
+      __syncwarp();
+      PF_T1(0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bx = lane + 32 * j;
+        if (bx < boxes) {
+          uint8_t* vd = v_smem + s * PF_TILE + (bx * p.box_rows >> 3) * p.kv_sbo + ((bx * p.box_rows) & 7) * 128;
+          if (p.dual) {
+            tma_load_4d(vd, &vmap, &v_full[s], 0, slot0[j], 0, kvh);
+          } else {
+            tma_load_4d(vd, &vmap, &v_full[s], 0, 0, kvh, slot0[j]);
+            tma_load_4d(vd + p.kv_chunk, &vmap, &v_full[s], 0, 1, kvh, slot0[j]);
+          }
+        }
       }
       __syncwarp();
       PF_T1(1);
     }
-    if (tr && lane == 0) {
+    if (TRACE && tr && lane == 0) {
       tr[8] = tacc[0];
       tr[9] = tacc[1];
     }
@@ -192,44 +249,51 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     constexpr uint32_t idesc_pv = pf_idesc(PF_ROWS, PF_D, FMT, 1);
     const uint32_t q_a = smem_u32(q_smem), k_a = smem_u32(k_smem), v_a = smem_u32(v_smem),
                    p_a = smem_u32(p_smem);
-    PF_T0();
-    mbar_wait(q_full, 0);
-    PF_T1(3);
-    for (int i = 0; i < n_tiles; ++i) {
+    auto issue_s = [&](int i) {   // S(i) = Q K(i)^T into S buffer i & 1; releases K(i)
       const int s = i & 1;
-      PF_T0();
-      mbar_wait(&kv_full[s], (i >> 1) & 1);
-      PF_T1(0);
+      mbar_wait(&k_full[s], (i >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // S = Q K^T over d: 16 per step, 4 steps per 64-d chunk
-          const uint32_t off = (ks >> 2) * PF_CHUNK + (ks & 3) * 32;
-          umma_bf16(s_tmem, umma_desc_kmajor_sw128(q_a + off), umma_desc_kmajor_sw128(k_a + s * PF_TILE + off),
-                    idesc_s, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {   // over d: 16 per step, 4 steps per 64-d chunk
+          const uint32_t sub = (ks & 3) * 32;
+          umma_bf16(tmem_base + s * 128, umma_desc_kmajor_sw128(q_a + (ks >> 2) * PF_CHUNK + sub),
+                    pf_desc_kmajor_sw128(k_a + s * PF_TILE + (ks >> 2) * p.kv_chunk + sub, p.kv_sbo), idesc_s,
+                    ks > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[s]);
+        umma_commit(&k_empty[s]);
       }
       __syncwarp();
-      PF_T1(2);
+    };
+    PF_T0();
+    mbar_wait(q_full, 0);
+    PF_T1(3);
+    issue_s(0);
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      PF_T0();
+      if (i + 1 < n_tiles) issue_s(i + 1);   // runs on the tensor pipe while the softmax of tile i runs
+      PF_T1(0);
       mbar_wait(p_full, i & 1);  // P(i) is in shared memory (and PV(i-1) has been read back)
+      mbar_wait(&v_full[s], (i >> 1) & 1);
       PF_T1(1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // PV = P V over keys: 16 per step = two 8-key atoms of V
+        for (int ks = 0; ks < 8; ++ks) {   // PV = P V over keys: 16 per step = two 8-key groups of V
           const uint32_t p_off = (ks >> 2) * PF_CHUNK + (ks & 3) * 32;
           umma_bf16(pv_tmem, umma_desc_kmajor_sw128(p_a + p_off),
-                    pf_desc_mnmajor_sw128(v_a + s * PF_TILE + ks * 2 * PF_ATOM, PF_CHUNK, PF_ATOM), idesc_pv,
+                    pf_desc_mnmajor_sw128(v_a + s * PF_TILE + ks * 2 * p.kv_sbo, p.kv_chunk, p.kv_sbo), idesc_pv,
                     ks > 0 ? 1u : 0u);
         }
         umma_commit(pv_full);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&v_empty[s]);
       }
       __syncwarp();
       PF_T1(2);
     }
-    if (tr && lane == 0) {
+    if (TRACE && tr && lane == 0) {
       tr[6] = tacc[0];
       tr[7] = tacc[1];
       tr[10] = tacc[3];
@@ -255,6 +319,17 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       v = fmaf(slope_log2, (float)pos, v);
       return (pos >= row_begin && pos < row_end) ? v : -INFINITY;
     };
+    // 32 keys = four 16-byte units of row r inside chunk (c0 / 64) of P (K-major, 128-byte swizzle)
+    auto store_p = [&](int c0, const uint32_t (&pk)[16]) {
+      uint8_t* prow = p_smem + (c0 >> 6) * PF_CHUNK + r * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int unit = ((c0 & 63) >> 3) + u;
+        *reinterpret_cast<uint4*>(prow + ((unit ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      }
+    };
+    const bool generic = p.use_cap != 0 || p.alibi != nullptr;   // CTA-uniform
     auto add_pv = [&](float c) {   // o = o * c + PV (the tile whose PV is in TMEM)
 #pragma unroll
       for (int c0 = 0; c0 < PF_D; c0 += 32) {
@@ -267,19 +342,57 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     };
     for (int i = 0; i < n_tiles; ++i) {
       const int pos0 = (t_begin + i) * PF_KEYS;
+      const uint32_t s_tmem = tmem_base + (i & 1) * 128;
       PF_T0();
-      mbar_wait(s_full, i & 1);
+      mbar_wait(&s_full[i & 1], (i >> 1) & 1);
       PF_T1(0);
       tc_fence_after();
+      // Columns of this tile that row r may see: [lo, hi) (causal diagonal, sliding window).  Without
+      // soft cap / alibi a 32-column chunk that is fully visible to every row of the warp (all chunks of
+      // an interior tile) costs one FMNMX per element in pass 1 and FFMA + ex2 + add in pass 2; a chunk
+      // no row of the warp sees is skipped; only chunks the diagonal crosses pay for the masks.
+      const int lo = row_begin - pos0, hi = row_end - pos0;
+      const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;
+      uint32_t full_mask = 0, none_mask = 0;   // bit c: chunk c fully visible / invisible (warp-uniform)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (__all_sync(0xffffffffu, lo <= c * 32 && hi >= c * 32 + 32)) full_mask |= 1u << c;
+        if (__all_sync(0xffffffffu, hi <= c * 32 || lo >= c * 32 + 32)) none_mask |= 1u << c;
+      }
       // pass 1: row maximum of the tile
       float mx = m;
+      if (generic) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
-        uint32_t x[32];
-        tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
+          uint32_t x[32];
+          tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score(x[j], pos0 + c0 + j));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score(x[j], pos0 + c0 + j));
+        }
+      } else {
+        float r0 = -INFINITY, r1 = -INFINITY, r2 = -INFINITY, r3 = -INFINITY;   // raw accumulator maxima
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if ((none_mask >> c) & 1u) continue;
+          uint32_t x[32];
+          tmem_ld_32x32b_x32(s_tmem + lane_addr + c * 32, x);
+          tmem_ld_wait();
+          if ((full_mask >> c) & 1u) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              r0 = fmaxf(r0, __uint_as_float(x[j]));
+              r1 = fmaxf(r1, __uint_as_float(x[j + 1]));
+              r2 = fmaxf(r2, __uint_as_float(x[j + 2]));
+              r3 = fmaxf(r3, __uint_as_float(x[j + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((unsigned)(c * 32 + j - lo) < span) r0 = fmaxf(r0, __uint_as_float(x[j]));
+          }
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * p.scale_log2);   // scale > 0: max commutes
       }
       PF_T1(1);
       const float ms = (mx == -INFINITY) ? 0.f : mx;
@@ -294,39 +407,75 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       PF_T1(2);
       // pass 2: p = exp2(s - m), row sum, P -> T -> shared memory (K-major, 128-byte swizzle)
       float sum = 0.f;
+      if (generic) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
-        uint32_t x[32];
-        tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
+          uint32_t x[32];
+          tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = exp2f(score(x[j], pos0 + c0 + j) - ms);
-          const float p1 = exp2f(score(x[j + 1], pos0 + c0 + j + 1) - ms);
-          pk[j >> 1] = Num<T>::pack(p0, p1);   // P rounded to T for the second GEMM ...
-          sum += p0 + p1;                       // ... the row sum stays fp32 (online_softmax.cuh:39-162)
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = exp2f(score(x[j], pos0 + c0 + j) - ms);
+            const float p1 = exp2f(score(x[j + 1], pos0 + c0 + j + 1) - ms);
+            pk[j >> 1] = Num<T>::pack(p0, p1);   // P rounded to T for the second GEMM ...
+            sum += p0 + p1;                       // ... the row sum stays fp32 (online_softmax.cuh:39-162)
+          }
+          store_p(c0, pk);
         }
-        // 32 keys = four 16-byte units of row r inside chunk (c0 / 64)
-        uint8_t* prow = p_smem + (c0 >> 6) * PF_CHUNK + r * 128;
+      } else {
+        float s0 = 0.f, s1 = 0.f;
+        const float neg_ms = -ms;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if ((none_mask >> c) & 1u) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = ((c0 & 63) >> 3) + u;
-          *reinterpret_cast<uint4*>(prow + ((unit ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          } else {
+            uint32_t x[32];
+            tmem_ld_32x32b_x32(s_tmem + lane_addr + c * 32, x);
+            tmem_ld_wait();
+            if ((full_mask >> c) & 1u) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
+                const float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
+                pk[j >> 1] = Num<T>::pack(p0, p1);
+                s0 += p0;
+                s1 += p1;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
+                float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
+                p0 = (unsigned)(c * 32 + j - lo) < span ? p0 : 0.f;
+                p1 = (unsigned)(c * 32 + j + 1 - lo) < span ? p1 : 0.f;
+                pk[j >> 1] = Num<T>::pack(p0, p1);
+                s0 += p0;
+                s1 += p1;
+              }
+            }
+          }
+          store_p(c * 32, pk);
         }
+        sum = s0 + s1;
       }
       l = fmaf(l, corr_new, sum);
       m = mx;
       // keys of the tile that do not exist: their V rows hold whatever the ring held (maybe NaN) and
       // 0 * NaN is NaN — zero them (their P columns are exactly 0 already)
       const int valid = min(PF_KEYS, kv_end - pos0);
-      if (r >= valid) {
-        uint8_t* vrow = v_smem + (i & 1) * PF_TILE + (r >> 3) * PF_ATOM + (r & 7) * 128;
+      if (valid < PF_KEYS) {   // CTA-uniform: the sequence's last tile
+        mbar_wait(&v_full[i & 1], (i >> 1) & 1);   // the boxes that do exist have landed
+        if (r >= valid) {
+          uint8_t* vrow = v_smem + (i & 1) * PF_TILE + (r >> 3) * p.kv_sbo + (r & 7) * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          *reinterpret_cast<uint4*>(vrow + u * 16) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(vrow + PF_CHUNK + u * 16) = make_uint4(0, 0, 0, 0);
+          for (int u = 0; u < 8; ++u) {
+            *reinterpret_cast<uint4*>(vrow + u * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(vrow + p.kv_chunk + u * 16) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
       tc_fence_before();
@@ -334,7 +483,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       mbar_arrive(p_full);
       PF_T1(3);
     }
-    if (tr && r == 0) {
+    if (TRACE && tr && r == 0) {
       tr[1] = n_tiles;
       tr[2] = tacc[0];
       tr[3] = tacc[1];
@@ -360,10 +509,10 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
+  if (TRACE && tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
   if (warp == PF_WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 #undef PF_T0
 #undef PF_T1
@@ -404,6 +553,14 @@ static int pf_get_map(const PfMapKey& k, CUtensorMap* out) {
     cuuint32_t box[3] = {64u, (cuuint32_t)k.box1, (cuuint32_t)k.box2};
     cuuint32_t estr[3] = {1, 1, 1};
     r = enc(&m, dt, 3, const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (k.kind == 2) {   // kv cache as {64, slots, D/64, Hkv}: one box = {64, 8 slots, both chunks, 1 head},
+                              // landing as [chunk][slot][64] — half the TMA operations at block_size 8
+    cuuint64_t dims[4] = {64u, (cuuint64_t)k.d2, (cuuint64_t)(k.d0 / 64), (cuuint64_t)k.d1};
+    cuuint64_t strides[3] = {(cuuint64_t)k.s2 * 2, 128u, (cuuint64_t)k.s1 * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)k.box2, (cuuint32_t)(k.d0 / 64), 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = enc(&m, dt, 4, const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {             // kv cache [slots, Hkv, D] as {64, D/64, Hkv, slots}: one 64-wide chunk per box
     cuuint64_t dims[4] = {64u, (cuuint64_t)(k.d0 / 64), (cuuint64_t)k.d1, (cuuint64_t)k.d2};
@@ -456,7 +613,15 @@ int launch_prefill_attn(void* out, const void* q, const void* k_cache, const voi
   while ((1 << sh) < block_size) ++sh;
   p.block_shift = sh;
   p.block_mask = block_size - 1;
-  p.box_rows = block_size < 8 ? block_size : 8;
+  // K / V boxes: block_size 8 (the serving default) -> one box per 8 slots carrying both d chunks, if the
+  // driver takes the re-ordered tensor map (B200_ATTN_PF_DUAL=0 disables); otherwise one box per chunk
+  // of min(block_size, 128) slots
+  static const bool dual_ok = [] {
+    const char* e = getenv("B200_ATTN_PF_DUAL");
+    return !(e && e[0] == '0');
+  }();
+  p.dual = (block_size == 8 && dual_ok) ? 1 : 0;
+  p.box_rows = p.dual ? 8 : (block_size < PF_KEYS ? block_size : PF_KEYS);
   constexpr float LOG2E = 1.4426950408889634f;
   if (soft_cap > 0.f) {
     p.use_cap = 1;
@@ -473,18 +638,31 @@ int launch_prefill_attn(void* out, const void* q, const void* k_cache, const voi
   if (rc != B200_OK) return rc;
   rc = pf_get_map(PfMapKey{q, PF_D, n_heads, n_tokens_bound, q_stride_h, q_stride_t, G, 1, dtype, 0}, &qmap1);
   if (rc != B200_OK) return rc;
-  rc = pf_get_map(PfMapKey{k_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &kmap);
-  if (rc != B200_OK) return rc;
-  rc = pf_get_map(PfMapKey{v_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &vmap);
-  if (rc != B200_OK) return rc;
+  if (p.dual) {
+    rc = pf_get_map(PfMapKey{k_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, 8, dtype, 2}, &kmap);
+    if (rc == B200_OK)
+      rc = pf_get_map(PfMapKey{v_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, 8, dtype, 2}, &vmap);
+    if (rc != B200_OK) {   // the driver refused the re-ordered map: per-chunk boxes
+      p.dual = 0;
+      p.box_rows = block_size < PF_KEYS ? block_size : PF_KEYS;
+    }
+  }
+  if (!p.dual) {
+    rc = pf_get_map(PfMapKey{k_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &kmap);
+    if (rc != B200_OK) return rc;
+    rc = pf_get_map(PfMapKey{v_cache, PF_D, n_kv_heads, n_slots, kv_stride_h, kv_stride_s, 1, p.box_rows, dtype, 1}, &vmap);
+    if (rc != B200_OK) return rc;
+  }
+  p.kv_sbo = p.dual ? 2048u : 1024u;
+  p.kv_chunk = p.dual ? 1024u : (uint32_t)PF_CHUNK;
   const unsigned n_rb = (unsigned)(((int64_t)max_q_len + p.tokens_per_block - 1) / p.tokens_per_block);
   dim3 grid(n_rb, (unsigned)n_kv_heads, (unsigned)batch);
   if (dtype == B200_BF16) {
-    auto kern = prefill_attn_kernel<__nv_bfloat16>;
+    auto kern = debug_trace_ptr() ? prefill_attn_kernel<__nv_bfloat16, true> : prefill_attn_kernel<__nv_bfloat16, false>;
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   } else {
-    auto kern = prefill_attn_kernel<__half>;
+    auto kern = debug_trace_ptr() ? prefill_attn_kernel<__half, true> : prefill_attn_kernel<__half, false>;
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   }

@@ -145,8 +145,9 @@ def test_gemm_bias_strided_and_large_m():
 
 @pytest.mark.parametrize("method", ["awq", "gptq"])
 def test_dense_prefill_path_of_the_int4_linear(method, monkeypatch):
-    """B200_W4_PREFILL_DENSE=1: above 256 rows the int4 linear dequantises once (bit-exact bf16
-    weights) and runs the library bf16 GEMM — same bar as the fused kernel vs the oracle."""
+    """Above 256 rows (prefill) the int4 linear dequantises once (bit-exact bf16 weights) and runs the
+    library bf16 GEMM (default; B200_W4_PREFILL_DENSE=0: the streaming kernel in 128-row passes) — same
+    bar as the fused kernel vs the oracle."""
     from scalellm_b200.layers import ColumnParallelQLinear, QuantArgs
     from scalellm_b200.model_parallel import ParallelArgs
     K, N, M, g = 1024, 768, 300, 128
@@ -157,10 +158,13 @@ def test_dense_prefill_path_of_the_int4_linear(method, monkeypatch):
     a = (torch.randn(M, K, generator=torch.Generator().manual_seed(6)) * 0.5).bfloat16()
     w_ref = quant.dequant(ck["q"], ck["z"], ck["scales"], g)
     ref = quant.w4a16_gemm(a, w_ref)
-    monkeypatch.setenv("B200_W4_PREFILL_DENSE", "1")
+    monkeypatch.delenv("B200_W4_PREFILL_DENSE", raising=False)
+    kernels.launch_count_reset()
     dense = lin(a.to(DEV))
-    monkeypatch.delenv("B200_W4_PREFILL_DENSE")
+    n_dense = kernels.launch_count()
+    monkeypatch.setenv("B200_W4_PREFILL_DENSE", "0")
     fused = lin(a.to(DEV))
+    assert n_dense >= 1                      # the dequant kernel of ours ran (then the library GEMM)
     assert rel_err(dense, ref) < 1e-3 and rel_err(fused, ref) < 1e-3
     assert (dense.cpu().view(torch.int16) == ref.view(torch.int16)).float().mean() > 0.85
 

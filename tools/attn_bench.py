@@ -34,6 +34,12 @@ def main():
         for B, q_len, kv_len in ((1, 128, 2048), (1, 512, 2048), (1, 2048, 2048), (8, 512, 2048), (4, 2048, 2048)):
             prefill_shape(B, q_len, kv_len, 32, 8, 128)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "tp":
+        # the per-rank attention problem under tensor parallelism (heads / kv heads divided by the
+        # world size, same sequences): where the fixed cost of a launch shows
+        for H, Hkv in ((16, 4), (8, 2), (4, 1)):
+            one_shape(64, 2048, H, Hkv, 128, bss=(8,), only_auto=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "locality":
         shapes = [(64, 2048, 32, 8, 128), (512, 2048, 4, 1, 128), (128, 2048, 16, 4, 128)]
     for shp in shapes:
