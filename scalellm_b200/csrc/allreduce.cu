@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
   constexpr int VEC = 16 / sizeof(T);
   ar_stamp(trace, 6);
   pdl_launch_dependents();  // the next GEMM may start prefetching its weights while we exchange
-  // Before griddepcontrol.wait: whatever does not depend on the producing GEMM.  When this kernel
-  // starts, that GEMM has passed its own wait, so everything older — the previous collective (the
-  // epoch), the previous norm (the residual stream) — is complete and visible.
+  // Before griddepcontrol.wait: whatever does not depend on the producing GEMM.  In the fused (NORM)
+  // form the producer is always a GEMM, which triggers its dependents after its own wait: when this
+  // kernel starts, everything older than that GEMM — the previous norm (the residual stream) — is
+  // complete and visible.  The epoch is NOT read here: a plain all-reduce may directly follow another
+  // one of this kernel (sliced large messages), which triggers at its top, and would see the epoch
+  // of the call still in flight (ranks then disagree on the epoch: a hang, found by tools/ar_bench.py).
   uint8_t* local = ptrs.base[rank];
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(local + ar_epoch_off(max_bytes));
-  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
-  const int64_t par_off = (e & 1) ? max_bytes : 0;
 
   const int row = blockIdx.x, rows = gridDim.x;
   const int C = (row_vecs + world - 1) / world;  // vectors of a row per owner (column partition)
@@ -359,6 +360,9 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_twoshot_kernel(
     }
   }
   pdl_wait();               // the contribution comes from the producing GEMM
+  // the epoch of this call: its load is in flight together with the partial-sum loads below
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_ptr) + 1;
+  const int64_t par_off = (e & 1) ? max_bytes : 0;
   ar_stamp(trace, 0);
 
   // ---- 1. push my contribution of every vector into its owner's inbox, slot = my rank ----

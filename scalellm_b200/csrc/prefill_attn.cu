@@ -29,12 +29,13 @@
 namespace b200 {
 
 constexpr int PF_ROWS = 128, PF_KEYS = 128, PF_D = 128;
-constexpr int PF_THREADS = 6 * 32;
-constexpr int PF_WARP_TMA = 4, PF_WARP_MMA = 5;
+constexpr int PF_THREADS = 10 * 32;   // 8 softmax warps (two threads per row), producer, MMA issuer
+constexpr int PF_WARP_TMA = 8, PF_WARP_MMA = 9;
 constexpr int PF_ATOM = 1024;               // 8 rows x 128 B
 constexpr int PF_CHUNK = 16 * PF_ATOM;      // 128 rows x 64 elements: 16 KB
 constexpr int PF_TILE = 2 * PF_CHUNK;       // 128 x 128 elements: 32 KB
-constexpr size_t PF_SMEM = 1024 + (size_t)PF_TILE * (1 /*Q*/ + 2 /*K*/ + 2 /*V*/ + 1 /*P*/) + 16 * 8 + 64;
+constexpr size_t PF_SMEM = 1024 + (size_t)PF_TILE * (1 /*Q*/ + 2 /*K*/ + 2 /*V*/ + 1 /*P*/) + 16 * 8 + 64 +
+                           4 * PF_ROWS * 4 /* row-max exchange */;
 
 struct PrefillParams {
   void* out;
@@ -86,7 +87,7 @@ __device__ __forceinline__ float pf_ex2(float x) {   // 2^x, one MUFU; 2^-inf = 
   return y;
 }
 
-template <typename T, bool TRACE>
+template <typename T, bool TRACE, bool GENERIC>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap1,
                     const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
@@ -108,6 +109,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   uint64_t* p_full = bars + 11;      // 1
   uint64_t* pv_full = bars + 12;     // 1
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+  float* mx_sh = reinterpret_cast<float*>(bars + 16 + 8);   // [parity][half][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -142,7 +144,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, PF_ROWS);
+    mbar_init(p_full, 2 * PF_ROWS);
     mbar_init(pv_full, 1);
     fence_mbar_init();
   }
@@ -300,18 +302,24 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       tr[11] = tacc[2];
     }
   } else {
-    // ===================== softmax / output: thread <-> packed row =====================
-    const int r = threadIdx.x;                     // 0..127 = TMEM lane
+    // ===================== softmax / output: two threads per packed row =====================
+    // Thread t: row r = t & 127 (its TMEM lane), column half h = t >> 7 — warps w and w + 4 share a
+    // TMEM lane quarter.  Half h owns the tile's keys [64 h, 64 h + 64) (chunk h of P) and the output
+    // columns d in [64 h, 64 h + 64).  The two halves agree on the row maximum through shared memory
+    // once per tile; their partial row sums are added at the end.
+    const int r = threadIdx.x & 127;
+    const int h = threadIdx.x >> 7;
     const int qi = r / G, g = r - qi * G;          // token inside the block, head inside the group
     const bool row_ok = qi < n_tok;
     const int head = kvh * G + g;
     const int row_end = row_ok ? q_pos0 + tok0 + qi + 1 : 0;               // keys [row_begin, row_end)
     const int row_begin = p.window >= 0 ? max(0, q_pos0 + tok0 + qi - p.window) : 0;
     const float slope_log2 = p.alibi ? p.alibi[head] * 1.4426950408889634f : 0.f;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float o[PF_D];
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int pair_bar = 1 + (warp & 3);           // named barrier of warps w and w + 4 (64 threads)
+    float o[64];
 #pragma unroll
-    for (int i = 0; i < PF_D; ++i) o[i] = 0.f;
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f, corr = 1.f;
     auto score = [&](uint32_t raw, int pos) -> float {
       const float acc = __uint_as_float(raw);
@@ -319,30 +327,31 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       v = fmaf(slope_log2, (float)pos, v);
       return (pos >= row_begin && pos < row_end) ? v : -INFINITY;
     };
-    // 32 keys = four 16-byte units of row r inside chunk (c0 / 64) of P (K-major, 128-byte swizzle)
-    auto store_p = [&](int c0, const uint32_t (&pk)[16]) {
-      uint8_t* prow = p_smem + (c0 >> 6) * PF_CHUNK + r * 128;
+    // 32 keys = four 16-byte units of row r inside chunk h of P (K-major, 128-byte swizzle); c = 0 / 1
+    auto store_p = [&](int c, const uint32_t (&pk)[16]) {
+      uint8_t* prow = p_smem + h * PF_CHUNK + r * 128;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int unit = ((c0 & 63) >> 3) + u;
+        const int unit = c * 4 + u;
         *reinterpret_cast<uint4*>(prow + ((unit ^ (r & 7)) << 4)) =
             make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
     };
-    const bool generic = p.use_cap != 0 || p.alibi != nullptr;   // CTA-uniform
-    auto add_pv = [&](float c) {   // o = o * c + PV (the tile whose PV is in TMEM)
+    constexpr bool generic = GENERIC;   // soft cap or alibi: the per-element score path (host-selected)
+    auto add_pv = [&](float c) {   // o = o * c + PV (the tile whose PV is in TMEM), this half's columns
 #pragma unroll
-      for (int c0 = 0; c0 < PF_D; c0 += 32) {
-        uint32_t x[32];
-        tmem_ld_32x32b_x32(pv_tmem + lane_addr + c0, x);
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t y[32];
+        tmem_ld_32x32b_x32(pv_tmem + lane_addr + h * 64 + c0, y);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], c, __uint_as_float(x[i]));
+        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], c, __uint_as_float(y[i]));
       }
     };
     for (int i = 0; i < n_tiles; ++i) {
       const int pos0 = (t_begin + i) * PF_KEYS;
-      const uint32_t s_tmem = tmem_base + (i & 1) * 128;
+      const uint32_t s_tmem = tmem_base + (i & 1) * 128 + lane_addr + h * 64;   // this thread's 64 columns
+      const int col0 = h * 64;
       PF_T0();
       mbar_wait(&s_full[i & 1], (i >> 1) & 1);
       PF_T1(0);
@@ -353,47 +362,48 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       // no row of the warp sees is skipped; only chunks the diagonal crosses pay for the masks.
       const int lo = row_begin - pos0, hi = row_end - pos0;
       const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;
-      uint32_t full_mask = 0, none_mask = 0;   // bit c: chunk c fully visible / invisible (warp-uniform)
+      uint32_t full_mask = 0, none_mask = 0;   // bit c: this half's chunk c fully visible / invisible (warp-uniform)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (__all_sync(0xffffffffu, lo <= c * 32 && hi >= c * 32 + 32)) full_mask |= 1u << c;
-        if (__all_sync(0xffffffffu, hi <= c * 32 || lo >= c * 32 + 32)) none_mask |= 1u << c;
+      for (int c = 0; c < 2; ++c) {
+        const int cb = col0 + c * 32;
+        if (__all_sync(0xffffffffu, lo <= cb && hi >= cb + 32)) full_mask |= 1u << c;
+        if (__all_sync(0xffffffffu, hi <= cb || lo >= cb + 32)) none_mask |= 1u << c;
       }
-      // pass 1: row maximum of the tile
-      float mx = m;
-      if (generic) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
-          uint32_t x[32];
-          tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
-          tmem_ld_wait();
+      // ---- pass 1: row maximum ----
+      float mx_part = -INFINITY;
+      if (none_mask != 3u) {
+        uint32_t x[64];   // this thread's 64 scores (raw accumulators)
+        tmem_ld_32x32b_x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
+        tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
+        tmem_ld_wait();
+        if (generic) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score(x[j], pos0 + c0 + j));
-        }
-      } else {
-        float r0 = -INFINITY, r1 = -INFINITY, r2 = -INFINITY, r3 = -INFINITY;   // raw accumulator maxima
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if ((none_mask >> c) & 1u) continue;
-          uint32_t x[32];
-          tmem_ld_32x32b_x32(s_tmem + lane_addr + c * 32, x);
-          tmem_ld_wait();
-          if ((full_mask >> c) & 1u) {
+          for (int j = 0; j < 64; ++j) mx_part = fmaxf(mx_part, score(x[j], pos0 + col0 + j));
+        } else {
+          float r0 = -INFINITY, r1 = -INFINITY, r2 = -INFINITY, r3 = -INFINITY;   // raw accumulator maxima
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              r0 = fmaxf(r0, __uint_as_float(x[j]));
-              r1 = fmaxf(r1, __uint_as_float(x[j + 1]));
-              r2 = fmaxf(r2, __uint_as_float(x[j + 2]));
-              r3 = fmaxf(r3, __uint_as_float(x[j + 3]));
+          for (int c = 0; c < 2; ++c) {
+            if ((full_mask >> c) & 1u) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                r0 = fmaxf(r0, __uint_as_float(x[c * 32 + j]));
+                r1 = fmaxf(r1, __uint_as_float(x[c * 32 + j + 1]));
+                r2 = fmaxf(r2, __uint_as_float(x[c * 32 + j + 2]));
+                r3 = fmaxf(r3, __uint_as_float(x[c * 32 + j + 3]));
+              }
+            } else if (!((none_mask >> c) & 1u)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((unsigned)(col0 + c * 32 + j - lo) < span) r0 = fmaxf(r0, __uint_as_float(x[c * 32 + j]));
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if ((unsigned)(c * 32 + j - lo) < span) r0 = fmaxf(r0, __uint_as_float(x[j]));
           }
+          mx_part = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * p.scale_log2;   // scale > 0: max commutes
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * p.scale_log2);   // scale > 0: max commutes
       }
+      // the other half's maximum (parity-buffered: a thread cannot be two tiles ahead of its partner)
+      mx_sh[((i & 1) * 2 + h) * PF_ROWS + r] = mx_part;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float mx = fmaxf(m, fmaxf(mx_part, mx_sh[((i & 1) * 2 + (h ^ 1)) * PF_ROWS + r]));
       PF_T1(1);
       const float ms = (mx == -INFINITY) ? 0.f : mx;
       const float corr_new = exp2f(m - ms);         // rescales everything accumulated so far
@@ -405,77 +415,63 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       }
       corr = corr_new;
       PF_T1(2);
-      // pass 2: p = exp2(s - m), row sum, P -> T -> shared memory (K-major, 128-byte swizzle)
-      float sum = 0.f;
-      if (generic) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < PF_KEYS; c0 += 32) {
-          uint32_t x[32];
-          tmem_ld_32x32b_x32(s_tmem + lane_addr + c0, x);
+      // ---- pass 2: p = exp2(s - m), row sum, P -> T -> shared memory ----
+      float s0 = 0.f, s1 = 0.f;
+      const float neg_ms = -ms;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+        uint32_t x[32];   // loaded again rather than kept across the fold above (registers)
+        if (!((none_mask >> c) & 1u)) {
+          tmem_ld_32x32b_x32(s_tmem + c * 32, x);
           tmem_ld_wait();
-          uint32_t pk[16];
+        }
+        if ((none_mask >> c) & 1u) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        } else if (generic) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = exp2f(score(x[j], pos0 + c0 + j) - ms);
-            const float p1 = exp2f(score(x[j + 1], pos0 + c0 + j + 1) - ms);
+            const float p0 = exp2f(score(x[j], pos0 + col0 + c * 32 + j) - ms);
+            const float p1 = exp2f(score(x[j + 1], pos0 + col0 + c * 32 + j + 1) - ms);
             pk[j >> 1] = Num<T>::pack(p0, p1);   // P rounded to T for the second GEMM ...
-            sum += p0 + p1;                       // ... the row sum stays fp32 (online_softmax.cuh:39-162)
+            s0 += p0;                             // ... the row sum stays fp32 (online_softmax.cuh:39-162)
+            s1 += p1;
           }
-          store_p(c0, pk);
-        }
-      } else {
-        float s0 = 0.f, s1 = 0.f;
-        const float neg_ms = -ms;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-          if ((none_mask >> c) & 1u) {
+        } else if ((full_mask >> c) & 1u) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          } else {
-            uint32_t x[32];
-            tmem_ld_32x32b_x32(s_tmem + lane_addr + c * 32, x);
-            tmem_ld_wait();
-            if ((full_mask >> c) & 1u) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
-                const float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
-                pk[j >> 1] = Num<T>::pack(p0, p1);
-                s0 += p0;
-                s1 += p1;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
-                float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
-                p0 = (unsigned)(c * 32 + j - lo) < span ? p0 : 0.f;
-                p1 = (unsigned)(c * 32 + j + 1 - lo) < span ? p1 : 0.f;
-                pk[j >> 1] = Num<T>::pack(p0, p1);
-                s0 += p0;
-                s1 += p1;
-              }
-            }
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
+            const float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
+            pk[j >> 1] = Num<T>::pack(p0, p1);
+            s0 += p0;
+            s1 += p1;
           }
-          store_p(c * 32, pk);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float p0 = pf_ex2(fmaf(__uint_as_float(x[j]), p.scale_log2, neg_ms));
+            float p1 = pf_ex2(fmaf(__uint_as_float(x[j + 1]), p.scale_log2, neg_ms));
+            p0 = (unsigned)(col0 + c * 32 + j - lo) < span ? p0 : 0.f;
+            p1 = (unsigned)(col0 + c * 32 + j + 1 - lo) < span ? p1 : 0.f;
+            pk[j >> 1] = Num<T>::pack(p0, p1);
+            s0 += p0;
+            s1 += p1;
+          }
         }
-        sum = s0 + s1;
+        store_p(c, pk);
       }
-      l = fmaf(l, corr_new, sum);
+      l = fmaf(l, corr_new, s0 + s1);   // this half's share of the row sum
       m = mx;
       // keys of the tile that do not exist: their V rows hold whatever the ring held (maybe NaN) and
-      // 0 * NaN is NaN — zero them (their P columns are exactly 0 already)
+      // 0 * NaN is NaN — zero them (their P columns are exactly 0 already); half h clears d chunk h
       const int valid = min(PF_KEYS, kv_end - pos0);
       if (valid < PF_KEYS) {   // CTA-uniform: the sequence's last tile
         mbar_wait(&v_full[i & 1], (i >> 1) & 1);   // the boxes that do exist have landed
         if (r >= valid) {
-          uint8_t* vrow = v_smem + (i & 1) * PF_TILE + (r >> 3) * p.kv_sbo + (r & 7) * 128;
+          uint8_t* vrow = v_smem + (i & 1) * PF_TILE + (r >> 3) * p.kv_sbo + (r & 7) * 128 + h * p.kv_chunk;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            *reinterpret_cast<uint4*>(vrow + u * 16) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(vrow + p.kv_chunk + u * 16) = make_uint4(0, 0, 0, 0);
-          }
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(vrow + u * 16) = make_uint4(0, 0, 0, 0);
         }
       }
       tc_fence_before();
@@ -483,7 +479,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       mbar_arrive(p_full);
       PF_T1(3);
     }
-    if (TRACE && tr && r == 0) {
+    if (TRACE && tr && threadIdx.x == 0) {
       tr[1] = n_tiles;
       tr[2] = tacc[0];
       tr[3] = tacc[1];
@@ -493,11 +489,15 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     mbar_wait(pv_full, (n_tiles - 1) & 1);
     tc_fence_after();
     add_pv(corr);
+    // the row sum: both halves' shares
+    mx_sh[h * PF_ROWS + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    l += mx_sh[(h ^ 1) * PF_ROWS + r];
     if (row_ok) {
       const float inv = 1.f / l;
-      T* dst = static_cast<T*>(p.out) + (int64_t)(q_begin + tok0 + qi) * p.o_stride_t + (int64_t)head * p.o_stride_h;
+      T* dst = static_cast<T*>(p.out) + (int64_t)(q_begin + tok0 + qi) * p.o_stride_t + (int64_t)head * p.o_stride_h + h * 64;
 #pragma unroll
-      for (int c0 = 0; c0 < PF_D; c0 += 8) {
+      for (int c0 = 0; c0 < 64; c0 += 8) {
         uint4 v;
         v.x = Num<T>::pack(o[c0] * inv, o[c0 + 1] * inv);
         v.y = Num<T>::pack(o[c0 + 2] * inv, o[c0 + 3] * inv);
@@ -658,11 +658,15 @@ int launch_prefill_attn(void* out, const void* q, const void* k_cache, const voi
   const unsigned n_rb = (unsigned)(((int64_t)max_q_len + p.tokens_per_block - 1) / p.tokens_per_block);
   dim3 grid(n_rb, (unsigned)n_kv_heads, (unsigned)batch);
   if (dtype == B200_BF16) {
-    auto kern = debug_trace_ptr() ? prefill_attn_kernel<__nv_bfloat16, true> : prefill_attn_kernel<__nv_bfloat16, false>;
+    const bool gen = p.use_cap != 0 || p.alibi != nullptr;
+    auto kern = debug_trace_ptr() ? (gen ? prefill_attn_kernel<__nv_bfloat16, true, true> : prefill_attn_kernel<__nv_bfloat16, true, false>)
+                                  : (gen ? prefill_attn_kernel<__nv_bfloat16, false, true> : prefill_attn_kernel<__nv_bfloat16, false, false>);
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   } else {
-    auto kern = debug_trace_ptr() ? prefill_attn_kernel<__half, true> : prefill_attn_kernel<__half, false>;
+    const bool gen = p.use_cap != 0 || p.alibi != nullptr;
+    auto kern = debug_trace_ptr() ? (gen ? prefill_attn_kernel<__half, true, true> : prefill_attn_kernel<__half, true, false>)
+                                  : (gen ? prefill_attn_kernel<__half, false, true> : prefill_attn_kernel<__half, false, false>);
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     B200_PDL_LAUNCH_L(1, "prefill_attn", kern, grid, PF_THREADS, PF_SMEM, st, qmap, qmap1, kmap, vmap, p, debug_trace_ptr());
   }

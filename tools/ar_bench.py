@@ -64,7 +64,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     pg = ProcessGroup(rank, world, dev)
     say = (lambda *a: print(*a, flush=True)) if rank == 0 else (lambda *a: None)
-    algo = os.environ.get("B200_AR_ALGO", "") or ("twoshot" if world > 2 else "oneshot")
+    algo = os.environ.get("B200_AR_ALGO", "") or "twoshot"
     say(f"== world {world}, all-reduce algorithm {algo}")
     for rows, n in ((64, 4096), (32, 8192), (8, 4096)):
         x = torch.randn(rows, n, device=dev).bfloat16()
