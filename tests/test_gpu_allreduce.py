@@ -145,6 +145,19 @@ def _worker(rank, world, port, algo=""):
             graph.replay()
             torch.cuda.synchronize()
             assert torch.equal(buf, torch.full_like(buf, expect))
+        # all-reduces directly after one another inside one graph (a sliced large message, a micro-
+        # benchmark): each launch may start while its predecessor is still exchanging — the epoch must be
+        # the one after the predecessor's (this sequence hung before the epoch was read after the wait)
+        small = torch.full((64, 4096), 1.0, device=dev, dtype=torch.float32)
+        chain = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(chain):
+            for _ in range(6):
+                pg.allreduce(small)
+        for rep in range(3):
+            small.fill_(1.0)
+            chain.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(small, torch.full_like(small, float(world) ** 6)), rep
     finally:
         pg.close()
         dist.destroy_process_group()
