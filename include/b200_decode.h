@@ -389,6 +389,15 @@ B200_API int b200_apply_frequency_presence_penalty(void* logits, const int64_t* 
                                                    int64_t vocab, int64_t max_len, int dtype,
                                                    b200_stream_t stream);
 B200_API int b200_softmax(void* logits, int64_t batch, int64_t vocab, int dtype, b200_stream_t stream);
+/* top-k / top-p filter, in place: replaces TopKTopPLogitsProcessor::forward
+ * (src/sampling/logits_processor.h:243-276: sort descending, mask sorted positions >= top_k[b], softmax of
+ * the rest, mask positions whose exclusive cumulative probability exceeds top_p[b], scatter back — a
+ * [batch, vocab] sort and four more library launches) by one launch that finds the cut with a radix
+ * histogram and writes -inf over everything outside it.  top_k [batch] int64 (<= 0: no top-k limit),
+ * top_p [batch] float (>= 1: no top-p limit); either may be NULL.  logits [batch, vocab] bf16 / fp16, row
+ * stride in elements.  Of equal logits straddling the cut the lowest vocabulary indices are kept. */
+B200_API int b200_topk_topp_filter(void* logits, const int64_t* top_k /*nullable*/, const float* top_p /*nullable*/,
+                                   int64_t batch, int64_t vocab, int64_t stride, int dtype, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * A9  Tensor-parallel all-reduce over NVLink peer memory

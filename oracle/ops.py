@@ -311,3 +311,40 @@ def softmax_inplace_semantics(logits: torch.Tensor) -> torch.Tensor:
     denom = torch.from_numpy((butterfly(red)[:, 0] + np.float32(1e-6)).astype(np.float32))
     denom = denom.to(dt).to(torch.float32)     # `logits[i] /= sum` is operator/=(T&, const T&): the divisor is rounded to T
     return (e.to(torch.float32) / denom[:, None]).to(dt)
+
+
+def top_k_top_p_filter(logits: torch.Tensor, top_k, top_p) -> torch.Tensor:
+    """TopKTopPLogitsProcessor::forward (src/sampling/logits_processor.h:243-276), restated:
+        sort each row descending; positions >= top_k -> -inf (top_k <= 0: no limit, :232-234);
+        probs = softmax of what is left; positions with (cumsum(probs) - probs) > top_p -> -inf;
+        scatter back to vocabulary order.
+    Restated with the choices the reference leaves open made explicit: the sort is STABLE (of equal
+    logits the lower vocabulary index comes first — torch.sort's order among ties is unspecified and the
+    reference's test, logits_processor_test.cpp:263-357, only compares sorted values), and softmax /
+    cumsum run in float64 where the reference's tensors are of the logits' dtype (bf16: every prob and
+    every partial sum rounded to 8 bits — a token whose exclusive cumulative probability is within
+    that rounding of top_p can fall on either side there).  logits [batch, vocab]; top_k int64 [batch] or
+    None; top_p float [batch] or None.  Returns a new tensor of the logits' dtype."""
+    x = logits.detach().cpu()
+    out = x.clone()
+    B, V = x.shape
+    for b in range(B):
+        v = x[b].double()
+        order = torch.sort(v, descending=True, stable=True).indices
+        keep = torch.ones(V, dtype=torch.bool)
+        k = V
+        if top_k is not None:
+            kk = int(top_k[b])
+            if 0 < kk < V:
+                k = kk
+        keep[k:] = False
+        if top_p is not None:
+            p = float(top_p[b])
+            vs = v[order].clone()
+            vs[k:] = float("-inf")
+            probs = torch.softmax(vs, dim=-1)
+            excl = torch.cumsum(probs, dim=-1) - probs
+            keep &= ~(excl > p)
+        dropped = order[~keep]
+        out[b, dropped] = float("-inf")
+    return out

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_apply_repetition_penalty": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_apply_frequency_presence_penalty": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_softmax": (_int, [_vp, _i64, _i64, _int, _vp]),
+    "b200_topk_topp_filter": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_argmax": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "b200_rope_kv_write_splitk": (_int, [_vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64,
                                          _i64, _i64, _int, _int, _vp]),

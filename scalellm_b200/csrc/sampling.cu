@@ -4,6 +4,8 @@
 //   src/kernels/sampling/penalty_kernels.cu:9-33,52-75,107-140   src/kernels/sampling/softmax_kernels.cu:11-54
 // restated, never copied.  Greedy selection is b200_argmax / b200_ar_argmax (elementwise.cu,
 // allreduce.cu).  All in place on logits [batch, vocab] (contiguous), one launch each, capturable.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -111,6 +113,262 @@ __global__ void __launch_bounds__(1024) softmax_kernel(T* __restrict__ logits, i
     for (int64_t i = threadIdx.x; i < vocab; i += BD) row[i] = Num<T>::from_f(Num<T>::to_f(row[i]) / denom);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// top-k / top-p filter (TopKTopPLogitsProcessor::forward, src/sampling/logits_processor.h:243-276: sort
+// descending, mask positions >= k, softmax of what is left, mask positions whose exclusive cumulative
+// probability exceeds p, scatter back — five library launches and a [batch, vocab] sort).  Both masks
+// keep a PREFIX of the sorted order, so the result is "keep the m largest logits": this kernel finds
+// m per row without sorting — a two-level radix histogram (count + probability mass per bin) over the
+// 16-bit order-preserving key of the bf16 / fp16 logit — and writes -inf over everything else, in place.
+//   * masses are accumulated in 2^-40 fixed point (integer adds commute: deterministic);
+//   * equal logits are exact ties (same key, same mass): of a tied group that straddles the cut, the
+//     ones with the lowest vocabulary index are kept (the reference's sort order among ties is
+//     unspecified; its test, logits_processor_test.cpp:263-357, compares sorted values only);
+//   * sums are fp32 / fixed point where the reference's are bf16 tensors (softmax and cumsum outputs
+//     rounded to T): a token whose exclusive cumulative probability is within bf16 rounding of p may
+//     fall on the other side (tests/test_gpu_sampling.py bounds that).
+// One block of 1024 threads per row, five passes over the row (L2 resident after the first).
+// ---------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 1024, TK_WARPS = 32, TK_BINS = 256;
+constexpr double TK_FIX = 1099511627776.0;   // 2^40
+
+__device__ __forceinline__ uint32_t tk_key(uint32_t u16) {   // ascending order-preserving key
+  return (u16 & 0x8000u) ? (~u16 & 0xFFFFu) : (u16 | 0x8000u);
+}
+__device__ __forceinline__ uint32_t tk_unkey(uint32_t key) {
+  return (key & 0x8000u) ? (key & 0x7FFFu) : (~key & 0xFFFFu);
+}
+template <typename T>
+__device__ __forceinline__ float tk_val(uint32_t u16) {
+  const uint16_t h = (uint16_t)u16;
+  return Num<T>::to_f(*reinterpret_cast<const T*>(&h));
+}
+__device__ __forceinline__ unsigned long long tk_mass(float x, float xmax) {
+  const float e = __expf(x - xmax);
+  return e >= 0.f ? (unsigned long long)((double)e * TK_FIX) : 0ull;   // NaN logits carry no mass
+}
+
+struct TkShared {
+  uint32_t cnt[TK_BINS];
+  unsigned long long mass[TK_BINS];
+  float red[TK_WARPS];
+  int red_i[TK_WARPS];
+  // decisions broadcast by thread 0
+  int bin_k, bin_p, need_level2_p, key_t, ties_kept, ties_total, done;
+  unsigned long long m_above, z_fix, t_fix;
+  uint32_t c_above;
+  float xmax;
+};
+
+// privatised histograms: [warp][bin] in dynamic shared memory, reduced into TkShared::cnt / mass
+template <typename T, int LEVEL>
+__device__ __forceinline__ void tk_histogram(const uint16_t* __restrict__ row, int n, float xmax, int bin_hi,
+                                             uint32_t* wcnt, unsigned long long* wmass, TkShared& sh) {
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < TK_WARPS * TK_BINS; i += TK_THREADS) {
+    wcnt[i] = 0;
+    wmass[i] = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += TK_THREADS) {
+    const uint32_t u = row[i];
+    const uint32_t key = tk_key(u);
+    int bin;
+    if (LEVEL == 1) {
+      bin = key >> 8;
+    } else {
+      if ((int)(key >> 8) != bin_hi) continue;
+      bin = key & 255;
+    }
+    atomicAdd(&wcnt[warp * TK_BINS + bin], 1u);
+    atomicAdd(&wmass[warp * TK_BINS + bin], tk_mass(tk_val<T>(u), xmax));
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < TK_BINS; b += TK_THREADS) {
+    uint32_t c = 0;
+    unsigned long long m = 0;
+    for (int w = 0; w < TK_WARPS; ++w) {
+      c += wcnt[w * TK_BINS + b];
+      m += wmass[w * TK_BINS + b];
+    }
+    sh.cnt[b] = c;
+    sh.mass[b] = m;
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ logits, const int64_t* __restrict__ top_k,
+                                                               const float* __restrict__ top_p, int64_t vocab,
+                                                               int64_t stride) {
+  extern __shared__ __align__(16) uint8_t tk_dyn[];
+  unsigned long long* wmass = reinterpret_cast<unsigned long long*>(tk_dyn);
+  uint32_t* wcnt = reinterpret_cast<uint32_t*>(wmass + TK_WARPS * TK_BINS);
+  __shared__ TkShared sh;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int n = (int)vocab;
+  uint16_t* row = reinterpret_cast<uint16_t*>(logits + (int64_t)blockIdx.x * stride);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t k64 = top_k ? top_k[blockIdx.x] : 0;
+  if (k64 <= 0 || k64 > n) k64 = n;   // <= 0 disables top-k (logits_processor.h:232-234)
+  const int k = (int)k64;
+  const float p = top_p ? top_p[blockIdx.x] : 2.0f;
+  if (k == n && !(p < 1.0f)) return;   // nothing to filter (block-uniform)
+
+  // ---- pass 0: row maximum ----
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += TK_THREADS) mx = fmaxf(mx, tk_val<T>(row[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) sh.red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = sh.red[0];
+    for (int w = 1; w < TK_WARPS; ++w) v = fmaxf(v, sh.red[w]);
+    sh.xmax = v;
+  }
+  __syncthreads();
+  const float xmax = sh.xmax;
+  if (xmax == -INFINITY) return;   // an all -inf row stays as it is
+
+  // ---- pass A: level-1 histogram (high byte of the key); the top-k boundary's bin ----
+  tk_histogram<T, 1>(row, n, xmax, 0, wcnt, wmass, sh);
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    unsigned long long m = 0;
+    int b = TK_BINS - 1;
+    for (; b > 0; --b) {
+      if (c + sh.cnt[b] >= (uint32_t)k) break;
+      c += sh.cnt[b];
+      m += sh.mass[b];
+    }
+    sh.bin_k = b;
+    sh.c_above = c;
+    sh.m_above = m;
+  }
+  __syncthreads();
+  const int bin_k = sh.bin_k;
+  // level-1 masses of the bins above bin_k are needed again after pass B overwrites the histogram
+  unsigned long long my_mass1 = 0;
+  uint32_t my_cnt1 = 0;
+  if (threadIdx.x < TK_BINS) {
+    my_mass1 = sh.mass[threadIdx.x];
+    my_cnt1 = sh.cnt[threadIdx.x];
+  }
+  __syncthreads();
+
+  // ---- pass B: level-2 histogram inside bin_k: the exact k-th key, Z of the top-k set ----
+  tk_histogram<T, 2>(row, n, xmax, bin_k, wcnt, wmass, sh);
+  if (threadIdx.x == 0) {
+    uint32_t c = sh.c_above;
+    unsigned long long m = sh.m_above;
+    int l = TK_BINS - 1;
+    for (; l > 0; --l) {
+      if (c + sh.cnt[l] >= (uint32_t)k) break;
+      c += sh.cnt[l];
+      m += sh.mass[l];
+    }
+    const int key_k = (bin_k << 8) | l;
+    const uint32_t need_k = (uint32_t)k - c;                      // ties of key_k inside the top k (>= 1)
+    const unsigned long long q_k = sh.cnt[l] ? sh.mass[l] / sh.cnt[l] : 0;   // every tie has the same mass
+    sh.z_fix = m + (unsigned long long)need_k * q_k;               // softmax denominator after the top-k mask
+    sh.key_t = key_k;
+    sh.ties_kept = (int)need_k;
+    sh.ties_total = (int)sh.cnt[l];
+    sh.t_fix = (p < 1.0f) ? (p > 0.f ? (unsigned long long)((double)p * (double)sh.z_fix) : 0ull) : ~0ull;
+    sh.bin_p = -1;
+    sh.need_level2_p = 0;
+  }
+  __syncthreads();
+
+  // ---- top-p: the level-1 bin (above bin_k) where the exclusive cumulative mass first exceeds p Z ----
+  if (p < 1.0f) {
+    // serial scan over <= 256 bins by warp 0 lane 0, reading the saved level-1 masses through shared memory
+    __shared__ unsigned long long m1[TK_BINS];
+    __shared__ uint32_t c1[TK_BINS];
+    if (threadIdx.x < TK_BINS) {
+      m1[threadIdx.x] = my_mass1;
+      c1[threadIdx.x] = my_cnt1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long M = 0;
+      uint32_t C = 0;
+      int found = -1;
+      for (int b = TK_BINS - 1; b > bin_k; --b) {
+        if (M + m1[b] > sh.t_fix) { found = b; break; }
+        M += m1[b];
+        C += c1[b];
+      }
+      if (found >= 0) {          // the cut lies inside a bin above bin_k: needs that bin's level-2 histogram
+        sh.bin_p = found;
+        sh.need_level2_p = 1;
+        sh.m_above = M;
+        sh.c_above = C;
+      } else {                   // inside bin_k (its top-k part), or not at all
+        sh.bin_p = bin_k;
+        // sh.m_above / c_above still describe the bins above bin_k (== M, C)
+      }
+    }
+    __syncthreads();
+    if (sh.need_level2_p) tk_histogram<T, 2>(row, n, xmax, sh.bin_p, wcnt, wmass, sh);   // block-uniform branch
+    if (threadIdx.x == 0) {
+      unsigned long long M = sh.m_above;
+      const int key_k = sh.key_t;
+      const int in_k_bin = sh.bin_p == bin_k;
+      for (int l = TK_BINS - 1; l >= 0; --l) {
+        const int key = (sh.bin_p << 8) | l;
+        if (in_k_bin && key < key_k) break;                                   // beyond the top-k set
+        uint32_t c = sh.cnt[l];
+        if (c == 0) continue;
+        const unsigned long long q = sh.mass[l] / c;
+        if (in_k_bin && key == key_k) c = (uint32_t)sh.ties_kept;             // only need_k of these ties are in the top k
+        if (M + (unsigned long long)c * q > sh.t_fix) {
+          // positions t = 0.. of this tied group have exclusive mass M + t q: kept while <= p Z
+          unsigned long long kept = q ? (sh.t_fix - M) / q + 1 : c;
+          if (kept > c) kept = c;
+          sh.key_t = key;
+          sh.ties_kept = (int)kept;
+          sh.ties_total = (int)sh.cnt[l];
+          break;
+        }
+        M += (unsigned long long)c * q;
+        if (in_k_bin && key == key_k) break;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- pass D: keep key > key_t, and the first ties_kept (by index) of key == key_t ----
+  const int key_t = sh.key_t, ties_kept = sh.ties_kept;
+  const bool rank_ties = ties_kept < sh.ties_total;
+  const uint16_t ninf = std::is_same<T, __nv_bfloat16>::value ? 0xFF80u : 0xFC00u;
+  int base = 0;   // ties seen in earlier chunks (block-uniform)
+  for (int i0 = 0; i0 < n; i0 += TK_THREADS) {
+    const int i = i0 + threadIdx.x;
+    const int key = i < n ? (int)tk_key(row[i]) : -1;
+    bool keep = key > key_t;
+    const bool tie = key == key_t;
+    if (rank_ties) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+      if (lane == 0) sh.red_i[warp] = __popc(bal);
+      __syncthreads();
+      int before = base;
+      for (int w = 0; w < warp; ++w) before += sh.red_i[w];
+      int total = 0;
+      for (int w = 0; w < TK_WARPS; ++w) total += sh.red_i[w];
+      if (tie) keep = before + __popc(bal & ((1u << lane) - 1u)) < ties_kept;
+      base += total;
+      __syncthreads();
+    } else if (tie) {
+      keep = true;
+    }
+    if (i < n && !keep) row[i] = ninf;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -174,6 +432,28 @@ int b200_softmax(void* logits, int64_t batch, int64_t vocab, int dtype, b200_str
   const int threads = (int)(vocab < 1024 ? ((vocab + 31) / 32) * 32 : 1024);
   SAMPLING_DISPATCH(dtype, B200_PDL_LAUNCH("softmax", softmax_kernel<T>, (unsigned)batch, threads, 0, st,
                                            static_cast<T*>(logits), vocab));
+  return B200_OK;
+}
+
+int b200_topk_topp_filter(void* logits, const int64_t* top_k, const float* top_p, int64_t batch, int64_t vocab,
+                          int64_t stride, int dtype, b200_stream_t stream) {
+  if (batch == 0 || (top_k == nullptr && top_p == nullptr)) return B200_OK;
+  B200_CHECK_ARG(logits && batch > 0 && vocab > 0 && vocab < (1ll << 31) && stride >= vocab,
+                 "topk_topp_filter: bad arguments");
+  B200_CHECK_ARG(dtype == B200_BF16 || dtype == B200_FP16, "topk_topp_filter: bf16 / fp16 logits only");
+  auto st = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)TK_WARPS * TK_BINS * (sizeof(unsigned long long) + sizeof(uint32_t));
+  if (dtype == B200_BF16) {
+    auto kern = topk_topp_kernel<__nv_bfloat16>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_PDL_LAUNCH("topk_topp_filter", kern, (unsigned)batch, TK_THREADS, smem, st,
+                    static_cast<__nv_bfloat16*>(logits), top_k, top_p, vocab, stride);
+  } else {
+    auto kern = topk_topp_kernel<__half>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_PDL_LAUNCH("topk_topp_filter", kern, (unsigned)batch, TK_THREADS, smem, st, static_cast<__half*>(logits),
+                    top_k, top_p, vocab, stride);
+  }
   return B200_OK;
 }
 

@@ -275,6 +275,18 @@ def invoke_softmax(logits: torch.Tensor) -> None:
     check(_lib.load().b200_softmax(_p(logits), logits.shape[0], logits.shape[1], _dt(logits), _stream()))
 
 
+def apply_top_k_top_p(logits: torch.Tensor, top_k: Optional[torch.Tensor], top_p: Optional[torch.Tensor]) -> None:
+    """TopKTopPLogitsProcessor::forward (src/sampling/logits_processor.h:243-276) in place, one launch:
+    everything outside the top-k / top-p cut of its row becomes -inf.  top_k [batch] int64 (<= 0: off),
+    top_p [batch] float32 (>= 1: off); either may be None."""
+    _cuda(logits, top_k, top_p)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float16)
+    assert top_k is None or (top_k.dtype == torch.int64 and top_k.is_contiguous() and top_k.numel() == logits.shape[0])
+    assert top_p is None or (top_p.dtype == torch.float32 and top_p.is_contiguous() and top_p.numel() == logits.shape[0])
+    check(_lib.load().b200_topk_topp_filter(_p(logits), _p(top_k), _p(top_p), logits.shape[0], logits.shape[1],
+                                            logits.stride(0), _dt(logits), _stream()))
+
+
 def _gelu(input: torch.Tensor, act: int, with_mul: bool) -> torch.Tensor:
     _cuda(input)
     assert input.dim() == 2 and input.stride(1) == 1 and (not with_mul or input.is_contiguous())

@@ -184,6 +184,25 @@ void invoke_softmax(torch::Tensor& logits) {
   ok(b200_softmax(logits.data_ptr(), logits.size(0), logits.size(1), dtype_of(logits), stream()), "softmax");
 }
 
+void apply_top_k_top_p(torch::Tensor& logits, const torch::Tensor& top_k, const torch::Tensor& top_p) {
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1, "apply_top_k_top_p: [batch, vocab] logits, dense rows");
+  TORCH_CHECK(logits.scalar_type() == torch::kBFloat16 || logits.scalar_type() == torch::kHalf,
+              "apply_top_k_top_p: bf16 / fp16 logits");
+  torch::Tensor k, p;
+  if (top_k.defined()) {
+    k = top_k.to(logits.device(), torch::kInt64).reshape({-1}).contiguous();
+    TORCH_CHECK(k.numel() == logits.size(0), "apply_top_k_top_p: one top_k per row");
+  }
+  if (top_p.defined()) {
+    p = top_p.to(logits.device(), torch::kFloat32).reshape({-1}).contiguous();
+    TORCH_CHECK(p.numel() == logits.size(0), "apply_top_k_top_p: one top_p per row");
+  }
+  ok(b200_topk_topp_filter(logits.data_ptr(), k.defined() ? k.const_data_ptr<int64_t>() : nullptr,
+                           p.defined() ? p.const_data_ptr<float>() : nullptr, logits.size(0), logits.size(1),
+                           logits.stride(0), dtype_of(logits), stream()),
+     "topk_topp_filter");
+}
+
 torch::Tensor gelu_new(torch::Tensor input) { return gelu_impl(input, 1, false); }
 torch::Tensor gelu_fast(torch::Tensor input) { return gelu_impl(input, 2, false); }
 torch::Tensor gelu_new_with_mul(torch::Tensor input) { return gelu_impl(input, 1, true); }

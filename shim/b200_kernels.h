@@ -60,6 +60,11 @@ void apply_frequency_presence_penalty(torch::Tensor& logits, const torch::Tensor
                                       const torch::Tensor& frequency_penalties,
                                       const torch::Tensor& presence_penalties);
 void invoke_softmax(torch::Tensor& logits);
+// B200 extension: TopKTopPLogitsProcessor::forward (src/sampling/logits_processor.h:243-276) in place in
+// one launch instead of sort + masked_fill + softmax + cumsum + gather.  top_k: int64 [n] (<= 0: no limit)
+// or undefined; top_p: float [n] (>= 1: no limit) or undefined.  The processor's forward() becomes
+//   auto out = logits.clone(); kernel::apply_top_k_top_p(out, top_k, top_p); return out;
+void apply_top_k_top_p(torch::Tensor& logits, const torch::Tensor& top_k, const torch::Tensor& top_p);
 
 // B200 extension used by B200AttnHandler: rope + cache write in one launch
 // (bit-identical to apply_rotary_pos_emb followed by set_kv_cache).

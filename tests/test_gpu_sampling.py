@@ -97,3 +97,74 @@ def test_softmax_in_place(dtype, B, V):
         r = logits.to(DEV).clone()
         ref.invoke_softmax(r)
         assert torch.equal(x, r)
+
+
+def _kept(t):
+    return torch.isfinite(t.float())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("vocab", [128256, 50257, 1000])
+def test_top_k_top_p_filter_matches_the_restated_processor(dtype, vocab):
+    """b200_topk_topp_filter against oracle.ops.top_k_top_p_filter (TopKTopPLogitsProcessor::forward,
+    logits_processor.h:243-276, stable sort, float64 sums): the same tokens survive, the survivors keep
+    their bits.  Rows cover: top-k only, top-p only, both, neither, k > vocab, p tiny (only the arg max
+    survives), p >= 1, and rows of few distinct values (many exact ties at the cut)."""
+    g = torch.Generator().manual_seed(vocab)
+    B = 10
+    x = (torch.randn(B, vocab, generator=g) * 3).to(dtype)
+    x[6] = torch.randint(-2, 3, (vocab,), generator=g).to(dtype)          # 5 distinct values: ties everywhere
+    x[7] = x[7].float().round().to(dtype)                                  # integer logits: ties at the cut
+    top_k = torch.tensor([50, 0, 40, 0, vocab + 5, 1, 300, 77, 0, 5], dtype=torch.int64)
+    top_p = torch.tensor([1.0, 0.9, 0.5, 1.0, 0.95, 0.3, 0.8, 0.6, 1e-6, 1.5], dtype=torch.float32)
+    want = ops.top_k_top_p_filter(x, top_k, top_p)
+    got = x.to(DEV).clone()
+    kernels.apply_top_k_top_p(got, top_k.to(DEV), top_p.to(DEV))
+    got = got.cpu()
+    for b in range(B):
+        kg, kw = _kept(got[b]), _kept(want[b])
+        # the kept counts agree up to the summation arithmetic at the top-p boundary (fixed point vs float64:
+        # identical unless a cumulative probability lands within ~1e-6 of p)
+        assert abs(int(kg.sum()) - int(kw.sum())) <= (0 if top_p[b] >= 1 else 1), (b, int(kg.sum()), int(kw.sum()))
+        if int(kg.sum()) == int(kw.sum()):
+            assert torch.equal(kg, kw), b                                   # same tokens, ties by lowest index
+        assert torch.equal(got[b][kg].view(torch.int16), x[b][kg].view(torch.int16))   # survivors untouched
+        assert bool((got[b][~kg] == float("-inf")).all())
+        # a prefix of the sorted order: every survivor >= every dropped logit
+        if (~kg).any():
+            assert float(x[b][kg].float().min()) >= float(x[b][~kg].float().max())
+    # either argument may be absent; a strided view works; run to run identical
+    only_k = x.to(DEV).clone()
+    kernels.apply_top_k_top_p(only_k, top_k.to(DEV), None)
+    assert torch.equal(_kept(only_k.cpu()), _kept(ops.top_k_top_p_filter(x, top_k, None)))
+    buf = torch.zeros(B, vocab + 24, dtype=dtype, device=DEV)
+    buf[:, :vocab] = x.to(DEV)
+    kernels.apply_top_k_top_p(buf[:, :vocab], top_k.to(DEV), top_p.to(DEV))
+    assert torch.equal(buf[:, :vocab].cpu().view(torch.int16), got.view(torch.int16))
+    assert bool((buf[:, vocab:] == 0).all())
+
+
+def test_top_k_top_p_filter_against_the_library_pipeline():
+    """The reference's own sequence of library calls (sort, masked_fill, softmax, cumsum, gather) on the
+    same bf16 logits on the GPU: same survivors except tokens whose exclusive cumulative probability is
+    within bf16 rounding of top_p, and except the order among exact ties."""
+    g = torch.Generator().manual_seed(3)
+    B, V = 16, 32000
+    x = (torch.randn(B, V, generator=g) * 4).bfloat16().to(DEV)
+    top_k = torch.tensor([0, 100, 1000, 20] * 4, dtype=torch.int64, device=DEV)
+    top_p = torch.tensor([0.9, 0.95, 0.5, 0.99] * 4, dtype=torch.float32, device=DEV)
+    # logits_processor.h:243-276 verbatim in torch
+    ls, li = x.sort(dim=-1, descending=True)
+    kk = torch.where(top_k <= 0, torch.full_like(top_k, 2 ** 62), top_k).unsqueeze(1)
+    ls = ls.masked_fill(torch.arange(V, device=DEV).expand_as(ls) >= kk, float("-inf"))
+    ps = ls.softmax(dim=-1)
+    ls = ls.masked_fill((ps.cumsum(dim=-1) - ps) > top_p.unsqueeze(1), float("-inf"))
+    lib = ls.gather(-1, li.argsort(-1))
+    got = x.clone()
+    kernels.apply_top_k_top_p(got, top_k, top_p)
+    n_lib, n_got = _kept(lib).sum(-1), _kept(got).sum(-1)
+    # bf16 cumsum saturates near 1: allow a slack proportional to the kept count for the top-p rows
+    assert bool(((n_lib - n_got).abs() <= 2 + n_got // 8).all()), (n_lib.tolist(), n_got.tolist())
+    # both keep a prefix of the sorted order containing the arg max
+    am = x.float().argmax(-1)
+    assert bool(_kept(got)[torch.arange(B), am].all()) and bool(_kept(lib)[torch.arange(B), am].all())
