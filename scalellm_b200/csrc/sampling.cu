@@ -161,28 +161,84 @@ struct TkShared {
   float xmax;
 };
 
-// privatised histograms: [warp][bin] in dynamic shared memory, reduced into TkShared::cnt / mass
+// The row as 16-byte vectors (8 logits) when its base and length allow, scalars otherwise: a single block
+// streaming 256 KB with 2-byte loads is latency bound (~40 us per pass at vocabulary 128 256).
+struct TkRow {
+  const uint16_t* p;
+  int n, nvec;   // nvec vectors of 8 cover [0, 8 nvec); the tail [8 nvec, n) is read as scalars
+};
+__device__ __forceinline__ TkRow tk_row(const uint16_t* row, int n) {
+  const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+  return TkRow{row, n, vec ? n / 8 : 0};
+}
+
+// privatised histograms: [warp][bin] in dynamic shared memory, reduced into TkShared::cnt / mass.
+// Level 1 (high byte: sign + 7 exponent bits — logits crowd into a handful of bins): the lanes of a warp
+// that hit the same bin are found with ballots and their masses added with warp reductions, one shared-
+// memory atomic per distinct bin instead of up to 32 conflicting ones.  Level 2 (low byte inside one
+// high-byte bin: few lanes, spread out): plain atomics.
 template <typename T, int LEVEL>
-__device__ __forceinline__ void tk_histogram(const uint16_t* __restrict__ row, int n, float xmax, int bin_hi,
-                                             uint32_t* wcnt, unsigned long long* wmass, TkShared& sh) {
+__device__ __forceinline__ void tk_add(uint32_t u, bool valid, float xmax, int bin_hi, uint32_t* wc,
+                                       unsigned long long* wm) {
+  const uint32_t key = tk_key(u);
+  if (LEVEL == 1) {
+    const int bin = valid ? (int)(key >> 8) : -1;
+    const unsigned long long q = valid ? tk_mass(tk_val<T>(u), xmax) : 0ull;
+    const uint32_t q_lo = (uint32_t)(q & 0xFFFFFu), q_hi = (uint32_t)(q >> 20);   // 32 x 2^20 < 2^32
+    uint32_t todo = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int lbin = __shfl_sync(0xffffffffu, bin, leader);
+      const bool mine = bin == lbin;
+      const uint32_t peers = __ballot_sync(0xffffffffu, mine);
+      const uint32_t lo = __reduce_add_sync(0xffffffffu, mine ? q_lo : 0u);
+      const uint32_t hi = __reduce_add_sync(0xffffffffu, mine ? q_hi : 0u);
+      if (lane == leader) {
+        wc[lbin] += __popc(peers);                       // this warp's private histogram: no atomics needed
+        wm[lbin] += ((unsigned long long)hi << 20) + lo;
+      }
+      todo &= ~peers;
+    }
+    __syncwarp();
+  } else {
+    if (valid && (int)(key >> 8) == bin_hi) {
+      atomicAdd(&wc[key & 255], 1u);
+      atomicAdd(&wm[key & 255], tk_mass(tk_val<T>(u), xmax));
+    }
+  }
+}
+
+template <typename T, int LEVEL>
+__device__ __forceinline__ void tk_histogram(const TkRow& r, float xmax, int bin_hi, uint32_t* wcnt,
+                                             unsigned long long* wmass, TkShared& sh) {
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < TK_WARPS * TK_BINS; i += TK_THREADS) {
     wcnt[i] = 0;
     wmass[i] = 0;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += TK_THREADS) {
-    const uint32_t u = row[i];
-    const uint32_t key = tk_key(u);
-    int bin;
-    if (LEVEL == 1) {
-      bin = key >> 8;
-    } else {
-      if ((int)(key >> 8) != bin_hi) continue;
-      bin = key & 255;
+  uint32_t* wc = wcnt + warp * TK_BINS;
+  unsigned long long* wm = wmass + warp * TK_BINS;
+  // whole warps iterate together (the level-1 path uses warp collectives): pad the trip counts
+  const int vec_iters = (r.nvec + TK_THREADS - 1) / TK_THREADS;
+  for (int it = 0; it < vec_iters; ++it) {
+    const int v = it * TK_THREADS + threadIdx.x;
+    const bool ok = v < r.nvec;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (ok) raw = reinterpret_cast<const uint4*>(r.p)[v];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tk_add<T, LEVEL>(w[j] & 0xFFFFu, ok, xmax, bin_hi, wc, wm);
+      tk_add<T, LEVEL>(w[j] >> 16, ok, xmax, bin_hi, wc, wm);
     }
-    atomicAdd(&wcnt[warp * TK_BINS + bin], 1u);
-    atomicAdd(&wmass[warp * TK_BINS + bin], tk_mass(tk_val<T>(u), xmax));
+  }
+  const int tail0 = r.nvec * 8, tail_iters = (r.n - tail0 + TK_THREADS - 1) / TK_THREADS;
+  for (int it = 0; it < tail_iters; ++it) {
+    const int i = tail0 + it * TK_THREADS + threadIdx.x;
+    const bool ok = i < r.n;
+    tk_add<T, LEVEL>(ok ? r.p[i] : 0u, ok, xmax, bin_hi, wc, wm);
   }
   __syncthreads();
   for (int b = threadIdx.x; b < TK_BINS; b += TK_THREADS) {
@@ -210,6 +266,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
   pdl_launch_dependents();
   const int n = (int)vocab;
   uint16_t* row = reinterpret_cast<uint16_t*>(logits + (int64_t)blockIdx.x * stride);
+  const TkRow rr = tk_row(row, n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t k64 = top_k ? top_k[blockIdx.x] : 0;
   if (k64 <= 0 || k64 > n) k64 = n;   // <= 0 disables top-k (logits_processor.h:232-234)
@@ -219,7 +276,13 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
 
   // ---- pass 0: row maximum ----
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += TK_THREADS) mx = fmaxf(mx, tk_val<T>(row[i]));
+  for (int v = threadIdx.x; v < rr.nvec; v += TK_THREADS) {
+    const uint4 raw = reinterpret_cast<const uint4*>(row)[v];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(tk_val<T>(w[j] & 0xFFFFu), tk_val<T>(w[j] >> 16)));
+  }
+  for (int i = rr.nvec * 8 + threadIdx.x; i < n; i += TK_THREADS) mx = fmaxf(mx, tk_val<T>(row[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) sh.red[warp] = mx;
@@ -234,7 +297,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
   if (xmax == -INFINITY) return;   // an all -inf row stays as it is
 
   // ---- pass A: level-1 histogram (high byte of the key); the top-k boundary's bin ----
-  tk_histogram<T, 1>(row, n, xmax, 0, wcnt, wmass, sh);
+  tk_histogram<T, 1>(rr, xmax, 0, wcnt, wmass, sh);
   if (threadIdx.x == 0) {
     uint32_t c = 0;
     unsigned long long m = 0;
@@ -260,7 +323,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
   __syncthreads();
 
   // ---- pass B: level-2 histogram inside bin_k: the exact k-th key, Z of the top-k set ----
-  tk_histogram<T, 2>(row, n, xmax, bin_k, wcnt, wmass, sh);
+  tk_histogram<T, 2>(rr, xmax, bin_k, wcnt, wmass, sh);
   if (threadIdx.x == 0) {
     uint32_t c = sh.c_above;
     unsigned long long m = sh.m_above;
@@ -313,7 +376,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
       }
     }
     __syncthreads();
-    if (sh.need_level2_p) tk_histogram<T, 2>(row, n, xmax, sh.bin_p, wcnt, wmass, sh);   // block-uniform branch
+    if (sh.need_level2_p) tk_histogram<T, 2>(rr, xmax, sh.bin_p, wcnt, wmass, sh);   // block-uniform branch
     if (threadIdx.x == 0) {
       unsigned long long M = sh.m_above;
       const int key_k = sh.key_t;
@@ -344,28 +407,74 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
   // ---- pass D: keep key > key_t, and the first ties_kept (by index) of key == key_t ----
   const int key_t = sh.key_t, ties_kept = sh.ties_kept;
   const bool rank_ties = ties_kept < sh.ties_total;
-  const uint16_t ninf = std::is_same<T, __nv_bfloat16>::value ? 0xFF80u : 0xFC00u;
+  const uint32_t ninf = std::is_same<T, __nv_bfloat16>::value ? 0xFF80u : 0xFC00u;
   int base = 0;   // ties seen in earlier chunks (block-uniform)
-  for (int i0 = 0; i0 < n; i0 += TK_THREADS) {
-    const int i = i0 + threadIdx.x;
-    const int key = i < n ? (int)tk_key(row[i]) : -1;
-    bool keep = key > key_t;
-    const bool tie = key == key_t;
-    if (rank_ties) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, tie);
-      if (lane == 0) sh.red_i[warp] = __popc(bal);
+  // chunks of 8 elements per thread (vector part) then 1 per thread (tail): index order = thread order
+  const int vec_iters = (rr.nvec + TK_THREADS - 1) / TK_THREADS;
+  const int tail0 = rr.nvec * 8, tail_iters = (n - tail0 + TK_THREADS - 1) / TK_THREADS;
+  for (int it = 0; it < vec_iters + tail_iters; ++it) {
+    const bool vec = it < vec_iters;
+    const int v = it * TK_THREADS + threadIdx.x;                         // vector index (vec part)
+    const int i1 = tail0 + (it - vec_iters) * TK_THREADS + threadIdx.x;   // element index (tail part)
+    const bool ok = vec ? v < rr.nvec : i1 < n;
+    uint32_t e[8];
+    int cnt = vec ? 8 : 1;
+    if (ok && vec) {
+      const uint4 raw = reinterpret_cast<const uint4*>(row)[v];
+      e[0] = raw.x & 0xFFFFu; e[1] = raw.x >> 16; e[2] = raw.y & 0xFFFFu; e[3] = raw.y >> 16;
+      e[4] = raw.z & 0xFFFFu; e[5] = raw.z >> 16; e[6] = raw.w & 0xFFFFu; e[7] = raw.w >> 16;
+    } else if (ok) {
+      e[0] = row[i1];
+    }
+    if (!ok) cnt = 0;
+    int my_ties = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < cnt && (int)tk_key(e[j]) == key_t) ++my_ties;
+    int before = 0;
+    if (rank_ties) {   // block-uniform
+      // exclusive prefix of my_ties over the block in thread order
+      int incl = my_ties;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) sh.red_i[warp] = incl;
       __syncthreads();
-      int before = base;
-      for (int w = 0; w < warp; ++w) before += sh.red_i[w];
+      before = base + incl - my_ties;
       int total = 0;
-      for (int w = 0; w < TK_WARPS; ++w) total += sh.red_i[w];
-      if (tie) keep = before + __popc(bal & ((1u << lane) - 1u)) < ties_kept;
+      for (int w = 0; w < TK_WARPS; ++w) {
+        if (w < warp) before += sh.red_i[w];
+        total += sh.red_i[w];
+      }
       base += total;
       __syncthreads();
-    } else if (tie) {
-      keep = true;
     }
-    if (i < n && !keep) row[i] = ninf;
+    bool changed = false;
+    int seen = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j >= cnt) continue;
+      const int key = (int)tk_key(e[j]);
+      bool keep = key > key_t;
+      if (key == key_t) {
+        keep = !rank_ties || (before + seen) < ties_kept;
+        ++seen;
+      }
+      if (!keep) {
+        e[j] = ninf;
+        changed = true;
+      }
+    }
+    if (changed) {
+      if (vec) {
+        reinterpret_cast<uint4*>(row)[v] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16),
+                                                      e[6] | (e[7] << 16));
+      } else {
+        row[i1] = (uint16_t)e[0];
+      }
+    }
   }
 }
 
