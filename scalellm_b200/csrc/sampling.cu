@@ -222,11 +222,15 @@ __device__ __forceinline__ void tk_histogram(const TkRow& r, float xmax, int bin
   unsigned long long* wm = wmass + warp * TK_BINS;
   // whole warps iterate together (the level-1 path uses warp collectives): pad the trip counts
   const int vec_iters = (r.nvec + TK_THREADS - 1) / TK_THREADS;
+  // the next iteration's vector is requested before this one's is consumed (one block per row: the
+  // pass is bound by the latency of its own loads otherwise)
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if ((int)threadIdx.x < r.nvec) nxt = reinterpret_cast<const uint4*>(r.p)[threadIdx.x];
   for (int it = 0; it < vec_iters; ++it) {
     const int v = it * TK_THREADS + threadIdx.x;
     const bool ok = v < r.nvec;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (ok) raw = reinterpret_cast<const uint4*>(r.p)[v];
+    const uint4 raw = nxt;
+    if (v + TK_THREADS < r.nvec) nxt = reinterpret_cast<const uint4*>(r.p)[v + TK_THREADS];
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_topp_kernel(T* __restrict__ l
 
   // ---- pass 0: row maximum ----
   float mx = -INFINITY;
+#pragma unroll 4
   for (int v = threadIdx.x; v < rr.nvec; v += TK_THREADS) {
     const uint4 raw = reinterpret_cast<const uint4*>(row)[v];
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
