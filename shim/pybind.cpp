@@ -20,6 +20,10 @@ PYBIND11_MODULE(_b200_shim, m) {
   });
   m.def("set_kv_cache", [](torch::Tensor slots, torch::Tensor k, torch::Tensor v, torch::Tensor kc,
                            torch::Tensor vc) { llm::kernel::set_kv_cache(slots, k, v, kc, vc); });
+  m.def("apply_top_k_top_p", [](torch::Tensor logits, c10::optional<torch::Tensor> top_k,
+                                c10::optional<torch::Tensor> top_p) {
+    llm::kernel::apply_top_k_top_p(logits, top_k.value_or(torch::Tensor()), top_p.value_or(torch::Tensor()));
+  });
   m.def("silu", &llm::kernel::silu);
   m.def("silu_with_mul", &llm::kernel::silu_with_mul);
   m.def("paged_kv_varlen_mha",

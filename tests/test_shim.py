@@ -72,6 +72,17 @@ def test_shim_matches_ctypes_path():
     kernels.paged_kv_varlen_mha(out1, *args)
     m.paged_kv_varlen_mha(out2, *args)
     assert torch.equal(out1, out2)
+    # the top-k / top-p filter through llm::kernel::apply_top_k_top_p (top_p handed over as fp16: converted)
+    lg = (torch.randn(5, 3000, device=dev) * 3).bfloat16()
+    tk = torch.tensor([10, 0, 5, 0, 50], dtype=torch.int64, device=dev)
+    tp = torch.tensor([0.9, 0.5, 1.0, 1.0, 0.25], dtype=torch.float32, device=dev)
+    f1, f2, f3 = lg.clone(), lg.clone(), lg.clone()
+    kernels.apply_top_k_top_p(f1, tk, tp)
+    m.apply_top_k_top_p(f2, tk, tp)
+    assert torch.equal(f1.view(torch.int16), f2.view(torch.int16))
+    m.apply_top_k_top_p(f3, None, tp)
+    kernels.apply_top_k_top_p(lg, None, tp)
+    assert torch.equal(f3.view(torch.int16), lg.view(torch.int16))
 
 
 def test_process_group_bindings_fail_loudly_without_gpu():
