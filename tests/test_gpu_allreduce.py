@@ -47,8 +47,12 @@ def _worker(rank, world, port, algo=""):
                         torch.cuda._sleep(2_000_000)
                     pg.allreduce(y)
                 torch.cuda.synchronize()
-                # ours == fp32 rank-order sum rounded once
-                assert torch.equal(y, host_sum.to(dtype)), (dtype, shape)
+                # ours == fp32 rank-order sum rounded once.  A message above the peer-memory limit (fp32
+                # [128, 4096] = 2 MiB) goes through NCCL, whose summation order is its own: close, not equal
+                if y.numel() * y.element_size() <= pg._nvlink_max_bytes:
+                    assert torch.equal(y, host_sum.to(dtype)), (dtype, shape)
+                else:
+                    assert torch.allclose(y.float(), host_sum, rtol=1e-5, atol=1e-5 * world), (dtype, shape)
                 # NCCL rounds its partial sums to the element type in its own order: only a sanity
                 # bound against it (the exact statement is the host sum above)
                 tol = 1e-2 * world if dtype != torch.float32 else 1e-5 * world
