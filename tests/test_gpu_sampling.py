@@ -83,14 +83,17 @@ def test_logits_processors_match_the_oracle_and_the_reference_kernels(dtype, B, 
 def test_softmax_in_place(dtype, B, V):
     """The GPU's __expf (ex2.approx of x * log2 e) differs from the host's exp by up to ~2e-5 relative
     at the arguments met here (|x - max| up to ~25), so the oracle comparison carries 2 ulp of T plus
-    that; against the reference's own kernel (same instruction) it is bit for bit."""
+    that — and 2 more because the divisor itself is rounded to T: an exponential that rounds the other
+    way on the host (its exp differs by CPU) can move the row sum across a rounding boundary of T, which
+    shifts every output of the row by one ulp of the divisor (seen on one GPU box, not on the others).
+    Against the reference's own kernel (same instruction) it is bit for bit."""
     logits = (torch.randn(B, V, generator=torch.Generator().manual_seed(V)) * 3).to(dtype)
     x = logits.to(DEV).clone()
     kernels.invoke_softmax(x)
     want = ops.softmax_inplace_semantics(logits)
     ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11, torch.float32: 2.0 ** -22}[dtype]
     tiny = 2.0 ** -23 if dtype == torch.float16 else 1e-12      # fp16: probabilities down in the subnormals
-    assert bool(((x.cpu().float() - want.float()).abs() <= (2 * ulp + 4e-5) * want.float().abs() + tiny).all())
+    assert bool(((x.cpu().float() - want.float()).abs() <= (4 * ulp + 4e-5) * want.float().abs() + tiny).all())
     assert abs(float(x.float().sum(-1).mean()) - 1.0) < 2e-2
     ref = _ref()
     if ref is not None:
