@@ -5,21 +5,30 @@
 //
 // Taken for query blocks of >= 64 packed rows (rows = (query token, head of the kv head's group),
 // the reference's own packing of q_len x group into M, sm80_kernel_mha.cuh:208-262), head_dim 128.
-// One CTA per (sequence, kv head, block of 128 packed rows); flash-attention over 128-key tiles:
-//   * warp 4 — producer: Q block once (3-D TMA {64 d, G heads, 128/G tokens} x 2, SWIZZLE_128B), then
-//     per tile the paged K and V rows as TMA boxes {64 d, min(block_size, 8) slots} through the block
-//     table (first-slot ids, sm80_kernel_mha.cuh:148-152) into a 2-stage ring; a tile lands as the
-//     tcgen05 canonical layouts directly: K = B operand, K-major atoms [8 keys x 64 d]; V = B operand
-//     of the second GEMM, MN-major atoms [8 keys x 64 d] — the same bytes, described differently;
-//   * warp 5 — MMA issuer: S = Q K^T (M 128 rows x N 128 keys x K 128) and PV = P V (M 128 x N 128 d
-//     x K 128 keys), tcgen05.mma.kind::f16, fp32 in TMEM (S and PV: 128 columns each);
-//   * warps 0-3 — softmax, thread <-> row (TMEM lane): two passes over S in TMEM (row max, then
-//     exp2 / sum), P rounded to T like the reference (sm80_collective_mha.cuh:289-290) and stored to
-//     shared memory as the K-major A operand of the second GEMM; O kept in registers, rescaled by
-//     exp2(m_old - m_new) and advanced by each tile's PV read back from TMEM.  Online softmax in
-//     the exp2 domain, masks (causal diagonal kv_len - q_len, sliding window, alibi, soft cap)
-//     exactly as the decode kernel.
-// No split-KV (a prefill block has enough CTAs), no workspace.
+// One CTA per (sequence, kv head, block of 128 packed rows); flash attention over 128-key tiles; ten warps:
+//   * warp 8 — producer: Q block once (3-D TMA {64 d, G heads, 128/G tokens} x 2, SWIZZLE_128B), then
+//     per tile the paged K and V rows as TMA boxes through the block table (first-slot ids,
+//     sm80_kernel_mha.cuh:148-152) into two separate 2-stage rings: K(i+2) may land as soon as S(i) has
+//     read K(i), V(i+2) once PV(i) has read V(i).  A tile lands as the tcgen05 canonical layouts directly:
+//     K = B operand of S = Q K^T, K-major atoms [8 keys x 64 d]; V = B operand of PV, MN-major atoms
+//     [8 keys x 64 d] — the same bytes, described differently.  block_size 8: one box of a re-ordered
+//     tensor map {64 d, slots, d chunks, heads} carries both d chunks of 8 slots ([chunk][slot][64], atoms
+//     2 KB apart); otherwise one box per d chunk of min(block_size, 128) slots;
+//   * warp 9 — MMA issuer: S = Q K^T (M 128 rows x N 128 keys x K 128) and PV = P V (M 128 x N 128 d
+//     x K 128 keys), tcgen05.mma.kind::f16, fp32 in TMEM; S is double buffered (S0 | S1 | PV: 384
+//     columns) and S(i+1) is issued before the wait for P(i), so it runs under the softmax of tile i;
+//   * warps 0-7 — softmax, two threads per row (warps w and w + 4 share a TMEM lane quarter; each thread
+//     owns 64 keys of the tile and 64 output columns; the row maximum crosses through shared memory once
+//     per tile): pass 1 row max, pass 2 exp2 / sum, P rounded to T like the reference
+//     (sm80_collective_mha.cuh:289-290) and stored to shared memory as the K-major A operand of the
+//     second GEMM; O kept in registers, rescaled by exp2(m_old - m_new) and advanced by each tile's PV
+//     read back from TMEM.  Every 32-column chunk is classified per warp: fully visible (one FMNMX per
+//     element in pass 1; FFMA + ex2.approx + FADD in pass 2), invisible (skipped) or crossed by the
+//     causal diagonal / window edge (masked).  Soft cap / alibi: a separate instantiation (GENERIC).
+// Online softmax in the exp2 domain; masks (causal diagonal kv_len - q_len, sliding window, alibi, soft
+// cap) exactly as the decode kernel.  No split-KV (a prefill block has enough CTAs), no workspace.
+// Per-role cycle traces of the four cuts that led here: profiles/r02_prefill_attn.md (TRACE instantiation,
+// tools/prefill_trace.py).
 #include <mutex>
 #include <type_traits>
 #include <vector>

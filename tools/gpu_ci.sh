@@ -9,7 +9,7 @@ OUT=gpurun_out
 STAGES="${*:-tests probe smoke bench ncu}"
 # "round2" = everything that was staged after round 1's GPU budget ran out, in one call
 if [[ " $STAGES " == *" round2 "* ]]; then
-  STAGES="$STAGES tests smoke bench staged timeline trace micro w4var occ refk"
+  STAGES="$STAGES tests smoke bench staged timeline trace micro occ refk"
 fi
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 echo "stages: $STAGES" | tee $OUT/summary.txt
@@ -103,7 +103,7 @@ if has deq; then
 fi
 if has refk; then
   # our kernels against the reference's own kernels (oracle/_ref), then the attention A/B timing
-  B200_TEST_REF_KERNELS=1 timeout 900 python -m pytest tests/test_gpu_vs_reference_kernels.py -m gpu -q \
+  timeout 900 python -m pytest tests/test_gpu_vs_reference_kernels.py -m gpu -q \
       --tb=short -p no:cacheprovider > $OUT/pytest_vs_reference.log 2>&1
   echo "pytest vs reference kernels rc=$? : $(tail -1 $OUT/pytest_vs_reference.log)" | tee -a $OUT/summary.txt
   timeout 600 python tools/attn_bench.py > $OUT/attn_bench.log 2>&1
@@ -119,7 +119,7 @@ if has occ; then
   for v in "0 0" "1 0" "0 1" "1 1"; do
     set -- $v
     if [ "$v" != "0 0" ]; then
-      B200_ATTN_OCC=$1 B200_ATTN_TR=$2 B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_gpu_attention.py \
+      B200_ATTN_OCC=$1 B200_ATTN_TR=$2 timeout 900 python -m pytest tests/test_gpu_attention.py \
           tests/test_gpu_decode_step.py -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_attention_occ$1_tr$2.log 2>&1
       echo "pytest attention[occ=$1 tr=$2] rc=$? : $(tail -1 $OUT/pytest_attention_occ$1_tr$2.log)" | tee -a $OUT/summary.txt
     fi
@@ -145,8 +145,8 @@ if has pdl; then
   done
 fi
 if has staged; then
-  # single-GPU tests written after round 1's GPU budget was spent (gate: B200_TEST_STAGED=1)
-  B200_TEST_STAGED=1 timeout 900 python -m pytest tests/test_cpp_host.py tests/test_gpu_w4a16.py -m gpu -q --tb=short \
+  # the C++ host classes, the prefill path of the int4 linear, TTFT by chunk size, the C++-only demo
+  timeout 900 python -m pytest tests/test_cpp_host.py tests/test_gpu_w4a16.py -m gpu -q --tb=short \
       -p no:cacheprovider -k "cuda_graph_step or model_runner or dense_prefill or cpp_decode_step" > $OUT/pytest_staged.log 2>&1
   echo "pytest staged (C++ CudaGraphStep / ModelRunner, dense prefill linear) rc=$? : $(tail -1 $OUT/pytest_staged.log)" | tee -a $OUT/summary.txt
   timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --ttft > $OUT/bench_ttft.json 2> $OUT/bench_ttft.err
@@ -164,40 +164,6 @@ if has timeline; then
   timeout 900 python tools/step_timeline.py > $OUT/step_timeline.log 2>&1
   echo "timeline rc=$?" | tee -a $OUT/summary.txt
   head -40 $OUT/step_timeline.log >> $OUT/summary.txt
-fi
-if has w4var; then
-  # opt-in variants of the W4A16 GEMM (B200_W4_VARIANT): a GEMM-only A/B of all of them (seconds
-  # each), then the parity tests for the fastest ones, fastest first, until one passes; the full
-  # bench runs for the default and for that variant
-  : > $OUT/w4_variants.jsonl
-  for v in 0 1 2 4 6 10 14 16 20 24 28; do
-    B200_W4_VARIANT=$v timeout 300 python tools/w4_variant_bench.py >> $OUT/w4_variants.jsonl 2> $OUT/w4_variant$v.err
-    echo "gemm a/b variant $v rc=$? $(tail -1 $OUT/w4_variants.jsonl)" | tee -a $OUT/summary.txt
-  done
-  ORDER=$(python - $OUT/w4_variants.jsonl <<'PY'
-import json, sys
-rows = [json.loads(l) for l in open(sys.argv[1]) if l.strip().startswith("{")]
-rows.sort(key=lambda r: r["sum_us"])
-print(" ".join(str(r["variant"]) for r in rows if str(r["variant"]) != "0"))
-PY
-)
-  BEST=0
-  tried=0
-  for v in $ORDER; do
-    [ $tried -ge 4 ] && break
-    tried=$((tried + 1))
-    B200_W4_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_w4a16.py tests/test_gpu_decode_step.py \
-        -m gpu -q --tb=short -p no:cacheprovider > $OUT/pytest_w4var$v.log 2>&1
-    rc=$?
-    echo "pytest w4a16[variant $v] rc=$rc : $(tail -1 $OUT/pytest_w4var$v.log)" | tee -a $OUT/summary.txt
-    if [ $rc -eq 0 ]; then BEST=$v; break; fi
-  done
-  for v in 0 $BEST; do
-    [ $v = 0 ] && [ "$BEST" = 0 ] && [ -s $OUT/bench_w4var0.json ] && continue
-    B200_W4_VARIANT=$v timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline \
-        > $OUT/bench_w4var$v.json 2> $OUT/bench_w4var$v.err
-    echo "bench w4 variant=$v rc=$? $(tail -1 $OUT/bench_w4var$v.json | head -c 200)" | tee -a $OUT/summary.txt
-  done
 fi
 if has ref; then
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
