@@ -323,8 +323,11 @@ def top_k_top_p_filter(logits: torch.Tensor, top_k, top_p) -> torch.Tensor:
     reference's test, logits_processor_test.cpp:263-357, only compares sorted values), and softmax /
     cumsum run in float64 where the reference's tensors are of the logits' dtype (bf16: every prob and
     every partial sum rounded to 8 bits — a token whose exclusive cumulative probability is within
-    that rounding of top_p can fall on either side there).  logits [batch, vocab]; top_k int64 [batch] or
-    None; top_p float [batch] or None.  Returns a new tensor of the logits' dtype."""
+    that rounding of top_p can fall on either side there).  top_p >= 1 means "no top-p limit": in the
+    reference `(cumsum - probs) > 1.0` is false in exact arithmetic and true only where the rounding of its
+    cumulative sum overshoots 1 (tail tokens of negligible mass, tests/test_sampling_oracle.py).
+    logits [batch, vocab]; top_k int64 [batch] or None; top_p float [batch] or None.  Returns a new tensor
+    of the logits' dtype."""
     x = logits.detach().cpu()
     out = x.clone()
     B, V = x.shape
@@ -338,7 +341,7 @@ def top_k_top_p_filter(logits: torch.Tensor, top_k, top_p) -> torch.Tensor:
             if 0 < kk < V:
                 k = kk
         keep[k:] = False
-        if top_p is not None:
+        if top_p is not None and float(top_p[b]) < 1.0:   # top_p >= 1: no limit (see the docstring)
             p = float(top_p[b])
             vs = v[order].clone()
             vs[k:] = float("-inf")
